@@ -1,0 +1,320 @@
+"""ctypes view of the CPU oracle (oracle/liboracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product (mixlab_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+WAVE_ON, WAVE_OFF, WAVE_SINE, WAVE_SQUARE, WAVE_TRIANGLE, WAVE_SAW = range(6)
+LINE_MONO, LINE_STEREO, LINE_VIDEO = range(3)
+(MOD_AMPLIFIER, MOD_ENVELOPE, MOD_EQ_THREE, MOD_FM_SINE, MOD_MIXER, MOD_OSCILLATOR, MOD_PLOTTER,
+ MOD_STEREO_PANNER, MOD_STEREO_SPLITTER, MOD_TRIGGER, MOD_METER, MOD_SOURCE_STEREO,
+ MOD_SOURCE_MONO) = range(13)
+
+
+def build(force=False):
+    """Compile liboracle.so with the committed Makefile (gcc -O2 -ffp-contract=off)."""
+    src = [os.path.join(_HERE, f) for f in ("mixlab_oracle.c", "mixlab_oracle.h", "Makefile")]
+    if (not force and os.path.exists(_LIB_PATH)
+            and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src)):
+        return _LIB_PATH
+    subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+class EqThreeState(C.Structure):
+    _fields_ = [("lo_coef", C.c_double), ("hi_coef", C.c_double), ("lo_poles", C.c_double * 4),
+                ("hi_poles", C.c_double * 4), ("history", C.c_double * 3)]
+
+
+class EnvelopeState(C.Structure):
+    _fields_ = [("state", C.c_int), ("seq", C.c_uint64), ("off_amplitude", C.c_double)]
+
+
+class FrameLayout(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("stride", C.c_uint32 * 3),
+                ("plane_h", C.c_uint32 * 3), ("offset", C.c_size_t * 3), ("size", C.c_size_t)]
+
+
+class ScaleGeometry(C.Structure):
+    _fields_ = [("scaled_w", C.c_uint32), ("scaled_h", C.c_uint32), ("letterbox_x", C.c_uint32),
+                ("letterbox_y", C.c_uint32)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.orc_db_to_linear.restype = C.c_double
+        _lib.orc_db_to_linear.argtypes = [C.c_double]
+        _lib.orc_graph_create.restype = C.c_void_p
+        _lib.orc_graph_create.argtypes = [C.c_double, C.c_uint32]
+        _lib.orc_graph_destroy.argtypes = [C.c_void_p]
+        _lib.orc_graph_add.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        _lib.orc_graph_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        _lib.orc_graph_set_source.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+        _lib.orc_graph_run_tick.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+        _lib.orc_graph_last_order.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        _lib.orc_graph_meter.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_fader_to_u8.restype = C.c_uint8
+        _lib.orc_fader_to_u8.argtypes = [C.c_double]
+        _lib.orc_clip_detect.restype = C.c_int
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def db_to_linear(db):
+    return lib().orc_db_to_linear(float(db))
+
+
+def mixer(inputs, gain_db, fader, cue, frames):
+    """inputs: list of stereo arrays (2*frames f32) or None.  Returns (master, cue)."""
+    n = len(inputs)
+    arrs = [None if a is None else _f32(a) for a in inputs]
+    ptrs = (C.c_void_p * max(n, 1))(*[None if a is None else a.ctypes.data for a in arrs])
+    g = np.ascontiguousarray(gain_db, dtype=np.float64)
+    f = np.ascontiguousarray(fader, dtype=np.float64)
+    c = np.ascontiguousarray(cue, dtype=np.uint8)
+    master = np.empty(2 * frames, np.float32)
+    cue_out = np.empty(2 * frames, np.float32)
+    lib().orc_mixer(ptrs, _p(g), _p(f), _p(c), C.c_int(n), _p(master), _p(cue_out),
+                    C.c_size_t(2 * frames))
+    return master, cue_out
+
+
+def amplifier(inp, mod, amplitude, mod_depth):
+    inp = _f32(inp)
+    mod = None if mod is None else _f32(mod)
+    out = np.empty_like(inp)
+    lib().orc_amplifier(_p(inp), _p(mod), C.c_double(amplitude), C.c_double(mod_depth), _p(out),
+                        C.c_size_t(inp.size))
+    return out
+
+
+class EqThree:
+    def __init__(self, sample_rate):
+        self.state = EqThreeState()
+        lib().orc_eq_three_create(C.byref(self.state), C.c_double(sample_rate))
+
+    def run(self, gains_db, inp):
+        inp = _f32(inp)
+        out = np.empty_like(inp)
+        lib().orc_eq_three_run(C.byref(self.state), C.c_double(gains_db[0]), C.c_double(gains_db[1]),
+                               C.c_double(gains_db[2]), _p(inp), _p(out), C.c_size_t(inp.size))
+        return out
+
+
+def oscillator(t, sample_rate, freq, waveform, n):
+    mono = np.empty(n, np.float32)
+    stereo = np.empty(2 * n, np.float32)
+    lib().orc_oscillator(C.c_uint64(t), C.c_double(sample_rate), C.c_double(freq), C.c_int(waveform),
+                         _p(mono), _p(stereo), C.c_size_t(n))
+    return mono, stereo
+
+
+class Envelope:
+    def __init__(self):
+        self.state = EnvelopeState()
+        lib().orc_envelope_create(C.byref(self.state))
+
+    def run(self, t, sample_rate, attack_ms, decay_ms, sustain, release_ms, inp):
+        inp = _f32(inp)
+        out = np.empty_like(inp)
+        lib().orc_envelope_run(C.byref(self.state), C.c_uint64(t), C.c_double(sample_rate),
+                               C.c_double(attack_ms), C.c_double(decay_ms), C.c_double(sustain),
+                               C.c_double(release_ms), _p(inp), _p(out), C.c_size_t(inp.size))
+        return out
+
+
+def fm_sine(t, sample_rate, freq_lo, freq_hi, inp, n=None):
+    inp = None if inp is None else _f32(inp)
+    n = inp.size if inp is not None else n
+    out = np.empty(2 * n, np.float32)
+    lib().orc_fm_sine(C.c_uint64(t), C.c_double(sample_rate), C.c_double(freq_lo), C.c_double(freq_hi),
+                      _p(inp), _p(out), C.c_size_t(n))
+    return out
+
+
+def stereo_panner(left, right, n):
+    left = None if left is None else _f32(left)
+    right = None if right is None else _f32(right)
+    out = np.empty(2 * n, np.float32)
+    lib().orc_stereo_panner(_p(left), _p(right), _p(out), C.c_size_t(n))
+    return out
+
+
+def stereo_splitter(inp, n):
+    inp = None if inp is None else _f32(inp)
+    left = np.empty(n, np.float32)
+    right = np.empty(n, np.float32)
+    lib().orc_stereo_splitter(_p(inp), _p(left), _p(right), C.c_size_t(n))
+    return left, right
+
+
+def trigger(is_open, n):
+    out = np.empty(n, np.float32)
+    lib().orc_trigger(C.c_int(1 if is_open else 0), _p(out), C.c_size_t(n))
+    return out
+
+
+def pcm_pack_i16(samples):
+    samples = _f32(samples)
+    out = np.empty(samples.size, np.int16)
+    lib().orc_pcm_pack_i16(_p(samples), _p(out), C.c_size_t(samples.size))
+    return out
+
+
+def pcm_unpack_i16(pcm):
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    out = np.empty(pcm.size, np.float32)
+    lib().orc_pcm_unpack_i16(_p(pcm), _p(out), C.c_size_t(pcm.size))
+    return out
+
+
+def plotter_tap(stereo):
+    stereo = _f32(stereo)
+    n = stereo.size // 2
+    left = np.empty(n, np.float32)
+    right = np.empty(n, np.float32)
+    lib().orc_plotter_tap(_p(stereo), _p(left), _p(right), C.c_size_t(n))
+    return left, right
+
+
+def clip_detect(stereo):
+    stereo = _f32(stereo)
+    return bool(lib().orc_clip_detect(_p(stereo), C.c_size_t(stereo.size)))
+
+
+def meter(stereo):
+    stereo = _f32(stereo)
+    peak = (C.c_float * 2)()
+    sumsq = (C.c_double * 2)()
+    clip = C.c_int(0)
+    lib().orc_meter(_p(stereo), C.c_size_t(stereo.size // 2), peak, sumsq, C.byref(clip))
+    return (peak[0], peak[1]), (sumsq[0], sumsq[1]), bool(clip.value)
+
+
+def frame_layout(width, height):
+    lay = FrameLayout()
+    lib().orc_frame_layout_yuv420p(C.c_uint32(width), C.c_uint32(height), C.byref(lay))
+    return lay
+
+
+def frame_blank(lay):
+    data = np.empty(lay.size, np.uint8)
+    lib().orc_frame_blank(C.byref(lay), _p(data))
+    return data
+
+
+def fader_to_u8(fader):
+    return int(lib().orc_fader_to_u8(float(fader)))
+
+
+def video_crossfade(lay, a, b, fade):
+    """a / b: full frame byte arrays in `lay` layout, or None (layer missing)."""
+    out = frame_blank(lay)
+    a = None if a is None else np.ascontiguousarray(a, dtype=np.uint8)
+    b = None if b is None else np.ascontiguousarray(b, dtype=np.uint8)
+    lib().orc_video_crossfade(C.byref(lay), _p(a), _p(b), C.c_uint8(fade), _p(out))
+    return out
+
+
+def unify_picture(aw, ah, bw, bh):
+    w, h = C.c_uint32(), C.c_uint32()
+    lib().orc_unify_picture(C.c_uint32(aw), C.c_uint32(ah), C.c_uint32(bw), C.c_uint32(bh),
+                            C.byref(w), C.byref(h))
+    return w.value, h.value
+
+
+def scale_geometry(in_w, in_h, out_w, out_h):
+    g = ScaleGeometry()
+    lib().orc_scale_geometry_yuv420p(C.c_uint32(in_w), C.c_uint32(in_h), C.c_uint32(out_w),
+                                     C.c_uint32(out_h), C.byref(g))
+    return g.scaled_w, g.scaled_h, g.letterbox_x, g.letterbox_y
+
+
+def yuv420p_to_rgba(lay, yuv):
+    yuv = np.ascontiguousarray(yuv, dtype=np.uint8)
+    out = np.empty(lay.width * lay.height * 4, np.uint8)
+    lib().orc_yuv420p_to_rgba(C.byref(lay), _p(yuv), _p(out))
+    return out
+
+
+def bicubic_plane(src, sw, sh, sstride, dw, dh, dstride):
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    dst = np.zeros(dstride * dh, np.uint8)
+    lib().orc_bicubic_plane(_p(src), C.c_uint32(sw), C.c_uint32(sh), C.c_uint32(sstride), _p(dst),
+                            C.c_uint32(dw), C.c_uint32(dh), C.c_uint32(dstride))
+    return dst
+
+
+class Graph:
+    """Engine::run_tick walker (engine.rs:400-510) over oracle modules."""
+
+    def __init__(self, sample_rate, samples_per_tick):
+        self.spt = samples_per_tick
+        self._g = lib().orc_graph_create(C.c_double(sample_rate), C.c_uint32(samples_per_tick))
+        self._keep = []
+        self.out_types = {}
+
+    def close(self):
+        if self._g:
+            lib().orc_graph_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        self.close()
+
+    def add(self, kind, params=()):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        mid = lib().orc_graph_add(self._g, C.c_int(kind), _p(p) if p.size else None, C.c_int(p.size))
+        if mid < 0:
+            raise ValueError("unknown module kind %r" % kind)
+        return mid
+
+    def connect(self, in_module, in_index, out_module, out_index):
+        return lib().orc_graph_connect(self._g, in_module, in_index, out_module, out_index)
+
+    def set_source(self, module, data, width):
+        data = _f32(data)
+        self._keep.append(data)
+        lib().orc_graph_set_source(self._g, module, _p(data), C.c_size_t(data.size // width))
+
+    def run_tick(self, tick, capture=None, capture_len=0):
+        buf = None
+        if capture is not None:
+            buf = np.zeros(capture_len, np.float32)
+            lib().orc_graph_run_tick(self._g, C.c_uint64(tick), capture[0], capture[1], _p(buf))
+        else:
+            lib().orc_graph_run_tick(self._g, C.c_uint64(tick), -1, -1, None)
+        return buf
+
+    def last_order(self):
+        arr = (C.c_int * 1024)()
+        n = lib().orc_graph_last_order(self._g, arr, 1024)
+        return list(arr[:n])
+
+    def meter(self, module):
+        peak = (C.c_float * 2)()
+        sumsq = (C.c_double * 2)()
+        clip = C.c_int(0)
+        lib().orc_graph_meter(self._g, module, peak, sumsq, C.byref(clip))
+        return (peak[0], peak[1]), (sumsq[0], sumsq[1]), bool(clip.value)
