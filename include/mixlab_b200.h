@@ -1,0 +1,295 @@
+/*
+ * mixlab_b200.h -- C ABI of the B200 (sm_100a) back end for Mixlab's per-tick module-graph path.
+ *
+ * This is the drop-in boundary: the entry points a Rust `impl ModuleT` shim
+ * binds with `extern "C"` to replace the arithmetic of the reference's src/module/ sources and the
+ * buffer routing of Engine::run_tick.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *  - Every function returning `int` returns MXL_OK (0) or a negative mxl_status.  The message
+ *    of the last failure on the calling thread is available from mxl_last_error().  Nothing ever
+ *    unwinds across this boundary (the reference's own FFI convention: negative c_int sentinels,
+ *    codec/src/ffmpeg.rs:25-26, codec/src/ffmpeg/ioctx.rs:136-152).
+ *  - Where the reference panics (line-type mismatch src/engine/io.rs:40-41,49-50; params-variant
+ *    mismatch src/engine/module.rs:108) this ABI returns MXL_ERR_LINE_TYPE / MXL_ERR_PARAMS.
+ *  - A context is single-threaded like the engine thread that owns the modules
+ *    (src/engine.rs:78-93): one CUDA stream per context, no internal locking.
+ *  - Line buffers are device-resident and owned by the back end.  Host pointers appear only in
+ *    upload/download calls.  A NULL input line means InputRef::Disconnected
+ *    (src/engine/io.rs:19-61).
+ *  - `t` is the absolute sample index of the first sample of the call (src/engine.rs:490).
+ *    run_tick is length-agnostic exactly like the reference loops: a line of n_ticks*S frames
+ *    processed in one call gives the same samples as n_ticks calls of S frames.
+ *  - There is no CPU fallback.  A context created with device = MXL_DEVICE_NONE can only be
+ *    used for host-side logic (graph planning, connect type checks, picture geometry); every
+ *    compute entry point returns MXL_ERR_NO_DEVICE on it.
+ *
+ * Citations `file:line` are relative to the reference repository (haileys/mixlab @ d73346d).
+ */
+#ifndef MIXLAB_B200_H
+#define MIXLAB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MXL_API __attribute__((visibility("default")))
+
+typedef struct mxl_ctx mxl_ctx;
+typedef struct mxl_line mxl_line;
+typedef struct mxl_frame mxl_frame;
+typedef struct mxl_module mxl_module;
+typedef struct mxl_graph mxl_graph;
+
+typedef enum mxl_status {
+    MXL_OK = 0,
+    MXL_ERR_INVALID = -1,        /* NULL handle, bad index, bad size */
+    MXL_ERR_LINE_TYPE = -2,      /* io.rs:40-41 "expected mono input, got stereo" */
+    MXL_ERR_PARAMS = -3,         /* module.rs:108 "module params mismatch" */
+    MXL_ERR_CUDA = -4,
+    MXL_ERR_NO_DEVICE = -5,
+    MXL_ERR_NO_INPUT = -6,       /* workspace.rs:100 ConnectError::NoInput */
+    MXL_ERR_NO_OUTPUT = -7,      /* workspace.rs:105 ConnectError::NoOutput */
+    MXL_ERR_TYPE_MISMATCH = -8,  /* workspace.rs:112 ConnectError::TypeMismatch */
+    MXL_ERR_OOM = -9,
+    MXL_ERR_UNSUPPORTED = -10,
+    MXL_ERR_LENGTH = -11         /* line shorter than the call needs (Rust: slice index panic) */
+} mxl_status;
+
+#define MXL_DEVICE_NONE (-1)
+
+/* protocol/src/lib.rs:176-181 */
+typedef enum mxl_line_type { MXL_LINE_MONO = 0, MXL_LINE_STEREO = 1, MXL_LINE_VIDEO = 2 } mxl_line_type;
+
+/* src/module/mod.rs:28-49 enumerate_modules!, same order.  Kinds marked (io) are I/O edges that
+ * stay in the reference; they are listed so the numbering matches protocol ModuleParams.
+ * METER and SOURCE_* have no reference counterpart. */
+typedef enum mxl_module_kind {
+    MXL_MOD_AMPLIFIER = 0,
+    MXL_MOD_ENVELOPE = 1,
+    MXL_MOD_EQ_THREE = 2,
+    MXL_MOD_FM_SINE = 3,
+    MXL_MOD_MIXER = 4,
+    MXL_MOD_MONITOR = 5,          /* (io) not provided */
+    MXL_MOD_OSCILLATOR = 6,
+    MXL_MOD_OUTPUT_DEVICE = 7,    /* (io) not provided */
+    MXL_MOD_PLOTTER = 8,
+    MXL_MOD_STEREO_PANNER = 9,
+    MXL_MOD_STEREO_SPLITTER = 10,
+    MXL_MOD_STREAM_INPUT = 11,    /* (io) not provided */
+    MXL_MOD_STREAM_OUTPUT = 12,   /* (io) not provided */
+    MXL_MOD_TRIGGER = 13,
+    MXL_MOD_VIDEO_MIXER = 14,
+    MXL_MOD_MEDIA_SOURCE = 15,    /* (io) not provided */
+    MXL_MOD_METER = 32,           /* new: per-tick peak / sum-of-squares / clip */
+    MXL_MOD_SOURCE_MONO = 33,     /* new: host-fed line, stands where StreamInput's output was */
+    MXL_MOD_SOURCE_STEREO = 34,
+    MXL_MOD_SOURCE_VIDEO = 35,
+    MXL_MOD_PCM_SINK = 36         /* new: f32 -> i16 pack of a stereo line (src/video/encode.rs:184-195) */
+} mxl_module_kind;
+
+/* ---- parameter PODs: mirrors of protocol/src/lib.rs structs, f64 fields stay f64 ----------- */
+
+typedef struct mxl_amplifier_params { double amplitude; double mod_depth; } mxl_amplifier_params;      /* lib.rs:298-302 */
+typedef struct mxl_envelope_params {                                                                   /* lib.rs:310-327 */
+    double attack_ms, decay_ms, sustain_amplitude, release_ms;
+} mxl_envelope_params;
+typedef struct mxl_eq_three_params { double gain_lo_db, gain_mid_db, gain_hi_db; } mxl_eq_three_params; /* lib.rs:285-290 */
+typedef struct mxl_fm_sine_params { double freq_lo, freq_hi; } mxl_fm_sine_params;                     /* lib.rs:292-296 */
+typedef struct mxl_mixer_channel_params { double gain_db; double fader; int32_t cue; int32_t _pad; } mxl_mixer_channel_params; /* lib.rs:342-347 */
+typedef struct mxl_mixer_params { const mxl_mixer_channel_params *channels; uint32_t n_channels; } mxl_mixer_params;          /* lib.rs:329-332 */
+/* lib.rs:233-241, declaration order */
+typedef enum mxl_waveform { MXL_WAVE_ON = 0, MXL_WAVE_OFF = 1, MXL_WAVE_SINE = 2, MXL_WAVE_SQUARE = 3,
+                            MXL_WAVE_TRIANGLE = 4, MXL_WAVE_SAW = 5 } mxl_waveform;
+typedef struct mxl_oscillator_params { double freq; int32_t waveform; int32_t _pad; } mxl_oscillator_params; /* lib.rs:243-247 */
+typedef enum mxl_gate_state { MXL_GATE_OPEN = 0, MXL_GATE_CLOSED = 1 } mxl_gate_state;                   /* lib.rs:304-308 */
+typedef struct mxl_trigger_params { int32_t gate; } mxl_trigger_params;
+/* lib.rs:405-420; a / b = -1 encodes Option::None */
+typedef struct mxl_video_mixer_params { int32_t a; int32_t b; double fader; } mxl_video_mixer_params;
+#define MXL_VIDEO_MIXER_CHANNELS 4                                                                     /* lib.rs:403 */
+
+/* ---- context --------------------------------------------------------------------------------- */
+
+/* sample_rate / samples_per_tick are the reference's compile-time SAMPLE_RATE / SAMPLES_PER_TICK
+ * (src/engine.rs:52-55) made runtime parameters. */
+MXL_API mxl_ctx *mxl_ctx_create(int device, uint32_t sample_rate, uint32_t samples_per_tick);
+/* Same, but launches on a caller-owned cudaStream_t (so the caller can time with its own events). */
+MXL_API mxl_ctx *mxl_ctx_create_on_stream(int device, uint32_t sample_rate, uint32_t samples_per_tick,
+                                          void *cuda_stream);
+MXL_API int mxl_ctx_destroy(mxl_ctx *ctx);
+MXL_API int mxl_ctx_synchronize(mxl_ctx *ctx);
+MXL_API void *mxl_ctx_stream(mxl_ctx *ctx);
+MXL_API uint32_t mxl_ctx_sample_rate(const mxl_ctx *ctx);
+MXL_API uint32_t mxl_ctx_samples_per_tick(const mxl_ctx *ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+MXL_API uint64_t mxl_ctx_launch_count(const mxl_ctx *ctx);
+/* Device-timed interval on the context's stream: begin/end record CUDA events, elapsed_ms
+ * synchronises on the end event. */
+MXL_API int mxl_ctx_timer_begin(mxl_ctx *ctx);
+MXL_API int mxl_ctx_timer_end(mxl_ctx *ctx);
+MXL_API int mxl_ctx_timer_elapsed_ms(mxl_ctx *ctx, float *ms);
+/* Overwrites a scratch buffer larger than L2 (bench hygiene between timed iterations). */
+MXL_API int mxl_ctx_flush_l2(mxl_ctx *ctx);
+MXL_API const char *mxl_last_error(void);
+MXL_API const char *mxl_version(void);
+/* Decibel::to_linear, protocol/src/lib.rs:469-471 (host scalar; exposed for tests) */
+MXL_API double mxl_db_to_linear(double db);
+
+/* Pinned host memory for upload/download staging. */
+MXL_API void *mxl_host_alloc(size_t bytes);
+MXL_API int mxl_host_free(void *p);
+
+/* ---- audio lines: Output::{Mono,Stereo} of src/engine/io.rs:64-77, device-resident ------------- */
+
+/* `frames` samples per channel; zero-filled like `vec![0.0; N]` (io.rs:73-74). */
+MXL_API mxl_line *mxl_line_alloc(mxl_ctx *ctx, int line_type, uint64_t frames);
+MXL_API int mxl_line_free(mxl_line *line);
+MXL_API int mxl_line_type_of(const mxl_line *line);
+MXL_API uint64_t mxl_line_frames(const mxl_line *line);
+/* number of f32 in the line (frames for mono, 2*frames for stereo) */
+MXL_API uint64_t mxl_line_len(const mxl_line *line);
+MXL_API void *mxl_line_device_ptr(mxl_line *line);
+MXL_API int mxl_line_zero(mxl_line *line);
+/* host <-> device, ordered on the context stream; both return after the copy has completed */
+MXL_API int mxl_line_upload(mxl_line *line, const float *host, uint64_t n_floats);
+MXL_API int mxl_line_download(const mxl_line *line, float *host, uint64_t n_floats);
+/* asynchronous variants for pinned host memory (mxl_host_alloc); complete at mxl_ctx_synchronize */
+MXL_API int mxl_line_upload_async(mxl_line *line, const float *host, uint64_t n_floats);
+MXL_API int mxl_line_download_async(const mxl_line *line, float *host, uint64_t n_floats);
+
+/* ---- video frames: AvFrame<Video> in yuv420p, codec/src/ffmpeg/frame.rs:76-138 ---------------- */
+
+typedef struct mxl_frame_layout {
+    uint32_t width, height;     /* luma size */
+    uint32_t stride[3];         /* bytes per row, each a multiple of 32 (video_mixer.rs:196-201) */
+    uint32_t plane_h[3];
+    uint64_t offset[3];         /* byte offset of each plane in the frame buffer */
+    uint64_t size;              /* bytes */
+} mxl_frame_layout;
+
+/* Host-side geometry; valid without a device. */
+MXL_API int mxl_frame_layout_yuv420p(uint32_t width, uint32_t height, mxl_frame_layout *out);
+/* video_mixer.rs:276-297 unify_picture_settings */
+MXL_API int mxl_unify_picture_settings(uint32_t aw, uint32_t ah, uint32_t bw, uint32_t bh,
+                                       uint32_t *w, uint32_t *h);
+/* src/video/encode.rs:354-374 DynamicScaler letterbox geometry */
+typedef struct mxl_scale_geometry { uint32_t scaled_w, scaled_h, letterbox_x, letterbox_y; } mxl_scale_geometry;
+MXL_API int mxl_scale_geometry_yuv420p(uint32_t in_w, uint32_t in_h, uint32_t out_w, uint32_t out_h,
+                                       mxl_scale_geometry *out);
+/* video_mixer.rs:168 `(fader * 255.0) as u8` */
+MXL_API uint8_t mxl_fader_to_u8(double fader);
+
+/* Frames are reference-counted like av_frame_clone / av_frame_free (frame.rs:351-361). */
+MXL_API mxl_frame *mxl_frame_alloc(mxl_ctx *ctx, uint32_t width, uint32_t height);
+/* AvFrame::blank: Y=0x00, U=V=0x80 (frame.rs:128-134), filled by a kernel */
+MXL_API mxl_frame *mxl_frame_blank(mxl_ctx *ctx, uint32_t width, uint32_t height);
+MXL_API mxl_frame *mxl_frame_retain(mxl_frame *frame);
+MXL_API int mxl_frame_release(mxl_frame *frame);
+MXL_API int mxl_frame_get_layout(const mxl_frame *frame, mxl_frame_layout *out);
+MXL_API void *mxl_frame_device_ptr(mxl_frame *frame);
+/* plane-wise copy with caller strides (what AvFrame::frame_data() exposes, frame.rs:188-197) */
+MXL_API int mxl_frame_upload(mxl_frame *frame, const uint8_t *const planes[3], const uint32_t strides[3]);
+MXL_API int mxl_frame_download(const mxl_frame *frame, uint8_t *const planes[3], const uint32_t strides[3]);
+/* whole buffer in mxl_frame_layout order, padding included */
+MXL_API int mxl_frame_upload_raw(mxl_frame *frame, const uint8_t *host, uint64_t size);
+MXL_API int mxl_frame_download_raw(const mxl_frame *frame, uint8_t *host, uint64_t size);
+MXL_API int mxl_frame_upload_raw_async(mxl_frame *frame, const uint8_t *host, uint64_t size);
+MXL_API int mxl_frame_download_raw_async(const mxl_frame *frame, uint8_t *host, uint64_t size);
+
+/* Video line = Output::Video(Option<VideoFrame>) per tick (io.rs:8-17,64-69): `ticks` slots. */
+MXL_API mxl_line *mxl_video_line_alloc(mxl_ctx *ctx, uint32_t ticks);
+/* frame may be NULL (None).  duration_hint / tick_offset are MediaDuration rationals
+ * (src/video.rs, util/src/time.rs:77-105).  The line retains the frame. */
+MXL_API int mxl_video_line_set(mxl_line *line, uint32_t slot, mxl_frame *frame, int64_t duration_num,
+                               int64_t duration_den, int64_t offset_num, int64_t offset_den);
+/* borrowed pointer, NULL if the slot is empty */
+MXL_API mxl_frame *mxl_video_line_get(const mxl_line *line, uint32_t slot);
+MXL_API int mxl_video_line_clear(mxl_line *line);
+
+/* ---- modules: trait ModuleT, src/module/mod.rs:7-19 ------------------------------------------- */
+
+/* create(params, ctx).  `params` points at the POD of that kind (NULL for kinds with `()`). */
+MXL_API mxl_module *mxl_module_create(mxl_ctx *ctx, int kind, const void *params);
+MXL_API void mxl_module_destroy(mxl_module *m);
+MXL_API int mxl_module_kind_of(const mxl_module *m);
+/* update(new_params); kind-checked against the module (module.rs:104-110) */
+MXL_API int mxl_module_update(mxl_module *m, int kind, const void *params);
+/* params(): copies the POD out.  For the mixer, `channels_out` receives up to `cap` channels and
+ * the return value is the channel count. */
+MXL_API int mxl_module_params(const mxl_module *m, void *params_out);
+MXL_API int mxl_mixer_params_get(const mxl_module *m, mxl_mixer_channel_params *channels_out, uint32_t cap);
+/* inputs() / outputs(): Terminal(label, LineType), protocol/src/lib.rs:160-174 */
+MXL_API uint32_t mxl_module_n_inputs(const mxl_module *m);
+MXL_API uint32_t mxl_module_n_outputs(const mxl_module *m);
+MXL_API int mxl_module_input_type(const mxl_module *m, uint32_t index);
+MXL_API int mxl_module_output_type(const mxl_module *m, uint32_t index);
+MXL_API const char *mxl_module_input_label(const mxl_module *m, uint32_t index);   /* NULL = unlabeled */
+MXL_API const char *mxl_module_output_label(const mxl_module *m, uint32_t index);
+/* run_tick(t, inputs, outputs).  The number of frames processed is taken from the lines, as the
+ * reference takes it from slice lengths.  Asynchronous on the context stream. */
+MXL_API int mxl_module_run_tick(mxl_module *m, uint64_t t, const mxl_line *const *inputs, uint32_t n_inputs,
+                                mxl_line *const *outputs, uint32_t n_outputs);
+
+/* State read-back (synchronises).  EqThree: lo poles[4], hi poles[4], history[3]. */
+MXL_API int mxl_eq_three_state(mxl_module *m, double state[11]);
+/* Envelope: state (0 Initial, 1 TriggerOn, 2 TriggerOff), seq, off_amplitude */
+MXL_API int mxl_envelope_state(mxl_module *m, int32_t *state, uint64_t *seq, double *off_amplitude);
+/* Meter: values of tick slot `slot` of the last call */
+MXL_API int mxl_meter_read(mxl_module *m, uint32_t slot, float peak[2], double sumsq[2], int32_t *clip);
+/* Plotter (plotter.rs:37-56): de-interleaved tap of the most recent tick whose count % 6 == 0
+ * within the last call.  Returns the number of frames written (0 = no indication). */
+MXL_API int mxl_plotter_read(mxl_module *m, float *left, float *right, uint32_t cap_frames);
+/* Source modules: the line (audio or video) that the module presents as its output. */
+MXL_API int mxl_source_set_line(mxl_module *m, mxl_line *line);
+/* PCM sink: packed i16 of the last call (src/video/encode.rs:184-195) */
+MXL_API int mxl_pcm_sink_download(mxl_module *m, int16_t *host, uint64_t n_samples);
+
+/* Stand-alone PCM converters on raw device memory of the context (N2/N3 rows of SURVEY §8f):
+ * i16 -> f32 `sample / 32768.0` (stream_input.rs:167-173) and the pack above. */
+MXL_API int mxl_pcm_unpack_i16(mxl_ctx *ctx, const int16_t *host_pcm, uint64_t n_samples, mxl_line *dst);
+MXL_API int mxl_pcm_pack_i16(mxl_ctx *ctx, const mxl_line *src, int16_t *host_pcm, uint64_t n_samples);
+
+/* yuv420p -> RGBA8 of a frame (self-specified BT.601 integer form; the reference
+ * never converts colour, video_mixer.rs:282-283).  rgba_host receives width*height*4 bytes. */
+MXL_API int mxl_frame_to_rgba(const mxl_frame *frame, uint8_t *rgba_host);
+/* Letterboxed bicubic rescale of `src` into a new frame of (out_w,out_h): DynamicScaler::scale
+ * (src/video/encode.rs:338-397).  Returns a retained `src` when sizes are equal (342-345). */
+MXL_API mxl_frame *mxl_frame_scale(mxl_frame *src, uint32_t out_w, uint32_t out_h);
+
+/* ---- graph: Workspace + Engine::run_tick, src/engine/workspace.rs, src/engine.rs:400-510 ------ */
+
+MXL_API mxl_graph *mxl_graph_create(mxl_ctx *ctx);
+MXL_API void mxl_graph_destroy(mxl_graph *g);
+/* The graph takes ownership of the module.  Returns the ModuleId (>= 0) or a negative status. */
+MXL_API int mxl_graph_add_module(mxl_graph *g, mxl_module *m);
+MXL_API int mxl_graph_remove_module(mxl_graph *g, int module_id);
+MXL_API mxl_module *mxl_graph_module(mxl_graph *g, int module_id);
+/* Workspace::connect (workspace.rs:97-114) / disconnect (116-118) */
+MXL_API int mxl_graph_connect(mxl_graph *g, int in_module, uint32_t in_index, int out_module, uint32_t out_index);
+MXL_API int mxl_graph_disconnect(mxl_graph *g, int in_module, uint32_t in_index);
+/* Run order the next run will use (terminal set + DFS, engine.rs:408-457).  Returns the count. */
+MXL_API int mxl_graph_plan(mxl_graph *g, int *order_out, uint32_t cap);
+/* Runs ticks tick0 .. tick0+n_ticks-1 (t = tick * samples_per_tick, engine.rs:490) as one batch:
+ * every audio line holds n_ticks*S frames, every video line n_ticks slots. */
+MXL_API int mxl_graph_run_ticks(mxl_graph *g, uint64_t tick0, uint32_t n_ticks);
+/* Output line of a module after the last run (borrowed; valid until the next run or edit). */
+MXL_API mxl_line *mxl_graph_output(mxl_graph *g, int module_id, uint32_t out_index);
+/* Per-launch device timings, shaped like EngineStat (src/engine/timing.rs:46-60,86-94). */
+MXL_API int mxl_graph_set_profiling(mxl_graph *g, int enabled);
+typedef struct mxl_stage_info {
+    int32_t kind;              /* mxl_module_kind of the batched launch */
+    int32_t n_modules;         /* module instances served by the launch */
+    int32_t n_launches;        /* kernels launched by this stage in the last run */
+    float last_ms;             /* device time of the last run (profiling on), else -1 */
+    uint64_t algorithmic_bytes;/* API-level line bytes read+written by the stage in the last run */
+} mxl_stage_info;
+MXL_API int mxl_graph_stage_count(mxl_graph *g);
+MXL_API int mxl_graph_stage_info(mxl_graph *g, uint32_t stage, mxl_stage_info *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

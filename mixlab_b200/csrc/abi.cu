@@ -1,0 +1,170 @@
+// abi.cu -- C ABI of the module layer: `trait ModuleT` (src/module/mod.rs:7-19) as seen through
+// DynModuleHostT (src/engine/module.rs:88-119), plus the stand-alone converters.
+#include <math.h>
+
+#include "modules.h"
+
+using namespace mxl;
+
+namespace {
+
+bool kind_has_params(int kind)
+{
+    switch (kind) {
+    case MXL_MOD_AMPLIFIER: case MXL_MOD_ENVELOPE: case MXL_MOD_EQ_THREE: case MXL_MOD_FM_SINE:
+    case MXL_MOD_MIXER: case MXL_MOD_OSCILLATOR: case MXL_MOD_TRIGGER: case MXL_MOD_VIDEO_MIXER:
+        return true;
+    default:
+        return false;   // `type Params = ()`
+    }
+}
+
+// transient device staging for the stand-alone PCM converters
+struct Staging {
+    void* p = nullptr;
+    ~Staging() { if (p) cudaFree(p); }
+};
+
+}  // namespace
+
+extern "C" {
+
+double mxl_db_to_linear(double db) { return pow(10.0, db / 20.0); }   // protocol/src/lib.rs:469-471
+
+mxl_module* mxl_module_create(mxl_ctx* ctx, int kind, const void* params) { return module_create(ctx, kind, params); }
+
+void mxl_module_destroy(mxl_module* m)
+{
+    if (!m) return;
+    if (m->ctx && m->ctx->has_device()) { m->ctx->activate(); cudaStreamSynchronize(m->ctx->stream); }
+    delete m;
+}
+
+int mxl_module_kind_of(const mxl_module* m) { return m ? m->kind : MXL_ERR_INVALID; }
+
+int mxl_module_update(mxl_module* m, int kind, const void* params)
+{
+    if (!m) MXL_FAIL(MXL_ERR_INVALID, "NULL module");
+    // module.rs:104-110: a ModuleParams variant of another module panics
+    if (kind != m->kind) MXL_FAIL(MXL_ERR_PARAMS, "module params mismatch! module = %s, params kind = %d", m->kind_name(), kind);
+    if (kind_has_params(kind) && !params) MXL_FAIL(MXL_ERR_PARAMS, "%s: NULL params", m->kind_name());
+    return m->update(params);
+}
+
+int mxl_module_params(const mxl_module* m, void* params_out)
+{
+    if (!m) MXL_FAIL(MXL_ERR_INVALID, "NULL module");
+    if (kind_has_params(m->kind) && !params_out) MXL_FAIL(MXL_ERR_INVALID, "NULL params_out");
+    return m->get_params(params_out);
+}
+
+int mxl_mixer_params_get(const mxl_module* m, mxl_mixer_channel_params* channels_out, uint32_t cap)
+{
+    return mixer_params_get(m, channels_out, cap);
+}
+
+uint32_t mxl_module_n_inputs(const mxl_module* m) { return m ? (uint32_t)m->inputs.size() : 0; }
+uint32_t mxl_module_n_outputs(const mxl_module* m) { return m ? (uint32_t)m->outputs.size() : 0; }
+
+int mxl_module_input_type(const mxl_module* m, uint32_t index)
+{
+    if (!m || index >= m->inputs.size()) MXL_FAIL(MXL_ERR_INVALID, "no input %u", index);
+    return m->inputs[index].type;
+}
+
+int mxl_module_output_type(const mxl_module* m, uint32_t index)
+{
+    if (!m || index >= m->outputs.size()) MXL_FAIL(MXL_ERR_INVALID, "no output %u", index);
+    return m->outputs[index].type;
+}
+
+const char* mxl_module_input_label(const mxl_module* m, uint32_t index)
+{
+    if (!m || index >= m->inputs.size() || !m->inputs[index].labeled) return nullptr;
+    return m->inputs[index].label.c_str();
+}
+
+const char* mxl_module_output_label(const mxl_module* m, uint32_t index)
+{
+    if (!m || index >= m->outputs.size() || !m->outputs[index].labeled) return nullptr;
+    return m->outputs[index].label.c_str();
+}
+
+int mxl_module_run_tick(mxl_module* m, uint64_t t, const mxl_line* const* inputs, uint32_t n_inputs,
+                        mxl_line* const* outputs, uint32_t n_outputs)
+{
+    if (!m) MXL_FAIL(MXL_ERR_INVALID, "NULL module");
+    if ((n_inputs && !inputs) || (n_outputs && !outputs)) MXL_FAIL(MXL_ERR_INVALID, "NULL line table");
+    for (uint32_t i = 0; i < n_inputs; i++)
+        if (inputs[i] && inputs[i]->ctx != m->ctx) MXL_FAIL(MXL_ERR_INVALID, "input %u belongs to another context", i);
+    for (uint32_t i = 0; i < n_outputs; i++)
+        if (outputs[i] && outputs[i]->ctx != m->ctx) MXL_FAIL(MXL_ERR_INVALID, "output %u belongs to another context", i);
+    IoSet io{inputs, n_inputs, outputs, n_outputs};
+    mxl_module* one = m;
+    return run_batch(m->ctx, m->kind, &one, 1, t, &io, nullptr);
+}
+
+int mxl_eq_three_state(mxl_module* m, double state[11]) { return eq_three_state(m, state); }
+int mxl_envelope_state(mxl_module* m, int32_t* state, uint64_t* seq, double* off_amplitude) { return envelope_state(m, state, seq, off_amplitude); }
+int mxl_meter_read(mxl_module* m, uint32_t slot, float peak[2], double sumsq[2], int32_t* clip) { return meter_read(m, slot, peak, sumsq, clip); }
+int mxl_plotter_read(mxl_module* m, float* left, float* right, uint32_t cap_frames) { return plotter_read(m, left, right, cap_frames); }
+int mxl_source_set_line(mxl_module* m, mxl_line* line) { return source_set_line(m, line); }
+int mxl_pcm_sink_download(mxl_module* m, int16_t* host, uint64_t n_samples) { return pcm_sink_download(m, host, n_samples); }
+
+// stream_input.rs:110-112,167-173: the i16 PCM crosses the bus (2 B/sample), the divide runs on the device
+int mxl_pcm_unpack_i16(mxl_ctx* ctx, const int16_t* host_pcm, uint64_t n_samples, mxl_line* dst)
+{
+    if (!ctx || !dst) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
+    if (!ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "mxl_pcm_unpack_i16: context has no CUDA device; there is no CPU fallback");
+    if (dst->type == MXL_LINE_VIDEO) MXL_FAIL(MXL_ERR_LINE_TYPE, "mxl_pcm_unpack_i16: video line");
+    if (n_samples > dst->len()) MXL_FAIL(MXL_ERR_LENGTH, "%llu samples, line holds %llu", (unsigned long long)n_samples, (unsigned long long)dst->len());
+    if (n_samples == 0) return MXL_OK;
+    if (!host_pcm) MXL_FAIL(MXL_ERR_INVALID, "NULL pcm");
+    MXL_TRY(ctx->activate());
+    Staging st;
+    MXL_CUDA(cudaMalloc(&st.p, n_samples * sizeof(int16_t)));
+    MXL_CUDA(cudaMemcpyAsync(st.p, host_pcm, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+    MXL_TRY(k::launch_pcm_unpack(ctx, (const int16_t*)st.p, dst->dev, n_samples));
+    MXL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MXL_OK;
+}
+
+// src/video/encode.rs:184-195
+int mxl_pcm_pack_i16(mxl_ctx* ctx, const mxl_line* src, int16_t* host_pcm, uint64_t n_samples)
+{
+    if (!ctx || !src) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
+    if (!ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "mxl_pcm_pack_i16: context has no CUDA device; there is no CPU fallback");
+    if (src->type == MXL_LINE_VIDEO) MXL_FAIL(MXL_ERR_LINE_TYPE, "mxl_pcm_pack_i16: video line");
+    if (n_samples > src->len()) MXL_FAIL(MXL_ERR_LENGTH, "%llu samples, line holds %llu", (unsigned long long)n_samples, (unsigned long long)src->len());
+    if (n_samples == 0) return MXL_OK;
+    if (!host_pcm) MXL_FAIL(MXL_ERR_INVALID, "NULL pcm");
+    MXL_TRY(ctx->activate());
+    Staging st;
+    MXL_CUDA(cudaMalloc(&st.p, n_samples * sizeof(int16_t)));
+    MXL_TRY(k::launch_pcm_pack(ctx, src->dev, (int16_t*)st.p, n_samples));
+    MXL_CUDA(cudaMemcpyAsync(host_pcm, st.p, n_samples * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+    MXL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MXL_OK;
+}
+
+int mxl_frame_to_rgba(const mxl_frame* frame, uint8_t* rgba_host)
+{
+    if (!frame || !rgba_host) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
+    mxl_ctx* ctx = frame->ctx;
+    MXL_TRY(ctx->activate());
+    const size_t bytes = (size_t)frame->layout.width * frame->layout.height * 4;
+    Staging st;
+    MXL_CUDA(cudaMalloc(&st.p, bytes));
+    MXL_TRY(k::launch_yuv_to_rgba(ctx, frame->layout, frame->dev, (uint8_t*)st.p));
+    MXL_CUDA(cudaMemcpyAsync(rgba_host, st.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MXL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MXL_OK;
+}
+
+mxl_frame* mxl_frame_scale(mxl_frame* src, uint32_t out_w, uint32_t out_h)
+{
+    if (src && (out_w == 0 || out_h == 0)) { set_error("mxl_frame_scale: empty target %ux%u", out_w, out_h); return nullptr; }
+    return frame_scale(src, out_w, out_h);
+}
+
+}  // extern "C"

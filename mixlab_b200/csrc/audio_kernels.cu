@@ -1,0 +1,491 @@
+// audio_kernels.cu -- element-wise audio module kernels for sm_100a.
+//
+// All of these are streaming, HBM-bound passes: one 16-byte (float4) access per thread per line,
+// fully coalesced, read-once inputs loaded through the non-coherent path without L1 allocation.
+// Arithmetic follows the reference operation by operation: f64 exactly where the Rust widens,
+// no FMA contraction (-fmad=false), round-to-nearest conversions.
+#include "dsp_math.cuh"
+#include "kernels.h"
+
+namespace mxl {
+namespace k {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float4 ldg_stream(const float* p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_stream1(const float* p)
+{
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+inline unsigned blocks_for(uint64_t items, int threads = kThreads)
+{
+    return (unsigned)((items + threads - 1) / threads);
+}
+
+// ------------------------------------------------------------------------------------------
+// Oscillator: oscillator.rs:73-89
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float osc_sample(uint64_t seq, double sr, double inv_sr, double freq, int wf)
+{
+    // `(t + i as u64) as f64 / SAMPLE_RATE as f64` -- correctly rounded quotient
+    double t0 = div_by_const((double)seq, sr, inv_sr);
+    double n = t0 * freq;
+    double v;
+    switch (wf) {
+    case MXL_WAVE_SINE: v = wave_sine(n); break;
+    case MXL_WAVE_SQUARE: v = sign_bit_f64(wave_sine(n)); break;
+    case MXL_WAVE_SAW: v = wave_saw(n); break;
+    case MXL_WAVE_TRIANGLE: v = wave_triangle(n); break;
+    case MXL_WAVE_ON: v = 1.0; break;
+    default: v = 0.0; break;
+    }
+    return (float)v;
+}
+
+__global__ void __launch_bounds__(kThreads) oscillator_kernel(const __grid_constant__ OscBatch b)
+{
+    const OscInst& in = b.inst[blockIdx.y];
+    uint64_t f0 = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+    if (f0 >= b.frames) return;
+    const double freq = in.freq;
+    const int wf = in.waveform;
+    if (f0 + 4 <= b.frames) {
+        float s0 = osc_sample(b.t0 + f0 + 0, b.sample_rate, b.inv_sample_rate, freq, wf);
+        float s1 = osc_sample(b.t0 + f0 + 1, b.sample_rate, b.inv_sample_rate, freq, wf);
+        float s2 = osc_sample(b.t0 + f0 + 2, b.sample_rate, b.inv_sample_rate, freq, wf);
+        float s3 = osc_sample(b.t0 + f0 + 3, b.sample_rate, b.inv_sample_rate, freq, wf);
+        if (in.mono) st4(in.mono + f0, make_float4(s0, s1, s2, s3));
+        if (in.stereo) {
+            st4(in.stereo + 2 * f0, make_float4(s0, s0, s1, s1));
+            st4(in.stereo + 2 * f0 + 4, make_float4(s2, s2, s3, s3));
+        }
+    } else {
+        for (uint64_t f = f0; f < b.frames; f++) {
+            float s = osc_sample(b.t0 + f, b.sample_rate, b.inv_sample_rate, freq, wf);
+            if (in.mono) in.mono[f] = s;
+            if (in.stereo) { in.stereo[2 * f] = s; in.stereo[2 * f + 1] = s; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// FmSine: fm_sine.rs:45-53
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fm_sample(uint64_t seq, double sr, double inv_sr, double mid, double amp, float x)
+{
+    double t = div_by_const((double)seq, sr, inv_sr);
+    double co = (mid + amp * (double)x) * 2.0 * kPi;
+    return (float)sin_f64(co * t);
+}
+
+__global__ void __launch_bounds__(kThreads) fm_sine_kernel(const __grid_constant__ FmBatch b)
+{
+    const FmInst& in = b.inst[blockIdx.y];
+    uint64_t f0 = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+    if (f0 >= b.frames) return;
+    if (f0 + 4 <= b.frames) {
+        float4 x = in.in ? ldg_stream(in.in + f0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float s0 = fm_sample(b.t0 + f0 + 0, b.sample_rate, b.inv_sample_rate, in.freq_mid, in.freq_amp, x.x);
+        float s1 = fm_sample(b.t0 + f0 + 1, b.sample_rate, b.inv_sample_rate, in.freq_mid, in.freq_amp, x.y);
+        float s2 = fm_sample(b.t0 + f0 + 2, b.sample_rate, b.inv_sample_rate, in.freq_mid, in.freq_amp, x.z);
+        float s3 = fm_sample(b.t0 + f0 + 3, b.sample_rate, b.inv_sample_rate, in.freq_mid, in.freq_amp, x.w);
+        st4(in.out + 2 * f0, make_float4(s0, s0, s1, s1));
+        st4(in.out + 2 * f0 + 4, make_float4(s2, s2, s3, s3));
+    } else {
+        for (uint64_t f = f0; f < b.frames; f++) {
+            float x = in.in ? in.in[f] : 0.f;
+            float s = fm_sample(b.t0 + f, b.sample_rate, b.inv_sample_rate, in.freq_mid, in.freq_amp, x);
+            in.out[2 * f] = s;
+            in.out[2 * f + 1] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Mixer: mixer.rs:54-68.  One thread per float4 of output, channels summed in channel order so
+// the f32 accumulation order is the reference's.  No inter-thread reduction exists on this bus:
+// the sum runs over channels, which a thread walks serially with all its loads in flight.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float mix1(float x, double g) { return (float)((double)x * g); }
+
+template <int UNROLL>
+__global__ void __launch_bounds__(kThreads) mixer_kernel(const __grid_constant__ MixerLaunch p)
+{
+    const uint64_t n4 = p.len >> 2;
+    const uint64_t i0 = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) * UNROLL;
+    if (i0 < n4) {
+        float4 m[UNROLL], c[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const bool live = i0 + u < n4;
+            if (p.accumulate && live) {
+                m[u] = *reinterpret_cast<const float4*>(p.master + 4 * (i0 + u));
+                c[u] = *reinterpret_cast<const float4*>(p.cue + 4 * (i0 + u));
+            } else {
+                m[u] = make_float4(0.f, 0.f, 0.f, 0.f);   // util::zero(master), util::zero(cue)
+                c[u] = m[u];
+            }
+        }
+#pragma unroll 4
+        for (int ch = 0; ch < p.channels; ch++) {
+            const float* src = p.ch[ch].in;
+            const double g = p.ch[ch].gain;
+            const bool cue = p.ch[ch].cue != 0;
+            float4 x[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++)
+                x[u] = (src && i0 + u < n4) ? ldg_stream(src + 4 * (i0 + u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                m[u].x += mix1(x[u].x, g); m[u].y += mix1(x[u].y, g);
+                m[u].z += mix1(x[u].z, g); m[u].w += mix1(x[u].w, g);
+                if (cue) { c[u].x += x[u].x; c[u].y += x[u].y; c[u].z += x[u].z; c[u].w += x[u].w; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            if (i0 + u < n4) {
+                st4(p.master + 4 * (i0 + u), m[u]);
+                st4(p.cue + 4 * (i0 + u), c[u]);
+            }
+        }
+    }
+    // scalar tail (len % 4 floats), handled by the first threads of block 0
+    const uint64_t tail0 = n4 << 2;
+    if (blockIdx.x == 0 && tail0 + threadIdx.x < p.len) {
+        const uint64_t i = tail0 + threadIdx.x;
+        float m = p.accumulate ? p.master[i] : 0.f, c = p.accumulate ? p.cue[i] : 0.f;
+        for (int ch = 0; ch < p.channels; ch++) {
+            float x = p.ch[ch].in ? p.ch[ch].in[i] : 0.f;
+            m += mix1(x, p.ch[ch].gain);
+            if (p.ch[ch].cue) c += x;
+        }
+        p.master[i] = m;
+        p.cue[i] = c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Amplifier: amplifier.rs:52-57,71-73.  One thread = 4 frames = 8 stereo floats + 4 control floats.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float amp1(float x, double mod_value, double depth, double amplitude)
+{
+    double dv = 1.0 - depth + depth * mod_value;      // depth(value, depth)
+    return (float)((double)x * dv * amplitude);
+}
+
+__global__ void __launch_bounds__(kThreads) amplifier_kernel(const __grid_constant__ AmpBatch b)
+{
+    const AmpInst& in = b.inst[blockIdx.y];
+    uint64_t f0 = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+    if (f0 >= b.frames) return;
+    const double d = in.mod_depth, a = in.amplitude;
+    if (f0 + 4 <= b.frames) {
+        float4 x0 = in.in ? ldg_stream(in.in + 2 * f0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 x1 = in.in ? ldg_stream(in.in + 2 * f0 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        double m0 = 1.0, m1 = 1.0, m2 = 1.0, m3 = 1.0;
+        if (in.mod) {
+            float4 mv = ldg_stream(in.mod + f0);
+            m0 = (double)mv.x; m1 = (double)mv.y; m2 = (double)mv.z; m3 = (double)mv.w;
+        }
+        st4(in.out + 2 * f0, make_float4(amp1(x0.x, m0, d, a), amp1(x0.y, m0, d, a),
+                                         amp1(x0.z, m1, d, a), amp1(x0.w, m1, d, a)));
+        st4(in.out + 2 * f0 + 4, make_float4(amp1(x1.x, m2, d, a), amp1(x1.y, m2, d, a),
+                                             amp1(x1.z, m3, d, a), amp1(x1.w, m3, d, a)));
+    } else {
+        for (uint64_t f = f0; f < b.frames; f++) {
+            double mv = in.mod ? (double)in.mod[f] : 1.0;
+            in.out[2 * f] = amp1(in.in ? in.in[2 * f] : 0.f, mv, d, a);
+            in.out[2 * f + 1] = amp1(in.in ? in.in[2 * f + 1] : 0.f, mv, d, a);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// StereoPanner stereo_panner.rs:35-38 ; StereoSplitter stereo_splitter.rs:41-44 ; Trigger trigger.rs:38-45
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) panner_kernel(const __grid_constant__ PanBatch b)
+{
+    const PanInst& in = b.inst[blockIdx.y];
+    uint64_t f0 = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+    if (f0 >= b.frames) return;
+    if (f0 + 4 <= b.frames) {
+        float4 l = in.left ? ldg_stream(in.left + f0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 r = in.right ? ldg_stream(in.right + f0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        st4(in.out + 2 * f0, make_float4(l.x, r.x, l.y, r.y));
+        st4(in.out + 2 * f0 + 4, make_float4(l.z, r.z, l.w, r.w));
+    } else {
+        for (uint64_t f = f0; f < b.frames; f++) {
+            in.out[2 * f] = in.left ? in.left[f] : 0.f;
+            in.out[2 * f + 1] = in.right ? in.right[f] : 0.f;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) splitter_kernel(const __grid_constant__ SplitBatch b)
+{
+    const SplitInst& in = b.inst[blockIdx.y];
+    uint64_t f0 = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+    if (f0 >= b.frames) return;
+    if (f0 + 4 <= b.frames) {
+        float4 a = in.in ? ldg_stream(in.in + 2 * f0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 c = in.in ? ldg_stream(in.in + 2 * f0 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        st4(in.left + f0, make_float4(a.x, a.z, c.x, c.z));
+        st4(in.right + f0, make_float4(a.y, a.w, c.y, c.w));
+    } else {
+        for (uint64_t f = f0; f < b.frames; f++) {
+            in.left[f] = in.in ? in.in[2 * f] : 0.f;
+            in.right[f] = in.in ? in.in[2 * f + 1] : 0.f;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) fill_kernel(const __grid_constant__ FillBatch b)
+{
+    const FillInst& in = b.inst[blockIdx.y];
+    uint64_t i0 = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+    if (i0 >= b.len) return;
+    const float v = in.value;
+    if (i0 + 4 <= b.len) st4(in.out + i0, make_float4(v, v, v, v));
+    else for (uint64_t i = i0; i < b.len; i++) in.out[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Meter (new): per tick slot, per channel: peak |s|, sum of s^2 in f64, and the
+// OutputDevice clip predicate `s < -1 || s > 1` (output_device.rs:192-194,202-204).
+// One block per (slot, instance); warp-shuffle tree, then one smem hop across warps.
+// ------------------------------------------------------------------------------------------
+constexpr int kMeterThreads = 128;
+
+__global__ void __launch_bounds__(kMeterThreads) meter_kernel(const __grid_constant__ MeterBatch b)
+{
+    const MeterInst& in = b.inst[blockIdx.y];
+    const uint64_t slot = blockIdx.x;
+    const uint64_t f_begin = slot * b.spt;
+    uint64_t f_end = f_begin + b.spt;
+    if (f_end > b.frames) f_end = b.frames;
+    float pk0 = 0.f, pk1 = 0.f;
+    double sq0 = 0.0, sq1 = 0.0;
+    int clip = 0;
+    if (in.in) {
+        const float2* src = reinterpret_cast<const float2*>(in.in);
+        for (uint64_t f = f_begin + threadIdx.x; f < f_end; f += kMeterThreads) {
+            float2 s = src[f];
+            pk0 = fmaxf(pk0, fabsf(s.x));      // fmaxf drops NaN like the oracle's `a > peak`
+            pk1 = fmaxf(pk1, fabsf(s.y));
+            sq0 += (double)s.x * (double)s.x;
+            sq1 += (double)s.y * (double)s.y;
+            clip |= (s.x < -1.0f || s.x > 1.0f || s.y < -1.0f || s.y > 1.0f) ? 1 : 0;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        pk0 = fmaxf(pk0, __shfl_xor_sync(0xffffffffu, pk0, o));
+        pk1 = fmaxf(pk1, __shfl_xor_sync(0xffffffffu, pk1, o));
+        sq0 += __shfl_xor_sync(0xffffffffu, sq0, o);
+        sq1 += __shfl_xor_sync(0xffffffffu, sq1, o);
+        clip |= __shfl_xor_sync(0xffffffffu, clip, o);
+    }
+    __shared__ float s_pk[2][kMeterThreads / 32];
+    __shared__ double s_sq[2][kMeterThreads / 32];
+    __shared__ int s_clip[kMeterThreads / 32];
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_pk[0][w] = pk0; s_pk[1][w] = pk1; s_sq[0][w] = sq0; s_sq[1][w] = sq1; s_clip[w] = clip; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        MeterRecord r;
+        r.peak[0] = r.peak[1] = 0.f; r.sumsq[0] = r.sumsq[1] = 0.0; r.clip = 0; r._pad = 0;
+        for (int i = 0; i < kMeterThreads / 32; i++) {
+            r.peak[0] = fmaxf(r.peak[0], s_pk[0][i]); r.peak[1] = fmaxf(r.peak[1], s_pk[1][i]);
+            r.sumsq[0] += s_sq[0][i]; r.sumsq[1] += s_sq[1][i];
+            r.clip |= s_clip[i];
+        }
+        in.out[slot] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// PCM pack: src/video/encode.rs:184-195 (clamp, *32767, `as i16`); unpack: stream_input.rs:167-173
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ short pack1(float s)
+{
+    s = s > 1.0f ? 1.0f : (s < -1.0f ? -1.0f : s);        // NaN falls through both tests, as in Rust
+    float v = s * 32767.0f;
+    // Rust `as i16`: NaN -> 0, saturating, toward zero.  cvt.rzi.s16.f32 saturates; NaN needs the guard.
+    return (v != v) ? (short)0 : (short)__float2int_rz(fminf(fmaxf(v, -32768.0f), 32767.0f));
+}
+
+__global__ void __launch_bounds__(kThreads) pcm_pack_kernel(const float* __restrict__ in, short* __restrict__ out, uint64_t len)
+{
+    uint64_t i0 = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+    if (i0 >= len) return;
+    if (i0 + 4 <= len) {
+        float4 x = ldg_stream(in + i0);
+        short4 r = make_short4(pack1(x.x), pack1(x.y), pack1(x.z), pack1(x.w));
+        *reinterpret_cast<short4*>(out + i0) = r;
+    } else {
+        for (uint64_t i = i0; i < len; i++) out[i] = pack1(in[i]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) pcm_unpack_kernel(const short* __restrict__ in, float* __restrict__ out, uint64_t len)
+{
+    uint64_t i0 = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+    if (i0 >= len) return;
+    if (i0 + 4 <= len) {
+        short4 x = *reinterpret_cast<const short4*>(in + i0);
+        st4(out + i0, make_float4((float)x.x / 32768.0f, (float)x.y / 32768.0f,
+                                  (float)x.z / 32768.0f, (float)x.w / 32768.0f));
+    } else {
+        for (uint64_t i = i0; i < len; i++) out[i] = (float)in[i] / 32768.0f;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) fill_bytes_kernel(uint4* dst, size_t n16, uint32_t word)
+{
+    size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * kThreads;
+    for (; i < n16; i += stride) dst[i] = make_uint4(word, word, word, word);
+}
+
+int check_launch(mxl_ctx* ctx, const char* name)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("launch of %s failed: %s", name, cudaGetErrorString(e));
+        return MXL_ERR_CUDA;
+    }
+    ctx->launches++;
+    return MXL_OK;
+}
+
+}  // namespace
+
+#define MXL_REQUIRE_DEVICE(ctx)                                                  \
+    do {                                                                         \
+        if (!(ctx) || !(ctx)->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "no CUDA device bound to this context"); \
+        MXL_TRY((ctx)->activate());                                              \
+    } while (0)
+
+int launch_oscillator(mxl_ctx* ctx, const OscBatch& b)
+{
+    MXL_REQUIRE_DEVICE(ctx);
+    if (b.n <= 0 || b.frames == 0) return MXL_OK;
+    dim3 grid(blocks_for((b.frames + 3) / 4), b.n);
+    oscillator_kernel<<<grid, kThreads, 0, ctx->stream>>>(b);
+    return check_launch(ctx, "oscillator_kernel");
+}
+
+int launch_fm_sine(mxl_ctx* ctx, const FmBatch& b)
+{
+    MXL_REQUIRE_DEVICE(ctx);
+    if (b.n <= 0 || b.frames == 0) return MXL_OK;
+    dim3 grid(blocks_for((b.frames + 3) / 4), b.n);
+    fm_sine_kernel<<<grid, kThreads, 0, ctx->stream>>>(b);
+    return check_launch(ctx, "fm_sine_kernel");
+}
+
+int launch_mixer(mxl_ctx* ctx, const MixerLaunch& p)
+{
+    MXL_REQUIRE_DEVICE(ctx);
+    if (p.len == 0) return MXL_OK;
+    const uint64_t n4 = p.len >> 2;
+    // Few channels: two float4 per thread so each thread still keeps >= 4 loads in flight.
+    if (p.channels <= 4) {
+        unsigned g = blocks_for((n4 + 1) / 2);
+        mixer_kernel<2><<<g ? g : 1, kThreads, 0, ctx->stream>>>(p);
+    } else {
+        unsigned g = blocks_for(n4);
+        mixer_kernel<1><<<g ? g : 1, kThreads, 0, ctx->stream>>>(p);
+    }
+    return check_launch(ctx, "mixer_kernel");
+}
+
+int launch_amplifier(mxl_ctx* ctx, const AmpBatch& b)
+{
+    MXL_REQUIRE_DEVICE(ctx);
+    if (b.n <= 0 || b.frames == 0) return MXL_OK;
+    dim3 grid(blocks_for((b.frames + 3) / 4), b.n);
+    amplifier_kernel<<<grid, kThreads, 0, ctx->stream>>>(b);
+    return check_launch(ctx, "amplifier_kernel");
+}
+
+int launch_panner(mxl_ctx* ctx, const PanBatch& b)
+{
+    MXL_REQUIRE_DEVICE(ctx);
+    if (b.n <= 0 || b.frames == 0) return MXL_OK;
+    dim3 grid(blocks_for((b.frames + 3) / 4), b.n);
+    panner_kernel<<<grid, kThreads, 0, ctx->stream>>>(b);
+    return check_launch(ctx, "panner_kernel");
+}
+
+int launch_splitter(mxl_ctx* ctx, const SplitBatch& b)
+{
+    MXL_REQUIRE_DEVICE(ctx);
+    if (b.n <= 0 || b.frames == 0) return MXL_OK;
+    dim3 grid(blocks_for((b.frames + 3) / 4), b.n);
+    splitter_kernel<<<grid, kThreads, 0, ctx->stream>>>(b);
+    return check_launch(ctx, "splitter_kernel");
+}
+
+int launch_fill(mxl_ctx* ctx, const FillBatch& b)
+{
+    MXL_REQUIRE_DEVICE(ctx);
+    if (b.n <= 0 || b.len == 0) return MXL_OK;
+    dim3 grid(blocks_for((b.len + 3) / 4), b.n);
+    fill_kernel<<<grid, kThreads, 0, ctx->stream>>>(b);
+    return check_launch(ctx, "fill_kernel");
+}
+
+int launch_meter(mxl_ctx* ctx, const MeterBatch& b, uint32_t n_slots)
+{
+    MXL_REQUIRE_DEVICE(ctx);
+    if (b.n <= 0 || n_slots == 0) return MXL_OK;
+    dim3 grid(n_slots, b.n);
+    meter_kernel<<<grid, kMeterThreads, 0, ctx->stream>>>(b);
+    return check_launch(ctx, "meter_kernel");
+}
+
+int launch_pcm_pack(mxl_ctx* ctx, const float* in, int16_t* out, uint64_t len)
+{
+    MXL_REQUIRE_DEVICE(ctx);
+    if (len == 0) return MXL_OK;
+    pcm_pack_kernel<<<blocks_for((len + 3) / 4), kThreads, 0, ctx->stream>>>(in, reinterpret_cast<short*>(out), len);
+    return check_launch(ctx, "pcm_pack_kernel");
+}
+
+int launch_pcm_unpack(mxl_ctx* ctx, const int16_t* in, float* out, uint64_t len)
+{
+    MXL_REQUIRE_DEVICE(ctx);
+    if (len == 0) return MXL_OK;
+    pcm_unpack_kernel<<<blocks_for((len + 3) / 4), kThreads, 0, ctx->stream>>>(reinterpret_cast<const short*>(in), out, len);
+    return check_launch(ctx, "pcm_unpack_kernel");
+}
+
+int launch_fill_bytes(mxl_ctx* ctx, void* dst, size_t bytes, uint8_t value)
+{
+    MXL_REQUIRE_DEVICE(ctx);
+    if (bytes == 0) return MXL_OK;
+    uint32_t word = 0x01010101u * value;
+    size_t n16 = bytes / 16;
+    unsigned blocks = ctx->sm_count > 0 ? ctx->sm_count * 8 : 1184;
+    fill_bytes_kernel<<<blocks, kThreads, 0, ctx->stream>>>(reinterpret_cast<uint4*>(dst), n16, word);
+    MXL_TRY(check_launch(ctx, "fill_bytes_kernel"));
+    if (bytes % 16) MXL_CUDA(cudaMemsetAsync((uint8_t*)dst + n16 * 16, value, bytes % 16, ctx->stream));
+    return MXL_OK;
+}
+
+}  // namespace k
+}  // namespace mxl

@@ -1,0 +1,121 @@
+// common.h -- internal types of libmixlab_b200 (context, lines, frames, error plumbing).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/mixlab_b200.h"
+
+namespace mxl {
+
+// ---- errors: never unwind across the C ABI ------------------------------------------------------
+void set_error(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
+const char* last_error();
+
+#define MXL_FAIL(code, ...)            \
+    do {                               \
+        ::mxl::set_error(__VA_ARGS__); \
+        return (code);                 \
+    } while (0)
+
+#define MXL_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            ::mxl::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                             __LINE__);                                                         \
+            return MXL_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+#define MXL_TRY(expr)              \
+    do {                           \
+        int _s = (expr);           \
+        if (_s != MXL_OK) return _s; \
+    } while (0)
+
+// Rational64 as used by MediaTime / MediaDuration (util/src/time.rs:9-10,77-78): always reduced,
+// denominator positive.
+struct Rational {
+    int64_t num = 0, den = 1;
+    static Rational make(int64_t n, int64_t d);
+    Rational operator+(const Rational& o) const;
+    bool operator>=(const Rational& o) const;
+    bool operator==(const Rational& o) const { return num == o.num && den == o.den; }
+};
+
+}  // namespace mxl
+
+struct mxl_ctx {
+    int device = MXL_DEVICE_NONE;
+    uint32_t sample_rate = 0;
+    uint32_t spt = 0;                 // SAMPLES_PER_TICK
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    void* flush_buf = nullptr;
+    size_t flush_bytes = 0;
+    int sm_count = 0;
+
+    // free yuv420p frame buffers by byte size: frames come and go every tick (AvFrame::blank per
+    // tick in the reference, video_mixer.rs:151), cudaMalloc/cudaFree must not.
+    std::unordered_map<uint64_t, std::vector<uint8_t*>> frame_pool;
+    // EqThree chunk plans by chunk length (see modules.cu: eq_plan_for)
+    std::map<uint32_t, std::vector<double>> eq_plans;
+
+    bool has_device() const { return device >= 0; }
+    int activate() const;            // cudaSetDevice
+};
+
+struct mxl_frame {
+    mxl_ctx* ctx = nullptr;
+    mxl_frame_layout layout{};
+    uint8_t* dev = nullptr;
+    std::atomic<int> refs{1};
+};
+
+struct VideoSlot {
+    mxl_frame* frame = nullptr;       // retained
+    mxl::Rational duration_hint;      // video::Frame.duration_hint (src/video.rs)
+    mxl::Rational tick_offset;        // engine::VideoFrame.tick_offset (io.rs:11-17)
+};
+
+struct mxl_line {
+    mxl_ctx* ctx = nullptr;
+    int type = MXL_LINE_MONO;
+    uint64_t frames = 0;              // audio: samples per channel; video: tick slots
+    uint64_t capacity = 0;            // audio: frames the allocation can hold
+    float* dev = nullptr;             // audio payload
+    std::vector<VideoSlot> slots;     // video payload
+
+    uint64_t len() const { return type == MXL_LINE_STEREO ? frames * 2 : (type == MXL_LINE_MONO ? frames : 0); }
+};
+
+namespace mxl {
+
+// Checked accessors mirroring InputRef::expect_* / OutputRef::expect_* (io.rs:36-61,100-126).
+// `line == nullptr` is InputRef::Disconnected.
+int expect_input(const mxl_line* line, int type, const char* what);
+int expect_output(const mxl_line* line, int type, const char* what);
+
+mxl_line* line_alloc(mxl_ctx* ctx, int type, uint64_t frames);
+void line_free(mxl_line* line);
+int line_resize(mxl_line* line, uint64_t frames);   // reallocates (contents undefined) if larger
+
+mxl_frame* frame_alloc(mxl_ctx* ctx, uint32_t w, uint32_t h);
+void frame_release(mxl_frame* f);
+inline mxl_frame* frame_retain(mxl_frame* f) { if (f) f->refs.fetch_add(1); return f; }
+void video_slot_set(VideoSlot& s, mxl_frame* f, Rational dur, Rational off);
+
+void frame_layout_yuv420p(uint32_t w, uint32_t h, mxl_frame_layout* out);
+
+}  // namespace mxl

@@ -1,0 +1,561 @@
+// core.cu -- context, line buffers, frames, error state.
+#include <string.h>
+
+#include <mutex>
+
+#include "common.h"
+#include "kernels.h"
+
+namespace mxl {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+}
+
+const char* last_error() { return g_error; }
+
+// ---- Rational64 (num_rational semantics: reduced, den > 0) ---------------------------------------
+static int64_t gcd64(int64_t a, int64_t b)
+{
+    if (a < 0) a = -a;
+    if (b < 0) b = -b;
+    while (b) { int64_t t = a % b; a = b; b = t; }
+    return a;
+}
+
+Rational Rational::make(int64_t n, int64_t d)
+{
+    Rational r;
+    if (d == 0) { r.num = n; r.den = 1; return r; }     // Rational64::new panics; callers validate
+    if (d < 0) { n = -n; d = -d; }
+    int64_t g = gcd64(n, d);
+    if (g > 1) { n /= g; d /= g; }
+    r.num = n; r.den = d;
+    return r;
+}
+
+Rational Rational::operator+(const Rational& o) const
+{
+    // lcm-based like num_rational's Add
+    int64_t g = gcd64(den, o.den);
+    int64_t l = den / g * o.den;
+    __int128 n = (__int128)num * (l / den) + (__int128)o.num * (l / o.den);
+    return Rational::make((int64_t)n, l);
+}
+
+bool Rational::operator>=(const Rational& o) const
+{
+    return (__int128)num * o.den >= (__int128)o.num * den;
+}
+
+// ---- checked line access (io.rs:36-61,100-126) ---------------------------------------------------
+static const char* type_name(int t)
+{
+    return t == MXL_LINE_MONO ? "mono" : (t == MXL_LINE_STEREO ? "stereo" : (t == MXL_LINE_VIDEO ? "video" : "?"));
+}
+
+int expect_input(const mxl_line* line, int type, const char* what)
+{
+    if (!line) return MXL_OK;   // Disconnected: expect_* hands out the static zero buffer / None
+    if (line->type != type)
+        MXL_FAIL(MXL_ERR_LINE_TYPE, "%s: expected %s input, got %s", what, type_name(type), type_name(line->type));
+    return MXL_OK;
+}
+
+int expect_output(const mxl_line* line, int type, const char* what)
+{
+    if (!line) MXL_FAIL(MXL_ERR_INVALID, "%s: output line is NULL", what);
+    if (line->type != type)
+        MXL_FAIL(MXL_ERR_LINE_TYPE, "%s: expected %s output, got %s", what, type_name(type), type_name(line->type));
+    return MXL_OK;
+}
+
+// ---- lines ---------------------------------------------------------------------------------------
+mxl_line* line_alloc(mxl_ctx* ctx, int type, uint64_t frames)
+{
+    if (!ctx) { set_error("line_alloc: NULL context"); return nullptr; }
+    if (type != MXL_LINE_MONO && type != MXL_LINE_STEREO && type != MXL_LINE_VIDEO) {
+        set_error("line_alloc: bad line type %d", type);
+        return nullptr;
+    }
+    mxl_line* l = new mxl_line();
+    l->ctx = ctx; l->type = type; l->frames = frames; l->capacity = frames;
+    if (type == MXL_LINE_VIDEO) {
+        l->slots.resize(frames);
+        return l;
+    }
+    if (!ctx->has_device()) { set_error("line_alloc: context has no device"); delete l; return nullptr; }
+    if (ctx->activate() != MXL_OK) { delete l; return nullptr; }
+    size_t bytes = (size_t)l->len() * sizeof(float);
+    if (bytes) {
+        cudaError_t e = cudaMalloc(&l->dev, bytes);
+        if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); delete l; return nullptr; }
+        e = cudaMemsetAsync(l->dev, 0, bytes, ctx->stream);        // vec![0.0; N]  (io.rs:73-74)
+        if (e != cudaSuccess) { set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(e)); cudaFree(l->dev); delete l; return nullptr; }
+    }
+    return l;
+}
+
+void line_free(mxl_line* l)
+{
+    if (!l) return;
+    if (l->type == MXL_LINE_VIDEO) {
+        for (auto& s : l->slots) frame_release(s.frame);
+    } else if (l->dev) {
+        if (l->ctx) l->ctx->activate();
+        cudaFree(l->dev);
+    }
+    delete l;
+}
+
+int line_resize(mxl_line* l, uint64_t frames)
+{
+    if (l->type == MXL_LINE_VIDEO) {
+        for (auto& s : l->slots) { frame_release(s.frame); s.frame = nullptr; }
+        l->slots.assign(frames, VideoSlot());
+        l->frames = frames;
+        return MXL_OK;
+    }
+    if (frames <= l->capacity) { l->frames = frames; return MXL_OK; }
+    MXL_TRY(l->ctx->activate());
+    // cudaFree synchronises the device; lines only grow between runs.
+    if (l->dev) { MXL_CUDA(cudaFree(l->dev)); l->dev = nullptr; }
+    l->frames = frames;
+    l->capacity = frames;
+    size_t bytes = (size_t)l->len() * sizeof(float);
+    if (bytes) {
+        MXL_CUDA(cudaMalloc(&l->dev, bytes));
+        MXL_CUDA(cudaMemsetAsync(l->dev, 0, bytes, l->ctx->stream));
+    }
+    return MXL_OK;
+}
+
+// ---- frames --------------------------------------------------------------------------------------
+static uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+void frame_layout_yuv420p(uint32_t w, uint32_t h, mxl_frame_layout* out)
+{
+    // The layout av_frame_get_buffer(frame, 0) gives the reference (codec/src/ffmpeg/frame.rs:84-86):
+    // luma linesize = width padded to 32, chroma linesize = ceil(luma/2) padded to 32;
+    // chroma rows = ceil(h/2).  All linesizes are multiples of 32, which video_mixer.rs:196-201 asserts.
+    uint32_t luma = align_up(w, 32);
+    uint32_t chroma = align_up((luma + 1) / 2, 32);
+    out->width = w; out->height = h;
+    out->stride[0] = luma; out->stride[1] = chroma; out->stride[2] = chroma;
+    out->plane_h[0] = h; out->plane_h[1] = (h + 1) / 2; out->plane_h[2] = (h + 1) / 2;
+    uint64_t off = 0;
+    for (int p = 0; p < 3; p++) { out->offset[p] = off; off += (uint64_t)out->stride[p] * out->plane_h[p]; }
+    out->size = off;
+}
+
+mxl_frame* frame_alloc(mxl_ctx* ctx, uint32_t w, uint32_t h)
+{
+    if (!ctx || !ctx->has_device()) { set_error("frame_alloc: context has no device"); return nullptr; }
+    if (w == 0 || h == 0) { set_error("frame_alloc: empty picture %ux%u", w, h); return nullptr; }
+    if (ctx->activate() != MXL_OK) return nullptr;
+    mxl_frame* f = new mxl_frame();
+    f->ctx = ctx;
+    frame_layout_yuv420p(w, h, &f->layout);
+    auto pooled = ctx->frame_pool.find(f->layout.size);
+    if (pooled != ctx->frame_pool.end() && !pooled->second.empty()) {
+        f->dev = pooled->second.back();      // same stream => reuse is ordered after the last use
+        pooled->second.pop_back();
+        return f;
+    }
+    cudaError_t e = cudaMalloc(&f->dev, f->layout.size);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%llu) failed: %s", (unsigned long long)f->layout.size, cudaGetErrorString(e)); delete f; return nullptr; }
+    return f;
+}
+
+void frame_release(mxl_frame* f)
+{
+    if (!f) return;
+    if (f->refs.fetch_sub(1) == 1) {
+        if (f->dev) f->ctx->frame_pool[f->layout.size].push_back(f->dev);
+        delete f;
+    }
+}
+
+void video_slot_set(VideoSlot& s, mxl_frame* f, Rational dur, Rational off)
+{
+    frame_retain(f);
+    frame_release(s.frame);
+    s.frame = f;
+    s.duration_hint = dur;
+    s.tick_offset = off;
+}
+
+}  // namespace mxl
+
+int mxl_ctx::activate() const
+{
+    if (device < 0) MXL_FAIL(MXL_ERR_NO_DEVICE, "no CUDA device bound to this context");
+    MXL_CUDA(cudaSetDevice(device));
+    return MXL_OK;
+}
+
+using namespace mxl;
+
+// ================================================================================================
+// C ABI: context, lines, frames
+// ================================================================================================
+extern "C" {
+
+static mxl_ctx* ctx_create(int device, uint32_t sample_rate, uint32_t spt, cudaStream_t stream, bool external)
+{
+    if (sample_rate == 0 || spt == 0) { set_error("mxl_ctx_create: sample_rate and samples_per_tick must be non-zero"); return nullptr; }
+    mxl_ctx* c = new mxl_ctx();
+    c->sample_rate = sample_rate;
+    c->spt = spt;
+    c->device = device;
+    if (device < 0) { c->device = MXL_DEVICE_NONE; return c; }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device >= count) {
+        set_error("mxl_ctx_create: CUDA device %d not available (%s, %d devices); there is no CPU fallback", device,
+                  e != cudaSuccess ? cudaGetErrorString(e) : "ok", count);
+        delete c;
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", device); delete c; return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+        c->sm_count = prop.multiProcessorCount;
+        if (prop.major < 10) {
+            set_error("mxl_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+            delete c;
+            return nullptr;
+        }
+    }
+    if (external) {
+        c->stream = stream;
+        c->own_stream = false;
+    } else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete c; return nullptr; }
+        c->own_stream = true;
+    }
+    cudaEventCreate(&c->ev_begin);
+    cudaEventCreate(&c->ev_end);
+    return c;
+}
+
+mxl_ctx* mxl_ctx_create(int device, uint32_t sample_rate, uint32_t samples_per_tick)
+{
+    return ctx_create(device, sample_rate, samples_per_tick, nullptr, false);
+}
+
+mxl_ctx* mxl_ctx_create_on_stream(int device, uint32_t sample_rate, uint32_t samples_per_tick, void* cuda_stream)
+{
+    return ctx_create(device, sample_rate, samples_per_tick, (cudaStream_t)cuda_stream, true);
+}
+
+int mxl_ctx_destroy(mxl_ctx* ctx)
+{
+    if (!ctx) return MXL_OK;
+    if (ctx->has_device()) {
+        ctx->activate();
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+        for (auto& kv : ctx->frame_pool)
+            for (uint8_t* p : kv.second) cudaFree(p);
+        if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+        if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+        if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+    return MXL_OK;
+}
+
+int mxl_ctx_synchronize(mxl_ctx* ctx)
+{
+    if (!ctx) MXL_FAIL(MXL_ERR_INVALID, "NULL context");
+    MXL_TRY(ctx->activate());
+    MXL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MXL_OK;
+}
+
+void* mxl_ctx_stream(mxl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint32_t mxl_ctx_sample_rate(const mxl_ctx* ctx) { return ctx ? ctx->sample_rate : 0; }
+uint32_t mxl_ctx_samples_per_tick(const mxl_ctx* ctx) { return ctx ? ctx->spt : 0; }
+uint64_t mxl_ctx_launch_count(const mxl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int mxl_ctx_timer_begin(mxl_ctx* ctx)
+{
+    if (!ctx) MXL_FAIL(MXL_ERR_INVALID, "NULL context");
+    MXL_TRY(ctx->activate());
+    MXL_CUDA(cudaEventRecord(ctx->ev_begin, ctx->stream));
+    return MXL_OK;
+}
+
+int mxl_ctx_timer_end(mxl_ctx* ctx)
+{
+    if (!ctx) MXL_FAIL(MXL_ERR_INVALID, "NULL context");
+    MXL_TRY(ctx->activate());
+    MXL_CUDA(cudaEventRecord(ctx->ev_end, ctx->stream));
+    return MXL_OK;
+}
+
+int mxl_ctx_timer_elapsed_ms(mxl_ctx* ctx, float* ms)
+{
+    if (!ctx || !ms) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
+    MXL_TRY(ctx->activate());
+    MXL_CUDA(cudaEventSynchronize(ctx->ev_end));
+    MXL_CUDA(cudaEventElapsedTime(ms, ctx->ev_begin, ctx->ev_end));
+    return MXL_OK;
+}
+
+int mxl_ctx_flush_l2(mxl_ctx* ctx)
+{
+    if (!ctx) MXL_FAIL(MXL_ERR_INVALID, "NULL context");
+    MXL_TRY(ctx->activate());
+    if (!ctx->flush_buf) {
+        ctx->flush_bytes = (size_t)256 << 20;     // 2x the 126 MB L2
+        MXL_CUDA(cudaMalloc(&ctx->flush_buf, ctx->flush_bytes));
+    }
+    // not counted as a path kernel
+    uint64_t before = ctx->launches;
+    int s = k::launch_fill_bytes(ctx, ctx->flush_buf, ctx->flush_bytes, 0);
+    ctx->launches = before;
+    return s;
+}
+
+const char* mxl_last_error(void) { return last_error(); }
+const char* mxl_version(void) { return "mixlab-b200 0.1 (sm_100a)"; }
+
+void* mxl_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) { set_error("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+
+int mxl_host_free(void* p)
+{
+    if (!p) return MXL_OK;
+    MXL_CUDA(cudaFreeHost(p));
+    return MXL_OK;
+}
+
+// ---- audio lines ---------------------------------------------------------------------------------
+mxl_line* mxl_line_alloc(mxl_ctx* ctx, int line_type, uint64_t frames)
+{
+    if (line_type == MXL_LINE_VIDEO) { set_error("mxl_line_alloc: use mxl_video_line_alloc for video lines"); return nullptr; }
+    return line_alloc(ctx, line_type, frames);
+}
+
+int mxl_line_free(mxl_line* line) { line_free(line); return MXL_OK; }
+int mxl_line_type_of(const mxl_line* line) { return line ? line->type : MXL_ERR_INVALID; }
+uint64_t mxl_line_frames(const mxl_line* line) { return line ? line->frames : 0; }
+uint64_t mxl_line_len(const mxl_line* line) { return line ? line->len() : 0; }
+void* mxl_line_device_ptr(mxl_line* line) { return line ? line->dev : nullptr; }
+
+static int audio_line(const mxl_line* line, uint64_t n, const char* what)
+{
+    if (!line) MXL_FAIL(MXL_ERR_INVALID, "%s: NULL line", what);
+    if (line->type == MXL_LINE_VIDEO) MXL_FAIL(MXL_ERR_LINE_TYPE, "%s: video line has no sample payload", what);
+    if (n > line->len()) MXL_FAIL(MXL_ERR_LENGTH, "%s: %llu floats requested, line holds %llu", what,
+                                  (unsigned long long)n, (unsigned long long)line->len());
+    return line->ctx->activate();
+}
+
+int mxl_line_zero(mxl_line* line)
+{
+    MXL_TRY(audio_line(line, 0, "mxl_line_zero"));
+    if (line->len()) MXL_CUDA(cudaMemsetAsync(line->dev, 0, line->len() * sizeof(float), line->ctx->stream));
+    return MXL_OK;
+}
+
+int mxl_line_upload_async(mxl_line* line, const float* host, uint64_t n)
+{
+    MXL_TRY(audio_line(line, n, "mxl_line_upload"));
+    if (n && !host) MXL_FAIL(MXL_ERR_INVALID, "mxl_line_upload: NULL host pointer");
+    if (n) MXL_CUDA(cudaMemcpyAsync(line->dev, host, n * sizeof(float), cudaMemcpyHostToDevice, line->ctx->stream));
+    return MXL_OK;
+}
+
+int mxl_line_download_async(const mxl_line* line, float* host, uint64_t n)
+{
+    MXL_TRY(audio_line(line, n, "mxl_line_download"));
+    if (n && !host) MXL_FAIL(MXL_ERR_INVALID, "mxl_line_download: NULL host pointer");
+    if (n) MXL_CUDA(cudaMemcpyAsync(host, line->dev, n * sizeof(float), cudaMemcpyDeviceToHost, line->ctx->stream));
+    return MXL_OK;
+}
+
+int mxl_line_upload(mxl_line* line, const float* host, uint64_t n)
+{
+    MXL_TRY(mxl_line_upload_async(line, host, n));
+    MXL_CUDA(cudaStreamSynchronize(line->ctx->stream));
+    return MXL_OK;
+}
+
+int mxl_line_download(const mxl_line* line, float* host, uint64_t n)
+{
+    MXL_TRY(mxl_line_download_async(line, host, n));
+    MXL_CUDA(cudaStreamSynchronize(line->ctx->stream));
+    return MXL_OK;
+}
+
+// ---- frames --------------------------------------------------------------------------------------
+int mxl_frame_layout_yuv420p(uint32_t width, uint32_t height, mxl_frame_layout* out)
+{
+    if (!out) MXL_FAIL(MXL_ERR_INVALID, "NULL layout");
+    frame_layout_yuv420p(width, height, out);
+    return MXL_OK;
+}
+
+int mxl_unify_picture_settings(uint32_t aw, uint32_t ah, uint32_t bw, uint32_t bh, uint32_t* w, uint32_t* h)
+{
+    if (!w || !h) MXL_FAIL(MXL_ERR_INVALID, "NULL output");
+    // video_mixer.rs:276-297; yuv420p => log2_chroma_w = log2_chroma_h = 1, masks = 1
+    uint32_t width = aw > bw ? aw : bw;
+    uint32_t height = ah > bh ? ah : bh;
+    *w = (width + 1u) & ~1u;
+    *h = (height + 1u) & ~1u;
+    return MXL_OK;
+}
+
+int mxl_scale_geometry_yuv420p(uint32_t in_w, uint32_t in_h, uint32_t out_w, uint32_t out_h, mxl_scale_geometry* out)
+{
+    if (!out) MXL_FAIL(MXL_ERR_INVALID, "NULL output");
+    if (in_w == 0 || in_h == 0) MXL_FAIL(MXL_ERR_INVALID, "empty input picture");   // Ratio::new would panic on /0
+    // src/video/encode.rs:355-374: scale_factor = min(W/w, H/h) as an exact ratio
+    uint64_t sn, sd;
+    if ((uint64_t)out_w * in_h <= (uint64_t)out_h * in_w) { sn = out_w; sd = in_w; } else { sn = out_h; sd = in_h; }
+    uint32_t sw = (uint32_t)((sn * in_w) / sd) & ~1u;       // to_integer() then align_horizontal (pixfmt.rs:104-106)
+    uint32_t sh = (uint32_t)((sn * in_h) / sd) & ~1u;       // align_vertical (pixfmt.rs:108-110)
+    out->scaled_w = sw;
+    out->scaled_h = sh;
+    out->letterbox_x = ((out_w - sw) / 2) & ~1u;
+    out->letterbox_y = ((out_h - sh) / 2) & ~1u;
+    return MXL_OK;
+}
+
+uint8_t mxl_fader_to_u8(double fader)
+{
+    // Rust `(fader * 255.0) as u8`: NaN -> 0, saturating, toward zero
+    double v = fader * 255.0;
+    if (v != v) return 0;
+    if (v >= 255.0) return 255;
+    if (v <= 0.0) return 0;
+    return (uint8_t)v;
+}
+
+mxl_frame* mxl_frame_alloc(mxl_ctx* ctx, uint32_t width, uint32_t height) { return frame_alloc(ctx, width, height); }
+
+mxl_frame* mxl_frame_blank(mxl_ctx* ctx, uint32_t width, uint32_t height)
+{
+    mxl_frame* f = frame_alloc(ctx, width, height);
+    if (!f) return nullptr;
+    if (k::launch_blank(ctx, f->layout, f->dev) != MXL_OK) { frame_release(f); return nullptr; }
+    return f;
+}
+
+mxl_frame* mxl_frame_retain(mxl_frame* frame) { return frame_retain(frame); }
+int mxl_frame_release(mxl_frame* frame) { frame_release(frame); return MXL_OK; }
+
+int mxl_frame_get_layout(const mxl_frame* frame, mxl_frame_layout* out)
+{
+    if (!frame || !out) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
+    *out = frame->layout;
+    return MXL_OK;
+}
+
+void* mxl_frame_device_ptr(mxl_frame* frame) { return frame ? frame->dev : nullptr; }
+
+static int frame_copy_planes(const mxl_frame* f, uint8_t* const host[3], const uint32_t strides[3], bool upload)
+{
+    if (!f || !host || !strides) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
+    MXL_TRY(f->ctx->activate());
+    for (int p = 0; p < 3; p++) {
+        uint32_t w = p == 0 ? f->layout.width : (f->layout.width + 1) / 2;
+        if (!host[p] || strides[p] < w) MXL_FAIL(MXL_ERR_INVALID, "plane %d: NULL pointer or stride %u < width %u", p, strides[p], w);
+        if (upload)
+            MXL_CUDA(cudaMemcpy2DAsync(f->dev + f->layout.offset[p], f->layout.stride[p], host[p], strides[p], w,
+                                       f->layout.plane_h[p], cudaMemcpyHostToDevice, f->ctx->stream));
+        else
+            MXL_CUDA(cudaMemcpy2DAsync(host[p], strides[p], f->dev + f->layout.offset[p], f->layout.stride[p], w,
+                                       f->layout.plane_h[p], cudaMemcpyDeviceToHost, f->ctx->stream));
+    }
+    MXL_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    return MXL_OK;
+}
+
+int mxl_frame_upload(mxl_frame* frame, const uint8_t* const planes[3], const uint32_t strides[3])
+{
+    return frame_copy_planes(frame, const_cast<uint8_t* const*>(planes), strides, true);
+}
+
+int mxl_frame_download(const mxl_frame* frame, uint8_t* const planes[3], const uint32_t strides[3])
+{
+    return frame_copy_planes(frame, planes, strides, false);
+}
+
+int mxl_frame_upload_raw_async(mxl_frame* frame, const uint8_t* host, uint64_t size)
+{
+    if (!frame || !host) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
+    if (size != frame->layout.size) MXL_FAIL(MXL_ERR_LENGTH, "raw size %llu != frame size %llu", (unsigned long long)size, (unsigned long long)frame->layout.size);
+    MXL_TRY(frame->ctx->activate());
+    MXL_CUDA(cudaMemcpyAsync(frame->dev, host, size, cudaMemcpyHostToDevice, frame->ctx->stream));
+    return MXL_OK;
+}
+
+int mxl_frame_download_raw_async(const mxl_frame* frame, uint8_t* host, uint64_t size)
+{
+    if (!frame || !host) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
+    if (size != frame->layout.size) MXL_FAIL(MXL_ERR_LENGTH, "raw size %llu != frame size %llu", (unsigned long long)size, (unsigned long long)frame->layout.size);
+    MXL_TRY(frame->ctx->activate());
+    MXL_CUDA(cudaMemcpyAsync(host, frame->dev, size, cudaMemcpyDeviceToHost, frame->ctx->stream));
+    return MXL_OK;
+}
+
+int mxl_frame_upload_raw(mxl_frame* frame, const uint8_t* host, uint64_t size)
+{
+    MXL_TRY(mxl_frame_upload_raw_async(frame, host, size));
+    MXL_CUDA(cudaStreamSynchronize(frame->ctx->stream));
+    return MXL_OK;
+}
+
+int mxl_frame_download_raw(const mxl_frame* frame, uint8_t* host, uint64_t size)
+{
+    MXL_TRY(mxl_frame_download_raw_async(frame, host, size));
+    MXL_CUDA(cudaStreamSynchronize(frame->ctx->stream));
+    return MXL_OK;
+}
+
+// ---- video lines ---------------------------------------------------------------------------------
+mxl_line* mxl_video_line_alloc(mxl_ctx* ctx, uint32_t ticks) { return line_alloc(ctx, MXL_LINE_VIDEO, ticks); }
+
+int mxl_video_line_set(mxl_line* line, uint32_t slot, mxl_frame* frame, int64_t duration_num, int64_t duration_den,
+                       int64_t offset_num, int64_t offset_den)
+{
+    if (!line) MXL_FAIL(MXL_ERR_INVALID, "NULL line");
+    if (line->type != MXL_LINE_VIDEO) MXL_FAIL(MXL_ERR_LINE_TYPE, "mxl_video_line_set: not a video line");
+    if (slot >= line->slots.size()) MXL_FAIL(MXL_ERR_LENGTH, "slot %u out of %zu", slot, line->slots.size());
+    if (frame && (duration_den == 0 || offset_den == 0)) MXL_FAIL(MXL_ERR_INVALID, "zero denominator");
+    video_slot_set(line->slots[slot], frame, frame ? Rational::make(duration_num, duration_den) : Rational(),
+                   frame ? Rational::make(offset_num, offset_den) : Rational());
+    return MXL_OK;
+}
+
+mxl_frame* mxl_video_line_get(const mxl_line* line, uint32_t slot)
+{
+    if (!line || line->type != MXL_LINE_VIDEO || slot >= line->slots.size()) return nullptr;
+    return line->slots[slot].frame;
+}
+
+int mxl_video_line_clear(mxl_line* line)
+{
+    if (!line) MXL_FAIL(MXL_ERR_INVALID, "NULL line");
+    if (line->type != MXL_LINE_VIDEO) MXL_FAIL(MXL_ERR_LINE_TYPE, "mxl_video_line_clear: not a video line");
+    for (auto& s : line->slots) { frame_release(s.frame); s = VideoSlot(); }
+    return MXL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,367 @@
+// graph.cu -- Workspace (src/engine/workspace.rs) + Engine::run_tick (src/engine.rs:400-510) with
+// device-resident line buffers.
+//
+// What the reference does every tick -- build the terminal set, DFS-topsort from it, allocate and
+// zero one Vec per output, run modules serially -- is done here once per topology change.  The plan
+// groups modules by (dependency level, kind) into STAGES; a stage is one batched kernel launch over
+// all its modules and over every tick of the call (each audio line holds n_ticks*S frames, legal
+// because the reference's run_tick loops are length-agnostic and module state carries across).
+#include <algorithm>
+#include <map>
+#include <set>
+
+#include "modules.h"
+
+using namespace mxl;
+
+struct Stage {
+    int level = 0;
+    int kind = 0;
+    std::vector<int> modules;
+    float last_ms = -1.f;
+    int last_launches = 0;
+    uint64_t last_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+struct mxl_graph {
+    mxl_ctx* ctx = nullptr;
+    std::vector<mxl_module*> modules;                                  // index = ModuleId; nullptr = removed
+    std::map<std::pair<int, uint32_t>, std::pair<int, uint32_t>> connections;   // InputId -> OutputId (workspace.rs:17)
+    bool dirty = true;
+    bool profiling = false;
+    bool timings_pending = false;
+
+    // plan
+    std::vector<int> run_order;
+    std::vector<int> position;                                         // module id -> index in run_order, -1 = does not run
+    std::vector<Stage> stages;
+    std::vector<std::vector<mxl_line*>> out_lines;                     // graph-owned output lines per module
+    // resolved inputs: per module, per input: producing (module, output) or (-1, 0) = Disconnected
+    std::vector<std::vector<std::pair<int, uint32_t>>> resolved;
+
+    ~mxl_graph()
+    {
+        for (auto& s : stages) {
+            if (s.ev0) cudaEventDestroy(s.ev0);
+            if (s.ev1) cudaEventDestroy(s.ev1);
+        }
+        for (auto& v : out_lines) for (mxl_line* l : v) line_free(l);
+        for (mxl_module* m : modules) delete m;
+    }
+};
+
+namespace {
+
+bool is_source(int kind) { return kind == MXL_MOD_SOURCE_MONO || kind == MXL_MOD_SOURCE_STEREO || kind == MXL_MOD_SOURCE_VIDEO; }
+
+mxl_module* module_at(mxl_graph* g, int id)
+{
+    return (id >= 0 && (size_t)id < g->modules.size()) ? g->modules[id] : nullptr;
+}
+
+// engine.rs:439-457
+void traverse(mxl_graph* g, int id, std::vector<char>& seen)
+{
+    if (seen[id]) return;
+    seen[id] = 1;
+    mxl_module* m = g->modules[id];
+    for (uint32_t i = 0; i < m->inputs.size(); i++) {
+        auto it = g->connections.find({id, i});
+        if (it != g->connections.end() && module_at(g, it->second.first)) traverse(g, it->second.first, seen);
+    }
+    g->run_order.push_back(id);
+}
+
+int build_plan(mxl_graph* g)
+{
+    const size_t n = g->modules.size();
+    // terminal modules = modules that feed nobody (engine.rs:408-416)
+    std::vector<char> terminal(n, 0), seen(n, 0);
+    for (size_t i = 0; i < n; i++) terminal[i] = g->modules[i] != nullptr;
+    for (auto& c : g->connections)
+        if (module_at(g, c.first.first) && module_at(g, c.second.first)) terminal[c.second.first] = 0;
+    // DFS from each terminal (engine.rs:421-430).  The reference walks a HashSet in arbitrary order;
+    // ascending ModuleId here, which is one of the orders it can take.
+    g->run_order.clear();
+    for (size_t i = 0; i < n; i++)
+        if (terminal[i]) traverse(g, (int)i, seen);
+    g->position.assign(n, -1);
+    for (size_t i = 0; i < g->run_order.size(); i++) g->position[g->run_order[i]] = (int)i;
+
+    // an input sees its producer's buffer only if the producer ran EARLIER in this tick
+    // (engine.rs:479-482: connections.get(..).and_then(|o| buffers.get(o)) else Disconnected)
+    g->resolved.assign(n, {});
+    std::vector<int> level(n, 0);
+    for (int id : g->run_order) {
+        mxl_module* m = g->modules[id];
+        g->resolved[id].assign(m->inputs.size(), {-1, 0u});
+        int lv = 0;
+        for (uint32_t i = 0; i < m->inputs.size(); i++) {
+            auto it = g->connections.find({id, i});
+            if (it == g->connections.end()) continue;
+            const int pm = it->second.first;
+            if (!module_at(g, pm) || g->position[pm] < 0 || g->position[pm] >= g->position[id]) continue;
+            g->resolved[id][i] = it->second;
+            lv = std::max(lv, level[pm] + 1);
+        }
+        level[id] = lv;
+    }
+
+    // stages by (level, kind)
+    for (auto& s : g->stages) {
+        if (s.ev0) cudaEventDestroy(s.ev0);
+        if (s.ev1) cudaEventDestroy(s.ev1);
+    }
+    g->stages.clear();
+    std::map<std::pair<int, int>, size_t> index;
+    for (int id : g->run_order) {
+        const int kind = g->modules[id]->kind;
+        auto key = std::make_pair(level[id], kind);
+        auto it = index.find(key);
+        if (it == index.end()) {
+            index[key] = g->stages.size();
+            Stage s;
+            s.level = level[id];
+            s.kind = kind;
+            g->stages.push_back(s);
+            it = index.find(key);
+        }
+        g->stages[it->second].modules.push_back(id);
+    }
+    std::stable_sort(g->stages.begin(), g->stages.end(), [](const Stage& a, const Stage& b) {
+        return a.level != b.level ? a.level < b.level : a.kind < b.kind;
+    });
+
+    // graph-owned output lines (sources present their own line)
+    if (g->out_lines.size() < n) g->out_lines.resize(n);
+    for (size_t id = 0; id < n; id++) {
+        mxl_module* m = g->modules[id];
+        const size_t want = (m && !is_source(m->kind) && g->position[id] >= 0) ? m->outputs.size() : 0;
+        std::vector<mxl_line*>& v = g->out_lines[id];
+        bool same = v.size() == want;
+        for (size_t o = 0; same && o < want; o++) same = v[o]->type == m->outputs[o].type;
+        if (same) continue;
+        for (mxl_line* l : v) line_free(l);
+        v.clear();
+        if (!g->ctx->has_device()) continue;          // planning-only context: no buffers
+        for (size_t o = 0; o < want; o++) {
+            mxl_line* l = line_alloc(g->ctx, m->outputs[o].type, 0);
+            if (!l) return MXL_ERR_OOM;
+            v.push_back(l);
+        }
+    }
+    g->dirty = false;
+    g->timings_pending = false;
+    return MXL_OK;
+}
+
+mxl_line* output_line(mxl_graph* g, int id, uint32_t out)
+{
+    mxl_module* m = module_at(g, id);
+    if (!m || out >= m->outputs.size() || g->position[id] < 0) return nullptr;
+    if (is_source(m->kind)) return source_line(m);
+    return out < g->out_lines[id].size() ? g->out_lines[id][out] : nullptr;
+}
+
+void collect_timings(mxl_graph* g)
+{
+    if (!g->timings_pending) return;
+    for (auto& s : g->stages) {
+        if (s.ev0 && s.ev1 && cudaEventSynchronize(s.ev1) == cudaSuccess) {
+            float ms = -1.f;
+            if (cudaEventElapsedTime(&ms, s.ev0, s.ev1) == cudaSuccess) s.last_ms = ms;
+        }
+    }
+    g->timings_pending = false;
+}
+
+}  // namespace
+
+extern "C" {
+
+mxl_graph* mxl_graph_create(mxl_ctx* ctx)
+{
+    if (!ctx) { set_error("mxl_graph_create: NULL context"); return nullptr; }
+    mxl_graph* g = new mxl_graph();
+    g->ctx = ctx;
+    return g;
+}
+
+void mxl_graph_destroy(mxl_graph* g)
+{
+    if (!g) return;
+    if (g->ctx->has_device()) { g->ctx->activate(); cudaStreamSynchronize(g->ctx->stream); }
+    delete g;
+}
+
+int mxl_graph_add_module(mxl_graph* g, mxl_module* m)
+{
+    if (!g || !m) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
+    if (m->ctx != g->ctx) MXL_FAIL(MXL_ERR_INVALID, "module belongs to another context");
+    g->modules.push_back(m);
+    g->dirty = true;
+    return (int)g->modules.size() - 1;
+}
+
+int mxl_graph_remove_module(mxl_graph* g, int module_id)
+{
+    if (!g) MXL_FAIL(MXL_ERR_INVALID, "NULL graph");
+    mxl_module* m = module_at(g, module_id);
+    if (!m) MXL_FAIL(MXL_ERR_INVALID, "no module %d", module_id);
+    if (g->ctx->has_device()) { MXL_TRY(g->ctx->activate()); MXL_CUDA(cudaStreamSynchronize(g->ctx->stream)); }
+    // engine.rs:321-352 DeleteModule drops every connection touching the module
+    for (auto it = g->connections.begin(); it != g->connections.end();) {
+        if (it->first.first == module_id || it->second.first == module_id) it = g->connections.erase(it);
+        else ++it;
+    }
+    delete m;
+    g->modules[module_id] = nullptr;
+    g->dirty = true;
+    return MXL_OK;
+}
+
+mxl_module* mxl_graph_module(mxl_graph* g, int module_id) { return g ? module_at(g, module_id) : nullptr; }
+
+int mxl_graph_connect(mxl_graph* g, int in_module, uint32_t in_index, int out_module, uint32_t out_index)
+{
+    if (!g) MXL_FAIL(MXL_ERR_INVALID, "NULL graph");
+    // workspace.rs:97-114
+    mxl_module* im = module_at(g, in_module);
+    if (!im || in_index >= im->inputs.size()) MXL_FAIL(MXL_ERR_NO_INPUT, "connect: no input %d:%u", in_module, in_index);
+    mxl_module* om = module_at(g, out_module);
+    if (!om || out_index >= om->outputs.size()) MXL_FAIL(MXL_ERR_NO_OUTPUT, "connect: no output %d:%u", out_module, out_index);
+    if (im->inputs[in_index].type != om->outputs[out_index].type)
+        MXL_FAIL(MXL_ERR_TYPE_MISMATCH, "connect: line type mismatch between input %d:%u and output %d:%u", in_module, in_index, out_module, out_index);
+    g->connections[{in_module, in_index}] = {out_module, out_index};
+    g->dirty = true;
+    return MXL_OK;
+}
+
+int mxl_graph_disconnect(mxl_graph* g, int in_module, uint32_t in_index)
+{
+    if (!g) MXL_FAIL(MXL_ERR_INVALID, "NULL graph");
+    g->connections.erase({in_module, in_index});       // workspace.rs:116-118
+    g->dirty = true;
+    return MXL_OK;
+}
+
+int mxl_graph_plan(mxl_graph* g, int* order_out, uint32_t cap)
+{
+    if (!g) MXL_FAIL(MXL_ERR_INVALID, "NULL graph");
+    if (g->dirty) MXL_TRY(build_plan(g));
+    for (size_t i = 0; i < g->run_order.size() && i < cap && order_out; i++) order_out[i] = g->run_order[i];
+    return (int)g->run_order.size();
+}
+
+int mxl_graph_run_ticks(mxl_graph* g, uint64_t tick0, uint32_t n_ticks)
+{
+    if (!g) MXL_FAIL(MXL_ERR_INVALID, "NULL graph");
+    mxl_ctx* ctx = g->ctx;
+    if (!ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "mxl_graph_run_ticks: context has no CUDA device; there is no CPU fallback");
+    if (n_ticks == 0) return MXL_OK;
+    MXL_TRY(ctx->activate());
+    // a module whose params changed its terminals (Mixer::update re-creates itself, mixer.rs:40-44)
+    for (size_t id = 0; id < g->modules.size() && !g->dirty; id++) {
+        mxl_module* m = g->modules[id];
+        if (m && !is_source(m->kind) && g->position.size() > id && g->position[id] >= 0 && g->out_lines[id].size() != m->outputs.size()) g->dirty = true;
+        if (m && g->resolved.size() > id && g->position[id] >= 0 && g->resolved[id].size() != m->inputs.size()) g->dirty = true;
+    }
+    if (g->dirty) MXL_TRY(build_plan(g));
+    collect_timings(g);
+
+    const uint64_t frames = (uint64_t)n_ticks * ctx->spt;
+    const uint64_t t = tick0 * (uint64_t)ctx->spt;                     // engine.rs:490
+    for (int id : g->run_order)
+        for (mxl_line* l : g->out_lines[id])
+            MXL_TRY(line_resize(l, l->type == MXL_LINE_VIDEO ? n_ticks : frames));
+    // host-fed sources must cover the call
+    for (int id : g->run_order) {
+        mxl_module* m = g->modules[id];
+        if (!is_source(m->kind)) continue;
+        mxl_line* l = source_line(m);
+        if (l && l->frames < (l->type == MXL_LINE_VIDEO ? (uint64_t)n_ticks : frames))
+            MXL_FAIL(MXL_ERR_LENGTH, "source module %d: line holds %llu frames/slots, the call needs %llu", id,
+                     (unsigned long long)l->frames, (unsigned long long)(l->type == MXL_LINE_VIDEO ? (uint64_t)n_ticks : frames));
+    }
+
+    std::vector<mxl_module*> mods;
+    std::vector<IoSet> ios;
+    std::vector<const mxl_line*> in_ptrs;
+    std::vector<mxl_line*> out_ptrs;
+    for (Stage& s : g->stages) {
+        if (is_source(s.kind)) { s.last_launches = 0; s.last_bytes = 0; continue; }
+        mods.clear(); ios.clear(); in_ptrs.clear(); out_ptrs.clear();
+        size_t n_in_total = 0, n_out_total = 0;
+        for (int id : s.modules) { n_in_total += g->modules[id]->inputs.size(); n_out_total += g->modules[id]->outputs.size(); }
+        in_ptrs.reserve(n_in_total + 1);
+        out_ptrs.reserve(n_out_total + 1);
+        for (int id : s.modules) {
+            mxl_module* m = g->modules[id];
+            IoSet io{};
+            io.in = in_ptrs.data() + in_ptrs.size();
+            io.n_in = (uint32_t)m->inputs.size();
+            for (uint32_t i = 0; i < io.n_in; i++) {
+                const auto& r = g->resolved[id][i];
+                const mxl_line* l = r.first >= 0 ? output_line(g, r.first, r.second) : nullptr;
+                // a source line longer than the call is presented at the call's length
+                in_ptrs.push_back(l);
+            }
+            io.out = out_ptrs.data() + out_ptrs.size();
+            io.n_out = (uint32_t)m->outputs.size();
+            for (mxl_line* l : g->out_lines[id]) out_ptrs.push_back(l);
+            mods.push_back(m);
+            ios.push_back(io);
+        }
+        if (g->profiling) {
+            if (!s.ev0) { MXL_CUDA(cudaEventCreate(&s.ev0)); MXL_CUDA(cudaEventCreate(&s.ev1)); }
+            MXL_CUDA(cudaEventRecord(s.ev0, ctx->stream));
+        }
+        const uint64_t before = ctx->launches;
+        uint64_t bytes = 0;
+        MXL_TRY(run_batch(ctx, s.kind, mods.data(), (int)mods.size(), t, ios.data(), &bytes));
+        s.last_launches = (int)(ctx->launches - before);
+        s.last_bytes = bytes;
+        if (g->profiling) MXL_CUDA(cudaEventRecord(s.ev1, ctx->stream));
+    }
+    g->timings_pending = g->profiling;
+    return MXL_OK;
+}
+
+mxl_line* mxl_graph_output(mxl_graph* g, int module_id, uint32_t out_index)
+{
+    if (!g) return nullptr;
+    if (g->dirty && build_plan(g) != MXL_OK) return nullptr;
+    return output_line(g, module_id, out_index);
+}
+
+int mxl_graph_set_profiling(mxl_graph* g, int enabled)
+{
+    if (!g) MXL_FAIL(MXL_ERR_INVALID, "NULL graph");
+    g->profiling = enabled != 0;
+    return MXL_OK;
+}
+
+int mxl_graph_stage_count(mxl_graph* g)
+{
+    if (!g) MXL_FAIL(MXL_ERR_INVALID, "NULL graph");
+    if (g->dirty) MXL_TRY(build_plan(g));
+    return (int)g->stages.size();
+}
+
+int mxl_graph_stage_info(mxl_graph* g, uint32_t stage, mxl_stage_info* out)
+{
+    if (!g || !out) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
+    if (g->dirty) MXL_TRY(build_plan(g));
+    if (stage >= g->stages.size()) MXL_FAIL(MXL_ERR_INVALID, "stage %u out of %zu", stage, g->stages.size());
+    collect_timings(g);
+    const Stage& s = g->stages[stage];
+    out->kind = s.kind;
+    out->n_modules = (int32_t)s.modules.size();
+    out->n_launches = s.last_launches;
+    out->last_ms = s.last_ms;
+    out->algorithmic_bytes = s.last_bytes;
+    return MXL_OK;
+}
+
+}  // extern "C"

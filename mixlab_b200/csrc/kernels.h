@@ -1,0 +1,133 @@
+// kernels.h -- launch-parameter structs and launchers of the sm_100a kernels.
+//
+// Every kernel serves a BATCH of module instances of one kind (blockIdx.y = instance): the graph
+// executor issues one launch per (dependency level, kind) instead of one per module, and the
+// single-module ABI path is the same launch with n = 1.  Instance tables travel as
+// __grid_constant__ kernel parameters: they are snapshotted at launch, so the host may rewrite
+// its copy immediately, and they are read through the constant bank as warp-uniform loads.
+#pragma once
+
+#include "common.h"
+
+namespace mxl {
+namespace k {
+
+constexpr int kMaxBatch = 32;        // instances per launch (keeps every table under 4 KB)
+constexpr int kMixerMaxCh = 160;     // channels per mixer launch (more => accumulate passes)
+
+// ---- Oscillator (src/module/oscillator.rs:65-92) ----
+struct OscInst { float* mono; float* stereo; double freq; int32_t waveform; int32_t _pad; };
+struct OscBatch {
+    uint64_t t0, frames;
+    double sample_rate, inv_sample_rate;
+    int32_t n, _pad;
+    OscInst inst[kMaxBatch];
+};
+int launch_oscillator(mxl_ctx* ctx, const OscBatch& b);
+
+// ---- FmSine (src/module/fm_sine.rs:37-56) ----
+struct FmInst { const float* in; float* out; double freq_mid, freq_amp; };
+struct FmBatch {
+    uint64_t t0, frames;
+    double sample_rate, inv_sample_rate;
+    int32_t n, _pad;
+    FmInst inst[kMaxBatch];
+};
+int launch_fm_sine(mxl_ctx* ctx, const FmBatch& b);
+
+// ---- Mixer (src/module/mixer.rs:46-71): one instance per launch, channel table inline ----
+struct MixChan { const float* in; double gain; int32_t cue; int32_t _pad; };
+struct MixerLaunch {
+    float* master; float* cue;
+    uint64_t len;                 // f32 per line (2*frames)
+    int32_t channels;
+    int32_t accumulate;           // continue a previous pass (channel counts above kMixerMaxCh)
+    MixChan ch[kMixerMaxCh];
+};
+int launch_mixer(mxl_ctx* ctx, const MixerLaunch& p);
+
+// ---- Amplifier (src/module/amplifier.rs:38-73) ----
+struct AmpInst { const float* in; const float* mod; float* out; double amplitude, mod_depth; };
+struct AmpBatch { uint64_t frames; int32_t n, _pad; AmpInst inst[kMaxBatch]; };
+int launch_amplifier(mxl_ctx* ctx, const AmpBatch& b);
+
+// ---- StereoPanner / StereoSplitter / Trigger ----
+struct PanInst { const float* left; const float* right; float* out; };
+struct PanBatch { uint64_t frames; int32_t n, _pad; PanInst inst[kMaxBatch]; };
+int launch_panner(mxl_ctx* ctx, const PanBatch& b);
+struct SplitInst { const float* in; float* left; float* right; };
+struct SplitBatch { uint64_t frames; int32_t n, _pad; SplitInst inst[kMaxBatch]; };
+int launch_splitter(mxl_ctx* ctx, const SplitBatch& b);
+struct FillInst { float* out; float value; int32_t _pad; };
+struct FillBatch { uint64_t len; int32_t n, _pad; FillInst inst[kMaxBatch]; };
+int launch_fill(mxl_ctx* ctx, const FillBatch& b);
+
+// ---- EqThree (src/module/eq_three.rs:58-89,106-125) ----
+constexpr int kEqMaxCarry = 8;       // J: previous chunks whose end states are summed into a start state
+struct EqInst {
+    const float* in; float* out;
+    const double* state;             // device: lo poles[4], hi poles[4], history[3] before the call
+    double* state_out;               // same layout, after the call (other half of a double buffer)
+    double* zend;                    // device scratch: per chunk 8 doubles (zero-state end poles)
+    double g_lo, g_mid, g_hi;
+};
+struct EqBatch {
+    uint64_t frames;
+    uint32_t chunk;                  // Lc samples per chunk
+    uint32_t n_chunks;
+    uint32_t carry_terms;            // J <= kEqMaxCarry
+    int32_t n;
+    double c_lo, c_hi;               // LowPass.freq (eq_three.rs:117-119)
+    // lower-triangular powers A^j = M^(j*Lc) of the homogeneous 4-pole step, row-major packed
+    // (10 entries each), j = 0..J, for the lo and hi filters
+    double pow_lo[kEqMaxCarry + 1][10];
+    double pow_hi[kEqMaxCarry + 1][10];
+    EqInst inst[kMaxBatch];
+};
+int launch_eq_three(mxl_ctx* ctx, const EqBatch& b);
+
+// ---- Envelope (src/module/envelope.rs:91-120) ----
+struct EnvState { int32_t state; int32_t _pad; uint64_t seq; double off_amplitude; };
+struct EnvLaunch {
+    const float* in; float* out;
+    EnvState* state;                 // device, persistent
+    EnvState* state_next;            // device staging for the state after the call
+    uint32_t* scratch_a; uint32_t* scratch_b; uint32_t* block_a; uint32_t* block_b;
+    uint64_t t0; uint32_t frames; uint32_t _pad;
+    double sample_rate;
+    double attack_ms, decay_ms, sustain, release_ms;
+};
+int launch_envelope(mxl_ctx* ctx, const EnvLaunch& p);
+uint32_t envelope_blocks(uint32_t frames);
+
+// ---- Meter (new): one record per tick slot ----
+struct MeterRecord { float peak[2]; int32_t clip; int32_t _pad; double sumsq[2]; };
+struct MeterInst { const float* in; MeterRecord* out; };
+struct MeterBatch { uint64_t frames; uint32_t spt; int32_t n; MeterInst inst[kMaxBatch]; };
+int launch_meter(mxl_ctx* ctx, const MeterBatch& b, uint32_t n_slots);
+
+// ---- PCM (src/video/encode.rs:184-195 ; src/module/stream_input.rs:167-173) ----
+int launch_pcm_pack(mxl_ctx* ctx, const float* in, int16_t* out, uint64_t len);
+int launch_pcm_unpack(mxl_ctx* ctx, const int16_t* in, float* out, uint64_t len);
+
+// ---- Video ----
+struct FadeJob {                     // one output frame
+    const uint8_t* a; const uint8_t* b;   // nullptr = layer missing (blank), video_mixer.rs:180-188
+    uint8_t* out;
+    uint32_t fade; uint32_t _pad;
+};
+// All jobs share one layout.  jobs_dev is a device array of n_jobs FadeJob.
+int launch_crossfade(mxl_ctx* ctx, const mxl_frame_layout& lay, const FadeJob* jobs_dev, uint32_t n_jobs);
+int launch_blank(mxl_ctx* ctx, const mxl_frame_layout& lay, uint8_t* frame);
+int launch_yuv_to_rgba(mxl_ctx* ctx, const mxl_frame_layout& lay, const uint8_t* yuv, uint8_t* rgba);
+// 4-tap separable resample of one plane with host-built 14-bit tables (device pointers)
+int launch_resample_h(mxl_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, uint32_t sstride,
+                      uint8_t* dst, uint32_t dw, uint32_t dstride, const int32_t* pos, const int16_t* coef);
+int launch_resample_v(mxl_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, uint32_t sstride,
+                      uint8_t* dst, uint32_t dh, uint32_t dstride, const int32_t* pos, const int16_t* coef);
+
+// L2 flush helper
+int launch_fill_bytes(mxl_ctx* ctx, void* dst, size_t bytes, uint8_t value);
+
+}  // namespace k
+}  // namespace mxl

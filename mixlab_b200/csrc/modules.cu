@@ -1,0 +1,1155 @@
+// modules.cu -- host side of the modules (see modules.h).
+#include "modules.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+namespace mxl {
+
+// protocol/src/lib.rs:469-471  Decibel::to_linear
+static double db_to_linear(double db) { return pow(10.0, db / 20.0); }
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(mxl_ctx* ctx, size_t bytes)
+    {
+        if (bytes <= cap) return MXL_OK;
+        MXL_TRY(ctx->activate());
+        if (p) { MXL_CUDA(cudaFree(p)); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 4;
+        MXL_CUDA(cudaMalloc(&p, want));
+        cap = want;
+        return MXL_OK;
+    }
+    void release(mxl_ctx* ctx)
+    {
+        if (p) { if (ctx && ctx->has_device()) ctx->activate(); cudaFree(p); p = nullptr; cap = 0; }
+    }
+};
+
+static uint64_t line_bytes(const mxl_line* l) { return l ? l->len() * sizeof(float) : 0; }
+
+// ================================================================================================
+// module classes
+// ================================================================================================
+
+struct Amplifier : mxl_module {                       // src/module/amplifier.rs
+    mxl_amplifier_params p{};
+    Amplifier(const mxl_amplifier_params* in)
+    {
+        kind = MXL_MOD_AMPLIFIER;
+        if (in) p = *in;
+        inputs = {labeled(MXL_LINE_STEREO, "Input"), labeled(MXL_LINE_MONO, "Control")};   // amplifier.rs:21-24
+        outputs = {unlabeled(MXL_LINE_STEREO)};
+    }
+    int update(const void* np) override { p = *(const mxl_amplifier_params*)np; return MXL_OK; }
+    int get_params(void* out) const override { *(mxl_amplifier_params*)out = p; return MXL_OK; }
+};
+
+struct Envelope : mxl_module {                        // src/module/envelope.rs
+    mxl_envelope_params p{25.0, 500.0, 0.8, 200.0};   // protocol lib.rs:318-327
+    DevBuf state, scratch;
+    bool state_init = false;
+    Envelope(const mxl_envelope_params* in)
+    {
+        kind = MXL_MOD_ENVELOPE;
+        if (in) p = *in;
+        inputs = {unlabeled(MXL_LINE_MONO)};
+        outputs = {unlabeled(MXL_LINE_MONO)};
+    }
+    ~Envelope() override { state.release(ctx); scratch.release(ctx); }
+    int update(const void* np) override { p = *(const mxl_envelope_params*)np; return MXL_OK; }
+    int get_params(void* out) const override { *(mxl_envelope_params*)out = p; return MXL_OK; }
+    int ensure_state()
+    {
+        if (state_init) return MXL_OK;
+        MXL_TRY(state.ensure(ctx, 2 * sizeof(k::EnvState)));
+        MXL_CUDA(cudaMemsetAsync(state.p, 0, 2 * sizeof(k::EnvState), ctx->stream));   // EnvelopeState::Initial
+        state_init = true;
+        return MXL_OK;
+    }
+};
+
+struct EqThree : mxl_module {                         // src/module/eq_three.rs
+    mxl_eq_three_params p{};
+    DevBuf state, zend;
+    bool state_init = false;
+    int cur = 0;                                      // which half of the state double buffer is current
+    EqThree(const mxl_eq_three_params* in)
+    {
+        kind = MXL_MOD_EQ_THREE;
+        if (in) p = *in;
+        inputs = {unlabeled(MXL_LINE_MONO)};
+        outputs = {unlabeled(MXL_LINE_MONO)};
+    }
+    ~EqThree() override { state.release(ctx); zend.release(ctx); }
+    int update(const void* np) override { p = *(const mxl_eq_three_params*)np; return MXL_OK; }   // state survives (eq_three.rs:53-56)
+    int get_params(void* out) const override { *(mxl_eq_three_params*)out = p; return MXL_OK; }
+    int ensure_state()
+    {
+        if (state_init) return MXL_OK;
+        MXL_TRY(state.ensure(ctx, 2 * 11 * sizeof(double)));
+        MXL_CUDA(cudaMemsetAsync(state.p, 0, 2 * 11 * sizeof(double), ctx->stream));   // poles, history = 0 (eq_three.rs:34-40,113)
+        state_init = true;
+        return MXL_OK;
+    }
+    double* state_ptr(int which) { return (double*)state.p + 11 * which; }
+};
+
+struct FmSine : mxl_module {                          // src/module/fm_sine.rs
+    mxl_fm_sine_params p{};
+    FmSine(const mxl_fm_sine_params* in)
+    {
+        kind = MXL_MOD_FM_SINE;
+        if (in) p = *in;
+        inputs = {unlabeled(MXL_LINE_MONO)};
+        outputs = {unlabeled(MXL_LINE_STEREO)};
+    }
+    int update(const void* np) override { p = *(const mxl_fm_sine_params*)np; return MXL_OK; }
+    int get_params(void* out) const override { *(mxl_fm_sine_params*)out = p; return MXL_OK; }
+};
+
+struct Mixer : mxl_module {                           // src/module/mixer.rs
+    std::vector<mxl_mixer_channel_params> channels;
+    Mixer(const mxl_mixer_params* in)
+    {
+        kind = MXL_MOD_MIXER;
+        set(in);
+    }
+    void set(const mxl_mixer_params* in)
+    {
+        channels.clear();
+        if (in && in->channels) channels.assign(in->channels, in->channels + in->n_channels);
+        inputs.clear();
+        for (size_t i = 0; i < channels.size(); i++) inputs.push_back(labeled(MXL_LINE_STEREO, std::to_string(i + 1)));   // mixer.rs:23-25
+        outputs = {labeled(MXL_LINE_STEREO, "Master"), labeled(MXL_LINE_STEREO, "Cue")};                                  // mixer.rs:26-29
+    }
+    int update(const void* np) override { set((const mxl_mixer_params*)np); return MXL_OK; }   // mixer.rs:40-44 re-creates
+    int get_params(void* out) const override
+    {
+        mxl_mixer_params* o = (mxl_mixer_params*)out;
+        o->channels = channels.data();
+        o->n_channels = (uint32_t)channels.size();
+        return MXL_OK;
+    }
+};
+
+struct Oscillator : mxl_module {                      // src/module/oscillator.rs
+    mxl_oscillator_params p{100.0, MXL_WAVE_SINE, 0};
+    Oscillator(const mxl_oscillator_params* in)
+    {
+        kind = MXL_MOD_OSCILLATOR;
+        if (in) p = *in;
+        outputs = {labeled(MXL_LINE_MONO, "Mono"), labeled(MXL_LINE_STEREO, "Stereo")};   // oscillator.rs:48-51
+    }
+    int update(const void* np) override { p = *(const mxl_oscillator_params*)np; return MXL_OK; }
+    int get_params(void* out) const override { *(mxl_oscillator_params*)out = p; return MXL_OK; }
+};
+
+struct Plotter : mxl_module {                         // src/module/plotter.rs
+    uint64_t count = 0;
+    DevBuf tap;                                       // left[S] then right[S]
+    uint32_t tap_frames = 0;
+    Plotter()
+    {
+        kind = MXL_MOD_PLOTTER;
+        inputs = {unlabeled(MXL_LINE_STEREO)};
+    }
+    ~Plotter() override { tap.release(ctx); }
+    int update(const void*) override { return MXL_OK; }
+    int get_params(void*) const override { return MXL_OK; }
+};
+
+struct StereoPanner : mxl_module {                    // src/module/stereo_panner.rs
+    StereoPanner()
+    {
+        kind = MXL_MOD_STEREO_PANNER;
+        inputs = {labeled(MXL_LINE_MONO, "L"), labeled(MXL_LINE_MONO, "R")};
+        outputs = {unlabeled(MXL_LINE_STEREO)};
+    }
+    int update(const void*) override { return MXL_OK; }
+    int get_params(void*) const override { return MXL_OK; }
+};
+
+struct StereoSplitter : mxl_module {                  // src/module/stereo_splitter.rs
+    StereoSplitter()
+    {
+        kind = MXL_MOD_STEREO_SPLITTER;
+        inputs = {unlabeled(MXL_LINE_STEREO)};
+        outputs = {labeled(MXL_LINE_MONO, "L"), labeled(MXL_LINE_MONO, "R")};
+    }
+    int update(const void*) override { return MXL_OK; }
+    int get_params(void*) const override { return MXL_OK; }
+};
+
+struct Trigger : mxl_module {                         // src/module/trigger.rs
+    mxl_trigger_params p{MXL_GATE_CLOSED};
+    Trigger(const mxl_trigger_params* in)
+    {
+        kind = MXL_MOD_TRIGGER;
+        if (in) p = *in;
+        outputs = {unlabeled(MXL_LINE_MONO)};
+    }
+    int update(const void* np) override { p = *(const mxl_trigger_params*)np; return MXL_OK; }
+    int get_params(void* out) const override { *(mxl_trigger_params*)out = p; return MXL_OK; }
+};
+
+struct Meter : mxl_module {                           // new
+    DevBuf records;
+    uint32_t n_slots = 0;
+    Meter()
+    {
+        kind = MXL_MOD_METER;
+        inputs = {unlabeled(MXL_LINE_STEREO)};
+    }
+    ~Meter() override { records.release(ctx); }
+    int update(const void*) override { return MXL_OK; }
+    int get_params(void*) const override { return MXL_OK; }
+};
+
+struct Source : mxl_module {                          // new: host-fed line (stands in for StreamInput's output)
+    mxl_line* line = nullptr;                         // borrowed
+    Source(int k, int type)
+    {
+        kind = k;
+        outputs = {unlabeled(type)};
+    }
+    int update(const void*) override { return MXL_OK; }
+    int get_params(void*) const override { return MXL_OK; }
+};
+
+struct PcmSink : mxl_module {                         // new: f32 -> i16 pack (src/video/encode.rs:184-195)
+    DevBuf pcm;
+    uint64_t n_samples = 0;
+    PcmSink()
+    {
+        kind = MXL_MOD_PCM_SINK;
+        inputs = {unlabeled(MXL_LINE_STEREO)};
+    }
+    ~PcmSink() override { pcm.release(ctx); }
+    int update(const void*) override { return MXL_OK; }
+    int get_params(void*) const override { return MXL_OK; }
+};
+
+// ---- VideoMixer: src/module/video_mixer.rs ---------------------------------------------------------
+struct PictureSettings { uint32_t w = 0, h = 0; bool operator==(const PictureSettings& o) const { return w == o.w && h == o.h; } bool operator!=(const PictureSettings& o) const { return !(*this == o); } };
+
+struct VideoMixer : mxl_module {
+    mxl_video_mixer_params p{-1, -1, 1.0};            // protocol lib.rs:412-420
+    struct Channel {
+        bool has_stored = false;
+        Rational active_until;
+        mxl_frame* frame = nullptr;                   // retained; scaled to the scaler's output
+        bool has_scaler = false;
+        PictureSettings scaler_out;
+    } ch[MXL_VIDEO_MIXER_CHANNELS];
+    DevBuf jobs;
+    VideoMixer(const mxl_video_mixer_params* in)
+    {
+        kind = MXL_MOD_VIDEO_MIXER;
+        if (in) p = *in;
+        for (int i = 0; i < MXL_VIDEO_MIXER_CHANNELS; i++) inputs.push_back(labeled(MXL_LINE_VIDEO, std::to_string(i + 1)));   // video_mixer.rs:29-31
+        outputs = {labeled(MXL_LINE_VIDEO, "Output"), labeled(MXL_LINE_VIDEO, "A"), labeled(MXL_LINE_VIDEO, "B")};            // video_mixer.rs:32-36
+    }
+    ~VideoMixer() override
+    {
+        for (auto& c : ch) frame_release(c.frame);
+        jobs.release(ctx);
+    }
+    int update(const void* np) override { p = *(const mxl_video_mixer_params*)np; return MXL_OK; }
+    int get_params(void* out) const override { *(mxl_video_mixer_params*)out = p; return MXL_OK; }
+    void clear_stored(Channel& c) { frame_release(c.frame); c.frame = nullptr; c.has_stored = false; }
+    int rescale(Channel& c, const PictureSettings& target);
+    int run(uint64_t t0, const IoSet& io, uint64_t* bytes);
+};
+
+}  // namespace mxl
+
+const char* mxl_module::kind_name() const
+{
+    switch (kind) {
+    case MXL_MOD_AMPLIFIER: return "Amplifier";
+    case MXL_MOD_ENVELOPE: return "Envelope";
+    case MXL_MOD_EQ_THREE: return "EqThree";
+    case MXL_MOD_FM_SINE: return "FmSine";
+    case MXL_MOD_MIXER: return "Mixer";
+    case MXL_MOD_OSCILLATOR: return "Oscillator";
+    case MXL_MOD_PLOTTER: return "Plotter";
+    case MXL_MOD_STEREO_PANNER: return "StereoPanner";
+    case MXL_MOD_STEREO_SPLITTER: return "StereoSplitter";
+    case MXL_MOD_TRIGGER: return "Trigger";
+    case MXL_MOD_VIDEO_MIXER: return "VideoMixer";
+    case MXL_MOD_METER: return "Meter";
+    case MXL_MOD_SOURCE_MONO: return "SourceMono";
+    case MXL_MOD_SOURCE_STEREO: return "SourceStereo";
+    case MXL_MOD_SOURCE_VIDEO: return "SourceVideo";
+    case MXL_MOD_PCM_SINK: return "PcmSink";
+    default: return "?";
+    }
+}
+
+namespace mxl {
+
+mxl_module* module_create(mxl_ctx* ctx, int kind, const void* params)
+{
+    if (!ctx) { set_error("mxl_module_create: NULL context"); return nullptr; }
+    mxl_module* m = nullptr;
+    switch (kind) {
+    case MXL_MOD_AMPLIFIER: m = new Amplifier((const mxl_amplifier_params*)params); break;
+    case MXL_MOD_ENVELOPE: m = new Envelope((const mxl_envelope_params*)params); break;
+    case MXL_MOD_EQ_THREE: m = new EqThree((const mxl_eq_three_params*)params); break;
+    case MXL_MOD_FM_SINE: m = new FmSine((const mxl_fm_sine_params*)params); break;
+    case MXL_MOD_MIXER: m = new Mixer((const mxl_mixer_params*)params); break;
+    case MXL_MOD_OSCILLATOR: m = new Oscillator((const mxl_oscillator_params*)params); break;
+    case MXL_MOD_PLOTTER: m = new Plotter(); break;
+    case MXL_MOD_STEREO_PANNER: m = new StereoPanner(); break;
+    case MXL_MOD_STEREO_SPLITTER: m = new StereoSplitter(); break;
+    case MXL_MOD_TRIGGER: m = new Trigger((const mxl_trigger_params*)params); break;
+    case MXL_MOD_VIDEO_MIXER: m = new VideoMixer((const mxl_video_mixer_params*)params); break;
+    case MXL_MOD_METER: m = new Meter(); break;
+    case MXL_MOD_SOURCE_MONO: m = new Source(kind, MXL_LINE_MONO); break;
+    case MXL_MOD_SOURCE_STEREO: m = new Source(kind, MXL_LINE_STEREO); break;
+    case MXL_MOD_SOURCE_VIDEO: m = new Source(kind, MXL_LINE_VIDEO); break;
+    case MXL_MOD_PCM_SINK: m = new PcmSink(); break;
+    case MXL_MOD_MONITOR: case MXL_MOD_OUTPUT_DEVICE: case MXL_MOD_STREAM_INPUT:
+    case MXL_MOD_STREAM_OUTPUT: case MXL_MOD_MEDIA_SOURCE:
+        set_error("module kind %d is an I/O edge that stays in the host application (out of scope of the tick hot path)", kind);
+        return nullptr;
+    default:
+        set_error("unknown module kind %d", kind);
+        return nullptr;
+    }
+    m->ctx = ctx;
+    return m;
+}
+
+// ================================================================================================
+// batched dispatch
+// ================================================================================================
+
+#define NEED_IO(io, nin, nout, name)                                                                     \
+    do {                                                                                                 \
+        if ((io).n_in != (nin) || (io).n_out != (nout))                                                  \
+            MXL_FAIL(MXL_ERR_INVALID, "%s: expected %u inputs / %u outputs, got %u / %u", name, (unsigned)(nin), (unsigned)(nout), (io).n_in, (io).n_out); \
+    } while (0)
+
+static int need_len(const mxl_line* l, uint64_t floats, const char* what)
+{
+    if (l && l->len() < floats)
+        MXL_FAIL(MXL_ERR_LENGTH, "%s: line holds %llu samples, the call needs %llu", what, (unsigned long long)l->len(), (unsigned long long)floats);
+    return MXL_OK;
+}
+
+// --- Oscillator ---
+static int run_oscillators(mxl_ctx* ctx, mxl_module* const* mods, int n, uint64_t t, const IoSet* io, uint64_t* bytes)
+{
+    int i = 0;
+    while (i < n) {
+        k::OscBatch b{};
+        b.t0 = t; b.sample_rate = (double)ctx->sample_rate; b.inv_sample_rate = 1.0 / b.sample_rate;
+        uint64_t frames = 0;
+        int cnt = 0;
+        for (; i < n && cnt < k::kMaxBatch; i++) {
+            NEED_IO(io[i], 0, 2, "Oscillator");
+            MXL_TRY(expect_output(io[i].out[0], MXL_LINE_MONO, "Oscillator.Mono"));
+            MXL_TRY(expect_output(io[i].out[1], MXL_LINE_STEREO, "Oscillator.Stereo"));
+            const uint64_t f = io[i].out[0]->frames;                      // let len = mono.len()  (oscillator.rs:71)
+            MXL_TRY(need_len(io[i].out[1], 2 * f, "Oscillator.Stereo"));
+            if (cnt && f != frames) break;
+            frames = f;
+            const Oscillator* o = (const Oscillator*)mods[i];
+            b.inst[cnt++] = k::OscInst{io[i].out[0]->dev, io[i].out[1]->dev, o->p.freq, o->p.waveform, 0};
+            if (bytes) *bytes += 12 * f;
+        }
+        b.frames = frames; b.n = cnt;
+        MXL_TRY(k::launch_oscillator(ctx, b));
+    }
+    return MXL_OK;
+}
+
+// --- FmSine ---
+static int run_fm_sines(mxl_ctx* ctx, mxl_module* const* mods, int n, uint64_t t, const IoSet* io, uint64_t* bytes)
+{
+    int i = 0;
+    while (i < n) {
+        k::FmBatch b{};
+        b.t0 = t; b.sample_rate = (double)ctx->sample_rate; b.inv_sample_rate = 1.0 / b.sample_rate;
+        uint64_t frames = 0;
+        int cnt = 0;
+        for (; i < n && cnt < k::kMaxBatch; i++) {
+            NEED_IO(io[i], 1, 1, "FmSine");
+            MXL_TRY(expect_input(io[i].in[0], MXL_LINE_MONO, "FmSine"));
+            MXL_TRY(expect_output(io[i].out[0], MXL_LINE_STEREO, "FmSine"));
+            const uint64_t f = io[i].out[0]->frames;                      // len = output.len() / CHANNELS (fm_sine.rs:40)
+            MXL_TRY(need_len(io[i].in[0], f, "FmSine input"));
+            if (cnt && f != frames) break;
+            frames = f;
+            const FmSine* m = (const FmSine*)mods[i];
+            const double freq_amp = (m->p.freq_hi - m->p.freq_lo) / 2.0;   // fm_sine.rs:42-43
+            const double freq_mid = m->p.freq_lo + freq_amp;
+            b.inst[cnt++] = k::FmInst{io[i].in[0] ? io[i].in[0]->dev : nullptr, io[i].out[0]->dev, freq_mid, freq_amp};
+            if (bytes) *bytes += (io[i].in[0] ? 4 * f : 0) + 8 * f;
+        }
+        b.frames = frames; b.n = cnt;
+        MXL_TRY(k::launch_fm_sine(ctx, b));
+    }
+    return MXL_OK;
+}
+
+// --- Mixer ---
+static int run_mixers(mxl_ctx* ctx, mxl_module* const* mods, int n, const IoSet* io, uint64_t* bytes)
+{
+    for (int i = 0; i < n; i++) {
+        const Mixer* m = (const Mixer*)mods[i];
+        const uint32_t C = (uint32_t)m->channels.size();
+        NEED_IO(io[i], C, 2, "Mixer");
+        MXL_TRY(expect_output(io[i].out[0], MXL_LINE_STEREO, "Mixer.Master"));
+        MXL_TRY(expect_output(io[i].out[1], MXL_LINE_STEREO, "Mixer.Cue"));
+        const uint64_t len = io[i].out[0]->len();                         // let len = master.len()  (mixer.rs:52)
+        MXL_TRY(need_len(io[i].out[1], len, "Mixer.Cue"));
+        for (uint32_t c = 0; c < C; c++) {
+            MXL_TRY(expect_input(io[i].in[c], MXL_LINE_STEREO, "Mixer input"));
+            MXL_TRY(need_len(io[i].in[c], len, "Mixer input"));
+        }
+        uint32_t done = 0;
+        do {
+            k::MixerLaunch p{};
+            p.master = io[i].out[0]->dev; p.cue = io[i].out[1]->dev; p.len = len;
+            p.accumulate = done > 0;
+            const uint32_t take = std::min<uint32_t>(C - done, k::kMixerMaxCh);
+            for (uint32_t c = 0; c < take; c++) {
+                const mxl_mixer_channel_params& cp = m->channels[done + c];
+                p.ch[c].in = io[i].in[done + c] ? io[i].in[done + c]->dev : nullptr;
+                p.ch[c].gain = cp.fader * db_to_linear(cp.gain_db);       // mixer.rs:59
+                p.ch[c].cue = cp.cue ? 1 : 0;
+                if (bytes && io[i].in[done + c]) *bytes += 4 * len;
+            }
+            p.channels = (int32_t)take;
+            MXL_TRY(k::launch_mixer(ctx, p));
+            done += take;
+        } while (done < C);
+        if (bytes) *bytes += 8 * len;
+    }
+    return MXL_OK;
+}
+
+// --- Amplifier ---
+static int run_amplifiers(mxl_ctx* ctx, mxl_module* const* mods, int n, const IoSet* io, uint64_t* bytes)
+{
+    int i = 0;
+    while (i < n) {
+        k::AmpBatch b{};
+        uint64_t frames = 0;
+        int cnt = 0;
+        for (; i < n && cnt < k::kMaxBatch; i++) {
+            NEED_IO(io[i], 2, 1, "Amplifier");
+            MXL_TRY(expect_input(io[i].in[0], MXL_LINE_STEREO, "Amplifier.Input"));
+            MXL_TRY(expect_input(io[i].in[1], MXL_LINE_MONO, "Amplifier.Control"));
+            MXL_TRY(expect_output(io[i].out[0], MXL_LINE_STEREO, "Amplifier"));
+            // let len = input.len() (amplifier.rs:50); a disconnected input is the engine's zero buffer,
+            // which has the length of the tick's lines
+            const uint64_t f = io[i].in[0] ? io[i].in[0]->frames : io[i].out[0]->frames;
+            MXL_TRY(need_len(io[i].out[0], 2 * f, "Amplifier output"));
+            MXL_TRY(need_len(io[i].in[1], f, "Amplifier.Control"));
+            if (cnt && f != frames) break;
+            frames = f;
+            const Amplifier* m = (const Amplifier*)mods[i];
+            b.inst[cnt++] = k::AmpInst{io[i].in[0] ? io[i].in[0]->dev : nullptr, io[i].in[1] ? io[i].in[1]->dev : nullptr,
+                                       io[i].out[0]->dev, m->p.amplitude, m->p.mod_depth};
+            if (bytes) *bytes += (io[i].in[0] ? 8 * f : 0) + (io[i].in[1] ? 4 * f : 0) + 8 * f;
+        }
+        b.frames = frames; b.n = cnt;
+        MXL_TRY(k::launch_amplifier(ctx, b));
+    }
+    return MXL_OK;
+}
+
+// --- StereoPanner / StereoSplitter / Trigger ---
+static int run_panners(mxl_ctx* ctx, int n, const IoSet* io, uint64_t* bytes)
+{
+    int i = 0;
+    while (i < n) {
+        k::PanBatch b{};
+        uint64_t frames = 0;
+        int cnt = 0;
+        for (; i < n && cnt < k::kMaxBatch; i++) {
+            NEED_IO(io[i], 2, 1, "StereoPanner");
+            MXL_TRY(expect_input(io[i].in[0], MXL_LINE_MONO, "StereoPanner.L"));
+            MXL_TRY(expect_input(io[i].in[1], MXL_LINE_MONO, "StereoPanner.R"));
+            MXL_TRY(expect_output(io[i].out[0], MXL_LINE_STEREO, "StereoPanner"));
+            const uint64_t f = io[i].in[0] ? io[i].in[0]->frames : io[i].out[0]->frames;   // 0..left.len() (stereo_panner.rs:35)
+            MXL_TRY(need_len(io[i].in[1], f, "StereoPanner.R"));
+            MXL_TRY(need_len(io[i].out[0], 2 * f, "StereoPanner output"));
+            if (cnt && f != frames) break;
+            frames = f;
+            b.inst[cnt++] = k::PanInst{io[i].in[0] ? io[i].in[0]->dev : nullptr, io[i].in[1] ? io[i].in[1]->dev : nullptr, io[i].out[0]->dev};
+            if (bytes) *bytes += (io[i].in[0] ? 4 * f : 0) + (io[i].in[1] ? 4 * f : 0) + 8 * f;
+        }
+        b.frames = frames; b.n = cnt;
+        MXL_TRY(k::launch_panner(ctx, b));
+    }
+    return MXL_OK;
+}
+
+static int run_splitters(mxl_ctx* ctx, int n, const IoSet* io, uint64_t* bytes)
+{
+    int i = 0;
+    while (i < n) {
+        k::SplitBatch b{};
+        uint64_t frames = 0;
+        int cnt = 0;
+        for (; i < n && cnt < k::kMaxBatch; i++) {
+            NEED_IO(io[i], 1, 2, "StereoSplitter");
+            MXL_TRY(expect_input(io[i].in[0], MXL_LINE_STEREO, "StereoSplitter"));
+            MXL_TRY(expect_output(io[i].out[0], MXL_LINE_MONO, "StereoSplitter.L"));
+            MXL_TRY(expect_output(io[i].out[1], MXL_LINE_MONO, "StereoSplitter.R"));
+            const uint64_t f = io[i].out[0]->frames;                      // 0..left.len() (stereo_splitter.rs:41)
+            MXL_TRY(need_len(io[i].out[1], f, "StereoSplitter.R"));
+            MXL_TRY(need_len(io[i].in[0], 2 * f, "StereoSplitter input"));
+            if (cnt && f != frames) break;
+            frames = f;
+            b.inst[cnt++] = k::SplitInst{io[i].in[0] ? io[i].in[0]->dev : nullptr, io[i].out[0]->dev, io[i].out[1]->dev};
+            if (bytes) *bytes += (io[i].in[0] ? 8 * f : 0) + 8 * f;
+        }
+        b.frames = frames; b.n = cnt;
+        MXL_TRY(k::launch_splitter(ctx, b));
+    }
+    return MXL_OK;
+}
+
+static int run_triggers(mxl_ctx* ctx, mxl_module* const* mods, int n, const IoSet* io, uint64_t* bytes)
+{
+    int i = 0;
+    while (i < n) {
+        k::FillBatch b{};
+        uint64_t len = 0;
+        int cnt = 0;
+        for (; i < n && cnt < k::kMaxBatch; i++) {
+            NEED_IO(io[i], 0, 1, "Trigger");
+            MXL_TRY(expect_output(io[i].out[0], MXL_LINE_MONO, "Trigger"));
+            const uint64_t f = io[i].out[0]->frames;
+            if (cnt && f != len) break;
+            len = f;
+            const Trigger* m = (const Trigger*)mods[i];
+            b.inst[cnt++] = k::FillInst{io[i].out[0]->dev, m->p.gate == MXL_GATE_OPEN ? 1.0f : 0.0f, 0};   // trigger.rs:38-41
+            if (bytes) *bytes += 4 * f;
+        }
+        b.len = len; b.n = cnt;
+        MXL_TRY(k::launch_fill(ctx, b));
+    }
+    return MXL_OK;
+}
+
+// --- EqThree ---
+// Homogeneous Lc-sample transition A = M^Lc of one 4-pole cascade and its powers A^0..A^J, packed
+// lower-triangular (10 doubles each).  Plan layout: [J, pow_lo[(J+1)*10], pow_hi[(J+1)*10]].
+static void cascade_power(double c, uint32_t steps, double A[4][4])
+{
+    for (int col = 0; col < 4; col++) {
+        double p[4] = {0, 0, 0, 0};
+        p[col] = 1.0;
+        for (uint32_t s = 0; s < steps; s++) {
+            p[0] += c * (0.0 - p[0]);
+            p[1] += c * (p[0] - p[1]);
+            p[2] += c * (p[1] - p[2]);
+            p[3] += c * (p[2] - p[3]);
+        }
+        for (int r = 0; r < 4; r++) A[r][col] = p[r];
+    }
+}
+
+static void matmul4(const double X[4][4], const double Y[4][4], double Z[4][4])
+{
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) {
+            double s = 0;
+            for (int q = 0; q < 4; q++) s += X[r][q] * Y[q][c];
+            Z[r][c] = s;
+        }
+}
+
+static double absmax4(const double X[4][4])
+{
+    double m = 0;
+    for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) m = std::max(m, fabs(X[r][c]));
+    return m;
+}
+
+static void pack_tri(const double X[4][4], double* out)
+{
+    int q = 0;
+    for (int r = 0; r < 4; r++) for (int c = 0; c <= r; c++) out[q++] = X[r][c];
+}
+
+struct EqCoefs { double c_lo, c_hi; };
+static EqCoefs eq_coefs(const mxl_ctx* ctx)
+{
+    // LowPass::set_freq (eq_three.rs:117-119), FREQ_LO = 420, FREQ_HI = 2700 (eq_three.rs:8-9)
+    const double pi = 3.14159265358979323846264338327950288;
+    return EqCoefs{2.0 * sin(pi * 420.0 / (double)ctx->sample_rate), 2.0 * sin(pi * 2700.0 / (double)ctx->sample_rate)};
+}
+
+// Returns the plan for chunk length `chunk`; if the cascade does not forget within kEqMaxCarry
+// chunks of that length (|A^J| >= 2^-75), *chunk is doubled until it does.
+static const std::vector<double>& eq_plan_for(mxl_ctx* ctx, uint32_t* chunk)
+{
+    const EqCoefs co = eq_coefs(ctx);
+    for (;;) {
+        auto it = ctx->eq_plans.find(*chunk);
+        if (it != ctx->eq_plans.end()) {
+            if (!it->second.empty()) return it->second;
+            *chunk *= 2;                      // remembered as "too short"
+            continue;
+        }
+        double Al[4][4], Ah[4][4];
+        cascade_power(co.c_lo, *chunk, Al);
+        cascade_power(co.c_hi, *chunk, Ah);
+        double Pl[k::kEqMaxCarry + 1][4][4], Ph[k::kEqMaxCarry + 1][4][4];
+        memset(Pl, 0, sizeof Pl); memset(Ph, 0, sizeof Ph);
+        for (int d = 0; d < 4; d++) { Pl[0][d][d] = 1.0; Ph[0][d][d] = 1.0; }
+        int J = -1;
+        const double tiny = ldexp(1.0, -75);
+        for (int j = 1; j <= k::kEqMaxCarry; j++) {
+            matmul4(Pl[j - 1], Al, Pl[j]);
+            matmul4(Ph[j - 1], Ah, Ph[j]);
+            if (J < 0 && absmax4(Pl[j]) < tiny && absmax4(Ph[j]) < tiny) J = j;
+        }
+        if (J < 0 && *chunk < (1u << 24)) {
+            ctx->eq_plans[*chunk] = std::vector<double>();
+            *chunk *= 2;
+            continue;
+        }
+        if (J < 0) J = k::kEqMaxCarry;
+        std::vector<double> plan(1 + 2 * (k::kEqMaxCarry + 1) * 10, 0.0);
+        plan[0] = (double)J;
+        for (int j = 0; j <= k::kEqMaxCarry; j++) {
+            pack_tri(Pl[j], &plan[1 + j * 10]);
+            pack_tri(Ph[j], &plan[1 + (k::kEqMaxCarry + 1) * 10 + j * 10]);
+        }
+        return ctx->eq_plans[*chunk] = plan;
+    }
+}
+
+static uint32_t eq_pick_chunk(const mxl_ctx* ctx, uint64_t frames, int n_inst)
+{
+    if (const char* e = getenv("MXL_EQ_CHUNK")) {
+        long v = atol(e);
+        if (v >= 4) return (uint32_t)(v / 4 * 4);
+    }
+    const uint64_t total = frames * (uint64_t)n_inst;
+    const uint64_t target_threads = (uint64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148) * 768;
+    uint64_t want = (total + target_threads - 1) / target_threads;
+    uint32_t chunk = 256;
+    while (chunk < want && chunk < 8192) chunk *= 2;
+    return chunk;
+}
+
+static int run_eq_threes(mxl_ctx* ctx, mxl_module* const* mods, int n, const IoSet* io, uint64_t* bytes)
+{
+    int i = 0;
+    while (i < n) {
+        // gather a batch of equal length
+        int first = i, cnt = 0;
+        uint64_t frames = 0;
+        for (; i < n && cnt < k::kMaxBatch; i++, cnt++) {
+            NEED_IO(io[i], 1, 1, "EqThree");
+            MXL_TRY(expect_input(io[i].in[0], MXL_LINE_MONO, "EqThree"));
+            MXL_TRY(expect_output(io[i].out[0], MXL_LINE_MONO, "EqThree"));
+            // input.iter().zip(output.iter_mut()) (eq_three.rs:66): the shorter of the two
+            uint64_t f = io[i].out[0]->frames;
+            if (io[i].in[0] && io[i].in[0]->frames < f) f = io[i].in[0]->frames;
+            if (cnt && f != frames) break;
+            frames = f;
+        }
+        if (frames == 0) continue;
+        if (frames >= (1ull << 40)) MXL_FAIL(MXL_ERR_LENGTH, "EqThree: call too long");
+        uint32_t chunk = eq_pick_chunk(ctx, frames, cnt);
+        const std::vector<double>& plan = eq_plan_for(ctx, &chunk);
+        k::EqBatch b{};
+        b.frames = frames;
+        b.chunk = chunk;
+        b.n_chunks = (uint32_t)((frames + chunk - 1) / chunk);
+        b.carry_terms = (uint32_t)plan[0];
+        b.n = cnt;
+        const EqCoefs co = eq_coefs(ctx);
+        b.c_lo = co.c_lo; b.c_hi = co.c_hi;
+        memcpy(b.pow_lo, &plan[1], sizeof b.pow_lo);
+        memcpy(b.pow_hi, &plan[1 + (k::kEqMaxCarry + 1) * 10], sizeof b.pow_hi);
+        for (int j = 0; j < cnt; j++) {
+            EqThree* m = (EqThree*)mods[first + j];
+            MXL_TRY(m->ensure_state());
+            MXL_TRY(m->zend.ensure(ctx, (size_t)b.n_chunks * 8 * sizeof(double)));
+            k::EqInst& e = b.inst[j];
+            e.in = io[first + j].in[0] ? io[first + j].in[0]->dev : nullptr;
+            e.out = io[first + j].out[0]->dev;
+            e.state = m->state_ptr(m->cur);
+            e.state_out = m->state_ptr(m->cur ^ 1);
+            e.zend = (double*)m->zend.p;
+            e.g_lo = db_to_linear(m->p.gain_lo_db);        // eq_three.rs:62-64
+            e.g_mid = db_to_linear(m->p.gain_mid_db);
+            e.g_hi = db_to_linear(m->p.gain_hi_db);
+            if (bytes) *bytes += (io[first + j].in[0] ? 4 * frames : 0) + 4 * frames;
+        }
+        MXL_TRY(k::launch_eq_three(ctx, b));
+        for (int j = 0; j < cnt; j++) ((EqThree*)mods[first + j])->cur ^= 1;
+    }
+    return MXL_OK;
+}
+
+// --- Envelope ---
+static int run_envelopes(mxl_ctx* ctx, mxl_module* const* mods, int n, uint64_t t, const IoSet* io, uint64_t* bytes)
+{
+    for (int i = 0; i < n; i++) {
+        Envelope* m = (Envelope*)mods[i];
+        NEED_IO(io[i], 1, 1, "Envelope");
+        MXL_TRY(expect_input(io[i].in[0], MXL_LINE_MONO, "Envelope"));
+        MXL_TRY(expect_output(io[i].out[0], MXL_LINE_MONO, "Envelope"));
+        const uint64_t f = io[i].in[0] ? io[i].in[0]->frames : io[i].out[0]->frames;   // let len = input.len() (envelope.rs:95)
+        MXL_TRY(need_len(io[i].out[0], f, "Envelope output"));
+        if (f == 0) continue;
+        if (f >= 0xffffff00ull) MXL_FAIL(MXL_ERR_LENGTH, "Envelope: call longer than 2^32 samples");
+        MXL_TRY(m->ensure_state());
+        const uint32_t nb = k::envelope_blocks((uint32_t)f);
+        const size_t words = 2 * (size_t)f + 2 * (size_t)nb + 8;
+        MXL_TRY(m->scratch.ensure(ctx, words * sizeof(uint32_t)));
+        k::EnvLaunch p{};
+        p.in = io[i].in[0] ? io[i].in[0]->dev : nullptr;
+        p.out = io[i].out[0]->dev;
+        p.state = (k::EnvState*)m->state.p;
+        p.state_next = (k::EnvState*)m->state.p + 1;
+        p.scratch_a = (uint32_t*)m->scratch.p;
+        p.scratch_b = p.scratch_a + f;
+        p.block_a = p.scratch_b + f;
+        p.block_b = p.block_a + nb;
+        p.t0 = t; p.frames = (uint32_t)f;
+        p.sample_rate = (double)ctx->sample_rate;
+        p.attack_ms = m->p.attack_ms; p.decay_ms = m->p.decay_ms;
+        p.sustain = m->p.sustain_amplitude; p.release_ms = m->p.release_ms;
+        MXL_TRY(k::launch_envelope(ctx, p));
+        if (bytes) *bytes += (io[i].in[0] ? 4 * f : 0) + 4 * f;
+    }
+    return MXL_OK;
+}
+
+// --- Meter ---
+static int run_meters(mxl_ctx* ctx, mxl_module* const* mods, int n, const IoSet* io, uint64_t* bytes)
+{
+    int i = 0;
+    while (i < n) {
+        k::MeterBatch b{};
+        uint64_t frames = 0;
+        int cnt = 0;
+        uint32_t slots = 0;
+        for (; i < n && cnt < k::kMaxBatch; i++) {
+            NEED_IO(io[i], 1, 0, "Meter");
+            MXL_TRY(expect_input(io[i].in[0], MXL_LINE_STEREO, "Meter"));
+            Meter* m = (Meter*)mods[i];
+            const uint64_t f = io[i].in[0] ? io[i].in[0]->frames : ctx->spt;
+            if (cnt && f != frames) break;
+            frames = f;
+            slots = (uint32_t)((f + ctx->spt - 1) / ctx->spt);
+            MXL_TRY(m->records.ensure(ctx, (size_t)slots * sizeof(k::MeterRecord)));
+            m->n_slots = slots;
+            b.inst[cnt++] = k::MeterInst{io[i].in[0] ? io[i].in[0]->dev : nullptr, (k::MeterRecord*)m->records.p};
+            if (bytes && io[i].in[0]) *bytes += 8 * f;
+        }
+        b.frames = frames; b.spt = ctx->spt; b.n = cnt;
+        MXL_TRY(k::launch_meter(ctx, b, slots));
+    }
+    return MXL_OK;
+}
+
+// --- Plotter: plotter.rs:37-56 ---
+static int run_plotters(mxl_ctx* ctx, mxl_module* const* mods, int n, const IoSet* io, uint64_t* bytes)
+{
+    for (int i = 0; i < n; i++) {
+        Plotter* m = (Plotter*)mods[i];
+        NEED_IO(io[i], 1, 0, "Plotter");
+        MXL_TRY(expect_input(io[i].in[0], MXL_LINE_STEREO, "Plotter"));
+        const uint32_t S = ctx->spt;
+        const uint64_t f = io[i].in[0] ? io[i].in[0]->frames : S;
+        const uint64_t ticks = (f + S - 1) / S;          // one reference run_tick per tick of the call
+        // the last tick k in [0, ticks) with (count + k + 1) % 6 == 0
+        int64_t hit = -1;
+        for (uint64_t kk = ticks; kk-- > 0;) {
+            if ((m->count + kk + 1) % 6 == 0) { hit = (int64_t)kk; break; }
+        }
+        m->count += ticks;
+        m->tap_frames = 0;
+        if (hit >= 0 && io[i].in[0]) {                   // `&& inputs[0].connected()` (plotter.rs:40)
+            const uint64_t begin = (uint64_t)hit * S;
+            const uint64_t len = std::min<uint64_t>(S, f - begin);
+            MXL_TRY(m->tap.ensure(ctx, 2 * (size_t)S * sizeof(float)));
+            // the splitter kernel's 16-byte vector path needs an aligned start; an odd `begin`
+            // (odd S, odd tick) starts mid-vector and goes through strided copies instead
+            if ((2 * begin * sizeof(float)) % 16 == 0) {
+                k::SplitBatch b{};
+                b.frames = len; b.n = 1;
+                b.inst[0] = k::SplitInst{io[i].in[0]->dev + 2 * begin, (float*)m->tap.p, (float*)m->tap.p + S};
+                MXL_TRY(k::launch_splitter(ctx, b));
+            } else {
+                MXL_CUDA(cudaMemcpy2DAsync(m->tap.p, sizeof(float), io[i].in[0]->dev + 2 * begin, 2 * sizeof(float), sizeof(float), len, cudaMemcpyDeviceToDevice, ctx->stream));
+                MXL_CUDA(cudaMemcpy2DAsync((float*)m->tap.p + S, sizeof(float), io[i].in[0]->dev + 2 * begin + 1, 2 * sizeof(float), sizeof(float), len, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+            m->tap_frames = (uint32_t)len;
+            if (bytes) *bytes += 16 * len;
+        }
+    }
+    return MXL_OK;
+}
+
+// --- PcmSink ---
+static int run_pcm_sinks(mxl_ctx* ctx, mxl_module* const* mods, int n, const IoSet* io, uint64_t* bytes)
+{
+    for (int i = 0; i < n; i++) {
+        PcmSink* m = (PcmSink*)mods[i];
+        NEED_IO(io[i], 1, 0, "PcmSink");
+        MXL_TRY(expect_input(io[i].in[0], MXL_LINE_STEREO, "PcmSink"));
+        m->n_samples = 0;
+        if (!io[i].in[0]) continue;
+        const uint64_t len = io[i].in[0]->len();
+        MXL_TRY(m->pcm.ensure(ctx, len * sizeof(int16_t)));
+        MXL_TRY(k::launch_pcm_pack(ctx, io[i].in[0]->dev, (int16_t*)m->pcm.p, len));
+        m->n_samples = len;
+        if (bytes) *bytes += 6 * len;
+    }
+    return MXL_OK;
+}
+
+// ================================================================================================
+// VideoMixer: src/module/video_mixer.rs:70-250
+// ================================================================================================
+
+// 4-tap tables of the letterbox scaler (self-specified stand-in for swscale's SWS_BICUBIC)
+static double cubic_weight(double x)
+{
+    const double a = -0.6;
+    x = fabs(x);
+    if (x <= 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1.0;
+    if (x < 2.0) return ((a * x - 5.0 * a) * x + 8.0 * a) * x - 4.0 * a;
+    return 0.0;
+}
+
+static void bicubic_table(uint32_t src_n, uint32_t dst_n, std::vector<int32_t>& pos, std::vector<int16_t>& coef)
+{
+    pos.resize(dst_n);
+    coef.resize((size_t)dst_n * 4);
+    for (uint32_t d = 0; d < dst_n; d++) {
+        const int64_t num = (int64_t)(2 * (uint64_t)d + 1) * src_n - dst_n;
+        const int64_t den = 2 * (int64_t)dst_n;
+        const int64_t ix = num >= 0 ? num / den : -((-num + den - 1) / den);
+        const double frac = (double)(num - ix * den) / (double)den;
+        int w[4], sum = 0, best = 0;
+        for (int q = 0; q < 4; q++) {
+            w[q] = (int)lrint(cubic_weight(frac - (double)(q - 1)) * 16384.0);
+            sum += w[q];
+            if (w[q] > w[best]) best = q;
+        }
+        w[best] += 16384 - sum;
+        pos[d] = (int32_t)ix - 1;
+        for (int q = 0; q < 4; q++) coef[(size_t)d * 4 + q] = (int16_t)w[q];
+    }
+}
+
+// DynamicScaler::scale (src/video/encode.rs:338-397)
+mxl_frame* frame_scale(mxl_frame* src, uint32_t out_w, uint32_t out_h)
+{
+    if (!src) { set_error("frame_scale: NULL frame"); return nullptr; }
+    mxl_ctx* ctx = src->ctx;
+    if (src->layout.width == out_w && src->layout.height == out_h) return frame_retain(src);   // encode.rs:342-345
+    mxl_scale_geometry g;
+    if (mxl_scale_geometry_yuv420p(src->layout.width, src->layout.height, out_w, out_h, &g) != MXL_OK) return nullptr;
+    mxl_frame* dst = mxl_frame_blank(ctx, out_w, out_h);                                        // encode.rs:382
+    if (!dst) return nullptr;
+    if (g.scaled_w == 0 || g.scaled_h == 0) return dst;
+    // per plane: horizontal pass into a temporary, vertical pass into the letterboxed sub-frame
+    // (subframe addressing: codec/src/ffmpeg/frame.rs:219-281; offsets are chroma-aligned already)
+    for (int p = 0; p < 3; p++) {
+        const uint32_t sh = p ? 1 : 0;
+        const uint32_t sw = p ? (src->layout.width + 1) / 2 : src->layout.width;
+        const uint32_t shh = src->layout.plane_h[p];
+        const uint32_t dw = g.scaled_w >> sh, dh = g.scaled_h >> sh;
+        if (dw == 0 || dh == 0) continue;
+        std::vector<int32_t> xpos, ypos;
+        std::vector<int16_t> xco, yco;
+        bicubic_table(sw, dw, xpos, xco);
+        bicubic_table(shh, dh, ypos, yco);
+        uint8_t* tmp = nullptr;
+        int32_t* dpos = nullptr;
+        int16_t* dco = nullptr;
+        const size_t tmp_bytes = (size_t)dw * shh;
+        const size_t tab_n = (size_t)dw + dh;
+        bool ok = cudaMalloc(&tmp, tmp_bytes) == cudaSuccess && cudaMalloc(&dpos, tab_n * sizeof(int32_t)) == cudaSuccess &&
+                  cudaMalloc(&dco, tab_n * 4 * sizeof(int16_t)) == cudaSuccess;
+        if (ok) {
+            ok = cudaMemcpyAsync(dpos, xpos.data(), dw * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
+                 cudaMemcpyAsync(dpos + dw, ypos.data(), dh * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
+                 cudaMemcpyAsync(dco, xco.data(), (size_t)dw * 4 * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
+                 cudaMemcpyAsync(dco + (size_t)dw * 4, yco.data(), (size_t)dh * 4 * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
+        }
+        if (ok) {
+            uint8_t* dplane = dst->dev + dst->layout.offset[p] + (uint64_t)(g.letterbox_y >> sh) * dst->layout.stride[p] + (g.letterbox_x >> sh);
+            ok = k::launch_resample_h(ctx, src->dev + src->layout.offset[p], sw, shh, src->layout.stride[p], tmp, dw, dw, dpos, dco) == MXL_OK &&
+                 k::launch_resample_v(ctx, tmp, dw, shh, dw, dplane, dh, dst->layout.stride[p], dpos + dw, dco + (size_t)dw * 4) == MXL_OK;
+        }
+        cudaStreamSynchronize(ctx->stream);      // tables and temporaries die here (scaler retargets are rare)
+        cudaFree(tmp); cudaFree(dpos); cudaFree(dco);
+        if (!ok) {
+            if (!*last_error()) set_error("frame_scale: CUDA failure");
+            frame_release(dst);
+            return nullptr;
+        }
+    }
+    return dst;
+}
+
+// Channel::rescale (video_mixer.rs:262-274)
+int VideoMixer::rescale(Channel& c, const PictureSettings& target)
+{
+    if (!c.has_scaler || c.scaler_out != target) {
+        c.has_scaler = true;
+        c.scaler_out = target;
+        if (c.has_stored) {
+            mxl_frame* scaled = frame_scale(c.frame, target.w, target.h);
+            if (!scaled) return MXL_ERR_CUDA;
+            frame_release(c.frame);
+            c.frame = scaled;
+        }
+    }
+    return MXL_OK;
+}
+
+int VideoMixer::run(uint64_t t0, const IoSet& io, uint64_t* bytes)
+{
+    NEED_IO(io, MXL_VIDEO_MIXER_CHANNELS, 3, "VideoMixer");
+    for (int i = 0; i < MXL_VIDEO_MIXER_CHANNELS; i++) MXL_TRY(expect_input(io.in[i], MXL_LINE_VIDEO, "VideoMixer input"));
+    for (int i = 0; i < 3; i++) MXL_TRY(expect_output(io.out[i], MXL_LINE_VIDEO, "VideoMixer output"));
+    const uint64_t ticks = io.out[0]->slots.size();
+    for (int i = 0; i < MXL_VIDEO_MIXER_CHANNELS; i++)
+        if (io.in[i] && io.in[i]->slots.size() < ticks) MXL_FAIL(MXL_ERR_LENGTH, "VideoMixer input %d has fewer tick slots than the output", i);
+    if (io.out[1]->slots.size() < ticks || io.out[2]->slots.size() < ticks) MXL_FAIL(MXL_ERR_LENGTH, "VideoMixer A/B outputs have fewer tick slots than Output");
+    if (ticks > 65535) MXL_FAIL(MXL_ERR_LENGTH, "VideoMixer: at most 65535 ticks per call");
+
+    std::vector<k::FadeJob> jobs;
+    std::vector<mxl_frame_layout> job_layouts;
+    // The crossfade of all ticks is ONE launch at the end of the call, so every frame a job points
+    // at must outlive later ticks' expiry/replacement (a released buffer goes back to the pool and
+    // could be handed out again as a later tick's output).
+    std::vector<mxl_frame*> keepalive;
+    struct KeepGuard { std::vector<mxl_frame*>& v; ~KeepGuard() { for (mxl_frame* f : v) frame_release(f); } } keep_guard{keepalive};
+    jobs.reserve(ticks);
+    const Rational tick_duration = Rational::make((int64_t)ctx->spt, (int64_t)ctx->sample_rate);   // 1/TICKS_PER_SECOND (video_mixer.rs:244)
+
+    for (uint64_t kk = 0; kk < ticks; kk++) {
+        const uint64_t t = t0 + kk * ctx->spt;
+        auto in_slot = [&](int idx) -> const VideoSlot* {
+            if (idx < 0 || idx >= MXL_VIDEO_MIXER_CHANNELS || !io.in[idx]) return nullptr;
+            const VideoSlot& s = io.in[idx]->slots[kk];
+            return s.frame ? &s : nullptr;
+        };
+        // send channel specific outputs (video_mixer.rs:80-90)
+        {
+            const VideoSlot* a = in_slot(p.a);
+            const VideoSlot* b = in_slot(p.b);
+            video_slot_set(io.out[1]->slots[kk], a ? a->frame : nullptr, a ? a->duration_hint : Rational(), a ? a->tick_offset : Rational());
+            video_slot_set(io.out[2]->slots[kk], b ? b->frame : nullptr, b ? b->duration_hint : Rational(), b ? b->tick_offset : Rational());
+        }
+        const Rational now = Rational::make((int64_t)t, (int64_t)ctx->sample_rate);                // video_mixer.rs:92
+        // expire stored frames (94-101)
+        for (auto& c : ch)
+            if (c.has_stored && now >= c.active_until) clear_stored(c);
+        // compatible output picture settings (104-119): fold1 over live-or-stored frames
+        bool have_target = false;
+        PictureSettings target;
+        for (int idx = 0; idx < MXL_VIDEO_MIXER_CHANNELS; idx++) {
+            const VideoSlot* s = in_slot(idx);
+            const mxl_frame* f = s ? s->frame : (ch[idx].has_stored ? ch[idx].frame : nullptr);
+            if (!f) continue;
+            PictureSettings ps{f->layout.width, f->layout.height};
+            if (!have_target) { target = ps; have_target = true; }
+            else { uint32_t w, h; mxl_unify_picture_settings(target.w, target.h, ps.w, ps.h, &w, &h); target = PictureSettings{w, h}; }
+        }
+        if (!have_target) {                                 // no inputs and no stored pictures (113-119)
+            video_slot_set(io.out[0]->slots[kk], nullptr, Rational(), Rational());
+            continue;
+        }
+        // receive new input frames (122-148)
+        for (int idx = 0; idx < MXL_VIDEO_MIXER_CHANNELS; idx++) {
+            Channel& c = ch[idx];
+            if (const VideoSlot* s = in_slot(idx)) {
+                clear_stored(c);
+                MXL_TRY(rescale(c, target));
+                mxl_frame* scaled = frame_scale(s->frame, target.w, target.h);
+                if (!scaled) return MXL_ERR_CUDA;
+                c.has_stored = true;
+                c.frame = scaled;
+                c.active_until = now + s->tick_offset + s->duration_hint;                          // 140
+            } else {
+                MXL_TRY(rescale(c, target));
+            }
+        }
+        // compose output frame (150-239)
+        mxl_frame* outf = frame_alloc(ctx, target.w, target.h);
+        if (!outf) return MXL_ERR_OOM;
+        const Channel* ca = (p.a >= 0 && p.a < MXL_VIDEO_MIXER_CHANNELS && ch[p.a].has_stored) ? &ch[p.a] : nullptr;
+        const Channel* cb = (p.b >= 0 && p.b < MXL_VIDEO_MIXER_CHANNELS && ch[p.b].has_stored) ? &ch[p.b] : nullptr;
+        k::FadeJob job{};
+        job.a = ca ? ca->frame->dev : nullptr;
+        job.b = cb ? cb->frame->dev : nullptr;
+        if (ca) keepalive.push_back(frame_retain(ca->frame));
+        if (cb) keepalive.push_back(frame_retain(cb->frame));
+        job.out = outf->dev;
+        job.fade = mxl_fader_to_u8(p.fader);                                                       // 168
+        jobs.push_back(job);
+        job_layouts.push_back(outf->layout);
+        if (bytes) *bytes += (ca ? outf->layout.size : 0) + (cb ? outf->layout.size : 0) + outf->layout.size;
+        video_slot_set(io.out[0]->slots[kk], outf, tick_duration, Rational());                     // 241-247
+        frame_release(outf);                                // the line holds the reference now
+    }
+
+    // one batched launch per run of equal layouts (normally exactly one)
+    if (!jobs.empty()) {
+        MXL_TRY(this->jobs.ensure(ctx, jobs.size() * sizeof(k::FadeJob)));
+        MXL_CUDA(cudaMemcpyAsync(this->jobs.p, jobs.data(), jobs.size() * sizeof(k::FadeJob), cudaMemcpyHostToDevice, ctx->stream));
+        size_t begin = 0;
+        while (begin < jobs.size()) {
+            size_t end = begin + 1;
+            while (end < jobs.size() && job_layouts[end].width == job_layouts[begin].width && job_layouts[end].height == job_layouts[begin].height) end++;
+            MXL_TRY(k::launch_crossfade(ctx, job_layouts[begin], (const k::FadeJob*)this->jobs.p + begin, (uint32_t)(end - begin)));
+            begin = end;
+        }
+    }
+    return MXL_OK;
+}
+
+// ================================================================================================
+// dispatch
+// ================================================================================================
+int run_batch(mxl_ctx* ctx, int kind, mxl_module* const* mods, int n, uint64_t t, const IoSet* io, uint64_t* bytes)
+{
+    if (!ctx || !ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "no CUDA device bound to this context; there is no CPU fallback");
+    if (bytes) *bytes = 0;
+    switch (kind) {
+    case MXL_MOD_OSCILLATOR: return run_oscillators(ctx, mods, n, t, io, bytes);
+    case MXL_MOD_FM_SINE: return run_fm_sines(ctx, mods, n, t, io, bytes);
+    case MXL_MOD_MIXER: return run_mixers(ctx, mods, n, io, bytes);
+    case MXL_MOD_AMPLIFIER: return run_amplifiers(ctx, mods, n, io, bytes);
+    case MXL_MOD_STEREO_PANNER: return run_panners(ctx, n, io, bytes);
+    case MXL_MOD_STEREO_SPLITTER: return run_splitters(ctx, n, io, bytes);
+    case MXL_MOD_TRIGGER: return run_triggers(ctx, mods, n, io, bytes);
+    case MXL_MOD_EQ_THREE: return run_eq_threes(ctx, mods, n, io, bytes);
+    case MXL_MOD_ENVELOPE: return run_envelopes(ctx, mods, n, t, io, bytes);
+    case MXL_MOD_METER: return run_meters(ctx, mods, n, io, bytes);
+    case MXL_MOD_PLOTTER: return run_plotters(ctx, mods, n, io, bytes);
+    case MXL_MOD_PCM_SINK: return run_pcm_sinks(ctx, mods, n, io, bytes);
+    case MXL_MOD_VIDEO_MIXER:
+        for (int i = 0; i < n; i++) {
+            uint64_t b = 0;
+            MXL_TRY(((VideoMixer*)mods[i])->run(t, io[i], &b));
+            if (bytes) *bytes += b;
+        }
+        return MXL_OK;
+    case MXL_MOD_SOURCE_MONO: case MXL_MOD_SOURCE_STEREO: case MXL_MOD_SOURCE_VIDEO:
+        return MXL_OK;       // the source's line IS its output
+    default:
+        MXL_FAIL(MXL_ERR_UNSUPPORTED, "run_tick: module kind %d has no device implementation", kind);
+    }
+}
+
+// ================================================================================================
+// accessors
+// ================================================================================================
+int eq_three_state(mxl_module* m, double state[11])
+{
+    if (!m || m->kind != MXL_MOD_EQ_THREE || !state) MXL_FAIL(MXL_ERR_PARAMS, "not an EqThree module");
+    EqThree* e = (EqThree*)m;
+    MXL_TRY(e->ensure_state());
+    MXL_CUDA(cudaMemcpyAsync(state, e->state_ptr(e->cur), 11 * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+    MXL_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    return MXL_OK;
+}
+
+int envelope_state(mxl_module* m, int32_t* state, uint64_t* seq, double* off_amplitude)
+{
+    if (!m || m->kind != MXL_MOD_ENVELOPE) MXL_FAIL(MXL_ERR_PARAMS, "not an Envelope module");
+    Envelope* e = (Envelope*)m;
+    MXL_TRY(e->ensure_state());
+    k::EnvState s;
+    MXL_CUDA(cudaMemcpyAsync(&s, e->state.p, sizeof s, cudaMemcpyDeviceToHost, m->ctx->stream));
+    MXL_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    if (state) *state = s.state;
+    if (seq) *seq = s.seq;
+    if (off_amplitude) *off_amplitude = s.off_amplitude;
+    return MXL_OK;
+}
+
+int meter_read(mxl_module* m, uint32_t slot, float peak[2], double sumsq[2], int32_t* clip)
+{
+    if (!m || m->kind != MXL_MOD_METER) MXL_FAIL(MXL_ERR_PARAMS, "not a Meter module");
+    Meter* me = (Meter*)m;
+    if (slot >= me->n_slots) MXL_FAIL(MXL_ERR_LENGTH, "meter slot %u out of %u", slot, me->n_slots);
+    k::MeterRecord r;
+    MXL_TRY(m->ctx->activate());
+    MXL_CUDA(cudaMemcpyAsync(&r, (k::MeterRecord*)me->records.p + slot, sizeof r, cudaMemcpyDeviceToHost, m->ctx->stream));
+    MXL_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    if (peak) { peak[0] = r.peak[0]; peak[1] = r.peak[1]; }
+    if (sumsq) { sumsq[0] = r.sumsq[0]; sumsq[1] = r.sumsq[1]; }
+    if (clip) *clip = r.clip;
+    return MXL_OK;
+}
+
+int plotter_read(mxl_module* m, float* left, float* right, uint32_t cap)
+{
+    if (!m || m->kind != MXL_MOD_PLOTTER) MXL_FAIL(MXL_ERR_PARAMS, "not a Plotter module");
+    Plotter* pl = (Plotter*)m;
+    const uint32_t nfr = std::min(cap, pl->tap_frames);
+    if (nfr == 0) return 0;
+    if (m->ctx->activate() != MXL_OK) return MXL_ERR_CUDA;
+    if (cudaMemcpyAsync(left, pl->tap.p, nfr * sizeof(float), cudaMemcpyDeviceToHost, m->ctx->stream) != cudaSuccess ||
+        cudaMemcpyAsync(right, (float*)pl->tap.p + m->ctx->spt, nfr * sizeof(float), cudaMemcpyDeviceToHost, m->ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(m->ctx->stream) != cudaSuccess)
+        MXL_FAIL(MXL_ERR_CUDA, "plotter read-back failed");
+    return (int)nfr;
+}
+
+int source_set_line(mxl_module* m, mxl_line* line)
+{
+    if (!m || (m->kind != MXL_MOD_SOURCE_MONO && m->kind != MXL_MOD_SOURCE_STEREO && m->kind != MXL_MOD_SOURCE_VIDEO))
+        MXL_FAIL(MXL_ERR_PARAMS, "not a Source module");
+    if (line && line->type != m->outputs[0].type) MXL_FAIL(MXL_ERR_LINE_TYPE, "source line type does not match the module's output");
+    ((Source*)m)->line = line;
+    return MXL_OK;
+}
+
+mxl_line* source_line(mxl_module* m)
+{
+    if (!m || (m->kind != MXL_MOD_SOURCE_MONO && m->kind != MXL_MOD_SOURCE_STEREO && m->kind != MXL_MOD_SOURCE_VIDEO)) return nullptr;
+    return ((Source*)m)->line;
+}
+
+int pcm_sink_download(mxl_module* m, int16_t* host, uint64_t n)
+{
+    if (!m || m->kind != MXL_MOD_PCM_SINK) MXL_FAIL(MXL_ERR_PARAMS, "not a PcmSink module");
+    PcmSink* s = (PcmSink*)m;
+    if (n > s->n_samples) MXL_FAIL(MXL_ERR_LENGTH, "%llu samples requested, sink holds %llu", (unsigned long long)n, (unsigned long long)s->n_samples);
+    if (n == 0) return MXL_OK;
+    MXL_TRY(m->ctx->activate());
+    MXL_CUDA(cudaMemcpyAsync(host, s->pcm.p, n * sizeof(int16_t), cudaMemcpyDeviceToHost, m->ctx->stream));
+    MXL_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    return MXL_OK;
+}
+
+int mixer_params_get(const mxl_module* m, mxl_mixer_channel_params* out, uint32_t cap)
+{
+    if (!m || m->kind != MXL_MOD_MIXER) MXL_FAIL(MXL_ERR_PARAMS, "not a Mixer module");
+    const Mixer* mx = (const Mixer*)m;
+    const uint32_t nch = (uint32_t)mx->channels.size();
+    for (uint32_t i = 0; i < nch && i < cap && out; i++) out[i] = mx->channels[i];
+    return (int)nch;
+}
+
+}  // namespace mxl

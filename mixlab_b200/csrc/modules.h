@@ -1,0 +1,67 @@
+// modules.h -- host side of the modules: the C++ mirror of `trait ModuleT` (src/module/mod.rs:7-19)
+// and of ModuleHost (src/engine/module.rs:62-119).  Arithmetic lives in the kernels; these classes
+// hold params, terminals and device-resident state, validate lines the way InputRef/OutputRef
+// expect_* do, and turn a set of same-kind modules into one batched launch.
+#pragma once
+
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "kernels.h"
+
+namespace mxl {
+
+struct Terminal {            // protocol/src/lib.rs:160-174  Terminal(Option<String>, LineType)
+    int type;
+    bool labeled;
+    std::string label;
+};
+
+inline Terminal labeled(int type, const std::string& l) { return Terminal{type, true, l}; }
+inline Terminal unlabeled(int type) { return Terminal{type, false, ""}; }
+
+// inputs / outputs of one module for one call; in[i] == nullptr is InputRef::Disconnected
+struct IoSet {
+    const mxl_line* const* in;
+    uint32_t n_in;
+    mxl_line* const* out;
+    uint32_t n_out;
+};
+
+}  // namespace mxl
+
+struct mxl_module {
+    mxl_ctx* ctx = nullptr;
+    int kind = -1;
+    std::vector<mxl::Terminal> inputs, outputs;
+
+    virtual ~mxl_module() {}
+    virtual int update(const void* params) = 0;          // ModuleT::update
+    virtual int get_params(void* out) const = 0;         // ModuleT::params
+    const char* kind_name() const;
+};
+
+namespace mxl {
+
+mxl_module* module_create(mxl_ctx* ctx, int kind, const void* params);
+
+// Runs `n` modules of one kind for the samples starting at absolute index t (ModuleT::run_tick for
+// each of them, engine.rs:490-494), batching same-length instances into single launches.
+// `bytes_out`, if given, receives the API-level line bytes read + written.
+int run_batch(mxl_ctx* ctx, int kind, mxl_module* const* mods, int n, uint64_t t, const IoSet* io,
+              uint64_t* bytes_out);
+
+// kind-specific accessors used by the ABI
+int eq_three_state(mxl_module* m, double state[11]);
+int envelope_state(mxl_module* m, int32_t* state, uint64_t* seq, double* off_amplitude);
+int meter_read(mxl_module* m, uint32_t slot, float peak[2], double sumsq[2], int32_t* clip);
+int plotter_read(mxl_module* m, float* left, float* right, uint32_t cap);
+int source_set_line(mxl_module* m, mxl_line* line);
+mxl_line* source_line(mxl_module* m);
+int pcm_sink_download(mxl_module* m, int16_t* host, uint64_t n);
+int mixer_params_get(const mxl_module* m, mxl_mixer_channel_params* out, uint32_t cap);
+
+mxl_frame* frame_scale(mxl_frame* src, uint32_t out_w, uint32_t out_h);
+
+}  // namespace mxl

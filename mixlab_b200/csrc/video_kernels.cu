@@ -1,0 +1,278 @@
+// video_kernels.cu -- VideoMixer compositing kernels for sm_100a (src/module/video_mixer.rs:150-239).
+//
+// Crossfade: out = (a*f + b*(255-f)) / 255 per byte, u16 lanes, truncating (fade_line, 211-235).
+// HBM-bound integer work: 16-byte (uint4) accesses, two per thread per layer for memory-level
+// parallelism, and SIMD-in-register arithmetic -- two bytes per 32-bit multiply:
+//     even/odd bytes are split into 16-bit lanes (lane value <= 255), x = lane_a*f + lane_b*(255-f)
+//     stays <= 65025 per lane so nothing carries across lanes, and the exact truncating /255 is
+//     (x + 1 + (x >> 8)) >> 8 (identity checked exhaustively for 0..65025 in tests/test_host_logic.py),
+//     whose intermediate (<= 65280) also fits the lane.
+// The reference first memsets a blank frame (AvFrame::blank, frame.rs:94-135) and lets a missing
+// layer alias it; here a missing layer is synthesised in registers (Y=0x00, U=V=0x80), which
+// removes the memset pass and the re-read of the blank plane.
+#include "kernels.h"
+
+namespace mxl {
+namespace k {
+
+namespace {
+
+constexpr int kVidThreads = 256;
+
+__device__ __forceinline__ uint4 ldg16(const uint8_t* p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t fade4(uint32_t a, uint32_t b, uint32_t f, uint32_t g)
+{
+    const uint32_t ae = a & 0x00FF00FFu, ao = (a >> 8) & 0x00FF00FFu;
+    const uint32_t be = b & 0x00FF00FFu, bo = (b >> 8) & 0x00FF00FFu;
+    const uint32_t xe = ae * f + be * g;
+    const uint32_t xo = ao * f + bo * g;
+    const uint32_t ye = xe + 0x00010001u + ((xe >> 8) & 0x00FF00FFu);
+    const uint32_t yo = xo + 0x00010001u + ((xo >> 8) & 0x00FF00FFu);
+    return ((ye >> 8) & 0x00FF00FFu) | (yo & 0xFF00FF00u);
+}
+
+__device__ __forceinline__ uint4 fade16(uint4 a, uint4 b, uint32_t f, uint32_t g)
+{
+    return make_uint4(fade4(a.x, b.x, f, g), fade4(a.y, b.y, f, g), fade4(a.z, b.z, f, g), fade4(a.w, b.w, f, g));
+}
+
+// Flat path: every plane has stride == processed row width and rows == plane height, so the
+// processed bytes of a frame are one contiguous range [0, size).
+constexpr int kFadeUnroll = 2;
+
+__global__ void __launch_bounds__(kVidThreads) crossfade_flat_kernel(const FadeJob* __restrict__ jobs, uint64_t n16, uint64_t chroma16)
+{
+    const FadeJob job = jobs[blockIdx.y];
+    const uint32_t f = job.fade, g = 255u - job.fade;
+    const uint64_t v0 = ((uint64_t)blockIdx.x * kVidThreads + threadIdx.x) * kFadeUnroll;
+    uint4 a[kFadeUnroll], b[kFadeUnroll];
+#pragma unroll
+    for (int u = 0; u < kFadeUnroll; u++) {
+        const uint64_t v = v0 + u;
+        if (v < n16) {
+            const uint32_t blank = v >= chroma16 ? 0x80808080u : 0u;
+            a[u] = job.a ? ldg16(job.a + v * 16) : make_uint4(blank, blank, blank, blank);
+            b[u] = job.b ? ldg16(job.b + v * 16) : make_uint4(blank, blank, blank, blank);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kFadeUnroll; u++) {
+        const uint64_t v = v0 + u;
+        if (v < n16) *reinterpret_cast<uint4*>(job.out + v * 16) = fade16(a[u], b[u], f, g);
+    }
+}
+
+// General path: one plane per launch, rows may carry untouched stride padding.
+__global__ void __launch_bounds__(kVidThreads) crossfade_plane_kernel(const FadeJob* __restrict__ jobs, uint64_t plane_offset,
+                                                                      uint32_t stride, uint32_t vec_per_row, uint32_t blank)
+{
+    const FadeJob job = jobs[blockIdx.z];
+    const uint32_t col = blockIdx.x * kVidThreads + threadIdx.x;
+    if (col >= vec_per_row) return;
+    const uint64_t off = plane_offset + (uint64_t)blockIdx.y * stride + (uint64_t)col * 16;
+    const uint32_t f = job.fade, g = 255u - job.fade;
+    const uint4 a = job.a ? ldg16(job.a + off) : make_uint4(blank, blank, blank, blank);
+    const uint4 b = job.b ? ldg16(job.b + off) : make_uint4(blank, blank, blank, blank);
+    *reinterpret_cast<uint4*>(job.out + off) = fade16(a, b, f, g);
+}
+
+__global__ void __launch_bounds__(kVidThreads) blank_kernel(uint4* dst, uint64_t n16, uint64_t chroma16)
+{
+    uint64_t i = (uint64_t)blockIdx.x * kVidThreads + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * kVidThreads;
+    for (; i < n16; i += stride) {
+        const uint32_t w = i >= chroma16 ? 0x80808080u : 0u;
+        dst[i] = make_uint4(w, w, w, w);
+    }
+}
+
+// yuv420p -> RGBA8, BT.601 limited range, integer (self-specified; see DESIGN.md "unpinned").
+__device__ __forceinline__ uint32_t clip8(int v) { return (uint32_t)min(max(v, 0), 255); }
+
+__device__ __forceinline__ uint32_t yuv_px(int y, int u, int v)
+{
+    const int c = y - 16, d = u - 128, e = v - 128;
+    const uint32_t r = clip8((298 * c + 409 * e + 128) >> 8);
+    const uint32_t g = clip8((298 * c - 100 * d - 208 * e + 128) >> 8);
+    const uint32_t b = clip8((298 * c + 516 * d + 128) >> 8);
+    return r | (g << 8) | (b << 16) | 0xFF000000u;
+}
+
+struct RgbaArgs {
+    const uint8_t* y; const uint8_t* u; const uint8_t* v; uint8_t* rgba;
+    uint32_t width, height, ystride, cstride;
+};
+
+__global__ void __launch_bounds__(kVidThreads) yuv_to_rgba_kernel(const __grid_constant__ RgbaArgs p)
+{
+    const uint32_t x0 = (blockIdx.x * kVidThreads + threadIdx.x) * 4;
+    const uint32_t row = blockIdx.y;
+    if (x0 >= p.width) return;
+    const uint8_t* yr = p.y + (uint64_t)row * p.ystride;
+    const uint8_t* ur = p.u + (uint64_t)(row >> 1) * p.cstride;
+    const uint8_t* vr = p.v + (uint64_t)(row >> 1) * p.cstride;
+    uint8_t* out = p.rgba + ((uint64_t)row * p.width + x0) * 4;
+    if (x0 + 4 <= p.width) {
+        const uint32_t yy = *reinterpret_cast<const uint32_t*>(yr + x0);
+        const uint32_t uu = *reinterpret_cast<const uint16_t*>(ur + (x0 >> 1));
+        const uint32_t vv = *reinterpret_cast<const uint16_t*>(vr + (x0 >> 1));
+        uint4 px;
+        px.x = yuv_px(yy & 0xFF, uu & 0xFF, vv & 0xFF);
+        px.y = yuv_px((yy >> 8) & 0xFF, uu & 0xFF, vv & 0xFF);
+        px.z = yuv_px((yy >> 16) & 0xFF, uu >> 8, vv >> 8);
+        px.w = yuv_px(yy >> 24, uu >> 8, vv >> 8);
+        *reinterpret_cast<uint4*>(out) = px;
+    } else {
+        for (uint32_t x = x0; x < p.width; x++)
+            reinterpret_cast<uint32_t*>(p.rgba + (uint64_t)row * p.width * 4)[x] = yuv_px(yr[x], ur[x >> 1], vr[x >> 1]);
+    }
+}
+
+// 4-tap separable resample with 14-bit tables; rounding (acc + 8192) >> 14, clipped to u8
+__global__ void __launch_bounds__(kVidThreads) resample_h_kernel(const uint8_t* __restrict__ src, uint32_t sw, uint32_t sstride,
+                                                                 uint8_t* __restrict__ dst, uint32_t dw, uint32_t dstride,
+                                                                 const int32_t* __restrict__ pos, const short* __restrict__ coef)
+{
+    const uint32_t x = blockIdx.x * kVidThreads + threadIdx.x;
+    if (x >= dw) return;
+    const uint8_t* row = src + (uint64_t)blockIdx.y * sstride;
+    const int p0 = pos[x];
+    int acc = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int sx = min(max(p0 + k, 0), (int)sw - 1);
+        acc += (int)coef[x * 4 + k] * (int)row[sx];
+    }
+    dst[(uint64_t)blockIdx.y * dstride + x] = (uint8_t)clip8((acc + 8192) >> 14);
+}
+
+__global__ void __launch_bounds__(kVidThreads) resample_v_kernel(const uint8_t* __restrict__ src, uint32_t sw, uint32_t sh, uint32_t sstride,
+                                                                 uint8_t* __restrict__ dst, uint32_t dstride,
+                                                                 const int32_t* __restrict__ pos, const short* __restrict__ coef)
+{
+    const uint32_t x = blockIdx.x * kVidThreads + threadIdx.x;
+    if (x >= sw) return;
+    const uint32_t y = blockIdx.y;
+    const int p0 = pos[y];
+    int acc = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int sy = min(max(p0 + k, 0), (int)sh - 1);
+        acc += (int)coef[y * 4 + k] * (int)src[(uint64_t)sy * sstride + x];
+    }
+    dst[(uint64_t)y * dstride + x] = (uint8_t)clip8((acc + 8192) >> 14);
+}
+
+int after_launch(mxl_ctx* ctx, const char* name)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("launch of %s failed: %s", name, cudaGetErrorString(e));
+        return MXL_ERR_CUDA;
+    }
+    ctx->launches++;
+    return MXL_OK;
+}
+
+int require_device(mxl_ctx* ctx)
+{
+    if (!ctx || !ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "no CUDA device bound to this context");
+    return ctx->activate();
+}
+
+struct PlaneGeom { uint32_t rows, padw; };
+
+// video_mixer.rs:176-177 (w >> log2_horz, h >> log2_vert) and the 32-byte `while out < end` of fade_line
+PlaneGeom plane_geom(const mxl_frame_layout& lay, int comp)
+{
+    const uint32_t shift = comp == 0 ? 0 : 1;
+    PlaneGeom g;
+    g.rows = lay.height >> shift;
+    g.padw = (((lay.width >> shift) + 31) / 32) * 32;
+    return g;
+}
+
+}  // namespace
+
+int launch_crossfade(mxl_ctx* ctx, const mxl_frame_layout& lay, const FadeJob* jobs_dev, uint32_t n_jobs)
+{
+    MXL_TRY(require_device(ctx));
+    if (n_jobs == 0) return MXL_OK;
+    bool flat = true;
+    for (int c = 0; c < 3; c++) {
+        PlaneGeom g = plane_geom(lay, c);
+        if (g.padw != lay.stride[c] || g.rows != lay.plane_h[c]) flat = false;
+    }
+    if (flat) {
+        const uint64_t n16 = lay.size / 16;
+        const uint64_t per_block = (uint64_t)kVidThreads * kFadeUnroll;
+        dim3 grid((unsigned)((n16 + per_block - 1) / per_block), n_jobs);
+        crossfade_flat_kernel<<<grid, kVidThreads, 0, ctx->stream>>>(jobs_dev, n16, lay.offset[1] / 16);
+        return after_launch(ctx, "crossfade_flat_kernel");
+    }
+    for (int c = 0; c < 3; c++) {
+        PlaneGeom g = plane_geom(lay, c);
+        if (g.rows == 0 || g.padw == 0) continue;
+        const uint32_t vpr = g.padw / 16;
+        dim3 grid((vpr + kVidThreads - 1) / kVidThreads, g.rows, n_jobs);
+        crossfade_plane_kernel<<<grid, kVidThreads, 0, ctx->stream>>>(jobs_dev, lay.offset[c], lay.stride[c], vpr,
+                                                                     c == 0 ? 0u : 0x80808080u);
+        MXL_TRY(after_launch(ctx, "crossfade_plane_kernel"));
+    }
+    return MXL_OK;
+}
+
+int launch_blank(mxl_ctx* ctx, const mxl_frame_layout& lay, uint8_t* frame)
+{
+    MXL_TRY(require_device(ctx));
+    const uint64_t n16 = lay.size / 16;
+    unsigned blocks = (unsigned)((n16 + kVidThreads - 1) / kVidThreads);
+    const unsigned cap = ctx->sm_count > 0 ? ctx->sm_count * 8 : 1184;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) return MXL_OK;
+    blank_kernel<<<blocks, kVidThreads, 0, ctx->stream>>>(reinterpret_cast<uint4*>(frame), n16, lay.offset[1] / 16);
+    return after_launch(ctx, "blank_kernel");
+}
+
+int launch_yuv_to_rgba(mxl_ctx* ctx, const mxl_frame_layout& lay, const uint8_t* yuv, uint8_t* rgba)
+{
+    MXL_TRY(require_device(ctx));
+    if (lay.width == 0 || lay.height == 0) return MXL_OK;
+    RgbaArgs a{yuv + lay.offset[0], yuv + lay.offset[1], yuv + lay.offset[2], rgba,
+               lay.width, lay.height, lay.stride[0], lay.stride[1]};
+    dim3 grid(((lay.width + 3) / 4 + kVidThreads - 1) / kVidThreads, lay.height);
+    yuv_to_rgba_kernel<<<grid, kVidThreads, 0, ctx->stream>>>(a);
+    return after_launch(ctx, "yuv_to_rgba_kernel");
+}
+
+int launch_resample_h(mxl_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, uint32_t sstride,
+                      uint8_t* dst, uint32_t dw, uint32_t dstride, const int32_t* pos, const int16_t* coef)
+{
+    MXL_TRY(require_device(ctx));
+    if (dw == 0 || sh == 0) return MXL_OK;
+    dim3 grid((dw + kVidThreads - 1) / kVidThreads, sh);
+    resample_h_kernel<<<grid, kVidThreads, 0, ctx->stream>>>(src, sw, sstride, dst, dw, dstride, pos,
+                                                             reinterpret_cast<const short*>(coef));
+    return after_launch(ctx, "resample_h_kernel");
+}
+
+int launch_resample_v(mxl_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, uint32_t sstride,
+                      uint8_t* dst, uint32_t dh, uint32_t dstride, const int32_t* pos, const int16_t* coef)
+{
+    MXL_TRY(require_device(ctx));
+    if (sw == 0 || dh == 0) return MXL_OK;
+    dim3 grid((sw + kVidThreads - 1) / kVidThreads, dh);
+    resample_v_kernel<<<grid, kVidThreads, 0, ctx->stream>>>(src, sw, sh, sstride, dst, dstride, pos,
+                                                             reinterpret_cast<const short*>(coef));
+    return after_launch(ctx, "resample_v_kernel");
+}
+
+}  // namespace k
+}  // namespace mxl

@@ -1,0 +1,172 @@
+"""GPU parity: VideoMixer compositing (src/module/video_mixer.rs:70-250) through the C ABI against the
+CPU oracle; u8 planes must be bit-exact."""
+import numpy as np
+import pytest
+
+from mixlab_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+FADERS = [0.0, 0.25, 0.5, 0.999, 1.0]          # -> f in {0, 63, 127, 254, 255}
+
+
+def make_frame(ctx, oracle, w, h, seed):
+    lay = oracle.frame_layout(w, h)
+    data = W.random_bytes(seed, lay.size)
+    return ctx.frame(w, h, data), data, lay
+
+
+def run_mixer(mxl, ctx, params, inputs, ticks=1, t0=0, mod=None):
+    """inputs: {channel: [frame or None per tick]}.  Returns (module, [Output, A, B] video lines)."""
+    mod = mod or ctx.module(mxl.MOD_VIDEO_MIXER, params)
+    ins = []
+    for ch in range(4):
+        if ch in inputs:
+            vl = ctx.video_line(ticks)
+            for k, fr in enumerate(inputs[ch]):
+                if fr is not None:
+                    vl.set(k, fr)
+            ins.append(vl)
+        else:
+            ins.append(None)
+    outs = [ctx.video_line(ticks) for _ in range(3)]
+    mod.run_tick(t0, ins, outs)
+    return mod, outs
+
+
+@pytest.mark.parametrize("size", [(1920, 1080), (560, 350), (1120, 700), (64, 36), (70, 50), (34, 18)])
+def test_crossfade_two_layers(mxl, oracle, ctx48, size):
+    w, h = size
+    fa, da, lay = make_frame(ctx48, oracle, w, h, 0xA11CE)
+    fb, db, _ = make_frame(ctx48, oracle, w, h, 0xB0B)
+    flay = mxl.frame_layout(w, h)
+    assert (list(flay.stride), list(flay.plane_h), list(flay.offset), flay.size) == (
+        list(lay.stride), list(lay.plane_h), list(lay.offset), lay.size)
+    for fader in FADERS:
+        mod, outs = run_mixer(mxl, ctx48, (0, 1, fader), {0: [fa], 1: [fb]})
+        got = outs[0].get(0).download_raw()
+        want = oracle.video_crossfade(lay, da, db, oracle.fader_to_u8(fader))
+        # bytes the reference never writes (stride padding beyond ceil(w/32)*32, odd last rows) are
+        # blank-valued in both
+        assert np.array_equal(got, want), (size, fader)
+        # pass-through outputs A / B are the input frames themselves (video_mixer.rs:80-90)
+        assert np.array_equal(outs[1].get(0).download_raw(), da)
+        assert np.array_equal(outs[2].get(0).download_raw(), db)
+        mod.destroy()
+
+
+@pytest.mark.parametrize("missing", ["a", "b", "both_params_none"])
+def test_crossfade_missing_layer_aliases_blank(mxl, oracle, ctx48, missing):
+    w, h = 1920, 1080
+    fa, da, lay = make_frame(ctx48, oracle, w, h, 1)
+    if missing == "a":
+        params, ins, a, b = (-1, 0, 0.5), {0: [fa]}, None, da
+    elif missing == "b":
+        params, ins, a, b = (0, -1, 0.5), {0: [fa]}, da, None
+    else:
+        params, ins, a, b = (-1, -1, 0.5), {0: [fa]}, None, None
+    mod, outs = run_mixer(mxl, ctx48, params, ins)
+    got = outs[0].get(0).download_raw()
+    want = oracle.video_crossfade(lay, a, b, 127)
+    assert np.array_equal(got, want)
+
+
+def test_no_inputs_no_output(mxl, ctx48):
+    # video_mixer.rs:113-119: no inputs and no stored pictures -> Output stays None
+    mod, outs = run_mixer(mxl, ctx48, (0, 1, 0.5), {})
+    assert outs[0].get(0) is None and outs[1].get(0) is None and outs[2].get(0) is None
+
+
+def test_stored_frame_persists_until_expiry(mxl, oracle, ctx48):
+    # video_mixer.rs:92-101,139-143: a frame with duration_hint 1/30 s received at tick 0 is still
+    # composited at tick 1 and expires at tick 2 (now >= active_until)
+    w, h = 64, 36
+    fa, da, lay = make_frame(ctx48, oracle, w, h, 3)
+    fb, db, _ = make_frame(ctx48, oracle, w, h, 4)
+    mod = ctx48.module(mxl.MOD_VIDEO_MIXER, (0, 1, 0.25))
+    ticks = 4
+    ina, inb = ctx48.video_line(ticks), ctx48.video_line(ticks)
+    ina.set(0, fa, duration=(1, 30))
+    for k in range(ticks):
+        inb.set(k, fb, duration=(1, 60))
+    outs = [ctx48.video_line(ticks) for _ in range(3)]
+    mod.run_tick(0, [ina, inb, None, None], outs)
+    f = oracle.fader_to_u8(0.25)
+    with_a = oracle.video_crossfade(lay, da, db, f)
+    without_a = oracle.video_crossfade(lay, None, db, f)
+    assert np.array_equal(outs[0].get(0).download_raw(), with_a)
+    assert np.array_equal(outs[0].get(1).download_raw(), with_a)
+    assert np.array_equal(outs[0].get(2).download_raw(), without_a)
+    assert np.array_equal(outs[0].get(3).download_raw(), without_a)
+    assert outs[1].get(0) is not None and outs[1].get(1) is None
+
+
+def test_batched_ticks_equal_single_ticks(mxl, oracle, ctx48):
+    w, h = 560, 350
+    ticks = 5
+    frames_a = [make_frame(ctx48, oracle, w, h, 100 + k) for k in range(ticks)]
+    frames_b = [make_frame(ctx48, oracle, w, h, 200 + k) for k in range(ticks)]
+    lay = frames_a[0][2]
+    mod, outs = run_mixer(mxl, ctx48, (2, 3, 0.7), {2: [f[0] for f in frames_a], 3: [f[0] for f in frames_b]}, ticks=ticks)
+    f = oracle.fader_to_u8(0.7)
+    for k in range(ticks):
+        want = oracle.video_crossfade(lay, frames_a[k][1], frames_b[k][1], f)
+        assert np.array_equal(outs[0].get(k).download_raw(), want), k
+
+
+def test_mixed_sizes_letterbox_geometry(mxl, oracle, ctx48):
+    # unify_picture_settings + DynamicScaler (video_mixer.rs:261-297; encode.rs:338-397): a 640x480
+    # layer next to a 1280x720 one is letterboxed to 960x720 at x=160 inside a blank 1280x720 frame.
+    # The resample itself stands in for third-party swscale (parity unpinned): checked against this
+    # repo's own oracle spec.
+    fa, da, laya = make_frame(ctx48, oracle, 1280, 720, 7)
+    fb, db, layb = make_frame(ctx48, oracle, 640, 480, 8)
+    assert mxl.unify_picture_settings(1280, 720, 640, 480) == oracle.unify_picture(1280, 720, 640, 480) == (1280, 720)
+    geo = mxl.scale_geometry(640, 480, 1280, 720)
+    assert geo == oracle.scale_geometry(640, 480, 1280, 720) == (960, 720, 160, 0)
+    scaled = fb.scale(1280, 720)
+    got = scaled.download_raw()
+    lay = oracle.frame_layout(1280, 720)
+    want = oracle.frame_blank(lay)
+    for p in range(3):
+        sh = 0 if p == 0 else 1
+        sw, shh = 640 >> sh, 480 >> sh
+        dw, dh = 960 >> sh, 720 >> sh
+        src = db[layb.offset[p]:layb.offset[p] + layb.stride[p] * layb.plane_h[p]]
+        dst = oracle.bicubic_plane(src, sw, shh, layb.stride[p], dw, dh, dw)
+        plane = want[lay.offset[p]:lay.offset[p] + lay.stride[p] * lay.plane_h[p]].reshape(lay.plane_h[p], lay.stride[p])
+        plane[0:dh, (160 >> sh):(160 >> sh) + dw] = dst.reshape(dh, dw)
+    assert np.array_equal(got, want)
+    # identity when sizes match (encode.rs:342-345): the very same frame comes back
+    same = fa.scale(1280, 720)
+    assert same.h == fa.h
+    # and the mixer composites the letterboxed layer
+    mod, outs = run_mixer(mxl, ctx48, (0, 1, 0.5), {0: [fa], 1: [fb]})
+    out = outs[0].get(0)
+    assert (out.layout.width, out.layout.height) == (1280, 720)
+    assert np.array_equal(out.download_raw(), oracle.video_crossfade(lay, da, want, 127))
+
+
+def test_yuv_to_rgba_self_specified(mxl, oracle, ctx48):
+    # UNPINNED: the reference never converts colour (video_mixer.rs:282-283); spec = oracle header
+    for (w, h) in [(1920, 1080), (70, 50), (34, 18)]:
+        fr, data, lay = make_frame(ctx48, oracle, w, h, 0xC0FFEE + w)
+        assert np.array_equal(fr.to_rgba(), oracle.yuv420p_to_rgba(lay, data))
+
+
+def test_blank_frame(mxl, oracle, ctx48):
+    for (w, h) in [(1920, 1080), (560, 350), (34, 18)]:
+        fr = ctx48.frame(w, h, blank=True)
+        assert np.array_equal(fr.download_raw(), oracle.frame_blank(oracle.frame_layout(w, h)))
+
+
+def test_plane_upload_download_with_caller_strides(mxl, oracle, ctx48):
+    w, h = 70, 50
+    fr = ctx48.frame(w, h, blank=True)
+    planes = [W.random_bytes(1, 80 * 50), W.random_bytes(2, 40 * 25), W.random_bytes(3, 40 * 25)]
+    fr.upload_planes(planes, (80, 40, 40))
+    back = fr.download_planes((80, 40, 40))
+    for p, (pw, ph, st) in enumerate([(70, 50, 80), (35, 25, 40), (35, 25, 40)]):
+        a = planes[p].reshape(ph, st)[:, :pw]
+        b = back[p].reshape(ph, st)[:, :pw]
+        assert np.array_equal(a, b)
