@@ -239,6 +239,9 @@ MXL_API int mxl_eq_three_state(mxl_module *m, double state[11]);
 MXL_API int mxl_envelope_state(mxl_module *m, int32_t *state, uint64_t *seq, double *off_amplitude);
 /* Meter: values of tick slot `slot` of the last call */
 MXL_API int mxl_meter_read(mxl_module *m, uint32_t slot, float peak[2], double sumsq[2], int32_t *clip);
+/* All tick slots of the last call in one copy (synchronises).  Returns the number of records. */
+typedef struct mxl_meter_record { float peak[2]; int32_t clip; int32_t _pad; double sumsq[2]; } mxl_meter_record;
+MXL_API int mxl_meter_download(mxl_module *m, mxl_meter_record *records, uint32_t cap);
 /* Plotter (plotter.rs:37-56): de-interleaved tap of the most recent tick whose count % 6 == 0
  * within the last call.  Returns the number of frames written (0 = no indication). */
 MXL_API int mxl_plotter_read(mxl_module *m, float *left, float *right, uint32_t cap_frames);

@@ -90,9 +90,7 @@ class StageInfo(C.Structure):
                 ("last_ms", C.c_float), ("algorithmic_bytes", C.c_uint64)]
 
 
-class SessionStats(C.Structure):
-    _fields_ = [("launches", C.c_uint64), ("algorithmic_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64)]
+METER_RECORD = np.dtype([("peak", np.float32, 2), ("clip", np.int32), ("_pad", np.int32), ("sumsq", np.float64, 2)])
 
 
 _PARAM_TYPES = {
@@ -185,6 +183,7 @@ def lib():
         "mxl_eq_three_state": (i32, [vp, C.POINTER(dbl)]),
         "mxl_envelope_state": (i32, [vp, C.POINTER(C.c_int32), C.POINTER(u64), C.POINTER(dbl)]),
         "mxl_meter_read": (i32, [vp, u32, C.POINTER(C.c_float), C.POINTER(dbl), C.POINTER(C.c_int32)]),
+        "mxl_meter_download": (i32, [vp, vp, u32]),
         "mxl_plotter_read": (i32, [vp, vp, vp, u32]),
         "mxl_source_set_line": (i32, [vp, vp]),
         "mxl_pcm_sink_download": (i32, [vp, vp, u64]),
@@ -578,6 +577,11 @@ class Module:
         pk, sq, cl = (C.c_float * 2)(), (C.c_double * 2)(), C.c_int32()
         check(lib().mxl_meter_read(self.h, slot, pk, sq, C.byref(cl)))
         return (pk[0], pk[1]), (sq[0], sq[1]), bool(cl.value)
+
+    def meter_download(self, n_slots, out=None):
+        out = np.empty(n_slots, METER_RECORD) if out is None else out
+        n = check(lib().mxl_meter_download(self.h, _ptr(out), n_slots))
+        return out[:n]
 
     def plotter_read(self, cap):
         left, right = np.zeros(cap, np.float32), np.zeros(cap, np.float32)

@@ -77,6 +77,7 @@ MXL_HD double sin_f64(double x)
 {
     if (!(fabs(x) < 35184372088832.0))   // 2^45, also catches NaN / inf
         return sin(x);
+    if (x == 0.0) return x;               // sin(-0.0) = -0.0: Square takes the sign BIT (oscillator.rs:15-23)
     return sin_reduced(x, nullptr);
 }
 

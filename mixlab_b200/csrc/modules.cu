@@ -1102,6 +1102,20 @@ int meter_read(mxl_module* m, uint32_t slot, float peak[2], double sumsq[2], int
     return MXL_OK;
 }
 
+int meter_download(mxl_module* m, mxl_meter_record* records, uint32_t cap)
+{
+    static_assert(sizeof(mxl_meter_record) == sizeof(k::MeterRecord), "ABI record mirrors the kernel's");
+    if (!m || m->kind != MXL_MOD_METER) MXL_FAIL(MXL_ERR_PARAMS, "not a Meter module");
+    Meter* me = (Meter*)m;
+    const uint32_t n = std::min(cap, me->n_slots);
+    if (n == 0) return 0;
+    if (!records) MXL_FAIL(MXL_ERR_INVALID, "NULL records");
+    MXL_TRY(m->ctx->activate());
+    MXL_CUDA(cudaMemcpyAsync(records, me->records.p, (size_t)n * sizeof(k::MeterRecord), cudaMemcpyDeviceToHost, m->ctx->stream));
+    MXL_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    return (int)n;
+}
+
 int plotter_read(mxl_module* m, float* left, float* right, uint32_t cap)
 {
     if (!m || m->kind != MXL_MOD_PLOTTER) MXL_FAIL(MXL_ERR_PARAMS, "not a Plotter module");

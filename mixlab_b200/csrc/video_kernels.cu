@@ -128,7 +128,12 @@ __global__ void __launch_bounds__(kVidThreads) yuv_to_rgba_kernel(const __grid_c
         px.y = yuv_px((yy >> 8) & 0xFF, uu & 0xFF, vv & 0xFF);
         px.z = yuv_px((yy >> 16) & 0xFF, uu >> 8, vv >> 8);
         px.w = yuv_px(yy >> 24, uu >> 8, vv >> 8);
-        *reinterpret_cast<uint4*>(out) = px;
+        if ((p.width & 3u) == 0) {
+            *reinterpret_cast<uint4*>(out) = px;          // rows start 16-byte aligned only then
+        } else {
+            uint32_t* o = reinterpret_cast<uint32_t*>(out);
+            o[0] = px.x; o[1] = px.y; o[2] = px.z; o[3] = px.w;
+        }
     } else {
         for (uint32_t x = x0; x < p.width; x++)
             reinterpret_cast<uint32_t*>(p.rgba + (uint64_t)row * p.width * 4)[x] = yuv_px(yr[x], ur[x >> 1], vr[x >> 1]);

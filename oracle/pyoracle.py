@@ -318,3 +318,40 @@ class Graph:
         clip = C.c_int(0)
         lib().orc_graph_meter(self._g, module, peak, sumsq, C.byref(clip))
         return (peak[0], peak[1]), (sumsq[0], sumsq[1]), bool(clip.value)
+
+
+# ---- GraphDesc (mixlab_b200.workloads) instantiated on the oracle engine walker ------------------
+def oracle_kind(name):
+    return {
+        "Amplifier": MOD_AMPLIFIER, "Envelope": MOD_ENVELOPE, "EqThree": MOD_EQ_THREE,
+        "FmSine": MOD_FM_SINE, "Mixer": MOD_MIXER, "Oscillator": MOD_OSCILLATOR,
+        "Plotter": MOD_PLOTTER, "StereoPanner": MOD_STEREO_PANNER,
+        "StereoSplitter": MOD_STEREO_SPLITTER, "Trigger": MOD_TRIGGER, "Meter": MOD_METER,
+        "SourceStereo": MOD_SOURCE_STEREO, "SourceMono": MOD_SOURCE_MONO,
+    }[name]
+
+
+def oracle_params(name, params):
+    if params is None:
+        return ()
+    if name == "Mixer":
+        flat = [float(len(params))]
+        for g, f, c in params:
+            flat += [float(g), float(f), 1.0 if c else 0.0]
+        return flat
+    if name == "Oscillator":
+        return [float(params[0]), float(params[1])]
+    if name == "Trigger":
+        return [1.0 if params[0] == 0 else 0.0]      # GATE_OPEN = 0
+    return [float(p) for p in params]
+
+
+def build_graph(desc, sample_rate, spt):
+    """desc: an object with .modules [(kind name, params)] and .connections [(im, ii, om, oi)]."""
+    g = Graph(float(sample_rate), spt)
+    ids = [g.add(oracle_kind(kind), oracle_params(kind, params)) for kind, params in desc.modules]
+    for im, ii, om, oi in desc.connections:
+        rc = g.connect(ids[im], ii, ids[om], oi)
+        if rc != 0:
+            raise ValueError("connect(%d,%d,%d,%d) -> %d" % (im, ii, om, oi, rc))
+    return g, ids

@@ -6,38 +6,8 @@ import numpy as np
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def oracle_kind(po, name):
-    return {
-        "Amplifier": po.MOD_AMPLIFIER, "Envelope": po.MOD_ENVELOPE, "EqThree": po.MOD_EQ_THREE,
-        "FmSine": po.MOD_FM_SINE, "Mixer": po.MOD_MIXER, "Oscillator": po.MOD_OSCILLATOR,
-        "Plotter": po.MOD_PLOTTER, "StereoPanner": po.MOD_STEREO_PANNER,
-        "StereoSplitter": po.MOD_STEREO_SPLITTER, "Trigger": po.MOD_TRIGGER, "Meter": po.MOD_METER,
-        "SourceStereo": po.MOD_SOURCE_STEREO, "SourceMono": po.MOD_SOURCE_MONO,
-    }[name]
-
-
-def oracle_params(name, params):
-    if params is None:
-        return ()
-    if name == "Mixer":
-        flat = [float(len(params))]
-        for g, f, c in params:
-            flat += [float(g), float(f), 1.0 if c else 0.0]
-        return flat
-    if name == "Oscillator":
-        return [float(params[0]), float(params[1])]
-    if name == "Trigger":
-        return [1.0 if params[0] == 0 else 0.0]      # GATE_OPEN = 0
-    return [float(p) for p in params]
-
-
 def build_oracle_graph(po, desc, sample_rate, spt):
-    g = po.Graph(float(sample_rate), spt)
-    ids = [g.add(oracle_kind(po, kind), oracle_params(kind, params)) for kind, params in desc.modules]
-    for im, ii, om, oi in desc.connections:
-        rc = g.connect(ids[im], ii, ids[om], oi)
-        assert rc == 0, (rc, im, ii, om, oi)
-    return g, ids
+    return po.build_graph(desc, sample_rate, spt)
 
 
 def oracle_run(po, desc, sample_rate, spt, tick0, n_ticks, tap, width, sources=None):
