@@ -121,6 +121,18 @@ MXL_API mxl_ctx *mxl_ctx_create_on_stream(int device, uint32_t sample_rate, uint
                                           void *cuda_stream);
 MXL_API int mxl_ctx_destroy(mxl_ctx *ctx);
 MXL_API int mxl_ctx_synchronize(mxl_ctx *ctx);
+/* Copy/compute overlap for host-fed sessions.  When enabled, the *_async upload calls run on an
+ * upload stream and the *_async download calls on a download stream, ordered against the compute
+ * stream by events (upload waits for the last run, a run waits for the uploads and downloads enqueued
+ * before it, a download waits for the last run), so step k+1's uploads overlap step k's downloads on
+ * the full-duplex bus.  Synchronous calls and mxl_ctx_synchronize still wait for everything. */
+MXL_API int mxl_ctx_set_copy_overlap(mxl_ctx *ctx, int enabled);
+/* Marks "all downloads enqueued so far" (slot 0..3) / blocks the host until that mark is reached. */
+MXL_API int mxl_ctx_download_fence(mxl_ctx *ctx, uint32_t slot);
+MXL_API int mxl_ctx_wait_fence(mxl_ctx *ctx, uint32_t slot);
+/* Bytes moved by the upload / download entry points of this context so far. */
+MXL_API uint64_t mxl_ctx_h2d_bytes(const mxl_ctx *ctx);
+MXL_API uint64_t mxl_ctx_d2h_bytes(const mxl_ctx *ctx);
 MXL_API void *mxl_ctx_stream(mxl_ctx *ctx);
 MXL_API uint32_t mxl_ctx_sample_rate(const mxl_ctx *ctx);
 MXL_API uint32_t mxl_ctx_samples_per_tick(const mxl_ctx *ctx);
@@ -242,6 +254,8 @@ MXL_API int mxl_meter_read(mxl_module *m, uint32_t slot, float peak[2], double s
 /* All tick slots of the last call in one copy (synchronises).  Returns the number of records. */
 typedef struct mxl_meter_record { float peak[2]; int32_t clip; int32_t _pad; double sumsq[2]; } mxl_meter_record;
 MXL_API int mxl_meter_download(mxl_module *m, mxl_meter_record *records, uint32_t cap);
+/* Same copy without the synchronisation (records should be pinned memory). */
+MXL_API int mxl_meter_download_async(mxl_module *m, mxl_meter_record *records, uint32_t cap);
 /* Plotter (plotter.rs:37-56): de-interleaved tap of the most recent tick whose count % 6 == 0
  * within the last call.  Returns the number of frames written (0 = no indication). */
 MXL_API int mxl_plotter_read(mxl_module *m, float *left, float *right, uint32_t cap_frames);

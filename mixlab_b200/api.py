@@ -123,6 +123,11 @@ def lib():
         "mxl_ctx_create_on_stream": (vp, [i32, u32, u32, vp]),
         "mxl_ctx_destroy": (i32, [vp]),
         "mxl_ctx_synchronize": (i32, [vp]),
+        "mxl_ctx_set_copy_overlap": (i32, [vp, i32]),
+        "mxl_ctx_download_fence": (i32, [vp, u32]),
+        "mxl_ctx_wait_fence": (i32, [vp, u32]),
+        "mxl_ctx_h2d_bytes": (u64, [vp]),
+        "mxl_ctx_d2h_bytes": (u64, [vp]),
         "mxl_ctx_stream": (vp, [vp]),
         "mxl_ctx_sample_rate": (u32, [vp]),
         "mxl_ctx_samples_per_tick": (u32, [vp]),
@@ -184,6 +189,7 @@ def lib():
         "mxl_envelope_state": (i32, [vp, C.POINTER(C.c_int32), C.POINTER(u64), C.POINTER(dbl)]),
         "mxl_meter_read": (i32, [vp, u32, C.POINTER(C.c_float), C.POINTER(dbl), C.POINTER(C.c_int32)]),
         "mxl_meter_download": (i32, [vp, vp, u32]),
+        "mxl_meter_download_async": (i32, [vp, vp, u32]),
         "mxl_plotter_read": (i32, [vp, vp, vp, u32]),
         "mxl_source_set_line": (i32, [vp, vp]),
         "mxl_pcm_sink_download": (i32, [vp, vp, u64]),
@@ -300,6 +306,23 @@ class Context:
 
     def synchronize(self):
         check(lib().mxl_ctx_synchronize(self.h))
+
+    def set_copy_overlap(self, on):
+        check(lib().mxl_ctx_set_copy_overlap(self.h, 1 if on else 0))
+
+    def download_fence(self, slot):
+        check(lib().mxl_ctx_download_fence(self.h, slot))
+
+    def wait_fence(self, slot):
+        check(lib().mxl_ctx_wait_fence(self.h, slot))
+
+    @property
+    def h2d_bytes(self):
+        return int(lib().mxl_ctx_h2d_bytes(self.h))
+
+    @property
+    def d2h_bytes(self):
+        return int(lib().mxl_ctx_d2h_bytes(self.h))
 
     @property
     def launch_count(self):

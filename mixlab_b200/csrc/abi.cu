@@ -101,13 +101,18 @@ int mxl_module_run_tick(mxl_module* m, uint64_t t, const mxl_line* const* inputs
         if (outputs[i] && outputs[i]->ctx != m->ctx) MXL_FAIL(MXL_ERR_INVALID, "output %u belongs to another context", i);
     IoSet io{inputs, n_inputs, outputs, n_outputs};
     mxl_module* one = m;
-    return run_batch(m->ctx, m->kind, &one, 1, t, &io, nullptr);
+    if (m->ctx->has_device()) MXL_TRY(m->ctx->activate());
+    MXL_TRY(m->ctx->compute_begin());
+    const int rc = run_batch(m->ctx, m->kind, &one, 1, t, &io, nullptr);
+    MXL_TRY(m->ctx->compute_end());
+    return rc;
 }
 
 int mxl_eq_three_state(mxl_module* m, double state[11]) { return eq_three_state(m, state); }
 int mxl_envelope_state(mxl_module* m, int32_t* state, uint64_t* seq, double* off_amplitude) { return envelope_state(m, state, seq, off_amplitude); }
 int mxl_meter_read(mxl_module* m, uint32_t slot, float peak[2], double sumsq[2], int32_t* clip) { return meter_read(m, slot, peak, sumsq, clip); }
 int mxl_meter_download(mxl_module* m, mxl_meter_record* records, uint32_t cap) { return meter_download(m, records, cap); }
+int mxl_meter_download_async(mxl_module* m, mxl_meter_record* records, uint32_t cap) { return meter_download_async(m, records, cap); }
 int mxl_plotter_read(mxl_module* m, float* left, float* right, uint32_t cap_frames) { return plotter_read(m, left, right, cap_frames); }
 int mxl_source_set_line(mxl_module* m, mxl_line* line) { return source_set_line(m, line); }
 int mxl_pcm_sink_download(mxl_module* m, int16_t* host, uint64_t n_samples) { return pcm_sink_download(m, host, n_samples); }

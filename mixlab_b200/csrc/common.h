@@ -71,6 +71,26 @@ struct mxl_ctx {
     std::unordered_map<uint64_t, std::vector<uint8_t*>> frame_pool;
     // EqThree chunk plans by chunk length (see modules.cu: eq_plan_for)
     std::map<uint32_t, std::vector<double>> eq_plans;
+    // single-launch EqThree plans by chunk length: [Hc, pow_lo[8][10], pow_hi[8][10]]; empty = unusable
+    std::map<uint32_t, std::vector<double>> eq_block_plans;
+    size_t eq_block_smem = 0;         // dynamic shared memory eq_block_kernel has been configured for
+
+    // Copy/compute overlap (mxl_ctx_set_copy_overlap): async uploads go to stream_in, async downloads
+    // to stream_out, ordered against the compute stream with events:
+    //   upload   waits for the last compute            (WAR on input lines/frames)
+    //   compute  waits for the uploads and downloads enqueued so far (RAW on inputs, WAR on recycled outputs)
+    //   download waits for the last compute            (RAW on outputs)
+    bool overlap = false;
+    cudaStream_t stream_in = nullptr, stream_out = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_compute = nullptr;
+    cudaEvent_t fences[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool in_dirty = false, out_dirty = false, in_must_wait = false, out_must_wait = false;
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;
+
+    int upload_stream(cudaStream_t* s);     // stream an async upload must be issued on
+    int download_stream(cudaStream_t* s);
+    int compute_begin();                    // called before kernels of a run are enqueued
+    int compute_end();
 
     bool has_device() const { return device >= 0; }
     int activate() const;            // cudaSetDevice

@@ -96,8 +96,10 @@ mxl_line* line_alloc(mxl_ctx* ctx, int type, uint64_t frames)
     if (bytes) {
         cudaError_t e = cudaMalloc(&l->dev, bytes);
         if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); delete l; return nullptr; }
+        ctx->compute_begin();
         e = cudaMemsetAsync(l->dev, 0, bytes, ctx->stream);        // vec![0.0; N]  (io.rs:73-74)
         if (e != cudaSuccess) { set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(e)); cudaFree(l->dev); delete l; return nullptr; }
+        ctx->compute_end();
     }
     return l;
 }
@@ -131,7 +133,9 @@ int line_resize(mxl_line* l, uint64_t frames)
     size_t bytes = (size_t)l->len() * sizeof(float);
     if (bytes) {
         MXL_CUDA(cudaMalloc(&l->dev, bytes));
+        MXL_TRY(l->ctx->compute_begin());
         MXL_CUDA(cudaMemsetAsync(l->dev, 0, bytes, l->ctx->stream));
+        MXL_TRY(l->ctx->compute_end());
     }
     return MXL_OK;
 }
@@ -197,6 +201,48 @@ int mxl_ctx::activate() const
 {
     if (device < 0) MXL_FAIL(MXL_ERR_NO_DEVICE, "no CUDA device bound to this context");
     MXL_CUDA(cudaSetDevice(device));
+    return MXL_OK;
+}
+
+int mxl_ctx::upload_stream(cudaStream_t* s)
+{
+    if (!overlap) { *s = stream; return MXL_OK; }
+    if (in_must_wait) { MXL_CUDA(cudaStreamWaitEvent(stream_in, ev_compute, 0)); in_must_wait = false; }
+    in_dirty = true;
+    *s = stream_in;
+    return MXL_OK;
+}
+
+int mxl_ctx::download_stream(cudaStream_t* s)
+{
+    if (!overlap) { *s = stream; return MXL_OK; }
+    if (out_must_wait) { MXL_CUDA(cudaStreamWaitEvent(stream_out, ev_compute, 0)); out_must_wait = false; }
+    out_dirty = true;
+    *s = stream_out;
+    return MXL_OK;
+}
+
+int mxl_ctx::compute_begin()
+{
+    if (!overlap) return MXL_OK;
+    if (in_dirty) {
+        MXL_CUDA(cudaEventRecord(ev_in, stream_in));
+        MXL_CUDA(cudaStreamWaitEvent(stream, ev_in, 0));
+        in_dirty = false;
+    }
+    if (out_dirty) {
+        MXL_CUDA(cudaEventRecord(ev_out, stream_out));
+        MXL_CUDA(cudaStreamWaitEvent(stream, ev_out, 0));
+        out_dirty = false;
+    }
+    return MXL_OK;
+}
+
+int mxl_ctx::compute_end()
+{
+    if (!overlap) return MXL_OK;
+    MXL_CUDA(cudaEventRecord(ev_compute, stream));
+    in_must_wait = out_must_wait = true;
     return MXL_OK;
 }
 
@@ -266,6 +312,10 @@ int mxl_ctx_destroy(mxl_ctx* ctx)
             for (uint8_t* p : kv.second) cudaFree(p);
         if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
         if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+        if (ctx->stream_in) { cudaStreamSynchronize(ctx->stream_in); cudaStreamDestroy(ctx->stream_in); }
+        if (ctx->stream_out) { cudaStreamSynchronize(ctx->stream_out); cudaStreamDestroy(ctx->stream_out); }
+        for (cudaEvent_t e : {ctx->ev_in, ctx->ev_out, ctx->ev_compute, ctx->fences[0], ctx->fences[1], ctx->fences[2], ctx->fences[3]})
+            if (e) cudaEventDestroy(e);
         if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     }
     delete ctx;
@@ -277,8 +327,51 @@ int mxl_ctx_synchronize(mxl_ctx* ctx)
     if (!ctx) MXL_FAIL(MXL_ERR_INVALID, "NULL context");
     MXL_TRY(ctx->activate());
     MXL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->stream_in) MXL_CUDA(cudaStreamSynchronize(ctx->stream_in));
+    if (ctx->stream_out) MXL_CUDA(cudaStreamSynchronize(ctx->stream_out));
     return MXL_OK;
 }
+
+int mxl_ctx_set_copy_overlap(mxl_ctx* ctx, int enabled)
+{
+    if (!ctx) MXL_FAIL(MXL_ERR_INVALID, "NULL context");
+    if (!ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "mxl_ctx_set_copy_overlap: context has no CUDA device");
+    MXL_TRY(mxl_ctx_synchronize(ctx));
+    if (enabled && !ctx->stream_in) {
+        MXL_CUDA(cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking));
+        MXL_CUDA(cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking));
+        MXL_CUDA(cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming));
+        MXL_CUDA(cudaEventCreateWithFlags(&ctx->ev_out, cudaEventDisableTiming));
+        MXL_CUDA(cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
+        for (auto& f : ctx->fences) MXL_CUDA(cudaEventCreateWithFlags(&f, cudaEventDisableTiming));
+    }
+    ctx->overlap = enabled != 0;
+    ctx->in_dirty = ctx->out_dirty = ctx->in_must_wait = ctx->out_must_wait = false;
+    return MXL_OK;
+}
+
+int mxl_ctx_download_fence(mxl_ctx* ctx, uint32_t slot)
+{
+    if (!ctx || slot >= 4) MXL_FAIL(MXL_ERR_INVALID, "bad fence slot");
+    if (!ctx->overlap) MXL_FAIL(MXL_ERR_INVALID, "fences need copy overlap enabled");
+    MXL_TRY(ctx->activate());
+    cudaStream_t s;
+    MXL_TRY(ctx->download_stream(&s));
+    MXL_CUDA(cudaEventRecord(ctx->fences[slot], s));
+    return MXL_OK;
+}
+
+int mxl_ctx_wait_fence(mxl_ctx* ctx, uint32_t slot)
+{
+    if (!ctx || slot >= 4) MXL_FAIL(MXL_ERR_INVALID, "bad fence slot");
+    if (!ctx->overlap) MXL_FAIL(MXL_ERR_INVALID, "fences need copy overlap enabled");
+    MXL_TRY(ctx->activate());
+    MXL_CUDA(cudaEventSynchronize(ctx->fences[slot]));
+    return MXL_OK;
+}
+
+uint64_t mxl_ctx_h2d_bytes(const mxl_ctx* ctx) { return ctx ? ctx->h2d_bytes : 0; }
+uint64_t mxl_ctx_d2h_bytes(const mxl_ctx* ctx) { return ctx ? ctx->d2h_bytes : 0; }
 
 void* mxl_ctx_stream(mxl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint32_t mxl_ctx_sample_rate(const mxl_ctx* ctx) { return ctx ? ctx->sample_rate : 0; }
@@ -368,7 +461,11 @@ static int audio_line(const mxl_line* line, uint64_t n, const char* what)
 int mxl_line_zero(mxl_line* line)
 {
     MXL_TRY(audio_line(line, 0, "mxl_line_zero"));
-    if (line->len()) MXL_CUDA(cudaMemsetAsync(line->dev, 0, line->len() * sizeof(float), line->ctx->stream));
+    if (line->len()) {
+        MXL_TRY(line->ctx->compute_begin());
+        MXL_CUDA(cudaMemsetAsync(line->dev, 0, line->len() * sizeof(float), line->ctx->stream));
+        MXL_TRY(line->ctx->compute_end());
+    }
     return MXL_OK;
 }
 
@@ -376,7 +473,12 @@ int mxl_line_upload_async(mxl_line* line, const float* host, uint64_t n)
 {
     MXL_TRY(audio_line(line, n, "mxl_line_upload"));
     if (n && !host) MXL_FAIL(MXL_ERR_INVALID, "mxl_line_upload: NULL host pointer");
-    if (n) MXL_CUDA(cudaMemcpyAsync(line->dev, host, n * sizeof(float), cudaMemcpyHostToDevice, line->ctx->stream));
+    if (n) {
+        cudaStream_t st;
+        MXL_TRY(line->ctx->upload_stream(&st));
+        MXL_CUDA(cudaMemcpyAsync(line->dev, host, n * sizeof(float), cudaMemcpyHostToDevice, st));
+        line->ctx->h2d_bytes += n * sizeof(float);
+    }
     return MXL_OK;
 }
 
@@ -384,22 +486,25 @@ int mxl_line_download_async(const mxl_line* line, float* host, uint64_t n)
 {
     MXL_TRY(audio_line(line, n, "mxl_line_download"));
     if (n && !host) MXL_FAIL(MXL_ERR_INVALID, "mxl_line_download: NULL host pointer");
-    if (n) MXL_CUDA(cudaMemcpyAsync(host, line->dev, n * sizeof(float), cudaMemcpyDeviceToHost, line->ctx->stream));
+    if (n) {
+        cudaStream_t st;
+        MXL_TRY(line->ctx->download_stream(&st));
+        MXL_CUDA(cudaMemcpyAsync(host, line->dev, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        line->ctx->d2h_bytes += n * sizeof(float);
+    }
     return MXL_OK;
 }
 
 int mxl_line_upload(mxl_line* line, const float* host, uint64_t n)
 {
     MXL_TRY(mxl_line_upload_async(line, host, n));
-    MXL_CUDA(cudaStreamSynchronize(line->ctx->stream));
-    return MXL_OK;
+    return mxl_ctx_synchronize(line->ctx);
 }
 
 int mxl_line_download(const mxl_line* line, float* host, uint64_t n)
 {
     MXL_TRY(mxl_line_download_async(line, host, n));
-    MXL_CUDA(cudaStreamSynchronize(line->ctx->stream));
-    return MXL_OK;
+    return mxl_ctx_synchronize(line->ctx);
 }
 
 // ---- frames --------------------------------------------------------------------------------------
@@ -453,7 +558,9 @@ mxl_frame* mxl_frame_blank(mxl_ctx* ctx, uint32_t width, uint32_t height)
 {
     mxl_frame* f = frame_alloc(ctx, width, height);
     if (!f) return nullptr;
+    ctx->compute_begin();
     if (k::launch_blank(ctx, f->layout, f->dev) != MXL_OK) { frame_release(f); return nullptr; }
+    ctx->compute_end();
     return f;
 }
 
@@ -473,18 +580,19 @@ static int frame_copy_planes(const mxl_frame* f, uint8_t* const host[3], const u
 {
     if (!f || !host || !strides) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
     MXL_TRY(f->ctx->activate());
+    cudaStream_t st;
+    if (upload) MXL_TRY(f->ctx->upload_stream(&st)); else MXL_TRY(f->ctx->download_stream(&st));
     for (int p = 0; p < 3; p++) {
         uint32_t w = p == 0 ? f->layout.width : (f->layout.width + 1) / 2;
         if (!host[p] || strides[p] < w) MXL_FAIL(MXL_ERR_INVALID, "plane %d: NULL pointer or stride %u < width %u", p, strides[p], w);
         if (upload)
             MXL_CUDA(cudaMemcpy2DAsync(f->dev + f->layout.offset[p], f->layout.stride[p], host[p], strides[p], w,
-                                       f->layout.plane_h[p], cudaMemcpyHostToDevice, f->ctx->stream));
+                                       f->layout.plane_h[p], cudaMemcpyHostToDevice, st));
         else
             MXL_CUDA(cudaMemcpy2DAsync(host[p], strides[p], f->dev + f->layout.offset[p], f->layout.stride[p], w,
-                                       f->layout.plane_h[p], cudaMemcpyDeviceToHost, f->ctx->stream));
+                                       f->layout.plane_h[p], cudaMemcpyDeviceToHost, st));
     }
-    MXL_CUDA(cudaStreamSynchronize(f->ctx->stream));
-    return MXL_OK;
+    return mxl_ctx_synchronize(f->ctx);
 }
 
 int mxl_frame_upload(mxl_frame* frame, const uint8_t* const planes[3], const uint32_t strides[3])
@@ -502,7 +610,10 @@ int mxl_frame_upload_raw_async(mxl_frame* frame, const uint8_t* host, uint64_t s
     if (!frame || !host) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
     if (size != frame->layout.size) MXL_FAIL(MXL_ERR_LENGTH, "raw size %llu != frame size %llu", (unsigned long long)size, (unsigned long long)frame->layout.size);
     MXL_TRY(frame->ctx->activate());
-    MXL_CUDA(cudaMemcpyAsync(frame->dev, host, size, cudaMemcpyHostToDevice, frame->ctx->stream));
+    cudaStream_t st;
+    MXL_TRY(frame->ctx->upload_stream(&st));
+    MXL_CUDA(cudaMemcpyAsync(frame->dev, host, size, cudaMemcpyHostToDevice, st));
+    frame->ctx->h2d_bytes += size;
     return MXL_OK;
 }
 
@@ -511,22 +622,23 @@ int mxl_frame_download_raw_async(const mxl_frame* frame, uint8_t* host, uint64_t
     if (!frame || !host) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
     if (size != frame->layout.size) MXL_FAIL(MXL_ERR_LENGTH, "raw size %llu != frame size %llu", (unsigned long long)size, (unsigned long long)frame->layout.size);
     MXL_TRY(frame->ctx->activate());
-    MXL_CUDA(cudaMemcpyAsync(host, frame->dev, size, cudaMemcpyDeviceToHost, frame->ctx->stream));
+    cudaStream_t st;
+    MXL_TRY(frame->ctx->download_stream(&st));
+    MXL_CUDA(cudaMemcpyAsync(host, frame->dev, size, cudaMemcpyDeviceToHost, st));
+    frame->ctx->d2h_bytes += size;
     return MXL_OK;
 }
 
 int mxl_frame_upload_raw(mxl_frame* frame, const uint8_t* host, uint64_t size)
 {
     MXL_TRY(mxl_frame_upload_raw_async(frame, host, size));
-    MXL_CUDA(cudaStreamSynchronize(frame->ctx->stream));
-    return MXL_OK;
+    return mxl_ctx_synchronize(frame->ctx);
 }
 
 int mxl_frame_download_raw(const mxl_frame* frame, uint8_t* host, uint64_t size)
 {
     MXL_TRY(mxl_frame_download_raw_async(frame, host, size));
-    MXL_CUDA(cudaStreamSynchronize(frame->ctx->stream));
-    return MXL_OK;
+    return mxl_ctx_synchronize(frame->ctx);
 }
 
 // ---- video lines ---------------------------------------------------------------------------------

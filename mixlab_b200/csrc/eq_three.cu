@@ -155,7 +155,201 @@ __global__ void __launch_bounds__(kEqThreads) eq_exact_kernel(const __grid_const
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Single-launch variant.  One CTA of 256 threads owns 256 consecutive chunks of Lc samples of one
+// instance; thread i owns chunk c = blockIdx.x*U - Hc + i, U = 256 - Hc.  The first Hc chunks are a
+// halo re-computed from the previous CTA's range: after Hc chunks the 4-pole cascades have forgotten
+// their start state to below 2^-75, so CTAs never talk to each other.
+//   1. the CTA's 256*Lc input samples are staged coalesced into a padded shared-memory tile
+//      (row stride Lc+1 words: thread-per-row reads are bank-conflict free);
+//   2. every thread runs its chunk from zero state (FMA form) -> z_i;  the chunk that starts the
+//      call runs from the module's stored state instead;
+//   3. inclusive scan of v_i = A v_(i-1) + z_i over the CTA: Hillis-Steele with A^(2^d) through
+//      shared memory;  the start state of chunk i is v_(i-1);
+//   4. the non-halo chunks are re-run from their start state in the reference's exact operation
+//      order, outputs overwrite the tile row and leave with coalesced float4 stores.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tri_apply(const double* A, const double x[4], double y[4])
+{
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c <= r; c++) acc = fma(A[tri(r, c)], x[c], acc);
+        y[r] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(kEqBlockThreads) eq_block_kernel(const __grid_constant__ EqBlockBatch b)
+{
+    extern __shared__ __align__(16) unsigned char eq_smem[];
+    const EqBlockInst& in = b.inst[blockIdx.y];
+    const int tid = threadIdx.x;
+    const uint32_t Lc = b.chunk, row = Lc + 1;
+    float* tile = reinterpret_cast<float*>(eq_smem);                                   // [256][Lc+1]
+    double* xch = reinterpret_cast<double*>(eq_smem + (((size_t)kEqBlockThreads * row * 4 + 15) & ~(size_t)15));   // [256][8]
+    const uint32_t U = kEqBlockThreads - b.halo_chunks;
+    const int64_t c0 = (int64_t)blockIdx.x * U - (int64_t)b.halo_chunks;               // chunk of thread 0
+    const int64_t c = c0 + tid;
+    const bool active = c >= 0 && c < (int64_t)b.n_chunks;
+
+    // ---- 1. stage the inputs ----
+    {
+        const uint32_t vec_per_row = Lc >> 2;
+        const uint32_t total = kEqBlockThreads * vec_per_row;
+        for (uint32_t idx = tid; idx < total; idx += kEqBlockThreads) {
+            const uint32_t i = idx / vec_per_row, j = (idx - i * vec_per_row) << 2;
+            const int64_t ci = c0 + i;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in.in && ci >= 0) {
+                const uint64_t g = (uint64_t)ci * Lc + j;
+                if (g + 4 <= b.frames) v = *reinterpret_cast<const float4*>(in.in + g);
+                else if (g < b.frames) {
+                    v.x = in.in[g];
+                    if (g + 1 < b.frames) v.y = in.in[g + 1];
+                    if (g + 2 < b.frames) v.z = in.in[g + 2];
+                }
+            }
+            float* d = tile + i * row + j;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+    }
+    __syncthreads();
+
+    const double cl = b.c_lo, ch = b.c_hi, al = 1.0 - b.c_lo, ah = 1.0 - b.c_hi;
+    const float* mine = tile + tid * row;
+    const double* st = in.state;
+
+    // ---- 2. zero-state (or stored-state, for the chunk that starts the call) run ----
+    double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (active) {
+        if (c == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) v[q] = st[q];
+        }
+        double l0 = v[0], l1 = v[1], l2 = v[2], l3 = v[3], h0 = v[4], h1 = v[5], h2 = v[6], h3 = v[7];
+        for (uint32_t j = 0; j < Lc; j++) {
+            const double s = (double)mine[j];
+            l0 = fma(al, l0, fma(cl, s, kVsa));
+            l1 = fma(cl, l0 - l1, l1);
+            l2 = fma(cl, l1 - l2, l2);
+            l3 = fma(cl, l2 - l3, l3);
+            h0 = fma(ah, h0, fma(ch, s, kVsa));
+            h1 = fma(ch, h0 - h1, h1);
+            h2 = fma(ch, h1 - h2, h2);
+            h3 = fma(ch, h2 - h3, h3);
+        }
+        v[0] = l0; v[1] = l1; v[2] = l2; v[3] = l3; v[4] = h0; v[5] = h1; v[6] = h2; v[7] = h3;
+    }
+
+    // ---- 3. inclusive scan over the CTA: Hillis-Steele, v_i += A^(2^d) v_(i - 2^d) ----
+    // (the partner's value must cover exactly the 2^d chunks before mine, so every step crosses warp
+    // boundaries: all steps go through shared memory)
+#pragma unroll
+    for (int d = 0; d < kEqBlockLevels; d++) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) xch[tid * 8 + q] = v[q];
+        __syncthreads();
+        if (tid >= (1 << d)) {
+            double o[8], yl[4], yh[4];
+#pragma unroll
+            for (int q = 0; q < 8; q++) o[q] = xch[(tid - (1 << d)) * 8 + q];
+            tri_apply(b.pow_lo[d], o, yl);
+            tri_apply(b.pow_hi[d], o + 4, yh);
+#pragma unroll
+            for (int q = 0; q < 4; q++) { v[q] += yl[q]; v[4 + q] += yh[q]; }
+        }
+        __syncthreads();
+    }
+    // start state of my chunk = inclusive result of the previous thread
+#pragma unroll
+    for (int q = 0; q < 8; q++) xch[tid * 8 + q] = v[q];
+    __syncthreads();
+
+    // ---- 4. exact re-run of the chunks this CTA owns ----
+    const bool owner = active && (tid >= (int)b.halo_chunks || blockIdx.x == 0);
+    EqRegs r{};
+    uint32_t count = 0;
+    if (owner) {
+        if (c == 0) {
+            r.l0 = st[0]; r.l1 = st[1]; r.l2 = st[2]; r.l3 = st[3];
+            r.h0 = st[4]; r.h1 = st[5]; r.h2 = st[6]; r.h3 = st[7];
+            r.x0 = st[8]; r.x1 = st[9]; r.x2 = st[10];
+        } else {
+            const double* p = xch + (tid - 1) * 8;       // tid >= 1 here: c > 0 and c0 + 0 >= 0 for blockIdx.x > 0 halo
+            r.l0 = p[0]; r.l1 = p[1]; r.l2 = p[2]; r.l3 = p[3];
+            r.h0 = p[4]; r.h1 = p[5]; r.h2 = p[6]; r.h3 = p[7];
+            // history = the three inputs before this chunk
+            double hist[3];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int64_t idx = c * (int64_t)Lc - 3 + j;       // absolute sample index, may precede the call
+                if (idx >= 0) {
+                    const int64_t rel = idx - c0 * (int64_t)Lc;    // position inside the tile
+                    hist[j] = (double)tile[(rel / Lc) * row + (rel % Lc)];
+                } else {
+                    hist[j] = st[8 + 3 + idx];
+                }
+            }
+            r.x0 = hist[0]; r.x1 = hist[1]; r.x2 = hist[2];
+        }
+        const uint64_t s0 = (uint64_t)c * Lc;
+        count = (uint32_t)((s0 + Lc <= b.frames) ? Lc : (b.frames - s0));
+    }
+    __syncthreads();                                     // every history read precedes any overwrite
+    if (owner) {
+        float* wr = tile + tid * row;
+        const double g_lo = in.g_lo, g_mid = in.g_mid, g_hi = in.g_hi;
+        for (uint32_t j = 0; j < count; j++) wr[j] = eq_step(r, wr[j], cl, ch, g_lo, g_mid, g_hi);
+        if (c + 1 == (int64_t)b.n_chunks) {              // state after this call
+            double* so = in.state_out;
+            so[0] = r.l0; so[1] = r.l1; so[2] = r.l2; so[3] = r.l3;
+            so[4] = r.h0; so[5] = r.h1; so[6] = r.h2; so[7] = r.h3;
+            so[8] = r.x0; so[9] = r.x1; so[10] = r.x2;
+        }
+    }
+    __syncthreads();
+
+    // ---- coalesced store of the owned rows ----
+    {
+        const uint32_t first = b.halo_chunks;            // tile rows below Hc are halo (or precede the call)
+        const uint32_t vec_per_row = Lc >> 2;
+        const uint32_t total = (kEqBlockThreads - first) * vec_per_row;
+        for (uint32_t idx = tid; idx < total; idx += kEqBlockThreads) {
+            const uint32_t i = first + idx / vec_per_row, j = (idx % vec_per_row) << 2;
+            const int64_t ci = c0 + i;
+            if (ci < 0 || ci >= (int64_t)b.n_chunks) continue;
+            const uint64_t g = (uint64_t)ci * Lc + j;
+            const float* sp = tile + i * row + j;
+            if (g + 4 <= b.frames) *reinterpret_cast<float4*>(in.out + g) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+            else for (uint32_t q = 0; q < 4 && g + q < b.frames; q++) in.out[g + q] = sp[q];
+        }
+    }
+}
+
 }  // namespace
+
+int launch_eq_three_block(mxl_ctx* ctx, const EqBlockBatch& b)
+{
+    if (!ctx || !ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "no CUDA device bound to this context");
+    MXL_TRY(ctx->activate());
+    if (b.n <= 0 || b.frames == 0) return MXL_OK;
+    if (b.chunk == 0 || (b.chunk & 3) || b.chunk > kEqBlockMaxChunk || b.halo_chunks == 0 || b.halo_chunks > kEqBlockThreads / 2)
+        MXL_FAIL(MXL_ERR_INVALID, "eq_block_kernel: bad plan (chunk %u, halo %u)", b.chunk, b.halo_chunks);
+    const size_t tile_bytes = ((size_t)kEqBlockThreads * (b.chunk + 1) * sizeof(float) + 15) & ~(size_t)15;
+    const size_t smem = tile_bytes + (size_t)kEqBlockThreads * 8 * sizeof(double);
+    if (smem > 48 * 1024 && smem > ctx->eq_block_smem) {
+        MXL_CUDA(cudaFuncSetAttribute(eq_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->eq_block_smem = smem;
+    }
+    const uint32_t U = kEqBlockThreads - b.halo_chunks;
+    dim3 grid((b.n_chunks + U - 1) / U, b.n);
+    eq_block_kernel<<<grid, kEqBlockThreads, smem, ctx->stream>>>(b);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) MXL_FAIL(MXL_ERR_CUDA, "launch of eq_block_kernel failed: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    return MXL_OK;
+}
 
 int launch_eq_three(mxl_ctx* ctx, const EqBatch& b)
 {

@@ -285,6 +285,8 @@ int mxl_graph_run_ticks(mxl_graph* g, uint64_t tick0, uint32_t n_ticks)
                      (unsigned long long)l->frames, (unsigned long long)(l->type == MXL_LINE_VIDEO ? (uint64_t)n_ticks : frames));
     }
 
+    MXL_TRY(ctx->compute_begin());
+    struct EndGuard { mxl_ctx* c; ~EndGuard() { c->compute_end(); } } end_guard{ctx};
     std::vector<mxl_module*> mods;
     std::vector<IoSet> ios;
     std::vector<const mxl_line*> in_ptrs;

@@ -86,6 +86,29 @@ struct EqBatch {
 };
 int launch_eq_three(mxl_ctx* ctx, const EqBatch& b);
 
+// Single-launch variant (eq_three.cu: eq_block_kernel): one CTA = 256 consecutive chunks of one
+// instance, the first `halo_chunks` of which only warm the pole state up.
+constexpr int kEqBlockThreads = 256;
+constexpr int kEqBlockLevels = 8;    // log2(kEqBlockThreads): A^(2^d) for the in-block scan
+constexpr uint32_t kEqBlockMaxChunk = 128;
+struct EqBlockInst {
+    const float* in; float* out;
+    const double* state; double* state_out;
+    double g_lo, g_mid, g_hi;
+};
+struct EqBlockBatch {
+    uint64_t frames;
+    uint32_t chunk;                  // Lc, multiple of 4, <= kEqBlockMaxChunk
+    uint32_t halo_chunks;            // Hc: |A^Hc| < 2^-75
+    uint32_t n_chunks;
+    int32_t n;
+    double c_lo, c_hi;
+    double pow_lo[kEqBlockLevels][10];   // A^(2^d), A = M^Lc, packed lower-triangular
+    double pow_hi[kEqBlockLevels][10];
+    EqBlockInst inst[kMaxBatch];
+};
+int launch_eq_three_block(mxl_ctx* ctx, const EqBlockBatch& b);
+
 // ---- Envelope (src/module/envelope.rs:91-120) ----
 struct EnvState { int32_t state; int32_t _pad; uint64_t seq; double off_amplitude; };
 struct EnvLaunch {

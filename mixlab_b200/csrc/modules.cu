@@ -648,6 +648,84 @@ static uint32_t eq_pick_chunk(const mxl_ctx* ctx, uint64_t frames, int n_inst)
     return chunk;
 }
 
+// Plan of the single-launch kernel for chunk length Lc: halo length Hc (chunks until the cascades have
+// forgotten their start state, |A^Hc| < 2^-75) and A^(2^d), d = 0..7.  Empty plan = Hc too long for Lc.
+static const std::vector<double>& eq_block_plan_for(mxl_ctx* ctx, uint32_t Lc)
+{
+    auto it = ctx->eq_block_plans.find(Lc);
+    if (it != ctx->eq_block_plans.end()) return it->second;
+    const EqCoefs co = eq_coefs(ctx);
+    double Al[4][4], Ah[4][4], Pl[4][4], Ph[4][4], T[4][4];
+    cascade_power(co.c_lo, Lc, Al);
+    cascade_power(co.c_hi, Lc, Ah);
+    memcpy(Pl, Al, sizeof Pl); memcpy(Ph, Ah, sizeof Ph);
+    const double tiny = ldexp(1.0, -75);
+    uint32_t Hc = 1;
+    while ((absmax4(Pl) >= tiny || absmax4(Ph) >= tiny) && Hc <= 64) {
+        matmul4(Pl, Al, T); memcpy(Pl, T, sizeof T);
+        matmul4(Ph, Ah, T); memcpy(Ph, T, sizeof T);
+        Hc++;
+    }
+    std::vector<double> plan;
+    if (Hc <= 64) {
+        plan.assign(1 + 2 * k::kEqBlockLevels * 10, 0.0);
+        plan[0] = (double)Hc;
+        memcpy(Pl, Al, sizeof Pl); memcpy(Ph, Ah, sizeof Ph);
+        for (int d = 0; d < k::kEqBlockLevels; d++) {
+            pack_tri(Pl, &plan[1 + d * 10]);
+            pack_tri(Ph, &plan[1 + k::kEqBlockLevels * 10 + d * 10]);
+            matmul4(Pl, Pl, T); memcpy(Pl, T, sizeof T);
+            matmul4(Ph, Ph, T); memcpy(Ph, T, sizeof T);
+        }
+    }
+    return ctx->eq_block_plans[Lc] = plan;
+}
+
+// Single-launch path (eq_block_kernel).  Returns 1 if it ran, 0 if no usable plan exists.
+static int run_eq_block(mxl_ctx* ctx, mxl_module* const* mods, const IoSet* io, int first, int cnt, uint64_t frames, uint64_t* bytes)
+{
+    uint32_t forced = 0;
+    if (const char* e = getenv("MXL_EQ_BLOCK_CHUNK")) forced = (uint32_t)atol(e) / 4 * 4;
+    const std::vector<double>* plan = nullptr;
+    uint32_t Lc = 0;
+    for (uint32_t cand : {32u, 64u, 128u}) {
+        if (forced && cand != forced) continue;
+        const std::vector<double>& p = eq_block_plan_for(ctx, cand);
+        if (!p.empty()) { plan = &p; Lc = cand; break; }
+    }
+    if (forced && !plan && forced >= 4 && forced <= k::kEqBlockMaxChunk) {
+        const std::vector<double>& p = eq_block_plan_for(ctx, forced);
+        if (!p.empty()) { plan = &p; Lc = forced; }
+    }
+    if (!plan) return 0;
+    k::EqBlockBatch b{};
+    b.frames = frames;
+    b.chunk = Lc;
+    b.halo_chunks = (uint32_t)(*plan)[0];
+    b.n_chunks = (uint32_t)((frames + Lc - 1) / Lc);
+    b.n = cnt;
+    const EqCoefs co = eq_coefs(ctx);
+    b.c_lo = co.c_lo; b.c_hi = co.c_hi;
+    memcpy(b.pow_lo, &(*plan)[1], sizeof b.pow_lo);
+    memcpy(b.pow_hi, &(*plan)[1 + k::kEqBlockLevels * 10], sizeof b.pow_hi);
+    for (int j = 0; j < cnt; j++) {
+        EqThree* m = (EqThree*)mods[first + j];
+        MXL_TRY(m->ensure_state());
+        k::EqBlockInst& e = b.inst[j];
+        e.in = io[first + j].in[0] ? io[first + j].in[0]->dev : nullptr;
+        e.out = io[first + j].out[0]->dev;
+        e.state = m->state_ptr(m->cur);
+        e.state_out = m->state_ptr(m->cur ^ 1);
+        e.g_lo = db_to_linear(m->p.gain_lo_db);            // eq_three.rs:62-64
+        e.g_mid = db_to_linear(m->p.gain_mid_db);
+        e.g_hi = db_to_linear(m->p.gain_hi_db);
+        if (bytes) *bytes += (io[first + j].in[0] ? 4 * frames : 0) + 4 * frames;
+    }
+    MXL_TRY(k::launch_eq_three_block(ctx, b));
+    for (int j = 0; j < cnt; j++) ((EqThree*)mods[first + j])->cur ^= 1;
+    return 1;
+}
+
 static int run_eq_threes(mxl_ctx* ctx, mxl_module* const* mods, int n, const IoSet* io, uint64_t* bytes)
 {
     int i = 0;
@@ -666,7 +744,12 @@ static int run_eq_threes(mxl_ctx* ctx, mxl_module* const* mods, int n, const IoS
             frames = f;
         }
         if (frames == 0) continue;
-        if (frames >= (1ull << 40)) MXL_FAIL(MXL_ERR_LENGTH, "EqThree: call too long");
+        if (frames >= (1ull << 36)) MXL_FAIL(MXL_ERR_LENGTH, "EqThree: call too long");
+        if (!getenv("MXL_EQ_CHUNK")) {                     // MXL_EQ_CHUNK selects the two-launch path
+            const int ran = run_eq_block(ctx, mods, io, first, cnt, frames, bytes);
+            if (ran < 0) return ran;
+            if (ran == 1) continue;
+        }
         uint32_t chunk = eq_pick_chunk(ctx, frames, cnt);
         const std::vector<double>& plan = eq_plan_for(ctx, &chunk);
         k::EqBatch b{};
@@ -1102,6 +1185,21 @@ int meter_read(mxl_module* m, uint32_t slot, float peak[2], double sumsq[2], int
     return MXL_OK;
 }
 
+int meter_download_async(mxl_module* m, mxl_meter_record* records, uint32_t cap)
+{
+    if (!m || m->kind != MXL_MOD_METER) MXL_FAIL(MXL_ERR_PARAMS, "not a Meter module");
+    Meter* me = (Meter*)m;
+    const uint32_t n = std::min(cap, me->n_slots);
+    if (n == 0) return 0;
+    if (!records) MXL_FAIL(MXL_ERR_INVALID, "NULL records");
+    MXL_TRY(m->ctx->activate());
+    cudaStream_t st;
+    MXL_TRY(m->ctx->download_stream(&st));
+    MXL_CUDA(cudaMemcpyAsync(records, me->records.p, (size_t)n * sizeof(k::MeterRecord), cudaMemcpyDeviceToHost, st));
+    m->ctx->d2h_bytes += (size_t)n * sizeof(k::MeterRecord);
+    return (int)n;
+}
+
 int meter_download(mxl_module* m, mxl_meter_record* records, uint32_t cap)
 {
     static_assert(sizeof(mxl_meter_record) == sizeof(k::MeterRecord), "ABI record mirrors the kernel's");
@@ -1110,9 +1208,9 @@ int meter_download(mxl_module* m, mxl_meter_record* records, uint32_t cap)
     const uint32_t n = std::min(cap, me->n_slots);
     if (n == 0) return 0;
     if (!records) MXL_FAIL(MXL_ERR_INVALID, "NULL records");
-    MXL_TRY(m->ctx->activate());
-    MXL_CUDA(cudaMemcpyAsync(records, me->records.p, (size_t)n * sizeof(k::MeterRecord), cudaMemcpyDeviceToHost, m->ctx->stream));
-    MXL_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    const int got = meter_download_async(m, records, cap);
+    if (got < 0) return got;
+    MXL_TRY(mxl_ctx_synchronize(m->ctx));
     return (int)n;
 }
 

@@ -57,6 +57,7 @@ int eq_three_state(mxl_module* m, double state[11]);
 int envelope_state(mxl_module* m, int32_t* state, uint64_t* seq, double* off_amplitude);
 int meter_read(mxl_module* m, uint32_t slot, float peak[2], double sumsq[2], int32_t* clip);
 int meter_download(mxl_module* m, mxl_meter_record* records, uint32_t cap);
+int meter_download_async(mxl_module* m, mxl_meter_record* records, uint32_t cap);
 int plotter_read(mxl_module* m, float* left, float* right, uint32_t cap);
 int source_set_line(mxl_module* m, mxl_line* line);
 mxl_line* source_line(mxl_module* m);

@@ -71,6 +71,7 @@ class AVSession:
             self.host_a = self._pin(self.T * self.frame_bytes)
             self.host_b = self._pin(self.T * self.frame_bytes)
             self.host_out = self._pin(self.T * self.frame_bytes)
+            self.host_out2 = None          # second result buffer, allocated by enable_pipelining()
             ua = [W.random_bytes(seed + 17 * i, self.frame_bytes) for i in range(unique_frames)]
             ub = [W.random_bytes(seed + 0xB0B + 31 * i, self.frame_bytes) for i in range(unique_frames)]
             va = self.host_a.array.reshape(self.T, self.frame_bytes)
@@ -82,6 +83,7 @@ class AVSession:
             self.host_master = self._pin(self.T * ctx.spt * 2 * 4, np.float32)
         self.meter_records = np.zeros(self.T, api.METER_RECORD)
         self._L = api.lib()
+        self._pipelined = False
 
     def _pin(self, nbytes, dtype=np.uint8):
         p = api.PinnedBuffer(nbytes, dtype)
@@ -142,6 +144,50 @@ class AVSession:
         self.upload_inputs()
         self.run_step(tick0)
         self.download_outputs()
+
+    # ---- pipelined host-fed steps (copy/compute overlap, double-buffered results) -------------
+    def enable_pipelining(self):
+        """Uploads, ticks and downloads of consecutive steps overlap (mxl_ctx_set_copy_overlap); results
+        alternate between two pinned buffers so the consumer of step k reads while step k+1 runs."""
+        if self._pipelined:
+            return
+        self.ctx.set_copy_overlap(True)
+        self._out = [self.host_out if self.video else None, self._pin(self.T * self.frame_bytes) if self.video else None]
+        if self.master is not None:
+            self._master = [self.host_master, self._pin(self.T * self.ctx.spt * 2 * 4, np.float32)]
+        self._meter = [self._pin(self.T * api.METER_RECORD.itemsize), self._pin(self.T * api.METER_RECORD.itemsize)]
+        self._pipelined = True
+
+    def enqueue_step_host(self, tick0, slot):
+        """Host-fed step without host synchronisation: upload -> T ticks -> download into result buffer
+        `slot` (0/1), then a download fence on `slot`.  wait_step(slot) blocks until its results landed."""
+        L, fb = self._L, self.frame_bytes
+        self.upload_inputs()
+        self.run_step(tick0)
+        if self.video:
+            out = L.mxl_graph_output(self.graph.h, self.vmix, 0)
+            po = self._out[slot].ptr
+            for k in range(self.T):
+                fr = L.mxl_video_line_get(out, k)
+                api.check(L.mxl_frame_download_raw_async(fr, po + k * fb, fb))
+        if self.master is not None:
+            line = L.mxl_graph_output(self.graph.h, self.ids[self.master[0]], self.master[1])
+            api.check(L.mxl_line_download_async(line, self._master[slot].ptr, self.T * self.ctx.spt * 2))
+        if self.meter is not None:
+            api.check(L.mxl_meter_download_async(self.graph.module(self.ids[self.meter[0]]).h, self._meter[slot].ptr, self.T))
+        self.ctx.download_fence(slot)
+
+    def wait_step(self, slot):
+        self.ctx.wait_fence(slot)
+
+    def result_frames(self, slot):
+        return self._out[slot].array.reshape(self.T, self.frame_bytes)
+
+    def result_master(self, slot):
+        return self._master[slot].array
+
+    def result_meter(self, slot):
+        return self._meter[slot].array.view(api.METER_RECORD)
 
     def output_frame(self, k):
         out = self.graph.output(self.vmix, 0)

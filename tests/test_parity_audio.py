@@ -86,12 +86,15 @@ def test_amplifier_update_and_extreme_params(mxl, oracle, ctx48):
 
 
 # ---- EqThree (eq_three.rs:58-89,106-125) ------------------------------------------------------
-@pytest.mark.parametrize("chunk", ["auto", "64", "256", "1024", "4096"])
+@pytest.mark.parametrize("chunk", ["auto", "b16", "b32", "b64", "b128", "64", "256", "1024", "4096"])
 def test_eq_three_golden(mxl, ctx44, chunk, monkeypatch):
-    """The reference's own golden vector (eq_three.rs:150-167), one run_tick over 355 285 samples."""
-    if chunk == "auto":
-        monkeypatch.delenv("MXL_EQ_CHUNK", raising=False)
-    else:
+    """The reference's own golden vector (eq_three.rs:150-167), one run_tick over 355 285 samples.
+    "auto"/"bN": the single-launch kernel (chunk N); plain numbers: the two-launch kernel."""
+    monkeypatch.delenv("MXL_EQ_CHUNK", raising=False)
+    monkeypatch.delenv("MXL_EQ_BLOCK_CHUNK", raising=False)
+    if chunk.startswith("b"):
+        monkeypatch.setenv("MXL_EQ_BLOCK_CHUNK", chunk[1:])
+    elif chunk != "auto":
         monkeypatch.setenv("MXL_EQ_CHUNK", chunk)
     x = load_f32(os.path.join(GOLDEN, "eq_three", "chronos.f32.raw"))
     want = load_f32(os.path.join(GOLDEN, "eq_three", "chronos-eq.f32.raw"))
@@ -126,7 +129,7 @@ def test_eq_three_state_carries_across_calls(mxl, oracle, ctx44, split):
     assert np.array_equal(st[8:], ref[8:])
 
 
-@pytest.mark.parametrize("frames", [1, 2, 3, 5, 255, 257, 800, 65536 + 3])
+@pytest.mark.parametrize("frames", [1, 2, 3, 5, 31, 33, 255, 257, 800, 7071, 7072, 7073, 65536 + 3, 1 << 20])
 @pytest.mark.parametrize("gains", [(-6.0, 0.0, 4.0), (0.0, 0.0, 0.0), (6.0, -24.0, 3.0)])
 def test_eq_three_random(mxl, oracle, ctx48, frames, gains):
     x = W.uniform_pm1(300 + frames, frames)
@@ -135,6 +138,43 @@ def test_eq_three_random(mxl, oracle, ctx48, frames, gains):
     out = ctx48.line(mxl.LINE_MONO, frames)
     mod.run_tick(0, [ctx48.mono(x)], [out])
     assert mismatch_count(out.download(), want) == 0
+
+
+@pytest.mark.parametrize("sr_spt", [(22050, 368), (96000, 1600), (192000, 3200)])
+def test_eq_three_other_sample_rates(mxl, oracle, sr_spt):
+    """The chunk/halo plan follows the pole decay at the context's sample rate."""
+    sr, spt = sr_spt
+    x = W.uniform_pm1(sr, 200000)
+    want = oracle.EqThree(float(sr)).run((4.0, -3.0, 2.0), x)
+    with mxl.Context(0, sr, spt) as ctx:
+        mod = ctx.module(mxl.MOD_EQ_THREE, (4.0, -3.0, 2.0))
+        out = ctx.line(mxl.LINE_MONO, x.size)
+        mod.run_tick(0, [ctx.mono(x)], [out])
+        assert mismatch_count(out.download(), want) == 0
+
+
+def test_eq_three_many_instances_one_launch(mxl, oracle, ctx48):
+    """Ten EqThree modules of a graph level share one launch (blockIdx.y = instance)."""
+    d = W.GraphDesc("eqs")
+    n, spt, ticks = 10, 800, 20
+    srcs, eqs = [], []
+    for k in range(n):
+        s = d.add("SourceMono")
+        e = d.add("EqThree", (k - 5.0, 0.5 * k, -1.0 * k))
+        d.connect(e, 0, s, 0)
+        srcs.append(s); eqs.append(e)
+    g, ids = W.build_graph(ctx48, d)
+    datas = [W.uniform_pm1(900 + k, spt * ticks) for k in range(n)]
+    lines = [ctx48.mono(x) for x in datas]
+    for k in range(n):
+        g.module(ids[srcs[k]]).set_source_line(lines[k])
+    before = ctx48.launch_count
+    g.run_ticks(0, ticks)
+    assert ctx48.launch_count - before == 1
+    for k in range(n):
+        want = oracle.EqThree(48000.0).run((k - 5.0, 0.5 * k, -1.0 * k), datas[k])
+        assert mismatch_count(g.output(ids[eqs[k]], 0).download(), want) == 0
+    g.destroy()
 
 
 def test_eq_three_disconnected_input(mxl, oracle, ctx48):

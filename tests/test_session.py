@@ -1,0 +1,154 @@
+"""Session driver: sharding logic (CPU, incl. a world_size-2 gloo run) and, on the GPU, the host-fed
+step in serial and pipelined (copy/compute overlap) mode against the oracle."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from mixlab_b200 import workloads as W
+from mixlab_b200.session import session_seed, shard_sessions
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_sessions_round_robin():
+    assert shard_sessions(8, 8) == [[i] for i in range(8)]
+    assert shard_sessions(8, 2) == [[0, 2, 4, 6], [1, 3, 5, 7]]
+    assert shard_sessions(3, 4) == [[0], [1], [2], []]
+    assert shard_sessions(0, 2) == [[], []]
+    with pytest.raises(ValueError):
+        shard_sessions(4, 0)
+    seeds = {session_seed(0xA11CE, s) for s in range(64)}
+    assert len(seeds) == 64
+
+
+GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+import torch
+import torch.distributed as dist
+from mixlab_b200.session import shard_sessions, session_seed
+from mixlab_b200 import workloads as W
+from oracle import pyoracle as po
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+mine = shard_sessions(6, world)[rank]
+# every rank runs its own sessions on the CPU oracle (stand-in for its GPU): no data-path exchange
+desc = W.config4_audio_graph()
+sums = []
+for s in mine:
+    g, ids = po.build_graph(desc, 48000, 800)
+    out = g.run_tick(s, (ids[desc.taps["master"][0]], 0), 1600)
+    sums.append(float(np.abs(out).sum()) + session_seed(1, s) % 7)
+# the only collectives: a barrier and the reductions bench.py uses for its report
+dist.barrier()
+t = torch.tensor([float(len(mine)), 1.0 + rank], dtype=torch.float64)
+tot = t.clone(); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+gathered = [None] * world
+dist.all_gather_object(gathered, mine)
+if rank == 0:
+    flat = sorted(x for part in gathered for x in part)
+    assert flat == list(range(6)), flat
+    assert tot[0].item() == 6.0 and mx[1].item() == float(world)
+    print("GLOO_OK", gathered)
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    """world_size 2 on CPU: sessions shard round-robin, ranks exchange nothing but the report reductions."""
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + os.getpid() % 300), str(script), ROOT]
+    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "GLOO_OK [[0, 2, 4], [1, 3, 5]]" in r.stdout
+
+
+def _check_step(oracle, desc, sess, frames, master, meter, tick0, T, spt=800, sr=48000):
+    lay = oracle.frame_layout(sess.width, sess.height)
+    fb = sess.frame_bytes
+    f = oracle.fader_to_u8(sess.fader)
+    for k in range(T):
+        a = sess.host_a.array[k * fb:(k + 1) * fb]
+        b = sess.host_b.array[k * fb:(k + 1) * fb]
+        assert np.array_equal(frames[k], oracle.video_crossfade(lay, a, b, f)), k
+    og, oids = oracle.build_graph(desc, sr, spt)
+    # oscillators are pure functions of t and the EQs are re-run from tick 0 to carry their state
+    want = None
+    for k in range(tick0 + T):
+        buf = og.run_tick(k, (oids[desc.taps["master"][0]], 0), 2 * spt)
+        if k >= tick0:
+            want = buf if want is None else np.concatenate([want, buf])
+    err = np.abs(master.astype(np.float64) - want.astype(np.float64))
+    assert np.all(err <= 1e-6 * np.abs(want) + 1e-6 * np.abs(want).max())
+    pk, sq, clip = og.meter(oids[desc.taps["meter"][0]])
+    assert abs(meter[T - 1]["peak"][0] - pk[0]) <= 1e-6 * pk[0]
+
+
+@pytest.mark.gpu
+def test_host_fed_steps_serial_and_pipelined(mxl, oracle):
+    from mixlab_b200.session import AVSession
+    T = 3
+    desc = W.config2_graph()
+    with mxl.Context(0, 48000, 800) as ctx:
+        sess = AVSession(ctx, desc, T, video=True, width=560, height=350, unique_frames=3)
+        sess.run_step_host(0)
+        _check_step(oracle, desc, sess, sess.host_out.array.reshape(T, sess.frame_bytes), np.array(sess.host_master.array),
+                    sess.meter_records, 0, T)
+        h2d0, d2h0 = ctx.h2d_bytes, ctx.d2h_bytes
+        sess.enable_pipelining()
+        # 4 pipelined steps; inputs change between steps while earlier steps are still in flight
+        for i in range(4):
+            if i == 2:
+                sess.wait_step(0)                 # results of step 0 must be complete and stable
+                keep = np.array(sess.result_frames(0))
+            sess.enqueue_step_host(T * (1 + i), i & 1)
+            if i > 0:
+                sess.wait_step((i - 1) & 1)
+        sess.wait_step(1)
+        ctx.synchronize()
+        assert ctx.h2d_bytes - h2d0 == 4 * sess.h2d_bytes_per_step
+        assert ctx.d2h_bytes - d2h0 == 4 * sess.d2h_bytes_per_step
+        _check_step(oracle, desc, sess, sess.result_frames(1), np.array(sess.result_master(1)), sess.result_meter(1), T * 4, T)
+        _check_step(oracle, desc, sess, sess.result_frames(0), np.array(sess.result_master(0)), sess.result_meter(0), T * 3, T)
+        assert np.array_equal(keep, sess.result_frames(0))     # same inputs every step -> same composite
+        sess.close()
+
+
+@pytest.mark.gpu
+def test_overlap_orders_upload_after_compute(mxl, oracle, ctx48):
+    """WAR hazard: an upload enqueued right after a run must not overwrite inputs the run still reads."""
+    ctx48.set_copy_overlap(True)
+    n = 1 << 22
+    a = W.uniform_pm1(1, n)
+    b = W.uniform_pm1(2, n)
+    pa, pb = mxl.PinnedBuffer(n * 4, np.float32), mxl.PinnedBuffer(n * 4, np.float32)
+    pa.array[:] = a
+    pb.array[:] = b
+    src = ctx48.line(mxl.LINE_STEREO, n // 2)
+    out = ctx48.line(mxl.LINE_STEREO, n // 2)
+    amp = ctx48.module(mxl.MOD_AMPLIFIER, (0.5, 0.0))
+    res = mxl.PinnedBuffer(n * 4, np.float32)
+    L = mxl.lib()
+    for _ in range(5):
+        mxl.check(L.mxl_line_upload_async(src.h, pa.ptr, n))
+        amp.run_tick(0, [src, None], [out])
+        mxl.check(L.mxl_line_upload_async(src.h, pb.ptr, n))       # must wait for the run above
+        mxl.check(L.mxl_line_download_async(out.h, res.ptr, n))
+        ctx48.synchronize()
+        assert np.array_equal(res.array, oracle.amplifier(a, None, 0.5, 0.0))
+        amp.run_tick(0, [src, None], [out])
+        mxl.check(L.mxl_line_download_async(out.h, res.ptr, n))
+        ctx48.synchronize()
+        assert np.array_equal(res.array, oracle.amplifier(b, None, 0.5, 0.0))
+    ctx48.set_copy_overlap(False)
+    for p in (pa, pb, res):
+        p.free()
