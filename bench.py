@@ -336,22 +336,34 @@ def b200_arm(args):
     total_ticks = K * T * dist.world
     value = total_ticks / (ms_max * 1e-3)
 
-    # ---- roofline of the dominant kernel: per-stage CUDA events over the same K steps ----
-    sess.graph.set_profiling(True)
-    stage_ms, stage_bytes, stage_launch = {}, {}, {}
-    for _ in range(K):
-        sess.run_step(tick)
-        tick += T
-        for s in sess.graph.stages():
-            if s["n_launches"] == 0:
-                continue
-            stage_ms.setdefault(s["kind"], []).append(s["last_ms"])
-            stage_bytes[s["kind"]] = s["algorithmic_bytes"]
-            stage_launch[s["kind"]] = s["n_launches"]
-    sess.graph.set_profiling(False)
+    # ---- roofline of the dominant kernel: per-stage CUDA events over the same K steps.  Two passes:
+    # the kernel's own launch duration with the stages serialised on one stream ("ms"), and its
+    # duration in the configuration of the timed region, where the audio stages run beside the
+    # compositor on a second stream ("ms_overlapped") ----
     kind_names = {v: k for k, v in W.KIND.items()}
-    stages = {kind_names[k]: {"ms": statistics.mean(v), "launches": stage_launch[k], "algorithmic_bytes": stage_bytes[k]}
-              for k, v in stage_ms.items()}
+
+    def stage_pass(split):
+        nonlocal tick
+        sess.graph.set_stream_split(split)
+        sess.graph.set_profiling(True)
+        acc, nbytes, nlaunch = {}, {}, {}
+        for _ in range(K):
+            sess.run_step(tick)
+            tick += T
+            for s in sess.graph.stages():
+                if s["n_launches"] == 0:
+                    continue
+                acc.setdefault(s["kind"], []).append(s["last_ms"])
+                nbytes[s["kind"]] = s["algorithmic_bytes"]
+                nlaunch[s["kind"]] = s["n_launches"]
+        sess.graph.set_profiling(False)
+        sess.graph.set_stream_split(True)
+        return {kind_names[k]: {"ms": statistics.mean(v), "launches": nlaunch[k], "algorithmic_bytes": nbytes[k]}
+                for k, v in acc.items()}
+
+    stages = stage_pass(False)
+    for name, st in stage_pass(True).items():
+        stages[name]["ms_overlapped"] = st["ms"]
     peak, peak_src = measured_peak()
     if args.workload in ("av", "video"):
         dom, dom_kernel = "VideoMixer", "crossfade_flat_kernel"
@@ -363,7 +375,10 @@ def b200_arm(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(dom_kernel, T), "kernel": dom_kernel, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": d["algorithmic_bytes"], "avg_launch_ms": d["ms"],
-                "step_share": d["ms"] / sum(s["ms"] for s in stages.values())}
+                "avg_launch_ms_overlapped": d["ms_overlapped"],
+                "step_share": d["ms"] / sum(s["ms"] for s in stages.values()),
+                "timing": "CUDA events around the stage on its launching stream, K steps; 'avg_launch_ms' with all stages "
+                          "serialised on one stream, '_overlapped' as in the timed region (audio stages on a second stream)"}
     whole = sess.algorithmic_bytes_per_step / (ms_max / K * 1e-3) / 1e9
 
     # ---- e2e: host buffers through the C ABI ----

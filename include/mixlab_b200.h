@@ -292,6 +292,9 @@ MXL_API int mxl_graph_plan(mxl_graph *g, int *order_out, uint32_t cap);
 /* Runs ticks tick0 .. tick0+n_ticks-1 (t = tick * samples_per_tick, engine.rs:490) as one batch:
  * every audio line holds n_ticks*S frames, every video line n_ticks slots. */
 MXL_API int mxl_graph_run_ticks(mxl_graph *g, uint64_t tick0, uint32_t n_ticks);
+/* Audio and video sub-graphs share no line, so by default their stages run on two streams of the
+ * context concurrently (joined before the call returns to the stream's order).  0 = one stream. */
+MXL_API int mxl_graph_set_stream_split(mxl_graph *g, int enabled);
 /* Output line of a module after the last run (borrowed; valid until the next run or edit). */
 MXL_API mxl_line *mxl_graph_output(mxl_graph *g, int module_id, uint32_t out_index);
 /* Per-launch device timings, shaped like EngineStat (src/engine/timing.rs:46-60,86-94). */

@@ -208,6 +208,7 @@ def lib():
         "mxl_graph_run_ticks": (i32, [vp, u64, u32]),
         "mxl_graph_output": (vp, [vp, i32, u32]),
         "mxl_graph_set_profiling": (i32, [vp, i32]),
+        "mxl_graph_set_stream_split": (i32, [vp, i32]),
         "mxl_graph_stage_count": (i32, [vp]),
         "mxl_graph_stage_info": (i32, [vp, u32, C.POINTER(StageInfo)]),
     }
@@ -674,6 +675,9 @@ class Graph:
 
     def set_profiling(self, on):
         check(lib().mxl_graph_set_profiling(self.h, 1 if on else 0))
+
+    def set_stream_split(self, on):
+        check(lib().mxl_graph_set_stream_split(self.h, 1 if on else 0))
 
     def stages(self):
         n = check(lib().mxl_graph_stage_count(self.h))

@@ -86,6 +86,11 @@ struct mxl_ctx {
     cudaEvent_t fences[4] = {nullptr, nullptr, nullptr, nullptr};
     bool in_dirty = false, out_dirty = false, in_must_wait = false, out_must_wait = false;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;
+    // Audio and video sub-graphs never share a line (no module of the path has terminals of both
+    // kinds), so the graph executor runs the small latency-bound audio kernels on a second,
+    // higher-priority stream while the bandwidth-bound compositor owns the main stream.
+    cudaStream_t stream_aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     int upload_stream(cudaStream_t* s);     // stream an async upload must be issued on
     int download_stream(cudaStream_t* s);

@@ -312,6 +312,9 @@ int mxl_ctx_destroy(mxl_ctx* ctx)
             for (uint8_t* p : kv.second) cudaFree(p);
         if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
         if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+        if (ctx->stream_aux) { cudaStreamSynchronize(ctx->stream_aux); cudaStreamDestroy(ctx->stream_aux); }
+        if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+        if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
         if (ctx->stream_in) { cudaStreamSynchronize(ctx->stream_in); cudaStreamDestroy(ctx->stream_in); }
         if (ctx->stream_out) { cudaStreamSynchronize(ctx->stream_out); cudaStreamDestroy(ctx->stream_out); }
         for (cudaEvent_t e : {ctx->ev_in, ctx->ev_out, ctx->ev_compute, ctx->fences[0], ctx->fences[1], ctx->fences[2], ctx->fences[3]})

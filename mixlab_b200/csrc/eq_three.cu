@@ -162,8 +162,9 @@ __global__ void __launch_bounds__(kEqThreads) eq_exact_kernel(const __grid_const
 // their start state to below 2^-75, so CTAs never talk to each other.
 //   1. the CTA's 256*Lc input samples are staged coalesced into a padded shared-memory tile
 //      (row stride Lc+1 words: thread-per-row reads are bank-conflict free);
-//   2. every thread runs its chunk from zero state (FMA form) -> z_i;  the chunk that starts the
-//      call runs from the module's stored state instead;
+//   2. every thread runs its chunk from zero state (FMA form) -> z_i, as four sub-chunks advanced
+//      in lock step (four independent FP64 dependency chains per thread);  the chunk that starts
+//      the call runs from the module's stored state instead;
 //   3. inclusive scan of v_i = A v_(i-1) + z_i over the CTA: Hillis-Steele with A^(2^d) through
 //      shared memory;  the start state of chunk i is v_(i-1);
 //   4. the non-halo chunks are re-run from their start state in the reference's exact operation
@@ -193,25 +194,35 @@ __global__ void __launch_bounds__(kEqBlockThreads) eq_block_kernel(const __grid_
     const int64_t c = c0 + tid;
     const bool active = c >= 0 && c < (int64_t)b.n_chunks;
 
-    // ---- 1. stage the inputs ----
+    // ---- 1. stage the inputs (loads of four iterations in flight before the first shared store) ----
     {
         const uint32_t vec_per_row = Lc >> 2;
-        const uint32_t total = kEqBlockThreads * vec_per_row;
-        for (uint32_t idx = tid; idx < total; idx += kEqBlockThreads) {
-            const uint32_t i = idx / vec_per_row, j = (idx - i * vec_per_row) << 2;
-            const int64_t ci = c0 + i;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (in.in && ci >= 0) {
-                const uint64_t g = (uint64_t)ci * Lc + j;
-                if (g + 4 <= b.frames) v = *reinterpret_cast<const float4*>(in.in + g);
-                else if (g < b.frames) {
-                    v.x = in.in[g];
-                    if (g + 1 < b.frames) v.y = in.in[g + 1];
-                    if (g + 2 < b.frames) v.z = in.in[g + 2];
+        const uint32_t total = kEqBlockThreads * vec_per_row;          // multiple of 4 * kEqBlockThreads (Lc % 16 == 0)
+        for (uint32_t base = tid; base < total; base += 4 * kEqBlockThreads) {
+            float4 v[4];
+            uint32_t dst[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t idx = base + u * kEqBlockThreads;
+                const uint32_t i = idx / vec_per_row, j = (idx - i * vec_per_row) << 2;
+                const int64_t ci = c0 + i;
+                dst[u] = i * row + j;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (in.in && ci >= 0) {
+                    const uint64_t g = (uint64_t)ci * Lc + j;
+                    if (g + 4 <= b.frames) v[u] = *reinterpret_cast<const float4*>(in.in + g);
+                    else if (g < b.frames) {
+                        v[u].x = in.in[g];
+                        if (g + 1 < b.frames) v[u].y = in.in[g + 1];
+                        if (g + 2 < b.frames) v[u].z = in.in[g + 2];
+                    }
                 }
             }
-            float* d = tile + i * row + j;
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                float* d = tile + dst[u];
+                d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+            }
         }
     }
     __syncthreads();
@@ -220,26 +231,47 @@ __global__ void __launch_bounds__(kEqBlockThreads) eq_block_kernel(const __grid_
     const float* mine = tile + tid * row;
     const double* st = in.state;
 
-    // ---- 2. zero-state (or stored-state, for the chunk that starts the call) run ----
+    // ---- 2. zero-state run; the chunk is cut into 4 sub-chunks advanced in lock step (4 independent
+    //         dependency chains per thread hide the FP64 latency).  w[q] = state at the start of
+    //         sub-chunk q for a zero state at the start of the chunk; the chunk that starts the call
+    //         runs its first sub-chunk from the module's stored state instead. ----
+    const uint32_t Ls = Lc >> 2;
+    double w[4][8];
     double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (active) {
-        if (c == 0) {
 #pragma unroll
-            for (int q = 0; q < 8; q++) v[q] = st[q];
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) w[q][e] = 0.0;
+    if (active) {
+        double z[4][8];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+            for (int e = 0; e < 8; e++) z[q][e] = (q == 0 && c == 0) ? st[e] : 0.0;
+        for (uint32_t j = 0; j < Ls; j++) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const double s = (double)mine[q * Ls + j];
+                z[q][0] = fma(al, z[q][0], fma(cl, s, kVsa));
+                z[q][1] = fma(cl, z[q][0] - z[q][1], z[q][1]);
+                z[q][2] = fma(cl, z[q][1] - z[q][2], z[q][2]);
+                z[q][3] = fma(cl, z[q][2] - z[q][3], z[q][3]);
+                z[q][4] = fma(ah, z[q][4], fma(ch, s, kVsa));
+                z[q][5] = fma(ch, z[q][4] - z[q][5], z[q][5]);
+                z[q][6] = fma(ch, z[q][5] - z[q][6], z[q][6]);
+                z[q][7] = fma(ch, z[q][6] - z[q][7], z[q][7]);
+            }
         }
-        double l0 = v[0], l1 = v[1], l2 = v[2], l3 = v[3], h0 = v[4], h1 = v[5], h2 = v[6], h3 = v[7];
-        for (uint32_t j = 0; j < Lc; j++) {
-            const double s = (double)mine[j];
-            l0 = fma(al, l0, fma(cl, s, kVsa));
-            l1 = fma(cl, l0 - l1, l1);
-            l2 = fma(cl, l1 - l2, l2);
-            l3 = fma(cl, l2 - l3, l3);
-            h0 = fma(ah, h0, fma(ch, s, kVsa));
-            h1 = fma(ch, h0 - h1, h1);
-            h2 = fma(ch, h1 - h2, h2);
-            h3 = fma(ch, h2 - h3, h3);
+        // w[q+1] = B w[q] + z[q];  v = w[4]
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            double yl[4], yh[4];
+            tri_apply(b.sub_lo[0], w[q], yl);
+            tri_apply(b.sub_hi[0], w[q] + 4, yh);
+            double* dst = q < 3 ? w[q + 1] : v;
+#pragma unroll
+            for (int e = 0; e < 4; e++) { dst[e] = yl[e] + z[q][e]; dst[4 + e] = yh[e] + z[q][4 + e]; }
         }
-        v[0] = l0; v[1] = l1; v[2] = l2; v[3] = l3; v[4] = h0; v[5] = h1; v[6] = h2; v[7] = h3;
     }
 
     // ---- 3. inclusive scan over the CTA: Hillis-Steele, v_i += A^(2^d) v_(i - 2^d) ----
@@ -266,32 +298,49 @@ __global__ void __launch_bounds__(kEqBlockThreads) eq_block_kernel(const __grid_
     for (int q = 0; q < 8; q++) xch[tid * 8 + q] = v[q];
     __syncthreads();
 
-    // ---- 4. exact re-run of the chunks this CTA owns ----
+    // ---- 4. exact re-run of the chunks this CTA owns: 4 sub-chunks in lock step, each from its own
+    //         start state  B^q S + w[q]  (S = start state of the chunk) ----
     const bool owner = active && (tid >= (int)b.halo_chunks || blockIdx.x == 0);
-    EqRegs r{};
+    EqRegs r[4];
     uint32_t count = 0;
     if (owner) {
-        if (c == 0) {
-            r.l0 = st[0]; r.l1 = st[1]; r.l2 = st[2]; r.l3 = st[3];
-            r.h0 = st[4]; r.h1 = st[5]; r.h2 = st[6]; r.h3 = st[7];
-            r.x0 = st[8]; r.x1 = st[9]; r.x2 = st[10];
-        } else {
-            const double* p = xch + (tid - 1) * 8;       // tid >= 1 here: c > 0 and c0 + 0 >= 0 for blockIdx.x > 0 halo
-            r.l0 = p[0]; r.l1 = p[1]; r.l2 = p[2]; r.l3 = p[3];
-            r.h0 = p[4]; r.h1 = p[5]; r.h2 = p[6]; r.h3 = p[7];
-            // history = the three inputs before this chunk
+        double S[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (c != 0) {
+            const double* p = xch + (tid - 1) * 8;       // c > 0 => tid >= 1
+#pragma unroll
+            for (int e = 0; e < 8; e++) S[e] = p[e];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            double pl[4], ph[4];
+            if (q == 0) {
+#pragma unroll
+                for (int e = 0; e < 4; e++) { pl[e] = S[e]; ph[e] = S[4 + e]; }
+            } else {
+                tri_apply(b.sub_lo[q - 1], S, pl);
+                tri_apply(b.sub_hi[q - 1], S + 4, ph);
+#pragma unroll
+                for (int e = 0; e < 4; e++) { pl[e] += w[q][e]; ph[e] += w[q][4 + e]; }
+            }
+            r[q].l0 = pl[0]; r[q].l1 = pl[1]; r[q].l2 = pl[2]; r[q].l3 = pl[3];
+            r[q].h0 = ph[0]; r[q].h1 = ph[1]; r[q].h2 = ph[2]; r[q].h3 = ph[3];
+            // history = the three inputs before the sub-chunk
             double hist[3];
 #pragma unroll
             for (int j = 0; j < 3; j++) {
-                const int64_t idx = c * (int64_t)Lc - 3 + j;       // absolute sample index, may precede the call
+                const int64_t idx = c * (int64_t)Lc + (int64_t)(q * Ls) - 3 + j;   // absolute sample index
                 if (idx >= 0) {
-                    const int64_t rel = idx - c0 * (int64_t)Lc;    // position inside the tile
+                    const int64_t rel = idx - c0 * (int64_t)Lc;                    // position inside the tile
                     hist[j] = (double)tile[(rel / Lc) * row + (rel % Lc)];
                 } else {
-                    hist[j] = st[8 + 3 + idx];
+                    hist[j] = st[8 + 3 + idx];                                     // inputs of the previous call
                 }
             }
-            r.x0 = hist[0]; r.x1 = hist[1]; r.x2 = hist[2];
+            r[q].x0 = hist[0]; r[q].x1 = hist[1]; r[q].x2 = hist[2];
+        }
+        if (c == 0) {                                    // the call starts from the stored state, exactly
+            r[0].l0 = st[0]; r[0].l1 = st[1]; r[0].l2 = st[2]; r[0].l3 = st[3];
+            r[0].h0 = st[4]; r[0].h1 = st[5]; r[0].h2 = st[6]; r[0].h3 = st[7];
         }
         const uint64_t s0 = (uint64_t)c * Lc;
         count = (uint32_t)((s0 + Lc <= b.frames) ? Lc : (b.frames - s0));
@@ -300,12 +349,27 @@ __global__ void __launch_bounds__(kEqBlockThreads) eq_block_kernel(const __grid_
     if (owner) {
         float* wr = tile + tid * row;
         const double g_lo = in.g_lo, g_mid = in.g_mid, g_hi = in.g_hi;
-        for (uint32_t j = 0; j < count; j++) wr[j] = eq_step(r, wr[j], cl, ch, g_lo, g_mid, g_hi);
-        if (c + 1 == (int64_t)b.n_chunks) {              // state after this call
+        if (count == Lc) {
+            for (uint32_t j = 0; j < Ls; j++) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) wr[q * Ls + j] = eq_step(r[q], wr[q * Ls + j], cl, ch, g_lo, g_mid, g_hi);
+            }
+        } else {
+            for (uint32_t j = 0; j < Ls; j++) {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (q * Ls + j < count) wr[q * Ls + j] = eq_step(r[q], wr[q * Ls + j], cl, ch, g_lo, g_mid, g_hi);
+            }
+        }
+        if (c + 1 == (int64_t)b.n_chunks) {              // state after this call: the sub-chunk holding the last sample
+            const uint32_t ql = (count - 1) / Ls;
+            EqRegs f = r[0];
+#pragma unroll
+            for (int q = 1; q < 4; q++) if (ql == (uint32_t)q) f = r[q];
             double* so = in.state_out;
-            so[0] = r.l0; so[1] = r.l1; so[2] = r.l2; so[3] = r.l3;
-            so[4] = r.h0; so[5] = r.h1; so[6] = r.h2; so[7] = r.h3;
-            so[8] = r.x0; so[9] = r.x1; so[10] = r.x2;
+            so[0] = f.l0; so[1] = f.l1; so[2] = f.l2; so[3] = f.l3;
+            so[4] = f.h0; so[5] = f.h1; so[6] = f.h2; so[7] = f.h3;
+            so[8] = f.x0; so[9] = f.x1; so[10] = f.x2;
         }
     }
     __syncthreads();
@@ -334,7 +398,7 @@ int launch_eq_three_block(mxl_ctx* ctx, const EqBlockBatch& b)
     if (!ctx || !ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "no CUDA device bound to this context");
     MXL_TRY(ctx->activate());
     if (b.n <= 0 || b.frames == 0) return MXL_OK;
-    if (b.chunk == 0 || (b.chunk & 3) || b.chunk > kEqBlockMaxChunk || b.halo_chunks == 0 || b.halo_chunks > kEqBlockThreads / 2)
+    if (b.chunk == 0 || (b.chunk & 15) || b.chunk > kEqBlockMaxChunk || b.halo_chunks == 0 || b.halo_chunks > kEqBlockThreads / 2)
         MXL_FAIL(MXL_ERR_INVALID, "eq_block_kernel: bad plan (chunk %u, halo %u)", b.chunk, b.halo_chunks);
     const size_t tile_bytes = ((size_t)kEqBlockThreads * (b.chunk + 1) * sizeof(float) + 15) & ~(size_t)15;
     const size_t smem = tile_bytes + (size_t)kEqBlockThreads * 8 * sizeof(double);

@@ -31,6 +31,7 @@ struct mxl_graph {
     bool dirty = true;
     bool profiling = false;
     bool timings_pending = false;
+    bool split_streams = true;                                         // audio stages on ctx->stream_aux next to video stages
 
     // plan
     std::vector<int> run_order;
@@ -287,6 +288,27 @@ int mxl_graph_run_ticks(mxl_graph* g, uint64_t tick0, uint32_t n_ticks)
 
     MXL_TRY(ctx->compute_begin());
     struct EndGuard { mxl_ctx* c; ~EndGuard() { c->compute_end(); } } end_guard{ctx};
+
+    // fork: audio stages -> aux stream when the graph also has video stages to overlap them with
+    bool has_audio = false, has_video = false;
+    for (const Stage& s : g->stages) {
+        if (is_source(s.kind)) continue;
+        if (s.kind == MXL_MOD_VIDEO_MIXER) has_video = true; else has_audio = true;
+    }
+    const bool split = g->split_streams && has_audio && has_video && !getenv("MXL_NO_STREAM_SPLIT");
+    cudaStream_t main_stream = ctx->stream;
+    struct StreamGuard { mxl_ctx* c; cudaStream_t s; ~StreamGuard() { c->stream = s; } } stream_guard{ctx, main_stream};
+    if (split) {
+        if (!ctx->stream_aux) {
+            int lo = 0, hi = 0;
+            MXL_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            MXL_CUDA(cudaStreamCreateWithPriority(&ctx->stream_aux, cudaStreamNonBlocking, hi));
+            MXL_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            MXL_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        }
+        MXL_CUDA(cudaEventRecord(ctx->ev_fork, main_stream));
+        MXL_CUDA(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_fork, 0));
+    }
     std::vector<mxl_module*> mods;
     std::vector<IoSet> ios;
     std::vector<const mxl_line*> in_ptrs;
@@ -315,6 +337,7 @@ int mxl_graph_run_ticks(mxl_graph* g, uint64_t tick0, uint32_t n_ticks)
             mods.push_back(m);
             ios.push_back(io);
         }
+        ctx->stream = (split && s.kind != MXL_MOD_VIDEO_MIXER) ? ctx->stream_aux : main_stream;
         if (g->profiling) {
             if (!s.ev0) { MXL_CUDA(cudaEventCreate(&s.ev0)); MXL_CUDA(cudaEventCreate(&s.ev1)); }
             MXL_CUDA(cudaEventRecord(s.ev0, ctx->stream));
@@ -326,7 +349,19 @@ int mxl_graph_run_ticks(mxl_graph* g, uint64_t tick0, uint32_t n_ticks)
         s.last_bytes = bytes;
         if (g->profiling) MXL_CUDA(cudaEventRecord(s.ev1, ctx->stream));
     }
+    ctx->stream = main_stream;
+    if (split) {                                                       // join before anything downstream of the run
+        MXL_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream_aux));
+        MXL_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
+    }
     g->timings_pending = g->profiling;
+    return MXL_OK;
+}
+
+int mxl_graph_set_stream_split(mxl_graph* g, int enabled)
+{
+    if (!g) MXL_FAIL(MXL_ERR_INVALID, "NULL graph");
+    g->split_streams = enabled != 0;
     return MXL_OK;
 }
 

@@ -105,6 +105,8 @@ struct EqBlockBatch {
     double c_lo, c_hi;
     double pow_lo[kEqBlockLevels][10];   // A^(2^d), A = M^Lc, packed lower-triangular
     double pow_hi[kEqBlockLevels][10];
+    double sub_lo[3][10];                // B^1..B^3, B = M^(Lc/4): the four sub-chunks a thread interleaves
+    double sub_hi[3][10];
     EqBlockInst inst[kMaxBatch];
 };
 int launch_eq_three_block(mxl_ctx* ctx, const EqBlockBatch& b);

@@ -31,8 +31,6 @@ struct DevBuf {
     }
 };
 
-static uint64_t line_bytes(const mxl_line* l) { return l ? l->len() * sizeof(float) : 0; }
-
 // ================================================================================================
 // module classes
 // ================================================================================================
@@ -668,8 +666,21 @@ static const std::vector<double>& eq_block_plan_for(mxl_ctx* ctx, uint32_t Lc)
     }
     std::vector<double> plan;
     if (Hc <= 64) {
-        plan.assign(1 + 2 * k::kEqBlockLevels * 10, 0.0);
+        plan.assign(1 + 2 * k::kEqBlockLevels * 10 + 60, 0.0);
         plan[0] = (double)Hc;
+        {   // B, B^2, B^3 with B = M^(Lc/4)
+            double Bl[4][4], Bh[4][4], Ql[4][4], Qh[4][4];
+            cascade_power(co.c_lo, Lc / 4, Bl);
+            cascade_power(co.c_hi, Lc / 4, Bh);
+            memcpy(Ql, Bl, sizeof Ql); memcpy(Qh, Bh, sizeof Qh);
+            const size_t base = 1 + 2 * k::kEqBlockLevels * 10;
+            for (int q = 0; q < 3; q++) {
+                pack_tri(Ql, &plan[base + q * 10]);
+                pack_tri(Qh, &plan[base + 30 + q * 10]);
+                matmul4(Ql, Bl, T); memcpy(Ql, T, sizeof T);
+                matmul4(Qh, Bh, T); memcpy(Qh, T, sizeof T);
+            }
+        }
         memcpy(Pl, Al, sizeof Pl); memcpy(Ph, Ah, sizeof Ph);
         for (int d = 0; d < k::kEqBlockLevels; d++) {
             pack_tri(Pl, &plan[1 + d * 10]);
@@ -685,7 +696,7 @@ static const std::vector<double>& eq_block_plan_for(mxl_ctx* ctx, uint32_t Lc)
 static int run_eq_block(mxl_ctx* ctx, mxl_module* const* mods, const IoSet* io, int first, int cnt, uint64_t frames, uint64_t* bytes)
 {
     uint32_t forced = 0;
-    if (const char* e = getenv("MXL_EQ_BLOCK_CHUNK")) forced = (uint32_t)atol(e) / 4 * 4;
+    if (const char* e = getenv("MXL_EQ_BLOCK_CHUNK")) forced = (uint32_t)atol(e) / 16 * 16;
     const std::vector<double>* plan = nullptr;
     uint32_t Lc = 0;
     for (uint32_t cand : {32u, 64u, 128u}) {
@@ -693,7 +704,7 @@ static int run_eq_block(mxl_ctx* ctx, mxl_module* const* mods, const IoSet* io, 
         const std::vector<double>& p = eq_block_plan_for(ctx, cand);
         if (!p.empty()) { plan = &p; Lc = cand; break; }
     }
-    if (forced && !plan && forced >= 4 && forced <= k::kEqBlockMaxChunk) {
+    if (forced && !plan && forced >= 16 && forced <= k::kEqBlockMaxChunk) {
         const std::vector<double>& p = eq_block_plan_for(ctx, forced);
         if (!p.empty()) { plan = &p; Lc = forced; }
     }
@@ -708,6 +719,8 @@ static int run_eq_block(mxl_ctx* ctx, mxl_module* const* mods, const IoSet* io, 
     b.c_lo = co.c_lo; b.c_hi = co.c_hi;
     memcpy(b.pow_lo, &(*plan)[1], sizeof b.pow_lo);
     memcpy(b.pow_hi, &(*plan)[1 + k::kEqBlockLevels * 10], sizeof b.pow_hi);
+    memcpy(b.sub_lo, &(*plan)[1 + 2 * k::kEqBlockLevels * 10], sizeof b.sub_lo);
+    memcpy(b.sub_hi, &(*plan)[1 + 2 * k::kEqBlockLevels * 10 + 30], sizeof b.sub_hi);
     for (int j = 0; j < cnt; j++) {
         EqThree* m = (EqThree*)mods[first + j];
         MXL_TRY(m->ensure_state());

@@ -51,11 +51,12 @@ __global__ void __launch_bounds__(kVidThreads) crossfade_flat_kernel(const FadeJ
 {
     const FadeJob job = jobs[blockIdx.y];
     const uint32_t f = job.fade, g = 255u - job.fade;
-    const uint64_t v0 = ((uint64_t)blockIdx.x * kVidThreads + threadIdx.x) * kFadeUnroll;
+    // the kFadeUnroll vectors of a thread are kVidThreads apart: each warp instruction is 512 contiguous bytes
+    const uint64_t v0 = (uint64_t)blockIdx.x * (kVidThreads * kFadeUnroll) + threadIdx.x;
     uint4 a[kFadeUnroll], b[kFadeUnroll];
 #pragma unroll
     for (int u = 0; u < kFadeUnroll; u++) {
-        const uint64_t v = v0 + u;
+        const uint64_t v = v0 + (uint64_t)u * kVidThreads;
         if (v < n16) {
             const uint32_t blank = v >= chroma16 ? 0x80808080u : 0u;
             a[u] = job.a ? ldg16(job.a + v * 16) : make_uint4(blank, blank, blank, blank);
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(kVidThreads) crossfade_flat_kernel(const FadeJ
     }
 #pragma unroll
     for (int u = 0; u < kFadeUnroll; u++) {
-        const uint64_t v = v0 + u;
+        const uint64_t v = v0 + (uint64_t)u * kVidThreads;
         if (v < n16) *reinterpret_cast<uint4*>(job.out + v * 16) = fade16(a[u], b[u], f, g);
     }
 }
