@@ -181,6 +181,7 @@ __device__ __forceinline__ void tri_apply(const double* A, const double x[4], do
     }
 }
 
+template <int NSUB>
 __global__ void __launch_bounds__(kEqBlockThreads) eq_block_kernel(const __grid_constant__ EqBlockBatch b)
 {
     extern __shared__ __align__(16) unsigned char eq_smem[];
@@ -235,22 +236,22 @@ __global__ void __launch_bounds__(kEqBlockThreads) eq_block_kernel(const __grid_
     //         dependency chains per thread hide the FP64 latency).  w[q] = state at the start of
     //         sub-chunk q for a zero state at the start of the chunk; the chunk that starts the call
     //         runs its first sub-chunk from the module's stored state instead. ----
-    const uint32_t Ls = Lc >> 2;
-    double w[4][8];
+    const uint32_t Ls = Lc / NSUB;
+    double w[NSUB][8];
     double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-    for (int q = 0; q < 4; q++)
+    for (int q = 0; q < NSUB; q++)
 #pragma unroll
         for (int e = 0; e < 8; e++) w[q][e] = 0.0;
     if (active) {
-        double z[4][8];
+        double z[NSUB][8];
 #pragma unroll
-        for (int q = 0; q < 4; q++)
+        for (int q = 0; q < NSUB; q++)
 #pragma unroll
             for (int e = 0; e < 8; e++) z[q][e] = (q == 0 && c == 0) ? st[e] : 0.0;
         for (uint32_t j = 0; j < Ls; j++) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < NSUB; q++) {
                 const double s = (double)mine[q * Ls + j];
                 z[q][0] = fma(al, z[q][0], fma(cl, s, kVsa));
                 z[q][1] = fma(cl, z[q][0] - z[q][1], z[q][1]);
@@ -262,13 +263,13 @@ __global__ void __launch_bounds__(kEqBlockThreads) eq_block_kernel(const __grid_
                 z[q][7] = fma(ch, z[q][6] - z[q][7], z[q][7]);
             }
         }
-        // w[q+1] = B w[q] + z[q];  v = w[4]
+        // w[q+1] = B w[q] + z[q];  v = w[NSUB]
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+        for (int q = 0; q < NSUB; q++) {
             double yl[4], yh[4];
             tri_apply(b.sub_lo[0], w[q], yl);
             tri_apply(b.sub_hi[0], w[q] + 4, yh);
-            double* dst = q < 3 ? w[q + 1] : v;
+            double* dst = q < NSUB - 1 ? w[q + 1 < NSUB ? q + 1 : 0] : v;
 #pragma unroll
             for (int e = 0; e < 4; e++) { dst[e] = yl[e] + z[q][e]; dst[4 + e] = yh[e] + z[q][4 + e]; }
         }
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(kEqBlockThreads) eq_block_kernel(const __grid_
     // ---- 4. exact re-run of the chunks this CTA owns: 4 sub-chunks in lock step, each from its own
     //         start state  B^q S + w[q]  (S = start state of the chunk) ----
     const bool owner = active && (tid >= (int)b.halo_chunks || blockIdx.x == 0);
-    EqRegs r[4];
+    EqRegs r[NSUB];
     uint32_t count = 0;
     if (owner) {
         double S[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -311,14 +312,14 @@ __global__ void __launch_bounds__(kEqBlockThreads) eq_block_kernel(const __grid_
             for (int e = 0; e < 8; e++) S[e] = p[e];
         }
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+        for (int q = 0; q < NSUB; q++) {
             double pl[4], ph[4];
             if (q == 0) {
 #pragma unroll
                 for (int e = 0; e < 4; e++) { pl[e] = S[e]; ph[e] = S[4 + e]; }
             } else {
-                tri_apply(b.sub_lo[q - 1], S, pl);
-                tri_apply(b.sub_hi[q - 1], S + 4, ph);
+                tri_apply(b.sub_lo[q > 0 ? q - 1 : 0], S, pl);
+                tri_apply(b.sub_hi[q > 0 ? q - 1 : 0], S + 4, ph);
 #pragma unroll
                 for (int e = 0; e < 4; e++) { pl[e] += w[q][e]; ph[e] += w[q][4 + e]; }
             }
@@ -352,12 +353,12 @@ __global__ void __launch_bounds__(kEqBlockThreads) eq_block_kernel(const __grid_
         if (count == Lc) {
             for (uint32_t j = 0; j < Ls; j++) {
 #pragma unroll
-                for (int q = 0; q < 4; q++) wr[q * Ls + j] = eq_step(r[q], wr[q * Ls + j], cl, ch, g_lo, g_mid, g_hi);
+                for (int q = 0; q < NSUB; q++) wr[q * Ls + j] = eq_step(r[q], wr[q * Ls + j], cl, ch, g_lo, g_mid, g_hi);
             }
         } else {
             for (uint32_t j = 0; j < Ls; j++) {
 #pragma unroll
-                for (int q = 0; q < 4; q++)
+                for (int q = 0; q < NSUB; q++)
                     if (q * Ls + j < count) wr[q * Ls + j] = eq_step(r[q], wr[q * Ls + j], cl, ch, g_lo, g_mid, g_hi);
             }
         }
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(kEqBlockThreads) eq_block_kernel(const __grid_
             const uint32_t ql = (count - 1) / Ls;
             EqRegs f = r[0];
 #pragma unroll
-            for (int q = 1; q < 4; q++) if (ql == (uint32_t)q) f = r[q];
+            for (int q = 1; q < NSUB; q++) if (ql == (uint32_t)q) f = r[q];
             double* so = in.state_out;
             so[0] = f.l0; so[1] = f.l1; so[2] = f.l2; so[3] = f.l3;
             so[4] = f.h0; so[5] = f.h1; so[6] = f.h2; so[7] = f.h3;
@@ -402,13 +403,18 @@ int launch_eq_three_block(mxl_ctx* ctx, const EqBlockBatch& b)
         MXL_FAIL(MXL_ERR_INVALID, "eq_block_kernel: bad plan (chunk %u, halo %u)", b.chunk, b.halo_chunks);
     const size_t tile_bytes = ((size_t)kEqBlockThreads * (b.chunk + 1) * sizeof(float) + 15) & ~(size_t)15;
     const size_t smem = tile_bytes + (size_t)kEqBlockThreads * 8 * sizeof(double);
+    const int nsub = b.subs == 4 ? 4 : (b.subs == 2 ? 2 : 1);
     if (smem > 48 * 1024 && smem > ctx->eq_block_smem) {
-        MXL_CUDA(cudaFuncSetAttribute(eq_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MXL_CUDA(cudaFuncSetAttribute(eq_block_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MXL_CUDA(cudaFuncSetAttribute(eq_block_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MXL_CUDA(cudaFuncSetAttribute(eq_block_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->eq_block_smem = smem;
     }
     const uint32_t U = kEqBlockThreads - b.halo_chunks;
     dim3 grid((b.n_chunks + U - 1) / U, b.n);
-    eq_block_kernel<<<grid, kEqBlockThreads, smem, ctx->stream>>>(b);
+    if (nsub == 4) eq_block_kernel<4><<<grid, kEqBlockThreads, smem, ctx->stream>>>(b);
+    else if (nsub == 2) eq_block_kernel<2><<<grid, kEqBlockThreads, smem, ctx->stream>>>(b);
+    else eq_block_kernel<1><<<grid, kEqBlockThreads, smem, ctx->stream>>>(b);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) MXL_FAIL(MXL_ERR_CUDA, "launch of eq_block_kernel failed: %s", cudaGetErrorString(e));
     ctx->launches++;

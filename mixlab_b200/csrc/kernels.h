@@ -102,10 +102,12 @@ struct EqBlockBatch {
     uint32_t halo_chunks;            // Hc: |A^Hc| < 2^-75
     uint32_t n_chunks;
     int32_t n;
+    uint32_t subs;                   // sub-chunks a thread advances in lock step: 1, 2 or 4
+    uint32_t _pad;
     double c_lo, c_hi;
     double pow_lo[kEqBlockLevels][10];   // A^(2^d), A = M^Lc, packed lower-triangular
     double pow_hi[kEqBlockLevels][10];
-    double sub_lo[3][10];                // B^1..B^3, B = M^(Lc/4): the four sub-chunks a thread interleaves
+    double sub_lo[3][10];                // B^1..B^3, B = M^(Lc/subs): the sub-chunks a thread interleaves
     double sub_hi[3][10];
     EqBlockInst inst[kMaxBatch];
 };

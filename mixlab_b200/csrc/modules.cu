@@ -648,9 +648,10 @@ static uint32_t eq_pick_chunk(const mxl_ctx* ctx, uint64_t frames, int n_inst)
 
 // Plan of the single-launch kernel for chunk length Lc: halo length Hc (chunks until the cascades have
 // forgotten their start state, |A^Hc| < 2^-75) and A^(2^d), d = 0..7.  Empty plan = Hc too long for Lc.
-static const std::vector<double>& eq_block_plan_for(mxl_ctx* ctx, uint32_t Lc)
+static const std::vector<double>& eq_block_plan_for(mxl_ctx* ctx, uint32_t Lc, uint32_t subs)
 {
-    auto it = ctx->eq_block_plans.find(Lc);
+    const uint32_t key = Lc * 8 + subs;
+    auto it = ctx->eq_block_plans.find(key);
     if (it != ctx->eq_block_plans.end()) return it->second;
     const EqCoefs co = eq_coefs(ctx);
     double Al[4][4], Ah[4][4], Pl[4][4], Ph[4][4], T[4][4];
@@ -668,10 +669,10 @@ static const std::vector<double>& eq_block_plan_for(mxl_ctx* ctx, uint32_t Lc)
     if (Hc <= 64) {
         plan.assign(1 + 2 * k::kEqBlockLevels * 10 + 60, 0.0);
         plan[0] = (double)Hc;
-        {   // B, B^2, B^3 with B = M^(Lc/4)
+        {   // B, B^2, B^3 with B = M^(Lc/subs)
             double Bl[4][4], Bh[4][4], Ql[4][4], Qh[4][4];
-            cascade_power(co.c_lo, Lc / 4, Bl);
-            cascade_power(co.c_hi, Lc / 4, Bh);
+            cascade_power(co.c_lo, Lc / subs, Bl);
+            cascade_power(co.c_hi, Lc / subs, Bh);
             memcpy(Ql, Bl, sizeof Ql); memcpy(Qh, Bh, sizeof Qh);
             const size_t base = 1 + 2 * k::kEqBlockLevels * 10;
             for (int q = 0; q < 3; q++) {
@@ -689,7 +690,7 @@ static const std::vector<double>& eq_block_plan_for(mxl_ctx* ctx, uint32_t Lc)
             matmul4(Ph, Ph, T); memcpy(Ph, T, sizeof T);
         }
     }
-    return ctx->eq_block_plans[Lc] = plan;
+    return ctx->eq_block_plans[key] = plan;
 }
 
 // Single-launch path (eq_block_kernel).  Returns 1 if it ran, 0 if no usable plan exists.
@@ -697,15 +698,17 @@ static int run_eq_block(mxl_ctx* ctx, mxl_module* const* mods, const IoSet* io, 
 {
     uint32_t forced = 0;
     if (const char* e = getenv("MXL_EQ_BLOCK_CHUNK")) forced = (uint32_t)atol(e) / 16 * 16;
+    uint32_t subs = 1;   // measured on B200 (tools/eq_tune.sh): 1 chain per thread and Lc = 32 is fastest at both ends
+    if (const char* e = getenv("MXL_EQ_SUBS")) { const long v = atol(e); subs = v == 1 ? 1 : (v == 2 ? 2 : 4); }
     const std::vector<double>* plan = nullptr;
     uint32_t Lc = 0;
     for (uint32_t cand : {32u, 64u, 128u}) {
         if (forced && cand != forced) continue;
-        const std::vector<double>& p = eq_block_plan_for(ctx, cand);
+        const std::vector<double>& p = eq_block_plan_for(ctx, cand, subs);
         if (!p.empty()) { plan = &p; Lc = cand; break; }
     }
     if (forced && !plan && forced >= 16 && forced <= k::kEqBlockMaxChunk) {
-        const std::vector<double>& p = eq_block_plan_for(ctx, forced);
+        const std::vector<double>& p = eq_block_plan_for(ctx, forced, subs);
         if (!p.empty()) { plan = &p; Lc = forced; }
     }
     if (!plan) return 0;
@@ -715,6 +718,7 @@ static int run_eq_block(mxl_ctx* ctx, mxl_module* const* mods, const IoSet* io, 
     b.halo_chunks = (uint32_t)(*plan)[0];
     b.n_chunks = (uint32_t)((frames + Lc - 1) / Lc);
     b.n = cnt;
+    b.subs = subs;
     const EqCoefs co = eq_coefs(ctx);
     b.c_lo = co.c_lo; b.c_hi = co.c_hi;
     memcpy(b.pow_lo, &(*plan)[1], sizeof b.pow_lo);

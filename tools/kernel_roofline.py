@@ -30,6 +30,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=1 << 25)      # 32 Mi frames: mono 128 MiB, stereo 256 MiB
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--only", default="", help="substring filter on kernel names")
     args = ap.parse_args()
     n = args.frames
     peak = 6549.8
@@ -48,6 +49,8 @@ def main():
     rows = []
 
     def run(name, kind, params, ins, outs, nbytes):
+        if args.only and args.only not in name:
+            return
         mod = ctx.module(kind, params)
         ms, launches = timed(ctx, lambda: mod.run_tick(0, ins, outs), args.reps)
         gbs = nbytes / (ms * 1e-3) / 1e9
@@ -69,6 +72,9 @@ def main():
     run("Meter", mxl.MOD_METER, None, [stereo], [], 8 * S)
     run("PcmSink(pack i16)", mxl.MOD_PCM_SINK, None, [stereo], [], 12 * S)
     run("Mixer(2)", mxl.MOD_MIXER, [(0.0, 1.0, True), (-6.0, 0.5, False)], [stereo, o_s2], [o_s, ctx.line(mxl.LINE_STEREO, n)], 8 * S * 4)
+    if args.only and args.only not in 'VideoMixer':
+        ctx.close()
+        return
     # video: 64 frames of 1080p per launch through the VideoMixer module
     T = 64
     fa = [ctx.frame(1920, 1080, blank=True) for _ in range(T)]
