@@ -162,53 +162,63 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU baseline: the oracle (C restatement of the reference CPU engine) on host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_engine_worker(po, desc, do_audio, do_video, n_ticks, seed, out, idx, barrier):
-    """One reference engine thread (src/engine.rs:78-93): per tick Engine::run_tick over the audio
-    graph (topsort + alloc/zero + serial dispatch) and VideoMixer's blank + crossfade."""
-    from mixlab_b200 import workloads as W
-    g = None
-    if do_audio:
-        g, _ = po.build_graph(desc, SAMPLE_RATE, SPT)
-    if do_video:
-        lay = po.frame_layout(W.FRAME_W, W.FRAME_H)
-        a = W.random_bytes(seed, lay.size)
-        b = W.random_bytes(seed + 1, lay.size)
-        f = po.fader_to_u8(0.5)
-    barrier.wait()
-    t0 = time.perf_counter()
-    for k in range(n_ticks):
-        if do_audio:
-            g.run_tick(k)
-        if do_video:
-            po.video_crossfade(lay, a, b, f)       # AvFrame::blank + fade_line, video_mixer.rs:151-237
-    out[idx] = time.perf_counter() - t0
-    barrier.wait()
+class CpuEngines:
+    """`threads` independent reference engines (src/engine.rs:78-93: one engine thread per session), each
+    on its own host thread (ctypes releases the GIL).  Engines, graphs and input frames are built once;
+    run(n) advances every engine by n ticks: per tick Engine::run_tick over the audio graph (topsort +
+    alloc/zero + serial dispatch) and VideoMixer's blank + crossfade (video_mixer.rs:151-237)."""
 
+    def __init__(self, po, desc, args, threads):
+        from mixlab_b200 import workloads as W
+        self.po, self.threads = po, threads
+        self.do_audio = args.workload in ("av", "audio")
+        self.do_video = args.workload in ("av", "video")
+        self.n_ticks = 0
+        self.stop = False
+        self.go = threading.Barrier(threads + 1)
+        self.done = threading.Barrier(threads + 1)
+        self.engines = []
+        for i in range(threads):
+            e = {"tick": 0}
+            if self.do_audio:
+                e["graph"], _ = po.build_graph(desc, SAMPLE_RATE, SPT)
+            if self.do_video:
+                e["lay"] = po.frame_layout(W.FRAME_W, W.FRAME_H)
+                e["a"] = W.random_bytes(0xC0DE + 7 * i, e["lay"].size)
+                e["b"] = W.random_bytes(0xC0DE + 7 * i + 1, e["lay"].size)
+                e["f"] = po.fader_to_u8(0.5)
+            self.engines.append(e)
+        self.workers = [threading.Thread(target=self._work, args=(e,), daemon=True) for e in self.engines]
+        for w in self.workers:
+            w.start()
 
-def cpu_run(po, desc, args, threads, ticks_per_thread):
-    """`threads` independent engines in parallel (ctypes releases the GIL).  Returns seconds (max)."""
-    do_audio = args.workload in ("av", "audio")
-    do_video = args.workload in ("av", "video")
-    out = [0.0] * threads
-    barrier = threading.Barrier(threads + 1)
-    ths = [threading.Thread(target=cpu_engine_worker, args=(po, desc, do_audio, do_video, ticks_per_thread,
-                                                            0xC0DE + 7 * i, out, i, barrier)) for i in range(threads)]
-    for t in ths:
-        t.start()
-    barrier.wait()
-    t0 = time.perf_counter()
-    barrier.wait()
-    dt = time.perf_counter() - t0
-    for t in ths:
-        t.join()
-    return dt
+    def _work(self, e):
+        po = self.po
+        while True:
+            self.go.wait()
+            if self.stop:
+                return
+            for _ in range(self.n_ticks):
+                if self.do_audio:
+                    e["graph"].run_tick(e["tick"])
+                if self.do_video:
+                    po.video_crossfade(e["lay"], e["a"], e["b"], e["f"])
+                e["tick"] += 1
+            self.done.wait()
 
+    def run(self, n_ticks):
+        """Every engine runs n_ticks ticks; returns the wall time of the slowest (seconds)."""
+        self.n_ticks = n_ticks
+        self.go.wait()
+        t0 = time.perf_counter()
+        self.done.wait()
+        return time.perf_counter() - t0
 
-def cpu_calibrate(po, desc, args):
-    """ticks/s of one engine thread from a short probe (sizes the bounded samples)."""
-    dt = cpu_run(po, desc, args, 1, 8)
-    dt = cpu_run(po, desc, args, 1, 24)
-    return 24.0 / dt
+    def close(self):
+        self.stop = True
+        self.go.wait()
+        for w in self.workers:
+            w.join()
 
 
 def cpu_baseline_leg(args):
@@ -217,13 +227,19 @@ def cpu_baseline_leg(args):
     po.build()
     desc = W.config2_graph()
     cores = os.cpu_count() or 1
-    one = cpu_calibrate(po, desc, args)
+    one_engine = CpuEngines(po, desc, args, 1)
+    one_engine.run(8)
+    one = 24.0 / one_engine.run(24)
     # ~1/4 of the budget on the single engine thread (faithful to the reference), the rest on all cores
     t1 = max(16, int(one * args.cpu_seconds * 0.25))
-    dt1 = cpu_run(po, desc, args, 1, t1)
+    dt1 = one_engine.run(t1)
+    one_engine.close()
     single = t1 / dt1
+    all_engines = CpuEngines(po, desc, args, cores)
+    all_engines.run(8)
     tn = max(8, int(single * args.cpu_seconds * 0.75 * 0.6))
-    dtn = cpu_run(po, desc, args, cores, tn)
+    dtn = all_engines.run(tn)
+    all_engines.close()
     multi = cores * tn / dtn
     return {
         "value": multi, "unit": UNIT, "cores": cores, "kind": "port",
@@ -235,7 +251,8 @@ def cpu_baseline_leg(args):
 
 
 def reference_arm(args):
-    """--impl reference: the oracle port on all host threads, bounded steps."""
+    """--impl reference: the oracle port of the reference CPU engine on all host threads -- one
+    independent engine (session) per core, built once; a step = every engine advances `tpt` ticks."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -244,16 +261,18 @@ def reference_arm(args):
     po.build()
     desc = W.config2_graph()
     cores = os.cpu_count() or 1
-    one = cpu_calibrate(po, desc, args)
-    # a step = every core runs `tpt` ticks of its own engine; sized so K+W steps stay within ~2 minutes
+    engines = CpuEngines(po, desc, args, cores)
+    engines.run(4)
+    per_engine = 16.0 / engines.run(16)                 # ticks/s of one engine with all of them busy
+    # sized so that K+W steps stay within ~2 minutes
     budget = 90.0
-    tpt = max(1, min(args.ticks_per_step, int(one * 0.6 * budget / max(1, args.steps + args.warmup))))
+    tpt = max(1, min(args.ticks_per_step, int(per_engine * budget / max(1, args.steps + args.warmup))))
     for _ in range(args.warmup):
-        cpu_run(po, desc, args, cores, tpt)
-    t0 = time.perf_counter()
+        engines.run(tpt)
+    dt = 0.0
     for _ in range(args.steps):
-        cpu_run(po, desc, args, cores, tpt)
-    dt = time.perf_counter() - t0
+        dt += engines.run(tpt)
+    engines.close()
     value = args.steps * cores * tpt / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -261,7 +280,8 @@ def reference_arm(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32 audio + u8 video",
         "data": "synthetic",
         "config": {"workload": workload_name(args), "ticks_per_step": cores * tpt, "samples_per_tick": SPT,
-                   "sample_rate": SAMPLE_RATE, "frame": "1920x1080 yuv420p"},
+                   "sample_rate": SAMPLE_RATE, "frame": "1920x1080 yuv420p", "sessions": cores,
+                   "parallelism": "%d independent engines, one host thread each (the reference runs one engine thread per session)" % cores},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "each step: %d independent engines x %d ticks" % (cores, tpt),
                          "note": "C restatement of the reference CPU engine (oracle/); the Rust reference cannot be built here"},

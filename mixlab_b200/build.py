@@ -16,7 +16,7 @@ OBJ_DIR = os.path.join(HERE, "build")
 LIB_PATH = os.path.join(HERE, "libmixlab_b200.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "mixlab_b200.h")
 
-SOURCES = ["core.cu", "abi.cu", "modules.cu", "graph.cu", "audio_kernels.cu", "eq_three.cu",
+SOURCES = ["core.cu", "abi.cu", "modules.cu", "graph.cu", "audio_kernels.cu", "eq_three.cu", "eq_stream.cu",
            "envelope.cu", "video_kernels.cu"]
 
 NVCC_FLAGS = [

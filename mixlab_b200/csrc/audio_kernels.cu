@@ -185,30 +185,49 @@ __device__ __forceinline__ float amp1(float x, double mod_value, double depth, d
     return (float)((double)x * dv * amplitude);
 }
 
+__device__ __forceinline__ float2 ldg_stream2(const float* p)
+{
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+
+// kAmpUnroll float4 (2 frames each) per thread, kThreads apart: every warp instruction covers 512
+// contiguous bytes of the stereo lines (256 of the control line) and all of a thread's loads are in
+// flight before the first f64 conversion (the conversions run on the 16-lane XU pipe and would
+// otherwise sit between a thread's loads: 0.73 of the copy peak with one vector pair per thread).
+constexpr int kAmpUnroll = 4;
+
 __global__ void __launch_bounds__(kThreads) amplifier_kernel(const __grid_constant__ AmpBatch b)
 {
     const AmpInst& in = b.inst[blockIdx.y];
-    uint64_t f0 = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
-    if (f0 >= b.frames) return;
+    const uint64_t n4 = b.frames >> 1;                              // float4 = 2 stereo frames
+    const uint64_t i0 = (uint64_t)blockIdx.x * (kThreads * kAmpUnroll) + threadIdx.x;
     const double d = in.mod_depth, a = in.amplitude;
-    if (f0 + 4 <= b.frames) {
-        float4 x0 = in.in ? ldg_stream(in.in + 2 * f0) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 x1 = in.in ? ldg_stream(in.in + 2 * f0 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        double m0 = 1.0, m1 = 1.0, m2 = 1.0, m3 = 1.0;
-        if (in.mod) {
-            float4 mv = ldg_stream(in.mod + f0);
-            m0 = (double)mv.x; m1 = (double)mv.y; m2 = (double)mv.z; m3 = (double)mv.w;
+    if (i0 < n4) {
+        float4 x[kAmpUnroll];
+        float2 m[kAmpUnroll];
+#pragma unroll
+        for (int u = 0; u < kAmpUnroll; u++) {
+            const uint64_t v = i0 + (uint64_t)u * kThreads;
+            x[u] = (in.in && v < n4) ? ldg_stream(in.in + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+            m[u] = (in.mod && v < n4) ? ldg_stream2(in.mod + 2 * v) : make_float2(1.f, 1.f);
         }
-        st4(in.out + 2 * f0, make_float4(amp1(x0.x, m0, d, a), amp1(x0.y, m0, d, a),
-                                         amp1(x0.z, m1, d, a), amp1(x0.w, m1, d, a)));
-        st4(in.out + 2 * f0 + 4, make_float4(amp1(x1.x, m2, d, a), amp1(x1.y, m2, d, a),
-                                             amp1(x1.z, m3, d, a), amp1(x1.w, m3, d, a)));
-    } else {
-        for (uint64_t f = f0; f < b.frames; f++) {
-            double mv = in.mod ? (double)in.mod[f] : 1.0;
-            in.out[2 * f] = amp1(in.in ? in.in[2 * f] : 0.f, mv, d, a);
-            in.out[2 * f + 1] = amp1(in.in ? in.in[2 * f + 1] : 0.f, mv, d, a);
+#pragma unroll
+        for (int u = 0; u < kAmpUnroll; u++) {
+            const uint64_t v = i0 + (uint64_t)u * kThreads;
+            if (v >= n4) break;
+            // without a control line the reference uses depth(1.0, d) = 1 - d + d * 1.0 as well (amplifier.rs:52-57)
+            const double m0 = (double)m[u].x, m1 = (double)m[u].y;
+            st4(in.out + 4 * v, make_float4(amp1(x[u].x, m0, d, a), amp1(x[u].y, m0, d, a),
+                                            amp1(x[u].z, m1, d, a), amp1(x[u].w, m1, d, a)));
         }
+    }
+    if ((b.frames & 1) && blockIdx.x == 0 && threadIdx.x == 0) {    // odd frame count: last frame
+        const uint64_t f = b.frames - 1;
+        const double mv = in.mod ? (double)in.mod[f] : 1.0;
+        in.out[2 * f] = amp1(in.in ? in.in[2 * f] : 0.f, mv, d, a);
+        in.out[2 * f + 1] = amp1(in.in ? in.in[2 * f + 1] : 0.f, mv, d, a);
     }
 }
 
@@ -279,14 +298,22 @@ __global__ void __launch_bounds__(kMeterThreads) meter_kernel(const __grid_const
     double sq0 = 0.0, sq1 = 0.0;
     int clip = 0;
     if (in.in) {
-        const float2* src = reinterpret_cast<const float2*>(in.in);
-        for (uint64_t f = f_begin + threadIdx.x; f < f_end; f += kMeterThreads) {
-            float2 s = src[f];
-            pk0 = fmaxf(pk0, fabsf(s.x));      // fmaxf drops NaN like the oracle's `a > peak`
-            pk1 = fmaxf(pk1, fabsf(s.y));
-            sq0 += (double)s.x * (double)s.x;
-            sq1 += (double)s.y * (double)s.y;
-            clip |= (s.x < -1.0f || s.x > 1.0f || s.y < -1.0f || s.y > 1.0f) ? 1 : 0;
+        constexpr int kU = 4;                  // frames in flight per thread (a tick of 800 frames = 2 rounds)
+        for (uint64_t base = f_begin; base < f_end; base += kU * kMeterThreads) {
+            float2 s[kU];
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const uint64_t f = base + (uint64_t)u * kMeterThreads + threadIdx.x;
+                s[u] = f < f_end ? ldg_stream2(in.in + 2 * f) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                pk0 = fmaxf(pk0, fabsf(s[u].x));   // fmaxf drops NaN like the oracle's `a > peak`
+                pk1 = fmaxf(pk1, fabsf(s[u].y));
+                sq0 += (double)s[u].x * (double)s[u].x;
+                sq1 += (double)s[u].y * (double)s[u].y;
+                clip |= (s[u].x < -1.0f || s[u].x > 1.0f || s[u].y < -1.0f || s[u].y > 1.0f) ? 1 : 0;
+            }
         }
     }
 #pragma unroll
@@ -326,30 +353,45 @@ __device__ __forceinline__ short pack1(float s)
     return (v != v) ? (short)0 : (short)__float2int_rz(fminf(fmaxf(v, -32768.0f), 32767.0f));
 }
 
+constexpr int kPcmUnroll = 4;
+
 __global__ void __launch_bounds__(kThreads) pcm_pack_kernel(const float* __restrict__ in, short* __restrict__ out, uint64_t len)
 {
-    uint64_t i0 = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
-    if (i0 >= len) return;
-    if (i0 + 4 <= len) {
-        float4 x = ldg_stream(in + i0);
-        short4 r = make_short4(pack1(x.x), pack1(x.y), pack1(x.z), pack1(x.w));
-        *reinterpret_cast<short4*>(out + i0) = r;
-    } else {
-        for (uint64_t i = i0; i < len; i++) out[i] = pack1(in[i]);
+    const uint64_t n4 = len >> 2;
+    const uint64_t i0 = (uint64_t)blockIdx.x * (kThreads * kPcmUnroll) + threadIdx.x;
+    float4 x[kPcmUnroll];
+#pragma unroll
+    for (int u = 0; u < kPcmUnroll; u++) {
+        const uint64_t v = i0 + (uint64_t)u * kThreads;
+        x[u] = v < n4 ? ldg_stream(in + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+#pragma unroll
+    for (int u = 0; u < kPcmUnroll; u++) {
+        const uint64_t v = i0 + (uint64_t)u * kThreads;
+        if (v < n4) *reinterpret_cast<short4*>(out + 4 * v) = make_short4(pack1(x[u].x), pack1(x[u].y), pack1(x[u].z), pack1(x[u].w));
+    }
+    const uint64_t tail = (n4 << 2) + threadIdx.x;
+    if (blockIdx.x == 0 && tail < len) out[tail] = pack1(in[tail]);
 }
 
 __global__ void __launch_bounds__(kThreads) pcm_unpack_kernel(const short* __restrict__ in, float* __restrict__ out, uint64_t len)
 {
-    uint64_t i0 = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
-    if (i0 >= len) return;
-    if (i0 + 4 <= len) {
-        short4 x = *reinterpret_cast<const short4*>(in + i0);
-        st4(out + i0, make_float4((float)x.x / 32768.0f, (float)x.y / 32768.0f,
-                                  (float)x.z / 32768.0f, (float)x.w / 32768.0f));
-    } else {
-        for (uint64_t i = i0; i < len; i++) out[i] = (float)in[i] / 32768.0f;
+    const uint64_t n4 = len >> 2;
+    const uint64_t i0 = (uint64_t)blockIdx.x * (kThreads * kPcmUnroll) + threadIdx.x;
+    short4 x[kPcmUnroll];
+#pragma unroll
+    for (int u = 0; u < kPcmUnroll; u++) {
+        const uint64_t v = i0 + (uint64_t)u * kThreads;
+        x[u] = v < n4 ? *reinterpret_cast<const short4*>(in + 4 * v) : make_short4(0, 0, 0, 0);
     }
+#pragma unroll
+    for (int u = 0; u < kPcmUnroll; u++) {
+        const uint64_t v = i0 + (uint64_t)u * kThreads;
+        if (v < n4) st4(out + 4 * v, make_float4((float)x[u].x / 32768.0f, (float)x[u].y / 32768.0f,
+                                                 (float)x[u].z / 32768.0f, (float)x[u].w / 32768.0f));
+    }
+    const uint64_t tail = (n4 << 2) + threadIdx.x;
+    if (blockIdx.x == 0 && tail < len) out[tail] = (float)in[tail] / 32768.0f;
 }
 
 __global__ void __launch_bounds__(kThreads) fill_bytes_kernel(uint4* dst, size_t n16, uint32_t word)
@@ -422,7 +464,9 @@ int launch_amplifier(mxl_ctx* ctx, const AmpBatch& b)
 {
     MXL_REQUIRE_DEVICE(ctx);
     if (b.n <= 0 || b.frames == 0) return MXL_OK;
-    dim3 grid(blocks_for((b.frames + 3) / 4), b.n);
+    const uint64_t n4 = b.frames >> 1;
+    unsigned gx = blocks_for((n4 + kAmpUnroll - 1) / kAmpUnroll);
+    dim3 grid(gx ? gx : 1, b.n);
     amplifier_kernel<<<grid, kThreads, 0, ctx->stream>>>(b);
     return check_launch(ctx, "amplifier_kernel");
 }
@@ -467,7 +511,8 @@ int launch_pcm_pack(mxl_ctx* ctx, const float* in, int16_t* out, uint64_t len)
 {
     MXL_REQUIRE_DEVICE(ctx);
     if (len == 0) return MXL_OK;
-    pcm_pack_kernel<<<blocks_for((len + 3) / 4), kThreads, 0, ctx->stream>>>(in, reinterpret_cast<short*>(out), len);
+    const unsigned g = blocks_for(((len >> 2) + kPcmUnroll - 1) / kPcmUnroll);
+    pcm_pack_kernel<<<g ? g : 1, kThreads, 0, ctx->stream>>>(in, reinterpret_cast<short*>(out), len);
     return check_launch(ctx, "pcm_pack_kernel");
 }
 
@@ -475,7 +520,8 @@ int launch_pcm_unpack(mxl_ctx* ctx, const int16_t* in, float* out, uint64_t len)
 {
     MXL_REQUIRE_DEVICE(ctx);
     if (len == 0) return MXL_OK;
-    pcm_unpack_kernel<<<blocks_for((len + 3) / 4), kThreads, 0, ctx->stream>>>(reinterpret_cast<const short*>(in), out, len);
+    const unsigned g = blocks_for(((len >> 2) + kPcmUnroll - 1) / kPcmUnroll);
+    pcm_unpack_kernel<<<g ? g : 1, kThreads, 0, ctx->stream>>>(reinterpret_cast<const short*>(in), out, len);
     return check_launch(ctx, "pcm_unpack_kernel");
 }
 

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/mixlab_b200.h"
+#include "eq_plan.h"
 
 namespace mxl {
 
@@ -74,6 +75,10 @@ struct mxl_ctx {
     // single-launch EqThree plans by chunk length: [Hc, pow_lo[8][10], pow_hi[8][10]]; empty = unusable
     std::map<uint32_t, std::vector<double>> eq_block_plans;
     size_t eq_block_smem = 0;         // dynamic shared memory eq_block_kernel has been configured for
+    // eq_stream_kernel plans by chunk length (eq_plan.h); ok == false = unusable at this sample rate
+    std::map<uint32_t, mxl::EqStreamPlan> eq_stream_plans;
+    uint32_t eq_stream_smem_set = 0;  // bit LC/16: opt-in shared memory size configured
+    std::map<uint32_t, void*> eq_stream_tables;   // device copies of EqStreamPlan::lane_pow by chunk length
 
     // Copy/compute overlap (mxl_ctx_set_copy_overlap): async uploads go to stream_in, async downloads
     // to stream_out, ordered against the compute stream with events:

@@ -113,6 +113,31 @@ struct EqBlockBatch {
 };
 int launch_eq_three_block(mxl_ctx* ctx, const EqBlockBatch& b);
 
+// Time-parallel single launch with dot-product zero pass and skewed exact pass (eq_stream.cu).
+constexpr int kEqStreamThreads = 256;
+struct EqStreamInst {
+    const float* in; float* out;
+    const double* state; double* state_out;      // lo poles[4], hi poles[4], history[3]; double-buffered
+    double g_lo, g_mid, g_hi;
+};
+struct EqStreamBatch {                           // ~7 KB of kernel parameters (limit 32 KB on sm_100)
+    uint64_t frames;
+    uint32_t chunk;                              // LC: 16, 32 or 64
+    uint32_t halo;                               // chunks recomputed ahead of a CTA's own range
+    uint32_t n_chunks;
+    uint32_t lev_lo, lev_hi;                     // scan levels per cascade (<= 8); levels >= 5 cross warps
+    uint32_t back_lo, back_hi;                   // previous warps a warp's start states still hear (<= 3)
+    int32_t n;
+    const double* lane_pow;                      // device: A^(lane+1), [cascade][entry][lane] (EqStreamPlan::lane_pow)
+    double c_lo, c_hi;
+    double pow_lo[8][10];                        // A^(2^d), packed lower-triangular
+    double pow_hi[8][10];
+    double K[8];                                 // zero-input (VSA) end state of a chunk
+    double V[64][8];                             // end-state response to a unit input at sample j
+    EqStreamInst inst[kMaxBatch];
+};
+int launch_eq_stream(mxl_ctx* ctx, const EqStreamBatch& b);
+
 // ---- Envelope (src/module/envelope.rs:91-120) ----
 struct EnvState { int32_t state; int32_t _pad; uint64_t seq; double off_amplitude; };
 struct EnvLaunch {

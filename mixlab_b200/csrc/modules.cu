@@ -693,7 +693,77 @@ static const std::vector<double>& eq_block_plan_for(mxl_ctx* ctx, uint32_t Lc, u
     return ctx->eq_block_plans[key] = plan;
 }
 
-// Single-launch path (eq_block_kernel).  Returns 1 if it ran, 0 if no usable plan exists.
+// Single-launch path (eq_stream_kernel).  Returns 1 if it ran, 0 if no usable plan exists at this
+// sample rate (the cascades would need more than 128 chunks to forget), < 0 on error.
+static int run_eq_stream(mxl_ctx* ctx, mxl_module* const* mods, const IoSet* io, int first, int cnt, uint64_t frames, uint64_t* bytes)
+{
+    // Chunk length: 64 samples per thread once that still fills every SM with a CTA (per-sample scan and
+    // halo overhead halve), else 32 (twice the threads for short calls); 16 only if forced.  A length whose
+    // cascade would not forget inside half a CTA at this sample rate is skipped.  MXL_EQ_STREAM_CHUNK forces one.
+    uint32_t forced = 0;
+    if (const char* e = getenv("MXL_EQ_STREAM_CHUNK")) forced = (uint32_t)atol(e);
+    auto plan_for = [&](uint32_t lc) -> const mxl::EqStreamPlan* {
+        auto it = ctx->eq_stream_plans.find(lc);
+        if (it == ctx->eq_stream_plans.end())
+            it = ctx->eq_stream_plans.emplace(lc, mxl::eq_stream_plan(ctx->sample_rate, lc, k::kEqStreamThreads / 2)).first;
+        return it->second.ok ? &it->second : nullptr;
+    };
+    const mxl::EqStreamPlan* plan = nullptr;
+    if (forced) {
+        plan = plan_for(forced);
+    } else {
+        const mxl::EqStreamPlan* p64 = plan_for(64);
+        const mxl::EqStreamPlan* p32 = plan_for(32);
+        if (p64) {
+            const uint64_t ctas64 = (uint64_t)cnt * (((frames + 63) / 64 + (k::kEqStreamThreads - p64->halo) - 1) / (k::kEqStreamThreads - p64->halo));
+            if (!p32 || ctas64 >= (uint64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148)) plan = p64;
+        }
+        if (!plan) plan = p32 ? p32 : plan_for(16);
+    }
+    if (!plan) return 0;
+    static_assert(sizeof(plan->V) == sizeof(k::EqStreamBatch::V) && sizeof(plan->pow_lo) == sizeof(k::EqStreamBatch::pow_lo), "plan layout");
+    k::EqStreamBatch b{};
+    b.frames = frames;
+    b.chunk = plan->lc;
+    b.halo = plan->halo;
+    b.n_chunks = (uint32_t)((frames + plan->lc - 1) / plan->lc);
+    b.lev_lo = plan->lev_lo;
+    b.lev_hi = plan->lev_hi;
+    b.back_lo = plan->back_lo;
+    b.back_hi = plan->back_hi;
+    b.n = cnt;
+    {   // per-lane powers live in device memory (5 KB per plan, uploaded once)
+        void*& tab = ctx->eq_stream_tables[plan->lc];
+        if (!tab) {
+            MXL_CUDA(cudaMalloc(&tab, sizeof plan->lane_pow));
+            MXL_CUDA(cudaMemcpyAsync(tab, plan->lane_pow, sizeof plan->lane_pow, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        b.lane_pow = (const double*)tab;
+    }
+    b.c_lo = plan->c_lo; b.c_hi = plan->c_hi;
+    memcpy(b.pow_lo, plan->pow_lo, sizeof b.pow_lo);
+    memcpy(b.pow_hi, plan->pow_hi, sizeof b.pow_hi);
+    memcpy(b.K, plan->K, sizeof b.K);
+    memcpy(b.V, plan->V, sizeof b.V);
+    for (int j = 0; j < cnt; j++) {
+        EqThree* m = (EqThree*)mods[first + j];
+        MXL_TRY(m->ensure_state());
+        k::EqStreamInst& e = b.inst[j];
+        e.in = io[first + j].in[0] ? io[first + j].in[0]->dev : nullptr;
+        e.out = io[first + j].out[0]->dev;
+        e.state = m->state_ptr(m->cur);
+        e.state_out = m->state_ptr(m->cur ^ 1);
+        e.g_lo = db_to_linear(m->p.gain_lo_db);            // eq_three.rs:62-64
+        e.g_mid = db_to_linear(m->p.gain_mid_db);
+        e.g_hi = db_to_linear(m->p.gain_hi_db);
+        if (bytes) *bytes += (io[first + j].in[0] ? 4 * frames : 0) + 4 * frames;
+    }
+    MXL_TRY(k::launch_eq_stream(ctx, b));
+    for (int j = 0; j < cnt; j++) ((EqThree*)mods[first + j])->cur ^= 1;
+    return 1;
+}
+
+// Previous single-launch path (eq_block_kernel), kept selectable with MXL_EQ_PATH=block for A/B runs.
 static int run_eq_block(mxl_ctx* ctx, mxl_module* const* mods, const IoSet* io, int first, int cnt, uint64_t frames, uint64_t* bytes)
 {
     uint32_t forced = 0;
@@ -763,7 +833,9 @@ static int run_eq_threes(mxl_ctx* ctx, mxl_module* const* mods, int n, const IoS
         if (frames == 0) continue;
         if (frames >= (1ull << 36)) MXL_FAIL(MXL_ERR_LENGTH, "EqThree: call too long");
         if (!getenv("MXL_EQ_CHUNK")) {                     // MXL_EQ_CHUNK selects the two-launch path
-            const int ran = run_eq_block(ctx, mods, io, first, cnt, frames, bytes);
+            const char* path = getenv("MXL_EQ_PATH");
+            const int ran = (path && !strcmp(path, "block")) ? run_eq_block(ctx, mods, io, first, cnt, frames, bytes)
+                                                             : run_eq_stream(ctx, mods, io, first, cnt, frames, bytes);
             if (ran < 0) return ran;
             if (ran == 1) continue;
         }
