@@ -33,10 +33,10 @@ inline unsigned blocks_for(uint64_t items, int threads = kThreads)
 // ------------------------------------------------------------------------------------------
 // Oscillator: oscillator.rs:73-89
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float osc_sample(uint64_t seq, double sr, double inv_sr, double freq, int wf)
+__device__ __forceinline__ float osc_sample(double seq, double sr, double inv_sr, double freq, int wf)
 {
     // `(t + i as u64) as f64 / SAMPLE_RATE as f64` -- correctly rounded quotient
-    double t0 = div_by_const((double)seq, sr, inv_sr);
+    double t0 = div_by_const(seq, sr, inv_sr);
     double n = t0 * freq;
     double v;
     switch (wf) {
@@ -58,10 +58,13 @@ __global__ void __launch_bounds__(kThreads) oscillator_kernel(const __grid_const
     const double freq = in.freq;
     const int wf = in.waveform;
     if (f0 + 4 <= b.frames) {
-        float s0 = osc_sample(b.t0 + f0 + 0, b.sample_rate, b.inv_sample_rate, freq, wf);
-        float s1 = osc_sample(b.t0 + f0 + 1, b.sample_rate, b.inv_sample_rate, freq, wf);
-        float s2 = osc_sample(b.t0 + f0 + 2, b.sample_rate, b.inv_sample_rate, freq, wf);
-        float s3 = osc_sample(b.t0 + f0 + 3, b.sample_rate, b.inv_sample_rate, freq, wf);
+        // one u64 -> f64 conversion per thread (XU pipe); the neighbours are exact +1.0 steps below 2^53
+        const double q0 = (double)(b.t0 + f0);
+        const bool exact = (b.t0 + f0 + 3) < (1ull << 53);
+        float s0 = osc_sample(q0, b.sample_rate, b.inv_sample_rate, freq, wf);
+        float s1 = osc_sample(exact ? q0 + 1.0 : (double)(b.t0 + f0 + 1), b.sample_rate, b.inv_sample_rate, freq, wf);
+        float s2 = osc_sample(exact ? q0 + 2.0 : (double)(b.t0 + f0 + 2), b.sample_rate, b.inv_sample_rate, freq, wf);
+        float s3 = osc_sample(exact ? q0 + 3.0 : (double)(b.t0 + f0 + 3), b.sample_rate, b.inv_sample_rate, freq, wf);
         if (in.mono) st4(in.mono + f0, make_float4(s0, s1, s2, s3));
         if (in.stereo) {
             st4(in.stereo + 2 * f0, make_float4(s0, s0, s1, s1));
@@ -69,7 +72,7 @@ __global__ void __launch_bounds__(kThreads) oscillator_kernel(const __grid_const
         }
     } else {
         for (uint64_t f = f0; f < b.frames; f++) {
-            float s = osc_sample(b.t0 + f, b.sample_rate, b.inv_sample_rate, freq, wf);
+            float s = osc_sample((double)(b.t0 + f), b.sample_rate, b.inv_sample_rate, freq, wf);
             if (in.mono) in.mono[f] = s;
             if (in.stereo) { in.stereo[2 * f] = s; in.stereo[2 * f + 1] = s; }
         }
@@ -79,10 +82,10 @@ __global__ void __launch_bounds__(kThreads) oscillator_kernel(const __grid_const
 // ------------------------------------------------------------------------------------------
 // FmSine: fm_sine.rs:45-53
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float fm_sample(uint64_t seq, double sr, double inv_sr, double mid, double amp, float x)
+__device__ __forceinline__ float fm_sample(double seq, double sr, double inv_sr, double mid, double amp, float x)
 {
-    double t = div_by_const((double)seq, sr, inv_sr);
-    double co = (mid + amp * (double)x) * 2.0 * kPi;
+    double t = div_by_const(seq, sr, inv_sr);
+    double co = (mid + amp * (double)x) * kTwoPi;      // (a * 2.0) * PI == a * (2.0 * PI): the doubling is exact
     return (float)sin_f64(co * t);
 }
 
@@ -93,16 +96,18 @@ __global__ void __launch_bounds__(kThreads) fm_sine_kernel(const __grid_constant
     if (f0 >= b.frames) return;
     if (f0 + 4 <= b.frames) {
         float4 x = in.in ? ldg_stream(in.in + f0) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float s0 = fm_sample(b.t0 + f0 + 0, b.sample_rate, b.inv_sample_rate, in.freq_mid, in.freq_amp, x.x);
-        float s1 = fm_sample(b.t0 + f0 + 1, b.sample_rate, b.inv_sample_rate, in.freq_mid, in.freq_amp, x.y);
-        float s2 = fm_sample(b.t0 + f0 + 2, b.sample_rate, b.inv_sample_rate, in.freq_mid, in.freq_amp, x.z);
-        float s3 = fm_sample(b.t0 + f0 + 3, b.sample_rate, b.inv_sample_rate, in.freq_mid, in.freq_amp, x.w);
+        const double q0 = (double)(b.t0 + f0);
+        const bool exact = (b.t0 + f0 + 3) < (1ull << 53);
+        float s0 = fm_sample(q0, b.sample_rate, b.inv_sample_rate, in.freq_mid, in.freq_amp, x.x);
+        float s1 = fm_sample(exact ? q0 + 1.0 : (double)(b.t0 + f0 + 1), b.sample_rate, b.inv_sample_rate, in.freq_mid, in.freq_amp, x.y);
+        float s2 = fm_sample(exact ? q0 + 2.0 : (double)(b.t0 + f0 + 2), b.sample_rate, b.inv_sample_rate, in.freq_mid, in.freq_amp, x.z);
+        float s3 = fm_sample(exact ? q0 + 3.0 : (double)(b.t0 + f0 + 3), b.sample_rate, b.inv_sample_rate, in.freq_mid, in.freq_amp, x.w);
         st4(in.out + 2 * f0, make_float4(s0, s0, s1, s1));
         st4(in.out + 2 * f0 + 4, make_float4(s2, s2, s3, s3));
     } else {
         for (uint64_t f = f0; f < b.frames; f++) {
             float x = in.in ? in.in[f] : 0.f;
-            float s = fm_sample(b.t0 + f, b.sample_rate, b.inv_sample_rate, in.freq_mid, in.freq_amp, x);
+            float s = fm_sample((double)(b.t0 + f), b.sample_rate, b.inv_sample_rate, in.freq_mid, in.freq_amp, x);
             in.out[2 * f] = s;
             in.out[2 * f + 1] = s;
         }
@@ -297,8 +302,35 @@ __global__ void __launch_bounds__(kMeterThreads) meter_kernel(const __grid_const
     float pk0 = 0.f, pk1 = 0.f;
     double sq0 = 0.0, sq1 = 0.0;
     int clip = 0;
-    if (in.in) {
-        constexpr int kU = 4;                  // frames in flight per thread (a tick of 800 frames = 2 rounds)
+    if (in.in && ((f_begin & 1) == 0) && (reinterpret_cast<uintptr_t>(in.in) & 15) == 0) {
+        // the slot starts 16-byte aligned: float4 = two frames, four vectors in flight per thread
+        // (a tick of 800 frames is one round of 128 threads x 4 vectors, predicated)
+        constexpr int kU = 4;
+        const uint64_t v_begin = f_begin >> 1, v_end = f_end >> 1;
+        for (uint64_t vb = v_begin; vb < v_end; vb += kU * kMeterThreads) {
+            float4 s[kU];
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const uint64_t v = vb + (uint64_t)u * kMeterThreads + threadIdx.x;
+                s[u] = v < v_end ? ldg_stream(in.in + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                pk0 = fmaxf(pk0, fmaxf(fabsf(s[u].x), fabsf(s[u].z)));   // fmaxf drops NaN like the oracle's `a > peak`
+                pk1 = fmaxf(pk1, fmaxf(fabsf(s[u].y), fabsf(s[u].w)));
+                sq0 += (double)s[u].x * (double)s[u].x;
+                sq1 += (double)s[u].y * (double)s[u].y;
+                sq0 += (double)s[u].z * (double)s[u].z;
+                sq1 += (double)s[u].w * (double)s[u].w;
+            }
+        }
+        if (((f_end - f_begin) & 1) && threadIdx.x == 0) {              // odd frame count: last frame
+            const float2 t = ldg_stream2(in.in + 2 * (f_end - 1));
+            pk0 = fmaxf(pk0, fabsf(t.x)); pk1 = fmaxf(pk1, fabsf(t.y));
+            sq0 += (double)t.x * (double)t.x; sq1 += (double)t.y * (double)t.y;
+        }
+    } else if (in.in) {
+        constexpr int kU = 4;                  // frames in flight per thread
         for (uint64_t base = f_begin; base < f_end; base += kU * kMeterThreads) {
             float2 s[kU];
 #pragma unroll
@@ -308,14 +340,16 @@ __global__ void __launch_bounds__(kMeterThreads) meter_kernel(const __grid_const
             }
 #pragma unroll
             for (int u = 0; u < kU; u++) {
-                pk0 = fmaxf(pk0, fabsf(s[u].x));   // fmaxf drops NaN like the oracle's `a > peak`
+                pk0 = fmaxf(pk0, fabsf(s[u].x));
                 pk1 = fmaxf(pk1, fabsf(s[u].y));
                 sq0 += (double)s[u].x * (double)s[u].x;
                 sq1 += (double)s[u].y * (double)s[u].y;
-                clip |= (s[u].x < -1.0f || s[u].x > 1.0f || s[u].y < -1.0f || s[u].y > 1.0f) ? 1 : 0;
             }
         }
     }
+    // output_device.rs:192-194: `s < -1.0 || s > 1.0` for any sample <=> the peak of |s| exceeds 1 (a NaN
+    // sample fails both tests there and is dropped by fmaxf here)
+    clip = (pk0 > 1.0f || pk1 > 1.0f) ? 1 : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         pk0 = fmaxf(pk0, __shfl_xor_sync(0xffffffffu, pk0, o));

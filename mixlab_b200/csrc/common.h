@@ -78,6 +78,7 @@ struct mxl_ctx {
     // eq_stream_kernel plans by chunk length (eq_plan.h); ok == false = unusable at this sample rate
     std::map<uint32_t, mxl::EqStreamPlan> eq_stream_plans;
     uint32_t eq_stream_smem_set = 0;  // bit LC/16: opt-in shared memory size configured
+    uint32_t env_epoch = 0;           // Envelope launches so far (tags the look-back flags of a launch)
     std::map<uint32_t, void*> eq_stream_tables;   // device copies of EqStreamPlan::lane_pow by chunk length
 
     // Copy/compute overlap (mxl_ctx_set_copy_overlap): async uploads go to stream_in, async downloads

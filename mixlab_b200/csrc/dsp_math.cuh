@@ -11,6 +11,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define MXL_HD __host__ __device__ __forceinline__
@@ -23,68 +24,120 @@ namespace mxl {
 // std::f64::consts::PI
 constexpr double kPi = 3.14159265358979323846264338327950288;
 
-// pi/2 split into three doubles: P1 = RN(pi/2), P2 = RN(pi/2 - P1), P3 = RN(pi/2 - P1 - P2)
-constexpr double kPio2_1 = 1.5707963267948966;        // 0x3ff921fb54442d18
-constexpr double kPio2_2 = 6.123233995736766e-17;     // 0x3c91a62633145c07
-constexpr double kPio2_3 = -1.4973849048591698e-33;   // 0xb91f1976b7ed8fbc
-constexpr double kTwoOverPi = 0.6366197723675814;     // 0x3fe45f306dc9c883
+// pi split into three doubles: P1 = RN(pi), P2 = RN(pi - P1), P3 = RN(pi - P1 - P2)
+constexpr double kPi_1 = 3.141592653589793;           // 0x400921fb54442d18
+constexpr double kPi_2 = 1.2246467991473532e-16;      // 0x3ca1a62633145c07
+constexpr double kPi_3 = -2.9947698097183397e-33;     // 0xb92f1976b7ed8fbc
+constexpr double kOneOverPi = 0.3183098861837907;     // 0x3fd45f306dc9c883
 
-// Minimax coefficients of the classic fdlibm k_sin.c / k_cos.c kernels on [-pi/4, pi/4]
-// (public constants; relative error below 2^-57).
-constexpr double kS1 = -1.66666666666666324348e-01, kS2 = 8.33333333332248946124e-03,
-                 kS3 = -1.98412698298579493134e-04, kS4 = 2.75573137070700676789e-06,
-                 kS5 = -2.50507602534068634195e-08, kS6 = 1.58969099521155010221e-10;
-constexpr double kC1 = 4.16666666666666019037e-02, kC2 = -1.38888888888741095749e-03,
-                 kC3 = 2.48015872894767294178e-05, kC4 = -2.75573143513906633035e-07,
-                 kC5 = 2.08757232129817482790e-09, kC6 = -1.13596475577881948265e-11;
+// Taylor coefficients of sin(r) = r + r z (T1 + z (T2 + ... z T10)), z = r^2: -1/3!, 1/5!, ... 1/21!.
+// On |r| <= pi/2 the truncation error r^23/23! stays below 1.3e-18.
+constexpr double kT1 = -1.66666666666666666667e-01, kT2 = 8.33333333333333333333e-03,
+                 kT3 = -1.98412698412698412698e-04, kT4 = 2.75573192239858906526e-06,
+                 kT5 = -2.50521083854417187751e-08, kT6 = 1.60590438368216145994e-10,
+                 kT7 = -7.64716373181981647590e-13, kT8 = 2.81145725434552076320e-15,
+                 kT9 = -8.22063524662432971696e-18, kT10 = 1.95729410633912612308e-20;
 
-// sin(x) for |x| < 2^45 with about 1 ulp error, branch-free apart from the range guard.
+// low / high 32 bits of a double's bit pattern
+MXL_HD uint32_t low_word(double t)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__double2loint(t);
+#else
+    uint64_t u;
+    memcpy(&u, &t, sizeof u);
+    return (uint32_t)u;
+#endif
+}
+MXL_HD uint32_t high_word(double t)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__double2hiint(t);
+#else
+    uint64_t u;
+    memcpy(&u, &t, sizeof u);
+    return (uint32_t)(u >> 32);
+#endif
+}
+MXL_HD double flip_sign_if(double v, uint32_t odd)
+{
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(v) ^ (int)(odd << 31), __double2loint(v));
+#else
+    uint64_t u;
+    memcpy(&u, &v, sizeof u);
+    u ^= (uint64_t)(odd & 1u) << 63;
+    memcpy(&v, &u, sizeof u);
+    return v;
+#endif
+}
+
+// sin(x) for 0 < |x| < 2^45 with 1-2 ulp error, branch-free.
 //
 // Why not CUDA's sin(): its fast path ends at |x| = 105615 and the Payne-Hanek slow path behind it
 // spills to local memory.  Oscillator phases 2*pi*f*t/SR pass that bound after seconds of audio
 // (oscillator.rs:25-27,74-75), so the common case would be the slow path.  With FMA a three-term
-// Cody-Waite reduction stays exact far beyond that: x - q*P1 is exactly representable for
-// |x| >= pi/4 (both are multiples of 2^-52 and the difference is below 1), and the P2, P3 terms
-// only add relative rounding errors of 2^-53.
-MXL_HD double sin_reduced(double x, double* cos_out)
+// Cody-Waite reduction stays accurate far beyond that: the first step x - q*P1 is one rounding of
+// an exact difference no larger than pi/2, and the P2, P3 terms only add relative errors of 2^-53.
+//
+// Cost matters: these kernels would be HBM-bound but for the f64 work (64 FP64 lanes/clk/SM) and
+// plain instruction issue, so
+//   * q = round(x / pi) comes from adding 1.5*2^52 (the sum's low word is q mod 2^32) -- no
+//     round-to-integer or float->int conversion, which run on the 16-lane XU pipe;
+//   * the reduction is modulo pi, not pi/2: sin(x) = (-1)^q sin(r), |r| <= pi/2, one odd polynomial
+//     in a single Horner chain -- no second (cosine) kernel and no per-quadrant selects; the sign
+//     is one XOR on the high word.
+constexpr double kRoundMagic = 6755399441055744.0;    // 1.5 * 2^52
+
+// On the device the constants live in constant memory: FP64 instructions take a constant-bank operand
+// directly, while a literal costs two 32-bit moves per use (measured: a third of the oscillator
+// kernel's issue slots went into re-materialising literals, and the kernel was issue-bound).
+#if defined(__CUDACC__)
+static __constant__ double c_sin_tab[15] = {kOneOverPi, kRoundMagic, kPi_1, kPi_2, kPi_3,
+                                            kT1, kT2, kT3, kT4, kT5, kT6, kT7, kT8, kT9, kT10};
+#endif
+
+MXL_HD double sin_reduced(double x)
 {
-    double q = rint(x * kTwoOverPi);
-    double r = fma(-q, kPio2_1, x);
-    r = fma(-q, kPio2_2, r);
-    r = fma(-q, kPio2_3, r);
-    double z = r * r;
-    // sin kernel
-    double w = z * z;
-    double ps = fma(z, fma(z, kS4, kS3), kS2) + z * w * fma(z, kS6, kS5);
-    double v = z * r;
-    double s = fma(v, fma(z, ps, kS1), r);
-    // cos kernel
-    double pc = z * fma(z, fma(z, kC3, kC2), kC1) + (w * w) * fma(z, fma(z, kC6, kC5), kC4);
-    double hz = 0.5 * z;
-    double wc = 1.0 - hz;
-    double c = wc + (((1.0 - wc) - hz) + z * pc);
-    // quadrant
-    long long n = (long long)q;
-    double rs = (n & 1) ? c : s;
-    double rc = (n & 1) ? s : c;
-    if (n & 2) rs = -rs;
-    if ((n + 1) & 2) rc = -rc;
-    if (cos_out) *cos_out = rc;
-    return rs;
+#if defined(__CUDA_ARCH__)
+    const double* c = c_sin_tab;
+#else
+    const double c[15] = {kOneOverPi, kRoundMagic, kPi_1, kPi_2, kPi_3, kT1, kT2, kT3, kT4, kT5, kT6, kT7, kT8, kT9, kT10};
+#endif
+    const double t = fma(x, c[0], c[1]);
+    const double q = t - c[1];
+    const uint32_t n = low_word(t);
+    double r = fma(-q, c[2], x);
+    r = fma(-q, c[3], r);
+    r = fma(-q, c[4], r);
+    const double z = r * r;
+    double p = fma(c[14], z, c[13]);
+    p = fma(p, z, c[12]);
+    p = fma(p, z, c[11]);
+    p = fma(p, z, c[10]);
+    p = fma(p, z, c[9]);
+    p = fma(p, z, c[8]);
+    p = fma(p, z, c[7]);
+    p = fma(p, z, c[6]);
+    p = fma(p, z, c[5]);
+    const double res = fma(r * z, p, r);
+    return flip_sign_if(res, n & 1u);
 }
 
 MXL_HD double sin_f64(double x)
 {
-    if (!(fabs(x) < 35184372088832.0))   // 2^45, also catches NaN / inf
+    const uint32_t hi = high_word(x) & 0x7fffffffu;     // integer tests: keep them off the FP64 pipe
+    if (hi >= 0x42c00000u)                              // |x| >= 2^45, inf or NaN
         return sin(x);
-    if (x == 0.0) return x;               // sin(-0.0) = -0.0: Square takes the sign BIT (oscillator.rs:15-23)
-    return sin_reduced(x, nullptr);
+    if ((hi | low_word(x)) == 0u) return x;             // sin(-0.0) = -0.0: Square takes the sign BIT (oscillator.rs:15-23)
+    return sin_reduced(x);
 }
 
 // oscillator.rs:15-23: `is_sign_positive` tests the sign bit, so -0.0 -> -1.0, NaN by its sign bit.
 MXL_HD double sign_bit_f64(double v) { return signbit(v) ? -1.0 : 1.0; }
-// oscillator.rs:25-27
-MXL_HD double wave_sine(double n) { return sin_f64(n * 2.0 * kPi); }
+// oscillator.rs:25-27.  n * 2.0 is exact, so (n * 2.0) * PI and n * (2.0 * PI) round the same real number
+constexpr double kTwoPi = 2.0 * kPi;
+MXL_HD double wave_sine(double n) { return sin_f64(n * kTwoPi); }
 // oscillator.rs:30-32
 MXL_HD double wave_saw(double n) { return 2.0 * (n - floor(0.5 + n)); }
 // oscillator.rs:35-37

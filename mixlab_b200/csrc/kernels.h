@@ -140,17 +140,26 @@ int launch_eq_stream(mxl_ctx* ctx, const EqStreamBatch& b);
 
 // ---- Envelope (src/module/envelope.rs:91-120) ----
 struct EnvState { int32_t state; int32_t _pad; uint64_t seq; double off_amplitude; };
-struct EnvLaunch {
+// look-back descriptor of one tile: three words (epoch << 2 | status) << 32 | key -- last event, latest two transitions
+struct EnvTile { unsigned long long ev, tr_a, tr_b; };
+struct EnvInst {
     const float* in; float* out;
-    EnvState* state;                 // device, persistent
-    EnvState* state_next;            // device staging for the state after the call
-    uint32_t* scratch_a; uint32_t* scratch_b; uint32_t* block_a; uint32_t* block_b;
-    uint64_t t0; uint32_t frames; uint32_t _pad;
-    double sample_rate;
-    double attack_ms, decay_ms, sustain, release_ms;
+    const EnvState* state;           // machine state before the call
+    EnvState* state_out;             // after the call (other half of a double buffer)
+    EnvTile* tiles;                  // device, one per tile of the call; flags carry the launch epoch
+    unsigned long long* ticket;      // device: tiles handed out so far (never reset)
+    unsigned long long ticket_base;  // value of *ticket when this launch starts
+    double attack_ms, inv_attack, inv_decay, sustain, inv_release;
 };
-int launch_envelope(mxl_ctx* ctx, const EnvLaunch& p);
-uint32_t envelope_blocks(uint32_t frames);
+struct EnvBatch {
+    uint64_t t0, frames;
+    double sample_rate, inv_sample_rate;
+    uint32_t epoch;                  // launch number of this context: stale tile flags never match
+    int32_t n;
+    EnvInst inst[kMaxBatch];
+};
+int launch_envelope(mxl_ctx* ctx, const EnvBatch& b);
+uint32_t envelope_tiles(uint64_t frames);
 
 // ---- Meter (new): one record per tick slot ----
 struct MeterRecord { float peak[2]; int32_t clip; int32_t _pad; double sumsq[2]; };

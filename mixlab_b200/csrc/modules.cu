@@ -52,6 +52,9 @@ struct Envelope : mxl_module {                        // src/module/envelope.rs
     mxl_envelope_params p{25.0, 500.0, 0.8, 200.0};   // protocol lib.rs:318-327
     DevBuf state, scratch;
     bool state_init = false;
+    int cur = 0;                                      // which half of the state double buffer is current
+    size_t tiles_cap = 0;                             // look-back descriptors allocated (scratch: [ticket][tiles])
+    unsigned long long tickets = 0;                   // tiles launched so far (mirrors the device ticket counter)
     Envelope(const mxl_envelope_params* in)
     {
         kind = MXL_MOD_ENVELOPE;
@@ -875,34 +878,60 @@ static int run_eq_threes(mxl_ctx* ctx, mxl_module* const* mods, int n, const IoS
 // --- Envelope ---
 static int run_envelopes(mxl_ctx* ctx, mxl_module* const* mods, int n, uint64_t t, const IoSet* io, uint64_t* bytes)
 {
-    for (int i = 0; i < n; i++) {
-        Envelope* m = (Envelope*)mods[i];
-        NEED_IO(io[i], 1, 1, "Envelope");
-        MXL_TRY(expect_input(io[i].in[0], MXL_LINE_MONO, "Envelope"));
-        MXL_TRY(expect_output(io[i].out[0], MXL_LINE_MONO, "Envelope"));
-        const uint64_t f = io[i].in[0] ? io[i].in[0]->frames : io[i].out[0]->frames;   // let len = input.len() (envelope.rs:95)
-        MXL_TRY(need_len(io[i].out[0], f, "Envelope output"));
-        if (f == 0) continue;
-        if (f >= 0xffffff00ull) MXL_FAIL(MXL_ERR_LENGTH, "Envelope: call longer than 2^32 samples");
-        MXL_TRY(m->ensure_state());
-        const uint32_t nb = k::envelope_blocks((uint32_t)f);
-        const size_t words = 2 * (size_t)f + 2 * (size_t)nb + 8;
-        MXL_TRY(m->scratch.ensure(ctx, words * sizeof(uint32_t)));
-        k::EnvLaunch p{};
-        p.in = io[i].in[0] ? io[i].in[0]->dev : nullptr;
-        p.out = io[i].out[0]->dev;
-        p.state = (k::EnvState*)m->state.p;
-        p.state_next = (k::EnvState*)m->state.p + 1;
-        p.scratch_a = (uint32_t*)m->scratch.p;
-        p.scratch_b = p.scratch_a + f;
-        p.block_a = p.scratch_b + f;
-        p.block_b = p.block_a + nb;
-        p.t0 = t; p.frames = (uint32_t)f;
-        p.sample_rate = (double)ctx->sample_rate;
-        p.attack_ms = m->p.attack_ms; p.decay_ms = m->p.decay_ms;
-        p.sustain = m->p.sustain_amplitude; p.release_ms = m->p.release_ms;
-        MXL_TRY(k::launch_envelope(ctx, p));
-        if (bytes) *bytes += (io[i].in[0] ? 4 * f : 0) + 4 * f;
+    int i = 0;
+    while (i < n) {
+        k::EnvBatch b{};
+        uint64_t frames = 0;
+        int cnt = 0, first = i;
+        for (; i < n && cnt < k::kMaxBatch; i++) {
+            NEED_IO(io[i], 1, 1, "Envelope");
+            MXL_TRY(expect_input(io[i].in[0], MXL_LINE_MONO, "Envelope"));
+            MXL_TRY(expect_output(io[i].out[0], MXL_LINE_MONO, "Envelope"));
+            const uint64_t f = io[i].in[0] ? io[i].in[0]->frames : io[i].out[0]->frames;   // let len = input.len() (envelope.rs:95)
+            MXL_TRY(need_len(io[i].out[0], f, "Envelope output"));
+            if (f >= 0x7ffffff0ull) MXL_FAIL(MXL_ERR_LENGTH, "Envelope: call longer than 2^31 samples");
+            if (cnt && f != frames) break;
+            frames = f;
+            cnt++;
+        }
+        if (frames == 0) continue;
+        const uint32_t nt = k::envelope_tiles(frames);
+        for (int j = 0; j < cnt; j++) {
+            Envelope* m = (Envelope*)mods[first + j];
+            MXL_TRY(m->ensure_state());
+            if (m->tiles_cap < nt) {                       // [ticket counter (16 B)][tiles]; zeroed once: epoch 0 is never used
+                const size_t cap = (size_t)nt + nt / 2 + 16;
+                MXL_TRY(m->scratch.ensure(ctx, 16 + cap * sizeof(k::EnvTile)));
+                MXL_CUDA(cudaMemsetAsync(m->scratch.p, 0, 16 + cap * sizeof(k::EnvTile), ctx->stream));
+                m->tiles_cap = cap;
+                m->tickets = 0;
+            }
+            k::EnvInst& e = b.inst[j];
+            e.in = io[first + j].in[0] ? io[first + j].in[0]->dev : nullptr;
+            e.out = io[first + j].out[0]->dev;
+            e.state = (const k::EnvState*)m->state.p + m->cur;
+            e.state_out = (k::EnvState*)m->state.p + (m->cur ^ 1);
+            e.ticket = (unsigned long long*)m->scratch.p;
+            e.tiles = (k::EnvTile*)((char*)m->scratch.p + 16);
+            e.ticket_base = m->tickets;
+            e.attack_ms = m->p.attack_ms;
+            e.inv_attack = 1.0 / m->p.attack_ms;           // envelope.rs:43,48,55: `1.0 / x_ms * ms`, left to right
+            e.inv_decay = 1.0 / m->p.decay_ms;
+            e.sustain = m->p.sustain_amplitude;
+            e.inv_release = 1.0 / m->p.release_ms;
+            if (bytes) *bytes += (io[first + j].in[0] ? 4 * frames : 0) + 4 * frames;
+        }
+        b.t0 = t; b.frames = frames; b.n = cnt;
+        b.sample_rate = (double)ctx->sample_rate;
+        b.inv_sample_rate = 1.0 / (double)ctx->sample_rate;
+        b.epoch = ++ctx->env_epoch;
+        if ((b.epoch << 2) == 0) b.epoch = ctx->env_epoch = 1;   // 30-bit epoch wrapped: flags of 2^30 launches ago are long gone
+        MXL_TRY(k::launch_envelope(ctx, b));
+        for (int j = 0; j < cnt; j++) {
+            Envelope* m = (Envelope*)mods[first + j];
+            m->cur ^= 1;
+            m->tickets += nt;
+        }
     }
     return MXL_OK;
 }
@@ -1251,7 +1280,7 @@ int envelope_state(mxl_module* m, int32_t* state, uint64_t* seq, double* off_amp
     Envelope* e = (Envelope*)m;
     MXL_TRY(e->ensure_state());
     k::EnvState s;
-    MXL_CUDA(cudaMemcpyAsync(&s, e->state.p, sizeof s, cudaMemcpyDeviceToHost, m->ctx->stream));
+    MXL_CUDA(cudaMemcpyAsync(&s, (const k::EnvState*)e->state.p + e->cur, sizeof s, cudaMemcpyDeviceToHost, m->ctx->stream));
     MXL_CUDA(cudaStreamSynchronize(m->ctx->stream));
     if (state) *state = s.state;
     if (seq) *seq = s.seq;

@@ -287,7 +287,7 @@ def gate_pattern(seed, frames, density):
     return g
 
 
-@pytest.mark.parametrize("frames", [1, 3, 800, 1024, 1025, 5000, 70000])
+@pytest.mark.parametrize("frames", [1, 3, 800, 1024, 1025, 2047, 2048, 2049, 5000, 70000])
 @pytest.mark.parametrize("density", [0.0005, 0.01, 0.5])
 def test_envelope_random_gates(mxl, oracle, ctx48, frames, density):
     g = gate_pattern(frames * 7 + int(density * 1e4), frames, density)
@@ -323,6 +323,44 @@ def test_envelope_state_across_calls(mxl, oracle, ctx48):
     out = ctx48.line(mxl.LINE_MONO, 800)
     mod.run_tick(frames, [None], [out])          # disconnected gate = zeros: releases
     want2 = env.run(frames, 48000.0, 10.0, 100.0, 0.5, 50.0, np.zeros(800, np.float32))
+    assert bits_equal(out.download(), want2)
+
+
+@pytest.mark.parametrize("kind", ["sparse", "dense", "all_on", "all_off", "inert", "tile_edges"])
+def test_envelope_long_call_many_tiles(mxl, oracle, ctx48, kind):
+    """A call of 1.2 M samples = 586 tiles of the streaming kernel: the look-back crosses several
+    32-tile windows; events sit on tile boundaries; whole tiles are inert or all events."""
+    frames = 1_200_003
+    if kind == "sparse":
+        g = gate_pattern(5, frames, 4e-6)
+    elif kind == "dense":
+        g = gate_pattern(6, frames, 0.3)
+    elif kind == "all_on":
+        g = np.ones(frames, np.float32)
+    elif kind == "all_off":
+        g = np.zeros(frames, np.float32)
+        g[0] = 1.0
+    elif kind == "inert":
+        g = np.full(frames, 0.25, np.float32)
+        g[7] = 1.0
+    else:
+        g = np.full(frames, 0.5, np.float32)
+        for k in range(1, frames // 2048, 3):
+            g[k * 2048 - 1] = 1.0
+            g[k * 2048] = 0.0
+            g[k * 2048 + 2047] = 1.0 if k % 2 else 0.0
+    env = oracle.Envelope()
+    want = env.run(123456789, 48000.0, 25.0, 500.0, 0.8, 200.0, g)
+    mod = ctx48.module(mxl.MOD_ENVELOPE, (25.0, 500.0, 0.8, 200.0))
+    out = ctx48.line(mxl.LINE_MONO, frames)
+    gl = ctx48.mono(g)
+    mod.run_tick(123456789, [gl], [out])
+    assert bits_equal(out.download(), want)
+    st, seq, off = mod.envelope_state()
+    assert st == env.state.state and (st == 0 or seq == env.state.seq) and (st != 2 or off == env.state.off_amplitude)
+    # the same module again: state carries, tile descriptors of the first launch are stale (epoch)
+    want2 = env.run(123456789 + frames, 48000.0, 25.0, 500.0, 0.8, 200.0, g[::-1].copy())
+    mod.run_tick(123456789 + frames, [ctx48.mono(g[::-1].copy())], [out])
     assert bits_equal(out.download(), want2)
 
 

@@ -128,6 +128,30 @@ def test_all_audio_modules_graph(mxl, oracle, ctx48):
     g.destroy()
 
 
+def test_batched_envelopes_one_launch(mxl, oracle, ctx48):
+    """Five Envelopes on one dependency level = one batched launch (blockIdx.y = instance): square-wave
+    gates of different rates (+1.0 opens, -1.0 is inert), an always-open and an always-closed gate."""
+    spt, n_ticks = 800, 16
+    d = W.GraphDesc("envs")
+    envs = []
+    for k, (freq, wave) in enumerate([(3.0, mxl.WAVE_SQUARE), (41.0, mxl.WAVE_SQUARE), (0.7, mxl.WAVE_SQUARE),
+                                       (1.0, mxl.WAVE_ON), (1.0, mxl.WAVE_OFF)]):
+        osc = d.add("Oscillator", (freq, wave, 0))
+        env = d.add("Envelope", (5.0 + k, 80.0 + 10 * k, 0.6, 30.0 + k))
+        d.connect(env, 0, osc, 0)
+        envs.append(env)
+    g, ids = W.build_graph(ctx48, d)
+    before = ctx48.launch_count
+    g.run_ticks(0, n_ticks)
+    assert ctx48.launch_count - before == 2            # one Oscillator launch, one Envelope launch
+    g.run_ticks(n_ticks, n_ticks)                      # state carries into a second call
+    for env in envs:
+        got = g.output(ids[env], 0).download()
+        want, _, _ = oracle_run(oracle, d, 48000, spt, 0, 2 * n_ticks, (env, 0), 1)
+        assert mismatch_count(got, want[spt * n_ticks:]) == 0
+    g.destroy()
+
+
 def test_cycle_reads_disconnected(mxl, oracle, ctx48):
     # engine.rs:440-442,479-482
     d = W.GraphDesc("cycle")
