@@ -275,6 +275,30 @@ MXL_API int mxl_frame_to_rgba(const mxl_frame *frame, uint8_t *rgba_host);
 /* Letterboxed bicubic rescale of `src` into a new frame of (out_w,out_h): DynamicScaler::scale
  * (src/video/encode.rs:338-397).  Returns a retained `src` when sizes are equal (342-345). */
 MXL_API mxl_frame *mxl_frame_scale(mxl_frame *src, uint32_t out_w, uint32_t out_h);
+/* The same for n frames that share one source size: all planes of all frames in ONE launch of the
+ * tiled scaler (what VideoMixer does with the frames of a multi-tick call).  dst[i] receives a new
+ * frame each (a retained src[i] when the sizes already agree). */
+MXL_API int mxl_frames_scale(mxl_ctx *ctx, mxl_frame *const *src, mxl_frame **dst, uint32_t n,
+                             uint32_t out_w, uint32_t out_h);
+
+/* Device-resident RGBA8 pictures (width*height*4 bytes each, rows packed), the output of the
+ * compositor's colour-converting path (BASELINE config 3).  Not a reference type: the reference
+ * keeps everything yuv420p (video_mixer.rs:282-283). */
+typedef struct mxl_rgba mxl_rgba;
+MXL_API mxl_rgba *mxl_rgba_alloc(mxl_ctx *ctx, uint32_t width, uint32_t height, uint32_t n_pictures);
+MXL_API int mxl_rgba_free(mxl_rgba *pics);
+MXL_API void *mxl_rgba_device_ptr(mxl_rgba *pics, uint32_t index);
+MXL_API int mxl_rgba_download(const mxl_rgba *pics, uint32_t first, uint32_t count, uint8_t *host);
+MXL_API int mxl_rgba_download_async(const mxl_rgba *pics, uint32_t first, uint32_t count, uint8_t *host);
+/* VideoMixer's crossfade (video_mixer.rs:150-239: out = (a*f + b*(255-f)) / 255 per byte, a missing
+ * layer = blank) of n layer pairs, written directly as RGBA8 of the blend -- one pass, one launch:
+ * the layers are read once and no yuv420p composite is stored.  a[i] / b[i] may be NULL.  Bit-exact
+ * to mxl_frame_to_rgba of the VideoMixer output for the same inputs. */
+MXL_API int mxl_video_compose_rgba(mxl_ctx *ctx, mxl_frame *const *a, mxl_frame *const *b, uint32_t n,
+                                   double fader, mxl_rgba *out, uint32_t first_picture);
+/* yuv420p -> RGBA8 of n frames of one size, one launch (the compose path with a single layer). */
+MXL_API int mxl_frames_to_rgba(mxl_ctx *ctx, mxl_frame *const *frames, uint32_t n, mxl_rgba *out,
+                               uint32_t first_picture);
 
 /* ---- graph: Workspace + Engine::run_tick, src/engine/workspace.rs, src/engine.rs:400-510 ------ */
 

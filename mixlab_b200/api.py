@@ -197,6 +197,14 @@ def lib():
         "mxl_pcm_pack_i16": (i32, [vp, vp, vp, u64]),
         "mxl_frame_to_rgba": (i32, [vp, vp]),
         "mxl_frame_scale": (vp, [vp, u32, u32]),
+        "mxl_frames_scale": (i32, [vp, C.POINTER(vp), C.POINTER(vp), u32, u32, u32]),
+        "mxl_rgba_alloc": (vp, [vp, u32, u32, u32]),
+        "mxl_rgba_free": (i32, [vp]),
+        "mxl_rgba_device_ptr": (vp, [vp, u32]),
+        "mxl_rgba_download": (i32, [vp, u32, u32, vp]),
+        "mxl_rgba_download_async": (i32, [vp, u32, u32, vp]),
+        "mxl_video_compose_rgba": (i32, [vp, C.POINTER(vp), C.POINTER(vp), u32, dbl, vp, u32]),
+        "mxl_frames_to_rgba": (i32, [vp, C.POINTER(vp), u32, vp, u32]),
         "mxl_graph_create": (vp, [vp]),
         "mxl_graph_destroy": (None, [vp]),
         "mxl_graph_add_module": (i32, [vp, vp]),
@@ -367,6 +375,29 @@ class Context:
             fr.upload_raw(data)
         return fr
 
+    def rgba(self, width, height, n_pictures):
+        return RgbaPictures(self, width, height, n_pictures)
+
+    def frames_scale(self, frames, out_w, out_h):
+        """Batched letterbox scaler: one launch for all planes of all frames (mxl_frames_scale)."""
+        n = len(frames)
+        src = (C.c_void_p * n)(*[f.h for f in frames])
+        dst = (C.c_void_p * n)()
+        check(lib().mxl_frames_scale(self.h, src, dst, n, out_w, out_h))
+        return [Frame(self, handle=dst[i]) for i in range(n)]
+
+    def compose_rgba(self, layers_a, layers_b, fader, out, first=0):
+        """Crossfade + colour conversion in one pass (mxl_video_compose_rgba); None = missing layer."""
+        n = len(layers_a)
+        a = (C.c_void_p * n)(*[f.h if f is not None else None for f in layers_a])
+        b = (C.c_void_p * n)(*[f.h if f is not None else None for f in layers_b])
+        check(lib().mxl_video_compose_rgba(self.h, a, b, n, float(fader), out.h, first))
+
+    def frames_to_rgba(self, frames, out, first=0):
+        n = len(frames)
+        a = (C.c_void_p * n)(*[f.h for f in frames])
+        check(lib().mxl_frames_to_rgba(self.h, a, n, out.h, first))
+
     def module(self, kind, params=None):
         return Module(self, kind, params)
 
@@ -414,6 +445,35 @@ class Line:
         if self.h and self.owned:
             lib().mxl_line_free(self.h)
         self.h = None
+
+
+class RgbaPictures:
+    """n device-resident RGBA8 pictures (mxl_rgba)."""
+
+    def __init__(self, ctx, width, height, n):
+        self.ctx, self.width, self.height, self.n = ctx, width, height, n
+        self.h = lib().mxl_rgba_alloc(ctx.h, width, height, n)
+        if not self.h:
+            raise MxlError(ERR_INVALID, last_error())
+
+    @property
+    def picture_bytes(self):
+        return self.width * self.height * 4
+
+    def download(self, first=0, count=None):
+        count = self.n - first if count is None else count
+        out = np.empty(count * self.picture_bytes, np.uint8)
+        check(lib().mxl_rgba_download(self.h, first, count, _ptr(out)))
+        return out.reshape(count, self.picture_bytes)
+
+    def download_async(self, host_ptr, first=0, count=None):
+        count = self.n - first if count is None else count
+        check(lib().mxl_rgba_download_async(self.h, first, count, host_ptr))
+
+    def free(self):
+        if self.h:
+            lib().mxl_rgba_free(self.h)
+            self.h = None
 
 
 class Frame:

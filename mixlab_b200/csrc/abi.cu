@@ -173,4 +173,125 @@ mxl_frame* mxl_frame_scale(mxl_frame* src, uint32_t out_w, uint32_t out_h)
     return frame_scale(src, out_w, out_h);
 }
 
+int mxl_frames_scale(mxl_ctx* ctx, mxl_frame* const* src, mxl_frame** dst, uint32_t n, uint32_t out_w, uint32_t out_h)
+{
+    if (!ctx || (n && (!src || !dst))) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
+    if (!ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "mxl_frames_scale: context has no CUDA device; there is no CPU fallback");
+    if (out_w == 0 || out_h == 0) MXL_FAIL(MXL_ERR_INVALID, "mxl_frames_scale: empty target %ux%u", out_w, out_h);
+    for (uint32_t i = 0; i < n; i++)
+        if (!src[i] || src[i]->ctx != ctx) MXL_FAIL(MXL_ERR_INVALID, "mxl_frames_scale: frame %u is NULL or of another context", i);
+    MXL_TRY(ctx->activate());
+    MXL_TRY(ctx->compute_begin());
+    const int st = frames_scale(ctx, src, dst, n, out_w, out_h);
+    MXL_TRY(ctx->compute_end());
+    return st;
+}
+
+struct mxl_rgba {
+    mxl_ctx* ctx = nullptr;
+    uint32_t width = 0, height = 0, n = 0;
+    uint8_t* dev = nullptr;
+    void* jobs = nullptr;          // device staging for ComposeRgbaJob arrays
+    size_t jobs_cap = 0;
+    size_t picture_bytes() const { return (size_t)width * height * 4; }
+};
+
+mxl_rgba* mxl_rgba_alloc(mxl_ctx* ctx, uint32_t width, uint32_t height, uint32_t n_pictures)
+{
+    if (!ctx || !ctx->has_device() || width == 0 || height == 0 || n_pictures == 0) {
+        set_error("mxl_rgba_alloc: needs a device context and a non-empty size");
+        return nullptr;
+    }
+    if (ctx->activate() != MXL_OK) return nullptr;
+    mxl_rgba* r = new mxl_rgba();
+    r->ctx = ctx; r->width = width; r->height = height; r->n = n_pictures;
+    if (cudaMalloc(&r->dev, r->picture_bytes() * n_pictures) != cudaSuccess) {
+        set_error("mxl_rgba_alloc: out of device memory (%zu bytes)", r->picture_bytes() * n_pictures);
+        delete r;
+        return nullptr;
+    }
+    return r;
+}
+
+int mxl_rgba_free(mxl_rgba* pics)
+{
+    if (!pics) return MXL_OK;
+    pics->ctx->activate();
+    cudaStreamSynchronize(pics->ctx->stream);
+    cudaFree(pics->dev);
+    if (pics->jobs) cudaFree(pics->jobs);
+    delete pics;
+    return MXL_OK;
+}
+
+void* mxl_rgba_device_ptr(mxl_rgba* pics, uint32_t index)
+{
+    return pics && index < pics->n ? pics->dev + pics->picture_bytes() * index : nullptr;
+}
+
+int mxl_rgba_download_async(const mxl_rgba* pics, uint32_t first, uint32_t count, uint8_t* host)
+{
+    if (!pics || !host) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
+    if ((uint64_t)first + count > pics->n) MXL_FAIL(MXL_ERR_LENGTH, "pictures %u..%u of %u", first, first + count, pics->n);
+    mxl_ctx* ctx = pics->ctx;
+    MXL_TRY(ctx->activate());
+    cudaStream_t s;
+    MXL_TRY(ctx->download_stream(&s));
+    const size_t bytes = pics->picture_bytes() * count;
+    MXL_CUDA(cudaMemcpyAsync(host, pics->dev + pics->picture_bytes() * first, bytes, cudaMemcpyDeviceToHost, s));
+    ctx->d2h_bytes += bytes;
+    return MXL_OK;
+}
+
+int mxl_rgba_download(const mxl_rgba* pics, uint32_t first, uint32_t count, uint8_t* host)
+{
+    MXL_TRY(mxl_rgba_download_async(pics, first, count, host));
+    return mxl_ctx_synchronize(pics->ctx);
+}
+
+static int compose_rgba(mxl_ctx* ctx, mxl_frame* const* a, mxl_frame* const* b, uint32_t n, uint32_t fade, mxl_rgba* out, uint32_t first)
+{
+    if (!ctx || !out || (n && !a)) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
+    if (!ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "compose_rgba: context has no CUDA device; there is no CPU fallback");
+    if (out->ctx != ctx) MXL_FAIL(MXL_ERR_INVALID, "compose_rgba: pictures belong to another context");
+    if ((uint64_t)first + n > out->n) MXL_FAIL(MXL_ERR_LENGTH, "pictures %u..%u of %u", first, first + n, out->n);
+    if (n == 0) return MXL_OK;
+    mxl_frame_layout lay;
+    frame_layout_yuv420p(out->width, out->height, &lay);
+    std::vector<k::ComposeRgbaJob> jobs(n);
+    for (uint32_t i = 0; i < n; i++) {
+        const mxl_frame* fa = a[i];
+        const mxl_frame* fb = b ? b[i] : nullptr;
+        for (const mxl_frame* f : {fa, fb})
+            if (f && (f->ctx != ctx || f->layout.width != out->width || f->layout.height != out->height))
+                MXL_FAIL(MXL_ERR_INVALID, "compose_rgba: layer %u is %ux%u, pictures are %ux%u", i, f->layout.width, f->layout.height, out->width, out->height);
+        jobs[i] = k::ComposeRgbaJob{fa ? fa->dev : nullptr, fb ? fb->dev : nullptr, out->dev + out->picture_bytes() * (first + i), fade, 0};
+    }
+    MXL_TRY(ctx->activate());
+    if (out->jobs_cap < n) {
+        if (out->jobs) { MXL_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(out->jobs); out->jobs = nullptr; }
+        MXL_CUDA(cudaMalloc(&out->jobs, (size_t)n * 2 * sizeof(k::ComposeRgbaJob)));
+        out->jobs_cap = (size_t)n * 2;
+    }
+    MXL_TRY(ctx->compute_begin());
+    MXL_CUDA(cudaMemcpyAsync(out->jobs, jobs.data(), n * sizeof(k::ComposeRgbaJob), cudaMemcpyHostToDevice, ctx->stream));
+    const int st = k::launch_compose_rgba(ctx, lay, (const k::ComposeRgbaJob*)out->jobs, n);
+    MXL_TRY(ctx->compute_end());
+    return st;
+}
+
+int mxl_video_compose_rgba(mxl_ctx* ctx, mxl_frame* const* a, mxl_frame* const* b, uint32_t n, double fader, mxl_rgba* out, uint32_t first_picture)
+{
+    if (n && !b) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
+    return compose_rgba(ctx, a, b, n, mxl_fader_to_u8(fader), out, first_picture);      // video_mixer.rs:168
+}
+
+int mxl_frames_to_rgba(mxl_ctx* ctx, mxl_frame* const* frames, uint32_t n, mxl_rgba* out, uint32_t first_picture)
+{
+    for (uint32_t i = 0; frames && i < n; i++)
+        if (!frames[i]) MXL_FAIL(MXL_ERR_INVALID, "mxl_frames_to_rgba: frame %u is NULL", i);
+    // fade = 255: out = (a*255 + blank*0) / 255 = a exactly
+    return compose_rgba(ctx, frames, nullptr, n, 255u, out, first_picture);
+}
+
 }  // extern "C"

@@ -33,21 +33,22 @@ inline unsigned blocks_for(uint64_t items, int threads = kThreads)
 // ------------------------------------------------------------------------------------------
 // Oscillator: oscillator.rs:73-89
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float osc_sample(double seq, double sr, double inv_sr, double freq, int wf)
+// `(t + i as u64) as f64 / SAMPLE_RATE as f64` (correctly rounded quotient) `* freq`: oscillator.rs:74-75
+__device__ __forceinline__ double osc_phase(double seq, double sr, double inv_sr, double freq)
 {
-    // `(t + i as u64) as f64 / SAMPLE_RATE as f64` -- correctly rounded quotient
-    double t0 = div_by_const(seq, sr, inv_sr);
-    double n = t0 * freq;
-    double v;
+    return div_by_const(seq, sr, inv_sr) * freq;
+}
+
+__device__ __forceinline__ float osc_wave(double n, int wf)
+{
     switch (wf) {
-    case MXL_WAVE_SINE: v = wave_sine(n); break;
-    case MXL_WAVE_SQUARE: v = sign_bit_f64(wave_sine(n)); break;
-    case MXL_WAVE_SAW: v = wave_saw(n); break;
-    case MXL_WAVE_TRIANGLE: v = wave_triangle(n); break;
-    case MXL_WAVE_ON: v = 1.0; break;
-    default: v = 0.0; break;
+    case MXL_WAVE_SINE: return (float)wave_sine(n);
+    case MXL_WAVE_SQUARE: return (float)sign_bit_f64(wave_sine(n));
+    case MXL_WAVE_SAW: return (float)wave_saw(n);
+    case MXL_WAVE_TRIANGLE: return (float)wave_triangle(n);
+    case MXL_WAVE_ON: return 1.0f;
+    default: return 0.0f;
     }
-    return (float)v;
 }
 
 __global__ void __launch_bounds__(kThreads) oscillator_kernel(const __grid_constant__ OscBatch b)
@@ -55,24 +56,36 @@ __global__ void __launch_bounds__(kThreads) oscillator_kernel(const __grid_const
     const OscInst& in = b.inst[blockIdx.y];
     uint64_t f0 = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
     if (f0 >= b.frames) return;
-    const double freq = in.freq;
+    const double freq = in.freq, sr = b.sample_rate, inv_sr = b.inv_sample_rate;
     const int wf = in.waveform;
     if (f0 + 4 <= b.frames) {
         // one u64 -> f64 conversion per thread (XU pipe); the neighbours are exact +1.0 steps below 2^53
         const double q0 = (double)(b.t0 + f0);
         const bool exact = (b.t0 + f0 + 3) < (1ull << 53);
-        float s0 = osc_sample(q0, b.sample_rate, b.inv_sample_rate, freq, wf);
-        float s1 = osc_sample(exact ? q0 + 1.0 : (double)(b.t0 + f0 + 1), b.sample_rate, b.inv_sample_rate, freq, wf);
-        float s2 = osc_sample(exact ? q0 + 2.0 : (double)(b.t0 + f0 + 2), b.sample_rate, b.inv_sample_rate, freq, wf);
-        float s3 = osc_sample(exact ? q0 + 3.0 : (double)(b.t0 + f0 + 3), b.sample_rate, b.inv_sample_rate, freq, wf);
-        if (in.mono) st4(in.mono + f0, make_float4(s0, s1, s2, s3));
+        double n[4];
+        n[0] = osc_phase(q0, sr, inv_sr, freq);
+#pragma unroll
+        for (int j = 1; j < 4; j++) n[j] = osc_phase(exact ? q0 + (double)j : (double)(b.t0 + f0 + j), sr, inv_sr, freq);
+        float s[4];
+        // the waveform is the same for every sample of an instance: branch once, not per sample
+        if (wf == MXL_WAVE_SINE) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) s[j] = (float)wave_sine(n[j]);
+        } else if (wf == MXL_WAVE_SAW) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) s[j] = (float)wave_saw(n[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) s[j] = osc_wave(n[j], wf);
+        }
+        if (in.mono) st4(in.mono + f0, make_float4(s[0], s[1], s[2], s[3]));
         if (in.stereo) {
-            st4(in.stereo + 2 * f0, make_float4(s0, s0, s1, s1));
-            st4(in.stereo + 2 * f0 + 4, make_float4(s2, s2, s3, s3));
+            st4(in.stereo + 2 * f0, make_float4(s[0], s[0], s[1], s[1]));
+            st4(in.stereo + 2 * f0 + 4, make_float4(s[2], s[2], s[3], s[3]));
         }
     } else {
         for (uint64_t f = f0; f < b.frames; f++) {
-            float s = osc_sample((double)(b.t0 + f), b.sample_rate, b.inv_sample_rate, freq, wf);
+            float s = osc_wave(osc_phase((double)(b.t0 + f), sr, inv_sr, freq), wf);
             if (in.mono) in.mono[f] = s;
             if (in.stereo) { in.stereo[2 * f] = s; in.stereo[2 * f + 1] = s; }
         }

@@ -78,6 +78,12 @@ struct mxl_ctx {
     // eq_stream_kernel plans by chunk length (eq_plan.h); ok == false = unusable at this sample rate
     std::map<uint32_t, mxl::EqStreamPlan> eq_stream_plans;
     uint32_t eq_stream_smem_set = 0;  // bit LC/16: opt-in shared memory size configured
+    size_t scale_smem = 0;            // dynamic shared memory scale_tiled_kernel has been configured for
+    // scaler tap tables by (source length, destination length): device [pos int32 x n][coef int16 x 4n]
+    std::map<uint64_t, void*> scale_tables;
+    std::map<uint64_t, std::vector<int32_t>> scale_positions;   // host copies of the first-tap columns (tile bounds)
+    void* scale_jobs = nullptr;       // device staging for ScaleJob arrays
+    size_t scale_jobs_cap = 0;
     uint32_t env_epoch = 0;           // Envelope launches so far (tags the look-back flags of a launch)
     std::map<uint32_t, void*> eq_stream_tables;   // device copies of EqStreamPlan::lane_pow by chunk length
 

@@ -309,6 +309,8 @@ int mxl_ctx_destroy(mxl_ctx* ctx)
         cudaStreamSynchronize(ctx->stream);
         if (ctx->flush_buf) cudaFree(ctx->flush_buf);
         for (auto& kv : ctx->eq_stream_tables) if (kv.second) cudaFree(kv.second);
+        for (auto& kv : ctx->scale_tables) if (kv.second) cudaFree(kv.second);
+        if (ctx->scale_jobs) cudaFree(ctx->scale_jobs);
         for (auto& kv : ctx->frame_pool)
             for (uint8_t* p : kv.second) cudaFree(p);
         if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);

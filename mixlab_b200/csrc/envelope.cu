@@ -10,14 +10,14 @@
 //       TriggerOff{off: p, ..}) and, for an off, the transition q before it:
 //       off_amplitude = amplitude(TriggerOn{on: q}, p) -- a "latest two" scan over transition keys.
 // Both scans have trivial combine steps (max / latest-two), so they run as decoupled look-back
-// scans inside ONE kernel: a CTA owns a tile of 2048 consecutive samples (8 per thread, read once
-// with two float4 loads), scans inside the tile with warp shuffles, publishes its tile aggregate,
+// scans inside ONE kernel: a CTA owns a tile of 4096 consecutive samples (16 per thread, read once
+// with four float4 loads), scans inside the tile with warp shuffles, publishes its tile aggregate,
 // and looks back over the preceding tiles 32 at a time (ballot + shuffle, no loops over lanes)
 // until the carry is decided: the nearest tile with any event decides scan (1), two transitions or
 // a tile whose inclusive value is known decide scan (3).  Every thread then starts the REFERENCE
-// state machine from its exact incoming state and walks its 8 samples, evaluating amplitude()
+// state machine from its exact incoming state and walks its 16 samples, evaluating amplitude()
 // with the reference's f64 expressions (bit-exact: only IEEE +,-,*,/).
-// Line traffic is the algorithmic 8 B/sample; tile descriptors add 24 B per 2048 samples.  Tiles
+// Line traffic is the algorithmic 8 B/sample; tile descriptors add 24 B per 4096 samples.  Tiles
 // are handed out by an atomic ticket, so a tile only ever waits for tiles that already run.
 #include "dsp_math.cuh"
 #include "kernels.h"
@@ -28,7 +28,7 @@ namespace k {
 namespace {
 
 constexpr int kEnvThreads = 256;
-constexpr int kEnvPerThread = 8;
+constexpr int kEnvPerThread = 16;
 constexpr int kEnvTileSamples = kEnvThreads * kEnvPerThread;
 constexpr int kEnvWarps = kEnvThreads / 32;
 
@@ -113,13 +113,15 @@ __global__ void __launch_bounds__(kEnvThreads, 6) envelope_kernel(const __grid_c
     const EnvParams p{b.sample_rate, b.inv_sample_rate, in.attack_ms, in.inv_attack, in.inv_decay, in.sustain, in.inv_release};
     const EnvState st0 = *in.state;                        // machine state before the call
 
-    // ---- my 8 samples ----
+    // ---- my samples ----
     const uint64_t base = (uint64_t)tile * kEnvTileSamples + (uint64_t)tid * kEnvPerThread;
     float x[kEnvPerThread];
     if (in.in && base + kEnvPerThread <= b.frames && (reinterpret_cast<uintptr_t>(in.in) & 15) == 0) {
-        const float4 a = *reinterpret_cast<const float4*>(in.in + base);
-        const float4 c = *reinterpret_cast<const float4*>(in.in + base + 4);
-        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = c.x; x[5] = c.y; x[6] = c.z; x[7] = c.w;
+#pragma unroll
+        for (int v = 0; v < kEnvPerThread / 4; v++) {
+            const float4 a = *reinterpret_cast<const float4*>(in.in + base + 4 * v);
+            x[4 * v] = a.x; x[4 * v + 1] = a.y; x[4 * v + 2] = a.z; x[4 * v + 3] = a.w;
+        }
     } else {
 #pragma unroll
         for (int j = 0; j < kEnvPerThread; j++)            // disconnected input = zeros (io.rs:8-9); past the end = inert
@@ -301,8 +303,9 @@ __global__ void __launch_bounds__(kEnvThreads, 6) envelope_kernel(const __grid_c
 #pragma unroll
             for (int j = 0; j < kEnvPerThread; j++) y[j] = 0.f;
         }
-        *reinterpret_cast<float4*>(in.out + base) = make_float4(y[0], y[1], y[2], y[3]);
-        *reinterpret_cast<float4*>(in.out + base + 4) = make_float4(y[4], y[5], y[6], y[7]);
+#pragma unroll
+        for (int v = 0; v < kEnvPerThread / 4; v++)
+            *reinterpret_cast<float4*>(in.out + base + 4 * v) = make_float4(y[4 * v], y[4 * v + 1], y[4 * v + 2], y[4 * v + 3]);
         if (base + kEnvPerThread == b.frames) *in.state_out = s;
     } else {
         // the reference state machine, sample by sample (envelope.rs:96-117)

@@ -187,6 +187,29 @@ int launch_resample_h(mxl_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh
 int launch_resample_v(mxl_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, uint32_t sstride,
                       uint8_t* dst, uint32_t dh, uint32_t dstride, const int32_t* pos, const int16_t* coef);
 
+// Tiled letterbox scaler: all planes of a batch of frames in one launch (video_kernels.cu)
+struct ScaleJob { const uint8_t* src; uint8_t* dst; };            // frame base pointers
+struct ScalePlane {
+    uint32_t src_off, src_w, src_h, src_stride;                   // plane inside the source frame
+    uint32_t dst_off, dst_w, dst_h, dst_stride;                   // scaled rectangle inside the destination frame
+    const int32_t* xpos; const int16_t* xcoef;                    // device tables: first tap and 4 x 14-bit weights per output column
+    const int32_t* ypos; const int16_t* ycoef;                    // ... per output row
+    uint32_t tiles_x, tiles_y, tile_base, _pad;
+};
+struct ScaleLaunch {
+    ScalePlane pl[3];
+    uint32_t total_tiles;
+    uint32_t region_pitch, region_rows;                           // staging bounds over all tiles (pitch % 16 == 0)
+    uint32_t _pad;
+    const ScaleJob* jobs;                                         // device
+};
+int launch_scale_tiled(mxl_ctx* ctx, const ScaleLaunch& L, uint32_t n_jobs);
+void scale_tile_dims(uint32_t* tw, uint32_t* th);
+
+// Crossfade + yuv420p -> RGBA8 in one pass
+struct ComposeRgbaJob { const uint8_t* a; const uint8_t* b; uint8_t* rgba; uint32_t fade; uint32_t _pad; };
+int launch_compose_rgba(mxl_ctx* ctx, const mxl_frame_layout& lay, const ComposeRgbaJob* jobs_dev, uint32_t n_jobs);
+
 // L2 flush helper
 int launch_fill_bytes(mxl_ctx* ctx, void* dst, size_t bytes, uint8_t value);
 

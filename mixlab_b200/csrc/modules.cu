@@ -1056,54 +1056,127 @@ static void bicubic_table(uint32_t src_n, uint32_t dst_n, std::vector<int32_t>& 
     }
 }
 
-// DynamicScaler::scale (src/video/encode.rs:338-397)
+// Device copy of one axis' tap table, cached per (source length, destination length): the tables only
+// depend on the two lengths, so a live session builds each of them once.
+static int axis_table(mxl_ctx* ctx, uint32_t src_n, uint32_t dst_n, const int32_t** pos, const int16_t** coef, const std::vector<int32_t>** host_pos)
+{
+    const uint64_t key = ((uint64_t)src_n << 32) | dst_n;
+    const size_t pos_bytes = (((size_t)dst_n * sizeof(int32_t)) + 7) & ~(size_t)7;
+    void*& dev = ctx->scale_tables[key];
+    if (!dev) {
+        std::vector<int32_t> p;
+        std::vector<int16_t> c;
+        bicubic_table(src_n, dst_n, p, c);
+        std::vector<uint8_t> blob(pos_bytes + c.size() * sizeof(int16_t), 0);
+        memcpy(blob.data(), p.data(), p.size() * sizeof(int32_t));
+        memcpy(blob.data() + pos_bytes, c.data(), c.size() * sizeof(int16_t));
+        MXL_CUDA(cudaMalloc(&dev, blob.size()));
+        // pageable source: the copy is staged before the call returns, `blob` may die
+        MXL_CUDA(cudaMemcpyAsync(dev, blob.data(), blob.size(), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->scale_positions[key] = std::move(p);
+    }
+    *pos = (const int32_t*)dev;
+    *coef = (const int16_t*)((const uint8_t*)dev + pos_bytes);
+    *host_pos = &ctx->scale_positions[key];
+    return MXL_OK;
+}
+
+// DynamicScaler::scale (src/video/encode.rs:338-397) for a batch of frames that share source and target
+// sizes: one blank fill per frame that gets letterbox bars, then ONE launch of the tiled scaler for all
+// planes of all frames.  dst[i] receives a new frame (or a retained src[i] when the sizes already agree).
+int frames_scale(mxl_ctx* ctx, mxl_frame* const* src, mxl_frame** dst, uint32_t n, uint32_t out_w, uint32_t out_h)
+{
+    if (n == 0) return MXL_OK;
+    const mxl_frame_layout& sl = src[0]->layout;
+    for (uint32_t i = 0; i < n; i++) {
+        dst[i] = nullptr;
+        if (!src[i] || src[i]->layout.width != sl.width || src[i]->layout.height != sl.height)
+            MXL_FAIL(MXL_ERR_INVALID, "frames_scale: frames of one batch must share a size");
+    }
+    if (sl.width == out_w && sl.height == out_h) {                                              // encode.rs:342-345
+        for (uint32_t i = 0; i < n; i++) dst[i] = frame_retain(src[i]);
+        return MXL_OK;
+    }
+    mxl_scale_geometry g;
+    MXL_TRY(mxl_scale_geometry_yuv420p(sl.width, sl.height, out_w, out_h, &g));
+    // The reference scales into AvFrame::blank (encode.rs:382).  The blank fill can be skipped only when the
+    // scaled picture covers every byte of the target, stride padding included.
+    mxl_frame_layout tl;
+    frame_layout_yuv420p(out_w, out_h, &tl);
+    const bool bars = g.scaled_w != out_w || g.scaled_h != out_h || tl.stride[0] != out_w || tl.stride[1] != (out_w + 1) / 2;
+    std::vector<k::ScaleJob> jobs(n);
+    for (uint32_t i = 0; i < n; i++) {
+        dst[i] = bars ? mxl_frame_blank(ctx, out_w, out_h) : frame_alloc(ctx, out_w, out_h);   // encode.rs:382
+        if (!dst[i]) {
+            for (uint32_t j = 0; j < i; j++) { frame_release(dst[j]); dst[j] = nullptr; }
+            return MXL_ERR_OOM;
+        }
+        jobs[i] = k::ScaleJob{src[i]->dev, dst[i]->dev};
+    }
+    if (g.scaled_w == 0 || g.scaled_h == 0) return MXL_OK;
+    const mxl_frame_layout& dl = dst[0]->layout;
+    k::ScaleLaunch L{};
+    uint32_t tw, th;
+    k::scale_tile_dims(&tw, &th);
+    uint32_t tile_base = 0, max_span = 16, max_rows = 1;
+    for (int p = 0; p < 3; p++) {
+        // subframe addressing (codec/src/ffmpeg/frame.rs:219-281): offsets are chroma-aligned already
+        const uint32_t sh = p ? 1 : 0;
+        k::ScalePlane& P = L.pl[p];
+        P.src_off = (uint32_t)sl.offset[p];
+        P.src_w = p ? (sl.width + 1) / 2 : sl.width;
+        P.src_h = sl.plane_h[p];
+        P.src_stride = sl.stride[p];
+        P.dst_w = g.scaled_w >> sh;
+        P.dst_h = g.scaled_h >> sh;
+        P.dst_stride = dl.stride[p];
+        P.dst_off = (uint32_t)(dl.offset[p] + (uint64_t)(g.letterbox_y >> sh) * dl.stride[p] + (g.letterbox_x >> sh));
+        P.tile_base = tile_base;
+        if (P.dst_w == 0 || P.dst_h == 0) { P.tiles_x = P.tiles_y = 0; continue; }
+        const std::vector<int32_t>*hx, *hy;
+        MXL_TRY(axis_table(ctx, P.src_w, P.dst_w, &P.xpos, &P.xcoef, &hx));
+        MXL_TRY(axis_table(ctx, P.src_h, P.dst_h, &P.ypos, &P.ycoef, &hy));
+        P.tiles_x = (P.dst_w + tw - 1) / tw;
+        P.tiles_y = (P.dst_h + th - 1) / th;
+        tile_base += P.tiles_x * P.tiles_y;
+        auto clampi = [](int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); };
+        for (uint32_t t = 0; t < P.tiles_x; t++) {          // staged bytes per row: from the 16-aligned first tap to the last tap
+            const uint32_t x0 = t * tw, x1 = std::min(x0 + tw, P.dst_w) - 1;
+            const int lo = clampi((*hx)[x0], (int)P.src_w - 1) & ~15, hi = clampi((*hx)[x1] + 3, (int)P.src_w - 1);
+            max_span = std::max<uint32_t>(max_span, (uint32_t)((hi - lo) / 16 + 1) * 16);
+        }
+        for (uint32_t t = 0; t < P.tiles_y; t++) {
+            const uint32_t y0 = t * th, y1 = std::min(y0 + th, P.dst_h) - 1;
+            const int lo = clampi((*hy)[y0], (int)P.src_h - 1), hi = clampi((*hy)[y1] + 3, (int)P.src_h - 1);
+            max_rows = std::max<uint32_t>(max_rows, (uint32_t)(hi - lo + 1));
+        }
+    }
+    L.total_tiles = tile_base;
+    L.region_pitch = max_span;
+    L.region_rows = max_rows;
+    if (ctx->scale_jobs_cap < n) {
+        if (ctx->scale_jobs) { MXL_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->scale_jobs); ctx->scale_jobs = nullptr; }
+        const size_t cap = std::max<size_t>(256, (size_t)n * 2);
+        MXL_CUDA(cudaMalloc(&ctx->scale_jobs, cap * sizeof(k::ScaleJob)));
+        ctx->scale_jobs_cap = cap;
+    }
+    MXL_CUDA(cudaMemcpyAsync(ctx->scale_jobs, jobs.data(), n * sizeof(k::ScaleJob), cudaMemcpyHostToDevice, ctx->stream));
+    L.jobs = (const k::ScaleJob*)ctx->scale_jobs;
+    const int st = k::launch_scale_tiled(ctx, L, n);
+    if (st != MXL_OK) {
+        for (uint32_t i = 0; i < n; i++) { frame_release(dst[i]); dst[i] = nullptr; }
+        return st;
+    }
+    return MXL_OK;
+}
+
 mxl_frame* frame_scale(mxl_frame* src, uint32_t out_w, uint32_t out_h)
 {
     if (!src) { set_error("frame_scale: NULL frame"); return nullptr; }
-    mxl_ctx* ctx = src->ctx;
-    if (src->layout.width == out_w && src->layout.height == out_h) return frame_retain(src);   // encode.rs:342-345
-    mxl_scale_geometry g;
-    if (mxl_scale_geometry_yuv420p(src->layout.width, src->layout.height, out_w, out_h, &g) != MXL_OK) return nullptr;
-    mxl_frame* dst = mxl_frame_blank(ctx, out_w, out_h);                                        // encode.rs:382
-    if (!dst) return nullptr;
-    if (g.scaled_w == 0 || g.scaled_h == 0) return dst;
-    // per plane: horizontal pass into a temporary, vertical pass into the letterboxed sub-frame
-    // (subframe addressing: codec/src/ffmpeg/frame.rs:219-281; offsets are chroma-aligned already)
-    for (int p = 0; p < 3; p++) {
-        const uint32_t sh = p ? 1 : 0;
-        const uint32_t sw = p ? (src->layout.width + 1) / 2 : src->layout.width;
-        const uint32_t shh = src->layout.plane_h[p];
-        const uint32_t dw = g.scaled_w >> sh, dh = g.scaled_h >> sh;
-        if (dw == 0 || dh == 0) continue;
-        std::vector<int32_t> xpos, ypos;
-        std::vector<int16_t> xco, yco;
-        bicubic_table(sw, dw, xpos, xco);
-        bicubic_table(shh, dh, ypos, yco);
-        uint8_t* tmp = nullptr;
-        int32_t* dpos = nullptr;
-        int16_t* dco = nullptr;
-        const size_t tmp_bytes = (size_t)dw * shh;
-        const size_t tab_n = (size_t)dw + dh;
-        bool ok = cudaMalloc(&tmp, tmp_bytes) == cudaSuccess && cudaMalloc(&dpos, tab_n * sizeof(int32_t)) == cudaSuccess &&
-                  cudaMalloc(&dco, tab_n * 4 * sizeof(int16_t)) == cudaSuccess;
-        if (ok) {
-            ok = cudaMemcpyAsync(dpos, xpos.data(), dw * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
-                 cudaMemcpyAsync(dpos + dw, ypos.data(), dh * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
-                 cudaMemcpyAsync(dco, xco.data(), (size_t)dw * 4 * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
-                 cudaMemcpyAsync(dco + (size_t)dw * 4, yco.data(), (size_t)dh * 4 * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
-        }
-        if (ok) {
-            uint8_t* dplane = dst->dev + dst->layout.offset[p] + (uint64_t)(g.letterbox_y >> sh) * dst->layout.stride[p] + (g.letterbox_x >> sh);
-            ok = k::launch_resample_h(ctx, src->dev + src->layout.offset[p], sw, shh, src->layout.stride[p], tmp, dw, dw, dpos, dco) == MXL_OK &&
-                 k::launch_resample_v(ctx, tmp, dw, shh, dw, dplane, dh, dst->layout.stride[p], dpos + dw, dco + (size_t)dw * 4) == MXL_OK;
-        }
-        cudaStreamSynchronize(ctx->stream);      // tables and temporaries die here (scaler retargets are rare)
-        cudaFree(tmp); cudaFree(dpos); cudaFree(dco);
-        if (!ok) {
-            if (!*last_error()) set_error("frame_scale: CUDA failure");
-            frame_release(dst);
-            return nullptr;
-        }
+    mxl_frame* dst = nullptr;
+    if (frames_scale(src->ctx, &src, &dst, 1, out_w, out_h) != MXL_OK) {
+        if (!*last_error()) set_error("frame_scale: CUDA failure");
+        return nullptr;
     }
     return dst;
 }

@@ -147,6 +147,84 @@ def test_mixed_sizes_letterbox_geometry(mxl, oracle, ctx48):
     assert np.array_equal(out.download_raw(), oracle.video_crossfade(lay, da, want, 127))
 
 
+def oracle_scale(oracle, data, lay_in, out_w, out_h):
+    """DynamicScaler::scale (encode.rs:338-397) from oracle pieces: blank target, per-plane resample into
+    the letterboxed sub-frame."""
+    sw_, sh_, lx, ly = oracle.scale_geometry(lay_in.width, lay_in.height, out_w, out_h)
+    lay = oracle.frame_layout(out_w, out_h)
+    want = oracle.frame_blank(lay)
+    for p in range(3):
+        sh = 0 if p == 0 else 1
+        sw = lay_in.width if p == 0 else (lay_in.width + 1) // 2
+        shh = lay_in.plane_h[p]
+        dw, dh = sw_ >> sh, sh_ >> sh
+        if dw == 0 or dh == 0:
+            continue
+        src = data[lay_in.offset[p]:lay_in.offset[p] + lay_in.stride[p] * lay_in.plane_h[p]]
+        dst = oracle.bicubic_plane(src, sw, shh, lay_in.stride[p], dw, dh, dw)
+        plane = want[lay.offset[p]:lay.offset[p] + lay.stride[p] * lay.plane_h[p]].reshape(lay.plane_h[p], lay.stride[p])
+        plane[(ly >> sh):(ly >> sh) + dh, (lx >> sh):(lx >> sh) + dw] = dst.reshape(dh, dw)
+    return want
+
+
+@pytest.mark.parametrize("src,dst", [((640, 480), (1280, 720)), ((1920, 1080), (1280, 720)), ((1280, 720), (1920, 1080)),
+                                     ((3840, 2160), (1920, 1080)), ((70, 50), (560, 350)), ((560, 350), (70, 50)),
+                                     ((1920, 1080), (480, 270)), ((34, 18), (36, 20)), ((1000, 1000), (1920, 1080)),
+                                     ((1920, 1080), (3840, 2160)), ((2, 2), (64, 64)), ((1366, 768), (1920, 1080))])
+def test_tiled_scaler_matches_two_pass_definition(mxl, oracle, ctx48, src, dst):
+    """Every tile of the fused scaler (clamped aprons, ragged last tiles, up- and down-scaling, letterbox
+    bars on either axis) against the oracle's plain two-pass definition.  UNPINNED arithmetic (stands in
+    for swscale), pinned geometry."""
+    fr, data, lay_in = make_frame(ctx48, oracle, src[0], src[1], src[0] * 31 + dst[1])
+    got = fr.scale(dst[0], dst[1])
+    assert (got.layout.width, got.layout.height) == dst
+    assert np.array_equal(got.download_raw(), oracle_scale(oracle, data, lay_in, dst[0], dst[1]))
+
+
+def test_batched_scaler_one_launch(mxl, oracle, ctx48):
+    frames = [make_frame(ctx48, oracle, 640, 360, 900 + k) for k in range(6)]
+    before = ctx48.launch_count
+    out = ctx48.frames_scale([f[0] for f in frames], 1280, 720)        # same aspect: no bars, no blank fill
+    assert ctx48.launch_count - before == 1
+    for k, fr in enumerate(out):
+        assert np.array_equal(fr.download_raw(), oracle_scale(oracle, frames[k][1], frames[k][2], 1280, 720)), k
+    same = ctx48.frames_scale([f[0] for f in frames], 640, 360)        # identity: the very same frames (encode.rs:342-345)
+    assert [f.h for f in same] == [f[0].h for f in frames]
+
+
+@pytest.mark.parametrize("size", [(1920, 1080), (560, 350), (70, 50), (34, 18)])
+def test_compose_rgba_equals_crossfade_then_convert(mxl, oracle, ctx48, size):
+    """The one-pass compositor output (blend + colour conversion) is bit-identical to VideoMixer's
+    crossfade (pinned, video_mixer.rs:211-235) followed by the self-specified yuv420p -> RGBA."""
+    w, h = size
+    n = 5
+    la = [make_frame(ctx48, oracle, w, h, 300 + k) for k in range(n)]
+    lb = [make_frame(ctx48, oracle, w, h, 400 + k) for k in range(n)]
+    lay = la[0][2]
+    pics = ctx48.rgba(w, h, n + 1)
+    for fader in (0.0, 0.25, 0.5, 0.999, 1.0):
+        before = ctx48.launch_count
+        ctx48.compose_rgba([f[0] for f in la], [f[0] for f in lb], fader, pics, first=1)
+        assert ctx48.launch_count - before == 1
+        got = pics.download(1, n)
+        f8 = oracle.fader_to_u8(fader)
+        for k in range(n):
+            want = oracle.yuv420p_to_rgba(lay, oracle.video_crossfade(lay, la[k][1], lb[k][1], f8))
+            assert np.array_equal(got[k], want), (fader, k)
+    # a missing layer is blank (video_mixer.rs:180-188), on either side
+    ctx48.compose_rgba([la[0][0], None], [None, lb[1][0]], 0.25, pics, first=0)
+    got = pics.download(0, 2)
+    f8 = oracle.fader_to_u8(0.25)
+    assert np.array_equal(got[0], oracle.yuv420p_to_rgba(lay, oracle.video_crossfade(lay, la[0][1], None, f8)))
+    assert np.array_equal(got[1], oracle.yuv420p_to_rgba(lay, oracle.video_crossfade(lay, None, lb[1][1], f8)))
+    # plain conversion of a batch = compose with a single layer
+    ctx48.frames_to_rgba([f[0] for f in la], pics, first=0)
+    got = pics.download(0, n)
+    for k in range(n):
+        assert np.array_equal(got[k], oracle.yuv420p_to_rgba(lay, la[k][1]))
+    pics.free()
+
+
 def test_yuv_to_rgba_self_specified(mxl, oracle, ctx48):
     # UNPINNED: the reference never converts colour (video_mixer.rs:282-283); spec = oracle header
     for (w, h) in [(1920, 1080), (70, 50), (34, 18)]:

@@ -93,6 +93,30 @@ def main():
     nb = T * 2 * W.FRAME_BYTES
     print(json.dumps({"kernel": "VideoMixer crossfade 1080p x64, layer B missing", "algorithmic_bytes": nb, "ms": ms, "gbs": nb / ms / 1e6,
                       "frac_of_measured_peak": nb / ms / 1e6 / peak, "launches": launches}), flush=True)
+    # one-pass compositor: crossfade + yuv420p -> RGBA8 (BASELINE config 3 output ii), 64 frames per launch
+    pics = ctx.rgba(1920, 1080, T)
+    ms, launches = timed(ctx, lambda: ctx.compose_rgba(fa, fb, 0.5, pics), args.reps)
+    nb = T * (2 * W.FRAME_BYTES + 1920 * 1080 * 4)
+    print(json.dumps({"kernel": "compose_rgba 1080p x64 (2 layers -> RGBA8)", "algorithmic_bytes": nb, "ms": ms, "gbs": nb / ms / 1e6,
+                      "frac_of_measured_peak": nb / ms / 1e6 / peak, "launches": launches}), flush=True)
+    ms, launches = timed(ctx, lambda: ctx.frames_to_rgba(fa, pics), args.reps)
+    nb = T * (W.FRAME_BYTES + 1920 * 1080 * 4)
+    print(json.dumps({"kernel": "frames_to_rgba 1080p x64", "algorithmic_bytes": nb, "ms": ms, "gbs": nb / ms / 1e6,
+                      "frac_of_measured_peak": nb / ms / 1e6 / peak, "launches": launches}), flush=True)
+    pics.free()
+    # tiled letterbox scaler: 32 frames per launch, 720p -> 1080p and 2160p -> 1080p (bytes: source read + scaled frame written)
+    for (sw, sh) in ((1280, 720), (3840, 2160)):
+        src = [ctx.frame(sw, sh, blank=True) for _ in range(32)]
+
+        def scale_once():
+            for f in ctx.frames_scale(src, 1920, 1080):
+                f.release()
+        ms, launches = timed(ctx, scale_once, args.reps)
+        nb = 32 * (sw * sh * 3 // 2 + W.FRAME_BYTES)
+        print(json.dumps({"kernel": "scale_tiled %dx%d -> 1080p x32" % (sw, sh), "algorithmic_bytes": nb, "ms": ms, "gbs": nb / ms / 1e6,
+                          "frac_of_measured_peak": nb / ms / 1e6 / peak, "launches": launches}), flush=True)
+        for f in src:
+            f.release()
     ctx.close()
 
 
