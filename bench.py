@@ -303,6 +303,19 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def pcie_ceiling():
+    """H2D GB/s of the 2-up : 1-down pinned-copy mix measured with tools/pcie_peak.cu on this pool
+    (profiles/r1_pcie_peak.jsonl): the ceiling of the e2e leg, which moves two layers up per frame down."""
+    try:
+        for line in open(os.path.join(ROOT, "profiles", "r1_pcie_peak.jsonl")):
+            d = json.loads(line)
+            if d.get("mix"):
+                return float(d["h2d_gbs"])
+    except Exception:
+        pass
+    return None
+
+
 def ncu_traffic(kernel, ticks_per_step):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -385,20 +398,45 @@ def b200_arm(args):
     for name, st in stage_pass(True).items():
         stages[name]["ms_overlapped"] = st["ms"]
     peak, peak_src = measured_peak()
+    for st in stages.values():
+        st["gbs"] = st["algorithmic_bytes"] / (st["ms"] * 1e-3) / 1e9
+        st["frac_of_hbm_peak"] = st["gbs"] / peak
+
+    # ---- per-kernel device time: CUDA event pairs directly around each launch (mxl_ctx_set_kernel_timing),
+    # over K more steps in the configuration of the timed region.  Unlike the stage times above these exclude
+    # the host-side preparation of a stage and its table copies ----
+    ctx.kernel_times()
+    ctx.set_kernel_timing(True)
+    for _ in range(K):
+        sess.run_step(tick)
+        tick += T
+    kt = ctx.kernel_times()
+    ctx.set_kernel_timing(False)
+    kernels = {name: {"launches": n, "avg_launch_ms": ms / n} for name, (n, ms) in kt.items() if n}
+    stage_kernel = {"VideoMixer": "crossfade_flat_kernel", "EqThree": "eq_stream_kernel", "Oscillator": "oscillator_kernel",
+                    "StereoPanner": "panner_kernel", "Mixer": "mixer_kernel", "Meter": "meter_kernel"}
+    for sname, kname in stage_kernel.items():
+        if sname in stages and kname in kernels:
+            kernels[kname]["algorithmic_bytes_per_launch"] = stages[sname]["algorithmic_bytes"]
+            kernels[kname]["gbs"] = stages[sname]["algorithmic_bytes"] / (kernels[kname]["avg_launch_ms"] * 1e-3) / 1e9
+            kernels[kname]["frac_of_hbm_peak"] = kernels[kname]["gbs"] / peak
     if args.workload in ("av", "video"):
         dom, dom_kernel = "VideoMixer", "crossfade_flat_kernel"
     else:
         dom = max(stages, key=lambda n: stages[n]["ms"])
-        dom_kernel = dom
+        dom_kernel = stage_kernel.get(dom, dom)
     d = stages[dom]
-    achieved = d["algorithmic_bytes"] / (d["ms"] * 1e-3) / 1e9
+    dk = kernels.get(dom_kernel, {"avg_launch_ms": d["ms"]})
+    achieved = d["algorithmic_bytes"] / (dk["avg_launch_ms"] * 1e-3) / 1e9
+    total_kernel_ms = sum(v["avg_launch_ms"] * v["launches"] for v in kernels.values()) / K
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(dom_kernel, T), "kernel": dom_kernel, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": d["algorithmic_bytes"], "avg_launch_ms": d["ms"],
-                "avg_launch_ms_overlapped": d["ms_overlapped"],
-                "step_share": d["ms"] / sum(s["ms"] for s in stages.values()),
-                "timing": "CUDA events around the stage on its launching stream, K steps; 'avg_launch_ms' with all stages "
-                          "serialised on one stream, '_overlapped' as in the timed region (audio stages on a second stream)"}
+                "algorithmic_bytes_per_launch": d["algorithmic_bytes"], "avg_launch_ms": dk["avg_launch_ms"],
+                "stage_ms_serialised": d["ms"], "stage_ms_overlapped": d["ms_overlapped"],
+                "step_share": dk["avg_launch_ms"] * dk.get("launches", K) / K / total_kernel_ms if total_kernel_ms else None,
+                "timing": "CUDA event pair recorded directly around each launch of the kernel on its launching stream "
+                          "(mxl_ctx_set_kernel_timing), averaged over K steps in the timed region's configuration; "
+                          "step_share = this kernel's device time / all kernels' device time per step"}
     whole = sess.algorithmic_bytes_per_step / (ms_max / K * 1e-3) / 1e9
 
     # ---- e2e: host buffers through the C ABI ----
@@ -439,6 +477,7 @@ def b200_arm(args):
         e2e = {"value": Ke * T * dist.world / dt_max, "unit": UNIT, "h2d_bytes_per_step": h2d_step,
                "d2h_bytes_per_step": d2h_step, "steps": Ke, "ms_per_step": dt_max / Ke * 1e3, "mode": args.e2e_mode,
                "h2d_gbs": h2d_step * Ke / dt_max / 1e9, "d2h_gbs": d2h_step * Ke / dt_max / 1e9,
+               "bound": "pcie" if sess.video else "launch", "pcie_h2d_ceiling_gbs": pcie_ceiling(),
                "timing": "host wall clock around K steps incl. pinned-host copies, synchronised both sides, max over ranks"}
     clocks = sampler.stop()
 
@@ -462,7 +501,7 @@ def b200_arm(args):
             "stereo_frames_per_s": value * SPT if args.workload != "video" else None,
             "video_fps": value if args.workload != "audio" else None,
             "whole_step_gbs": whole, "whole_step_frac": whole / peak,
-            "host_enqueue_ms_per_step": host_enqueue_s / K * 1e3, "stages": stages,
+            "host_enqueue_ms_per_step": host_enqueue_s / K * 1e3, "stages": stages, "kernels": kernels,
         }
         print(json.dumps(line))
     sess.close()

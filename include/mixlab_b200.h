@@ -145,6 +145,13 @@ MXL_API int mxl_ctx_timer_end(mxl_ctx *ctx);
 MXL_API int mxl_ctx_timer_elapsed_ms(mxl_ctx *ctx, float *ms);
 /* Overwrites a scratch buffer larger than L2 (bench hygiene between timed iterations). */
 MXL_API int mxl_ctx_flush_l2(mxl_ctx *ctx);
+/* Per-kernel device timing: while enabled, every kernel launch of the context is bracketed by a CUDA event
+ * pair on its launching stream (host preparation and table copies stay outside).  mxl_ctx_kernel_times
+ * synchronises, folds the pairs recorded since the last call into one entry per kernel and returns the
+ * number of entries written.  (The reference's EngineStat, src/engine/timing.rs:46-60, at kernel grain.) */
+typedef struct mxl_kernel_time { char name[48]; uint32_t launches; float total_ms; } mxl_kernel_time;
+MXL_API int mxl_ctx_set_kernel_timing(mxl_ctx *ctx, int enabled);
+MXL_API int mxl_ctx_kernel_times(mxl_ctx *ctx, mxl_kernel_time *out, uint32_t cap);
 MXL_API const char *mxl_last_error(void);
 MXL_API const char *mxl_version(void);
 /* Decibel::to_linear, protocol/src/lib.rs:469-471 (host scalar; exposed for tests) */

@@ -85,6 +85,10 @@ class ScaleGeometry(C.Structure):
                 ("letterbox_y", C.c_uint32)]
 
 
+class KernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("launches", C.c_uint32), ("total_ms", C.c_float)]
+
+
 class StageInfo(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n_modules", C.c_int32), ("n_launches", C.c_int32),
                 ("last_ms", C.c_float), ("algorithmic_bytes", C.c_uint64)]
@@ -136,6 +140,8 @@ def lib():
         "mxl_ctx_timer_end": (i32, [vp]),
         "mxl_ctx_timer_elapsed_ms": (i32, [vp, C.POINTER(C.c_float)]),
         "mxl_ctx_flush_l2": (i32, [vp]),
+        "mxl_ctx_set_kernel_timing": (i32, [vp, i32]),
+        "mxl_ctx_kernel_times": (i32, [vp, C.POINTER(KernelTime), u32]),
         "mxl_last_error": (C.c_char_p, []),
         "mxl_version": (C.c_char_p, []),
         "mxl_db_to_linear": (dbl, [dbl]),
@@ -374,6 +380,15 @@ class Context:
         if data is not None:
             fr.upload_raw(data)
         return fr
+
+    def set_kernel_timing(self, enabled):
+        check(lib().mxl_ctx_set_kernel_timing(self.h, 1 if enabled else 0))
+
+    def kernel_times(self):
+        """{kernel name: (launches, total ms)} of the launches since the last call (synchronises)."""
+        buf = (KernelTime * 64)()
+        n = check(lib().mxl_ctx_kernel_times(self.h, buf, 64))
+        return {buf[i].name.decode(): (buf[i].launches, buf[i].total_ms) for i in range(n)}
 
     def rgba(self, width, height, n_pictures):
         return RgbaPictures(self, width, height, n_pictures)

@@ -157,14 +157,13 @@ int mxl_frame_to_rgba(const mxl_frame* frame, uint8_t* rgba_host)
 {
     if (!frame || !rgba_host) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
     mxl_ctx* ctx = frame->ctx;
-    MXL_TRY(ctx->activate());
-    const size_t bytes = (size_t)frame->layout.width * frame->layout.height * 4;
-    Staging st;
-    MXL_CUDA(cudaMalloc(&st.p, bytes));
-    MXL_TRY(k::launch_yuv_to_rgba(ctx, frame->layout, frame->dev, (uint8_t*)st.p));
-    MXL_CUDA(cudaMemcpyAsync(rgba_host, st.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    MXL_CUDA(cudaStreamSynchronize(ctx->stream));
-    return MXL_OK;
+    mxl_rgba* pic = mxl_rgba_alloc(ctx, frame->layout.width, frame->layout.height, 1);
+    if (!pic) return MXL_ERR_OOM;
+    mxl_frame* f = const_cast<mxl_frame*>(frame);
+    int st = mxl_frames_to_rgba(ctx, &f, 1, pic, 0);
+    if (st == MXL_OK) st = mxl_rgba_download(pic, 0, 1, rgba_host);
+    mxl_rgba_free(pic);
+    return st;
 }
 
 mxl_frame* mxl_frame_scale(mxl_frame* src, uint32_t out_w, uint32_t out_h)

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kThreads) fm_sine_kernel(const __grid_constant
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float mix1(float x, double g) { return (float)((double)x * g); }
 
-template <int UNROLL>
+template <int UNROLL, int CU>
 __global__ void __launch_bounds__(kThreads) mixer_kernel(const __grid_constant__ MixerLaunch p)
 {
     const uint64_t n4 = p.len >> 2;
@@ -155,20 +155,28 @@ __global__ void __launch_bounds__(kThreads) mixer_kernel(const __grid_constant__
                 c[u] = m[u];
             }
         }
-#pragma unroll 4
-        for (int ch = 0; ch < p.channels; ch++) {
-            const float* src = p.ch[ch].in;
-            const double g = p.ch[ch].gain;
-            const bool cue = p.ch[ch].cue != 0;
-            float4 x[UNROLL];
+        // CU channels at a time: their loads are all in flight before the first sum, the sums then run in
+        // channel order (the reference's f32 accumulation order)
+        for (int ch0 = 0; ch0 < p.channels; ch0 += CU) {
+            float4 x[CU][UNROLL];
 #pragma unroll
-            for (int u = 0; u < UNROLL; u++)
-                x[u] = (src && i0 + u * kStep < n4) ? ldg_stream(src + 4 * (i0 + u * kStep)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < CU; k++) {
+                const float* src = ch0 + k < p.channels ? p.ch[ch0 + k].in : nullptr;
 #pragma unroll
-            for (int u = 0; u < UNROLL; u++) {
-                m[u].x += mix1(x[u].x, g); m[u].y += mix1(x[u].y, g);
-                m[u].z += mix1(x[u].z, g); m[u].w += mix1(x[u].w, g);
-                if (cue) { c[u].x += x[u].x; c[u].y += x[u].y; c[u].z += x[u].z; c[u].w += x[u].w; }
+                for (int u = 0; u < UNROLL; u++)
+                    x[k][u] = (src && i0 + u * kStep < n4) ? ldg_stream(src + 4 * (i0 + u * kStep)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int k = 0; k < CU; k++) {
+                if (ch0 + k >= p.channels) break;
+                const double g = p.ch[ch0 + k].gain;
+                const bool cue = p.ch[ch0 + k].cue != 0;
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    m[u].x += mix1(x[k][u].x, g); m[u].y += mix1(x[k][u].y, g);
+                    m[u].z += mix1(x[k][u].z, g); m[u].w += mix1(x[k][u].w, g);
+                    if (cue) { c[u].x += x[k][u].x; c[u].y += x[k][u].y; c[u].z += x[k][u].z; c[u].w += x[k][u].w; }
+                }
             }
         }
 #pragma unroll
@@ -472,6 +480,7 @@ int launch_oscillator(mxl_ctx* ctx, const OscBatch& b)
     MXL_REQUIRE_DEVICE(ctx);
     if (b.n <= 0 || b.frames == 0) return MXL_OK;
     dim3 grid(blocks_for((b.frames + 3) / 4), b.n);
+    MXL_TIMED(ctx, "oscillator_kernel");
     oscillator_kernel<<<grid, kThreads, 0, ctx->stream>>>(b);
     return check_launch(ctx, "oscillator_kernel");
 }
@@ -481,6 +490,7 @@ int launch_fm_sine(mxl_ctx* ctx, const FmBatch& b)
     MXL_REQUIRE_DEVICE(ctx);
     if (b.n <= 0 || b.frames == 0) return MXL_OK;
     dim3 grid(blocks_for((b.frames + 3) / 4), b.n);
+    MXL_TIMED(ctx, "fm_sine_kernel");
     fm_sine_kernel<<<grid, kThreads, 0, ctx->stream>>>(b);
     return check_launch(ctx, "fm_sine_kernel");
 }
@@ -490,19 +500,24 @@ int launch_mixer(mxl_ctx* ctx, const MixerLaunch& p)
     MXL_REQUIRE_DEVICE(ctx);
     if (p.len == 0) return MXL_OK;
     const uint64_t n4 = p.len >> 2;
-    // Two float4 per thread, kThreads apart (measured on B200, C = 2..10, 805 MB..2.4 GB per launch:
-    // 0.93-0.95 of the copy peak; one per thread 0.92, four per thread 0.69 at 64 registers).
+    // Long lines: two float4 per thread, kThreads apart, four channels in flight (measured on B200, C = 2..10,
+    // 805 MB..2.4 GB per launch: 0.93-0.98 of the copy peak).  Short lines (one tick of a wide bus) do not
+    // fill the machine with threads, so each thread keeps 16 channels in flight instead.
     int unroll = 2;
     if (const char* e = getenv("MXL_MIXER_UNROLL")) unroll = atoi(e);
-    if (unroll >= 4) {
-        unsigned g = blocks_for((n4 + 3) / 4);
-        mixer_kernel<4><<<g ? g : 1, kThreads, 0, ctx->stream>>>(p);
+    const uint64_t machine = (uint64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148) * 2048;
+    if (n4 < machine && p.channels > 4) {
+        unsigned g = blocks_for(n4);
+        MXL_TIMED(ctx, "mixer_kernel");
+        mixer_kernel<1, 16><<<g ? g : 1, kThreads, 0, ctx->stream>>>(p);
     } else if (unroll >= 2) {
         unsigned g = blocks_for((n4 + 1) / 2);
-        mixer_kernel<2><<<g ? g : 1, kThreads, 0, ctx->stream>>>(p);
+        MXL_TIMED(ctx, "mixer_kernel");
+        mixer_kernel<2, 4><<<g ? g : 1, kThreads, 0, ctx->stream>>>(p);
     } else {
         unsigned g = blocks_for(n4);
-        mixer_kernel<1><<<g ? g : 1, kThreads, 0, ctx->stream>>>(p);
+        MXL_TIMED(ctx, "mixer_kernel");
+        mixer_kernel<1, 4><<<g ? g : 1, kThreads, 0, ctx->stream>>>(p);
     }
     return check_launch(ctx, "mixer_kernel");
 }
@@ -514,6 +529,7 @@ int launch_amplifier(mxl_ctx* ctx, const AmpBatch& b)
     const uint64_t n4 = b.frames >> 1;
     unsigned gx = blocks_for((n4 + kAmpUnroll - 1) / kAmpUnroll);
     dim3 grid(gx ? gx : 1, b.n);
+    MXL_TIMED(ctx, "amplifier_kernel");
     amplifier_kernel<<<grid, kThreads, 0, ctx->stream>>>(b);
     return check_launch(ctx, "amplifier_kernel");
 }
@@ -523,6 +539,7 @@ int launch_panner(mxl_ctx* ctx, const PanBatch& b)
     MXL_REQUIRE_DEVICE(ctx);
     if (b.n <= 0 || b.frames == 0) return MXL_OK;
     dim3 grid(blocks_for((b.frames + 3) / 4), b.n);
+    MXL_TIMED(ctx, "panner_kernel");
     panner_kernel<<<grid, kThreads, 0, ctx->stream>>>(b);
     return check_launch(ctx, "panner_kernel");
 }
@@ -532,6 +549,7 @@ int launch_splitter(mxl_ctx* ctx, const SplitBatch& b)
     MXL_REQUIRE_DEVICE(ctx);
     if (b.n <= 0 || b.frames == 0) return MXL_OK;
     dim3 grid(blocks_for((b.frames + 3) / 4), b.n);
+    MXL_TIMED(ctx, "splitter_kernel");
     splitter_kernel<<<grid, kThreads, 0, ctx->stream>>>(b);
     return check_launch(ctx, "splitter_kernel");
 }
@@ -541,6 +559,7 @@ int launch_fill(mxl_ctx* ctx, const FillBatch& b)
     MXL_REQUIRE_DEVICE(ctx);
     if (b.n <= 0 || b.len == 0) return MXL_OK;
     dim3 grid(blocks_for((b.len + 3) / 4), b.n);
+    MXL_TIMED(ctx, "fill_kernel");
     fill_kernel<<<grid, kThreads, 0, ctx->stream>>>(b);
     return check_launch(ctx, "fill_kernel");
 }
@@ -550,6 +569,7 @@ int launch_meter(mxl_ctx* ctx, const MeterBatch& b, uint32_t n_slots)
     MXL_REQUIRE_DEVICE(ctx);
     if (b.n <= 0 || n_slots == 0) return MXL_OK;
     dim3 grid(n_slots, b.n);
+    MXL_TIMED(ctx, "meter_kernel");
     meter_kernel<<<grid, kMeterThreads, 0, ctx->stream>>>(b);
     return check_launch(ctx, "meter_kernel");
 }
@@ -559,6 +579,7 @@ int launch_pcm_pack(mxl_ctx* ctx, const float* in, int16_t* out, uint64_t len)
     MXL_REQUIRE_DEVICE(ctx);
     if (len == 0) return MXL_OK;
     const unsigned g = blocks_for(((len >> 2) + kPcmUnroll - 1) / kPcmUnroll);
+    MXL_TIMED(ctx, "pcm_pack_kernel");
     pcm_pack_kernel<<<g ? g : 1, kThreads, 0, ctx->stream>>>(in, reinterpret_cast<short*>(out), len);
     return check_launch(ctx, "pcm_pack_kernel");
 }
@@ -568,6 +589,7 @@ int launch_pcm_unpack(mxl_ctx* ctx, const int16_t* in, float* out, uint64_t len)
     MXL_REQUIRE_DEVICE(ctx);
     if (len == 0) return MXL_OK;
     const unsigned g = blocks_for(((len >> 2) + kPcmUnroll - 1) / kPcmUnroll);
+    MXL_TIMED(ctx, "pcm_unpack_kernel");
     pcm_unpack_kernel<<<g ? g : 1, kThreads, 0, ctx->stream>>>(reinterpret_cast<const short*>(in), out, len);
     return check_launch(ctx, "pcm_unpack_kernel");
 }
@@ -579,6 +601,7 @@ int launch_fill_bytes(mxl_ctx* ctx, void* dst, size_t bytes, uint8_t value)
     uint32_t word = 0x01010101u * value;
     size_t n16 = bytes / 16;
     unsigned blocks = ctx->sm_count > 0 ? ctx->sm_count * 8 : 1184;
+    MXL_TIMED(ctx, "fill_bytes_kernel");
     fill_bytes_kernel<<<blocks, kThreads, 0, ctx->stream>>>(reinterpret_cast<uint4*>(dst), n16, word);
     MXL_TRY(check_launch(ctx, "fill_bytes_kernel"));
     if (bytes % 16) MXL_CUDA(cudaMemsetAsync((uint8_t*)dst + n16 * 16, value, bytes % 16, ctx->stream));

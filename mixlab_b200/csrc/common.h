@@ -72,18 +72,19 @@ struct mxl_ctx {
     std::unordered_map<uint64_t, std::vector<uint8_t*>> frame_pool;
     // EqThree chunk plans by chunk length (see modules.cu: eq_plan_for)
     std::map<uint32_t, std::vector<double>> eq_plans;
-    // single-launch EqThree plans by chunk length: [Hc, pow_lo[8][10], pow_hi[8][10]]; empty = unusable
-    std::map<uint32_t, std::vector<double>> eq_block_plans;
-    size_t eq_block_smem = 0;         // dynamic shared memory eq_block_kernel has been configured for
     // eq_stream_kernel plans by chunk length (eq_plan.h); ok == false = unusable at this sample rate
     std::map<uint32_t, mxl::EqStreamPlan> eq_stream_plans;
     uint32_t eq_stream_smem_set = 0;  // bit LC/16: opt-in shared memory size configured
-    size_t scale_smem = 0;            // dynamic shared memory scale_tiled_kernel has been configured for
+    uint32_t scale_smem[3] = {0, 0, 0};   // dynamic shared memory the scale_tiled_kernel variants have been configured for
     // scaler tap tables by (source length, destination length): device [pos int32 x n][coef int16 x 4n]
     std::map<uint64_t, void*> scale_tables;
     std::map<uint64_t, std::vector<int32_t>> scale_positions;   // host copies of the first-tap columns (tile bounds)
     void* scale_jobs = nullptr;       // device staging for ScaleJob arrays
-    size_t scale_jobs_cap = 0;
+    size_t scale_jobs_cap = 0, scale_jobs_used = 0;   // bytes; tables rotate through the buffer
+    bool kernel_timing = false;
+    struct KernelEvents { const char* name; cudaEvent_t a, b; };
+    std::vector<KernelEvents> kernel_events;      // pairs recorded since the last read
+    std::vector<cudaEvent_t> kernel_event_pool;
     uint32_t env_epoch = 0;           // Envelope launches so far (tags the look-back flags of a launch)
     std::map<uint32_t, void*> eq_stream_tables;   // device copies of EqStreamPlan::lane_pow by chunk length
 
@@ -119,6 +120,19 @@ struct mxl_frame {
     uint8_t* dev = nullptr;
     std::atomic<int> refs{1};
 };
+
+namespace mxl {
+// Optional per-kernel timing (mxl_ctx_set_kernel_timing): every launcher records a CUDA event pair
+// directly around its kernel launch on the launching stream -- host preparation, table copies and the
+// work of other stages stay outside the pair.  bench.py's roofline numbers come from here.
+struct KernelTimer {
+    mxl_ctx* ctx;
+    int slot = -1;
+    KernelTimer(mxl_ctx* c, const char* name);
+    ~KernelTimer();
+};
+}  // namespace mxl
+#define MXL_TIMED(ctx, name) ::mxl::KernelTimer mxl_kernel_timer_((ctx), (name))
 
 struct VideoSlot {
     mxl_frame* frame = nullptr;       // retained

@@ -195,6 +195,24 @@ void video_slot_set(VideoSlot& s, mxl_frame* f, Rational dur, Rational off)
     s.tick_offset = off;
 }
 
+KernelTimer::KernelTimer(mxl_ctx* c, const char* name) : ctx(c)
+{
+    if (!c || !c->kernel_timing) return;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    for (auto& e : ev) {
+        if (!c->kernel_event_pool.empty()) { e = c->kernel_event_pool.back(); c->kernel_event_pool.pop_back(); }
+        else if (cudaEventCreate(&e) != cudaSuccess) return;
+    }
+    if (cudaEventRecord(ev[0], c->stream) != cudaSuccess) return;
+    c->kernel_events.push_back(mxl_ctx::KernelEvents{name, ev[0], ev[1]});
+    slot = (int)c->kernel_events.size() - 1;
+}
+
+KernelTimer::~KernelTimer()
+{
+    if (slot >= 0) cudaEventRecord(ctx->kernel_events[slot].b, ctx->stream);
+}
+
 }  // namespace mxl
 
 int mxl_ctx::activate() const
@@ -301,6 +319,39 @@ mxl_ctx* mxl_ctx_create_on_stream(int device, uint32_t sample_rate, uint32_t sam
     return ctx_create(device, sample_rate, samples_per_tick, (cudaStream_t)cuda_stream, true);
 }
 
+int mxl_ctx_set_kernel_timing(mxl_ctx* ctx, int enabled)
+{
+    if (!ctx) MXL_FAIL(MXL_ERR_INVALID, "NULL context");
+    ctx->kernel_timing = enabled != 0;
+    return MXL_OK;
+}
+
+// Synchronises, then folds the event pairs recorded since the last read into one entry per kernel name.
+int mxl_ctx_kernel_times(mxl_ctx* ctx, mxl_kernel_time* out, uint32_t cap)
+{
+    if (!ctx || (cap && !out)) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
+    if (!ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "no CUDA device bound to this context");
+    MXL_TRY(mxl_ctx_synchronize(ctx));
+    uint32_t n = 0;
+    for (auto& e : ctx->kernel_events) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+            uint32_t i = 0;
+            for (; i < n; i++) if (!strncmp(out[i].name, e.name, sizeof out[i].name - 1)) break;
+            if (i == n && n < cap) {
+                memset(&out[n], 0, sizeof out[n]);
+                strncpy(out[n].name, e.name, sizeof out[n].name - 1);
+                n++;
+            }
+            if (i < n) { out[i].launches++; out[i].total_ms += ms; }
+        }
+        ctx->kernel_event_pool.push_back(e.a);
+        ctx->kernel_event_pool.push_back(e.b);
+    }
+    ctx->kernel_events.clear();
+    return (int)n;
+}
+
 int mxl_ctx_destroy(mxl_ctx* ctx)
 {
     if (!ctx) return MXL_OK;
@@ -308,6 +359,8 @@ int mxl_ctx_destroy(mxl_ctx* ctx)
         ctx->activate();
         cudaStreamSynchronize(ctx->stream);
         if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+        for (auto& e : ctx->kernel_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+        for (cudaEvent_t e : ctx->kernel_event_pool) cudaEventDestroy(e);
         for (auto& kv : ctx->eq_stream_tables) if (kv.second) cudaFree(kv.second);
         for (auto& kv : ctx->scale_tables) if (kv.second) cudaFree(kv.second);
         if (ctx->scale_jobs) cudaFree(ctx->scale_jobs);

@@ -340,6 +340,7 @@ int launch_envelope(mxl_ctx* ctx, const EnvBatch& b)
     if (b.n <= 0 || b.frames == 0) return MXL_OK;
     if (b.frames >= 0x7ffffff0ull) MXL_FAIL(MXL_ERR_LENGTH, "Envelope: call longer than 2^31 samples");
     dim3 grid(envelope_tiles(b.frames), b.n);
+    MXL_TIMED(ctx, "envelope_kernel");
     envelope_kernel<<<grid, kEnvThreads, 0, ctx->stream>>>(b);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) MXL_FAIL(MXL_ERR_CUDA, "envelope launch failed: %s", cudaGetErrorString(e));

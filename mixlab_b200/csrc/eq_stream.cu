@@ -313,6 +313,7 @@ int launch_lc(mxl_ctx* ctx, const EqStreamBatch& b)
     }
     const uint32_t U = kT - b.halo;
     dim3 grid((b.n_chunks + U - 1) / U, b.n);
+    MXL_TIMED(ctx, "eq_stream_kernel");
     eq_stream_kernel<LC><<<grid, kT, smem, ctx->stream>>>(b);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) MXL_FAIL(MXL_ERR_CUDA, "launch of eq_stream_kernel<%d> failed: %s", LC, cudaGetErrorString(e));

@@ -86,33 +86,6 @@ struct EqBatch {
 };
 int launch_eq_three(mxl_ctx* ctx, const EqBatch& b);
 
-// Single-launch variant (eq_three.cu: eq_block_kernel): one CTA = 256 consecutive chunks of one
-// instance, the first `halo_chunks` of which only warm the pole state up.
-constexpr int kEqBlockThreads = 256;
-constexpr int kEqBlockLevels = 8;    // log2(kEqBlockThreads): A^(2^d) for the in-block scan
-constexpr uint32_t kEqBlockMaxChunk = 128;
-struct EqBlockInst {
-    const float* in; float* out;
-    const double* state; double* state_out;
-    double g_lo, g_mid, g_hi;
-};
-struct EqBlockBatch {
-    uint64_t frames;
-    uint32_t chunk;                  // Lc, multiple of 4, <= kEqBlockMaxChunk
-    uint32_t halo_chunks;            // Hc: |A^Hc| < 2^-75
-    uint32_t n_chunks;
-    int32_t n;
-    uint32_t subs;                   // sub-chunks a thread advances in lock step: 1, 2 or 4
-    uint32_t _pad;
-    double c_lo, c_hi;
-    double pow_lo[kEqBlockLevels][10];   // A^(2^d), A = M^Lc, packed lower-triangular
-    double pow_hi[kEqBlockLevels][10];
-    double sub_lo[3][10];                // B^1..B^3, B = M^(Lc/subs): the sub-chunks a thread interleaves
-    double sub_hi[3][10];
-    EqBlockInst inst[kMaxBatch];
-};
-int launch_eq_three_block(mxl_ctx* ctx, const EqBlockBatch& b);
-
 // Time-parallel single launch with dot-product zero pass and skewed exact pass (eq_stream.cu).
 constexpr int kEqStreamThreads = 256;
 struct EqStreamInst {
@@ -180,12 +153,6 @@ struct FadeJob {                     // one output frame
 // All jobs share one layout.  jobs_dev is a device array of n_jobs FadeJob.
 int launch_crossfade(mxl_ctx* ctx, const mxl_frame_layout& lay, const FadeJob* jobs_dev, uint32_t n_jobs);
 int launch_blank(mxl_ctx* ctx, const mxl_frame_layout& lay, uint8_t* frame);
-int launch_yuv_to_rgba(mxl_ctx* ctx, const mxl_frame_layout& lay, const uint8_t* yuv, uint8_t* rgba);
-// 4-tap separable resample of one plane with host-built 14-bit tables (device pointers)
-int launch_resample_h(mxl_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, uint32_t sstride,
-                      uint8_t* dst, uint32_t dw, uint32_t dstride, const int32_t* pos, const int16_t* coef);
-int launch_resample_v(mxl_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, uint32_t sstride,
-                      uint8_t* dst, uint32_t dh, uint32_t dstride, const int32_t* pos, const int16_t* coef);
 
 // Tiled letterbox scaler: all planes of a batch of frames in one launch (video_kernels.cu)
 struct ScaleJob { const uint8_t* src; uint8_t* dst; };            // frame base pointers
@@ -200,11 +167,13 @@ struct ScaleLaunch {
     ScalePlane pl[3];
     uint32_t total_tiles;
     uint32_t region_pitch, region_rows;                           // staging bounds over all tiles (pitch % 16 == 0)
-    uint32_t _pad;
+    uint32_t tile_h;                                              // output rows per tile: 32, 8 or 2
     const ScaleJob* jobs;                                         // device
 };
 int launch_scale_tiled(mxl_ctx* ctx, const ScaleLaunch& L, uint32_t n_jobs);
-void scale_tile_dims(uint32_t* tw, uint32_t* th);
+constexpr size_t kScaleMaxSmem = 160 * 1024;                      // per CTA; beyond it a shorter tile is used
+size_t scale_smem_bytes(uint32_t region_rows, uint32_t region_pitch);
+uint32_t scale_tile_width();
 
 // Crossfade + yuv420p -> RGBA8 in one pass
 struct ComposeRgbaJob { const uint8_t* a; const uint8_t* b; uint8_t* rgba; uint32_t fade; uint32_t _pad; };

@@ -649,53 +649,6 @@ static uint32_t eq_pick_chunk(const mxl_ctx* ctx, uint64_t frames, int n_inst)
     return chunk;
 }
 
-// Plan of the single-launch kernel for chunk length Lc: halo length Hc (chunks until the cascades have
-// forgotten their start state, |A^Hc| < 2^-75) and A^(2^d), d = 0..7.  Empty plan = Hc too long for Lc.
-static const std::vector<double>& eq_block_plan_for(mxl_ctx* ctx, uint32_t Lc, uint32_t subs)
-{
-    const uint32_t key = Lc * 8 + subs;
-    auto it = ctx->eq_block_plans.find(key);
-    if (it != ctx->eq_block_plans.end()) return it->second;
-    const EqCoefs co = eq_coefs(ctx);
-    double Al[4][4], Ah[4][4], Pl[4][4], Ph[4][4], T[4][4];
-    cascade_power(co.c_lo, Lc, Al);
-    cascade_power(co.c_hi, Lc, Ah);
-    memcpy(Pl, Al, sizeof Pl); memcpy(Ph, Ah, sizeof Ph);
-    const double tiny = ldexp(1.0, -75);
-    uint32_t Hc = 1;
-    while ((absmax4(Pl) >= tiny || absmax4(Ph) >= tiny) && Hc <= 64) {
-        matmul4(Pl, Al, T); memcpy(Pl, T, sizeof T);
-        matmul4(Ph, Ah, T); memcpy(Ph, T, sizeof T);
-        Hc++;
-    }
-    std::vector<double> plan;
-    if (Hc <= 64) {
-        plan.assign(1 + 2 * k::kEqBlockLevels * 10 + 60, 0.0);
-        plan[0] = (double)Hc;
-        {   // B, B^2, B^3 with B = M^(Lc/subs)
-            double Bl[4][4], Bh[4][4], Ql[4][4], Qh[4][4];
-            cascade_power(co.c_lo, Lc / subs, Bl);
-            cascade_power(co.c_hi, Lc / subs, Bh);
-            memcpy(Ql, Bl, sizeof Ql); memcpy(Qh, Bh, sizeof Qh);
-            const size_t base = 1 + 2 * k::kEqBlockLevels * 10;
-            for (int q = 0; q < 3; q++) {
-                pack_tri(Ql, &plan[base + q * 10]);
-                pack_tri(Qh, &plan[base + 30 + q * 10]);
-                matmul4(Ql, Bl, T); memcpy(Ql, T, sizeof T);
-                matmul4(Qh, Bh, T); memcpy(Qh, T, sizeof T);
-            }
-        }
-        memcpy(Pl, Al, sizeof Pl); memcpy(Ph, Ah, sizeof Ph);
-        for (int d = 0; d < k::kEqBlockLevels; d++) {
-            pack_tri(Pl, &plan[1 + d * 10]);
-            pack_tri(Ph, &plan[1 + k::kEqBlockLevels * 10 + d * 10]);
-            matmul4(Pl, Pl, T); memcpy(Pl, T, sizeof T);
-            matmul4(Ph, Ph, T); memcpy(Ph, T, sizeof T);
-        }
-    }
-    return ctx->eq_block_plans[key] = plan;
-}
-
 // Single-launch path (eq_stream_kernel).  Returns 1 if it ran, 0 if no usable plan exists at this
 // sample rate (the cascades would need more than 128 chunks to forget), < 0 on error.
 static int run_eq_stream(mxl_ctx* ctx, mxl_module* const* mods, const IoSet* io, int first, int cnt, uint64_t frames, uint64_t* bytes)
@@ -766,56 +719,6 @@ static int run_eq_stream(mxl_ctx* ctx, mxl_module* const* mods, const IoSet* io,
     return 1;
 }
 
-// Previous single-launch path (eq_block_kernel), kept selectable with MXL_EQ_PATH=block for A/B runs.
-static int run_eq_block(mxl_ctx* ctx, mxl_module* const* mods, const IoSet* io, int first, int cnt, uint64_t frames, uint64_t* bytes)
-{
-    uint32_t forced = 0;
-    if (const char* e = getenv("MXL_EQ_BLOCK_CHUNK")) forced = (uint32_t)atol(e) / 16 * 16;
-    uint32_t subs = 1;   // measured on B200 (tools/eq_tune.sh): 1 chain per thread and Lc = 32 is fastest at both ends
-    if (const char* e = getenv("MXL_EQ_SUBS")) { const long v = atol(e); subs = v == 1 ? 1 : (v == 2 ? 2 : 4); }
-    const std::vector<double>* plan = nullptr;
-    uint32_t Lc = 0;
-    for (uint32_t cand : {32u, 64u, 128u}) {
-        if (forced && cand != forced) continue;
-        const std::vector<double>& p = eq_block_plan_for(ctx, cand, subs);
-        if (!p.empty()) { plan = &p; Lc = cand; break; }
-    }
-    if (forced && !plan && forced >= 16 && forced <= k::kEqBlockMaxChunk) {
-        const std::vector<double>& p = eq_block_plan_for(ctx, forced, subs);
-        if (!p.empty()) { plan = &p; Lc = forced; }
-    }
-    if (!plan) return 0;
-    k::EqBlockBatch b{};
-    b.frames = frames;
-    b.chunk = Lc;
-    b.halo_chunks = (uint32_t)(*plan)[0];
-    b.n_chunks = (uint32_t)((frames + Lc - 1) / Lc);
-    b.n = cnt;
-    b.subs = subs;
-    const EqCoefs co = eq_coefs(ctx);
-    b.c_lo = co.c_lo; b.c_hi = co.c_hi;
-    memcpy(b.pow_lo, &(*plan)[1], sizeof b.pow_lo);
-    memcpy(b.pow_hi, &(*plan)[1 + k::kEqBlockLevels * 10], sizeof b.pow_hi);
-    memcpy(b.sub_lo, &(*plan)[1 + 2 * k::kEqBlockLevels * 10], sizeof b.sub_lo);
-    memcpy(b.sub_hi, &(*plan)[1 + 2 * k::kEqBlockLevels * 10 + 30], sizeof b.sub_hi);
-    for (int j = 0; j < cnt; j++) {
-        EqThree* m = (EqThree*)mods[first + j];
-        MXL_TRY(m->ensure_state());
-        k::EqBlockInst& e = b.inst[j];
-        e.in = io[first + j].in[0] ? io[first + j].in[0]->dev : nullptr;
-        e.out = io[first + j].out[0]->dev;
-        e.state = m->state_ptr(m->cur);
-        e.state_out = m->state_ptr(m->cur ^ 1);
-        e.g_lo = db_to_linear(m->p.gain_lo_db);            // eq_three.rs:62-64
-        e.g_mid = db_to_linear(m->p.gain_mid_db);
-        e.g_hi = db_to_linear(m->p.gain_hi_db);
-        if (bytes) *bytes += (io[first + j].in[0] ? 4 * frames : 0) + 4 * frames;
-    }
-    MXL_TRY(k::launch_eq_three_block(ctx, b));
-    for (int j = 0; j < cnt; j++) ((EqThree*)mods[first + j])->cur ^= 1;
-    return 1;
-}
-
 static int run_eq_threes(mxl_ctx* ctx, mxl_module* const* mods, int n, const IoSet* io, uint64_t* bytes)
 {
     int i = 0;
@@ -836,9 +739,7 @@ static int run_eq_threes(mxl_ctx* ctx, mxl_module* const* mods, int n, const IoS
         if (frames == 0) continue;
         if (frames >= (1ull << 36)) MXL_FAIL(MXL_ERR_LENGTH, "EqThree: call too long");
         if (!getenv("MXL_EQ_CHUNK")) {                     // MXL_EQ_CHUNK selects the two-launch path
-            const char* path = getenv("MXL_EQ_PATH");
-            const int ran = (path && !strcmp(path, "block")) ? run_eq_block(ctx, mods, io, first, cnt, frames, bytes)
-                                                             : run_eq_stream(ctx, mods, io, first, cnt, frames, bytes);
+            const int ran = run_eq_stream(ctx, mods, io, first, cnt, frames, bytes);
             if (ran < 0) return ran;
             if (ran == 1) continue;
         }
@@ -1081,9 +982,95 @@ static int axis_table(mxl_ctx* ctx, uint32_t src_n, uint32_t dst_n, const int32_
     return MXL_OK;
 }
 
-// DynamicScaler::scale (src/video/encode.rs:338-397) for a batch of frames that share source and target
-// sizes: one blank fill per frame that gets letterbox bars, then ONE launch of the tiled scaler for all
-// planes of all frames.  dst[i] receives a new frame (or a retained src[i] when the sizes already agree).
+// DynamicScaler::scale (src/video/encode.rs:338-397), split so that the frames of a multi-tick call can be
+// scaled by one launch: scale_target() makes the destination frame of one source (encode.rs:382), scale_run()
+// scales a batch of (source, destination) pairs that share source and target sizes -- all planes of all
+// frames in ONE launch of the tiled kernel.
+mxl_frame* scale_target(mxl_ctx* ctx, const mxl_frame_layout& sl, uint32_t out_w, uint32_t out_h)
+{
+    mxl_scale_geometry g;
+    if (mxl_scale_geometry_yuv420p(sl.width, sl.height, out_w, out_h, &g) != MXL_OK) return nullptr;
+    // The reference scales into AvFrame::blank.  The blank fill can be skipped only when the scaled picture
+    // covers every byte of the target, stride padding included.
+    mxl_frame_layout tl;
+    frame_layout_yuv420p(out_w, out_h, &tl);
+    const bool bars = g.scaled_w != out_w || g.scaled_h != out_h || tl.stride[0] != out_w || tl.stride[1] != (out_w + 1) / 2;
+    return bars ? mxl_frame_blank(ctx, out_w, out_h) : frame_alloc(ctx, out_w, out_h);
+}
+
+int scale_run(mxl_ctx* ctx, const mxl_frame_layout& sl, uint32_t out_w, uint32_t out_h, const k::ScaleJob* jobs, uint32_t n)
+{
+    if (n == 0) return MXL_OK;
+    mxl_scale_geometry g;
+    MXL_TRY(mxl_scale_geometry_yuv420p(sl.width, sl.height, out_w, out_h, &g));
+    if (g.scaled_w == 0 || g.scaled_h == 0) return MXL_OK;
+    mxl_frame_layout dl;
+    frame_layout_yuv420p(out_w, out_h, &dl);
+    k::ScaleLaunch L{};
+    const uint32_t tw = k::scale_tile_width();
+    auto clampi = [](int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); };
+    // tallest tile whose staged source rectangle fits: 32 output rows, or 8 / 2 for strong down-scales
+    for (uint32_t th : {32u, 8u, 2u}) {
+        uint32_t tile_base = 0, max_span = 16, max_rows = 1;
+        for (int p = 0; p < 3; p++) {
+            // subframe addressing (codec/src/ffmpeg/frame.rs:219-281): offsets are chroma-aligned already
+            const uint32_t sh = p ? 1 : 0;
+            k::ScalePlane& P = L.pl[p];
+            P.src_off = (uint32_t)sl.offset[p];
+            P.src_w = p ? (sl.width + 1) / 2 : sl.width;
+            P.src_h = sl.plane_h[p];
+            P.src_stride = sl.stride[p];
+            P.dst_w = g.scaled_w >> sh;
+            P.dst_h = g.scaled_h >> sh;
+            P.dst_stride = dl.stride[p];
+            P.dst_off = (uint32_t)(dl.offset[p] + (uint64_t)(g.letterbox_y >> sh) * dl.stride[p] + (g.letterbox_x >> sh));
+            P.tile_base = tile_base;
+            if (P.dst_w == 0 || P.dst_h == 0) { P.tiles_x = P.tiles_y = 0; continue; }
+            const std::vector<int32_t>*hx, *hy;
+            MXL_TRY(axis_table(ctx, P.src_w, P.dst_w, &P.xpos, &P.xcoef, &hx));
+            MXL_TRY(axis_table(ctx, P.src_h, P.dst_h, &P.ypos, &P.ycoef, &hy));
+            P.tiles_x = (P.dst_w + tw - 1) / tw;
+            P.tiles_y = (P.dst_h + th - 1) / th;
+            tile_base += P.tiles_x * P.tiles_y;
+            for (uint32_t t = 0; t < P.tiles_x; t++) {      // staged bytes per row: from the 16-aligned first tap to the last tap
+                const uint32_t x0 = t * tw, x1 = std::min(x0 + tw, P.dst_w) - 1;
+                const int lo = clampi((*hx)[x0], (int)P.src_w - 1) & ~15, hi = clampi((*hx)[x1] + 3, (int)P.src_w - 1);
+                max_span = std::max<uint32_t>(max_span, (uint32_t)((hi - lo) / 16 + 1) * 16);
+            }
+            for (uint32_t t = 0; t < P.tiles_y; t++) {
+                const uint32_t y0 = t * th, y1 = std::min(y0 + th, P.dst_h) - 1;
+                const int lo = clampi((*hy)[y0], (int)P.src_h - 1), hi = clampi((*hy)[y1] + 3, (int)P.src_h - 1);
+                max_rows = std::max<uint32_t>(max_rows, (uint32_t)(hi - lo + 1));
+            }
+        }
+        L.total_tiles = tile_base;
+        L.region_pitch = max_span;
+        L.region_rows = max_rows;
+        L.tile_h = th;
+        if (k::scale_smem_bytes(max_rows, max_span) <= k::kScaleMaxSmem) break;
+    }
+    // job tables rotate through a ring: a table must stay intact until the launch that reads it has run,
+    // and several batches may be queued before the stream gets to the first
+    const size_t need = (size_t)n * sizeof(k::ScaleJob);
+    if (ctx->scale_jobs_cap < need * 2 || ctx->scale_jobs_used + need > ctx->scale_jobs_cap) {
+        MXL_CUDA(cudaStreamSynchronize(ctx->stream));                                  // every queued reader is done
+        if (ctx->scale_jobs_cap < need * 2) {
+            if (ctx->scale_jobs) cudaFree(ctx->scale_jobs);
+            ctx->scale_jobs = nullptr;
+            const size_t cap = std::max<size_t>(64 * 1024, need * 4);
+            MXL_CUDA(cudaMalloc(&ctx->scale_jobs, cap));
+            ctx->scale_jobs_cap = cap;
+        }
+        ctx->scale_jobs_used = 0;
+    }
+    k::ScaleJob* dev_jobs = (k::ScaleJob*)((uint8_t*)ctx->scale_jobs + ctx->scale_jobs_used);
+    ctx->scale_jobs_used += (need + 15) & ~(size_t)15;
+    MXL_CUDA(cudaMemcpyAsync(dev_jobs, jobs, need, cudaMemcpyHostToDevice, ctx->stream));
+    L.jobs = dev_jobs;
+    return k::launch_scale_tiled(ctx, L, n);
+}
+
+// dst[i] receives a new frame (or a retained src[i] when the sizes already agree, encode.rs:342-345).
 int frames_scale(mxl_ctx* ctx, mxl_frame* const* src, mxl_frame** dst, uint32_t n, uint32_t out_w, uint32_t out_h)
 {
     if (n == 0) return MXL_OK;
@@ -1093,81 +1080,21 @@ int frames_scale(mxl_ctx* ctx, mxl_frame* const* src, mxl_frame** dst, uint32_t 
         if (!src[i] || src[i]->layout.width != sl.width || src[i]->layout.height != sl.height)
             MXL_FAIL(MXL_ERR_INVALID, "frames_scale: frames of one batch must share a size");
     }
-    if (sl.width == out_w && sl.height == out_h) {                                              // encode.rs:342-345
+    if (sl.width == out_w && sl.height == out_h) {
         for (uint32_t i = 0; i < n; i++) dst[i] = frame_retain(src[i]);
         return MXL_OK;
     }
-    mxl_scale_geometry g;
-    MXL_TRY(mxl_scale_geometry_yuv420p(sl.width, sl.height, out_w, out_h, &g));
-    // The reference scales into AvFrame::blank (encode.rs:382).  The blank fill can be skipped only when the
-    // scaled picture covers every byte of the target, stride padding included.
-    mxl_frame_layout tl;
-    frame_layout_yuv420p(out_w, out_h, &tl);
-    const bool bars = g.scaled_w != out_w || g.scaled_h != out_h || tl.stride[0] != out_w || tl.stride[1] != (out_w + 1) / 2;
     std::vector<k::ScaleJob> jobs(n);
-    for (uint32_t i = 0; i < n; i++) {
-        dst[i] = bars ? mxl_frame_blank(ctx, out_w, out_h) : frame_alloc(ctx, out_w, out_h);   // encode.rs:382
-        if (!dst[i]) {
-            for (uint32_t j = 0; j < i; j++) { frame_release(dst[j]); dst[j] = nullptr; }
-            return MXL_ERR_OOM;
-        }
-        jobs[i] = k::ScaleJob{src[i]->dev, dst[i]->dev};
+    int st = MXL_OK;
+    for (uint32_t i = 0; i < n && st == MXL_OK; i++) {
+        dst[i] = scale_target(ctx, sl, out_w, out_h);
+        if (!dst[i]) st = MXL_ERR_OOM;
+        else jobs[i] = k::ScaleJob{src[i]->dev, dst[i]->dev};
     }
-    if (g.scaled_w == 0 || g.scaled_h == 0) return MXL_OK;
-    const mxl_frame_layout& dl = dst[0]->layout;
-    k::ScaleLaunch L{};
-    uint32_t tw, th;
-    k::scale_tile_dims(&tw, &th);
-    uint32_t tile_base = 0, max_span = 16, max_rows = 1;
-    for (int p = 0; p < 3; p++) {
-        // subframe addressing (codec/src/ffmpeg/frame.rs:219-281): offsets are chroma-aligned already
-        const uint32_t sh = p ? 1 : 0;
-        k::ScalePlane& P = L.pl[p];
-        P.src_off = (uint32_t)sl.offset[p];
-        P.src_w = p ? (sl.width + 1) / 2 : sl.width;
-        P.src_h = sl.plane_h[p];
-        P.src_stride = sl.stride[p];
-        P.dst_w = g.scaled_w >> sh;
-        P.dst_h = g.scaled_h >> sh;
-        P.dst_stride = dl.stride[p];
-        P.dst_off = (uint32_t)(dl.offset[p] + (uint64_t)(g.letterbox_y >> sh) * dl.stride[p] + (g.letterbox_x >> sh));
-        P.tile_base = tile_base;
-        if (P.dst_w == 0 || P.dst_h == 0) { P.tiles_x = P.tiles_y = 0; continue; }
-        const std::vector<int32_t>*hx, *hy;
-        MXL_TRY(axis_table(ctx, P.src_w, P.dst_w, &P.xpos, &P.xcoef, &hx));
-        MXL_TRY(axis_table(ctx, P.src_h, P.dst_h, &P.ypos, &P.ycoef, &hy));
-        P.tiles_x = (P.dst_w + tw - 1) / tw;
-        P.tiles_y = (P.dst_h + th - 1) / th;
-        tile_base += P.tiles_x * P.tiles_y;
-        auto clampi = [](int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); };
-        for (uint32_t t = 0; t < P.tiles_x; t++) {          // staged bytes per row: from the 16-aligned first tap to the last tap
-            const uint32_t x0 = t * tw, x1 = std::min(x0 + tw, P.dst_w) - 1;
-            const int lo = clampi((*hx)[x0], (int)P.src_w - 1) & ~15, hi = clampi((*hx)[x1] + 3, (int)P.src_w - 1);
-            max_span = std::max<uint32_t>(max_span, (uint32_t)((hi - lo) / 16 + 1) * 16);
-        }
-        for (uint32_t t = 0; t < P.tiles_y; t++) {
-            const uint32_t y0 = t * th, y1 = std::min(y0 + th, P.dst_h) - 1;
-            const int lo = clampi((*hy)[y0], (int)P.src_h - 1), hi = clampi((*hy)[y1] + 3, (int)P.src_h - 1);
-            max_rows = std::max<uint32_t>(max_rows, (uint32_t)(hi - lo + 1));
-        }
-    }
-    L.total_tiles = tile_base;
-    L.region_pitch = max_span;
-    L.region_rows = max_rows;
-    if (ctx->scale_jobs_cap < n) {
-        if (ctx->scale_jobs) { MXL_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->scale_jobs); ctx->scale_jobs = nullptr; }
-        const size_t cap = std::max<size_t>(256, (size_t)n * 2);
-        MXL_CUDA(cudaMalloc(&ctx->scale_jobs, cap * sizeof(k::ScaleJob)));
-        ctx->scale_jobs_cap = cap;
-    }
-    MXL_CUDA(cudaMemcpyAsync(ctx->scale_jobs, jobs.data(), n * sizeof(k::ScaleJob), cudaMemcpyHostToDevice, ctx->stream));
-    L.jobs = (const k::ScaleJob*)ctx->scale_jobs;
-    const int st = k::launch_scale_tiled(ctx, L, n);
-    if (st != MXL_OK) {
-        for (uint32_t i = 0; i < n; i++) { frame_release(dst[i]); dst[i] = nullptr; }
-        return st;
-    }
-    return MXL_OK;
+    if (st == MXL_OK) st = scale_run(ctx, sl, out_w, out_h, jobs.data(), n);
+    if (st != MXL_OK)
+        for (uint32_t i = 0; i < n; i++) { if (dst[i]) frame_release(dst[i]); dst[i] = nullptr; }
+    return st;
 }
 
 mxl_frame* frame_scale(mxl_frame* src, uint32_t out_w, uint32_t out_h)
@@ -1210,6 +1137,8 @@ int VideoMixer::run(uint64_t t0, const IoSet& io, uint64_t* bytes)
 
     std::vector<k::FadeJob> jobs;
     std::vector<mxl_frame_layout> job_layouts;
+    struct ScaleGroup { mxl_frame_layout sl; uint32_t w, h; std::vector<k::ScaleJob> jobs; };
+    std::vector<ScaleGroup> scale_groups;                 // input frames waiting for the scaler, by geometry
     // The crossfade of all ticks is ONE launch at the end of the call, so every frame a job points
     // at must outlive later ticks' expiry/replacement (a released buffer goes back to the pool and
     // could be handed out again as a later tick's output).
@@ -1257,8 +1186,25 @@ int VideoMixer::run(uint64_t t0, const IoSet& io, uint64_t* bytes)
             if (const VideoSlot* s = in_slot(idx)) {
                 clear_stored(c);
                 MXL_TRY(rescale(c, target));
-                mxl_frame* scaled = frame_scale(s->frame, target.w, target.h);
-                if (!scaled) return MXL_ERR_CUDA;
+                // Channel::scale (video_mixer.rs:276-279): identity when the sizes agree, else into a new
+                // frame whose pixels are produced by ONE scaler launch per geometry at the end of the call
+                mxl_frame* scaled;
+                const mxl_frame_layout& sl = s->frame->layout;
+                if (sl.width == target.w && sl.height == target.h) {
+                    scaled = frame_retain(s->frame);
+                } else {
+                    scaled = scale_target(ctx, sl, target.w, target.h);
+                    if (!scaled) return MXL_ERR_OOM;
+                    ScaleGroup* grp = nullptr;
+                    for (auto& gq : scale_groups)
+                        if (gq.sl.width == sl.width && gq.sl.height == sl.height && gq.w == target.w && gq.h == target.h) grp = &gq;
+                    if (!grp) { scale_groups.push_back(ScaleGroup{sl, target.w, target.h, {}}); grp = &scale_groups.back(); }
+                    grp->jobs.push_back(k::ScaleJob{s->frame->dev, scaled->dev});
+                    // source and destination stay out of the frame pool until the call ends: the launch that
+                    // reads / writes them is still to come, whatever later ticks do with this channel
+                    keepalive.push_back(frame_retain(s->frame));
+                    keepalive.push_back(frame_retain(scaled));
+                }
                 c.has_stored = true;
                 c.frame = scaled;
                 c.active_until = now + s->tick_offset + s->duration_hint;                          // 140
@@ -1285,6 +1231,8 @@ int VideoMixer::run(uint64_t t0, const IoSet& io, uint64_t* bytes)
         frame_release(outf);                                // the line holds the reference now
     }
 
+    // the scaler first (its outputs are crossfade inputs): one launch per geometry
+    for (auto& gq : scale_groups) MXL_TRY(scale_run(ctx, gq.sl, gq.w, gq.h, gq.jobs.data(), (uint32_t)gq.jobs.size()));
     // one batched launch per run of equal layouts (normally exactly one)
     if (!jobs.empty()) {
         MXL_TRY(this->jobs.ensure(ctx, jobs.size() * sizeof(k::FadeJob)));

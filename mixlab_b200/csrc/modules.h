@@ -65,6 +65,7 @@ int pcm_sink_download(mxl_module* m, int16_t* host, uint64_t n);
 int mixer_params_get(const mxl_module* m, mxl_mixer_channel_params* out, uint32_t cap);
 
 mxl_frame* frame_scale(mxl_frame* src, uint32_t out_w, uint32_t out_h);
+mxl_frame* scale_target(mxl_ctx* ctx, const mxl_frame_layout& sl, uint32_t out_w, uint32_t out_h);
 int frames_scale(mxl_ctx* ctx, mxl_frame* const* src, mxl_frame** dst, uint32_t n, uint32_t out_w, uint32_t out_h);
 
 }  // namespace mxl

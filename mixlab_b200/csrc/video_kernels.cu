@@ -106,80 +106,35 @@ __device__ __forceinline__ uint32_t yuv_px(int y, int u, int v)
     return r | (g << 8) | (b << 16) | 0xFF000000u;
 }
 
-struct RgbaArgs {
-    const uint8_t* y; const uint8_t* u; const uint8_t* v; uint8_t* rgba;
-    uint32_t width, height, ystride, cstride;
-};
-
-__global__ void __launch_bounds__(kVidThreads) yuv_to_rgba_kernel(const __grid_constant__ RgbaArgs p)
+// The same conversion arranged for throughput (the compositor is integer-ALU-bound, not HBM-bound, when every
+// pixel runs yuv_px): the chroma terms of a 2x2 block are formed once, each channel is one multiply-add
+// 298*y + term, the clip works on the unshifted sum (clamp to [0, 65535], then byte 1 is the clipped
+// (sum >> 8): a negative sum gives 0, a sum >= 65536 gives 255), and bytes are gathered with PRMT.
+struct ChromaTerms { int r, g, b; };
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return __byte_perm(w, 0u, 0x4440u | (uint32_t)i); }
+__device__ __forceinline__ ChromaTerms chroma_terms(uint32_t u, uint32_t v)
 {
-    const uint32_t x0 = (blockIdx.x * kVidThreads + threadIdx.x) * 4;
-    const uint32_t row = blockIdx.y;
-    if (x0 >= p.width) return;
-    const uint8_t* yr = p.y + (uint64_t)row * p.ystride;
-    const uint8_t* ur = p.u + (uint64_t)(row >> 1) * p.cstride;
-    const uint8_t* vr = p.v + (uint64_t)(row >> 1) * p.cstride;
-    uint8_t* out = p.rgba + ((uint64_t)row * p.width + x0) * 4;
-    if (x0 + 4 <= p.width) {
-        const uint32_t yy = *reinterpret_cast<const uint32_t*>(yr + x0);
-        const uint32_t uu = *reinterpret_cast<const uint16_t*>(ur + (x0 >> 1));
-        const uint32_t vv = *reinterpret_cast<const uint16_t*>(vr + (x0 >> 1));
-        uint4 px;
-        px.x = yuv_px(yy & 0xFF, uu & 0xFF, vv & 0xFF);
-        px.y = yuv_px((yy >> 8) & 0xFF, uu & 0xFF, vv & 0xFF);
-        px.z = yuv_px((yy >> 16) & 0xFF, uu >> 8, vv >> 8);
-        px.w = yuv_px(yy >> 24, uu >> 8, vv >> 8);
-        if ((p.width & 3u) == 0) {
-            *reinterpret_cast<uint4*>(out) = px;          // rows start 16-byte aligned only then
-        } else {
-            uint32_t* o = reinterpret_cast<uint32_t*>(out);
-            o[0] = px.x; o[1] = px.y; o[2] = px.z; o[3] = px.w;
-        }
-    } else {
-        for (uint32_t x = x0; x < p.width; x++)
-            reinterpret_cast<uint32_t*>(p.rgba + (uint64_t)row * p.width * 4)[x] = yuv_px(yr[x], ur[x >> 1], vr[x >> 1]);
-    }
+    // 128 (rounding) - 298*16 folded in:  409 e + 128 - 4768,  -100 d - 208 e + 128 - 4768,  516 d + 128 - 4768
+    ChromaTerms t;
+    t.r = 409 * (int)v - 56992;
+    t.g = -100 * (int)u - 208 * (int)v + 34784;
+    t.b = 516 * (int)u - 70688;
+    return t;
 }
-
-// 4-tap separable resample with 14-bit tables; rounding (acc + 8192) >> 14, clipped to u8
-__global__ void __launch_bounds__(kVidThreads) resample_h_kernel(const uint8_t* __restrict__ src, uint32_t sw, uint32_t sstride,
-                                                                 uint8_t* __restrict__ dst, uint32_t dw, uint32_t dstride,
-                                                                 const int32_t* __restrict__ pos, const short* __restrict__ coef)
+__device__ __forceinline__ uint32_t yuv_px_terms(uint32_t y, const ChromaTerms& t)
 {
-    const uint32_t x = blockIdx.x * kVidThreads + threadIdx.x;
-    if (x >= dw) return;
-    const uint8_t* row = src + (uint64_t)blockIdx.y * sstride;
-    const int p0 = pos[x];
-    int acc = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        int sx = min(max(p0 + k, 0), (int)sw - 1);
-        acc += (int)coef[x * 4 + k] * (int)row[sx];
-    }
-    dst[(uint64_t)blockIdx.y * dstride + x] = (uint8_t)clip8((acc + 8192) >> 14);
-}
-
-__global__ void __launch_bounds__(kVidThreads) resample_v_kernel(const uint8_t* __restrict__ src, uint32_t sw, uint32_t sh, uint32_t sstride,
-                                                                 uint8_t* __restrict__ dst, uint32_t dstride,
-                                                                 const int32_t* __restrict__ pos, const short* __restrict__ coef)
-{
-    const uint32_t x = blockIdx.x * kVidThreads + threadIdx.x;
-    if (x >= sw) return;
-    const uint32_t y = blockIdx.y;
-    const int p0 = pos[y];
-    int acc = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        int sy = min(max(p0 + k, 0), (int)sh - 1);
-        acc += (int)coef[y * 4 + k] * (int)src[(uint64_t)sy * sstride + x];
-    }
-    dst[(uint64_t)y * dstride + x] = (uint8_t)clip8((acc + 8192) >> 14);
+    const int r = __vimin_s32_relu(298 * (int)y + t.r, 65535);
+    const int g = __vimin_s32_relu(298 * (int)y + t.g, 65535);
+    const int b = __vimin_s32_relu(298 * (int)y + t.b, 65535);
+    const uint32_t rg = __byte_perm((uint32_t)r, (uint32_t)g, 0x4451u);      // byte1(r), byte1(g), 0, 0
+    return __byte_perm(rg, (uint32_t)b, 0x4510u) | 0xFF000000u;              // r, g, byte1(b), alpha
 }
 
 // ------------------------------------------------------------------------------------------------
 // Tiled letterbox scaler (DynamicScaler::scale, src/video/encode.rs:338-397; the arithmetic is this
 // repository's stand-in for swscale's SWS_BICUBIC -- DESIGN.md "unpinned"): all three planes of a
-// batch of frames in ONE launch.  A CTA owns a 64x16 tile of output pixels of one plane:
+// batch of frames in ONE launch.  A CTA owns a 64x32 tile of output pixels of one plane (64x8 or 64x2 when a
+// strong down-scale would make the source rectangle of a taller tile outgrow shared memory):
 //   1. the source rectangle the tile's taps touch is staged global -> shared with 16-byte cp.async
 //      (rows and columns clamped the way the taps clamp, so edges need no special case);
 //   2. horizontal 4-tap pass shared -> shared into a u8 intermediate (rounded and clipped exactly as the
@@ -188,7 +143,7 @@ __global__ void __launch_bounds__(kVidThreads) resample_v_kernel(const uint8_t* 
 // Every source byte is read from HBM once per tile that needs it (neighbouring tiles share a 3-pixel
 // apron through L2); the intermediate never leaves the SM.
 // ------------------------------------------------------------------------------------------------
-constexpr int kScaleTW = 64, kScaleTH = 16;
+constexpr int kScaleTW = 64;      // tile width; the tile height is a template parameter (32, 8 or 2 output rows)
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src)
 {
@@ -196,9 +151,21 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
 }
 
+// first tap of output index d (the tables' pos[d]; modules.cu bicubic_table): floor(((2d+1) src - dst) / (2 dst)) - 1.
+// Recomputed here so that a tile can start staging its source rectangle without first waiting for a table load.
+__device__ __forceinline__ int first_tap(uint32_t d, uint32_t src_n, uint32_t dst_n)
+{
+    const long long num = (long long)(2ull * d + 1ull) * src_n - dst_n, den = 2ll * dst_n;
+    const long long ix = num >= 0 ? num / den : -((-num + den - 1) / den);
+    return (int)ix - 1;
+}
+
+template <int kScaleTH>
 __global__ void __launch_bounds__(kVidThreads) scale_tiled_kernel(const __grid_constant__ ScaleLaunch L)
 {
     extern __shared__ __align__(16) uint8_t sc_smem[];
+    __shared__ int s_xpos[kScaleTW], s_ypos[kScaleTH];
+    __shared__ short4 s_xco[kScaleTW], s_yco[kScaleTH];
     const ScaleJob job = L.jobs[blockIdx.y];
     int pi = 0;
     if (blockIdx.x >= L.pl[1].tile_base) pi = 1;
@@ -208,11 +175,11 @@ __global__ void __launch_bounds__(kVidThreads) scale_tiled_kernel(const __grid_c
     const uint32_t x0 = (t % P.tiles_x) * kScaleTW, y0 = (t / P.tiles_x) * kScaleTH;
     const uint32_t x1 = min(x0 + kScaleTW, P.dst_w) - 1, y1 = min(y0 + kScaleTH, P.dst_h) - 1;
     const int sw = (int)P.src_w, sh = (int)P.src_h;
-    // source rectangle touched by the tile's taps (tables are monotonic)
-    const int cx_lo = min(max(P.xpos[x0], 0), sw - 1) & ~15;
-    const int cx_hi = min(max(P.xpos[x1] + 3, 0), sw - 1);
-    const int ry_lo = min(max(P.ypos[y0], 0), sh - 1);
-    const int ry_hi = min(max(P.ypos[y1] + 3, 0), sh - 1);
+    // source rectangle touched by the tile's taps (first taps are monotonic in the output index)
+    const int cx_lo = min(max(first_tap(x0, P.src_w, P.dst_w), 0), sw - 1) & ~15;
+    const int cx_hi = min(max(first_tap(x1, P.src_w, P.dst_w) + 3, 0), sw - 1);
+    const int ry_lo = min(max(first_tap(y0, P.src_h, P.dst_h), 0), sh - 1);
+    const int ry_hi = min(max(first_tap(y1, P.src_h, P.dst_h) + 3, 0), sh - 1);
     const int chunks = (cx_hi - cx_lo) / 16 + 1, rows = ry_hi - ry_lo + 1;
     const int pitch = (int)L.region_pitch;                       // bytes per staged row (host bound, multiple of 16)
     uint8_t* region = sc_smem;                                   // [rows][pitch]
@@ -222,34 +189,69 @@ __global__ void __launch_bounds__(kVidThreads) scale_tiled_kernel(const __grid_c
         const int r = i / chunks, c = i - r * chunks;
         cp_async_16(region + r * pitch + c * 16, src + (size_t)(ry_lo + r) * P.src_stride + cx_lo + c * 16);
     }
+    // the tile's slices of the tap tables, in flight together with the staging
+    if (threadIdx.x < kScaleTW) {
+        const uint32_t gx = min(x0 + threadIdx.x, x1);
+        s_xpos[threadIdx.x] = P.xpos[gx];
+        s_xco[threadIdx.x] = *reinterpret_cast<const short4*>(P.xcoef + (size_t)gx * 4);
+    } else if (threadIdx.x < kScaleTW + kScaleTH) {
+        const uint32_t i = threadIdx.x - kScaleTW, gy = min(y0 + i, y1);
+        s_ypos[i] = P.ypos[gy];
+        s_yco[i] = *reinterpret_cast<const short4*>(P.ycoef + (size_t)gy * 4);
+    }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    // horizontal pass: mid[r][x] for every staged row
-    const int lx = threadIdx.x % kScaleTW;
-    const uint32_t gx = x0 + lx;
-    if (gx <= x1) {
-        const int p0 = P.xpos[gx];
-        const short4 cf = *reinterpret_cast<const short4*>(P.xcoef + (size_t)gx * 4);
-        const int o0 = min(max(p0, 0), sw - 1) - cx_lo, o1 = min(max(p0 + 1, 0), sw - 1) - cx_lo;
-        const int o2 = min(max(p0 + 2, 0), sw - 1) - cx_lo, o3 = min(max(p0 + 3, 0), sw - 1) - cx_lo;
-        for (int r = threadIdx.x / kScaleTW; r < rows; r += kVidThreads / kScaleTW) {
+    // horizontal pass: thread = 4 adjacent output columns of one staged row at a time; mid[r][x] packed 4 per store
+    {
+        const int q = threadIdx.x % (kScaleTW / 4);               // column quad
+        int off[4][4];
+        short4 cf[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int p0 = s_xpos[4 * q + j];
+            cf[j] = s_xco[4 * q + j];
+#pragma unroll
+            for (int k = 0; k < 4; k++) off[j][k] = min(max(p0 + k, 0), sw - 1) - cx_lo;
+        }
+        for (int r = threadIdx.x / (kScaleTW / 4); r < rows; r += kVidThreads / (kScaleTW / 4)) {
             const uint8_t* row = region + r * pitch;
-            const int acc = cf.x * (int)row[o0] + cf.y * (int)row[o1] + cf.z * (int)row[o2] + cf.w * (int)row[o3];
-            mid[r * kScaleTW + lx] = (uint8_t)clip8((acc + 8192) >> 14);
+            uint32_t packed = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int acc = cf[j].x * (int)row[off[j][0]] + cf[j].y * (int)row[off[j][1]] +
+                                cf[j].z * (int)row[off[j][2]] + cf[j].w * (int)row[off[j][3]];
+                packed |= clip8((acc + 8192) >> 14) << (8 * j);
+            }
+            reinterpret_cast<uint32_t*>(mid + r * kScaleTW)[q] = packed;
         }
     }
     __syncthreads();
-    // vertical pass
-    if (gx <= x1) {
+    // vertical pass: thread = 4 adjacent output columns of one output row at a time, one 32-bit load per tap
+    {
+        const int q = threadIdx.x % (kScaleTW / 4);
         uint8_t* dst = job.dst + P.dst_off;
-        for (uint32_t gy = y0 + threadIdx.x / kScaleTW; gy <= y1; gy += kVidThreads / kScaleTW) {
-            const int p0 = P.ypos[gy];
-            const short4 cf = *reinterpret_cast<const short4*>(P.ycoef + (size_t)gy * 4);
+        const bool word_ok = ((P.dst_off | P.dst_stride) & 3u) == 0;
+        for (uint32_t ly = threadIdx.x / (kScaleTW / 4); y0 + ly <= y1; ly += kVidThreads / (kScaleTW / 4)) {
+            const int p0 = s_ypos[ly];
+            const short4 cf = s_yco[ly];
             const int r0 = min(max(p0, 0), sh - 1) - ry_lo, r1 = min(max(p0 + 1, 0), sh - 1) - ry_lo;
             const int r2 = min(max(p0 + 2, 0), sh - 1) - ry_lo, r3 = min(max(p0 + 3, 0), sh - 1) - ry_lo;
-            const int acc = cf.x * (int)mid[r0 * kScaleTW + lx] + cf.y * (int)mid[r1 * kScaleTW + lx] +
-                            cf.z * (int)mid[r2 * kScaleTW + lx] + cf.w * (int)mid[r3 * kScaleTW + lx];
-            dst[(size_t)gy * P.dst_stride + gx] = (uint8_t)clip8((acc + 8192) >> 14);
+            const uint32_t a0 = reinterpret_cast<const uint32_t*>(mid + r0 * kScaleTW)[q], a1 = reinterpret_cast<const uint32_t*>(mid + r1 * kScaleTW)[q];
+            const uint32_t a2 = reinterpret_cast<const uint32_t*>(mid + r2 * kScaleTW)[q], a3 = reinterpret_cast<const uint32_t*>(mid + r3 * kScaleTW)[q];
+            uint32_t packed = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int acc = cf.x * (int)((a0 >> (8 * j)) & 0xFF) + cf.y * (int)((a1 >> (8 * j)) & 0xFF) +
+                                cf.z * (int)((a2 >> (8 * j)) & 0xFF) + cf.w * (int)((a3 >> (8 * j)) & 0xFF);
+                packed |= clip8((acc + 8192) >> 14) << (8 * j);
+            }
+            const uint32_t gx = x0 + 4 * q;
+            uint8_t* o = dst + (size_t)(y0 + ly) * P.dst_stride + gx;
+            if (word_ok && gx + 3 <= x1) {
+                *reinterpret_cast<uint32_t*>(o) = packed;
+            } else {
+                for (uint32_t j = 0; j < 4 && gx + j <= x1; j++) o[j] = (uint8_t)(packed >> (8 * j));
+            }
         }
     }
 }
@@ -290,10 +292,14 @@ __global__ void __launch_bounds__(kVidThreads) compose_rgba_kernel(const Compose
     const uint32_t u = fade4(ua, ub, f, g), v = fade4(va, vb, f, g);
     uint32_t px0[8], px1[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const int uu = (u >> (8 * (i >> 1))) & 0xFF, vv = (v >> (8 * (i >> 1))) & 0xFF;
-        px0[i] = yuv_px((y0w[i >> 2] >> (8 * (i & 3))) & 0xFF, uu, vv);
-        px1[i] = yuv_px((y1w[i >> 2] >> (8 * (i & 3))) & 0xFF, uu, vv);
+    for (int j = 0; j < 4; j++) {                                  // one chroma sample = a 2x2 block of pixels
+        const ChromaTerms ct = chroma_terms(byte_of(u, j), byte_of(v, j));
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int i = 2 * j + h;
+            px0[i] = yuv_px_terms(byte_of(y0w[i >> 2], i & 3), ct);
+            px1[i] = yuv_px_terms(byte_of(y1w[i >> 2], i & 3), ct);
+        }
     }
     uint8_t* o0 = job.rgba + ((uint64_t)(2 * cy) * width + x0) * 4;
     uint8_t* o1 = o0 + (uint64_t)width * 4;
@@ -356,6 +362,7 @@ int launch_crossfade(mxl_ctx* ctx, const mxl_frame_layout& lay, const FadeJob* j
         const uint64_t n16 = lay.size / 16;
         const uint64_t per_block = (uint64_t)kVidThreads * kFadeUnroll;
         dim3 grid((unsigned)((n16 + per_block - 1) / per_block), n_jobs);
+        MXL_TIMED(ctx, "crossfade_flat_kernel");
         crossfade_flat_kernel<<<grid, kVidThreads, 0, ctx->stream>>>(jobs_dev, n16, lay.offset[1] / 16);
         return after_launch(ctx, "crossfade_flat_kernel");
     }
@@ -364,6 +371,7 @@ int launch_crossfade(mxl_ctx* ctx, const mxl_frame_layout& lay, const FadeJob* j
         if (g.rows == 0 || g.padw == 0) continue;
         const uint32_t vpr = g.padw / 16;
         dim3 grid((vpr + kVidThreads - 1) / kVidThreads, g.rows, n_jobs);
+        MXL_TIMED(ctx, "crossfade_plane_kernel");
         crossfade_plane_kernel<<<grid, kVidThreads, 0, ctx->stream>>>(jobs_dev, lay.offset[c], lay.stride[c], vpr,
                                                                      c == 0 ? 0u : 0x80808080u);
         MXL_TRY(after_launch(ctx, "crossfade_plane_kernel"));
@@ -379,59 +387,41 @@ int launch_blank(mxl_ctx* ctx, const mxl_frame_layout& lay, uint8_t* frame)
     const unsigned cap = ctx->sm_count > 0 ? ctx->sm_count * 8 : 1184;
     if (blocks > cap) blocks = cap;
     if (blocks == 0) return MXL_OK;
+    MXL_TIMED(ctx, "blank_kernel");
     blank_kernel<<<blocks, kVidThreads, 0, ctx->stream>>>(reinterpret_cast<uint4*>(frame), n16, lay.offset[1] / 16);
     return after_launch(ctx, "blank_kernel");
 }
 
-int launch_yuv_to_rgba(mxl_ctx* ctx, const mxl_frame_layout& lay, const uint8_t* yuv, uint8_t* rgba)
+template <int TH>
+static int launch_scale_th(mxl_ctx* ctx, const ScaleLaunch& L, uint32_t n_jobs, size_t smem)
 {
-    MXL_TRY(require_device(ctx));
-    if (lay.width == 0 || lay.height == 0) return MXL_OK;
-    RgbaArgs a{yuv + lay.offset[0], yuv + lay.offset[1], yuv + lay.offset[2], rgba,
-               lay.width, lay.height, lay.stride[0], lay.stride[1]};
-    dim3 grid(((lay.width + 3) / 4 + kVidThreads - 1) / kVidThreads, lay.height);
-    yuv_to_rgba_kernel<<<grid, kVidThreads, 0, ctx->stream>>>(a);
-    return after_launch(ctx, "yuv_to_rgba_kernel");
+    uint32_t& configured = ctx->scale_smem[TH == 32 ? 0 : (TH == 8 ? 1 : 2)];
+    if (smem > 48 * 1024 && smem > configured) {
+        MXL_CUDA(cudaFuncSetAttribute(scale_tiled_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = (uint32_t)smem;
+    }
+    dim3 grid(L.total_tiles, n_jobs);
+    MXL_TIMED(ctx, "scale_tiled_kernel");
+    scale_tiled_kernel<TH><<<grid, kVidThreads, smem, ctx->stream>>>(L);
+    return after_launch(ctx, "scale_tiled_kernel");
 }
 
-int launch_resample_h(mxl_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, uint32_t sstride,
-                      uint8_t* dst, uint32_t dw, uint32_t dstride, const int32_t* pos, const int16_t* coef)
-{
-    MXL_TRY(require_device(ctx));
-    if (dw == 0 || sh == 0) return MXL_OK;
-    dim3 grid((dw + kVidThreads - 1) / kVidThreads, sh);
-    resample_h_kernel<<<grid, kVidThreads, 0, ctx->stream>>>(src, sw, sstride, dst, dw, dstride, pos,
-                                                             reinterpret_cast<const short*>(coef));
-    return after_launch(ctx, "resample_h_kernel");
-}
-
-int launch_resample_v(mxl_ctx* ctx, const uint8_t* src, uint32_t sw, uint32_t sh, uint32_t sstride,
-                      uint8_t* dst, uint32_t dh, uint32_t dstride, const int32_t* pos, const int16_t* coef)
-{
-    MXL_TRY(require_device(ctx));
-    if (sw == 0 || dh == 0) return MXL_OK;
-    dim3 grid((sw + kVidThreads - 1) / kVidThreads, dh);
-    resample_v_kernel<<<grid, kVidThreads, 0, ctx->stream>>>(src, sw, sh, sstride, dst, dstride, pos,
-                                                             reinterpret_cast<const short*>(coef));
-    return after_launch(ctx, "resample_v_kernel");
-}
+size_t scale_smem_bytes(uint32_t region_rows, uint32_t region_pitch) { return (size_t)region_rows * region_pitch + (size_t)region_rows * kScaleTW; }
+uint32_t scale_tile_width() { return kScaleTW; }
 
 int launch_scale_tiled(mxl_ctx* ctx, const ScaleLaunch& L, uint32_t n_jobs)
 {
     MXL_TRY(require_device(ctx));
     if (n_jobs == 0 || L.total_tiles == 0) return MXL_OK;
-    const size_t smem = (size_t)L.region_rows * L.region_pitch + (size_t)L.region_rows * kScaleTW;
-    if (smem > 200 * 1024) MXL_FAIL(MXL_ERR_INVALID, "scale_tiled_kernel: source rectangle of a tile needs %zu bytes of shared memory", smem);
-    if (smem > 48 * 1024 && smem > ctx->scale_smem) {
-        MXL_CUDA(cudaFuncSetAttribute(scale_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ctx->scale_smem = smem;
+    const size_t smem = scale_smem_bytes(L.region_rows, L.region_pitch);
+    if (smem > kScaleMaxSmem) MXL_FAIL(MXL_ERR_INVALID, "scale_tiled_kernel: source rectangle of a tile needs %zu bytes of shared memory", smem);
+    switch (L.tile_h) {
+    case 32: return launch_scale_th<32>(ctx, L, n_jobs, smem);
+    case 8: return launch_scale_th<8>(ctx, L, n_jobs, smem);
+    case 2: return launch_scale_th<2>(ctx, L, n_jobs, smem);
+    default: MXL_FAIL(MXL_ERR_INVALID, "scale_tiled_kernel: tile height %u", L.tile_h);
     }
-    dim3 grid(L.total_tiles, n_jobs);
-    scale_tiled_kernel<<<grid, kVidThreads, smem, ctx->stream>>>(L);
-    return after_launch(ctx, "scale_tiled_kernel");
 }
-
-void scale_tile_dims(uint32_t* tw, uint32_t* th) { *tw = kScaleTW; *th = kScaleTH; }
 
 int launch_compose_rgba(mxl_ctx* ctx, const mxl_frame_layout& lay, const ComposeRgbaJob* jobs_dev, uint32_t n_jobs)
 {
@@ -440,6 +430,7 @@ int launch_compose_rgba(mxl_ctx* ctx, const mxl_frame_layout& lay, const Compose
     if ((lay.stride[0] & 7) || (lay.stride[1] & 3) || (lay.offset[1] & 3) || (lay.offset[2] & 3))
         MXL_FAIL(MXL_ERR_INVALID, "compose_rgba: plane strides/offsets must be 8/4-byte aligned");
     dim3 grid(((lay.width + 7) / 8 + kVidThreads - 1) / kVidThreads, (lay.height + 1) / 2, n_jobs);
+    MXL_TIMED(ctx, "compose_rgba_kernel");
     compose_rgba_kernel<<<grid, kVidThreads, 0, ctx->stream>>>(jobs_dev, lay.width, lay.height, lay.stride[0], lay.stride[1],
                                                                lay.offset[1], lay.offset[2]);
     return after_launch(ctx, "compose_rgba_kernel");

@@ -199,6 +199,26 @@ def test_params_update_and_topology_edit_between_runs(mxl, oracle, ctx48):
     g.destroy()
 
 
+def test_kernel_timing_brackets_every_launch(mxl, ctx48):
+    """mxl_ctx_set_kernel_timing: one event pair per kernel launch, folded per kernel name."""
+    g, ids = W.build_graph(ctx48, W.config2_graph())
+    g.run_ticks(0, 4)
+    ctx48.kernel_times()
+    ctx48.set_kernel_timing(True)
+    before = ctx48.launch_count
+    g.run_ticks(4, 8)
+    g.run_ticks(12, 8)
+    launched = ctx48.launch_count - before
+    times = ctx48.kernel_times()
+    ctx48.set_kernel_timing(False)
+    assert sum(n for n, _ in times.values()) == launched
+    assert set(times) == {"oscillator_kernel", "eq_stream_kernel", "panner_kernel", "mixer_kernel", "meter_kernel"}
+    assert all(n == 2 and 0.0 < ms < 50.0 for n, ms in times.values())
+    g.run_ticks(20, 8)
+    assert ctx48.kernel_times() == {}                  # disabled: nothing recorded
+    g.destroy()
+
+
 def test_graph_stage_info_and_launch_count(mxl, ctx48):
     d = W.config2_graph()
     g, ids = W.build_graph(ctx48, d)

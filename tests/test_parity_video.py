@@ -170,7 +170,8 @@ def oracle_scale(oracle, data, lay_in, out_w, out_h):
 @pytest.mark.parametrize("src,dst", [((640, 480), (1280, 720)), ((1920, 1080), (1280, 720)), ((1280, 720), (1920, 1080)),
                                      ((3840, 2160), (1920, 1080)), ((70, 50), (560, 350)), ((560, 350), (70, 50)),
                                      ((1920, 1080), (480, 270)), ((34, 18), (36, 20)), ((1000, 1000), (1920, 1080)),
-                                     ((1920, 1080), (3840, 2160)), ((2, 2), (64, 64)), ((1366, 768), (1920, 1080))])
+                                     ((1920, 1080), (3840, 2160)), ((2, 2), (64, 64)), ((1366, 768), (1920, 1080)),
+                                     ((3840, 2160), (320, 180)), ((3840, 2160), (96, 54)), ((4096, 64), (64, 64))])
 def test_tiled_scaler_matches_two_pass_definition(mxl, oracle, ctx48, src, dst):
     """Every tile of the fused scaler (clamped aprons, ragged last tiles, up- and down-scaling, letterbox
     bars on either axis) against the oracle's plain two-pass definition.  UNPINNED arithmetic (stands in
@@ -179,6 +180,22 @@ def test_tiled_scaler_matches_two_pass_definition(mxl, oracle, ctx48, src, dst):
     got = fr.scale(dst[0], dst[1])
     assert (got.layout.width, got.layout.height) == dst
     assert np.array_equal(got.download_raw(), oracle_scale(oracle, data, lay_in, dst[0], dst[1]))
+
+
+def test_mixer_scales_all_ticks_of_a_call_in_one_launch(mxl, oracle, ctx48):
+    """Six ticks, layer B smaller than layer A on every tick: one blank fill per letterboxed frame, ONE
+    scaler launch for all six frames, one crossfade launch (video_mixer.rs:122-148, encode.rs:338-397)."""
+    ticks = 6
+    fa = [make_frame(ctx48, oracle, 1280, 720, 600 + k) for k in range(ticks)]
+    fb = [make_frame(ctx48, oracle, 640, 480, 700 + k) for k in range(ticks)]
+    before = ctx48.launch_count
+    mod, outs = run_mixer(mxl, ctx48, (0, 1, 0.3), {0: [f[0] for f in fa], 1: [f[0] for f in fb]}, ticks=ticks)
+    assert ctx48.launch_count - before == ticks + 2
+    lay = oracle.frame_layout(1280, 720)
+    f8 = oracle.fader_to_u8(0.3)
+    for k in range(ticks):
+        scaled = oracle_scale(oracle, fb[k][1], fb[k][2], 1280, 720)
+        assert np.array_equal(outs[0].get(k).download_raw(), oracle.video_crossfade(lay, fa[k][1], scaled, f8)), k
 
 
 def test_batched_scaler_one_launch(mxl, oracle, ctx48):

@@ -72,7 +72,7 @@ def main():
     run("Meter", mxl.MOD_METER, None, [stereo], [], 8 * S)
     run("PcmSink(pack i16)", mxl.MOD_PCM_SINK, None, [stereo], [], 12 * S)
     run("Mixer(2)", mxl.MOD_MIXER, [(0.0, 1.0, True), (-6.0, 0.5, False)], [stereo, o_s2], [o_s, ctx.line(mxl.LINE_STEREO, n)], 8 * S * 4)
-    if args.only and args.only not in 'VideoMixer':
+    if args.only and args.only not in "VideoMixer NOAUDIO":
         ctx.close()
         return
     # video: 64 frames of 1080p per launch through the VideoMixer module
