@@ -403,15 +403,18 @@ def b200_arm(args):
         st["frac_of_hbm_peak"] = st["gbs"] / peak
 
     # ---- per-kernel device time: CUDA event pairs directly around each launch (mxl_ctx_set_kernel_timing),
-    # over K more steps in the configuration of the timed region.  Unlike the stage times above these exclude
-    # the host-side preparation of a stage and its table copies ----
+    # over K more steps with the stages serialised on one stream (each kernel alone on the device, as in the
+    # ncu launch list under profiles/).  Unlike the stage times above these exclude the host-side preparation
+    # of a stage and its table copies ----
     ctx.kernel_times()
+    sess.graph.set_stream_split(False)
     ctx.set_kernel_timing(True)
     for _ in range(K):
         sess.run_step(tick)
         tick += T
     kt = ctx.kernel_times()
     ctx.set_kernel_timing(False)
+    sess.graph.set_stream_split(True)
     kernels = {name: {"launches": n, "avg_launch_ms": ms / n} for name, (n, ms) in kt.items() if n}
     stage_kernel = {"VideoMixer": "crossfade_flat_kernel", "EqThree": "eq_stream_kernel", "Oscillator": "oscillator_kernel",
                     "StereoPanner": "panner_kernel", "Mixer": "mixer_kernel", "Meter": "meter_kernel"}
@@ -435,8 +438,9 @@ def b200_arm(args):
                 "stage_ms_serialised": d["ms"], "stage_ms_overlapped": d["ms_overlapped"],
                 "step_share": dk["avg_launch_ms"] * dk.get("launches", K) / K / total_kernel_ms if total_kernel_ms else None,
                 "timing": "CUDA event pair recorded directly around each launch of the kernel on its launching stream "
-                          "(mxl_ctx_set_kernel_timing), averaged over K steps in the timed region's configuration; "
-                          "step_share = this kernel's device time / all kernels' device time per step"}
+                          "(mxl_ctx_set_kernel_timing), averaged over K steps, stages serialised on one stream; "
+                          "step_share = this kernel's device time / all kernels' device time per step; "
+                          "stage_ms_overlapped = the stage as it runs in the timed region, beside the audio stream"}
     whole = sess.algorithmic_bytes_per_step / (ms_max / K * 1e-3) / 1e9
 
     # ---- e2e: host buffers through the C ABI ----

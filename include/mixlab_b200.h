@@ -307,6 +307,19 @@ MXL_API int mxl_video_compose_rgba(mxl_ctx *ctx, mxl_frame *const *a, mxl_frame 
 MXL_API int mxl_frames_to_rgba(mxl_ctx *ctx, mxl_frame *const *frames, uint32_t n, mxl_rgba *out,
                                uint32_t first_picture);
 
+/* ---- optional shared-source mode (NEW: no reference counterpart; one receiver per mountpoint there,
+ * src/source.rs:93-95).  Sessions on different GPUs share nothing on the tick path; when several graphs fan
+ * out from ONE ingest, the ingest GPU broadcasts the source line / frame to the others over NVLink with NCCL
+ * (bound at run time; these calls fail with MXL_ERR_INVALID where libnccl.so.2 is absent).  One process per GPU:
+ * rank 0 makes the id, every rank passes it to mxl_ctx_comm_init.  Broadcasts are asynchronous on the context
+ * stream, ordered with the kernels that produce / consume the buffer. */
+#define MXL_COMM_ID_BYTES 128
+MXL_API int mxl_comm_unique_id(uint8_t id_out[MXL_COMM_ID_BYTES]);
+MXL_API int mxl_ctx_comm_init(mxl_ctx *ctx, const uint8_t id[MXL_COMM_ID_BYTES], int rank, int world);
+MXL_API int mxl_ctx_comm_destroy(mxl_ctx *ctx);
+MXL_API int mxl_line_broadcast(mxl_line *line, int root);
+MXL_API int mxl_frame_broadcast(mxl_frame *frame, int root);
+
 /* ---- graph: Workspace + Engine::run_tick, src/engine/workspace.rs, src/engine.rs:400-510 ------ */
 
 MXL_API mxl_graph *mxl_graph_create(mxl_ctx *ctx);

@@ -211,6 +211,11 @@ def lib():
         "mxl_rgba_download_async": (i32, [vp, u32, u32, vp]),
         "mxl_video_compose_rgba": (i32, [vp, C.POINTER(vp), C.POINTER(vp), u32, dbl, vp, u32]),
         "mxl_frames_to_rgba": (i32, [vp, C.POINTER(vp), u32, vp, u32]),
+        "mxl_comm_unique_id": (i32, [vp]),
+        "mxl_ctx_comm_init": (i32, [vp, vp, i32, i32]),
+        "mxl_ctx_comm_destroy": (i32, [vp]),
+        "mxl_line_broadcast": (i32, [vp, i32]),
+        "mxl_frame_broadcast": (i32, [vp, i32]),
         "mxl_graph_create": (vp, [vp]),
         "mxl_graph_destroy": (None, [vp]),
         "mxl_graph_add_module": (i32, [vp, vp]),
@@ -267,6 +272,16 @@ def unify_picture_settings(aw, ah, bw, bh):
     w, h = C.c_uint32(), C.c_uint32()
     check(lib().mxl_unify_picture_settings(aw, ah, bw, bh, C.byref(w), C.byref(h)))
     return w.value, h.value
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """ncclUniqueId made by rank 0 and handed to every rank's Context.comm_init (any side channel)."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    check(lib().mxl_comm_unique_id(buf))
+    return bytes(buf)
 
 
 def scale_geometry(in_w, in_h, out_w, out_h):
@@ -381,6 +396,14 @@ class Context:
             fr.upload_raw(data)
         return fr
 
+    # ---- optional shared-source mode (NCCL broadcast from the ingest GPU) ----
+    def comm_init(self, unique_id, rank, world):
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        check(lib().mxl_ctx_comm_init(self.h, buf, rank, world))
+
+    def comm_destroy(self):
+        check(lib().mxl_ctx_comm_destroy(self.h))
+
     def set_kernel_timing(self, enabled):
         check(lib().mxl_ctx_set_kernel_timing(self.h, 1 if enabled else 0))
 
@@ -456,6 +479,10 @@ class Line:
     def zero(self):
         check(lib().mxl_line_zero(self.h))
 
+    def broadcast(self, root):
+        """Shared-source mode: the root rank's samples replace this line on every rank (mxl_line_broadcast)."""
+        check(lib().mxl_line_broadcast(self.h, root))
+
     def free(self):
         if self.h and self.owned:
             lib().mxl_line_free(self.h)
@@ -512,6 +539,9 @@ class Frame:
     def upload_raw(self, data):
         data = np.ascontiguousarray(data, np.uint8)
         check(lib().mxl_frame_upload_raw(self.h, _ptr(data), data.size))
+
+    def broadcast(self, root):
+        check(lib().mxl_frame_broadcast(self.h, root))
 
     def download_raw(self):
         out = np.empty(self.layout.size, np.uint8)

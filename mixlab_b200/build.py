@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(HERE, "libmixlab_b200.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "mixlab_b200.h")
 
 SOURCES = ["core.cu", "abi.cu", "modules.cu", "graph.cu", "audio_kernels.cu", "eq_three.cu", "eq_stream.cu",
-           "envelope.cu", "video_kernels.cu"]
+           "envelope.cu", "video_kernels.cu", "comm.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -85,7 +85,7 @@ def build(force=False, verbose=False):
     if verbose:
         sys.stderr.write(log)
     cmd = [nvcc(), "-shared", "-o", LIB_PATH] + [o for o, _ in results] + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                                          "-cudart", "static"]
+                                                                          "-cudart", "static", "-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s" % r.stdout)

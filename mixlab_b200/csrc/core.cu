@@ -358,6 +358,7 @@ int mxl_ctx_destroy(mxl_ctx* ctx)
     if (ctx->has_device()) {
         ctx->activate();
         cudaStreamSynchronize(ctx->stream);
+        mxl_ctx_comm_destroy(ctx);
         if (ctx->flush_buf) cudaFree(ctx->flush_buf);
         for (auto& e : ctx->kernel_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         for (cudaEvent_t e : ctx->kernel_event_pool) cudaEventDestroy(e);

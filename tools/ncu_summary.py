@@ -12,7 +12,8 @@ RAW_KEYS = {
     "gpu__time_duration.sum": "duration_ns",
     "dram__bytes_read.sum": "dram_read",
     "dram__bytes_write.sum": "dram_write",
-    "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct_of_peak",
+    "FBSP.TriageCompute.dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct_of_peak",
+    "dram__bytes.sum.per_second": "dram_bytes_per_second",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_pct_of_peak",
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed": "fp64_pipe_pct",
     "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_elapsed": "xu_pipe_pct",
