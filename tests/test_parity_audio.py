@@ -86,14 +86,14 @@ def test_amplifier_update_and_extreme_params(mxl, oracle, ctx48):
 
 
 # ---- EqThree (eq_three.rs:58-89,106-125) ------------------------------------------------------
-@pytest.mark.parametrize("chunk", ["auto", "b16", "b32", "b64", "b128", "64", "256", "1024", "4096"])
+@pytest.mark.parametrize("chunk", ["auto", "s16", "s32", "s64", "64", "256", "1024", "4096"])
 def test_eq_three_golden(mxl, ctx44, chunk, monkeypatch):
     """The reference's own golden vector (eq_three.rs:150-167), one run_tick over 355 285 samples.
-    "auto"/"bN": the single-launch kernel (chunk N); plain numbers: the two-launch kernel."""
+    "auto"/"sN": the single-launch kernel eq_stream_kernel<N>; plain numbers: the two-launch kernel."""
     monkeypatch.delenv("MXL_EQ_CHUNK", raising=False)
-    monkeypatch.delenv("MXL_EQ_BLOCK_CHUNK", raising=False)
-    if chunk.startswith("b"):
-        monkeypatch.setenv("MXL_EQ_BLOCK_CHUNK", chunk[1:])
+    monkeypatch.delenv("MXL_EQ_STREAM_CHUNK", raising=False)
+    if chunk.startswith("s"):
+        monkeypatch.setenv("MXL_EQ_STREAM_CHUNK", chunk[1:])
     elif chunk != "auto":
         monkeypatch.setenv("MXL_EQ_CHUNK", chunk)
     x = load_f32(os.path.join(GOLDEN, "eq_three", "chronos.f32.raw"))
