@@ -216,6 +216,13 @@ MXL_API int mxl_frame_download(const mxl_frame *frame, uint8_t *const planes[3],
 MXL_API int mxl_frame_upload_raw(mxl_frame *frame, const uint8_t *host, uint64_t size);
 MXL_API int mxl_frame_download_raw(const mxl_frame *frame, uint8_t *host, uint64_t size);
 MXL_API int mxl_frame_upload_raw_async(mxl_frame *frame, const uint8_t *host, uint64_t size);
+/* n frames of one size in ONE device allocation, adjacent in memory (freed with the last of them): what an
+ * ingest that hands over several frames per engine call allocates, so that mxl_frames_upload_raw_async /
+ * _download_raw_async move every run of adjacent frames as a single copy (host = n * bytes_each contiguous
+ * bytes).  Frames from mxl_frame_alloc work too, one copy each. */
+MXL_API int mxl_frames_alloc_batch(mxl_ctx *ctx, uint32_t width, uint32_t height, uint32_t n, mxl_frame **frames_out);
+MXL_API int mxl_frames_upload_raw_async(mxl_frame *const *frames, uint32_t n, const uint8_t *host, uint64_t bytes_each);
+MXL_API int mxl_frames_download_raw_async(mxl_frame *const *frames, uint32_t n, uint8_t *host, uint64_t bytes_each);
 MXL_API int mxl_frame_download_raw_async(const mxl_frame *frame, uint8_t *host, uint64_t size);
 
 /* Video line = Output::Video(Option<VideoFrame>) per tick (io.rs:8-17,64-69): `ticks` slots. */

@@ -174,6 +174,9 @@ def lib():
         "mxl_frame_download_raw": (i32, [vp, vp, u64]),
         "mxl_frame_upload_raw_async": (i32, [vp, vp, u64]),
         "mxl_frame_download_raw_async": (i32, [vp, vp, u64]),
+        "mxl_frames_alloc_batch": (i32, [vp, u32, u32, u32, C.POINTER(vp)]),
+        "mxl_frames_upload_raw_async": (i32, [C.POINTER(vp), u32, vp, u64]),
+        "mxl_frames_download_raw_async": (i32, [C.POINTER(vp), u32, vp, u64]),
         "mxl_video_line_alloc": (vp, [vp, u32]),
         "mxl_video_line_set": (i32, [vp, u32, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
         "mxl_video_line_get": (vp, [vp, u32]),
@@ -412,6 +415,12 @@ class Context:
         buf = (KernelTime * 64)()
         n = check(lib().mxl_ctx_kernel_times(self.h, buf, 64))
         return {buf[i].name.decode(): (buf[i].launches, buf[i].total_ms) for i in range(n)}
+
+    def frames_batch(self, width, height, n):
+        """n frames adjacent in one device allocation (mxl_frames_alloc_batch)."""
+        out = (C.c_void_p * n)()
+        check(lib().mxl_frames_alloc_batch(self.h, width, height, n, out))
+        return [Frame(self, handle=out[i]) for i in range(n)]
 
     def rgba(self, width, height, n_pictures):
         return RgbaPictures(self, width, height, n_pictures)

@@ -116,8 +116,16 @@ struct mxl_ctx {
     int activate() const;            // cudaSetDevice
 };
 
+// One device allocation shared by a batch of frames (mxl_frames_alloc_batch): consecutive frames are
+// adjacent in memory, so a whole batch moves over PCIe as one copy.  Freed with its last frame.
+struct FrameSlab {
+    uint8_t* base = nullptr;
+    std::atomic<int> refs{0};
+};
+
 struct mxl_frame {
     mxl_ctx* ctx = nullptr;
+    FrameSlab* slab = nullptr;        // non-null: `dev` points into a slab and never enters the frame pool
     mxl_frame_layout layout{};
     uint8_t* dev = nullptr;
     std::atomic<int> refs{1};

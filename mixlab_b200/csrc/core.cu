@@ -181,7 +181,15 @@ void frame_release(mxl_frame* f)
 {
     if (!f) return;
     if (f->refs.fetch_sub(1) == 1) {
-        if (f->dev) f->ctx->frame_pool[f->layout.size].push_back(f->dev);
+        if (f->slab) {
+            if (f->slab->refs.fetch_sub(1) == 1) {
+                f->ctx->activate();
+                cudaFree(f->slab->base);      // synchronises with whatever still reads the slab
+                delete f->slab;
+            }
+        } else if (f->dev) {
+            f->ctx->frame_pool[f->layout.size].push_back(f->dev);
+        }
         delete f;
     }
 }
@@ -687,6 +695,71 @@ int mxl_frame_download_raw_async(const mxl_frame* frame, uint8_t* host, uint64_t
     MXL_CUDA(cudaMemcpyAsync(host, frame->dev, size, cudaMemcpyDeviceToHost, st));
     frame->ctx->d2h_bytes += size;
     return MXL_OK;
+}
+
+int mxl_frames_alloc_batch(mxl_ctx* ctx, uint32_t width, uint32_t height, uint32_t n, mxl_frame** frames_out)
+{
+    if (!ctx || (n && !frames_out)) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
+    if (!ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "mxl_frames_alloc_batch: context has no CUDA device");
+    if (width == 0 || height == 0) MXL_FAIL(MXL_ERR_INVALID, "empty picture %ux%u", width, height);
+    if (n == 0) return MXL_OK;
+    MXL_TRY(ctx->activate());
+    mxl_frame_layout lay;
+    frame_layout_yuv420p(width, height, &lay);
+    const uint64_t pitch = (lay.size + 255) & ~(uint64_t)255;     // frames stay 256-byte aligned; 1080p: pitch == size
+    FrameSlab* slab = new FrameSlab();
+    cudaError_t e = cudaMalloc(&slab->base, pitch * n);
+    if (e != cudaSuccess) {
+        delete slab;
+        MXL_FAIL(MXL_ERR_OOM, "cudaMalloc(%llu) failed: %s", (unsigned long long)(pitch * n), cudaGetErrorString(e));
+    }
+    slab->refs = (int)n;
+    for (uint32_t i = 0; i < n; i++) {
+        mxl_frame* f = new mxl_frame();
+        f->ctx = ctx;
+        f->layout = lay;
+        f->slab = slab;
+        f->dev = slab->base + pitch * i;
+        frames_out[i] = f;
+    }
+    return MXL_OK;
+}
+
+// One cudaMemcpyAsync per run of frames that are adjacent on the device (and, by construction, in `host`).
+static int frames_copy_raw(mxl_frame* const* frames, uint32_t n, uint8_t* host, uint64_t bytes_each, bool upload)
+{
+    if (n == 0) return MXL_OK;
+    if (!frames || !host) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
+    mxl_ctx* ctx = frames[0] ? frames[0]->ctx : nullptr;
+    for (uint32_t i = 0; i < n; i++) {
+        if (!frames[i] || frames[i]->ctx != ctx) MXL_FAIL(MXL_ERR_INVALID, "frame %u is NULL or of another context", i);
+        if (frames[i]->layout.size != bytes_each)
+            MXL_FAIL(MXL_ERR_LENGTH, "raw size %llu != size %llu of frame %u", (unsigned long long)bytes_each, (unsigned long long)frames[i]->layout.size, i);
+    }
+    MXL_TRY(ctx->activate());
+    cudaStream_t st;
+    MXL_TRY(upload ? ctx->upload_stream(&st) : ctx->download_stream(&st));
+    uint32_t i = 0;
+    while (i < n) {
+        uint32_t j = i + 1;
+        while (j < n && frames[j]->dev == frames[j - 1]->dev + bytes_each) j++;
+        const uint64_t bytes = (uint64_t)(j - i) * bytes_each;
+        if (upload) MXL_CUDA(cudaMemcpyAsync(frames[i]->dev, host + (uint64_t)i * bytes_each, bytes, cudaMemcpyHostToDevice, st));
+        else MXL_CUDA(cudaMemcpyAsync(host + (uint64_t)i * bytes_each, frames[i]->dev, bytes, cudaMemcpyDeviceToHost, st));
+        i = j;
+    }
+    (upload ? ctx->h2d_bytes : ctx->d2h_bytes) += (uint64_t)n * bytes_each;
+    return MXL_OK;
+}
+
+int mxl_frames_upload_raw_async(mxl_frame* const* frames, uint32_t n, const uint8_t* host, uint64_t bytes_each)
+{
+    return frames_copy_raw(frames, n, const_cast<uint8_t*>(host), bytes_each, true);
+}
+
+int mxl_frames_download_raw_async(mxl_frame* const* frames, uint32_t n, uint8_t* host, uint64_t bytes_each)
+{
+    return frames_copy_raw(frames, n, host, bytes_each, false);
 }
 
 int mxl_frame_upload_raw(mxl_frame* frame, const uint8_t* host, uint64_t size)

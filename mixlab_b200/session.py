@@ -58,8 +58,11 @@ class AVSession:
             g.connect(self.vmix, 0, self.src_a, 0)
             g.connect(self.vmix, 1, self.src_b, 0)
             # T device frames per layer, presented as the sources' video lines (one slot per tick)
-            self.frames_a = [ctx.frame(width, height) for _ in range(self.T)]
-            self.frames_b = [ctx.frame(width, height) for _ in range(self.T)]
+            # the T frames of a layer are adjacent on the device: a step's layer goes up as one copy
+            self.frames_a = ctx.frames_batch(width, height, self.T)
+            self.frames_b = ctx.frames_batch(width, height, self.T)
+            self._fa = (C.c_void_p * self.T)(*[f.h for f in self.frames_a])
+            self._fb = (C.c_void_p * self.T)(*[f.h for f in self.frames_b])
             self.line_a, self.line_b = ctx.video_line(self.T), ctx.video_line(self.T)
             rate = (ctx.spt, ctx.sample_rate)
             for k in range(self.T):
@@ -114,10 +117,8 @@ class AVSession:
         if not self.video:
             return
         L, fb = self._L, self.frame_bytes
-        pa, pb = self.host_a.ptr, self.host_b.ptr
-        for k in range(self.T):
-            api.check(L.mxl_frame_upload_raw_async(self.frames_a[k].h, pa + k * fb, fb))
-            api.check(L.mxl_frame_upload_raw_async(self.frames_b[k].h, pb + k * fb, fb))
+        api.check(L.mxl_frames_upload_raw_async(self._fa, self.T, self.host_a.ptr, fb))
+        api.check(L.mxl_frames_upload_raw_async(self._fb, self.T, self.host_b.ptr, fb))
 
     def run_step(self, tick0):
         """Device-resident step: T ticks of the whole graph, asynchronous on the context stream."""
@@ -127,11 +128,7 @@ class AVSession:
         """What the reference's sinks read each tick, to pinned host memory; synchronises."""
         L, fb = self._L, self.frame_bytes
         if self.video:
-            out = L.mxl_graph_output(self.graph.h, self.vmix, 0)
-            po = self.host_out.ptr
-            for k in range(self.T):
-                fr = L.mxl_video_line_get(out, k)
-                api.check(L.mxl_frame_download_raw_async(fr, po + k * fb, fb))
+            api.check(L.mxl_frames_download_raw_async(self._out_frames(), self.T, self.host_out.ptr, fb))
         if self.master is not None:
             line = L.mxl_graph_output(self.graph.h, self.ids[self.master[0]], self.master[1])
             api.check(L.mxl_line_download_async(line, self.host_master.ptr, self.T * self.ctx.spt * 2))
@@ -165,17 +162,22 @@ class AVSession:
         self.upload_inputs()
         self.run_step(tick0)
         if self.video:
-            out = L.mxl_graph_output(self.graph.h, self.vmix, 0)
-            po = self._out[slot].ptr
-            for k in range(self.T):
-                fr = L.mxl_video_line_get(out, k)
-                api.check(L.mxl_frame_download_raw_async(fr, po + k * fb, fb))
+            api.check(L.mxl_frames_download_raw_async(self._out_frames(), self.T, self._out[slot].ptr, fb))
         if self.master is not None:
             line = L.mxl_graph_output(self.graph.h, self.ids[self.master[0]], self.master[1])
             api.check(L.mxl_line_download_async(line, self._master[slot].ptr, self.T * self.ctx.spt * 2))
         if self.meter is not None:
             api.check(L.mxl_meter_download_async(self.graph.module(self.ids[self.meter[0]]).h, self._meter[slot].ptr, self.T))
         self.ctx.download_fence(slot)
+
+    def _out_frames(self):
+        """Handles of this step's composited frames (the VideoMixer output line's slots)."""
+        L = self._L
+        out = L.mxl_graph_output(self.graph.h, self.vmix, 0)
+        arr = (C.c_void_p * self.T)()
+        for k in range(self.T):
+            arr[k] = L.mxl_video_line_get(out, k)
+        return arr
 
     def wait_step(self, slot):
         self.ctx.wait_fence(slot)

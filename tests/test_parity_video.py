@@ -242,6 +242,44 @@ def test_compose_rgba_equals_crossfade_then_convert(mxl, oracle, ctx48, size):
     pics.free()
 
 
+def test_frame_batch_moves_as_one_copy(mxl, oracle, ctx48):
+    """mxl_frames_alloc_batch: adjacent frames, uploaded / downloaded as one copy per run, usable like any frame,
+    freed with the last of them whatever the release order."""
+    import ctypes as C
+    w, h, n = 1920, 1080, 6
+    lay = oracle.frame_layout(w, h)
+    frames = ctx48.frames_batch(w, h, n)
+    ptrs = [mxl.lib().mxl_frame_device_ptr(f.h) for f in frames]
+    assert all(ptrs[i + 1] - ptrs[i] == lay.size for i in range(n - 1))
+    host = mxl.PinnedBuffer(n * lay.size)
+    host.array[:] = W.random_bytes(1234, n * lay.size)
+    arr = (C.c_void_p * n)(*[f.h for f in frames])
+    before = ctx48.h2d_bytes
+    mxl.check(mxl.lib().mxl_frames_upload_raw_async(arr, n, host.ptr, lay.size))
+    ctx48.synchronize()
+    assert ctx48.h2d_bytes - before == n * lay.size
+    for k, f in enumerate(frames):
+        assert np.array_equal(f.download_raw(), host.array[k * lay.size:(k + 1) * lay.size]), k
+    # a mixed list (batch frames interleaved with a pool frame) still lands frame by frame
+    other = ctx48.frame(w, h, blank=True)
+    mixed = [frames[3], other, frames[0], frames[1]]
+    marr = (C.c_void_p * 4)(*[f.h for f in mixed])
+    back = mxl.PinnedBuffer(4 * lay.size)
+    mxl.check(mxl.lib().mxl_frames_download_raw_async(marr, 4, back.ptr, lay.size))
+    ctx48.synchronize()
+    got = back.array.reshape(4, lay.size)
+    assert np.array_equal(got[0], frames[3].download_raw()) and np.array_equal(got[1], oracle.frame_blank(lay))
+    assert np.array_equal(got[2], frames[0].download_raw()) and np.array_equal(got[3], frames[1].download_raw())
+    # the mixer takes them like any frame
+    mod, outs = run_mixer(mxl, ctx48, (0, 1, 0.5), {0: frames[:3], 1: frames[3:]}, ticks=3)
+    for k in range(3):
+        want = oracle.video_crossfade(lay, host.array[k * lay.size:(k + 1) * lay.size], host.array[(k + 3) * lay.size:(k + 4) * lay.size], 127)
+        assert np.array_equal(outs[0].get(k).download_raw(), want), k
+    for f in (frames[2], frames[5], frames[0], frames[4], frames[1], frames[3], other):
+        f.release()
+    host.free(); back.free()
+
+
 def test_yuv_to_rgba_self_specified(mxl, oracle, ctx48):
     # UNPINNED: the reference never converts colour (video_mixer.rs:282-283); spec = oracle header
     for (w, h) in [(1920, 1080), (70, 50), (34, 18)]:
