@@ -282,6 +282,11 @@ MXL_API int mxl_pcm_sink_download(mxl_module *m, int16_t *host, uint64_t n_sampl
  * i16 -> f32 `sample / 32768.0` (stream_input.rs:167-173) and the pack above. */
 MXL_API int mxl_pcm_unpack_i16(mxl_ctx *ctx, const int16_t *host_pcm, uint64_t n_samples, mxl_line *dst);
 MXL_API int mxl_pcm_pack_i16(mxl_ctx *ctx, const mxl_line *src, int16_t *host_pcm, uint64_t n_samples);
+/* The same without allocation or synchronisation per call (device staging is a ring owned by the context):
+ * host_pcm should be pinned (mxl_host_alloc) and stay valid until the context has been synchronised or a
+ * download fence has passed.  With copy overlap enabled the bus transfer runs on the copy streams. */
+MXL_API int mxl_pcm_unpack_i16_async(mxl_ctx *ctx, const int16_t *host_pcm, uint64_t n_samples, mxl_line *dst);
+MXL_API int mxl_pcm_pack_i16_async(mxl_ctx *ctx, const mxl_line *src, int16_t *host_pcm, uint64_t n_samples);
 
 /* yuv420p -> RGBA8 of a frame (self-specified BT.601 integer form; the reference
  * never converts colour, video_mixer.rs:282-283).  rgba_host receives width*height*4 bytes. */

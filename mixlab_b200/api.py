@@ -204,6 +204,8 @@ def lib():
         "mxl_pcm_sink_download": (i32, [vp, vp, u64]),
         "mxl_pcm_unpack_i16": (i32, [vp, vp, u64, vp]),
         "mxl_pcm_pack_i16": (i32, [vp, vp, vp, u64]),
+        "mxl_pcm_unpack_i16_async": (i32, [vp, vp, u64, vp]),
+        "mxl_pcm_pack_i16_async": (i32, [vp, vp, vp, u64]),
         "mxl_frame_to_rgba": (i32, [vp, vp]),
         "mxl_frame_scale": (vp, [vp, u32, u32]),
         "mxl_frames_scale": (i32, [vp, C.POINTER(vp), C.POINTER(vp), u32, u32, u32]),

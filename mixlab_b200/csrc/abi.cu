@@ -2,6 +2,8 @@
 // DynModuleHostT (src/engine/module.rs:88-119), plus the stand-alone converters.
 #include <math.h>
 
+#include <algorithm>
+
 #include "modules.h"
 
 using namespace mxl;
@@ -117,8 +119,31 @@ int mxl_plotter_read(mxl_module* m, float* left, float* right, uint32_t cap_fram
 int mxl_source_set_line(mxl_module* m, mxl_line* line) { return source_set_line(m, line); }
 int mxl_pcm_sink_download(mxl_module* m, int16_t* host, uint64_t n_samples) { return pcm_sink_download(m, host, n_samples); }
 
+// Device staging for i16 PCM on its way in or out: a ring owned by the context, so the asynchronous
+// converters neither allocate nor synchronise per call.  A region is reused only after a wrap, which
+// first waits for everything queued on the context.
+static int pcm_staging(mxl_ctx* ctx, uint64_t n_samples, int16_t** out)
+{
+    const size_t need = ((size_t)n_samples * sizeof(int16_t) + 255) & ~(size_t)255;
+    if (ctx->pcm_ring_cap < 2 * need || ctx->pcm_ring_used + need > ctx->pcm_ring_cap) {
+        MXL_TRY(mxl_ctx_synchronize(ctx));
+        if (ctx->pcm_ring_cap < 2 * need) {
+            if (ctx->pcm_ring) cudaFree(ctx->pcm_ring);
+            ctx->pcm_ring = nullptr;
+            ctx->pcm_ring_cap = 0;
+            const size_t cap = std::max<size_t>(1 << 20, 4 * need);
+            MXL_CUDA(cudaMalloc(&ctx->pcm_ring, cap));
+            ctx->pcm_ring_cap = cap;
+        }
+        ctx->pcm_ring_used = 0;
+    }
+    *out = (int16_t*)((uint8_t*)ctx->pcm_ring + ctx->pcm_ring_used);
+    ctx->pcm_ring_used += need;
+    return MXL_OK;
+}
+
 // stream_input.rs:110-112,167-173: the i16 PCM crosses the bus (2 B/sample), the divide runs on the device
-int mxl_pcm_unpack_i16(mxl_ctx* ctx, const int16_t* host_pcm, uint64_t n_samples, mxl_line* dst)
+int mxl_pcm_unpack_i16_async(mxl_ctx* ctx, const int16_t* host_pcm, uint64_t n_samples, mxl_line* dst)
 {
     if (!ctx || !dst) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
     if (!ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "mxl_pcm_unpack_i16: context has no CUDA device; there is no CPU fallback");
@@ -127,16 +152,26 @@ int mxl_pcm_unpack_i16(mxl_ctx* ctx, const int16_t* host_pcm, uint64_t n_samples
     if (n_samples == 0) return MXL_OK;
     if (!host_pcm) MXL_FAIL(MXL_ERR_INVALID, "NULL pcm");
     MXL_TRY(ctx->activate());
-    Staging st;
-    MXL_CUDA(cudaMalloc(&st.p, n_samples * sizeof(int16_t)));
-    MXL_CUDA(cudaMemcpyAsync(st.p, host_pcm, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
-    MXL_TRY(k::launch_pcm_unpack(ctx, (const int16_t*)st.p, dst->dev, n_samples));
-    MXL_CUDA(cudaStreamSynchronize(ctx->stream));
-    return MXL_OK;
+    int16_t* staging;
+    MXL_TRY(pcm_staging(ctx, n_samples, &staging));
+    cudaStream_t up;
+    MXL_TRY(ctx->upload_stream(&up));
+    MXL_CUDA(cudaMemcpyAsync(staging, host_pcm, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, up));
+    ctx->h2d_bytes += n_samples * sizeof(int16_t);
+    MXL_TRY(ctx->compute_begin());
+    const int st = k::launch_pcm_unpack(ctx, staging, dst->dev, n_samples);
+    MXL_TRY(ctx->compute_end());
+    return st;
+}
+
+int mxl_pcm_unpack_i16(mxl_ctx* ctx, const int16_t* host_pcm, uint64_t n_samples, mxl_line* dst)
+{
+    MXL_TRY(mxl_pcm_unpack_i16_async(ctx, host_pcm, n_samples, dst));
+    return mxl_ctx_synchronize(ctx);
 }
 
 // src/video/encode.rs:184-195
-int mxl_pcm_pack_i16(mxl_ctx* ctx, const mxl_line* src, int16_t* host_pcm, uint64_t n_samples)
+int mxl_pcm_pack_i16_async(mxl_ctx* ctx, const mxl_line* src, int16_t* host_pcm, uint64_t n_samples)
 {
     if (!ctx || !src) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
     if (!ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "mxl_pcm_pack_i16: context has no CUDA device; there is no CPU fallback");
@@ -145,12 +180,23 @@ int mxl_pcm_pack_i16(mxl_ctx* ctx, const mxl_line* src, int16_t* host_pcm, uint6
     if (n_samples == 0) return MXL_OK;
     if (!host_pcm) MXL_FAIL(MXL_ERR_INVALID, "NULL pcm");
     MXL_TRY(ctx->activate());
-    Staging st;
-    MXL_CUDA(cudaMalloc(&st.p, n_samples * sizeof(int16_t)));
-    MXL_TRY(k::launch_pcm_pack(ctx, src->dev, (int16_t*)st.p, n_samples));
-    MXL_CUDA(cudaMemcpyAsync(host_pcm, st.p, n_samples * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
-    MXL_CUDA(cudaStreamSynchronize(ctx->stream));
+    int16_t* staging;
+    MXL_TRY(pcm_staging(ctx, n_samples, &staging));
+    MXL_TRY(ctx->compute_begin());
+    const int st = k::launch_pcm_pack(ctx, src->dev, staging, n_samples);
+    MXL_TRY(ctx->compute_end());
+    MXL_TRY(st);
+    cudaStream_t down;
+    MXL_TRY(ctx->download_stream(&down));
+    MXL_CUDA(cudaMemcpyAsync(host_pcm, staging, n_samples * sizeof(int16_t), cudaMemcpyDeviceToHost, down));
+    ctx->d2h_bytes += n_samples * sizeof(int16_t);
     return MXL_OK;
+}
+
+int mxl_pcm_pack_i16(mxl_ctx* ctx, const mxl_line* src, int16_t* host_pcm, uint64_t n_samples)
+{
+    MXL_TRY(mxl_pcm_pack_i16_async(ctx, src, host_pcm, n_samples));
+    return mxl_ctx_synchronize(ctx);
 }
 
 int mxl_frame_to_rgba(const mxl_frame* frame, uint8_t* rgba_host)

@@ -81,6 +81,8 @@ struct mxl_ctx {
     std::map<uint64_t, std::vector<int32_t>> scale_positions;   // host copies of the first-tap columns (tile bounds)
     void* scale_jobs = nullptr;       // device staging for ScaleJob arrays
     size_t scale_jobs_cap = 0, scale_jobs_used = 0;   // bytes; tables rotate through the buffer
+    void* pcm_ring = nullptr;         // device staging ring of the asynchronous i16 converters (abi.cu)
+    size_t pcm_ring_cap = 0, pcm_ring_used = 0;
     void* comm = nullptr;             // ncclComm_t of the optional shared-source mode (comm.cu)
     int comm_rank = 0, comm_world = 0;
     bool kernel_timing = false;

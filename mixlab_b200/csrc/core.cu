@@ -373,6 +373,7 @@ int mxl_ctx_destroy(mxl_ctx* ctx)
         for (auto& kv : ctx->eq_stream_tables) if (kv.second) cudaFree(kv.second);
         for (auto& kv : ctx->scale_tables) if (kv.second) cudaFree(kv.second);
         if (ctx->scale_jobs) cudaFree(ctx->scale_jobs);
+        if (ctx->pcm_ring) cudaFree(ctx->pcm_ring);
         for (auto& kv : ctx->frame_pool)
             for (uint8_t* p : kv.second) cudaFree(p);
         if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);

@@ -364,6 +364,29 @@ def test_envelope_long_call_many_tiles(mxl, oracle, ctx48, kind):
     assert bits_equal(out.download(), want2)
 
 
+def test_pcm_async_ring_many_calls(mxl, oracle, ctx48):
+    """N2/N3 hand-off without per-call allocation: 40 blocks of i16 PCM in, Amplifier, i16 PCM out, all queued
+    before one synchronise; 5 MB pass through the 1 MB staging ring, which wraps several times
+    (encode.rs:184-195, stream_input.rs:167-173)."""
+    spt, ticks = 16384, 40
+    n = 2 * spt
+    pin_in = mxl.PinnedBuffer(ticks * n * 2, np.int16)
+    pin_out = mxl.PinnedBuffer(ticks * n * 2, np.int16)
+    pcm = (W.splitmix64(11, ticks * n) & np.uint64(0xFFFF)).astype(np.uint16).view(np.int16)
+    pin_in.array[:] = pcm
+    amp = ctx48.module(mxl.MOD_AMPLIFIER, (0.5, 0.0))
+    lines = [(ctx48.line(mxl.LINE_STEREO, spt), ctx48.line(mxl.LINE_STEREO, spt)) for _ in range(ticks)]
+    L = mxl.lib()
+    for k, (src, dst) in enumerate(lines):
+        mxl.check(L.mxl_pcm_unpack_i16_async(ctx48.h, pin_in.ptr + k * n * 2, n, src.h))
+        amp.run_tick(k * spt, [src, None], [dst])
+        mxl.check(L.mxl_pcm_pack_i16_async(ctx48.h, dst.h, pin_out.ptr + k * n * 2, n))
+    ctx48.synchronize()
+    want = oracle.pcm_pack_i16(oracle.amplifier(oracle.pcm_unpack_i16(pcm), None, 0.5, 0.0))
+    assert np.array_equal(pin_out.array, want)
+    pin_in.free(); pin_out.free()
+
+
 # ---- Meter / Plotter / PCM --------------------------------------------------------------------
 def test_meter(mxl, oracle, ctx48):
     spt, ticks = 800, 7
