@@ -151,10 +151,28 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
 }
 
+// Four taps in two instructions: weights as two s16 pairs, the four u8 samples in one word (dp2a.lo takes the
+// two low bytes, dp2a.hi the two high ones); then the two-pass definition's rounding and clip.
+__device__ __forceinline__ int pack_s16x2(short lo, short hi) { return (int)(((uint32_t)(uint16_t)hi << 16) | (uint16_t)lo); }
+__device__ __forceinline__ uint32_t tap4(uint32_t px, int c01, int c23)
+{
+    int acc;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(acc) : "r"(c01), "r"(px), "r"(8192));
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(acc) : "r"(c23), "r"(px), "r"(acc));
+    return (uint32_t)__vimin_s32_relu(acc >> 14, 255);
+}
+
 // first tap of output index d (the tables' pos[d]; modules.cu bicubic_table): floor(((2d+1) src - dst) / (2 dst)) - 1.
 // Recomputed here so that a tile can start staging its source rectangle without first waiting for a table load.
 __device__ __forceinline__ int first_tap(uint32_t d, uint32_t src_n, uint32_t dst_n)
 {
+    // planes up to 32767 pixels a side keep (2d+1)*src inside 31 bits: 32-bit division (the 64-bit one is a
+    // long dependent subroutine, and four of them stood between a CTA's start and its first staging request)
+    if ((src_n | dst_n) < 32768u) {
+        const int num = (int)((2u * d + 1u) * src_n) - (int)dst_n, den = (int)(2u * dst_n);
+        const int ix = num >= 0 ? num / den : -((-num + den - 1) / den);
+        return ix - 1;
+    }
     const long long num = (long long)(2ull * d + 1ull) * src_n - dst_n, den = 2ll * dst_n;
     const long long ix = num >= 0 ? num / den : -((-num + den - 1) / den);
     return (int)ix - 1;
@@ -167,10 +185,11 @@ __global__ void __launch_bounds__(kVidThreads) scale_tiled_kernel(const __grid_c
     __shared__ int s_xpos[kScaleTW], s_ypos[kScaleTH];
     __shared__ short4 s_xco[kScaleTW], s_yco[kScaleTH];
     const ScaleJob job = L.jobs[blockIdx.y];
-    int pi = 0;
-    if (blockIdx.x >= L.pl[1].tile_base) pi = 1;
-    if (blockIdx.x >= L.pl[2].tile_base) pi = 2;
-    const ScalePlane& P = L.pl[pi];
+    // the plane's geometry into registers through statically addressed parameter reads (a run-time index into
+    // the parameter block turns every field access into a slow indexed constant load)
+    ScalePlane P = L.pl[0];
+    if (blockIdx.x >= L.pl[2].tile_base) P = L.pl[2];
+    else if (blockIdx.x >= L.pl[1].tile_base) P = L.pl[1];
     const uint32_t t = blockIdx.x - P.tile_base;
     const uint32_t x0 = (t % P.tiles_x) * kScaleTW, y0 = (t / P.tiles_x) * kScaleTH;
     const uint32_t x1 = min(x0 + kScaleTW, P.dst_w) - 1, y1 = min(y0 + kScaleTH, P.dst_h) - 1;
@@ -185,8 +204,8 @@ __global__ void __launch_bounds__(kVidThreads) scale_tiled_kernel(const __grid_c
     uint8_t* region = sc_smem;                                   // [rows][pitch]
     uint8_t* mid = sc_smem + (size_t)L.region_rows * pitch;      // [rows][kScaleTW]
     const uint8_t* src = job.src + P.src_off;
-    for (int i = threadIdx.x; i < rows * chunks; i += kVidThreads) {
-        const int r = i / chunks, c = i - r * chunks;
+    for (uint32_t i = threadIdx.x; i < (uint32_t)(rows * chunks); i += kVidThreads) {
+        const uint32_t r = i / (uint32_t)chunks, c = i - r * (uint32_t)chunks;
         cp_async_16(region + r * pitch + c * 16, src + (size_t)(ry_lo + r) * P.src_stride + cx_lo + c * 16);
     }
     // the tile's slices of the tap tables, in flight together with the staging
@@ -201,15 +220,18 @@ __global__ void __launch_bounds__(kVidThreads) scale_tiled_kernel(const __grid_c
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    // horizontal pass: thread = 4 adjacent output columns of one staged row at a time; mid[r][x] packed 4 per store
+    // horizontal pass: thread = 4 adjacent output columns of one staged row at a time; the four taps of a pixel
+    // are gathered into one word and reduced by two dp2a (s16 weights x u8 pixels); mid[r][x] packed 4 per store
     {
         const int q = threadIdx.x % (kScaleTW / 4);               // column quad
         int off[4][4];
-        short4 cf[4];
+        int c01[4], c23[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int p0 = s_xpos[4 * q + j];
-            cf[j] = s_xco[4 * q + j];
+            const short4 cf = s_xco[4 * q + j];
+            c01[j] = pack_s16x2(cf.x, cf.y);
+            c23[j] = pack_s16x2(cf.z, cf.w);
 #pragma unroll
             for (int k = 0; k < 4; k++) off[j][k] = min(max(p0 + k, 0), sw - 1) - cx_lo;
         }
@@ -218,9 +240,9 @@ __global__ void __launch_bounds__(kVidThreads) scale_tiled_kernel(const __grid_c
             uint32_t packed = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int acc = cf[j].x * (int)row[off[j][0]] + cf[j].y * (int)row[off[j][1]] +
-                                cf[j].z * (int)row[off[j][2]] + cf[j].w * (int)row[off[j][3]];
-                packed |= clip8((acc + 8192) >> 14) << (8 * j);
+                const uint32_t px = (uint32_t)row[off[j][0]] | ((uint32_t)row[off[j][1]] << 8) |
+                                    ((uint32_t)row[off[j][2]] << 16) | ((uint32_t)row[off[j][3]] << 24);
+                packed |= tap4(px, c01[j], c23[j]) << (8 * j);
             }
             reinterpret_cast<uint32_t*>(mid + r * kScaleTW)[q] = packed;
         }
@@ -238,13 +260,14 @@ __global__ void __launch_bounds__(kVidThreads) scale_tiled_kernel(const __grid_c
             const int r2 = min(max(p0 + 2, 0), sh - 1) - ry_lo, r3 = min(max(p0 + 3, 0), sh - 1) - ry_lo;
             const uint32_t a0 = reinterpret_cast<const uint32_t*>(mid + r0 * kScaleTW)[q], a1 = reinterpret_cast<const uint32_t*>(mid + r1 * kScaleTW)[q];
             const uint32_t a2 = reinterpret_cast<const uint32_t*>(mid + r2 * kScaleTW)[q], a3 = reinterpret_cast<const uint32_t*>(mid + r3 * kScaleTW)[q];
-            uint32_t packed = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int acc = cf.x * (int)((a0 >> (8 * j)) & 0xFF) + cf.y * (int)((a1 >> (8 * j)) & 0xFF) +
-                                cf.z * (int)((a2 >> (8 * j)) & 0xFF) + cf.w * (int)((a3 >> (8 * j)) & 0xFF);
-                packed |= clip8((acc + 8192) >> 14) << (8 * j);
-            }
+            // transpose 4 rows x 4 pixels into 4 pixels x 4 taps with byte permutes, then two dp2a per pixel
+            const uint32_t lo01 = __byte_perm(a0, a1, 0x5140), hi01 = __byte_perm(a0, a1, 0x7362);   // (a0.b0,a1.b0,a0.b1,a1.b1), (.b2,.b3)
+            const uint32_t lo23 = __byte_perm(a2, a3, 0x5140), hi23 = __byte_perm(a2, a3, 0x7362);
+            const int c01 = pack_s16x2(cf.x, cf.y), c23 = pack_s16x2(cf.z, cf.w);
+            const uint32_t packed = tap4(__byte_perm(lo01, lo23, 0x5410), c01, c23) |
+                                    (tap4(__byte_perm(lo01, lo23, 0x7632), c01, c23) << 8) |
+                                    (tap4(__byte_perm(hi01, hi23, 0x5410), c01, c23) << 16) |
+                                    (tap4(__byte_perm(hi01, hi23, 0x7632), c01, c23) << 24);
             const uint32_t gx = x0 + 4 * q;
             uint8_t* o = dst + (size_t)(y0 + ly) * P.dst_stride + gx;
             if (word_ok && gx + 3 <= x1) {
