@@ -63,14 +63,22 @@ __global__ void __launch_bounds__(kThreads) oscillator_kernel(const __grid_const
         const double q0 = (double)(b.t0 + f0);
         const bool exact = (b.t0 + f0 + 3) < (1ull << 53);
         double n[4];
-        n[0] = osc_phase(q0, sr, inv_sr, freq);
+        if (exact) {                                   // one well-predicted branch: no conversions on this side
 #pragma unroll
-        for (int j = 1; j < 4; j++) n[j] = osc_phase(exact ? q0 + (double)j : (double)(b.t0 + f0 + j), sr, inv_sr, freq);
+            for (int j = 0; j < 4; j++) n[j] = osc_phase(q0 + (double)j, sr, inv_sr, freq);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) n[j] = osc_phase((double)(b.t0 + f0 + j), sr, inv_sr, freq);
+        }
         float s[4];
         // the waveform is the same for every sample of an instance: branch once, not per sample
-        if (wf == MXL_WAVE_SINE) {
+        if (wf == MXL_WAVE_SINE || wf == MXL_WAVE_SQUARE) {
+            double x[4], y[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) s[j] = (float)wave_sine(n[j]);
+            for (int j = 0; j < 4; j++) x[j] = n[j] * kTwoPi;          // oscillator.rs:25-27
+            sin_f64x4(x, y);
+#pragma unroll
+            for (int j = 0; j < 4; j++) s[j] = (float)(wf == MXL_WAVE_SINE ? y[j] : sign_bit_f64(y[j]));
         } else if (wf == MXL_WAVE_SAW) {
 #pragma unroll
             for (int j = 0; j < 4; j++) s[j] = (float)wave_saw(n[j]);
@@ -111,10 +119,23 @@ __global__ void __launch_bounds__(kThreads) fm_sine_kernel(const __grid_constant
         float4 x = in.in ? ldg_stream(in.in + f0) : make_float4(0.f, 0.f, 0.f, 0.f);
         const double q0 = (double)(b.t0 + f0);
         const bool exact = (b.t0 + f0 + 3) < (1ull << 53);
-        float s0 = fm_sample(q0, b.sample_rate, b.inv_sample_rate, in.freq_mid, in.freq_amp, x.x);
-        float s1 = fm_sample(exact ? q0 + 1.0 : (double)(b.t0 + f0 + 1), b.sample_rate, b.inv_sample_rate, in.freq_mid, in.freq_amp, x.y);
-        float s2 = fm_sample(exact ? q0 + 2.0 : (double)(b.t0 + f0 + 2), b.sample_rate, b.inv_sample_rate, in.freq_mid, in.freq_amp, x.z);
-        float s3 = fm_sample(exact ? q0 + 3.0 : (double)(b.t0 + f0 + 3), b.sample_rate, b.inv_sample_rate, in.freq_mid, in.freq_amp, x.w);
+        const float xs[4] = {x.x, x.y, x.z, x.w};
+        double seq[4], arg[4], y[4];
+        if (exact) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) seq[j] = q0 + (double)j;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) seq[j] = (double)(b.t0 + f0 + j);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {                                  // fm_sine.rs:45-47
+            const double t = div_by_const(seq[j], b.sample_rate, b.inv_sample_rate);
+            const double co = (in.freq_mid + in.freq_amp * (double)xs[j]) * kTwoPi;
+            arg[j] = co * t;
+        }
+        sin_f64x4(arg, y);
+        const float s0 = (float)y[0], s1 = (float)y[1], s2 = (float)y[2], s3 = (float)y[3];
         st4(in.out + 2 * f0, make_float4(s0, s0, s1, s1));
         st4(in.out + 2 * f0 + 4, make_float4(s2, s2, s3, s3));
     } else {

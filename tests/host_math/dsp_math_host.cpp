@@ -4,6 +4,12 @@
 
 extern "C" {
 void mxl_host_sin(const double* x, double* y, size_t n) { for (size_t i = 0; i < n; i++) y[i] = mxl::sin_f64(x[i]); }
+void mxl_host_sin4(const double* x, double* y, size_t n)
+{
+    size_t i = 0;
+    for (; i + 4 <= n; i += 4) mxl::sin_f64x4(x + i, y + i);
+    for (; i < n; i++) y[i] = mxl::sin_f64(x[i]);
+}
 void mxl_host_libm_sin(const double* x, double* y, size_t n) { for (size_t i = 0; i < n; i++) y[i] = sin(x[i]); }
 void mxl_host_div(const double* a, double b, double* q, size_t n)
 {

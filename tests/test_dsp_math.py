@@ -53,6 +53,18 @@ def test_sine_random_arguments(hm):
     assert np.array_equal(np.signbit(got), np.signbit(want))
 
 
+def test_four_wide_sine_equals_scalar_sine(hm):
+    """sin_f64x4 (what the oscillator kernels call) is the scalar routine step for step, incl. the groups that
+    fall back because one member is +-0, huge, inf or NaN."""
+    rng = np.random.default_rng(8)
+    x = np.concatenate([rng.uniform(-1e7, 1e7, 40000), np.array([0.0, 1.0, 2.0, 3.0, -0.0, 5.0, 1e300, 7.0, np.inf, 1.0, np.nan, 2.0])])
+    a, b = np.empty_like(x), np.empty_like(x)
+    hm.mxl_host_sin(x.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_void_p), C.c_size_t(x.size))
+    hm.mxl_host_sin4(x.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), C.c_size_t(x.size))
+    assert np.array_equal(a.view(np.uint64)[~np.isnan(a)], b.view(np.uint64)[~np.isnan(b)])
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+
+
 def test_division_by_sample_rate_is_correctly_rounded(hm):
     rng = np.random.default_rng(4)
     for sr in (48000.0, 44100.0, 96000.0, 22050.0):
