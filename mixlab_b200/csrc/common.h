@@ -75,7 +75,7 @@ struct mxl_ctx {
     // eq_stream_kernel plans by chunk length (eq_plan.h); ok == false = unusable at this sample rate
     std::map<uint32_t, mxl::EqStreamPlan> eq_stream_plans;
     uint32_t eq_stream_smem_set = 0;  // bit LC/16: opt-in shared memory size configured
-    uint32_t scale_smem[3] = {0, 0, 0};   // dynamic shared memory the scale_tiled_kernel variants have been configured for
+    uint32_t scale_smem[4] = {0, 0, 0, 0};   // dynamic shared memory the scale_tiled_kernel variants have been configured for
     // scaler tap tables by (source length, destination length): device [pos int32 x n][coef int16 x 4n]
     std::map<uint64_t, void*> scale_tables;
     std::map<uint64_t, std::vector<int32_t>> scale_positions;   // host copies of the first-tap columns (tile bounds)

@@ -167,11 +167,11 @@ struct ScaleLaunch {
     ScalePlane pl[3];
     uint32_t total_tiles;
     uint32_t region_pitch, region_rows;                           // staging bounds over all tiles (pitch % 16 == 0)
-    uint32_t tile_h;                                              // output rows per tile: 32, 8 or 2
+    uint32_t tile_h;                                              // output rows per tile: 64, 32, 8 or 2
     const ScaleJob* jobs;                                         // device
 };
 int launch_scale_tiled(mxl_ctx* ctx, const ScaleLaunch& L, uint32_t n_jobs);
-constexpr size_t kScaleMaxSmem = 160 * 1024;                      // per CTA; beyond it a shorter tile is used
+constexpr size_t kScaleMaxSmem = 200 * 1024;                      // per CTA; beyond it a shorter tile is used
 size_t scale_smem_bytes(uint32_t region_rows, uint32_t region_pitch);
 uint32_t scale_tile_width();
 

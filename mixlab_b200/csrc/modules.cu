@@ -1009,8 +1009,9 @@ int scale_run(mxl_ctx* ctx, const mxl_frame_layout& sl, uint32_t out_w, uint32_t
     k::ScaleLaunch L{};
     const uint32_t tw = k::scale_tile_width();
     auto clampi = [](int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); };
-    // tallest tile whose staged source rectangle fits: 32 output rows, or 8 / 2 for strong down-scales
-    for (uint32_t th : {32u, 8u, 2u}) {
+    // tallest tile whose staged source rectangle fits comfortably (several CTAs per SM): 64 output rows, else
+    // 32, or 8 / 2 for strong down-scales
+    for (uint32_t th : {64u, 32u, 8u, 2u}) {
         uint32_t tile_base = 0, max_span = 16, max_rows = 1;
         for (int p = 0; p < 3; p++) {
             // subframe addressing (codec/src/ffmpeg/frame.rs:219-281): offsets are chroma-aligned already
@@ -1047,7 +1048,7 @@ int scale_run(mxl_ctx* ctx, const mxl_frame_layout& sl, uint32_t out_w, uint32_t
         L.region_pitch = max_span;
         L.region_rows = max_rows;
         L.tile_h = th;
-        if (k::scale_smem_bytes(max_rows, max_span) <= k::kScaleMaxSmem) break;
+        if (k::scale_smem_bytes(max_rows, max_span) <= (th == 64 ? 72u * 1024u : k::kScaleMaxSmem)) break;
     }
     // job tables rotate through a ring: a table must stay intact until the launch that reads it has run,
     // and several batches may be queued before the stream gets to the first

@@ -133,7 +133,7 @@ __device__ __forceinline__ uint32_t yuv_px_terms(uint32_t y, const ChromaTerms& 
 // ------------------------------------------------------------------------------------------------
 // Tiled letterbox scaler (DynamicScaler::scale, src/video/encode.rs:338-397; the arithmetic is this
 // repository's stand-in for swscale's SWS_BICUBIC -- DESIGN.md "unpinned"): all three planes of a
-// batch of frames in ONE launch.  A CTA owns a 64x32 tile of output pixels of one plane (64x8 or 64x2 when a
+// batch of frames in ONE launch.  A CTA owns a 128x64 tile of output pixels of one plane (128x32, 128x8 or 128x2 when a
 // strong down-scale would make the source rectangle of a taller tile outgrow shared memory):
 //   1. the source rectangle the tile's taps touch is staged global -> shared with 16-byte cp.async
 //      (rows and columns clamped the way the taps clamp, so edges need no special case);
@@ -143,7 +143,7 @@ __device__ __forceinline__ uint32_t yuv_px_terms(uint32_t y, const ChromaTerms& 
 // Every source byte is read from HBM once per tile that needs it (neighbouring tiles share a 3-pixel
 // apron through L2); the intermediate never leaves the SM.
 // ------------------------------------------------------------------------------------------------
-constexpr int kScaleTW = 64;      // tile width; the tile height is a template parameter (32, 8 or 2 output rows)
+constexpr int kScaleTW = 128;     // tile width; the tile height is a template parameter (64, 32, 8 or 2 output rows)
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src)
 {
@@ -418,7 +418,7 @@ int launch_blank(mxl_ctx* ctx, const mxl_frame_layout& lay, uint8_t* frame)
 template <int TH>
 static int launch_scale_th(mxl_ctx* ctx, const ScaleLaunch& L, uint32_t n_jobs, size_t smem)
 {
-    uint32_t& configured = ctx->scale_smem[TH == 32 ? 0 : (TH == 8 ? 1 : 2)];
+    uint32_t& configured = ctx->scale_smem[TH == 64 ? 3 : (TH == 32 ? 0 : (TH == 8 ? 1 : 2))];
     if (smem > 48 * 1024 && smem > configured) {
         MXL_CUDA(cudaFuncSetAttribute(scale_tiled_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = (uint32_t)smem;
@@ -439,6 +439,7 @@ int launch_scale_tiled(mxl_ctx* ctx, const ScaleLaunch& L, uint32_t n_jobs)
     const size_t smem = scale_smem_bytes(L.region_rows, L.region_pitch);
     if (smem > kScaleMaxSmem) MXL_FAIL(MXL_ERR_INVALID, "scale_tiled_kernel: source rectangle of a tile needs %zu bytes of shared memory", smem);
     switch (L.tile_h) {
+    case 64: return launch_scale_th<64>(ctx, L, n_jobs, smem);
     case 32: return launch_scale_th<32>(ctx, L, n_jobs, smem);
     case 8: return launch_scale_th<8>(ctx, L, n_jobs, smem);
     case 2: return launch_scale_th<2>(ctx, L, n_jobs, smem);
