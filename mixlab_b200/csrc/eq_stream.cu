@@ -22,6 +22,13 @@
 // communicate and the whole module is a single launch.  The chunk that starts the call runs from the
 // module's stored state, exactly, so successive calls continue bit-exactly.
 //
+// Non-finite samples: in the reference a NaN or an infinity entering the poles stays there for ever (every
+// later output is NaN, in this call and the next).  The carry above forgets by construction, so it would let
+// chunks further than `halo` behind such a sample recover.  Every thread therefore checks its zero-pass
+// vector; the first chunk with a non-finite carry is recorded (atomicMin), and the CTA of an instance that
+// finishes last rewrites everything after that chunk as NaN, poles included -- inside the chunk itself the
+// exact pass already did the right thing sample by sample.  Cost when nothing is wrong: one atomic per CTA.
+//
 // Roofline: 8 B/sample of line traffic against ~47 FP64 operations per sample (34 exact + 8 zero
 // pass + ~4 scan + halo): at the measured 64 FP64 lanes/clk/SM (tools/pipe_rates.cu) the FP64 pipe
 // allows 0.40 of the HBM copy peak, so this kernel is FP64-issue-bound, not HBM-bound.
@@ -145,6 +152,14 @@ __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ E
 #pragma unroll
             for (int e = 0; e < 4; e++) { v[e] += yl[e]; v[4 + e] += yh[e]; }
         }
+    }
+
+    // a non-finite carry (NaN / inf input in my chunk, or a non-finite stored state): remember the first such chunk
+    if (active) {
+        uint32_t bad = 0;
+#pragma unroll
+        for (int e = 0; e < 8; e++) bad |= ((uint32_t)__double2hiint(v[e]) & 0x7ff00000u) == 0x7ff00000u ? 1u : 0u;
+        if (bad) atomicMin(in.poison, (uint32_t)c);
     }
 
     // ---- 3. scan.  Inside a warp: Hillis-Steele with shuffles, v_i += A^(2^d) v_(i - 2^d), only the
@@ -298,6 +313,34 @@ __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ E
                 if (g + 1 < b.frames) dst[g + 1] = y.y;
                 if (g + 2 < b.frames) dst[g + 2] = y.z;
                 if (g + 3 < b.frames) dst[g + 3] = y.w;
+            }
+        }
+    }
+
+    // ---- 6. poison fix-up by the CTA of this instance that finishes last ----
+    __shared__ uint32_t s_first_bad;
+    __threadfence();                                       // my outputs are visible before I count myself done
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t first_bad = 0xffffffffu;
+        if (atomicAdd(in.poison + 1, 1u) == gridDim.x - 1) {
+            first_bad = atomicExch(in.poison, 0xffffffffu) ;  // read and re-arm for the next launch
+            in.poison[1] = 0u;
+            __threadfence();
+        }
+        s_first_bad = first_bad;
+    }
+    __syncthreads();
+    if (s_first_bad != 0xffffffffu) {
+        const float nan = __int_as_float(0x7fc00000);
+        for (uint64_t i = ((uint64_t)s_first_bad + 1) * LC + tid; i < b.frames; i += kT) in.out[i] = nan;
+        if (tid == 0 && s_first_bad + 1 < b.n_chunks) {     // (in the last chunk the exact pass already left the true state)
+            double* so = in.state_out;
+#pragma unroll
+            for (int e = 0; e < 8; e++) so[e] = __longlong_as_double(0x7ff8000000000000ll);
+            for (int j = 0; j < 3; j++) {                  // history = the last three inputs, whatever they are
+                const int64_t idx2 = (int64_t)b.frames - 3 + j;
+                so[8 + j] = idx2 >= 0 ? (in.in ? (double)in.in[idx2] : 0.0) : st[8 + 3 + idx2];
             }
         }
     }

@@ -91,6 +91,7 @@ constexpr int kEqStreamThreads = 256;
 struct EqStreamInst {
     const float* in; float* out;
     const double* state; double* state_out;      // lo poles[4], hi poles[4], history[3]; double-buffered
+    uint32_t* poison;                            // device: {first chunk with a non-finite carry (~0 = none), CTAs finished}
     double g_lo, g_mid, g_hi;
 };
 struct EqStreamBatch {                           // ~7 KB of kernel parameters (limit 32 KB on sm_100)

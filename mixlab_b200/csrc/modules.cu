@@ -93,12 +93,15 @@ struct EqThree : mxl_module {                         // src/module/eq_three.rs
     int ensure_state()
     {
         if (state_init) return MXL_OK;
-        MXL_TRY(state.ensure(ctx, 2 * 11 * sizeof(double)));
-        MXL_CUDA(cudaMemsetAsync(state.p, 0, 2 * 11 * sizeof(double), ctx->stream));   // poles, history = 0 (eq_three.rs:34-40,113)
+        // [2][11] doubles, then the poison words of eq_stream_kernel: {first non-finite chunk (none = ~0), CTAs done}
+        MXL_TRY(state.ensure(ctx, 2 * 11 * sizeof(double) + 2 * sizeof(uint32_t)));
+        MXL_CUDA(cudaMemsetAsync(state.p, 0, 2 * 11 * sizeof(double) + 2 * sizeof(uint32_t), ctx->stream));   // poles, history = 0 (eq_three.rs:34-40,113)
+        MXL_CUDA(cudaMemsetAsync((char*)state.p + 2 * 11 * sizeof(double), 0xFF, sizeof(uint32_t), ctx->stream));
         state_init = true;
         return MXL_OK;
     }
     double* state_ptr(int which) { return (double*)state.p + 11 * which; }
+    uint32_t* poison_ptr() { return (uint32_t*)((double*)state.p + 22); }
 };
 
 struct FmSine : mxl_module {                          // src/module/fm_sine.rs
@@ -709,6 +712,7 @@ static int run_eq_stream(mxl_ctx* ctx, mxl_module* const* mods, const IoSet* io,
         e.out = io[first + j].out[0]->dev;
         e.state = m->state_ptr(m->cur);
         e.state_out = m->state_ptr(m->cur ^ 1);
+        e.poison = m->poison_ptr();
         e.g_lo = db_to_linear(m->p.gain_lo_db);            // eq_three.rs:62-64
         e.g_mid = db_to_linear(m->p.gain_mid_db);
         e.g_hi = db_to_linear(m->p.gain_hi_db);

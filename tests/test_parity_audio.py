@@ -177,6 +177,37 @@ def test_eq_three_many_instances_one_launch(mxl, oracle, ctx48):
     g.destroy()
 
 
+@pytest.mark.parametrize("bad", [np.nan, np.inf, -np.inf])
+@pytest.mark.parametrize("pos", [0, 1000, 70001, 299999])
+def test_eq_three_non_finite_sample_is_sticky(mxl, oracle, ctx48, bad, pos):
+    """eq_three.rs:121-128: once a NaN or an infinity is in the poles it never leaves -- every later output is
+    NaN, in this call and the following ones.  The time-parallel carry forgets by construction, so the kernel
+    has to re-impose that; samples before the bad one stay bit-exact."""
+    n = 300000
+    x = W.uniform_pm1(4321, n)
+    x[pos] = bad
+    ref = oracle.EqThree(48000.0)
+    want = ref.run((3.0, -2.0, 1.0), x)
+    mod = ctx48.module(mxl.MOD_EQ_THREE, (3.0, -2.0, 1.0))
+    out = ctx48.line(mxl.LINE_MONO, n)
+    mod.run_tick(0, [ctx48.mono(x)], [out])
+    got = out.download()
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.all(np.isnan(got[pos + 1:])) and not np.any(np.isnan(got[:pos]))
+    assert mismatch_count(got[:pos], want[:pos]) == 0
+    # the next call starts from poisoned poles: all NaN, as in the reference
+    y = W.uniform_pm1(55, 5000)
+    want2 = ref.run((3.0, -2.0, 1.0), y)
+    out2 = ctx48.line(mxl.LINE_MONO, y.size)
+    mod.run_tick(n, [ctx48.mono(y)], [out2])
+    assert np.all(np.isnan(want2)) and np.all(np.isnan(out2.download()))
+    # and a clean module is not disturbed by another one's poison (the flags are per instance)
+    clean = ctx48.module(mxl.MOD_EQ_THREE, (3.0, -2.0, 1.0))
+    mod.run_tick(n + 5000, [ctx48.mono(y)], [out2])
+    clean.run_tick(0, [ctx48.mono(y)], [out2])
+    assert mismatch_count(out2.download(), oracle.EqThree(48000.0).run((3.0, -2.0, 1.0), y)) == 0
+
+
 def test_eq_three_disconnected_input(mxl, oracle, ctx48):
     # Disconnected = static zero buffer (io.rs:36-41): only the VSA terms drive the poles
     want = oracle.EqThree(48000.0).run((4.0, 0.0, 4.0), np.zeros(5000, np.float32))
