@@ -206,6 +206,7 @@ void video_slot_set(VideoSlot& s, mxl_frame* f, Rational dur, Rational off)
 KernelTimer::KernelTimer(mxl_ctx* c, const char* name) : ctx(c)
 {
     if (!c || !c->kernel_timing) return;
+    if (c->kernel_events.size() >= (1u << 16)) return;      // nobody is reading: stop recording rather than grow without bound
     cudaEvent_t ev[2] = {nullptr, nullptr};
     for (auto& e : ev) {
         if (!c->kernel_event_pool.empty()) { e = c->kernel_event_pool.back(); c->kernel_event_pool.pop_back(); }

@@ -70,6 +70,9 @@ __global__ void __launch_bounds__(kEqThreads) eq_zero_state_kernel(const __grid_
     double* z = in.zend + (uint64_t)k * 8;
     z[0] = l0; z[1] = l1; z[2] = l2; z[3] = l3;
     z[4] = h0; z[5] = h1; z[6] = h2; z[7] = h3;
+    // a NaN / inf that entered the poles never leaves them in the reference: remember the first such chunk
+    // (eq_stream.cu explains; eq_exact_kernel's last CTA rewrites what follows it)
+    if (!isfinite(l3 + h3 + l0 + h0)) atomicMin(in.poison, k);
 }
 
 struct EqRegs {
@@ -155,7 +158,24 @@ __global__ void __launch_bounds__(kEqThreads) eq_exact_kernel(const __grid_const
         so[0] = r.l0; so[1] = r.l1; so[2] = r.l2; so[3] = r.l3;
         so[4] = r.h0; so[5] = r.h1; so[6] = r.h2; so[7] = r.h3;
         so[8] = r.x0; so[9] = r.x1; so[10] = r.x2;
+        // a non-finite sample in the last chunk (which has no zero-state run) or a poisoned stored state
+        if (!isfinite(r.l3 + r.h3 + r.l0 + r.h0)) atomicMin(in.poison, k);
     }
+    if (k == 0 && !isfinite(st[0] + st[3] + st[4] + st[7])) atomicMin(in.poison, 0u);
+}
+
+// Runs after eq_exact_kernel, one small CTA per instance: everything after the first poisoned chunk becomes NaN.
+__global__ void __launch_bounds__(kEqThreads) eq_poison_fix_kernel(const __grid_constant__ EqBatch b)
+{
+    const EqInst& in = b.inst[blockIdx.x];
+    __shared__ uint32_t s_first_bad;
+    if (threadIdx.x == 0) s_first_bad = atomicExch(in.poison, 0xffffffffu);      // read and re-arm
+    __syncthreads();
+    const uint32_t first_bad = s_first_bad;
+    if (first_bad == 0xffffffffu || first_bad + 1 >= b.n_chunks) return;
+    const float nan = __int_as_float(0x7fc00000);
+    for (uint64_t i = ((uint64_t)first_bad + 1) * b.chunk + threadIdx.x; i < b.frames; i += kEqThreads) in.out[i] = nan;
+    if (threadIdx.x < 8) in.state_out[threadIdx.x] = __longlong_as_double(0x7ff8000000000000ll);
 }
 
 }  // namespace
@@ -173,10 +193,19 @@ int launch_eq_three(mxl_ctx* ctx, const EqBatch& b)
         if (e != cudaSuccess) MXL_FAIL(MXL_ERR_CUDA, "launch of eq_zero_state_kernel failed: %s", cudaGetErrorString(e));
         ctx->launches++;
     }
-    MXL_TIMED(ctx, "eq_exact_kernel");
-    eq_exact_kernel<<<grid, kEqThreads, 0, ctx->stream>>>(b);
+    {
+        MXL_TIMED(ctx, "eq_exact_kernel");
+        eq_exact_kernel<<<grid, kEqThreads, 0, ctx->stream>>>(b);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) MXL_FAIL(MXL_ERR_CUDA, "launch of eq_exact_kernel failed: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    {
+        MXL_TIMED(ctx, "eq_poison_fix_kernel");
+        eq_poison_fix_kernel<<<b.n, kEqThreads, 0, ctx->stream>>>(b);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) MXL_FAIL(MXL_ERR_CUDA, "launch of eq_poison_fix_kernel failed: %s", cudaGetErrorString(e));
     ctx->launches++;
     return MXL_OK;
 }

@@ -69,6 +69,7 @@ struct EqInst {
     const double* state;             // device: lo poles[4], hi poles[4], history[3] before the call
     double* state_out;               // same layout, after the call (other half of a double buffer)
     double* zend;                    // device scratch: per chunk 8 doubles (zero-state end poles)
+    uint32_t* poison;                // device: first chunk with a non-finite carry (~0 = none)
     double g_lo, g_mid, g_hi;
 };
 struct EqBatch {

@@ -769,6 +769,7 @@ static int run_eq_threes(mxl_ctx* ctx, mxl_module* const* mods, int n, const IoS
             e.state = m->state_ptr(m->cur);
             e.state_out = m->state_ptr(m->cur ^ 1);
             e.zend = (double*)m->zend.p;
+            e.poison = m->poison_ptr();
             e.g_lo = db_to_linear(m->p.gain_lo_db);        // eq_three.rs:62-64
             e.g_mid = db_to_linear(m->p.gain_mid_db);
             e.g_hi = db_to_linear(m->p.gain_hi_db);

@@ -177,12 +177,16 @@ def test_eq_three_many_instances_one_launch(mxl, oracle, ctx48):
     g.destroy()
 
 
+@pytest.mark.parametrize("path", ["stream", "two_launch"])
 @pytest.mark.parametrize("bad", [np.nan, np.inf, -np.inf])
 @pytest.mark.parametrize("pos", [0, 1000, 70001, 299999])
-def test_eq_three_non_finite_sample_is_sticky(mxl, oracle, ctx48, bad, pos):
+def test_eq_three_non_finite_sample_is_sticky(mxl, oracle, ctx48, bad, pos, path, monkeypatch):
     """eq_three.rs:121-128: once a NaN or an infinity is in the poles it never leaves -- every later output is
     NaN, in this call and the following ones.  The time-parallel carry forgets by construction, so the kernel
     has to re-impose that; samples before the bad one stay bit-exact."""
+    monkeypatch.delenv("MXL_EQ_CHUNK", raising=False)
+    if path == "two_launch":
+        monkeypatch.setenv("MXL_EQ_CHUNK", "256")
     n = 300000
     x = W.uniform_pm1(4321, n)
     x[pos] = bad
