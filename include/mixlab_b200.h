@@ -145,6 +145,8 @@ MXL_API int mxl_ctx_timer_end(mxl_ctx *ctx);
 MXL_API int mxl_ctx_timer_elapsed_ms(mxl_ctx *ctx, float *ms);
 /* Overwrites a scratch buffer larger than L2 (bench hygiene between timed iterations). */
 MXL_API int mxl_ctx_flush_l2(mxl_ctx *ctx);
+/* Free / total device memory of the context's GPU (cudaMemGetInfo), after synchronising the context. */
+MXL_API int mxl_ctx_device_memory(mxl_ctx *ctx, uint64_t *free_bytes, uint64_t *total_bytes);
 /* Per-kernel device timing: while enabled, every kernel launch of the context is bracketed by a CUDA event
  * pair on its launching stream (host preparation and table copies stay outside).  mxl_ctx_kernel_times
  * synchronises, folds the pairs recorded since the last call into one entry per kernel and returns the

@@ -140,6 +140,7 @@ def lib():
         "mxl_ctx_timer_end": (i32, [vp]),
         "mxl_ctx_timer_elapsed_ms": (i32, [vp, C.POINTER(C.c_float)]),
         "mxl_ctx_flush_l2": (i32, [vp]),
+        "mxl_ctx_device_memory": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
         "mxl_ctx_set_kernel_timing": (i32, [vp, i32]),
         "mxl_ctx_kernel_times": (i32, [vp, C.POINTER(KernelTime), u32]),
         "mxl_last_error": (C.c_char_p, []),
@@ -408,6 +409,11 @@ class Context:
 
     def comm_destroy(self):
         check(lib().mxl_ctx_comm_destroy(self.h))
+
+    def device_memory(self):
+        f, t = C.c_uint64(), C.c_uint64()
+        check(lib().mxl_ctx_device_memory(self.h, C.byref(f), C.byref(t)))
+        return f.value, t.value
 
     def set_kernel_timing(self, enabled):
         check(lib().mxl_ctx_set_kernel_timing(self.h, 1 if enabled else 0))

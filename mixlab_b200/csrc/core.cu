@@ -328,6 +328,18 @@ mxl_ctx* mxl_ctx_create_on_stream(int device, uint32_t sample_rate, uint32_t sam
     return ctx_create(device, sample_rate, samples_per_tick, (cudaStream_t)cuda_stream, true);
 }
 
+int mxl_ctx_device_memory(mxl_ctx* ctx, uint64_t* free_bytes, uint64_t* total_bytes)
+{
+    if (!ctx) MXL_FAIL(MXL_ERR_INVALID, "NULL context");
+    if (!ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "no CUDA device bound to this context");
+    MXL_TRY(mxl_ctx_synchronize(ctx));
+    size_t f = 0, t = 0;
+    MXL_CUDA(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return MXL_OK;
+}
+
 int mxl_ctx_set_kernel_timing(mxl_ctx* ctx, int enabled)
 {
     if (!ctx) MXL_FAIL(MXL_ERR_INVALID, "NULL context");

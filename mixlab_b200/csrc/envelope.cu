@@ -30,6 +30,8 @@ namespace k {
 namespace {
 
 constexpr int kEnvThreads = 256;
+constexpr int kEnvPerThread = 16;     // 32 per thread (tiles of 8192) measured slower: 0.155 vs 0.130 ms per 2^25 samples
+constexpr int kEnvTileSamples = kEnvThreads * kEnvPerThread;
 constexpr int kEnvWarps = kEnvThreads / 32;
 
 // event / transition key of sample idx (index inside the call): 0 = none; later samples have larger keys
@@ -97,10 +99,8 @@ __device__ __forceinline__ uint32_t wait_word(const unsigned long long* p, uint3
     return (uint32_t)(v >> 32) & 3u;
 }
 
-template <int kEnvPerThread>
-__global__ void __launch_bounds__(kEnvThreads, kEnvPerThread <= 16 ? 6 : 4) envelope_kernel(const __grid_constant__ EnvBatch b)
+__global__ void __launch_bounds__(kEnvThreads, 6) envelope_kernel(const __grid_constant__ EnvBatch b)
 {
-    constexpr int kEnvTileSamples = kEnvThreads * kEnvPerThread;
     const EnvInst& in = b.inst[blockIdx.y];
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_ev[kEnvWarps];                  // per-warp last-event key
@@ -333,19 +333,7 @@ __global__ void __launch_bounds__(kEnvThreads, kEnvPerThread <= 16 ? 6 : 4) enve
 
 }  // namespace
 
-// samples per thread: 16 (tiles of 4096); MXL_ENV_PER_THREAD=32 selects tiles of 8192 for A/B runs
-static int env_per_thread()
-{
-    static int v = 0;
-    if (!v) { const char* e = getenv("MXL_ENV_PER_THREAD"); v = (e && atoi(e) == 32) ? 32 : 16; }
-    return v;
-}
-
-uint32_t envelope_tiles(uint64_t frames)
-{
-    const uint64_t tile = (uint64_t)kEnvThreads * env_per_thread();
-    return (uint32_t)((frames + tile - 1) / tile);
-}
+uint32_t envelope_tiles(uint64_t frames) { return (uint32_t)((frames + kEnvTileSamples - 1) / kEnvTileSamples); }
 
 int launch_envelope(mxl_ctx* ctx, const EnvBatch& b)
 {
@@ -355,8 +343,7 @@ int launch_envelope(mxl_ctx* ctx, const EnvBatch& b)
     if (b.frames >= 0x7ffffff0ull) MXL_FAIL(MXL_ERR_LENGTH, "Envelope: call longer than 2^31 samples");
     dim3 grid(envelope_tiles(b.frames), b.n);
     MXL_TIMED(ctx, "envelope_kernel");
-    if (env_per_thread() == 32) envelope_kernel<32><<<grid, kEnvThreads, 0, ctx->stream>>>(b);
-    else envelope_kernel<16><<<grid, kEnvThreads, 0, ctx->stream>>>(b);
+    envelope_kernel<<<grid, kEnvThreads, 0, ctx->stream>>>(b);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) MXL_FAIL(MXL_ERR_CUDA, "envelope launch failed: %s", cudaGetErrorString(e));
     ctx->launches++;

@@ -152,3 +152,25 @@ def test_overlap_orders_upload_after_compute(mxl, oracle, ctx48):
     ctx48.set_copy_overlap(False)
     for p in (pa, pb, res):
         p.free()
+
+
+@pytest.mark.gpu
+def test_steady_state_holds_device_memory_constant(mxl, oracle):
+    """A live session must not grow: frames recycle through the context's pool, job tables and staging rings are
+    reused, tap tables are cached.  300 host-fed steps of an A/V session whose layer B is smaller than layer A
+    (so the scaler, the blank fill and the crossfade all run every tick), then the free device memory is what it
+    was after warm-up."""
+    from mixlab_b200.session import AVSession
+    with mxl.Context(0, 48000, 800) as ctx:
+        sess = AVSession(ctx, W.config4_audio_graph(), 4, video=True, unique_frames=2)
+        small = [ctx.frame(1280, 720, W.random_bytes(70 + k, oracle.frame_layout(1280, 720).size)) for k in range(4)]
+        for k in range(4):
+            sess.line_b.set(k, small[k], duration=(ctx.spt, ctx.sample_rate))
+        for step in range(20):
+            sess.run_step_host(step * 4)
+        free0, _ = ctx.device_memory()
+        for step in range(20, 320):
+            sess.run_step_host(step * 4)
+        free1, _ = ctx.device_memory()
+        assert free1 >= free0 - (1 << 20), (free0, free1)
+        sess.close()
