@@ -379,7 +379,7 @@ def b200_arm(args):
         nonlocal tick
         sess.graph.set_stream_split(split)
         sess.graph.set_profiling(True)
-        acc, nbytes, nlaunch = {}, {}, {}
+        acc, nbytes, nlaunch, host = {}, {}, {}, {}
         for _ in range(K):
             sess.run_step(tick)
             tick += T
@@ -389,9 +389,11 @@ def b200_arm(args):
                 acc.setdefault(s["kind"], []).append(s["last_ms"])
                 nbytes[s["kind"]] = s["algorithmic_bytes"]
                 nlaunch[s["kind"]] = s["n_launches"]
+                host.setdefault(s["kind"], []).append(s["host_us"])
         sess.graph.set_profiling(False)
         sess.graph.set_stream_split(True)
-        return {kind_names[k]: {"ms": statistics.mean(v), "launches": nlaunch[k], "algorithmic_bytes": nbytes[k]}
+        return {kind_names[k]: {"ms": statistics.mean(v), "launches": nlaunch[k], "algorithmic_bytes": nbytes[k],
+                                "host_enqueue_us": statistics.median(host[k])}
                 for k, v in acc.items()}
 
     stages = stage_pass(False)

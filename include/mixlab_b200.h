@@ -261,6 +261,30 @@ MXL_API const char *mxl_module_output_label(const mxl_module *m, uint32_t index)
 MXL_API int mxl_module_run_tick(mxl_module *m, uint64_t t, const mxl_line *const *inputs, uint32_t n_inputs,
                                 mxl_line *const *outputs, uint32_t n_outputs);
 
+/* The reference's own run_tick, host slices in and out: what the UNMODIFIED engine loop hands a module
+ * (src/engine.rs:461-494).  One mxl_host_ref per terminal mirrors InputRef::{Disconnected, Mono(&[f32]),
+ * Stereo(&[f32]), Video(Option<&VideoFrame>)} and OutputRef::{Mono(&mut [f32]), Stereo(&mut [f32]),
+ * Video(&mut Option<VideoFrame>)} (src/engine/io.rs:19-34,79-98).  Audio slices are ordinary host memory:
+ * inputs are copied to device lines cached in the module, the module runs, outputs are copied back, and
+ * the call returns when the output slices are complete (it synchronises the context).  The number of frames
+ * is taken from the slice lengths, as in the reference.  A video terminal carries a frame handle
+ * (Arc<AvFrame> there, a retained mxl_frame here: upload once with mxl_frame_upload*, pass it to as many
+ * ticks and modules as hold it); a video output is written by the call -- NULL = None, else a frame the
+ * caller owns one reference of (mxl_frame_download, mxl_frame_release).  A `type` that differs from the
+ * terminal's is MXL_ERR_TYPE_MISMATCH (the reference panics, io.rs:40-41,49-50,58-59).
+ * This is the literal drop-in (one bus round trip per module per tick); mxl_graph_run_ticks is the fast path. */
+typedef struct mxl_host_ref {
+    int32_t type;               /* mxl_line_type of the terminal */
+    int32_t connected;          /* inputs: 0 = InputRef::Disconnected (the other fields are ignored) */
+    float *samples;             /* Mono / Stereo: first sample of the slice */
+    uint64_t len;               /* f32 in the slice: frames (mono), 2 * frames (stereo) */
+    mxl_frame *frame;           /* Video: Some(frame) / NULL = None */
+    int64_t duration_num, duration_den;   /* video::Frame.duration_hint (src/video.rs), seconds as a ratio */
+    int64_t offset_num, offset_den;       /* engine::VideoFrame.tick_offset (io.rs:11-17) */
+} mxl_host_ref;
+MXL_API int mxl_module_run_tick_host(mxl_module *m, uint64_t t, const mxl_host_ref *inputs, uint32_t n_inputs,
+                                     mxl_host_ref *outputs, uint32_t n_outputs);
+
 /* State read-back (synchronises).  EqThree: lo poles[4], hi poles[4], history[3]. */
 MXL_API int mxl_eq_three_state(mxl_module *m, double state[11]);
 /* Envelope: state (0 Initial, 1 TriggerOn, 2 TriggerOff), seq, off_amplitude */
@@ -363,6 +387,9 @@ typedef struct mxl_stage_info {
     int32_t n_launches;        /* kernels launched by this stage in the last run */
     float last_ms;             /* device time of the last run (profiling on), else -1 */
     uint64_t algorithmic_bytes;/* API-level line bytes read+written by the stage in the last run */
+    float host_us;             /* host time the engine thread spent enqueueing the stage in the last run
+                                * (what a one-tick live call is bound by); always measured */
+    float _pad;
 } mxl_stage_info;
 MXL_API int mxl_graph_stage_count(mxl_graph *g);
 MXL_API int mxl_graph_stage_info(mxl_graph *g, uint32_t stage, mxl_stage_info *out);

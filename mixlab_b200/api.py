@@ -91,7 +91,14 @@ class KernelTime(C.Structure):
 
 class StageInfo(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n_modules", C.c_int32), ("n_launches", C.c_int32),
-                ("last_ms", C.c_float), ("algorithmic_bytes", C.c_uint64)]
+                ("last_ms", C.c_float), ("algorithmic_bytes", C.c_uint64), ("host_us", C.c_float), ("_pad", C.c_float)]
+
+
+class HostRef(C.Structure):
+    """mxl_host_ref: one InputRef / OutputRef of the reference with host slices (io.rs:19-34,79-98)."""
+    _fields_ = [("type", C.c_int32), ("connected", C.c_int32), ("samples", C.c_void_p), ("len", C.c_uint64),
+                ("frame", C.c_void_p), ("duration_num", C.c_int64), ("duration_den", C.c_int64),
+                ("offset_num", C.c_int64), ("offset_den", C.c_int64)]
 
 
 METER_RECORD = np.dtype([("peak", np.float32, 2), ("clip", np.int32), ("_pad", np.int32), ("sumsq", np.float64, 2)])
@@ -195,6 +202,7 @@ def lib():
         "mxl_module_input_label": (C.c_char_p, [vp, u32]),
         "mxl_module_output_label": (C.c_char_p, [vp, u32]),
         "mxl_module_run_tick": (i32, [vp, u64, C.POINTER(vp), u32, C.POINTER(vp), u32]),
+        "mxl_module_run_tick_host": (i32, [vp, u64, C.POINTER(HostRef), u32, C.POINTER(HostRef), u32]),
         "mxl_eq_three_state": (i32, [vp, C.POINTER(dbl)]),
         "mxl_envelope_state": (i32, [vp, C.POINTER(C.c_int32), C.POINTER(u64), C.POINTER(dbl)]),
         "mxl_meter_read": (i32, [vp, u32, C.POINTER(C.c_float), C.POINTER(dbl), C.POINTER(C.c_int32)]),
@@ -708,6 +716,52 @@ class Module:
         outs = (C.c_void_p * max(len(outputs), 1))(*[x.h for x in outputs])
         check(lib().mxl_module_run_tick(self.h, t, ins, len(inputs), outs, len(outputs)))
 
+    def run_tick_host(self, t, inputs, outputs):
+        """ModuleT::run_tick with host slices (mxl_module_run_tick_host), synchronous.
+        inputs: per terminal None (InputRef::Disconnected), a float32 numpy array (Mono / Stereo slice) or, for a
+        video terminal, ("video", Frame-or-None, (dur_num, dur_den), (off_num, off_den)).
+        outputs: float32 numpy arrays written in place, or the string "video".  Returns, per video output, the
+        Frame handed back (owned) or None."""
+        kinds_in = [ty for _, ty in self.inputs()]
+        kinds_out = [ty for _, ty in self.outputs()]
+        ins = (HostRef * max(len(inputs), 1))()
+        outs = (HostRef * max(len(outputs), 1))()
+        for i, x in enumerate(inputs):
+            ty = kinds_in[i] if i < len(kinds_in) else LINE_MONO
+            ins[i].type = ty
+            if x is None:
+                continue
+            ins[i].connected = 1
+            if isinstance(x, tuple) and x[0] == "video":
+                _, fr, dur, off = x
+                ins[i].type = LINE_VIDEO
+                ins[i].frame = fr.h if fr is not None else None
+                ins[i].duration_num, ins[i].duration_den = dur
+                ins[i].offset_num, ins[i].offset_den = off
+            else:
+                if isinstance(x, tuple):                      # (line_type, array): claim another line type
+                    ins[i].type, x = x
+                assert x.dtype == np.float32 and x.flags.c_contiguous
+                ins[i].samples = x.ctypes.data
+                ins[i].len = x.size
+        for i, y in enumerate(outputs):
+            ty = kinds_out[i] if i < len(kinds_out) else LINE_MONO
+            outs[i].type = ty
+            if isinstance(y, str) and y == "video":
+                outs[i].type = LINE_VIDEO
+            else:
+                if isinstance(y, tuple):
+                    outs[i].type, y = y
+                assert y.dtype == np.float32 and y.flags.c_contiguous
+                outs[i].samples = y.ctypes.data
+                outs[i].len = y.size
+        check(lib().mxl_module_run_tick_host(self.h, t, ins, len(inputs), outs, len(outputs)))
+        frames = []
+        for i, y in enumerate(outputs):
+            if isinstance(y, str) and y == "video":
+                frames.append(Frame(self.ctx, handle=outs[i].frame) if outs[i].frame else None)
+        return frames
+
     # kind-specific read-backs
     def eq_three_state(self):
         st = (C.c_double * 11)()
@@ -808,7 +862,7 @@ class Graph:
             s = StageInfo()
             check(lib().mxl_graph_stage_info(self.h, i, C.byref(s)))
             out.append(dict(kind=s.kind, n_modules=s.n_modules, n_launches=s.n_launches,
-                            last_ms=s.last_ms, algorithmic_bytes=int(s.algorithmic_bytes)))
+                            last_ms=s.last_ms, algorithmic_bytes=int(s.algorithmic_bytes), host_us=s.host_us))
         return out
 
     def destroy(self):

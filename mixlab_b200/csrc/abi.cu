@@ -110,6 +110,93 @@ int mxl_module_run_tick(mxl_module* m, uint64_t t, const mxl_line* const* inputs
     return rc;
 }
 
+// The line cached behind terminal `idx` of a host-slice call, at `frames` frames (audio) or one tick slot (video).
+static int host_ref_line(mxl_module* m, std::vector<mxl_line*>& cache, uint32_t idx, int type, uint64_t frames, mxl_line** out)
+{
+    if (cache.size() <= idx) cache.resize(idx + 1, nullptr);
+    mxl_line*& l = cache[idx];
+    if (l && l->type != type) { line_free(l); l = nullptr; }      // Mixer::update re-creates its terminals (mixer.rs:40-44)
+    if (!l) {
+        l = line_alloc(m->ctx, type, frames);
+        if (!l) return MXL_ERR_OOM;
+    } else if (type == MXL_LINE_VIDEO ? l->slots.size() != frames : l->frames != frames) {
+        MXL_TRY(line_resize(l, frames));
+    }
+    *out = l;
+    return MXL_OK;
+}
+
+int mxl_module_run_tick_host(mxl_module* m, uint64_t t, const mxl_host_ref* inputs, uint32_t n_inputs,
+                             mxl_host_ref* outputs, uint32_t n_outputs)
+{
+    if (!m) MXL_FAIL(MXL_ERR_INVALID, "NULL module");
+    if ((n_inputs && !inputs) || (n_outputs && !outputs)) MXL_FAIL(MXL_ERR_INVALID, "NULL terminal table");
+    if (n_inputs != m->inputs.size() || n_outputs != m->outputs.size())
+        MXL_FAIL(MXL_ERR_INVALID, "%s: expected %zu inputs / %zu outputs, got %u / %u", m->kind_name(), m->inputs.size(), m->outputs.size(), n_inputs, n_outputs);
+    mxl_ctx* ctx = m->ctx;
+    if (!ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "mxl_module_run_tick_host: context has no CUDA device; there is no CPU fallback");
+    MXL_TRY(ctx->activate());
+    // the slices are ordinary host memory and the call is synchronous: everything goes on the compute stream
+    // (with copy overlap enabled, first wait for what the side streams still carry)
+    if (ctx->overlap) MXL_TRY(mxl_ctx_synchronize(ctx));
+    std::vector<const mxl_line*> in(n_inputs, nullptr);
+    std::vector<mxl_line*> out(n_outputs, nullptr);
+    for (uint32_t i = 0; i < n_inputs; i++) {
+        const mxl_host_ref& r = inputs[i];
+        if (!r.connected) continue;                                     // InputRef::Disconnected
+        const int type = m->inputs[i].type;
+        if (r.type != type) MXL_FAIL(MXL_ERR_TYPE_MISMATCH, "%s input %u: expected line type %d, got %d", m->kind_name(), i, type, r.type);
+        mxl_line* l = nullptr;
+        if (type == MXL_LINE_VIDEO) {
+            MXL_TRY(host_ref_line(m, m->host_in, i, type, 1, &l));
+            if (r.frame && r.frame->ctx != ctx) MXL_FAIL(MXL_ERR_INVALID, "input %u: frame belongs to another context", i);
+            if (r.frame && (r.duration_den == 0 || r.offset_den == 0)) MXL_FAIL(MXL_ERR_INVALID, "input %u: zero denominator", i);
+            video_slot_set(l->slots[0], r.frame, r.frame ? Rational::make(r.duration_num, r.duration_den) : Rational(),
+                           r.frame ? Rational::make(r.offset_num, r.offset_den) : Rational());
+        } else {
+            if (type == MXL_LINE_STEREO && (r.len & 1)) MXL_FAIL(MXL_ERR_LENGTH, "%s input %u: stereo slice of odd length %llu", m->kind_name(), i, (unsigned long long)r.len);
+            if (r.len && !r.samples) MXL_FAIL(MXL_ERR_INVALID, "input %u: NULL slice", i);
+            MXL_TRY(host_ref_line(m, m->host_in, i, type, type == MXL_LINE_STEREO ? r.len / 2 : r.len, &l));
+            if (r.len) MXL_CUDA(cudaMemcpyAsync(l->dev, r.samples, r.len * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+            ctx->h2d_bytes += r.len * sizeof(float);
+        }
+        in[i] = l;
+    }
+    for (uint32_t i = 0; i < n_outputs; i++) {
+        mxl_host_ref& r = outputs[i];
+        const int type = m->outputs[i].type;
+        if (r.type != type) MXL_FAIL(MXL_ERR_TYPE_MISMATCH, "%s output %u: expected line type %d, got %d", m->kind_name(), i, type, r.type);
+        if (type == MXL_LINE_VIDEO) {
+            MXL_TRY(host_ref_line(m, m->host_out, i, type, 1, &out[i]));
+            video_slot_set(out[i]->slots[0], nullptr, Rational(), Rational());
+        } else {
+            if (type == MXL_LINE_STEREO && (r.len & 1)) MXL_FAIL(MXL_ERR_LENGTH, "%s output %u: stereo slice of odd length %llu", m->kind_name(), i, (unsigned long long)r.len);
+            if (r.len && !r.samples) MXL_FAIL(MXL_ERR_INVALID, "output %u: NULL slice", i);
+            MXL_TRY(host_ref_line(m, m->host_out, i, type, type == MXL_LINE_STEREO ? r.len / 2 : r.len, &out[i]));
+        }
+    }
+    IoSet io{in.data(), n_inputs, out.data(), n_outputs};
+    mxl_module* one = m;
+    MXL_TRY(run_batch(ctx, m->kind, &one, 1, t, &io, nullptr));
+    for (uint32_t i = 0; i < n_outputs; i++) {
+        mxl_host_ref& r = outputs[i];
+        if (m->outputs[i].type == MXL_LINE_VIDEO) {
+            const VideoSlot& s = out[i]->slots[0];
+            r.frame = frame_retain(s.frame);                            // NULL = None
+            r.duration_num = s.duration_hint.num; r.duration_den = s.duration_hint.den;
+            r.offset_num = s.tick_offset.num; r.offset_den = s.tick_offset.den;
+        } else if (r.len) {
+            MXL_CUDA(cudaMemcpyAsync(r.samples, out[i]->dev, r.len * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->d2h_bytes += r.len * sizeof(float);
+        }
+    }
+    // input frames are referenced by the cached one-slot lines only for the duration of the call
+    for (uint32_t i = 0; i < n_inputs; i++)
+        if (in[i] && in[i]->type == MXL_LINE_VIDEO) video_slot_set(m->host_in[i]->slots[0], nullptr, Rational(), Rational());
+    MXL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MXL_OK;
+}
+
 int mxl_eq_three_state(mxl_module* m, double state[11]) { return eq_three_state(m, state); }
 int mxl_envelope_state(mxl_module* m, int32_t* state, uint64_t* seq, double* off_amplitude) { return envelope_state(m, state, seq, off_amplitude); }
 int mxl_meter_read(mxl_module* m, uint32_t slot, float peak[2], double sumsq[2], int32_t* clip) { return meter_read(m, slot, peak, sumsq, clip); }

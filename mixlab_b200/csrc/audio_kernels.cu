@@ -330,11 +330,14 @@ __global__ void __launch_bounds__(kThreads) fill_kernel(const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 // Meter (new): per tick slot, per channel: peak |s|, sum of s^2 in f64, and the
 // OutputDevice clip predicate `s < -1 || s > 1` (output_device.rs:192-194,202-204).
-// One block per (slot, instance); warp-shuffle tree, then one smem hop across warps.
+// Two shapes: a warp per (slot, instance) when the call has enough slots to fill the machine, else a block per
+// slot (a live one-tick call: shortest latency).
 // ------------------------------------------------------------------------------------------
 constexpr int kMeterThreads = 128;
+constexpr int kMeterWarps = kMeterThreads / 32;
 
-__global__ void __launch_bounds__(kMeterThreads) meter_kernel(const __grid_constant__ MeterBatch b)
+// One block per (slot, instance); warp-shuffle tree, then one smem hop across warps.
+__global__ void __launch_bounds__(kMeterThreads) meter_block_kernel(const __grid_constant__ MeterBatch b)
 {
     const MeterInst& in = b.inst[blockIdx.y];
     const uint64_t slot = blockIdx.x;
@@ -354,8 +357,11 @@ __global__ void __launch_bounds__(kMeterThreads) meter_kernel(const __grid_const
 #pragma unroll
             for (int u = 0; u < kU; u++) {
                 const uint64_t v = vb + (uint64_t)u * kMeterThreads + threadIdx.x;
-                s[u] = v < v_end ? ldg_stream(in.in + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+                s[u] = ldg_stream(in.in + 4 * (v < v_end ? v : v_end - 1));     // see meter_warp_kernel
             }
+#pragma unroll
+            for (int u = 0; u < kU; u++)
+                if (vb + (uint64_t)u * kMeterThreads + threadIdx.x >= v_end) s[u] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int u = 0; u < kU; u++) {
                 pk0 = fmaxf(pk0, fmaxf(fabsf(s[u].x), fabsf(s[u].z)));   // fmaxf drops NaN like the oracle's `a > peak`
@@ -414,6 +420,87 @@ __global__ void __launch_bounds__(kMeterThreads) meter_kernel(const __grid_const
             r.sumsq[0] += s_sq[0][i]; r.sumsq[1] += s_sq[1][i];
             r.clip |= s_clip[i];
         }
+        in.out[slot] = r;
+    }
+}
+
+// One WARP per (slot, instance): a tick of 800 stereo frames is 400 float4 = 12.5 per lane, so the
+// shuffle tree is paid once per ~13 loads (a block per slot paid it, a shared-memory hop and a barrier
+// once per ~3 loads and was issue-bound at 0.79 of the copy peak).  No shared memory, no barrier.
+__global__ void __launch_bounds__(kMeterThreads) meter_warp_kernel(const __grid_constant__ MeterBatch b, uint32_t n_slots)
+{
+    const MeterInst& in = b.inst[blockIdx.y];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t slot = (uint64_t)blockIdx.x * kMeterWarps + (threadIdx.x >> 5);
+    if (slot >= n_slots) return;
+    const uint64_t f_begin = slot * b.spt;
+    uint64_t f_end = f_begin + b.spt;
+    if (f_end > b.frames) f_end = b.frames;
+    float pk0 = 0.f, pk1 = 0.f;
+    double sq0 = 0.0, sq1 = 0.0;
+    if (in.in && ((f_begin & 1) == 0) && (reinterpret_cast<uintptr_t>(in.in) & 15) == 0) {
+        // the slot starts 16-byte aligned: float4 = two frames, eight vectors in flight per lane (a warp has no
+        // other warp of its slot to hide the latency behind), each warp instruction covering 512 contiguous bytes
+        constexpr int kU = 8;
+        const uint64_t v_begin = f_begin >> 1, v_end = f_end >> 1;
+        for (uint64_t vb = v_begin; vb < v_end; vb += kU * 32) {
+            float4 s[kU];
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                // unconditional loads (index clamped, value masked below): a predicated load ends up scheduled
+                // behind the arithmetic of the one before it, which leaves one or two loads in flight per warp
+                const uint64_t v = vb + (uint64_t)u * 32 + lane;
+                s[u] = ldg_stream(in.in + 4 * (v < v_end ? v : v_end - 1));
+            }
+#pragma unroll
+            for (int u = 0; u < kU; u++)
+                if (vb + (uint64_t)u * 32 + lane >= v_end) s[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                pk0 = fmaxf(pk0, fmaxf(fabsf(s[u].x), fabsf(s[u].z)));   // fmaxf drops NaN like the oracle's `a > peak`
+                pk1 = fmaxf(pk1, fmaxf(fabsf(s[u].y), fabsf(s[u].w)));
+                sq0 += (double)s[u].x * (double)s[u].x;
+                sq1 += (double)s[u].y * (double)s[u].y;
+                sq0 += (double)s[u].z * (double)s[u].z;
+                sq1 += (double)s[u].w * (double)s[u].w;
+            }
+        }
+        if (((f_end - f_begin) & 1) && lane == 0) {                     // odd frame count: last frame
+            const float2 t = ldg_stream2(in.in + 2 * (f_end - 1));
+            pk0 = fmaxf(pk0, fabsf(t.x)); pk1 = fmaxf(pk1, fabsf(t.y));
+            sq0 += (double)t.x * (double)t.x; sq1 += (double)t.y * (double)t.y;
+        }
+    } else if (in.in) {
+        constexpr int kU = 4;                  // frames in flight per lane
+        for (uint64_t base = f_begin; base < f_end; base += kU * 32) {
+            float2 s[kU];
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const uint64_t f = base + (uint64_t)u * 32 + lane;
+                s[u] = f < f_end ? ldg_stream2(in.in + 2 * f) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                pk0 = fmaxf(pk0, fabsf(s[u].x));
+                pk1 = fmaxf(pk1, fabsf(s[u].y));
+                sq0 += (double)s[u].x * (double)s[u].x;
+                sq1 += (double)s[u].y * (double)s[u].y;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        pk0 = fmaxf(pk0, __shfl_xor_sync(0xffffffffu, pk0, o));
+        pk1 = fmaxf(pk1, __shfl_xor_sync(0xffffffffu, pk1, o));
+        sq0 += __shfl_xor_sync(0xffffffffu, sq0, o);
+        sq1 += __shfl_xor_sync(0xffffffffu, sq1, o);
+    }
+    if (lane == 0) {
+        MeterRecord r;
+        r.peak[0] = pk0; r.peak[1] = pk1; r.sumsq[0] = sq0; r.sumsq[1] = sq1; r._pad = 0;
+        // output_device.rs:192-194: `s < -1.0 || s > 1.0` for any sample <=> the peak of |s| exceeds 1 (a NaN
+        // sample fails both tests there and is dropped by fmaxf here)
+        r.clip = (pk0 > 1.0f || pk1 > 1.0f) ? 1 : 0;
         in.out[slot] = r;
     }
 }
@@ -589,9 +676,15 @@ int launch_meter(mxl_ctx* ctx, const MeterBatch& b, uint32_t n_slots)
 {
     MXL_REQUIRE_DEVICE(ctx);
     if (b.n <= 0 || n_slots == 0) return MXL_OK;
-    dim3 grid(n_slots, b.n);
     MXL_TIMED(ctx, "meter_kernel");
-    meter_kernel<<<grid, kMeterThreads, 0, ctx->stream>>>(b);
+    const uint64_t machine = (uint64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148) * 16;     // warps that fill every SM's schedulers 4 deep
+    if ((uint64_t)n_slots * b.n >= machine) {
+        dim3 grid((n_slots + kMeterWarps - 1) / kMeterWarps, b.n);
+        meter_warp_kernel<<<grid, kMeterThreads, 0, ctx->stream>>>(b, n_slots);
+    } else {
+        dim3 grid(n_slots, b.n);
+        meter_block_kernel<<<grid, kMeterThreads, 0, ctx->stream>>>(b);
+    }
     return check_launch(ctx, "meter_kernel");
 }
 

@@ -154,6 +154,10 @@ struct FadeJob {                     // one output frame
 };
 // All jobs share one layout.  jobs_dev is a device array of n_jobs FadeJob.
 int launch_crossfade(mxl_ctx* ctx, const mxl_frame_layout& lay, const FadeJob* jobs_dev, uint32_t n_jobs);
+// Same launch with the job table (a HOST array of at most kFadeInlineJobs entries) carried in the kernel parameters
+constexpr int kFadeInlineJobs = 8;
+struct FadeJobsInline { FadeJob job[kFadeInlineJobs]; };
+int launch_crossfade_inline(mxl_ctx* ctx, const mxl_frame_layout& lay, const FadeJob* jobs_host, uint32_t n_jobs);
 int launch_blank(mxl_ctx* ctx, const mxl_frame_layout& lay, uint8_t* frame);
 
 // Tiled letterbox scaler: all planes of a batch of frames in one launch (video_kernels.cu)

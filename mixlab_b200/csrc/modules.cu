@@ -273,6 +273,12 @@ struct VideoMixer : mxl_module {
 
 }  // namespace mxl
 
+mxl_module::~mxl_module()
+{
+    for (mxl_line* l : host_in) mxl::line_free(l);
+    for (mxl_line* l : host_out) mxl::line_free(l);
+}
+
 const char* mxl_module::kind_name() const
 {
     switch (kind) {
@@ -1241,13 +1247,18 @@ int VideoMixer::run(uint64_t t0, const IoSet& io, uint64_t* bytes)
     for (auto& gq : scale_groups) MXL_TRY(scale_run(ctx, gq.sl, gq.w, gq.h, gq.jobs.data(), (uint32_t)gq.jobs.size()));
     // one batched launch per run of equal layouts (normally exactly one)
     if (!jobs.empty()) {
-        MXL_TRY(this->jobs.ensure(ctx, jobs.size() * sizeof(k::FadeJob)));
-        MXL_CUDA(cudaMemcpyAsync(this->jobs.p, jobs.data(), jobs.size() * sizeof(k::FadeJob), cudaMemcpyHostToDevice, ctx->stream));
+        // a call of a few ticks (the live engine thread: one) carries its job table in the kernel parameters
+        const bool inline_jobs = jobs.size() <= (size_t)k::kFadeInlineJobs;
+        if (!inline_jobs) {
+            MXL_TRY(this->jobs.ensure(ctx, jobs.size() * sizeof(k::FadeJob)));
+            MXL_CUDA(cudaMemcpyAsync(this->jobs.p, jobs.data(), jobs.size() * sizeof(k::FadeJob), cudaMemcpyHostToDevice, ctx->stream));
+        }
         size_t begin = 0;
         while (begin < jobs.size()) {
             size_t end = begin + 1;
             while (end < jobs.size() && job_layouts[end].width == job_layouts[begin].width && job_layouts[end].height == job_layouts[begin].height) end++;
-            MXL_TRY(k::launch_crossfade(ctx, job_layouts[begin], (const k::FadeJob*)this->jobs.p + begin, (uint32_t)(end - begin)));
+            if (inline_jobs) MXL_TRY(k::launch_crossfade_inline(ctx, job_layouts[begin], jobs.data() + begin, (uint32_t)(end - begin)));
+            else MXL_TRY(k::launch_crossfade(ctx, job_layouts[begin], (const k::FadeJob*)this->jobs.p + begin, (uint32_t)(end - begin)));
             begin = end;
         }
     }

@@ -35,8 +35,10 @@ struct mxl_module {
     mxl_ctx* ctx = nullptr;
     int kind = -1;
     std::vector<mxl::Terminal> inputs, outputs;
+    // device lines behind the host slices of mxl_module_run_tick_host, one per terminal, kept across ticks
+    std::vector<mxl_line*> host_in, host_out;
 
-    virtual ~mxl_module() {}
+    virtual ~mxl_module();
     virtual int update(const void* params) = 0;          // ModuleT::update
     virtual int get_params(void* out) const = 0;         // ModuleT::params
     const char* kind_name() const;

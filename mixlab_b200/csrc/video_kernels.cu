@@ -47,9 +47,8 @@ __device__ __forceinline__ uint4 fade16(uint4 a, uint4 b, uint32_t f, uint32_t g
 // processed bytes of a frame are one contiguous range [0, size).
 constexpr int kFadeUnroll = 2;
 
-__global__ void __launch_bounds__(kVidThreads) crossfade_flat_kernel(const FadeJob* __restrict__ jobs, uint64_t n16, uint64_t chroma16)
+__device__ __forceinline__ void crossfade_flat_body(const FadeJob& job, uint64_t n16, uint64_t chroma16)
 {
-    const FadeJob job = jobs[blockIdx.y];
     const uint32_t f = job.fade, g = 255u - job.fade;
     // the kFadeUnroll vectors of a thread are kVidThreads apart: each warp instruction is 512 contiguous bytes
     const uint64_t v0 = (uint64_t)blockIdx.x * (kVidThreads * kFadeUnroll) + threadIdx.x;
@@ -70,11 +69,21 @@ __global__ void __launch_bounds__(kVidThreads) crossfade_flat_kernel(const FadeJ
     }
 }
 
-// General path: one plane per launch, rows may carry untouched stride padding.
-__global__ void __launch_bounds__(kVidThreads) crossfade_plane_kernel(const FadeJob* __restrict__ jobs, uint64_t plane_offset,
-                                                                      uint32_t stride, uint32_t vec_per_row, uint32_t blank)
+__global__ void __launch_bounds__(kVidThreads) crossfade_flat_kernel(const FadeJob* __restrict__ jobs, uint64_t n16, uint64_t chroma16)
 {
-    const FadeJob job = jobs[blockIdx.z];
+    crossfade_flat_body(jobs[blockIdx.y], n16, chroma16);
+}
+
+// A call of a few ticks (the 60 Hz engine thread: one) carries its job table in the kernel parameters: no
+// table upload precedes the launch.
+__global__ void __launch_bounds__(kVidThreads) crossfade_flat_inline_kernel(const __grid_constant__ FadeJobsInline jobs, uint64_t n16, uint64_t chroma16)
+{
+    crossfade_flat_body(jobs.job[blockIdx.y], n16, chroma16);
+}
+
+// General path: one plane per launch, rows may carry untouched stride padding.
+__device__ __forceinline__ void crossfade_plane_body(const FadeJob& job, uint64_t plane_offset, uint32_t stride, uint32_t vec_per_row, uint32_t blank)
+{
     const uint32_t col = blockIdx.x * kVidThreads + threadIdx.x;
     if (col >= vec_per_row) return;
     const uint64_t off = plane_offset + (uint64_t)blockIdx.y * stride + (uint64_t)col * 16;
@@ -82,6 +91,18 @@ __global__ void __launch_bounds__(kVidThreads) crossfade_plane_kernel(const Fade
     const uint4 a = job.a ? ldg16(job.a + off) : make_uint4(blank, blank, blank, blank);
     const uint4 b = job.b ? ldg16(job.b + off) : make_uint4(blank, blank, blank, blank);
     *reinterpret_cast<uint4*>(job.out + off) = fade16(a, b, f, g);
+}
+
+__global__ void __launch_bounds__(kVidThreads) crossfade_plane_kernel(const FadeJob* __restrict__ jobs, uint64_t plane_offset,
+                                                                      uint32_t stride, uint32_t vec_per_row, uint32_t blank)
+{
+    crossfade_plane_body(jobs[blockIdx.z], plane_offset, stride, vec_per_row, blank);
+}
+
+__global__ void __launch_bounds__(kVidThreads) crossfade_plane_inline_kernel(const __grid_constant__ FadeJobsInline jobs, uint64_t plane_offset,
+                                                                             uint32_t stride, uint32_t vec_per_row, uint32_t blank)
+{
+    crossfade_plane_body(jobs.job[blockIdx.z], plane_offset, stride, vec_per_row, blank);
 }
 
 __global__ void __launch_bounds__(kVidThreads) blank_kernel(uint4* dst, uint64_t n16, uint64_t chroma16)
@@ -372,16 +393,20 @@ PlaneGeom plane_geom(const mxl_frame_layout& lay, int comp)
 
 }  // namespace
 
+static bool crossfade_is_flat(const mxl_frame_layout& lay)
+{
+    for (int c = 0; c < 3; c++) {
+        PlaneGeom g = plane_geom(lay, c);
+        if (g.padw != lay.stride[c] || g.rows != lay.plane_h[c]) return false;
+    }
+    return true;
+}
+
 int launch_crossfade(mxl_ctx* ctx, const mxl_frame_layout& lay, const FadeJob* jobs_dev, uint32_t n_jobs)
 {
     MXL_TRY(require_device(ctx));
     if (n_jobs == 0) return MXL_OK;
-    bool flat = true;
-    for (int c = 0; c < 3; c++) {
-        PlaneGeom g = plane_geom(lay, c);
-        if (g.padw != lay.stride[c] || g.rows != lay.plane_h[c]) flat = false;
-    }
-    if (flat) {
+    if (crossfade_is_flat(lay)) {
         const uint64_t n16 = lay.size / 16;
         const uint64_t per_block = (uint64_t)kVidThreads * kFadeUnroll;
         dim3 grid((unsigned)((n16 + per_block - 1) / per_block), n_jobs);
@@ -398,6 +423,34 @@ int launch_crossfade(mxl_ctx* ctx, const mxl_frame_layout& lay, const FadeJob* j
         crossfade_plane_kernel<<<grid, kVidThreads, 0, ctx->stream>>>(jobs_dev, lay.offset[c], lay.stride[c], vpr,
                                                                      c == 0 ? 0u : 0x80808080u);
         MXL_TRY(after_launch(ctx, "crossfade_plane_kernel"));
+    }
+    return MXL_OK;
+}
+
+int launch_crossfade_inline(mxl_ctx* ctx, const mxl_frame_layout& lay, const FadeJob* jobs_host, uint32_t n_jobs)
+{
+    MXL_TRY(require_device(ctx));
+    if (n_jobs == 0) return MXL_OK;
+    if (n_jobs > (uint32_t)kFadeInlineJobs) MXL_FAIL(MXL_ERR_INVALID, "launch_crossfade_inline: %u jobs, at most %d", n_jobs, kFadeInlineJobs);
+    FadeJobsInline tab;
+    for (uint32_t i = 0; i < n_jobs; i++) tab.job[i] = jobs_host[i];
+    if (crossfade_is_flat(lay)) {
+        const uint64_t n16 = lay.size / 16;
+        const uint64_t per_block = (uint64_t)kVidThreads * kFadeUnroll;
+        dim3 grid((unsigned)((n16 + per_block - 1) / per_block), n_jobs);
+        MXL_TIMED(ctx, "crossfade_flat_kernel");
+        crossfade_flat_inline_kernel<<<grid, kVidThreads, 0, ctx->stream>>>(tab, n16, lay.offset[1] / 16);
+        return after_launch(ctx, "crossfade_flat_inline_kernel");
+    }
+    for (int c = 0; c < 3; c++) {
+        PlaneGeom g = plane_geom(lay, c);
+        if (g.rows == 0 || g.padw == 0) continue;
+        const uint32_t vpr = g.padw / 16;
+        dim3 grid((vpr + kVidThreads - 1) / kVidThreads, g.rows, n_jobs);
+        MXL_TIMED(ctx, "crossfade_plane_kernel");
+        crossfade_plane_inline_kernel<<<grid, kVidThreads, 0, ctx->stream>>>(tab, lay.offset[c], lay.stride[c], vpr,
+                                                                            c == 0 ? 0u : 0x80808080u);
+        MXL_TRY(after_launch(ctx, "crossfade_plane_inline_kernel"));
     }
     return MXL_OK;
 }

@@ -439,6 +439,25 @@ def test_meter(mxl, oracle, ctx48):
     assert clips[3] is True
 
 
+def test_meter_many_ticks_odd_tick_length(mxl, oracle, ctx44):
+    """Enough slots for the warp-per-slot shape of the meter, 735-sample ticks (odd slots start 8-byte
+    aligned only: the float2 path), a ragged last tick, a NaN (dropped by the peak, poisons the sum) and
+    one sample beyond +-1."""
+    spt, ticks, tail = 735, 2600, 201
+    frames = spt * ticks + tail
+    x = W.uniform_pm1(78, 2 * frames)
+    x[2 * spt * 1001 + 5] = np.float32(1.25)
+    x[2 * spt * 1002 + 8] = np.float32(np.nan)
+    mod = ctx44.module(mxl.MOD_METER)
+    mod.run_tick(0, [ctx44.stereo(x)], [])
+    rec = mod.meter_download(ticks + 1)
+    for k in list(range(0, ticks + 1, 97)) + [1001, 1002, ticks]:
+        wp, ws, wc = oracle.meter(x[2 * spt * k:2 * spt * (k + 1)])
+        assert tuple(rec["peak"][k]) == tuple(wp) and bool(rec["clip"][k]) == wc, k
+        assert np.allclose(rec["sumsq"][k], ws, rtol=1e-13, atol=0, equal_nan=True), k
+    assert bool(rec["clip"][1001]) and np.isnan(rec["sumsq"][1002]).any()
+
+
 def test_plotter_tap(mxl, oracle, ctx48):
     # plotter.rs:37-56: every 6th tick the de-interleaved tick is reported
     spt = 800
