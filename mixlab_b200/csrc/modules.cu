@@ -1238,7 +1238,8 @@ int VideoMixer::run(uint64_t t0, const IoSet& io, uint64_t* bytes)
         job.fade = mxl_fader_to_u8(p.fader);                                                       // 168
         jobs.push_back(job);
         job_layouts.push_back(outf->layout);
-        if (bytes) *bytes += (ca ? outf->layout.size : 0) + (cb ? outf->layout.size : 0) + outf->layout.size;
+        // a layer at weight 0 (fader at an end stop) is not read by the kernel
+        if (bytes) *bytes += ((ca && job.fade != 0) ? outf->layout.size : 0) + ((cb && job.fade != 255) ? outf->layout.size : 0) + outf->layout.size;
         video_slot_set(io.out[0]->slots[kk], outf, tick_duration, Rational());                     // 241-247
         frame_release(outf);                                // the line holds the reference now
     }
