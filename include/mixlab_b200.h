@@ -79,7 +79,9 @@ typedef enum mxl_module_kind {
     MXL_MOD_PLOTTER = 8,
     MXL_MOD_STEREO_PANNER = 9,
     MXL_MOD_STEREO_SPLITTER = 10,
-    MXL_MOD_STREAM_INPUT = 11,    /* (io) not provided */
+    MXL_MOD_STREAM_INPUT = 11,    /* run_tick provided (queue assembly + gating, stream_input.rs:72-147); the
+                                   * RTMP / Icecast receivers that feed it stay in the host application and push
+                                   * with mxl_stream_input_write_audio / _write_video */
     MXL_MOD_STREAM_OUTPUT = 12,   /* (io) not provided */
     MXL_MOD_TRIGGER = 13,
     MXL_MOD_VIDEO_MIXER = 14,
@@ -235,6 +237,9 @@ MXL_API int mxl_video_line_set(mxl_line *line, uint32_t slot, mxl_frame *frame, 
                                int64_t duration_den, int64_t offset_num, int64_t offset_den);
 /* borrowed pointer, NULL if the slot is empty */
 MXL_API mxl_frame *mxl_video_line_get(const mxl_line *line, uint32_t slot);
+/* duration_hint and tick_offset of a slot's VideoFrame (io.rs:11-17) as {numerator, denominator};
+ * MXL_ERR_INVALID if the slot is empty */
+MXL_API int mxl_video_line_get_timing(const mxl_line *line, uint32_t slot, int64_t duration[2], int64_t offset[2]);
 MXL_API int mxl_video_line_clear(mxl_line *line);
 
 /* ---- modules: trait ModuleT, src/module/mod.rs:7-19 ------------------------------------------- */
@@ -303,6 +308,25 @@ MXL_API int mxl_plotter_read(mxl_module *m, float *left, float *right, uint32_t 
 MXL_API int mxl_source_set_line(mxl_module *m, mxl_line *line);
 /* PCM sink: packed i16 of the last call (src/video/encode.rs:184-195) */
 MXL_API int mxl_pcm_sink_download(mxl_module *m, int16_t *host, uint64_t n_samples);
+
+/* ---- StreamInput (src/module/stream_input.rs): the module just before the path ------------------
+ * outputs: Video "Video", Stereo "Audio" (stream_input.rs:44-47); params: none here (protocol and mountpoint
+ * select the receiver, which stays in the host application).  The receiver side pushes what
+ * SourceSend::write_audio / write_video push (src/source.rs:156-190): Frame { source_id, source_time, data }.
+ * Audio data is interleaved i16 as the decoder delivers it: it crosses the bus at 2 B/sample and is converted
+ * by the device (convert_sample, stream_input.rs:167-173).  run_tick then does what the reference does per tick
+ * (72-147): fills the tick's stereo line from the queued frames (several frames, or part of one), zero-fills on
+ * underrun, re-bases the source clock when the source id changes, and holds a video frame back until it is
+ * due (tick_offset <= tick duration).  A call over n ticks (video line of n slots, stereo line of n * S frames)
+ * is n such ticks with one upload and one conversion launch.
+ * Queues hold 65536 frames like the reference's ring buffers (source.rs:97-98); a full queue is MXL_ERR_LENGTH
+ * (write_* returns Err(()) there).  `frame` is retained by the queue. */
+MXL_API int mxl_stream_input_write_audio(mxl_module *m, uint64_t source_id, int64_t time_num, int64_t time_den,
+                                         const int16_t *samples, uint64_t n_samples);
+MXL_API int mxl_stream_input_write_video(mxl_module *m, uint64_t source_id, int64_t time_num, int64_t time_den,
+                                         mxl_frame *frame, int64_t duration_num, int64_t duration_den);
+/* Frames waiting in the two queues (a partly consumed audio frame / a held-back video frame count as one). */
+MXL_API int mxl_stream_input_pending(const mxl_module *m, uint32_t *audio_frames, uint32_t *video_frames);
 
 /* Stand-alone PCM converters on raw device memory of the context (N2/N3 rows of SURVEY §8f):
  * i16 -> f32 `sample / 32768.0` (stream_input.rs:167-173) and the pack above. */

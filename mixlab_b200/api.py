@@ -203,6 +203,10 @@ def lib():
         "mxl_module_output_label": (C.c_char_p, [vp, u32]),
         "mxl_module_run_tick": (i32, [vp, u64, C.POINTER(vp), u32, C.POINTER(vp), u32]),
         "mxl_module_run_tick_host": (i32, [vp, u64, C.POINTER(HostRef), u32, C.POINTER(HostRef), u32]),
+        "mxl_stream_input_write_audio": (i32, [vp, u64, C.c_int64, C.c_int64, vp, u64]),
+        "mxl_stream_input_write_video": (i32, [vp, u64, C.c_int64, C.c_int64, vp, C.c_int64, C.c_int64]),
+        "mxl_stream_input_pending": (i32, [vp, C.POINTER(u32), C.POINTER(u32)]),
+        "mxl_video_line_get_timing": (i32, [vp, u32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
         "mxl_eq_three_state": (i32, [vp, C.POINTER(dbl)]),
         "mxl_envelope_state": (i32, [vp, C.POINTER(C.c_int32), C.POINTER(u64), C.POINTER(dbl)]),
         "mxl_meter_read": (i32, [vp, u32, C.POINTER(C.c_float), C.POINTER(dbl), C.POINTER(C.c_int32)]),
@@ -633,6 +637,12 @@ class VideoLine:
         h = lib().mxl_video_line_get(self.h, slot)
         return Frame(self.ctx, handle=h) if h else None      # borrowed: do not release
 
+    def timing(self, slot):
+        """((duration_num, duration_den), (offset_num, offset_den)) of the slot's VideoFrame."""
+        d, o = (C.c_int64 * 2)(), (C.c_int64 * 2)()
+        check(lib().mxl_video_line_get_timing(self.h, slot, d, o))
+        return (d[0], d[1]), (o[0], o[1])
+
     def clear(self):
         check(lib().mxl_video_line_clear(self.h))
 
@@ -761,6 +771,20 @@ class Module:
             if isinstance(y, str) and y == "video":
                 frames.append(Frame(self.ctx, handle=outs[i].frame) if outs[i].frame else None)
         return frames
+
+    # StreamInput: what the receiver pushes (SourceSend::write_audio / write_video, src/source.rs:156-190)
+    def stream_write_audio(self, source_id, source_time, samples):
+        """source_time: (num, den) seconds; samples: interleaved int16."""
+        samples = np.ascontiguousarray(samples, np.int16)
+        check(lib().mxl_stream_input_write_audio(self.h, source_id, source_time[0], source_time[1], _ptr(samples), samples.size))
+
+    def stream_write_video(self, source_id, source_time, frame, duration):
+        check(lib().mxl_stream_input_write_video(self.h, source_id, source_time[0], source_time[1], frame.h, duration[0], duration[1]))
+
+    def stream_pending(self):
+        a, v = C.c_uint32(), C.c_uint32()
+        check(lib().mxl_stream_input_pending(self.h, C.byref(a), C.byref(v)))
+        return a.value, v.value
 
     # kind-specific read-backs
     def eq_three_state(self):

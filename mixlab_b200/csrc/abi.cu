@@ -206,6 +206,21 @@ int mxl_plotter_read(mxl_module* m, float* left, float* right, uint32_t cap_fram
 int mxl_source_set_line(mxl_module* m, mxl_line* line) { return source_set_line(m, line); }
 int mxl_pcm_sink_download(mxl_module* m, int16_t* host, uint64_t n_samples) { return pcm_sink_download(m, host, n_samples); }
 
+int mxl_stream_input_write_audio(mxl_module* m, uint64_t source_id, int64_t time_num, int64_t time_den, const int16_t* samples, uint64_t n_samples)
+{
+    if (time_den == 0) MXL_FAIL(MXL_ERR_INVALID, "mxl_stream_input_write_audio: zero denominator");
+    return stream_input_write_audio(m, source_id, Rational::make(time_num, time_den), samples, n_samples);
+}
+
+int mxl_stream_input_write_video(mxl_module* m, uint64_t source_id, int64_t time_num, int64_t time_den, mxl_frame* frame,
+                                 int64_t duration_num, int64_t duration_den)
+{
+    if (time_den == 0 || duration_den == 0) MXL_FAIL(MXL_ERR_INVALID, "mxl_stream_input_write_video: zero denominator");
+    return stream_input_write_video(m, source_id, Rational::make(time_num, time_den), frame, Rational::make(duration_num, duration_den));
+}
+
+int mxl_stream_input_pending(const mxl_module* m, uint32_t* audio_frames, uint32_t* video_frames) { return stream_input_pending(m, audio_frames, video_frames); }
+
 // Device staging for i16 PCM on its way in or out: a ring owned by the context, so the asynchronous
 // converters neither allocate nor synchronise per call.  A region is reused only after a wrap, which
 // first waits for everything queued on the context.

@@ -49,7 +49,9 @@ struct Rational {
     int64_t num = 0, den = 1;
     static Rational make(int64_t n, int64_t d);
     Rational operator+(const Rational& o) const;
+    Rational operator-(const Rational& o) const;
     bool operator>=(const Rational& o) const;
+    bool operator>(const Rational& o) const;
     bool operator==(const Rational& o) const { return num == o.num && den == o.den; }
 };
 

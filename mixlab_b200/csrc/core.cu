@@ -49,9 +49,22 @@ Rational Rational::operator+(const Rational& o) const
     return Rational::make((int64_t)n, l);
 }
 
+Rational Rational::operator-(const Rational& o) const
+{
+    int64_t g = gcd64(den, o.den);
+    int64_t l = den / g * o.den;
+    __int128 n = (__int128)num * (l / den) - (__int128)o.num * (l / o.den);
+    return Rational::make((int64_t)n, l);
+}
+
 bool Rational::operator>=(const Rational& o) const
 {
     return (__int128)num * o.den >= (__int128)o.num * den;
+}
+
+bool Rational::operator>(const Rational& o) const
+{
+    return (__int128)num * o.den > (__int128)o.num * den;
 }
 
 // ---- checked line access (io.rs:36-61,100-126) ---------------------------------------------------
@@ -807,6 +820,16 @@ mxl_frame* mxl_video_line_get(const mxl_line* line, uint32_t slot)
 {
     if (!line || line->type != MXL_LINE_VIDEO || slot >= line->slots.size()) return nullptr;
     return line->slots[slot].frame;
+}
+
+int mxl_video_line_get_timing(const mxl_line* line, uint32_t slot, int64_t duration[2], int64_t offset[2])
+{
+    if (!line || line->type != MXL_LINE_VIDEO || slot >= line->slots.size()) MXL_FAIL(MXL_ERR_INVALID, "mxl_video_line_get_timing: no such slot");
+    const VideoSlot& s = line->slots[slot];
+    if (!s.frame) MXL_FAIL(MXL_ERR_INVALID, "mxl_video_line_get_timing: slot %u is empty", slot);
+    if (duration) { duration[0] = s.duration_hint.num; duration[1] = s.duration_hint.den; }
+    if (offset) { offset[0] = s.tick_offset.num; offset[1] = s.tick_offset.den; }
+    return MXL_OK;
 }
 
 int mxl_video_line_clear(mxl_line* line)

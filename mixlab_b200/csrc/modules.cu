@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <deque>
 
 namespace mxl {
 
@@ -239,6 +240,52 @@ struct PcmSink : mxl_module {                         // new: f32 -> i16 pack (s
     int get_params(void*) const override { return MXL_OK; }
 };
 
+// ---- StreamInput: src/module/stream_input.rs -------------------------------------------------------
+// The receiver (RTMP / Icecast) stays in the host application and pushes Frame { source_id, source_time, data }
+// (src/source.rs:63-70) through mxl_stream_input_write_*; this class is the module's run_tick: the queue
+// assembly and gating on the host (integer / rational bookkeeping, a few frames per tick), the sample
+// conversion on the device.
+struct StreamInput : mxl_module {
+    static constexpr size_t kRingCapacity = 65536;                 // RingBuffer::new(65536), source.rs:97-98
+    struct AudioFrame { uint64_t source_id = 0; Rational source_time; std::vector<int16_t> data; size_t head = 0; };
+    struct VideoFrame { uint64_t source_id = 0; Rational source_time; mxl_frame* frame = nullptr; Rational duration_hint; };
+    std::deque<AudioFrame> audio_rx;                               // SourceRecv::audio_rx
+    std::deque<VideoFrame> video_rx;                               // SourceRecv::video_rx
+    bool has_audio_frame = false, has_video_frame = false;         // self.audio_frame / self.video_frame (stream_input.rs:17-18)
+    AudioFrame audio_frame;
+    VideoFrame video_frame;
+    bool has_source = false;                                       // Option<SourceTiming> (21-25)
+    uint64_t source_id = 0;
+    Rational epoch;
+    // i16 of one call on its way to the device: two pinned buffers used in turn, each guarded by an event
+    int16_t* pinned[2] = {nullptr, nullptr};
+    size_t pinned_cap[2] = {0, 0};
+    cudaEvent_t pinned_ev[2] = {nullptr, nullptr};
+    int turn = 0;
+    DevBuf pcm;
+
+    StreamInput()
+    {
+        kind = MXL_MOD_STREAM_INPUT;
+        outputs = {labeled(MXL_LINE_VIDEO, "Video"), labeled(MXL_LINE_STEREO, "Audio")};   // stream_input.rs:44-47
+    }
+    ~StreamInput() override
+    {
+        if (ctx && ctx->has_device()) { ctx->activate(); cudaStreamSynchronize(ctx->stream); }
+        for (auto& v : video_rx) frame_release(v.frame);
+        if (has_video_frame) frame_release(video_frame.frame);
+        for (int i = 0; i < 2; i++) {
+            if (pinned[i]) cudaFreeHost(pinned[i]);
+            if (pinned_ev[i]) cudaEventDestroy(pinned_ev[i]);
+        }
+        pcm.release(ctx);
+    }
+    int update(const void*) override { return MXL_OK; }            // protocol / mountpoint select the receiver (host side)
+    int get_params(void*) const override { return MXL_OK; }
+    int staging(size_t samples, int16_t** out);
+    int run(uint64_t t0, const IoSet& io, uint64_t* bytes);
+};
+
 // ---- VideoMixer: src/module/video_mixer.rs ---------------------------------------------------------
 struct PictureSettings { uint32_t w = 0, h = 0; bool operator==(const PictureSettings& o) const { return w == o.w && h == o.h; } bool operator!=(const PictureSettings& o) const { return !(*this == o); } };
 
@@ -297,6 +344,7 @@ const char* mxl_module::kind_name() const
     case MXL_MOD_SOURCE_MONO: return "SourceMono";
     case MXL_MOD_SOURCE_STEREO: return "SourceStereo";
     case MXL_MOD_SOURCE_VIDEO: return "SourceVideo";
+    case MXL_MOD_STREAM_INPUT: return "StreamInput";
     case MXL_MOD_PCM_SINK: return "PcmSink";
     default: return "?";
     }
@@ -325,7 +373,8 @@ mxl_module* module_create(mxl_ctx* ctx, int kind, const void* params)
     case MXL_MOD_SOURCE_STEREO: m = new Source(kind, MXL_LINE_STEREO); break;
     case MXL_MOD_SOURCE_VIDEO: m = new Source(kind, MXL_LINE_VIDEO); break;
     case MXL_MOD_PCM_SINK: m = new PcmSink(); break;
-    case MXL_MOD_MONITOR: case MXL_MOD_OUTPUT_DEVICE: case MXL_MOD_STREAM_INPUT:
+    case MXL_MOD_STREAM_INPUT: m = new StreamInput(); break;
+    case MXL_MOD_MONITOR: case MXL_MOD_OUTPUT_DEVICE:
     case MXL_MOD_STREAM_OUTPUT: case MXL_MOD_MEDIA_SOURCE:
         set_error("module kind %d is an I/O edge that stays in the host application (out of scope of the tick hot path)", kind);
         return nullptr;
@@ -934,6 +983,146 @@ static int run_pcm_sinks(mxl_ctx* ctx, mxl_module* const* mods, int n, const IoS
 }
 
 // ================================================================================================
+// StreamInput::run_tick: src/module/stream_input.rs:72-147
+// ================================================================================================
+int StreamInput::staging(size_t samples, int16_t** out)
+{
+    turn ^= 1;
+    const int i = turn;
+    if (!pinned_ev[i]) MXL_CUDA(cudaEventCreateWithFlags(&pinned_ev[i], cudaEventDisableTiming));
+    else MXL_CUDA(cudaEventSynchronize(pinned_ev[i]));             // the copy that last read this buffer has finished
+    if (pinned_cap[i] < samples) {
+        if (pinned[i]) { MXL_CUDA(cudaFreeHost(pinned[i])); pinned[i] = nullptr; pinned_cap[i] = 0; }
+        const size_t want = samples + samples / 4 + 64;
+        MXL_CUDA(cudaMallocHost(&pinned[i], want * sizeof(int16_t)));
+        pinned_cap[i] = want;
+    }
+    *out = pinned[i];
+    return MXL_OK;
+}
+
+int StreamInput::run(uint64_t t0, const IoSet& io, uint64_t* bytes)
+{
+    NEED_IO(io, 0, 2, "StreamInput");
+    MXL_TRY(expect_output(io.out[0], MXL_LINE_VIDEO, "StreamInput.Video"));
+    MXL_TRY(expect_output(io.out[1], MXL_LINE_STEREO, "StreamInput.Audio"));
+    const uint64_t ticks = io.out[0]->slots.size();
+    const uint64_t total = io.out[1]->len();                          // f32 of the stereo line over the whole call
+    if (ticks == 0) { if (total) MXL_FAIL(MXL_ERR_LENGTH, "StreamInput: audio line without a video tick slot"); return MXL_OK; }
+    if (total % ticks) MXL_FAIL(MXL_ERR_LENGTH, "StreamInput: %llu samples do not divide into %llu ticks", (unsigned long long)total, (unsigned long long)ticks);
+    const uint64_t len_tick = total / ticks;                          // audio_out.len()
+    int16_t* stage = nullptr;
+    if (total) MXL_TRY(staging(total, &stage));
+    const int64_t sr = (int64_t)ctx->sample_rate;
+
+    for (uint64_t kk = 0; kk < ticks; kk++) {
+        const Rational engine_time = Rational::make((int64_t)(t0 + kk * (len_tick / 2)), sr);       // 73
+        const Rational tick_duration = Rational::make((int64_t)(len_tick / 2), sr);                  // 80
+        // 82-86: the frame held back from an earlier tick, else the next one from the receiver
+        bool have_video = false;
+        VideoFrame vf;
+        if (has_video_frame) { vf = video_frame; has_video_frame = false; have_video = true; }
+        else if (!video_rx.empty()) { vf = video_rx.front(); video_rx.pop_front(); have_video = true; }
+        const bool had_source = has_source;                                                           // 88
+        const uint64_t existing_source_id = source_id;
+        // 92-124: several input audio frames (or part of one) fill the tick
+        int16_t* out = stage + kk * len_tick;
+        uint64_t remaining = len_tick;
+        while (remaining > 0) {
+            AudioFrame fr;
+            bool have = false;
+            if (has_audio_frame) { fr = std::move(audio_frame); has_audio_frame = false; have = true; }
+            else if (!audio_rx.empty()) { fr = std::move(audio_rx.front()); audio_rx.pop_front(); have = true; }
+            if (!have) {                                                                              // 120-123 util::zero
+                memset(out, 0, remaining * sizeof(int16_t));                                          // 0 / 32768.0 == 0.0
+                break;
+            }
+            if (!had_source || existing_source_id != fr.source_id) {                                  // 100-106 source changed
+                has_source = true;
+                source_id = fr.source_id;
+                epoch = engine_time - fr.source_time;                                                 // remove_epoch
+            }
+            const uint64_t avail = fr.data.size() - fr.head;
+            const uint64_t len = std::min<uint64_t>(remaining, avail);                                // 108
+            memcpy(out, fr.data.data() + fr.head, len * sizeof(int16_t));                             // 110-112 (converted on the device)
+            out += len;                                                                               // 114
+            remaining -= len;
+            if (len < avail) {                                                                        // 116-119 drain + put back
+                fr.head += len;
+                audio_frame = std::move(fr);
+                has_audio_frame = true;
+            }
+        }
+        // 126-143
+        if (have_video) {
+            Rational tick_offset;                                                                     // zero
+            if (has_source) {
+                const Rational off = (vf.source_time + epoch) - engine_time;                          // add_epoch(..) - engine_time
+                if (off >= Rational()) tick_offset = off;                                             // filter(>= zero).unwrap_or(zero)
+            }
+            if (tick_offset > tick_duration) {                                                        // not due for this tick, put it back
+                video_frame = vf;
+                has_video_frame = true;
+                video_slot_set(io.out[0]->slots[kk], nullptr, Rational(), Rational());
+            } else {
+                video_slot_set(io.out[0]->slots[kk], vf.frame, vf.duration_hint, tick_offset);
+                frame_release(vf.frame);                                                              // the line holds the reference now
+            }
+        } else {
+            video_slot_set(io.out[0]->slots[kk], nullptr, Rational(), Rational());
+        }
+    }
+    if (total) {
+        MXL_TRY(pcm.ensure(ctx, total * sizeof(int16_t)));
+        MXL_CUDA(cudaMemcpyAsync(pcm.p, stage, total * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+        MXL_CUDA(cudaEventRecord(pinned_ev[turn], ctx->stream));
+        ctx->h2d_bytes += total * sizeof(int16_t);
+        MXL_TRY(k::launch_pcm_unpack(ctx, (const int16_t*)pcm.p, io.out[1]->dev, total));
+        if (bytes) *bytes += 6 * total;
+    }
+    return MXL_OK;
+}
+
+int stream_input_write_audio(mxl_module* m, uint64_t source_id, Rational time, const int16_t* samples, uint64_t n)
+{
+    if (!m || m->kind != MXL_MOD_STREAM_INPUT) MXL_FAIL(MXL_ERR_PARAMS, "not a StreamInput module");
+    if (n && !samples) MXL_FAIL(MXL_ERR_INVALID, "NULL samples");
+    StreamInput* s = (StreamInput*)m;
+    if (s->audio_rx.size() >= StreamInput::kRingCapacity) MXL_FAIL(MXL_ERR_LENGTH, "StreamInput: audio queue full");   // push -> Err(()) (source.rs:168)
+    StreamInput::AudioFrame f;
+    f.source_id = source_id;
+    f.source_time = time;
+    f.data.assign(samples, samples + n);
+    s->audio_rx.push_back(std::move(f));
+    return MXL_OK;
+}
+
+int stream_input_write_video(mxl_module* m, uint64_t source_id, Rational time, mxl_frame* frame, Rational duration)
+{
+    if (!m || m->kind != MXL_MOD_STREAM_INPUT) MXL_FAIL(MXL_ERR_PARAMS, "not a StreamInput module");
+    if (!frame) MXL_FAIL(MXL_ERR_INVALID, "NULL frame");
+    if (frame->ctx != m->ctx) MXL_FAIL(MXL_ERR_INVALID, "frame belongs to another context");
+    StreamInput* s = (StreamInput*)m;
+    if (s->video_rx.size() >= StreamInput::kRingCapacity) MXL_FAIL(MXL_ERR_LENGTH, "StreamInput: video queue full");   // source.rs:186
+    StreamInput::VideoFrame f;
+    f.source_id = source_id;
+    f.source_time = time;
+    f.frame = frame_retain(frame);
+    f.duration_hint = duration;
+    s->video_rx.push_back(f);
+    return MXL_OK;
+}
+
+int stream_input_pending(const mxl_module* m, uint32_t* audio_frames, uint32_t* video_frames)
+{
+    if (!m || m->kind != MXL_MOD_STREAM_INPUT) MXL_FAIL(MXL_ERR_PARAMS, "not a StreamInput module");
+    const StreamInput* s = (const StreamInput*)m;
+    if (audio_frames) *audio_frames = (uint32_t)(s->audio_rx.size() + (s->has_audio_frame ? 1 : 0));
+    if (video_frames) *video_frames = (uint32_t)(s->video_rx.size() + (s->has_video_frame ? 1 : 0));
+    return MXL_OK;
+}
+
+// ================================================================================================
 // VideoMixer: src/module/video_mixer.rs:70-250
 // ================================================================================================
 
@@ -1286,6 +1475,13 @@ int run_batch(mxl_ctx* ctx, int kind, mxl_module* const* mods, int n, uint64_t t
     case MXL_MOD_METER: return run_meters(ctx, mods, n, io, bytes);
     case MXL_MOD_PLOTTER: return run_plotters(ctx, mods, n, io, bytes);
     case MXL_MOD_PCM_SINK: return run_pcm_sinks(ctx, mods, n, io, bytes);
+    case MXL_MOD_STREAM_INPUT:
+        for (int i = 0; i < n; i++) {
+            uint64_t b = 0;
+            MXL_TRY(((StreamInput*)mods[i])->run(t, io[i], &b));
+            if (bytes) *bytes += b;
+        }
+        return MXL_OK;
     case MXL_MOD_VIDEO_MIXER:
         for (int i = 0; i < n; i++) {
             uint64_t b = 0;

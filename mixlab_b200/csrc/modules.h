@@ -64,6 +64,9 @@ int plotter_read(mxl_module* m, float* left, float* right, uint32_t cap);
 int source_set_line(mxl_module* m, mxl_line* line);
 mxl_line* source_line(mxl_module* m);
 int pcm_sink_download(mxl_module* m, int16_t* host, uint64_t n);
+int stream_input_write_audio(mxl_module* m, uint64_t source_id, Rational time, const int16_t* samples, uint64_t n);
+int stream_input_write_video(mxl_module* m, uint64_t source_id, Rational time, mxl_frame* frame, Rational duration);
+int stream_input_pending(const mxl_module* m, uint32_t* audio_frames, uint32_t* video_frames);
 int mixer_params_get(const mxl_module* m, mxl_mixer_channel_params* out, uint32_t cap);
 
 mxl_frame* frame_scale(mxl_frame* src, uint32_t out_w, uint32_t out_h);

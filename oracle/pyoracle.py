@@ -212,6 +212,74 @@ def meter(stereo):
     return (peak[0], peak[1]), (sumsq[0], sumsq[1]), bool(clip.value)
 
 
+class StreamInput:
+    """StreamInput::run_tick (src/module/stream_input.rs:72-147) restated.  MediaTime / MediaDuration are
+    Rational64 (util/src/time.rs:9-10,77-78): fractions.Fraction here.  The receiver's two ring buffers
+    (src/source.rs:73-78,97-98) are deques fed by write_audio / write_video (source.rs:156-190)."""
+    RING_CAPACITY = 65536
+
+    def __init__(self, sample_rate):
+        from collections import deque
+        self.sample_rate = int(sample_rate)
+        self.audio_rx, self.video_rx = deque(), deque()
+        self.audio_frame = None          # self.audio_frame: [source_id, source_time, data]
+        self.video_frame = None          # self.video_frame: (source_id, source_time, data, duration_hint)
+        self.source = None               # SourceTiming (id, epoch)
+
+    def write_audio(self, source_id, source_time, data):
+        if len(self.audio_rx) >= self.RING_CAPACITY:
+            return False                 # tx.audio.push(frame).map_err(|_| ())
+        self.audio_rx.append([source_id, source_time, np.array(data, np.int16)])
+        return True
+
+    def write_video(self, source_id, source_time, data, duration_hint):
+        if len(self.video_rx) >= self.RING_CAPACITY:
+            return False
+        self.video_rx.append((source_id, source_time, data, duration_hint))
+        return True
+
+    def run_tick(self, engine_time, audio_len):
+        """engine_time: absolute sample index (u64); audio_len: f32 in the tick's stereo line.
+        Returns (video_out, audio_out): video_out = None or (data, duration_hint, tick_offset)."""
+        from fractions import Fraction
+        engine_time = Fraction(int(engine_time), self.sample_rate)                  # 73
+        audio_out = np.empty(audio_len, np.float32)
+        pos = 0
+        tick_duration = Fraction(audio_len // 2, self.sample_rate)                   # 80
+        video_frame, self.video_frame = self.video_frame, None                      # 82-86
+        if video_frame is None and self.video_rx:
+            video_frame = self.video_rx.popleft()
+        existing_source_id = self.source[0] if self.source is not None else None    # 88
+        while pos < audio_len:                                                       # 92
+            frame, self.audio_frame = self.audio_frame, None                        # 93-97
+            if frame is None and self.audio_rx:
+                frame = self.audio_rx.popleft()
+            if frame is not None:
+                if existing_source_id != frame[0]:                                   # 100-106
+                    self.source = (frame[0], engine_time - frame[1])
+                n = min(audio_len - pos, frame[2].size)                              # 108
+                audio_out[pos:pos + n] = pcm_unpack_i16(frame[2][:n])                # 110-112 convert_sample
+                pos += n                                                             # 114
+                if n < frame[2].size:                                                # 116-119
+                    frame[2] = frame[2][n:]
+                    self.audio_frame = frame
+            else:
+                audio_out[pos:] = 0.0                                                # 121 util::zero
+                break
+        video_out = None                                                             # 126-143
+        if video_frame is not None:
+            tick_offset = Fraction(0)
+            if self.source is not None:
+                off = video_frame[1] + self.source[1] - engine_time
+                if off >= 0:
+                    tick_offset = off
+            if tick_offset > tick_duration:
+                self.video_frame = video_frame
+            else:
+                video_out = (video_frame[2], video_frame[3], tick_offset)
+        return video_out, audio_out
+
+
 def frame_layout(width, height):
     lay = FrameLayout()
     lib().orc_frame_layout_yuv420p(C.c_uint32(width), C.c_uint32(height), C.byref(lay))

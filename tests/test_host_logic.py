@@ -88,9 +88,20 @@ def test_terminals_match_the_reference(mxl, host_ctx):
 
 
 def test_io_edge_kinds_are_not_provided(mxl, host_ctx):
-    for kind in (mxl.MOD_MONITOR, mxl.MOD_OUTPUT_DEVICE, mxl.MOD_STREAM_INPUT, mxl.MOD_STREAM_OUTPUT, mxl.MOD_MEDIA_SOURCE, 99):
+    for kind in (mxl.MOD_MONITOR, mxl.MOD_OUTPUT_DEVICE, mxl.MOD_STREAM_OUTPUT, mxl.MOD_MEDIA_SOURCE, 99):
         with pytest.raises(mxl.MxlError):
             host_ctx.module(kind, None)
+
+
+def test_stream_input_queues_without_a_device(mxl, host_ctx):
+    """StreamInput's run_tick is provided; its queues are host state and work without a GPU."""
+    si = host_ctx.module(mxl.MOD_STREAM_INPUT, None)
+    assert si.inputs() == [] and si.outputs() == [("Video", mxl.LINE_VIDEO), ("Audio", mxl.LINE_STEREO)]   # stream_input.rs:44-47
+    si.stream_write_audio(1, (0, 1), np.zeros(2048, np.int16))
+    si.stream_write_audio(1, (1024, 48000), np.zeros(2048, np.int16))
+    assert si.stream_pending() == (2, 0)
+    with pytest.raises(mxl.MxlError):
+        mxl.check(mxl.lib().mxl_stream_input_write_audio(si.h, 1, 0, 0, None, 0))       # zero denominator
 
 
 def test_params_roundtrip_and_defaults(mxl, host_ctx):

@@ -71,6 +71,25 @@ def test_crossfade_missing_layer_aliases_blank(mxl, oracle, ctx48, missing):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("fader", [0.0, 1.0])
+@pytest.mark.parametrize("missing", ["a", "b"])
+def test_end_stop_fader_with_missing_layer(mxl, oracle, ctx48, missing, fader):
+    """A layer at weight 0 is not read by the kernel; the result must still be the reference's
+    (a*f + b*(255-f)) / 255 with the missing layer aliasing the blank frame (video_mixer.rs:180-188)."""
+    w, h = 560, 350
+    fa, da, lay = make_frame(ctx48, oracle, w, h, 21)
+    params, a, b = ((-1, 0, fader), None, da) if missing == "a" else ((0, -1, fader), da, None)
+    for size_case in (0, 1):                                   # flat layout (560 = 17.5 x 32 is padded) and 1080p
+        if size_case == 1:
+            w, h = 1920, 1080
+            fa, da, lay = make_frame(ctx48, oracle, w, h, 22)
+            a, b = (None, da) if missing == "a" else (da, None)
+        mod, outs = run_mixer(mxl, ctx48, params, {0: [fa]})
+        want = oracle.video_crossfade(lay, a, b, oracle.fader_to_u8(fader))
+        assert np.array_equal(outs[0].get(0).download_raw(), want), (missing, fader, w)
+        mod.destroy()
+
+
 def test_no_inputs_no_output(mxl, ctx48):
     # video_mixer.rs:113-119: no inputs and no stored pictures -> Output stays None
     mod, outs = run_mixer(mxl, ctx48, (0, 1, 0.5), {})
