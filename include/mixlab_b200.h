@@ -73,7 +73,9 @@ typedef enum mxl_module_kind {
     MXL_MOD_EQ_THREE = 2,
     MXL_MOD_FM_SINE = 3,
     MXL_MOD_MIXER = 4,
-    MXL_MOD_MONITOR = 5,          /* (io) not provided */
+    MXL_MOD_MONITOR = 5,          /* run_tick + the codec thread's feed up to the encoder calls provided
+                                   * (monitor.rs:112-140,235-247; EncodeStream, src/video/encode.rs:34-107,184-221);
+                                   * x264 / fdk-aac and the websocket stay in the host application */
     MXL_MOD_OSCILLATOR = 6,
     MXL_MOD_OUTPUT_DEVICE = 7,    /* (io) not provided */
     MXL_MOD_PLOTTER = 8,
@@ -327,6 +329,40 @@ MXL_API int mxl_stream_input_write_video(mxl_module *m, uint64_t source_id, int6
                                          mxl_frame *frame, int64_t duration_num, int64_t duration_den);
 /* Frames waiting in the two queues (a partly consumed audio frame / a held-back video frame count as one). */
 MXL_API int mxl_stream_input_pending(const mxl_module *m, uint32_t *audio_frames, uint32_t *video_frames);
+
+/* ---- Monitor (src/module/monitor.rs) + EncodeStream (src/video/encode.rs): the module just after the path ----
+ * inputs: Video "Video", Stereo "Audio" (monitor.rs:97-100); no outputs.  run_tick does what Monitor::run_tick
+ * (112-140) and the codec thread's loop body (235-247) do with a tick, up to the two encoder calls:
+ *   timestamp = tick time - time of the module's first tick (epoch);
+ *   AudioCtx::send_audio (encode.rs:184-221): samples clamped to [-1, 1], * 32767, `as i16` -- on the device, the
+ *     whole call in one launch, downloaded at 2 B/sample -- appended to the PCM buffer; whenever it holds MORE than
+ *     2 * 1024 samples, one fragment of exactly 2 * 1024 leaves it (decode_timestamp = running audio clock,
+ *     duration = 1024 / sample_rate): what aac::Encoder::encode is called with;
+ *   EncodeStream::send_video (61-76): frame_timestamp = timestamp + tick_offset; a frame that ends before the video
+ *     clock is dropped, else its duration becomes end - video clock;  EncodeStream::barrier (78-84): a gap up to the
+ *     tick's timestamp is filled with the blank frame;  encode_video (86-100): pts = round_to_base(start),
+ *     duration = round_to_base(end) - pts in `time_base` units; VideoCtx::send_frame (279-287): the picture is
+ *     letterbox-scaled to the monitor's size (DynamicScaler) -- on the device, one launch per geometry per call:
+ *     what AvcEncoder::send_frame is called with.
+ * The reference drops a tick when its 2-deep channel to the codec thread is full (monitor.rs:162-172): timing
+ * dependent, not mirrored -- every tick is processed.
+ * mxl_monitor_recv_audio / _video pop the two feeds in order; each returns 1 if it wrote an entry, 0 if none is
+ * pending, negative on error.  recv_audio waits for the download that carries the fragment. */
+typedef struct mxl_monitor_params { uint32_t width, height; int64_t time_base; } mxl_monitor_params;   /* 560 x 350, SAMPLE_RATE (monitor.rs:21-22,193-196) */
+typedef struct mxl_audio_fragment {
+    int64_t decode_num, decode_den;        /* AudioSegment.decode_timestamp */
+    int64_t duration_num, duration_den;    /* AudioSegment.duration = 1024 / sample_rate */
+    uint32_t n_samples, _pad;              /* interleaved i16 written: 2 * 1024 */
+} mxl_audio_fragment;
+typedef struct mxl_video_job {
+    int64_t pts;                           /* frame.set_presentation_timestamp(frame_start_in_base) */
+    int64_t duration;                      /* duration_in_base */
+    int64_t time_base;
+    int32_t blank, _pad;                   /* 1 = VideoCtx::blank_frame() filling a gap */
+    mxl_frame *frame;                      /* monitor-sized picture, one reference owned by the caller */
+} mxl_video_job;
+MXL_API int mxl_monitor_recv_audio(mxl_module *m, mxl_audio_fragment *info, int16_t *pcm, uint32_t cap_samples);
+MXL_API int mxl_monitor_recv_video(mxl_module *m, mxl_video_job *out);
 
 /* Stand-alone PCM converters on raw device memory of the context (N2/N3 rows of SURVEY §8f):
  * i16 -> f32 `sample / 32768.0` (stream_input.rs:167-173) and the pack above. */

@@ -94,6 +94,20 @@ class StageInfo(C.Structure):
                 ("last_ms", C.c_float), ("algorithmic_bytes", C.c_uint64), ("host_us", C.c_float), ("_pad", C.c_float)]
 
 
+class MonitorParams(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("time_base", C.c_int64)]
+
+
+class AudioFragment(C.Structure):
+    _fields_ = [("decode_num", C.c_int64), ("decode_den", C.c_int64), ("duration_num", C.c_int64),
+                ("duration_den", C.c_int64), ("n_samples", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class VideoJob(C.Structure):
+    _fields_ = [("pts", C.c_int64), ("duration", C.c_int64), ("time_base", C.c_int64), ("blank", C.c_int32),
+                ("_pad", C.c_int32), ("frame", C.c_void_p)]
+
+
 class HostRef(C.Structure):
     """mxl_host_ref: one InputRef / OutputRef of the reference with host slices (io.rs:19-34,79-98)."""
     _fields_ = [("type", C.c_int32), ("connected", C.c_int32), ("samples", C.c_void_p), ("len", C.c_uint64),
@@ -107,7 +121,7 @@ METER_RECORD = np.dtype([("peak", np.float32, 2), ("clip", np.int32), ("_pad", n
 _PARAM_TYPES = {
     MOD_AMPLIFIER: AmplifierParams, MOD_ENVELOPE: EnvelopeParams, MOD_EQ_THREE: EqThreeParams,
     MOD_FM_SINE: FmSineParams, MOD_MIXER: MixerParams, MOD_OSCILLATOR: OscillatorParams,
-    MOD_TRIGGER: TriggerParams, MOD_VIDEO_MIXER: VideoMixerParams,
+    MOD_TRIGGER: TriggerParams, MOD_VIDEO_MIXER: VideoMixerParams, MOD_MONITOR: MonitorParams,
 }
 
 _lib = None
@@ -206,6 +220,8 @@ def lib():
         "mxl_stream_input_write_audio": (i32, [vp, u64, C.c_int64, C.c_int64, vp, u64]),
         "mxl_stream_input_write_video": (i32, [vp, u64, C.c_int64, C.c_int64, vp, C.c_int64, C.c_int64]),
         "mxl_stream_input_pending": (i32, [vp, C.POINTER(u32), C.POINTER(u32)]),
+        "mxl_monitor_recv_audio": (i32, [vp, C.POINTER(AudioFragment), vp, u32]),
+        "mxl_monitor_recv_video": (i32, [vp, C.POINTER(VideoJob)]),
         "mxl_video_line_get_timing": (i32, [vp, u32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
         "mxl_eq_three_state": (i32, [vp, C.POINTER(dbl)]),
         "mxl_envelope_state": (i32, [vp, C.POINTER(C.c_int32), C.POINTER(u64), C.POINTER(dbl)]),
@@ -785,6 +801,21 @@ class Module:
         a, v = C.c_uint32(), C.c_uint32()
         check(lib().mxl_stream_input_pending(self.h, C.byref(a), C.byref(v)))
         return a.value, v.value
+
+    # Monitor: what the encoders are fed (AudioCtx::send_audio -> aac encode, VideoCtx::send_frame -> x264)
+    def monitor_recv_audio(self):
+        """None, or (decode_timestamp (num, den), duration (num, den), int16 fragment)."""
+        info, buf = AudioFragment(), np.empty(2048, np.int16)
+        if check(lib().mxl_monitor_recv_audio(self.h, C.byref(info), _ptr(buf), buf.size)) == 0:
+            return None
+        return (info.decode_num, info.decode_den), (info.duration_num, info.duration_den), buf[:info.n_samples]
+
+    def monitor_recv_video(self):
+        """None, or (pts, duration, time_base, blank, Frame owned by the caller)."""
+        job = VideoJob()
+        if check(lib().mxl_monitor_recv_video(self.h, C.byref(job))) == 0:
+            return None
+        return job.pts, job.duration, job.time_base, bool(job.blank), Frame(self.ctx, handle=job.frame)
 
     # kind-specific read-backs
     def eq_three_state(self):

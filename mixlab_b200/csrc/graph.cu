@@ -294,15 +294,18 @@ int mxl_graph_run_ticks(mxl_graph* g, uint64_t tick0, uint32_t n_ticks)
     struct EndGuard { mxl_ctx* c; ~EndGuard() { c->compute_end(); } } end_guard{ctx};
 
     // fork: audio stages -> aux stream when the graph also has video stages to overlap them with
-    bool has_audio = false, has_video = false;
+    // (modules with terminals of both kinds -- StreamInput, Monitor -- tie the two sub-graphs together: one stream then)
+    bool has_audio = false, has_video = false, has_mixed = false;
     for (const Stage& s : g->stages) {
         if (is_source(s.kind)) continue;
-        if (s.kind == MXL_MOD_VIDEO_MIXER) has_video = true; else has_audio = true;
+        if (s.kind == MXL_MOD_STREAM_INPUT || s.kind == MXL_MOD_MONITOR) has_mixed = true;
+        else if (s.kind == MXL_MOD_VIDEO_MIXER) has_video = true;
+        else has_audio = true;
     }
     // measured on a one-tick live call (the worst case for the fork/join's four API calls): 26.4 us per tick with
     // the split, 29.2 us without -- the overlap of the audio chain with the compositor still pays
     static const uint32_t split_min_ticks = getenv("MXL_SPLIT_MIN_TICKS") ? (uint32_t)atoi(getenv("MXL_SPLIT_MIN_TICKS")) : 1u;
-    const bool split = g->split_streams && has_audio && has_video && n_ticks >= split_min_ticks && !getenv("MXL_NO_STREAM_SPLIT");
+    const bool split = g->split_streams && has_audio && has_video && !has_mixed && n_ticks >= split_min_ticks && !getenv("MXL_NO_STREAM_SPLIT");
     cudaStream_t main_stream = ctx->stream;
     struct StreamGuard { mxl_ctx* c; cudaStream_t s; ~StreamGuard() { c->stream = s; } } stream_guard{ctx, main_stream};
     if (split) {

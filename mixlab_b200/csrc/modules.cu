@@ -286,6 +286,49 @@ struct StreamInput : mxl_module {
     int run(uint64_t t0, const IoSet& io, uint64_t* bytes);
 };
 
+// ---- Monitor: src/module/monitor.rs + EncodeStream (src/video/encode.rs) ------------------------------
+struct Monitor : mxl_module {
+    static constexpr uint64_t kFragmentSamples = 2 * 1024;         // AUDIO_CHANNELS * SAMPLES_PER_CHANNEL_PER_FRAGMENT (encode.rs:20-22,197)
+    mxl_monitor_params p{560, 350, 0};                             // monitor.rs:21-22; time_base 0 = the context's sample rate
+    bool has_epoch = false;                                        // self.epoch (monitor.rs:119)
+    Rational epoch;
+    Rational audio_timestamp, video_timestamp;                     // EncodeStream::new: MediaTime::new(0, 1)
+    uint64_t pcm_len = 0;                                          // AudioCtx::pcm_buff.len()
+    // the packed i16 stream, one pinned chunk per call, in order; fragments are consecutive windows of it
+    struct Chunk { int16_t* host = nullptr; size_t cap = 0, n = 0; cudaEvent_t ev = nullptr; bool in_flight = false; };
+    std::deque<Chunk> chunks;
+    size_t chunk_head = 0;                                         // samples of chunks.front() already handed out
+    std::vector<Chunk> free_chunks;
+    struct Fragment { Rational decode_timestamp, duration; };
+    std::deque<Fragment> audio_segments;
+    struct Job { int64_t pts, duration; bool blank; mxl_frame* frame; };
+    std::deque<Job> video_jobs;
+    mxl_frame* blank = nullptr;                                    // VideoCtx::blank_frame (encode.rs:275)
+    DevBuf pcm;
+
+    Monitor(const mxl_monitor_params* in)
+    {
+        kind = MXL_MOD_MONITOR;
+        if (in) p = *in;
+        inputs = {labeled(MXL_LINE_VIDEO, "Video"), labeled(MXL_LINE_STEREO, "Audio")};   // monitor.rs:97-100
+    }
+    ~Monitor() override
+    {
+        if (ctx && ctx->has_device()) { ctx->activate(); cudaStreamSynchronize(ctx->stream); }
+        for (auto& j : video_jobs) frame_release(j.frame);
+        frame_release(blank);
+        for (auto& c : chunks) { if (c.host) cudaFreeHost(c.host); if (c.ev) cudaEventDestroy(c.ev); }
+        for (auto& c : free_chunks) { if (c.host) cudaFreeHost(c.host); if (c.ev) cudaEventDestroy(c.ev); }
+        pcm.release(ctx);
+    }
+    int update(const void*) override { return MXL_OK; }            // Params = () (monitor.rs:105-111)
+    int get_params(void* out) const override { if (out) *(mxl_monitor_params*)out = p; return MXL_OK; }
+    int64_t time_base() const { return p.time_base ? p.time_base : (int64_t)ctx->sample_rate; }
+    int chunk_for(size_t samples, Chunk* out);
+    void encode_video(Rational duration, mxl_frame* frame, bool is_blank);
+    int run(uint64_t t0, const IoSet& io, uint64_t* bytes);
+};
+
 // ---- VideoMixer: src/module/video_mixer.rs ---------------------------------------------------------
 struct PictureSettings { uint32_t w = 0, h = 0; bool operator==(const PictureSettings& o) const { return w == o.w && h == o.h; } bool operator!=(const PictureSettings& o) const { return !(*this == o); } };
 
@@ -345,6 +388,7 @@ const char* mxl_module::kind_name() const
     case MXL_MOD_SOURCE_STEREO: return "SourceStereo";
     case MXL_MOD_SOURCE_VIDEO: return "SourceVideo";
     case MXL_MOD_STREAM_INPUT: return "StreamInput";
+    case MXL_MOD_MONITOR: return "Monitor";
     case MXL_MOD_PCM_SINK: return "PcmSink";
     default: return "?";
     }
@@ -374,7 +418,8 @@ mxl_module* module_create(mxl_ctx* ctx, int kind, const void* params)
     case MXL_MOD_SOURCE_VIDEO: m = new Source(kind, MXL_LINE_VIDEO); break;
     case MXL_MOD_PCM_SINK: m = new PcmSink(); break;
     case MXL_MOD_STREAM_INPUT: m = new StreamInput(); break;
-    case MXL_MOD_MONITOR: case MXL_MOD_OUTPUT_DEVICE:
+    case MXL_MOD_MONITOR: m = new Monitor((const mxl_monitor_params*)params); break;
+    case MXL_MOD_OUTPUT_DEVICE:
     case MXL_MOD_STREAM_OUTPUT: case MXL_MOD_MEDIA_SOURCE:
         set_error("module kind %d is an I/O edge that stays in the host application (out of scope of the tick hot path)", kind);
         return nullptr;
@@ -1123,6 +1168,180 @@ int stream_input_pending(const mxl_module* m, uint32_t* audio_frames, uint32_t* 
 }
 
 // ================================================================================================
+// Monitor::run_tick (monitor.rs:112-140), the codec thread's loop body (235-247) and EncodeStream
+// (src/video/encode.rs:46-100) up to the encoder calls
+// ================================================================================================
+static int64_t round_to_base(const Rational& r, int64_t base)     // MediaTime::round_to_base (util/src/time.rs:17-19)
+{
+    return (int64_t)(((__int128)r.num * base) / r.den);            // Ratio * base, to_integer(): toward zero
+}
+
+int Monitor::chunk_for(size_t samples, Chunk* out)
+{
+    Chunk c;
+    for (size_t i = 0; i < free_chunks.size(); i++)
+        if (free_chunks[i].cap >= samples) { c = free_chunks[i]; free_chunks.erase(free_chunks.begin() + i); break; }
+    if (!c.host) {
+        if (!free_chunks.empty()) {                                // too small: replace the oldest spare
+            Chunk old = free_chunks.front();
+            free_chunks.erase(free_chunks.begin());
+            cudaFreeHost(old.host);
+            c.ev = old.ev;
+        }
+        const size_t want = samples + samples / 4 + 64;
+        MXL_CUDA(cudaMallocHost(&c.host, want * sizeof(int16_t)));
+        c.cap = want;
+        if (!c.ev) MXL_CUDA(cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming));
+    }
+    c.n = samples;
+    c.in_flight = false;
+    *out = c;
+    return MXL_OK;
+}
+
+// EncodeStream::encode_video (encode.rs:86-100) up to video_ctx.send_frame's scaler (done for the whole call at once)
+void Monitor::encode_video(Rational duration, mxl_frame* frame, bool is_blank)
+{
+    const int64_t tb = time_base();
+    const Rational start = video_timestamp, end = video_timestamp + duration;
+    video_timestamp = end;
+    const int64_t start_in_base = round_to_base(start, tb), end_in_base = round_to_base(end, tb);
+    video_jobs.push_back(Job{start_in_base, end_in_base - start_in_base, is_blank, frame_retain(frame)});
+}
+
+int Monitor::run(uint64_t t0, const IoSet& io, uint64_t* bytes)
+{
+    NEED_IO(io, 2, 0, "Monitor");
+    MXL_TRY(expect_input(io.in[0], MXL_LINE_VIDEO, "Monitor.Video"));
+    MXL_TRY(expect_input(io.in[1], MXL_LINE_STEREO, "Monitor.Audio"));
+    const mxl_line* video = io.in[0];
+    const mxl_line* audio = io.in[1];
+    // ticks of the call: the video line's slots, else the audio line in ticks of SAMPLES_PER_TICK, else one
+    // (a disconnected input is the engine's static buffer of one tick, io.rs:8-9)
+    uint64_t ticks = 1;
+    if (video) ticks = video->slots.size();
+    else if (audio) ticks = std::max<uint64_t>(1, (audio->frames + ctx->spt - 1) / ctx->spt);
+    if (ticks == 0) return MXL_OK;
+    const uint64_t total = audio ? audio->len() : 2ull * ctx->spt * ticks;
+    if (total % ticks) MXL_FAIL(MXL_ERR_LENGTH, "Monitor: %llu samples do not divide into %llu ticks", (unsigned long long)total, (unsigned long long)ticks);
+    const uint64_t len_tick = total / ticks;                          // audio.len()
+    const int64_t sr = (int64_t)ctx->sample_rate;
+    if (!blank) {
+        blank = mxl_frame_blank(ctx, p.width, p.height);
+        if (!blank) return MXL_ERR_OOM;
+    }
+
+    // ---- audio: the whole call packed in one launch, downloaded into one pinned chunk ----
+    if (total) {
+        Chunk c;
+        MXL_TRY(chunk_for(total, &c));
+        if (audio) {
+            MXL_TRY(pcm.ensure(ctx, total * sizeof(int16_t)));
+            MXL_TRY(k::launch_pcm_pack(ctx, audio->dev, (int16_t*)pcm.p, total));
+            MXL_CUDA(cudaMemcpyAsync(c.host, pcm.p, total * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+            MXL_CUDA(cudaEventRecord(c.ev, ctx->stream));
+            c.in_flight = true;
+            ctx->d2h_bytes += total * sizeof(int16_t);
+            if (bytes) *bytes += 6 * total;
+        } else {
+            memset(c.host, 0, total * sizeof(int16_t));               // (0.0 * 32767) as i16
+        }
+        chunks.push_back(c);
+    }
+
+    const size_t first_job = video_jobs.size();
+    for (uint64_t kk = 0; kk < ticks; kk++) {
+        const Rational absolute = Rational::make((int64_t)(t0 + kk * (len_tick / 2)), sr);             // monitor.rs:118
+        if (!has_epoch) { has_epoch = true; epoch = absolute; }                                         // 119 get_or_insert
+        const Rational timestamp = absolute - epoch;                                                    // 120
+        // encode.send_audio(&tick.audio) (monitor.rs:236; encode.rs:46-59,184-221): one fragment at most per tick
+        pcm_len += len_tick;
+        if (pcm_len > kFragmentSamples) {
+            const Rational duration = Rational::make(1024, sr);
+            audio_segments.push_back(Fragment{audio_timestamp, duration});
+            audio_timestamp = audio_timestamp + duration;
+            pcm_len -= kFragmentSamples;
+        }
+        // monitor.rs:238-243
+        if (video && video->slots[kk].frame) {
+            const VideoSlot& vs = video->slots[kk];
+            const Rational frame_timestamp = timestamp + vs.tick_offset;
+            const Rational end_timestamp = frame_timestamp + vs.duration_hint;                          // encode.rs:62
+            if (end_timestamp >= video_timestamp)                                                       // 64-67: ends before the clock -> dropped
+                encode_video(end_timestamp - video_timestamp, vs.frame, false);                         // 73-75
+        }
+        if (timestamp > video_timestamp) encode_video(timestamp - video_timestamp, blank, true);       // 245; encode.rs:78-84
+    }
+
+    // ---- VideoCtx::send_frame's scaler (encode.rs:279-287) for the jobs of this call, one launch per geometry ----
+    std::vector<size_t> todo;
+    for (size_t j = first_job; j < video_jobs.size(); j++) {
+        const mxl_frame_layout& l = video_jobs[j].frame->layout;
+        if (!video_jobs[j].blank && (l.width != p.width || l.height != p.height)) todo.push_back(j);
+    }
+    while (!todo.empty()) {
+        const mxl_frame_layout l0 = video_jobs[todo[0]].frame->layout;
+        std::vector<size_t> grp, rest;
+        for (size_t j : todo) {
+            const mxl_frame_layout& l = video_jobs[j].frame->layout;
+            (l.width == l0.width && l.height == l0.height ? grp : rest).push_back(j);
+        }
+        std::vector<mxl_frame*> src(grp.size()), dst(grp.size(), nullptr);
+        for (size_t i = 0; i < grp.size(); i++) src[i] = video_jobs[grp[i]].frame;
+        MXL_TRY(frames_scale(ctx, src.data(), dst.data(), (uint32_t)grp.size(), p.width, p.height));
+        for (size_t i = 0; i < grp.size(); i++) {
+            frame_release(video_jobs[grp[i]].frame);
+            video_jobs[grp[i]].frame = dst[i];
+        }
+        todo.swap(rest);
+    }
+    return MXL_OK;
+}
+
+int monitor_recv_audio(mxl_module* m, mxl_audio_fragment* info, int16_t* pcm_out, uint32_t cap)
+{
+    if (!m || m->kind != MXL_MOD_MONITOR) MXL_FAIL(MXL_ERR_PARAMS, "not a Monitor module");
+    Monitor* mo = (Monitor*)m;
+    if (mo->audio_segments.empty()) return 0;
+    if (!info || !pcm_out || cap < Monitor::kFragmentSamples) MXL_FAIL(MXL_ERR_INVALID, "mxl_monitor_recv_audio: room for %llu samples needed", (unsigned long long)Monitor::kFragmentSamples);
+    const Monitor::Fragment f = mo->audio_segments.front();
+    mo->audio_segments.pop_front();
+    uint64_t need = Monitor::kFragmentSamples;
+    int16_t* out = pcm_out;
+    while (need > 0) {
+        if (mo->chunks.empty()) MXL_FAIL(MXL_ERR_INVALID, "Monitor: PCM stream shorter than its fragments (internal)");
+        Monitor::Chunk& c = mo->chunks.front();
+        if (c.in_flight) { MXL_TRY(m->ctx->activate()); MXL_CUDA(cudaEventSynchronize(c.ev)); c.in_flight = false; }
+        const uint64_t take = std::min<uint64_t>(need, c.n - mo->chunk_head);
+        memcpy(out, c.host + mo->chunk_head, take * sizeof(int16_t));
+        out += take; need -= take; mo->chunk_head += take;
+        if (mo->chunk_head == c.n) {
+            mo->free_chunks.push_back(c);
+            mo->chunks.pop_front();
+            mo->chunk_head = 0;
+        }
+    }
+    info->decode_num = f.decode_timestamp.num; info->decode_den = f.decode_timestamp.den;
+    info->duration_num = f.duration.num; info->duration_den = f.duration.den;
+    info->n_samples = (uint32_t)Monitor::kFragmentSamples; info->_pad = 0;
+    return 1;
+}
+
+int monitor_recv_video(mxl_module* m, mxl_video_job* out)
+{
+    if (!m || m->kind != MXL_MOD_MONITOR) MXL_FAIL(MXL_ERR_PARAMS, "not a Monitor module");
+    Monitor* mo = (Monitor*)m;
+    if (mo->video_jobs.empty()) return 0;
+    if (!out) MXL_FAIL(MXL_ERR_INVALID, "NULL job");
+    const Monitor::Job j = mo->video_jobs.front();
+    mo->video_jobs.pop_front();
+    out->pts = j.pts; out->duration = j.duration; out->time_base = mo->time_base();
+    out->blank = j.blank ? 1 : 0; out->_pad = 0;
+    out->frame = j.frame;                                             // the queue's reference passes to the caller
+    return 1;
+}
+
+// ================================================================================================
 // VideoMixer: src/module/video_mixer.rs:70-250
 // ================================================================================================
 
@@ -1475,6 +1694,13 @@ int run_batch(mxl_ctx* ctx, int kind, mxl_module* const* mods, int n, uint64_t t
     case MXL_MOD_METER: return run_meters(ctx, mods, n, io, bytes);
     case MXL_MOD_PLOTTER: return run_plotters(ctx, mods, n, io, bytes);
     case MXL_MOD_PCM_SINK: return run_pcm_sinks(ctx, mods, n, io, bytes);
+    case MXL_MOD_MONITOR:
+        for (int i = 0; i < n; i++) {
+            uint64_t b = 0;
+            MXL_TRY(((Monitor*)mods[i])->run(t, io[i], &b));
+            if (bytes) *bytes += b;
+        }
+        return MXL_OK;
     case MXL_MOD_STREAM_INPUT:
         for (int i = 0; i < n; i++) {
             uint64_t b = 0;

@@ -67,6 +67,8 @@ int pcm_sink_download(mxl_module* m, int16_t* host, uint64_t n);
 int stream_input_write_audio(mxl_module* m, uint64_t source_id, Rational time, const int16_t* samples, uint64_t n);
 int stream_input_write_video(mxl_module* m, uint64_t source_id, Rational time, mxl_frame* frame, Rational duration);
 int stream_input_pending(const mxl_module* m, uint32_t* audio_frames, uint32_t* video_frames);
+int monitor_recv_audio(mxl_module* m, mxl_audio_fragment* info, int16_t* pcm, uint32_t cap);
+int monitor_recv_video(mxl_module* m, mxl_video_job* out);
 int mixer_params_get(const mxl_module* m, mxl_mixer_channel_params* out, uint32_t cap);
 
 mxl_frame* frame_scale(mxl_frame* src, uint32_t out_w, uint32_t out_h);

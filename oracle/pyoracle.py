@@ -334,6 +334,88 @@ def bicubic_plane(src, sw, sh, sstride, dw, dh, dstride):
     return dst
 
 
+def letterbox_scale(data, lay_in, out_w, out_h):
+    """DynamicScaler::scale (src/video/encode.rs:338-397) from the pieces above: identity when the sizes agree,
+    else a blank target and a per-plane resample into the letterboxed sub-frame."""
+    if (lay_in.width, lay_in.height) == (out_w, out_h):
+        return np.array(data, np.uint8)
+    sw_, sh_, lx, ly = scale_geometry(lay_in.width, lay_in.height, out_w, out_h)
+    lay = frame_layout(out_w, out_h)
+    want = frame_blank(lay)
+    for p in range(3):
+        sh = 0 if p == 0 else 1
+        sw = lay_in.width if p == 0 else (lay_in.width + 1) // 2
+        shh = lay_in.plane_h[p]
+        dw, dh = sw_ >> sh, sh_ >> sh
+        if dw == 0 or dh == 0:
+            continue
+        src = data[lay_in.offset[p]:lay_in.offset[p] + lay_in.stride[p] * lay_in.plane_h[p]]
+        dst = bicubic_plane(src, sw, shh, lay_in.stride[p], dw, dh, dw)
+        plane = want[lay.offset[p]:lay.offset[p] + lay.stride[p] * lay.plane_h[p]].reshape(lay.plane_h[p], lay.stride[p])
+        plane[(ly >> sh):(ly >> sh) + dh, (lx >> sh):(lx >> sh) + dw] = dst.reshape(dh, dw)
+    return want
+
+
+class MonitorFeed:
+    """Monitor::run_tick (src/module/monitor.rs:112-140), the codec thread's loop body (235-247) and EncodeStream
+    (src/video/encode.rs:34-107) with AudioCtx::send_audio (184-221) and VideoCtx::send_frame (279-287), up to
+    the two encoder calls.  Collects what aac::Encoder::encode and AvcEncoder::send_frame would be called with."""
+    FRAGMENT = 2 * 1024                      # AUDIO_CHANNELS * SAMPLES_PER_CHANNEL_PER_FRAGMENT (encode.rs:20-22)
+
+    def __init__(self, sample_rate, width=560, height=350, time_base=None):
+        from fractions import Fraction
+        self.F = Fraction
+        self.sample_rate = int(sample_rate)
+        self.width, self.height = width, height                     # monitor.rs:21-22
+        self.time_base = int(time_base if time_base is not None else sample_rate)   # monitor.rs:195
+        self.epoch = None
+        self.audio_timestamp = Fraction(0)                           # EncodeStream::new (encode.rs:36-44)
+        self.video_timestamp = Fraction(0)
+        self.pcm_buff = np.empty(0, np.int16)
+        self.audio_out = []                  # (decode_timestamp, duration, fragment i16)
+        self.video_out = []                  # (pts, duration_in_base, blank?, picture bytes)
+        self.blank = frame_blank(frame_layout(width, height))        # VideoCtx::new (encode.rs:273-276)
+
+    @staticmethod
+    def _round_to_base(x, base):             # util/src/time.rs:17-19: (ratio * base).to_integer(), toward zero
+        y = x * base
+        n, d = y.numerator, y.denominator
+        return n // d if n >= 0 else -((-n) // d)
+
+    def _encode_video(self, duration, picture, blank):               # encode.rs:86-100
+        start = self.video_timestamp
+        end = start + duration
+        self.video_timestamp = end
+        s, e = self._round_to_base(start, self.time_base), self._round_to_base(end, self.time_base)
+        self.video_out.append((s, e - s, blank, picture))
+
+    def run_tick(self, time, audio, video):
+        """time: absolute sample index; audio: the tick's stereo f32; video: None or
+        (data, layout, duration_hint, tick_offset) with Fractions."""
+        F = self.F
+        absolute = F(int(time), self.sample_rate)                    # monitor.rs:118
+        if self.epoch is None:
+            self.epoch = absolute                                    # 119
+        timestamp = absolute - self.epoch                            # 120
+        # encode.send_audio (monitor.rs:236 -> encode.rs:46-59 -> 184-221)
+        self.pcm_buff = np.concatenate([self.pcm_buff, pcm_pack_i16(audio)])
+        if self.pcm_buff.size > self.FRAGMENT:
+            frag = self.pcm_buff[:self.FRAGMENT].copy()
+            duration = F(1024, self.sample_rate)
+            self.pcm_buff = self.pcm_buff[self.FRAGMENT:]
+            self.audio_out.append((self.audio_timestamp, duration, frag))
+            self.audio_timestamp += duration
+        if video is not None:                                        # monitor.rs:238-243
+            data, lay, duration_hint, tick_offset = video
+            frame_timestamp = timestamp + tick_offset
+            end_timestamp = frame_timestamp + duration_hint          # encode.rs:62
+            if not (end_timestamp < self.video_timestamp):           # 64-67
+                self._encode_video(end_timestamp - self.video_timestamp,
+                                   letterbox_scale(data, lay, self.width, self.height), False)   # 73-75; 279-287
+        if self.video_timestamp < timestamp:                         # barrier (monitor.rs:245; encode.rs:78-84)
+            self._encode_video(timestamp - self.video_timestamp, self.blank, True)
+
+
 class Graph:
     """Engine::run_tick walker (engine.rs:400-510) over oracle modules."""
 

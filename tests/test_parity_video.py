@@ -167,23 +167,7 @@ def test_mixed_sizes_letterbox_geometry(mxl, oracle, ctx48):
 
 
 def oracle_scale(oracle, data, lay_in, out_w, out_h):
-    """DynamicScaler::scale (encode.rs:338-397) from oracle pieces: blank target, per-plane resample into
-    the letterboxed sub-frame."""
-    sw_, sh_, lx, ly = oracle.scale_geometry(lay_in.width, lay_in.height, out_w, out_h)
-    lay = oracle.frame_layout(out_w, out_h)
-    want = oracle.frame_blank(lay)
-    for p in range(3):
-        sh = 0 if p == 0 else 1
-        sw = lay_in.width if p == 0 else (lay_in.width + 1) // 2
-        shh = lay_in.plane_h[p]
-        dw, dh = sw_ >> sh, sh_ >> sh
-        if dw == 0 or dh == 0:
-            continue
-        src = data[lay_in.offset[p]:lay_in.offset[p] + lay_in.stride[p] * lay_in.plane_h[p]]
-        dst = oracle.bicubic_plane(src, sw, shh, lay_in.stride[p], dw, dh, dw)
-        plane = want[lay.offset[p]:lay.offset[p] + lay.stride[p] * lay.plane_h[p]].reshape(lay.plane_h[p], lay.stride[p])
-        plane[(ly >> sh):(ly >> sh) + dh, (lx >> sh):(lx >> sh) + dw] = dst.reshape(dh, dw)
-    return want
+    return oracle.letterbox_scale(data, lay_in, out_w, out_h)
 
 
 @pytest.mark.parametrize("src,dst", [((640, 480), (1280, 720)), ((1920, 1080), (1280, 720)), ((1280, 720), (1920, 1080)),
