@@ -2,6 +2,7 @@
 (terminals, Workspace::connect, run-order planning, picture geometry) agrees with the reference text
 and with the oracle.  No compute entry point is called: they must report MXL_ERR_NO_DEVICE."""
 import ctypes as C
+import os
 import subprocess
 
 import numpy as np
@@ -85,6 +86,19 @@ def test_terminals_match_the_reference(mxl, host_ctx):
     assert mix.outputs() == [("Master", S), ("Cue", S)]                                  # mixer.rs:26-29
     mix.update([(-3.0, 0.5, True)] * 2)                                                  # update re-creates (mixer.rs:40-44)
     assert len(mix.inputs()) == 2 and mix.params() == [(-3.0, 0.5, True)] * 2
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/mixlab_b200.h must compile as C99 on its own (cgo / bindgen / cffi read it so)."""
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "mixlab_b200.h"\n'
+                   'int probe(void) { mxl_host_ref r; mxl_stage_info s; mxl_video_job j; mxl_audio_fragment f;\n'
+                   '  r.len = 0; s.host_us = 0; j.pts = 0; f.n_samples = 0;\n'
+                   '  return (int)sizeof(mxl_frame_layout) + (int)r.len + (int)s.host_us + (int)j.pts + (int)f.n_samples + MXL_MOD_MONITOR; }\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", inc, "-c", str(src), "-o", str(tmp_path / "use_header.o")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
 
 
 def test_io_edge_kinds_are_not_provided(mxl, host_ctx):
