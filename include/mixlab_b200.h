@@ -84,7 +84,8 @@ typedef enum mxl_module_kind {
     MXL_MOD_STREAM_INPUT = 11,    /* run_tick provided (queue assembly + gating, stream_input.rs:72-147); the
                                    * RTMP / Icecast receivers that feed it stay in the host application and push
                                    * with mxl_stream_input_write_audio / _write_video */
-    MXL_MOD_STREAM_OUTPUT = 12,   /* (io) not provided */
+    MXL_MOD_STREAM_OUTPUT = 12,   /* the Monitor feed at 1120 x 700 while the host reports the RTMP connection Live
+                                   * (mxl_stream_output_set_live); the publisher stays in the host application */
     MXL_MOD_TRIGGER = 13,
     MXL_MOD_VIDEO_MIXER = 14,
     MXL_MOD_MEDIA_SOURCE = 15,    /* (io) not provided */
@@ -363,6 +364,11 @@ typedef struct mxl_video_job {
 } mxl_video_job;
 MXL_API int mxl_monitor_recv_audio(mxl_module *m, mxl_audio_fragment *info, int16_t *pcm, uint32_t cap_samples);
 MXL_API int mxl_monitor_recv_video(mxl_module *m, mxl_video_job *out);
+/* StreamOutput (src/module/stream_output.rs): the same two feeds (LiveOutput::tick, 369-381) at 1120 x 700 (13-14),
+ * read with mxl_monitor_recv_*.  The RTMP connection state machine lives in the host application; it reports
+ * Connection::Live with live = 1 (a new EncodeStream; the next tick is the epoch, 126,328-366) and anything else
+ * with live = 0 (run_tick sends nothing, 112-151).  Created Offline. */
+MXL_API int mxl_stream_output_set_live(mxl_module *m, int live);
 
 /* Stand-alone PCM converters on raw device memory of the context (N2/N3 rows of SURVEY §8f):
  * i16 -> f32 `sample / 32768.0` (stream_input.rs:167-173) and the pack above. */

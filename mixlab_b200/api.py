@@ -122,6 +122,7 @@ _PARAM_TYPES = {
     MOD_AMPLIFIER: AmplifierParams, MOD_ENVELOPE: EnvelopeParams, MOD_EQ_THREE: EqThreeParams,
     MOD_FM_SINE: FmSineParams, MOD_MIXER: MixerParams, MOD_OSCILLATOR: OscillatorParams,
     MOD_TRIGGER: TriggerParams, MOD_VIDEO_MIXER: VideoMixerParams, MOD_MONITOR: MonitorParams,
+    MOD_STREAM_OUTPUT: MonitorParams,
 }
 
 _lib = None
@@ -222,6 +223,7 @@ def lib():
         "mxl_stream_input_pending": (i32, [vp, C.POINTER(u32), C.POINTER(u32)]),
         "mxl_monitor_recv_audio": (i32, [vp, C.POINTER(AudioFragment), vp, u32]),
         "mxl_monitor_recv_video": (i32, [vp, C.POINTER(VideoJob)]),
+        "mxl_stream_output_set_live": (i32, [vp, i32]),
         "mxl_video_line_get_timing": (i32, [vp, u32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
         "mxl_eq_three_state": (i32, [vp, C.POINTER(dbl)]),
         "mxl_envelope_state": (i32, [vp, C.POINTER(C.c_int32), C.POINTER(u64), C.POINTER(dbl)]),
@@ -816,6 +818,9 @@ class Module:
         if check(lib().mxl_monitor_recv_video(self.h, C.byref(job))) == 0:
             return None
         return job.pts, job.duration, job.time_base, bool(job.blank), Frame(self.ctx, handle=job.frame)
+
+    def stream_output_set_live(self, live):
+        check(lib().mxl_stream_output_set_live(self.h, 1 if live else 0))
 
     # kind-specific read-backs
     def eq_three_state(self):

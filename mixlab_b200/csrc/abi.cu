@@ -222,6 +222,7 @@ int mxl_stream_input_write_video(mxl_module* m, uint64_t source_id, int64_t time
 int mxl_stream_input_pending(const mxl_module* m, uint32_t* audio_frames, uint32_t* video_frames) { return stream_input_pending(m, audio_frames, video_frames); }
 int mxl_monitor_recv_audio(mxl_module* m, mxl_audio_fragment* info, int16_t* pcm, uint32_t cap_samples) { return monitor_recv_audio(m, info, pcm, cap_samples); }
 int mxl_monitor_recv_video(mxl_module* m, mxl_video_job* out) { return monitor_recv_video(m, out); }
+int mxl_stream_output_set_live(mxl_module* m, int live) { return stream_output_set_live(m, live); }
 
 // Device staging for i16 PCM on its way in or out: a ring owned by the context, so the asynchronous
 // converters neither allocate nor synchronise per call.  A region is reused only after a wrap, which

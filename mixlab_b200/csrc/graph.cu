@@ -298,7 +298,7 @@ int mxl_graph_run_ticks(mxl_graph* g, uint64_t tick0, uint32_t n_ticks)
     bool has_audio = false, has_video = false, has_mixed = false;
     for (const Stage& s : g->stages) {
         if (is_source(s.kind)) continue;
-        if (s.kind == MXL_MOD_STREAM_INPUT || s.kind == MXL_MOD_MONITOR) has_mixed = true;
+        if (s.kind == MXL_MOD_STREAM_INPUT || s.kind == MXL_MOD_MONITOR || s.kind == MXL_MOD_STREAM_OUTPUT) has_mixed = true;
         else if (s.kind == MXL_MOD_VIDEO_MIXER) has_video = true;
         else has_audio = true;
     }

@@ -306,12 +306,18 @@ struct Monitor : mxl_module {
     mxl_frame* blank = nullptr;                                    // VideoCtx::blank_frame (encode.rs:275)
     DevBuf pcm;
 
-    Monitor(const mxl_monitor_params* in)
+    // StreamOutput (src/module/stream_output.rs) feeds the same EncodeStream from LiveOutput::tick (369-381) once its
+    // RTMP connection is Live: 1120 x 700 (13-14,347-351), epoch = the tick the connection completed (126,328-366).
+    // The connection itself stays in the host application, which reports it with mxl_stream_output_set_live.
+    bool live = true;
+    Monitor(int k, const mxl_monitor_params* in)
     {
-        kind = MXL_MOD_MONITOR;
+        kind = k;
+        if (k == MXL_MOD_STREAM_OUTPUT) { p.width = 1120; p.height = 700; live = false; }   // Connection::Offline (stream_output.rs:42)
         if (in) p = *in;
-        inputs = {labeled(MXL_LINE_VIDEO, "Video"), labeled(MXL_LINE_STEREO, "Audio")};   // monitor.rs:97-100
+        inputs = {labeled(MXL_LINE_VIDEO, "Video"), labeled(MXL_LINE_STEREO, "Audio")};   // monitor.rs:97-100; stream_output.rs:43-46
     }
+    void reset_stream();
     ~Monitor() override
     {
         if (ctx && ctx->has_device()) { ctx->activate(); cudaStreamSynchronize(ctx->stream); }
@@ -389,6 +395,7 @@ const char* mxl_module::kind_name() const
     case MXL_MOD_SOURCE_VIDEO: return "SourceVideo";
     case MXL_MOD_STREAM_INPUT: return "StreamInput";
     case MXL_MOD_MONITOR: return "Monitor";
+    case MXL_MOD_STREAM_OUTPUT: return "StreamOutput";
     case MXL_MOD_PCM_SINK: return "PcmSink";
     default: return "?";
     }
@@ -418,9 +425,8 @@ mxl_module* module_create(mxl_ctx* ctx, int kind, const void* params)
     case MXL_MOD_SOURCE_VIDEO: m = new Source(kind, MXL_LINE_VIDEO); break;
     case MXL_MOD_PCM_SINK: m = new PcmSink(); break;
     case MXL_MOD_STREAM_INPUT: m = new StreamInput(); break;
-    case MXL_MOD_MONITOR: m = new Monitor((const mxl_monitor_params*)params); break;
-    case MXL_MOD_OUTPUT_DEVICE:
-    case MXL_MOD_STREAM_OUTPUT: case MXL_MOD_MEDIA_SOURCE:
+    case MXL_MOD_MONITOR: case MXL_MOD_STREAM_OUTPUT: m = new Monitor(kind, (const mxl_monitor_params*)params); break;
+    case MXL_MOD_OUTPUT_DEVICE: case MXL_MOD_MEDIA_SOURCE:
         set_error("module kind %d is an I/O edge that stays in the host application (out of scope of the tick hot path)", kind);
         return nullptr;
     default:
@@ -1209,11 +1215,39 @@ void Monitor::encode_video(Rational duration, mxl_frame* frame, bool is_blank)
     video_jobs.push_back(Job{start_in_base, end_in_base - start_in_base, is_blank, frame_retain(frame)});
 }
 
+// a new LiveOutput (stream_output.rs:328-366): fresh EncodeStream, epoch taken from the next tick
+void Monitor::reset_stream()
+{
+    has_epoch = false;
+    audio_timestamp = Rational();
+    video_timestamp = Rational();
+    pcm_len = 0;
+    // what the previous stream still holds is the previous publisher's: dropped with it
+    audio_segments.clear();
+    for (auto& j : video_jobs) frame_release(j.frame);
+    video_jobs.clear();
+    if (ctx && ctx->has_device() && !chunks.empty()) { ctx->activate(); cudaStreamSynchronize(ctx->stream); }
+    for (auto& c : chunks) { c.in_flight = false; free_chunks.push_back(c); }
+    chunks.clear();
+    chunk_head = 0;
+}
+
+int stream_output_set_live(mxl_module* m, int live)
+{
+    if (!m || m->kind != MXL_MOD_STREAM_OUTPUT) MXL_FAIL(MXL_ERR_PARAMS, "not a StreamOutput module");
+    Monitor* mo = (Monitor*)m;
+    if ((live != 0) == mo->live) return MXL_OK;
+    mo->live = live != 0;
+    if (mo->live) mo->reset_stream();
+    return MXL_OK;
+}
+
 int Monitor::run(uint64_t t0, const IoSet& io, uint64_t* bytes)
 {
     NEED_IO(io, 2, 0, "Monitor");
     MXL_TRY(expect_input(io.in[0], MXL_LINE_VIDEO, "Monitor.Video"));
     MXL_TRY(expect_input(io.in[1], MXL_LINE_STEREO, "Monitor.Audio"));
+    if (!live) return MXL_OK;                                          // Connection::Offline / Failed / Connecting: nothing is sent (stream_output.rs:112-151)
     const mxl_line* video = io.in[0];
     const mxl_line* audio = io.in[1];
     // ticks of the call: the video line's slots, else the audio line in ticks of SAMPLES_PER_TICK, else one
@@ -1300,7 +1334,7 @@ int Monitor::run(uint64_t t0, const IoSet& io, uint64_t* bytes)
 
 int monitor_recv_audio(mxl_module* m, mxl_audio_fragment* info, int16_t* pcm_out, uint32_t cap)
 {
-    if (!m || m->kind != MXL_MOD_MONITOR) MXL_FAIL(MXL_ERR_PARAMS, "not a Monitor module");
+    if (!m || (m->kind != MXL_MOD_MONITOR && m->kind != MXL_MOD_STREAM_OUTPUT)) MXL_FAIL(MXL_ERR_PARAMS, "not a Monitor / StreamOutput module");
     Monitor* mo = (Monitor*)m;
     if (mo->audio_segments.empty()) return 0;
     if (!info || !pcm_out || cap < Monitor::kFragmentSamples) MXL_FAIL(MXL_ERR_INVALID, "mxl_monitor_recv_audio: room for %llu samples needed", (unsigned long long)Monitor::kFragmentSamples);
@@ -1329,7 +1363,7 @@ int monitor_recv_audio(mxl_module* m, mxl_audio_fragment* info, int16_t* pcm_out
 
 int monitor_recv_video(mxl_module* m, mxl_video_job* out)
 {
-    if (!m || m->kind != MXL_MOD_MONITOR) MXL_FAIL(MXL_ERR_PARAMS, "not a Monitor module");
+    if (!m || (m->kind != MXL_MOD_MONITOR && m->kind != MXL_MOD_STREAM_OUTPUT)) MXL_FAIL(MXL_ERR_PARAMS, "not a Monitor / StreamOutput module");
     Monitor* mo = (Monitor*)m;
     if (mo->video_jobs.empty()) return 0;
     if (!out) MXL_FAIL(MXL_ERR_INVALID, "NULL job");
@@ -1694,7 +1728,7 @@ int run_batch(mxl_ctx* ctx, int kind, mxl_module* const* mods, int n, uint64_t t
     case MXL_MOD_METER: return run_meters(ctx, mods, n, io, bytes);
     case MXL_MOD_PLOTTER: return run_plotters(ctx, mods, n, io, bytes);
     case MXL_MOD_PCM_SINK: return run_pcm_sinks(ctx, mods, n, io, bytes);
-    case MXL_MOD_MONITOR:
+    case MXL_MOD_MONITOR: case MXL_MOD_STREAM_OUTPUT:
         for (int i = 0; i < n; i++) {
             uint64_t b = 0;
             MXL_TRY(((Monitor*)mods[i])->run(t, io[i], &b));

@@ -69,6 +69,7 @@ int stream_input_write_video(mxl_module* m, uint64_t source_id, Rational time, m
 int stream_input_pending(const mxl_module* m, uint32_t* audio_frames, uint32_t* video_frames);
 int monitor_recv_audio(mxl_module* m, mxl_audio_fragment* info, int16_t* pcm, uint32_t cap);
 int monitor_recv_video(mxl_module* m, mxl_video_job* out);
+int stream_output_set_live(mxl_module* m, int live);
 int mixer_params_get(const mxl_module* m, mxl_mixer_channel_params* out, uint32_t cap);
 
 mxl_frame* frame_scale(mxl_frame* src, uint32_t out_w, uint32_t out_h);

@@ -144,3 +144,37 @@ def test_in_a_graph_behind_the_mixers(mxl, oracle, ctx48):
         orc.run_tick(k * SPT, master, (oracle.video_crossfade(lay, pix[k], None, 255), lay, Fraction(SPT, SR), Fraction(0)))
     compare(g.module(mon), orc)
     g.destroy()
+
+
+def test_stream_output_feeds_only_while_live(mxl, oracle, ctx48):
+    """StreamOutput (src/module/stream_output.rs): Offline at creation (42), nothing is sent until the connection is
+    Live (112-151); the tick the connection completes is the epoch (126); 1120 x 700 pictures (13-14); a re-connect
+    starts a new EncodeStream (328-366)."""
+    mod = ctx48.module(mxl.MOD_STREAM_OUTPUT)
+    assert mod.inputs() == [("Video", mxl.LINE_VIDEO), ("Audio", mxl.LINE_STEREO)] and mod.outputs() == []
+    p = mod.params()
+    assert (p.width, p.height) == (1120, 700)
+    lay = oracle.frame_layout(560, 350)
+    x = W.uniform_pm1(31, 2 * SPT * 12)
+    pix = {k: W.random_bytes(40 + k, lay.size) for k in (2, 5, 9)}
+
+    def tick(k):
+        vl = ctx48.video_line(1)
+        if k in pix:
+            vl.set(0, ctx48.frame(560, 350, pix[k]), duration=(1, 30))
+        mod.run_tick(k * SPT, [vl, ctx48.stereo(x[2 * SPT * k:2 * SPT * (k + 1)])], [])
+
+    for k in range(3):
+        tick(k)                                                       # Offline: nothing
+    assert drain(mod) == ([], [])
+    for start, stop in ((3, 8), (8, 12)):                            # two connections
+        mod.stream_output_set_live(True)
+        orc = oracle.MonitorFeed(SR, 1120, 700)
+        for k in range(start, stop):
+            tick(k)
+            orc.run_tick(k * SPT, x[2 * SPT * k:2 * SPT * (k + 1)],
+                         (pix[k], lay, Fraction(1, 30), Fraction(0)) if k in pix else None)
+        compare(mod, orc)
+        mod.stream_output_set_live(False)
+        tick(stop)
+        assert drain(mod) == ([], [])
