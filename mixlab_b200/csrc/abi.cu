@@ -415,7 +415,9 @@ static int compose_rgba(mxl_ctx* ctx, mxl_frame* const* a, mxl_frame* const* b, 
         for (const mxl_frame* f : {fa, fb})
             if (f && (f->ctx != ctx || f->layout.width != out->width || f->layout.height != out->height))
                 MXL_FAIL(MXL_ERR_INVALID, "compose_rgba: layer %u is %ux%u, pictures are %ux%u", i, f->layout.width, f->layout.height, out->width, out->height);
-        jobs[i] = k::ComposeRgbaJob{fa ? fa->dev : nullptr, fb ? fb->dev : nullptr, out->dev + out->picture_bytes() * (first + i), fade, 0};
+        // a layer whose weight is 0 goes to the kernel as missing (never read): (a*255 + b*0) / 255 == a
+        jobs[i] = k::ComposeRgbaJob{(fa && fade != 0) ? fa->dev : nullptr, (fb && fade != 255) ? fb->dev : nullptr,
+                                    out->dev + out->picture_bytes() * (first + i), fade, 0};
     }
     MXL_TRY(ctx->activate());
     if (out->jobs_cap < n) {

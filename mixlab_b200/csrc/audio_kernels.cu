@@ -53,6 +53,7 @@ __device__ __forceinline__ float osc_wave(double n, int wf)
 
 __global__ void __launch_bounds__(kThreads) oscillator_kernel(const __grid_constant__ OscBatch b)
 {
+    pdl_prologue();
     const OscInst& in = b.inst[blockIdx.y];
     uint64_t f0 = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
     if (f0 >= b.frames) return;
@@ -112,6 +113,7 @@ __device__ __forceinline__ float fm_sample(double seq, double sr, double inv_sr,
 
 __global__ void __launch_bounds__(kThreads) fm_sine_kernel(const __grid_constant__ FmBatch b)
 {
+    pdl_prologue();
     const FmInst& in = b.inst[blockIdx.y];
     uint64_t f0 = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
     if (f0 >= b.frames) return;
@@ -158,6 +160,7 @@ __device__ __forceinline__ float mix1(float x, double g) { return (float)((doubl
 template <int UNROLL, int CU>
 __global__ void __launch_bounds__(kThreads) mixer_kernel(const __grid_constant__ MixerLaunch p)
 {
+    pdl_prologue();
     const uint64_t n4 = p.len >> 2;
     // the UNROLL float4 of a thread are kThreads apart: every load/store instruction of a warp covers
     // 512 contiguous bytes
@@ -247,6 +250,7 @@ constexpr int kAmpUnroll = 4;
 
 __global__ void __launch_bounds__(kThreads) amplifier_kernel(const __grid_constant__ AmpBatch b)
 {
+    pdl_prologue();
     const AmpInst& in = b.inst[blockIdx.y];
     const uint64_t n4 = b.frames >> 1;                              // float4 = 2 stereo frames
     const uint64_t i0 = (uint64_t)blockIdx.x * (kThreads * kAmpUnroll) + threadIdx.x;
@@ -283,6 +287,7 @@ __global__ void __launch_bounds__(kThreads) amplifier_kernel(const __grid_consta
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) panner_kernel(const __grid_constant__ PanBatch b)
 {
+    pdl_prologue();
     const PanInst& in = b.inst[blockIdx.y];
     uint64_t f0 = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
     if (f0 >= b.frames) return;
@@ -301,6 +306,7 @@ __global__ void __launch_bounds__(kThreads) panner_kernel(const __grid_constant_
 
 __global__ void __launch_bounds__(kThreads) splitter_kernel(const __grid_constant__ SplitBatch b)
 {
+    pdl_prologue();
     const SplitInst& in = b.inst[blockIdx.y];
     uint64_t f0 = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
     if (f0 >= b.frames) return;
@@ -319,6 +325,7 @@ __global__ void __launch_bounds__(kThreads) splitter_kernel(const __grid_constan
 
 __global__ void __launch_bounds__(kThreads) fill_kernel(const __grid_constant__ FillBatch b)
 {
+    pdl_prologue();
     const FillInst& in = b.inst[blockIdx.y];
     uint64_t i0 = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
     if (i0 >= b.len) return;
@@ -339,6 +346,7 @@ constexpr int kMeterWarps = kMeterThreads / 32;
 // One block per (slot, instance); warp-shuffle tree, then one smem hop across warps.
 __global__ void __launch_bounds__(kMeterThreads) meter_block_kernel(const __grid_constant__ MeterBatch b)
 {
+    pdl_prologue();
     const MeterInst& in = b.inst[blockIdx.y];
     const uint64_t slot = blockIdx.x;
     const uint64_t f_begin = slot * b.spt;
@@ -429,6 +437,7 @@ __global__ void __launch_bounds__(kMeterThreads) meter_block_kernel(const __grid
 // once per ~3 loads and was issue-bound at 0.79 of the copy peak).  No shared memory, no barrier.
 __global__ void __launch_bounds__(kMeterThreads) meter_warp_kernel(const __grid_constant__ MeterBatch b, uint32_t n_slots)
 {
+    pdl_prologue();
     const MeterInst& in = b.inst[blockIdx.y];
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t slot = (uint64_t)blockIdx.x * kMeterWarps + (threadIdx.x >> 5);
@@ -520,6 +529,7 @@ constexpr int kPcmUnroll = 4;
 
 __global__ void __launch_bounds__(kThreads) pcm_pack_kernel(const float* __restrict__ in, short* __restrict__ out, uint64_t len)
 {
+    pdl_prologue();
     const uint64_t n4 = len >> 2;
     const uint64_t i0 = (uint64_t)blockIdx.x * (kThreads * kPcmUnroll) + threadIdx.x;
     float4 x[kPcmUnroll];
@@ -539,6 +549,7 @@ __global__ void __launch_bounds__(kThreads) pcm_pack_kernel(const float* __restr
 
 __global__ void __launch_bounds__(kThreads) pcm_unpack_kernel(const short* __restrict__ in, float* __restrict__ out, uint64_t len)
 {
+    pdl_prologue();
     const uint64_t n4 = len >> 2;
     const uint64_t i0 = (uint64_t)blockIdx.x * (kThreads * kPcmUnroll) + threadIdx.x;
     short4 x[kPcmUnroll];
@@ -589,7 +600,7 @@ int launch_oscillator(mxl_ctx* ctx, const OscBatch& b)
     if (b.n <= 0 || b.frames == 0) return MXL_OK;
     dim3 grid(blocks_for((b.frames + 3) / 4), b.n);
     MXL_TIMED(ctx, "oscillator_kernel");
-    oscillator_kernel<<<grid, kThreads, 0, ctx->stream>>>(b);
+    launch_chained(ctx, oscillator_kernel, grid, dim3(kThreads), 0, b);
     return check_launch(ctx, "oscillator_kernel");
 }
 
@@ -599,7 +610,7 @@ int launch_fm_sine(mxl_ctx* ctx, const FmBatch& b)
     if (b.n <= 0 || b.frames == 0) return MXL_OK;
     dim3 grid(blocks_for((b.frames + 3) / 4), b.n);
     MXL_TIMED(ctx, "fm_sine_kernel");
-    fm_sine_kernel<<<grid, kThreads, 0, ctx->stream>>>(b);
+    launch_chained(ctx, fm_sine_kernel, grid, dim3(kThreads), 0, b);
     return check_launch(ctx, "fm_sine_kernel");
 }
 
@@ -617,15 +628,15 @@ int launch_mixer(mxl_ctx* ctx, const MixerLaunch& p)
     if (n4 < machine && p.channels > 4) {
         unsigned g = blocks_for(n4);
         MXL_TIMED(ctx, "mixer_kernel");
-        mixer_kernel<1, 16><<<g ? g : 1, kThreads, 0, ctx->stream>>>(p);
+        launch_chained(ctx, mixer_kernel<1, 16>, dim3(g ? g : 1), dim3(kThreads), 0, p);
     } else if (unroll >= 2) {
         unsigned g = blocks_for((n4 + 1) / 2);
         MXL_TIMED(ctx, "mixer_kernel");
-        mixer_kernel<2, 4><<<g ? g : 1, kThreads, 0, ctx->stream>>>(p);
+        launch_chained(ctx, mixer_kernel<2, 4>, dim3(g ? g : 1), dim3(kThreads), 0, p);
     } else {
         unsigned g = blocks_for(n4);
         MXL_TIMED(ctx, "mixer_kernel");
-        mixer_kernel<1, 4><<<g ? g : 1, kThreads, 0, ctx->stream>>>(p);
+        launch_chained(ctx, mixer_kernel<1, 4>, dim3(g ? g : 1), dim3(kThreads), 0, p);
     }
     return check_launch(ctx, "mixer_kernel");
 }
@@ -638,7 +649,7 @@ int launch_amplifier(mxl_ctx* ctx, const AmpBatch& b)
     unsigned gx = blocks_for((n4 + kAmpUnroll - 1) / kAmpUnroll);
     dim3 grid(gx ? gx : 1, b.n);
     MXL_TIMED(ctx, "amplifier_kernel");
-    amplifier_kernel<<<grid, kThreads, 0, ctx->stream>>>(b);
+    launch_chained(ctx, amplifier_kernel, grid, dim3(kThreads), 0, b);
     return check_launch(ctx, "amplifier_kernel");
 }
 
@@ -648,7 +659,7 @@ int launch_panner(mxl_ctx* ctx, const PanBatch& b)
     if (b.n <= 0 || b.frames == 0) return MXL_OK;
     dim3 grid(blocks_for((b.frames + 3) / 4), b.n);
     MXL_TIMED(ctx, "panner_kernel");
-    panner_kernel<<<grid, kThreads, 0, ctx->stream>>>(b);
+    launch_chained(ctx, panner_kernel, grid, dim3(kThreads), 0, b);
     return check_launch(ctx, "panner_kernel");
 }
 
@@ -658,7 +669,7 @@ int launch_splitter(mxl_ctx* ctx, const SplitBatch& b)
     if (b.n <= 0 || b.frames == 0) return MXL_OK;
     dim3 grid(blocks_for((b.frames + 3) / 4), b.n);
     MXL_TIMED(ctx, "splitter_kernel");
-    splitter_kernel<<<grid, kThreads, 0, ctx->stream>>>(b);
+    launch_chained(ctx, splitter_kernel, grid, dim3(kThreads), 0, b);
     return check_launch(ctx, "splitter_kernel");
 }
 
@@ -668,7 +679,7 @@ int launch_fill(mxl_ctx* ctx, const FillBatch& b)
     if (b.n <= 0 || b.len == 0) return MXL_OK;
     dim3 grid(blocks_for((b.len + 3) / 4), b.n);
     MXL_TIMED(ctx, "fill_kernel");
-    fill_kernel<<<grid, kThreads, 0, ctx->stream>>>(b);
+    launch_chained(ctx, fill_kernel, grid, dim3(kThreads), 0, b);
     return check_launch(ctx, "fill_kernel");
 }
 
@@ -680,10 +691,10 @@ int launch_meter(mxl_ctx* ctx, const MeterBatch& b, uint32_t n_slots)
     const uint64_t machine = (uint64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148) * 16;     // warps that fill every SM's schedulers 4 deep
     if ((uint64_t)n_slots * b.n >= machine) {
         dim3 grid((n_slots + kMeterWarps - 1) / kMeterWarps, b.n);
-        meter_warp_kernel<<<grid, kMeterThreads, 0, ctx->stream>>>(b, n_slots);
+        launch_chained(ctx, meter_warp_kernel, grid, dim3(kMeterThreads), 0, b, n_slots);
     } else {
         dim3 grid(n_slots, b.n);
-        meter_block_kernel<<<grid, kMeterThreads, 0, ctx->stream>>>(b);
+        launch_chained(ctx, meter_block_kernel, grid, dim3(kMeterThreads), 0, b);
     }
     return check_launch(ctx, "meter_kernel");
 }
@@ -694,7 +705,7 @@ int launch_pcm_pack(mxl_ctx* ctx, const float* in, int16_t* out, uint64_t len)
     if (len == 0) return MXL_OK;
     const unsigned g = blocks_for(((len >> 2) + kPcmUnroll - 1) / kPcmUnroll);
     MXL_TIMED(ctx, "pcm_pack_kernel");
-    pcm_pack_kernel<<<g ? g : 1, kThreads, 0, ctx->stream>>>(in, reinterpret_cast<short*>(out), len);
+    launch_chained(ctx, pcm_pack_kernel, dim3(g ? g : 1), dim3(kThreads), 0, in, reinterpret_cast<short*>(out), len);
     return check_launch(ctx, "pcm_pack_kernel");
 }
 
@@ -704,7 +715,7 @@ int launch_pcm_unpack(mxl_ctx* ctx, const int16_t* in, float* out, uint64_t len)
     if (len == 0) return MXL_OK;
     const unsigned g = blocks_for(((len >> 2) + kPcmUnroll - 1) / kPcmUnroll);
     MXL_TIMED(ctx, "pcm_unpack_kernel");
-    pcm_unpack_kernel<<<g ? g : 1, kThreads, 0, ctx->stream>>>(reinterpret_cast<const short*>(in), out, len);
+    launch_chained(ctx, pcm_unpack_kernel, dim3(g ? g : 1), dim3(kThreads), 0, reinterpret_cast<const short*>(in), out, len);
     return check_launch(ctx, "pcm_unpack_kernel");
 }
 

@@ -3,6 +3,8 @@
 
 #include <mutex>
 
+#include <stdlib.h>
+
 #include "common.h"
 #include "kernels.h"
 
@@ -228,6 +230,12 @@ KernelTimer::KernelTimer(mxl_ctx* c, const char* name) : ctx(c)
     if (cudaEventRecord(ev[0], c->stream) != cudaSuccess) return;
     c->kernel_events.push_back(mxl_ctx::KernelEvents{name, ev[0], ev[1]});
     slot = (int)c->kernel_events.size() - 1;
+}
+
+bool pdl_enabled(const mxl_ctx* ctx)
+{
+    static const bool off = getenv("MXL_NO_PDL") != nullptr;
+    return !off && ctx && !ctx->kernel_timing && !ctx->pdl_hold;
 }
 
 KernelTimer::~KernelTimer()

@@ -101,6 +101,7 @@ __device__ __forceinline__ uint32_t wait_word(const unsigned long long* p, uint3
 
 __global__ void __launch_bounds__(kEnvThreads, 6) envelope_kernel(const __grid_constant__ EnvBatch b)
 {
+    pdl_prologue();
     const EnvInst& in = b.inst[blockIdx.y];
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_ev[kEnvWarps];                  // per-warp last-event key
@@ -343,7 +344,7 @@ int launch_envelope(mxl_ctx* ctx, const EnvBatch& b)
     if (b.frames >= 0x7ffffff0ull) MXL_FAIL(MXL_ERR_LENGTH, "Envelope: call longer than 2^31 samples");
     dim3 grid(envelope_tiles(b.frames), b.n);
     MXL_TIMED(ctx, "envelope_kernel");
-    envelope_kernel<<<grid, kEnvThreads, 0, ctx->stream>>>(b);
+    launch_chained(ctx, envelope_kernel, grid, dim3(kEnvThreads), 0, b);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) MXL_FAIL(MXL_ERR_CUDA, "envelope launch failed: %s", cudaGetErrorString(e));
     ctx->launches++;

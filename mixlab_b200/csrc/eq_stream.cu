@@ -94,6 +94,7 @@ template <int LC>
 __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ EqStreamBatch b)
 {
     constexpr int VPR = LC / 4;
+    pdl_prologue();
     extern __shared__ __align__(16) unsigned char eq_smem[];
     float4* tile = reinterpret_cast<float4*>(eq_smem);                              // [256][VPR], swizzled
     double* xch = reinterpret_cast<double*>(eq_smem + (size_t)kT * LC * sizeof(float));   // kEqXchDoubles
@@ -357,7 +358,7 @@ int launch_lc(mxl_ctx* ctx, const EqStreamBatch& b)
     const uint32_t U = kT - b.halo;
     dim3 grid((b.n_chunks + U - 1) / U, b.n);
     MXL_TIMED(ctx, "eq_stream_kernel");
-    eq_stream_kernel<LC><<<grid, kT, smem, ctx->stream>>>(b);
+    launch_chained(ctx, eq_stream_kernel<LC>, grid, dim3(kT), smem, b);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) MXL_FAIL(MXL_ERR_CUDA, "launch of eq_stream_kernel<%d> failed: %s", LC, cudaGetErrorString(e));
     ctx->launches++;

@@ -307,7 +307,8 @@ int mxl_graph_run_ticks(mxl_graph* g, uint64_t tick0, uint32_t n_ticks)
     static const uint32_t split_min_ticks = getenv("MXL_SPLIT_MIN_TICKS") ? (uint32_t)atoi(getenv("MXL_SPLIT_MIN_TICKS")) : 1u;
     const bool split = g->split_streams && has_audio && has_video && !has_mixed && n_ticks >= split_min_ticks && !getenv("MXL_NO_STREAM_SPLIT");
     cudaStream_t main_stream = ctx->stream;
-    struct StreamGuard { mxl_ctx* c; cudaStream_t s; ~StreamGuard() { c->stream = s; } } stream_guard{ctx, main_stream};
+    struct StreamGuard { mxl_ctx* c; cudaStream_t s; ~StreamGuard() { c->stream = s; c->pdl_hold = false; } } stream_guard{ctx, main_stream};
+    ctx->pdl_hold = split && n_ticks > 8;                            // see common.h: launch_chained
     if (split) {
         if (!ctx->stream_aux) {
             int lo = 0, hi = 0;

@@ -1672,16 +1672,19 @@ int VideoMixer::run(uint64_t t0, const IoSet& io, uint64_t* bytes)
         const Channel* ca = (p.a >= 0 && p.a < MXL_VIDEO_MIXER_CHANNELS && ch[p.a].has_stored) ? &ch[p.a] : nullptr;
         const Channel* cb = (p.b >= 0 && p.b < MXL_VIDEO_MIXER_CHANNELS && ch[p.b].has_stored) ? &ch[p.b] : nullptr;
         k::FadeJob job{};
+        job.fade = mxl_fader_to_u8(p.fader);                                                       // 168
+        // a layer whose weight is 0 (fader at an end stop) is handed to the kernel as missing and so never read:
+        // (a*255 + b*0) / 255 == a exactly, whatever stands in for b
+        if (job.fade == 0) ca = nullptr;
+        if (job.fade == 255) cb = nullptr;
         job.a = ca ? ca->frame->dev : nullptr;
         job.b = cb ? cb->frame->dev : nullptr;
         if (ca) keepalive.push_back(frame_retain(ca->frame));
         if (cb) keepalive.push_back(frame_retain(cb->frame));
         job.out = outf->dev;
-        job.fade = mxl_fader_to_u8(p.fader);                                                       // 168
         jobs.push_back(job);
         job_layouts.push_back(outf->layout);
-        // a layer at weight 0 (fader at an end stop) is not read by the kernel
-        if (bytes) *bytes += ((ca && job.fade != 0) ? outf->layout.size : 0) + ((cb && job.fade != 255) ? outf->layout.size : 0) + outf->layout.size;
+        if (bytes) *bytes += (ca ? outf->layout.size : 0) + (cb ? outf->layout.size : 0) + outf->layout.size;
         video_slot_set(io.out[0]->slots[kk], outf, tick_duration, Rational());                     // 241-247
         frame_release(outf);                                // the line holds the reference now
     }

@@ -47,7 +47,7 @@ __device__ __forceinline__ uint4 fade16(uint4 a, uint4 b, uint32_t f, uint32_t g
 // processed bytes of a frame are one contiguous range [0, size).
 constexpr int kFadeUnroll = 2;     // 4 measured slower: 0.79 vs 0.96 of the copy peak (64 frames)
 
-__device__ __forceinline__ void crossfade_flat_body(const FadeJob& job, uint64_t n16, uint64_t chroma16)
+__device__ __forceinline__ void crossfade_flat_body(const FadeJob job, uint64_t n16, uint64_t chroma16)
 {
     const uint32_t f = job.fade, g = 255u - job.fade;
     // the kFadeUnroll vectors of a thread are kVidThreads apart: each warp instruction is 512 contiguous bytes
@@ -58,9 +58,9 @@ __device__ __forceinline__ void crossfade_flat_body(const FadeJob& job, uint64_t
         const uint64_t v = v0 + (uint64_t)u * kVidThreads;
         if (v < n16) {
             const uint32_t blank = v >= chroma16 ? 0x80808080u : 0u;
-            // a layer whose weight is 0 (fader at an end stop) is not read: (a*255 + b*0) / 255 == a exactly
-            a[u] = (job.a && f) ? ldg16(job.a + v * 16) : make_uint4(blank, blank, blank, blank);
-            b[u] = (job.b && g) ? ldg16(job.b + v * 16) : make_uint4(blank, blank, blank, blank);
+            // (the host passes a layer whose weight is 0 -- fader at an end stop -- as missing: it is not read)
+            a[u] = job.a ? ldg16(job.a + v * 16) : make_uint4(blank, blank, blank, blank);
+            b[u] = job.b ? ldg16(job.b + v * 16) : make_uint4(blank, blank, blank, blank);
         }
     }
 #pragma unroll
@@ -83,14 +83,14 @@ __global__ void __launch_bounds__(kVidThreads) crossfade_flat_inline_kernel(cons
 }
 
 // General path: one plane per launch, rows may carry untouched stride padding.
-__device__ __forceinline__ void crossfade_plane_body(const FadeJob& job, uint64_t plane_offset, uint32_t stride, uint32_t vec_per_row, uint32_t blank)
+__device__ __forceinline__ void crossfade_plane_body(const FadeJob job, uint64_t plane_offset, uint32_t stride, uint32_t vec_per_row, uint32_t blank)
 {
     const uint32_t col = blockIdx.x * kVidThreads + threadIdx.x;
     if (col >= vec_per_row) return;
     const uint64_t off = plane_offset + (uint64_t)blockIdx.y * stride + (uint64_t)col * 16;
     const uint32_t f = job.fade, g = 255u - job.fade;
-    const uint4 a = (job.a && f) ? ldg16(job.a + off) : make_uint4(blank, blank, blank, blank);   // weight 0: not read
-    const uint4 b = (job.b && g) ? ldg16(job.b + off) : make_uint4(blank, blank, blank, blank);
+    const uint4 a = job.a ? ldg16(job.a + off) : make_uint4(blank, blank, blank, blank);
+    const uint4 b = job.b ? ldg16(job.b + off) : make_uint4(blank, blank, blank, blank);
     *reinterpret_cast<uint4*>(job.out + off) = fade16(a, b, f, g);
 }
 
@@ -309,12 +309,12 @@ __global__ void __launch_bounds__(kVidThreads) compose_rgba_kernel(const Compose
     uint32_t ua = 0x80808080u, va = 0x80808080u, ub = 0x80808080u, vb = 0x80808080u;   // a missing layer is blank
     const uint64_t yo = (uint64_t)(2 * cy) * ystride + x0, co = (uint64_t)cy * cstride + (x0 >> 1);
     const bool row1 = 2 * cy + 1 < height;
-    if (job.a && f) {                                              // a layer whose weight is 0 is not read
+    if (job.a) {                                                   // (a layer whose weight is 0 arrives as missing)
         ya0 = ldg8(job.a + yo);
         if (row1) ya1 = ldg8(job.a + yo + ystride);
         ua = ldg4(job.a + off_u + co); va = ldg4(job.a + off_v + co);
     }
-    if (job.b && g) {
+    if (job.b) {
         yb0 = ldg8(job.b + yo);
         if (row1) yb1 = ldg8(job.b + yo + ystride);
         ub = ldg4(job.b + off_u + co); vb = ldg4(job.b + off_v + co);
