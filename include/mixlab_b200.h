@@ -77,7 +77,8 @@ typedef enum mxl_module_kind {
                                    * (monitor.rs:112-140,235-247; EncodeStream, src/video/encode.rs:34-107,184-221);
                                    * x264 / fdk-aac and the websocket stay in the host application */
     MXL_MOD_OSCILLATOR = 6,
-    MXL_MOD_OUTPUT_DEVICE = 7,    /* (io) not provided */
+    MXL_MOD_OUTPUT_DEVICE = 7,    /* run_tick provided (channel routing into the device's interleaved buffer + clip,
+                                   * output_device.rs:177-206); cpal and its callback stay in the host application */
     MXL_MOD_PLOTTER = 8,
     MXL_MOD_STEREO_PANNER = 9,
     MXL_MOD_STEREO_SPLITTER = 10,
@@ -364,6 +365,19 @@ typedef struct mxl_video_job {
 } mxl_video_job;
 MXL_API int mxl_monitor_recv_audio(mxl_module *m, mxl_audio_fragment *info, int16_t *pcm, uint32_t cap_samples);
 MXL_API int mxl_monitor_recv_video(mxl_module *m, mxl_video_job *out);
+/* ---- OutputDevice (src/module/output_device.rs) ---------------------------------------------------
+ * input: Stereo (unlabeled).  params: the output channel each side is routed to (-1 = None) and the channel count
+ * of the opened device stream (stream.config.channels; 0 = no stream: run_tick queues nothing).  update() zeroes the
+ * scratch buffer when an assignment changes and drops assignments beyond the channel count (152-168).  run_tick
+ * (173-206) writes left then right into the interleaved scratch buffer, sets the clip flag when a routed sample lies
+ * outside [-1, 1] and queues frames * channels samples for the device callback; the queue holds 65536 samples like
+ * the reference's ring buffer (128) and takes only what fits.  mxl_output_device_read pops what the cpal callback
+ * would pop (waits for the download); mxl_output_device_clip returns the flag of the last run_tick (synchronises;
+ * the Instant-based temporal warnings, 208-230, stay with the host). */
+typedef struct mxl_output_device_params { int32_t left, right; uint32_t channels, _pad; } mxl_output_device_params;
+MXL_API int64_t mxl_output_device_read(mxl_module *m, float *out, uint64_t cap_samples);
+MXL_API int mxl_output_device_clip(mxl_module *m, int32_t *clip);
+
 /* StreamOutput (src/module/stream_output.rs): the same two feeds (LiveOutput::tick, 369-381) at 1120 x 700 (13-14),
  * read with mxl_monitor_recv_*.  The RTMP connection state machine lives in the host application; it reports
  * Connection::Live with live = 1 (a new EncodeStream; the next tick is the epoch, 126,328-366) and anything else

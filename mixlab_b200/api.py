@@ -108,6 +108,10 @@ class VideoJob(C.Structure):
                 ("_pad", C.c_int32), ("frame", C.c_void_p)]
 
 
+class OutputDeviceParams(C.Structure):
+    _fields_ = [("left", C.c_int32), ("right", C.c_int32), ("channels", C.c_uint32), ("_pad", C.c_uint32)]
+
+
 class HostRef(C.Structure):
     """mxl_host_ref: one InputRef / OutputRef of the reference with host slices (io.rs:19-34,79-98)."""
     _fields_ = [("type", C.c_int32), ("connected", C.c_int32), ("samples", C.c_void_p), ("len", C.c_uint64),
@@ -122,7 +126,7 @@ _PARAM_TYPES = {
     MOD_AMPLIFIER: AmplifierParams, MOD_ENVELOPE: EnvelopeParams, MOD_EQ_THREE: EqThreeParams,
     MOD_FM_SINE: FmSineParams, MOD_MIXER: MixerParams, MOD_OSCILLATOR: OscillatorParams,
     MOD_TRIGGER: TriggerParams, MOD_VIDEO_MIXER: VideoMixerParams, MOD_MONITOR: MonitorParams,
-    MOD_STREAM_OUTPUT: MonitorParams,
+    MOD_STREAM_OUTPUT: MonitorParams, MOD_OUTPUT_DEVICE: OutputDeviceParams,
 }
 
 _lib = None
@@ -224,6 +228,8 @@ def lib():
         "mxl_monitor_recv_audio": (i32, [vp, C.POINTER(AudioFragment), vp, u32]),
         "mxl_monitor_recv_video": (i32, [vp, C.POINTER(VideoJob)]),
         "mxl_stream_output_set_live": (i32, [vp, i32]),
+        "mxl_output_device_read": (C.c_int64, [vp, vp, u64]),
+        "mxl_output_device_clip": (i32, [vp, C.POINTER(C.c_int32)]),
         "mxl_video_line_get_timing": (i32, [vp, u32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
         "mxl_eq_three_state": (i32, [vp, C.POINTER(dbl)]),
         "mxl_envelope_state": (i32, [vp, C.POINTER(C.c_int32), C.POINTER(u64), C.POINTER(dbl)]),
@@ -818,6 +824,16 @@ class Module:
         if check(lib().mxl_monitor_recv_video(self.h, C.byref(job))) == 0:
             return None
         return job.pts, job.duration, job.time_base, bool(job.blank), Frame(self.ctx, handle=job.frame)
+
+    def output_device_read(self, cap):
+        out = np.empty(cap, np.float32)
+        n = check(lib().mxl_output_device_read(self.h, _ptr(out), cap))
+        return out[:n]
+
+    def output_device_clip(self):
+        c = C.c_int32()
+        check(lib().mxl_output_device_clip(self.h, C.byref(c)))
+        return bool(c.value)
 
     def stream_output_set_live(self, live):
         check(lib().mxl_stream_output_set_live(self.h, 1 if live else 0))

@@ -223,6 +223,8 @@ int mxl_stream_input_pending(const mxl_module* m, uint32_t* audio_frames, uint32
 int mxl_monitor_recv_audio(mxl_module* m, mxl_audio_fragment* info, int16_t* pcm, uint32_t cap_samples) { return monitor_recv_audio(m, info, pcm, cap_samples); }
 int mxl_monitor_recv_video(mxl_module* m, mxl_video_job* out) { return monitor_recv_video(m, out); }
 int mxl_stream_output_set_live(mxl_module* m, int live) { return stream_output_set_live(m, live); }
+int64_t mxl_output_device_read(mxl_module* m, float* out, uint64_t cap_samples) { return output_device_read(m, out, cap_samples); }
+int mxl_output_device_clip(mxl_module* m, int32_t* clip) { return output_device_clip(m, clip); }
 
 // Device staging for i16 PCM on its way in or out: a ring owned by the context, so the asynchronous
 // converters neither allocate nor synchronise per call.  A region is reused only after a wrap, which

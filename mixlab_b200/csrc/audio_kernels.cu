@@ -515,6 +515,25 @@ __global__ void __launch_bounds__(kMeterThreads) meter_warp_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------
+// OutputDevice (output_device.rs:177-206): left / right of the stereo line into two channels of the
+// device's interleaved scratch buffer, clip = any routed sample outside [-1, 1].  Left is stored first,
+// so right wins when both sides map to one channel, as in the reference's loop.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) route_kernel(const __grid_constant__ RouteLaunch p)
+{
+    pdl_prologue();
+    const uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    bool clip = false;
+    if (i < p.frames) {
+        const float2 s = p.in ? ldg_stream2(p.in + 2 * i) : make_float2(0.f, 0.f);
+        float* o = p.scratch + i * p.channels;
+        if (p.left >= 0) { clip |= s.x < -1.0f || s.x > 1.0f; o[p.left] = s.x; }
+        if (p.right >= 0) { clip |= s.y < -1.0f || s.y > 1.0f; o[p.right] = s.y; }
+    }
+    if (__any_sync(0xffffffffu, clip) && (threadIdx.x & 31) == 0) atomicOr(p.clip, 1);
+}
+
+// ------------------------------------------------------------------------------------------
 // PCM pack: src/video/encode.rs:184-195 (clamp, *32767, `as i16`); unpack: stream_input.rs:167-173
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ short pack1(float s)
@@ -697,6 +716,16 @@ int launch_meter(mxl_ctx* ctx, const MeterBatch& b, uint32_t n_slots)
         launch_chained(ctx, meter_block_kernel, grid, dim3(kMeterThreads), 0, b);
     }
     return check_launch(ctx, "meter_kernel");
+}
+
+int launch_route(mxl_ctx* ctx, const RouteLaunch& p)
+{
+    MXL_REQUIRE_DEVICE(ctx);
+    if (p.frames == 0) return MXL_OK;
+    const unsigned g = blocks_for(p.frames);
+    MXL_TIMED(ctx, "route_kernel");
+    launch_chained(ctx, route_kernel, dim3(g), dim3(kThreads), 0, p);
+    return check_launch(ctx, "route_kernel");
 }
 
 int launch_pcm_pack(mxl_ctx* ctx, const float* in, int16_t* out, uint64_t len)

@@ -142,6 +142,17 @@ struct MeterInst { const float* in; MeterRecord* out; };
 struct MeterBatch { uint64_t frames; uint32_t spt; int32_t n; MeterInst inst[kMaxBatch]; };
 int launch_meter(mxl_ctx* ctx, const MeterBatch& b, uint32_t n_slots);
 
+// ---- OutputDevice channel routing + clip (src/module/output_device.rs:177-206) ----
+struct RouteLaunch {
+    const float* in;                 // stereo line, nullptr = disconnected (zeros)
+    float* scratch;                  // [frames][channels], device
+    uint64_t frames;
+    uint32_t channels;
+    int32_t left, right;             // output channel of each side, -1 = None
+    int32_t* clip;                   // device flag, set to 1 when a routed sample lies outside [-1, 1]
+};
+int launch_route(mxl_ctx* ctx, const RouteLaunch& p);
+
 // ---- PCM (src/video/encode.rs:184-195 ; src/module/stream_input.rs:167-173) ----
 int launch_pcm_pack(mxl_ctx* ctx, const float* in, int16_t* out, uint64_t len);
 int launch_pcm_unpack(mxl_ctx* ctx, const int16_t* in, float* out, uint64_t len);

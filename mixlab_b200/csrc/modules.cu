@@ -335,6 +335,67 @@ struct Monitor : mxl_module {
     int run(uint64_t t0, const IoSet& io, uint64_t* bytes);
 };
 
+// ---- OutputDevice: src/module/output_device.rs ---------------------------------------------------------
+struct OutputDevice : mxl_module {
+    static constexpr uint64_t kRingCapacity = 65536;               // RingBuffer::<f32>::new(65536) (output_device.rs:128)
+    mxl_output_device_params p{-1, -1, 0, 0};
+    DevBuf scratch;                                                // self.scratch, on the device
+    uint64_t scratch_len = 0;
+    DevBuf clip_flag;
+    int32_t* clip_host = nullptr;                                  // pinned
+    // samples queued for the device callback, one pinned chunk per call
+    struct Chunk { float* host = nullptr; size_t cap = 0, n = 0; cudaEvent_t ev = nullptr; bool in_flight = false; };
+    std::deque<Chunk> chunks;
+    std::vector<Chunk> spare;
+    size_t head = 0;
+    uint64_t pending = 0;
+
+    OutputDevice(const mxl_output_device_params* in)
+    {
+        kind = MXL_MOD_OUTPUT_DEVICE;
+        inputs = {unlabeled(MXL_LINE_STEREO)};                     // output_device.rs:84
+        if (in) { p = *in; filter(); }
+    }
+    ~OutputDevice() override
+    {
+        if (ctx && ctx->has_device()) { ctx->activate(); cudaStreamSynchronize(ctx->stream); }
+        for (auto& c : chunks) { if (c.host) cudaFreeHost(c.host); if (c.ev) cudaEventDestroy(c.ev); }
+        for (auto& c : spare) { if (c.host) cudaFreeHost(c.host); if (c.ev) cudaEventDestroy(c.ev); }
+        if (clip_host) cudaFreeHost(clip_host);
+        scratch.release(ctx);
+        clip_flag.release(ctx);
+    }
+    void filter()                                                  // 161-167: assignments must be within range
+    {
+        if (p.left >= 0 && (uint32_t)p.left >= p.channels) p.left = -1;
+        if (p.right >= 0 && (uint32_t)p.right >= p.channels) p.right = -1;
+    }
+    int update(const void* params) override
+    {
+        if (!params) MXL_FAIL(MXL_ERR_PARAMS, "OutputDevice: NULL params");
+        const mxl_output_device_params n = *(const mxl_output_device_params*)params;
+        const bool reopened = n.channels != p.channels;            // another device stream (100-149): a new, empty ring
+        if (n.channels) {                                          // `if let Some(stream)` (152)
+            // 156-160: zero the scratch buffer when an assignment changes, so that no left-over data keeps playing
+            if ((p.left != n.left || p.right != n.right || reopened) && scratch.p && ctx && ctx->has_device()) {
+                MXL_TRY(ctx->activate());
+                MXL_CUDA(cudaMemsetAsync(scratch.p, 0, scratch_len * sizeof(float), ctx->stream));
+            }
+            p.left = n.left; p.right = n.right;
+        }
+        p.channels = n.channels;
+        filter();
+        if (reopened) {
+            if (ctx && ctx->has_device() && !chunks.empty()) { ctx->activate(); cudaStreamSynchronize(ctx->stream); }
+            for (auto& c : chunks) { c.in_flight = false; spare.push_back(c); }
+            chunks.clear(); head = 0; pending = 0;
+        }
+        return MXL_OK;
+    }
+    int get_params(void* out) const override { if (out) *(mxl_output_device_params*)out = p; return MXL_OK; }
+    int run(const IoSet& io, uint64_t* bytes);
+};
+
 // ---- VideoMixer: src/module/video_mixer.rs ---------------------------------------------------------
 struct PictureSettings { uint32_t w = 0, h = 0; bool operator==(const PictureSettings& o) const { return w == o.w && h == o.h; } bool operator!=(const PictureSettings& o) const { return !(*this == o); } };
 
@@ -394,6 +455,7 @@ const char* mxl_module::kind_name() const
     case MXL_MOD_SOURCE_STEREO: return "SourceStereo";
     case MXL_MOD_SOURCE_VIDEO: return "SourceVideo";
     case MXL_MOD_STREAM_INPUT: return "StreamInput";
+    case MXL_MOD_OUTPUT_DEVICE: return "OutputDevice";
     case MXL_MOD_MONITOR: return "Monitor";
     case MXL_MOD_STREAM_OUTPUT: return "StreamOutput";
     case MXL_MOD_PCM_SINK: return "PcmSink";
@@ -426,7 +488,8 @@ mxl_module* module_create(mxl_ctx* ctx, int kind, const void* params)
     case MXL_MOD_PCM_SINK: m = new PcmSink(); break;
     case MXL_MOD_STREAM_INPUT: m = new StreamInput(); break;
     case MXL_MOD_MONITOR: case MXL_MOD_STREAM_OUTPUT: m = new Monitor(kind, (const mxl_monitor_params*)params); break;
-    case MXL_MOD_OUTPUT_DEVICE: case MXL_MOD_MEDIA_SOURCE:
+    case MXL_MOD_OUTPUT_DEVICE: m = new OutputDevice((const mxl_output_device_params*)params); break;
+    case MXL_MOD_MEDIA_SOURCE:
         set_error("module kind %d is an I/O edge that stays in the host application (out of scope of the tick hot path)", kind);
         return nullptr;
     default:
@@ -1376,6 +1439,87 @@ int monitor_recv_video(mxl_module* m, mxl_video_job* out)
 }
 
 // ================================================================================================
+// OutputDevice::run_tick: src/module/output_device.rs:173-206
+// ================================================================================================
+int OutputDevice::run(const IoSet& io, uint64_t* bytes)
+{
+    NEED_IO(io, 1, 0, "OutputDevice");
+    MXL_TRY(expect_input(io.in[0], MXL_LINE_STEREO, "OutputDevice"));
+    if (!clip_host) {
+        MXL_CUDA(cudaMallocHost(&clip_host, sizeof(int32_t)));
+        MXL_TRY(clip_flag.ensure(ctx, sizeof(int32_t)));
+    }
+    MXL_CUDA(cudaMemsetAsync(clip_flag.p, 0, sizeof(int32_t), ctx->stream));                      // let mut clip = false (176)
+    if (p.channels == 0) return MXL_OK;                                                            // no stream (178)
+    const uint64_t frames = io.in[0] ? io.in[0]->frames : ctx->spt;                                // input.len() / CHANNELS (180)
+    const uint64_t n = frames * p.channels;                                                        // scratch_len (181)
+    if (n == 0) return MXL_OK;
+    if (scratch_len < n) {                                                                         // 183-185 resize(.., 0.0)
+        // unrouted channels only ever hold zeros (update() clears on every re-assignment), so a fresh zeroed
+        // buffer equals the grown one
+        MXL_TRY(scratch.ensure(ctx, n * sizeof(float)));
+        MXL_CUDA(cudaMemsetAsync(scratch.p, 0, n * sizeof(float), ctx->stream));
+        scratch_len = n;
+    }
+    k::RouteLaunch r{io.in[0] ? io.in[0]->dev : nullptr, (float*)scratch.p, frames, p.channels, p.left, p.right, (int32_t*)clip_flag.p};
+    MXL_TRY(k::launch_route(ctx, r));                                                              // 187-205
+    if (bytes) *bytes += (io.in[0] ? 8 * frames : 0) + 4 * frames * ((p.left >= 0) + (p.right >= 0 && p.right != p.left));
+    // stream.tx.push_slice(&scratch[0..n]) (207): as much as the ring still takes
+    const uint64_t take = std::min<uint64_t>(n, kRingCapacity - std::min<uint64_t>(pending, kRingCapacity));
+    if (take) {
+        Chunk c;
+        for (size_t i = 0; i < spare.size(); i++)
+            if (spare[i].cap >= take) { c = spare[i]; spare.erase(spare.begin() + i); break; }
+        if (!c.host) {
+            if (!spare.empty()) { Chunk old = spare.front(); spare.erase(spare.begin()); cudaFreeHost(old.host); c.ev = old.ev; }
+            const size_t want = take + take / 4 + 64;
+            MXL_CUDA(cudaMallocHost(&c.host, want * sizeof(float)));
+            c.cap = want;
+            if (!c.ev) MXL_CUDA(cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming));
+        }
+        c.n = take;
+        MXL_CUDA(cudaMemcpyAsync(c.host, scratch.p, take * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        MXL_CUDA(cudaEventRecord(c.ev, ctx->stream));
+        c.in_flight = true;
+        ctx->d2h_bytes += take * sizeof(float);
+        chunks.push_back(c);
+        pending += take;
+    }
+    return MXL_OK;
+}
+
+int64_t output_device_read(mxl_module* m, float* out, uint64_t cap)
+{
+    if (!m || m->kind != MXL_MOD_OUTPUT_DEVICE) MXL_FAIL(MXL_ERR_PARAMS, "not an OutputDevice module");
+    if (cap && !out) MXL_FAIL(MXL_ERR_INVALID, "NULL buffer");
+    OutputDevice* d = (OutputDevice*)m;
+    uint64_t got = 0;
+    while (got < cap && !d->chunks.empty()) {
+        OutputDevice::Chunk& c = d->chunks.front();
+        if (c.in_flight) { MXL_TRY(m->ctx->activate()); MXL_CUDA(cudaEventSynchronize(c.ev)); c.in_flight = false; }
+        const uint64_t take = std::min<uint64_t>(cap - got, c.n - d->head);
+        memcpy(out + got, c.host + d->head, take * sizeof(float));
+        got += take; d->head += take;
+        if (d->head == c.n) { d->spare.push_back(c); d->chunks.pop_front(); d->head = 0; }
+    }
+    d->pending -= got;
+    return (int64_t)got;
+}
+
+int output_device_clip(mxl_module* m, int32_t* clip)
+{
+    if (!m || m->kind != MXL_MOD_OUTPUT_DEVICE || !clip) MXL_FAIL(MXL_ERR_PARAMS, "not an OutputDevice module");
+    OutputDevice* d = (OutputDevice*)m;
+    *clip = 0;
+    if (!d->clip_host) return MXL_OK;                                 // never ran
+    MXL_TRY(m->ctx->activate());
+    MXL_CUDA(cudaMemcpyAsync(d->clip_host, d->clip_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, m->ctx->stream));
+    MXL_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    *clip = *d->clip_host;
+    return MXL_OK;
+}
+
+// ================================================================================================
 // VideoMixer: src/module/video_mixer.rs:70-250
 // ================================================================================================
 
@@ -1731,6 +1875,13 @@ int run_batch(mxl_ctx* ctx, int kind, mxl_module* const* mods, int n, uint64_t t
     case MXL_MOD_METER: return run_meters(ctx, mods, n, io, bytes);
     case MXL_MOD_PLOTTER: return run_plotters(ctx, mods, n, io, bytes);
     case MXL_MOD_PCM_SINK: return run_pcm_sinks(ctx, mods, n, io, bytes);
+    case MXL_MOD_OUTPUT_DEVICE:
+        for (int i = 0; i < n; i++) {
+            uint64_t b = 0;
+            MXL_TRY(((OutputDevice*)mods[i])->run(io[i], &b));
+            if (bytes) *bytes += b;
+        }
+        return MXL_OK;
     case MXL_MOD_MONITOR: case MXL_MOD_STREAM_OUTPUT:
         for (int i = 0; i < n; i++) {
             uint64_t b = 0;

@@ -70,6 +70,8 @@ int stream_input_pending(const mxl_module* m, uint32_t* audio_frames, uint32_t* 
 int monitor_recv_audio(mxl_module* m, mxl_audio_fragment* info, int16_t* pcm, uint32_t cap);
 int monitor_recv_video(mxl_module* m, mxl_video_job* out);
 int stream_output_set_live(mxl_module* m, int live);
+int64_t output_device_read(mxl_module* m, float* out, uint64_t cap);
+int output_device_clip(mxl_module* m, int32_t* clip);
 int mixer_params_get(const mxl_module* m, mxl_mixer_channel_params* out, uint32_t cap);
 
 mxl_frame* frame_scale(mxl_frame* src, uint32_t out_w, uint32_t out_h);

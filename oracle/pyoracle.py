@@ -356,6 +356,51 @@ def letterbox_scale(data, lay_in, out_w, out_h):
     return want
 
 
+class OutputDevice:
+    """OutputDevice::update's channel assignment (src/module/output_device.rs:152-168) and run_tick (173-207)
+    restated; `channels` = stream.config.channels of the opened device (0 = no stream)."""
+    RING_CAPACITY = 65536
+
+    def __init__(self, left, right, channels):
+        self.scratch = np.zeros(0, np.float32)
+        self.left = self.right = None
+        self.channels = channels
+        self.ring = np.zeros(0, np.float32)
+        self.update(left, right)
+
+    def update(self, left, right):
+        if self.channels:                                            # `if let Some(stream)` (152)
+            if self.left != left or self.right != right:             # 156-160
+                self.scratch[:] = 0.0
+            self.left = left if (left is not None and left < self.channels) else None       # 164-165
+            self.right = right if (right is not None and right < self.channels) else None   # 167-168
+
+    def run_tick(self, inp):
+        inp = _f32(inp)
+        clip = False                                                 # 176
+        if self.channels:                                            # 178
+            oc = self.channels
+            n = inp.size // 2                                        # 180
+            if self.scratch.size < n * oc:                           # 183-185
+                self.scratch = np.concatenate([self.scratch, np.zeros(n * oc - self.scratch.size, np.float32)])
+            view = self.scratch[:n * oc].reshape(n, oc)
+            if self.left is not None:                                # 188-196
+                s = inp[0::2]
+                clip |= bool(np.any((s < -1.0) | (s > 1.0)))
+                view[:, self.left] = s
+            if self.right is not None:                               # 198-206 (after left: wins on a shared channel)
+                s = inp[1::2]
+                clip |= bool(np.any((s < -1.0) | (s > 1.0)))
+                view[:, self.right] = s
+            room = self.RING_CAPACITY - self.ring.size               # push_slice (207): what fits
+            self.ring = np.concatenate([self.ring, self.scratch[:min(n * oc, room)]])
+        return clip
+
+    def pop(self, cap):
+        out, self.ring = self.ring[:cap], self.ring[cap:]
+        return out
+
+
 class MonitorFeed:
     """Monitor::run_tick (src/module/monitor.rs:112-140), the codec thread's loop body (235-247) and EncodeStream
     (src/video/encode.rs:34-107) with AudioCtx::send_audio (184-221) and VideoCtx::send_frame (279-287), up to

@@ -102,7 +102,7 @@ def test_header_is_plain_c(tmp_path):
 
 
 def test_io_edge_kinds_are_not_provided(mxl, host_ctx):
-    for kind in (mxl.MOD_OUTPUT_DEVICE, mxl.MOD_MEDIA_SOURCE, 99):
+    for kind in (mxl.MOD_MEDIA_SOURCE, 99):
         with pytest.raises(mxl.MxlError):
             host_ctx.module(kind, None)
 
