@@ -1630,10 +1630,10 @@ int scale_run(mxl_ctx* ctx, const mxl_frame_layout& sl, uint32_t out_w, uint32_t
             P.tiles_x = (P.dst_w + tw - 1) / tw;
             P.tiles_y = (P.dst_h + th - 1) / th;
             tile_base += P.tiles_x * P.tiles_y;
-            for (uint32_t t = 0; t < P.tiles_x; t++) {      // staged bytes per row: from the 16-aligned first tap to the last tap
-                const uint32_t x0 = t * tw, x1 = std::min(x0 + tw, P.dst_w) - 1;
-                const int lo = clampi((*hx)[x0], (int)P.src_w - 1) & ~15, hi = clampi((*hx)[x1] + 3, (int)P.src_w - 1);
-                max_span = std::max<uint32_t>(max_span, (uint32_t)((hi - lo) / 16 + 1) * 16);
+            for (uint32_t t = 0; t < P.tiles_x; t++) {      // staged bytes per row: from the 16-floored (unclamped) first tap
+                const uint32_t x0 = t * tw, x1 = std::min(x0 + tw, P.dst_w) - 1;     // to the word after the last tap set
+                const int lo = (*hx)[x0] & ~15, hi = (*hx)[x1] + 3;
+                max_span = std::max<uint32_t>(max_span, (uint32_t)((hi - lo + 5 + 15) & ~15));
             }
             for (uint32_t t = 0; t < P.tiles_y; t++) {
                 const uint32_t y0 = t * th, y1 = std::min(y0 + th, P.dst_h) - 1;

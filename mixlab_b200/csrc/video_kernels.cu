@@ -157,10 +157,12 @@ __device__ __forceinline__ uint32_t yuv_px_terms(uint32_t y, const ChromaTerms& 
 // repository's stand-in for swscale's SWS_BICUBIC -- DESIGN.md "unpinned"): all three planes of a
 // batch of frames in ONE launch.  A CTA owns a 128x64 tile of output pixels of one plane (128x32, 128x8 or 128x2 when a
 // strong down-scale would make the source rectangle of a taller tile outgrow shared memory):
-//   1. the source rectangle the tile's taps touch is staged global -> shared with 16-byte cp.async
-//      (rows and columns clamped the way the taps clamp, so edges need no special case);
+//   1. the source rectangle the tile's taps touch is staged global -> shared with 16-byte cp.async; tiles at the
+//      left / right edge of the plane then replicate the edge column outwards, so that the four taps of a pixel are
+//      always four consecutive staged bytes (the taps clamp);
 //   2. horizontal 4-tap pass shared -> shared into a u8 intermediate (rounded and clipped exactly as the
-//      two-pass definition does);
+//      two-pass definition does): two aligned word loads + one byte permute per pixel instead of four byte
+//      gathers;
 //   3. vertical 4-tap pass shared -> global.
 // Every source byte is read from HBM once per tile that needs it (neighbouring tiles share a 3-pixel
 // apron through L2); the intermediate never leaves the SM.
@@ -188,8 +190,11 @@ template <int kScaleTH>
 __global__ void __launch_bounds__(kVidThreads) scale_tiled_kernel(const __grid_constant__ ScaleLaunch L)
 {
     extern __shared__ __align__(16) uint8_t sc_smem[];
-    __shared__ int s_xpos[kScaleTW], s_ypos[kScaleTH];
-    __shared__ short4 s_xco[kScaleTW], s_yco[kScaleTH];
+    // per output column: {byte offset of the aligned word holding the first tap, PRMT selector of the four taps,
+    // weights 0|1, weights 2|3}; per output row: the byte offsets of the four tap rows in `mid`, and the weights
+    __shared__ uint4 s_x[kScaleTW];
+    __shared__ uint4 s_yr[kScaleTH];
+    __shared__ uint2 s_yc[kScaleTH];
     const ScaleJob job = L.jobs[blockIdx.y];
     // the plane's geometry into registers through statically addressed parameter reads (a run-time index into
     // the parameter block turns every field access into a slow indexed constant load)
@@ -200,86 +205,115 @@ __global__ void __launch_bounds__(kVidThreads) scale_tiled_kernel(const __grid_c
     const uint32_t x0 = (t % P.tiles_x) * kScaleTW, y0 = (t / P.tiles_x) * kScaleTH;
     const uint32_t x1 = min(x0 + kScaleTW, P.dst_w) - 1, y1 = min(y0 + kScaleTH, P.dst_h) - 1;
     const int sw = (int)P.src_w, sh = (int)P.src_h;
-    // source rectangle touched by the tile's taps (first taps are monotonic in the output index)
-    // the first taps of the tile's corner columns / rows come from the tap tables (four warp-uniform loads, L2 hits
-    // after the first tile of a geometry): recomputing them costs four integer divisions = a fifth of the tile's
-    // instructions
-    const int cx_lo = min(max(__ldg(P.xpos + x0), 0), sw - 1) & ~15;
-    const int cx_hi = min(max(__ldg(P.xpos + x1) + 3, 0), sw - 1);
+    // source rectangle touched by the tile's taps (first taps are monotonic in the output index); the first taps of
+    // the tile's corner columns / rows come from the tap tables (four warp-uniform loads, L2 hits after the first
+    // tile of a geometry).  Columns are kept UNclamped: the staged rows carry replicated edge pixels left of column
+    // 0 and right of column sw-1, so the four taps of a pixel are always four consecutive staged bytes.
+    const int px_lo = __ldg(P.xpos + x0), px_hi = __ldg(P.xpos + x1) + 3;       // px_lo >= -2, px_hi <= sw + 1
+    const int gx0 = px_lo & ~15;                                                 // floor to 16 (-16 for a negative first tap)
+    const int width = (px_hi - gx0 + 5 + 15) & ~15;                              // the second word of the last tap set included
     const int ry_lo = min(max(__ldg(P.ypos + y0), 0), sh - 1);
     const int ry_hi = min(max(__ldg(P.ypos + y1) + 3, 0), sh - 1);
-    const int chunks = (cx_hi - cx_lo) / 16 + 1, rows = ry_hi - ry_lo + 1;
+    const int nch = width >> 4, rows = ry_hi - ry_lo + 1;
     const int pitch = (int)L.region_pitch;                       // bytes per staged row (host bound, multiple of 16)
     uint8_t* region = sc_smem;                                   // [rows][pitch]
     uint8_t* mid = sc_smem + (size_t)L.region_rows * pitch;      // [rows][kScaleTW]
     const uint8_t* src = job.src + P.src_off;
-    for (uint32_t i = threadIdx.x; i < (uint32_t)(rows * chunks); i += kVidThreads) {
-        const uint32_t r = i / (uint32_t)chunks, c = i - r * (uint32_t)chunks;
-        cp_async_16(region + r * pitch + c * 16, src + (size_t)(ry_lo + r) * P.src_stride + cx_lo + c * 16);
+    // 16 threads per staged row, 16 rows per pass; chunks outside [0, stride) -- the 16 bytes left of column 0, or
+    // beyond the padded row -- are not loaded (the fix-up below fills them)
+    for (int r = threadIdx.x >> 4; r < rows; r += kVidThreads / 16) {
+        const uint8_t* srow = src + (size_t)(ry_lo + r) * P.src_stride;
+        for (int c = threadIdx.x & 15; c < nch; c += 16) {
+            const int x = gx0 + 16 * c;
+            if (x >= 0 && x < (int)P.src_stride) cp_async_16(region + r * pitch + c * 16, srow + x);
+        }
     }
     // the tile's slices of the tap tables, in flight together with the staging
     if (threadIdx.x < kScaleTW) {
         const uint32_t gx = min(x0 + threadIdx.x, x1);
-        s_xpos[threadIdx.x] = P.xpos[gx];
-        s_xco[threadIdx.x] = *reinterpret_cast<const short4*>(P.xcoef + (size_t)gx * 4);
+        const int rel = __ldg(P.xpos + gx) - gx0;                 // >= 0
+        const short4 cf = *reinterpret_cast<const short4*>(P.xcoef + (size_t)gx * 4);
+        s_x[threadIdx.x] = make_uint4((uint32_t)(rel & ~3), 0x3210u + 0x1111u * (uint32_t)(rel & 3),
+                                      (uint32_t)pack_s16x2(cf.x, cf.y), (uint32_t)pack_s16x2(cf.z, cf.w));
     } else if (threadIdx.x < kScaleTW + kScaleTH) {
         const uint32_t i = threadIdx.x - kScaleTW, gy = min(y0 + i, y1);
-        s_ypos[i] = P.ypos[gy];
-        s_yco[i] = *reinterpret_cast<const short4*>(P.ycoef + (size_t)gy * 4);
+        const int p0 = __ldg(P.ypos + gy);
+        const short4 cf = *reinterpret_cast<const short4*>(P.ycoef + (size_t)gy * 4);
+        s_yr[i] = make_uint4((uint32_t)(min(max(p0, 0), sh - 1) - ry_lo) * kScaleTW, (uint32_t)(min(max(p0 + 1, 0), sh - 1) - ry_lo) * kScaleTW,
+                             (uint32_t)(min(max(p0 + 2, 0), sh - 1) - ry_lo) * kScaleTW, (uint32_t)(min(max(p0 + 3, 0), sh - 1) - ry_lo) * kScaleTW);
+        s_yc[i] = make_uint2((uint32_t)pack_s16x2(cf.x, cf.y), (uint32_t)pack_s16x2(cf.z, cf.w));
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    // horizontal pass: thread = 4 adjacent output columns of one staged row at a time; the four taps of a pixel
-    // are gathered into one word and reduced by two dp2a (s16 weights x u8 pixels); mid[r][x] packed 4 per store
+    // edge tiles: replicate column 0 to the left and column sw-1 to the right (the taps clamp, video scalers do)
+    if (gx0 < 0 || gx0 + width > sw) {
+        for (int i = threadIdx.x; i < rows * 2; i += kVidThreads) {
+            uint8_t* row = region + (i >> 1) * pitch;
+            if ((i & 1) == 0) {
+                if (gx0 < 0) {
+                    const uint8_t v = row[-gx0];
+                    for (int c = 0; c < -gx0; c++) row[c] = v;
+                }
+            } else if (gx0 + width > sw) {
+                const uint8_t v = row[sw - 1 - gx0];
+                for (int c = sw - gx0; c < width; c++) row[c] = v;
+            }
+        }
+        __syncthreads();
+    }
+    // horizontal pass: thread = 4 adjacent output columns of one staged row at a time.  The four taps of a pixel are
+    // four consecutive staged bytes: two aligned word loads and one byte permute bring them into one register, two
+    // dp2a (s16 weights x u8 pixels) reduce them; mid[r][x] packed 4 per store
     {
         const int q = threadIdx.x % (kScaleTW / 4);               // column quad
-        int off[4][4];
+        uint32_t sel[4];
         int c01[4], c23[4];
+        const uint8_t* a[4];
+        const int r_first = threadIdx.x / (kScaleTW / 4);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const int p0 = s_xpos[4 * q + j];
-            const short4 cf = s_xco[4 * q + j];
-            c01[j] = pack_s16x2(cf.x, cf.y);
-            c23[j] = pack_s16x2(cf.z, cf.w);
-#pragma unroll
-            for (int k = 0; k < 4; k++) off[j][k] = min(max(p0 + k, 0), sw - 1) - cx_lo;
+            const uint4 e = s_x[4 * q + j];
+            a[j] = region + r_first * pitch + e.x;
+            sel[j] = e.y; c01[j] = (int)e.z; c23[j] = (int)e.w;
         }
-        for (int r = threadIdx.x / (kScaleTW / 4); r < rows; r += kVidThreads / (kScaleTW / 4)) {
-            const uint8_t* row = region + r * pitch;
+        const int step = (kVidThreads / (kScaleTW / 4)) * pitch;
+        uint32_t* out = reinterpret_cast<uint32_t*>(mid + r_first * kScaleTW) + q;
+        for (int r = r_first; r < rows; r += kVidThreads / (kScaleTW / 4)) {
             uint32_t packed = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const uint32_t px = (uint32_t)row[off[j][0]] | ((uint32_t)row[off[j][1]] << 8) |
-                                    ((uint32_t)row[off[j][2]] << 16) | ((uint32_t)row[off[j][3]] << 24);
-                packed |= tap4(px, c01[j], c23[j]) << (8 * j);
+                const uint32_t lo = *reinterpret_cast<const uint32_t*>(a[j]), hi = *reinterpret_cast<const uint32_t*>(a[j] + 4);
+                packed |= tap4(__byte_perm(lo, hi, sel[j]), c01[j], c23[j]) << (8 * j);
+                a[j] += step;
             }
-            reinterpret_cast<uint32_t*>(mid + r * kScaleTW)[q] = packed;
+            *out = packed;
+            out += (kVidThreads / (kScaleTW / 4)) * (kScaleTW / 4);
         }
     }
     __syncthreads();
-    // vertical pass: thread = 4 adjacent output columns of one output row at a time, one 32-bit load per tap
+    // vertical pass: thread = 4 adjacent output columns of one output row at a time, one 32-bit load per tap row
     {
         const int q = threadIdx.x % (kScaleTW / 4);
-        uint8_t* dst = job.dst + P.dst_off;
-        const bool word_ok = ((P.dst_off | P.dst_stride) & 3u) == 0;
-        for (uint32_t ly = threadIdx.x / (kScaleTW / 4); y0 + ly <= y1; ly += kVidThreads / (kScaleTW / 4)) {
-            const int p0 = s_ypos[ly];
-            const short4 cf = s_yco[ly];
-            const int r0 = min(max(p0, 0), sh - 1) - ry_lo, r1 = min(max(p0 + 1, 0), sh - 1) - ry_lo;
-            const int r2 = min(max(p0 + 2, 0), sh - 1) - ry_lo, r3 = min(max(p0 + 3, 0), sh - 1) - ry_lo;
-            const uint32_t a0 = reinterpret_cast<const uint32_t*>(mid + r0 * kScaleTW)[q], a1 = reinterpret_cast<const uint32_t*>(mid + r1 * kScaleTW)[q];
-            const uint32_t a2 = reinterpret_cast<const uint32_t*>(mid + r2 * kScaleTW)[q], a3 = reinterpret_cast<const uint32_t*>(mid + r3 * kScaleTW)[q];
+        const uint32_t gx = x0 + 4 * q;
+        const bool word_ok = ((P.dst_off | P.dst_stride) & 3u) == 0 && gx + 3 <= x1;
+        const uint32_t ly0 = threadIdx.x / (kScaleTW / 4);
+        uint8_t* o = job.dst + P.dst_off + (size_t)(y0 + ly0) * P.dst_stride + gx;
+        const size_t ostep = (size_t)(kVidThreads / (kScaleTW / 4)) * P.dst_stride;
+        const uint8_t* mq = mid + 4 * q;
+        for (uint32_t ly = ly0; y0 + ly <= y1; ly += kVidThreads / (kScaleTW / 4), o += ostep) {
+            const uint4 rr = s_yr[ly];
+            const uint2 cc = s_yc[ly];
+            const uint32_t a0 = *reinterpret_cast<const uint32_t*>(mq + rr.x), a1 = *reinterpret_cast<const uint32_t*>(mq + rr.y);
+            const uint32_t a2 = *reinterpret_cast<const uint32_t*>(mq + rr.z), a3 = *reinterpret_cast<const uint32_t*>(mq + rr.w);
             // transpose 4 rows x 4 pixels into 4 pixels x 4 taps with byte permutes, then two dp2a per pixel
             const uint32_t lo01 = __byte_perm(a0, a1, 0x5140), hi01 = __byte_perm(a0, a1, 0x7362);   // (a0.b0,a1.b0,a0.b1,a1.b1), (.b2,.b3)
             const uint32_t lo23 = __byte_perm(a2, a3, 0x5140), hi23 = __byte_perm(a2, a3, 0x7362);
-            const int c01 = pack_s16x2(cf.x, cf.y), c23 = pack_s16x2(cf.z, cf.w);
+            const int c01 = (int)cc.x, c23 = (int)cc.y;
             const uint32_t packed = tap4(__byte_perm(lo01, lo23, 0x5410), c01, c23) |
                                     (tap4(__byte_perm(lo01, lo23, 0x7632), c01, c23) << 8) |
                                     (tap4(__byte_perm(hi01, hi23, 0x5410), c01, c23) << 16) |
                                     (tap4(__byte_perm(hi01, hi23, 0x7632), c01, c23) << 24);
-            const uint32_t gx = x0 + 4 * q;
-            uint8_t* o = dst + (size_t)(y0 + ly) * P.dst_stride + gx;
-            if (word_ok && gx + 3 <= x1) {
+            if (word_ok) {
                 *reinterpret_cast<uint32_t*>(o) = packed;
             } else {
                 for (uint32_t j = 0; j < 4 && gx + j <= x1; j++) o[j] = (uint8_t)(packed >> (8 * j));
