@@ -178,7 +178,8 @@ struct ScalePlane {
     uint32_t dst_off, dst_w, dst_h, dst_stride;                   // scaled rectangle inside the destination frame
     const int32_t* xpos; const int16_t* xcoef;                    // device tables: first tap and 4 x 14-bit weights per output column
     const int32_t* ypos; const int16_t* ycoef;                    // ... per output row
-    uint32_t tiles_x, tiles_y, tile_base, _pad;
+    uint32_t tiles_x, tiles_y, tile_base;
+    uint32_t tiles_x_magic;                                       // ceil(2^32 / tiles_x): t / tiles_x == umulhi(t, magic) for tiles_x > 1
 };
 struct ScaleLaunch {
     ScalePlane pl[3];

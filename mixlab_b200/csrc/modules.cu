@@ -1629,6 +1629,7 @@ int scale_run(mxl_ctx* ctx, const mxl_frame_layout& sl, uint32_t out_w, uint32_t
             MXL_TRY(axis_table(ctx, P.src_h, P.dst_h, &P.ypos, &P.ycoef, &hy));
             P.tiles_x = (P.dst_w + tw - 1) / tw;
             P.tiles_y = (P.dst_h + th - 1) / th;
+            P.tiles_x_magic = (uint32_t)((0x100000000ull + P.tiles_x - 1) / P.tiles_x);     // unused when tiles_x == 1
             tile_base += P.tiles_x * P.tiles_y;
             for (uint32_t t = 0; t < P.tiles_x; t++) {      // staged bytes per row: from the 16-floored (unclamped) first tap
                 const uint32_t x0 = t * tw, x1 = std::min(x0 + tw, P.dst_w) - 1;     // to the word after the last tap set

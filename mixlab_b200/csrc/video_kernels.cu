@@ -175,6 +175,18 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
 }
 
+// Shared-memory accesses through 32-bit shared-window addresses held in registers: with generic pointers to static
+// __shared__ arrays the compiler re-derived the window base (S2UR CgaCtaId + uniform adds) inside the tap loops.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds128(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void cp_async_16s(uint32_t smem_dst, const void* gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_dst), "l"(gmem_src) : "memory");
+}
+
 // Four taps in two instructions: weights as two s16 pairs, the four u8 samples in one word (dp2a.lo takes the
 // two low bytes, dp2a.hi the two high ones); then the two-pass definition's rounding and clip.
 __device__ __forceinline__ int pack_s16x2(short lo, short hi) { return (int)(((uint32_t)(uint16_t)hi << 16) | (uint16_t)lo); }
@@ -202,7 +214,8 @@ __global__ void __launch_bounds__(kVidThreads) scale_tiled_kernel(const __grid_c
     if (blockIdx.x >= L.pl[2].tile_base) P = L.pl[2];
     else if (blockIdx.x >= L.pl[1].tile_base) P = L.pl[1];
     const uint32_t t = blockIdx.x - P.tile_base;
-    const uint32_t x0 = (t % P.tiles_x) * kScaleTW, y0 = (t / P.tiles_x) * kScaleTH;
+    const uint32_t tyi = P.tiles_x == 1 ? t : __umulhi(t, P.tiles_x_magic);   // t / tiles_x (magic = ceil(2^32 / tiles_x))
+    const uint32_t x0 = (t - tyi * P.tiles_x) * kScaleTW, y0 = tyi * kScaleTH;
     const uint32_t x1 = min(x0 + kScaleTW, P.dst_w) - 1, y1 = min(y0 + kScaleTH, P.dst_h) - 1;
     const int sw = (int)P.src_w, sh = (int)P.src_h;
     // source rectangle touched by the tile's taps (first taps are monotonic in the output index); the first taps of
@@ -220,13 +233,18 @@ __global__ void __launch_bounds__(kVidThreads) scale_tiled_kernel(const __grid_c
     uint8_t* mid = sc_smem + (size_t)L.region_rows * pitch;      // [rows][kScaleTW]
     const uint8_t* src = job.src + P.src_off;
     // 16 threads per staged row, 16 rows per pass; chunks outside [0, stride) -- the 16 bytes left of column 0, or
-    // beyond the padded row -- are not loaded (the fix-up below fills them)
-    for (int r = threadIdx.x >> 4; r < rows; r += kVidThreads / 16) {
-        const uint8_t* srow = src + (size_t)(ry_lo + r) * P.src_stride;
-        for (int c = threadIdx.x & 15; c < nch; c += 16) {
-            const int x = gx0 + 16 * c;
-            if (x >= 0 && x < (int)P.src_stride) cp_async_16(region + r * pitch + c * 16, srow + x);
-        }
+    // beyond the padded row -- are not loaded (the fix-up below fills them).  Pointers advance by a constant per
+    // pass: no address arithmetic inside the loop.
+    const uint32_t region_a = smem_addr(region), mid_a = smem_addr(mid);
+    for (int c = threadIdx.x & 15; c < nch; c += 16) {            // one trip unless a strong down-scale widens the rows
+        const int x = gx0 + 16 * c;
+        if (x < 0 || x >= (int)P.src_stride) continue;
+        const int r0 = threadIdx.x >> 4;
+        const uint8_t* g = src + (size_t)(ry_lo + r0) * P.src_stride + x;
+        uint32_t d = region_a + r0 * pitch + c * 16;
+        const size_t gstep = (size_t)(kVidThreads / 16) * P.src_stride;
+        const uint32_t dstep = (kVidThreads / 16) * pitch;
+        for (int r = r0; r < rows; r += kVidThreads / 16, g += gstep, d += dstep) cp_async_16s(d, g);
     }
     // the tile's slices of the tap tables, in flight together with the staging
     if (threadIdx.x < kScaleTW) {
@@ -266,28 +284,27 @@ __global__ void __launch_bounds__(kVidThreads) scale_tiled_kernel(const __grid_c
     // dp2a (s16 weights x u8 pixels) reduce them; mid[r][x] packed 4 per store
     {
         const int q = threadIdx.x % (kScaleTW / 4);               // column quad
-        uint32_t sel[4];
+        uint32_t sel[4], a[4];
         int c01[4], c23[4];
-        const uint8_t* a[4];
         const int r_first = threadIdx.x / (kScaleTW / 4);
+        const uint32_t sx_a = smem_addr(s_x);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const uint4 e = s_x[4 * q + j];
-            a[j] = region + r_first * pitch + e.x;
+            const uint4 e = lds128(sx_a + (4 * q + j) * 16);
+            a[j] = region_a + r_first * pitch + e.x;
             sel[j] = e.y; c01[j] = (int)e.z; c23[j] = (int)e.w;
         }
-        const int step = (kVidThreads / (kScaleTW / 4)) * pitch;
-        uint32_t* out = reinterpret_cast<uint32_t*>(mid + r_first * kScaleTW) + q;
+        const uint32_t step = (kVidThreads / (kScaleTW / 4)) * pitch;
+        uint32_t out = mid_a + r_first * kScaleTW + 4 * q;
         for (int r = r_first; r < rows; r += kVidThreads / (kScaleTW / 4)) {
-            uint32_t packed = 0;
+            uint32_t v[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const uint32_t lo = *reinterpret_cast<const uint32_t*>(a[j]), hi = *reinterpret_cast<const uint32_t*>(a[j] + 4);
-                packed |= tap4(__byte_perm(lo, hi, sel[j]), c01[j], c23[j]) << (8 * j);
+                v[j] = tap4(__byte_perm(lds32(a[j]), lds32(a[j] + 4), sel[j]), c01[j], c23[j]);
                 a[j] += step;
             }
-            *out = packed;
-            out += (kVidThreads / (kScaleTW / 4)) * (kScaleTW / 4);
+            sts32(out, __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410));
+            out += (kVidThreads / (kScaleTW / 4)) * kScaleTW;
         }
     }
     __syncthreads();
@@ -299,20 +316,20 @@ __global__ void __launch_bounds__(kVidThreads) scale_tiled_kernel(const __grid_c
         const uint32_t ly0 = threadIdx.x / (kScaleTW / 4);
         uint8_t* o = job.dst + P.dst_off + (size_t)(y0 + ly0) * P.dst_stride + gx;
         const size_t ostep = (size_t)(kVidThreads / (kScaleTW / 4)) * P.dst_stride;
-        const uint8_t* mq = mid + 4 * q;
-        for (uint32_t ly = ly0; y0 + ly <= y1; ly += kVidThreads / (kScaleTW / 4), o += ostep) {
-            const uint4 rr = s_yr[ly];
-            const uint2 cc = s_yc[ly];
-            const uint32_t a0 = *reinterpret_cast<const uint32_t*>(mq + rr.x), a1 = *reinterpret_cast<const uint32_t*>(mq + rr.y);
-            const uint32_t a2 = *reinterpret_cast<const uint32_t*>(mq + rr.z), a3 = *reinterpret_cast<const uint32_t*>(mq + rr.w);
+        const uint32_t mq = mid_a + 4 * q;
+        uint32_t yr_a = smem_addr(s_yr) + ly0 * 16, yc_a = smem_addr(s_yc) + ly0 * 8;
+        for (uint32_t ly = ly0; y0 + ly <= y1; ly += kVidThreads / (kScaleTW / 4), o += ostep,
+                      yr_a += (kVidThreads / (kScaleTW / 4)) * 16, yc_a += (kVidThreads / (kScaleTW / 4)) * 8) {
+            const uint4 rr = lds128(yr_a);
+            const uint2 cc = lds64(yc_a);
+            const uint32_t a0 = lds32(mq + rr.x), a1 = lds32(mq + rr.y), a2 = lds32(mq + rr.z), a3 = lds32(mq + rr.w);
             // transpose 4 rows x 4 pixels into 4 pixels x 4 taps with byte permutes, then two dp2a per pixel
             const uint32_t lo01 = __byte_perm(a0, a1, 0x5140), hi01 = __byte_perm(a0, a1, 0x7362);   // (a0.b0,a1.b0,a0.b1,a1.b1), (.b2,.b3)
             const uint32_t lo23 = __byte_perm(a2, a3, 0x5140), hi23 = __byte_perm(a2, a3, 0x7362);
             const int c01 = (int)cc.x, c23 = (int)cc.y;
-            const uint32_t packed = tap4(__byte_perm(lo01, lo23, 0x5410), c01, c23) |
-                                    (tap4(__byte_perm(lo01, lo23, 0x7632), c01, c23) << 8) |
-                                    (tap4(__byte_perm(hi01, hi23, 0x5410), c01, c23) << 16) |
-                                    (tap4(__byte_perm(hi01, hi23, 0x7632), c01, c23) << 24);
+            const uint32_t v0 = tap4(__byte_perm(lo01, lo23, 0x5410), c01, c23), v1 = tap4(__byte_perm(lo01, lo23, 0x7632), c01, c23);
+            const uint32_t v2 = tap4(__byte_perm(hi01, hi23, 0x5410), c01, c23), v3 = tap4(__byte_perm(hi01, hi23, 0x7632), c01, c23);
+            const uint32_t packed = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
             if (word_ok) {
                 *reinterpret_cast<uint32_t*>(o) = packed;
             } else {
