@@ -131,10 +131,10 @@ int mxl_module_run_tick_host(mxl_module* m, uint64_t t, const mxl_host_ref* inpu
 {
     if (!m) MXL_FAIL(MXL_ERR_INVALID, "NULL module");
     if ((n_inputs && !inputs) || (n_outputs && !outputs)) MXL_FAIL(MXL_ERR_INVALID, "NULL terminal table");
-    if (n_inputs != m->inputs.size() || n_outputs != m->outputs.size())
-        MXL_FAIL(MXL_ERR_INVALID, "%s: expected %zu inputs / %zu outputs, got %u / %u", m->kind_name(), m->inputs.size(), m->outputs.size(), n_inputs, n_outputs);
     mxl_ctx* ctx = m->ctx;
     if (!ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "mxl_module_run_tick_host: context has no CUDA device; there is no CPU fallback");
+    if (n_inputs != m->inputs.size() || n_outputs != m->outputs.size())
+        MXL_FAIL(MXL_ERR_INVALID, "%s: expected %zu inputs / %zu outputs, got %u / %u", m->kind_name(), m->inputs.size(), m->outputs.size(), n_inputs, n_outputs);
     MXL_TRY(ctx->activate());
     // the slices are ordinary host memory and the call is synchronous: everything goes on the compute stream
     // (with copy overlap enabled, first wait for what the side streams still carry)

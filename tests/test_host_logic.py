@@ -101,6 +101,46 @@ def test_header_is_plain_c(tmp_path):
     assert r.returncode == 0, r.stdout
 
 
+def _build_c_example(mxl, tmp_path):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_engine")
+    libdir = os.path.dirname(mxl.api.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-O2", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                        os.path.join(root, "examples", "host_engine.c"), "-L", libdir, "-lmixlab_b200",
+                        "-Wl,-rpath," + libdir, "-o", exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    return exe
+
+
+def test_c_host_links_and_refuses_to_compute_without_a_device(mxl, tmp_path):
+    """examples/host_engine.c: the ABI from plain C (what a cgo / Rust FFI host does).  Without a GPU the compute entry
+    points must refuse with MXL_ERR_NO_DEVICE -- there is no CPU fallback."""
+    exe = _build_c_example(mxl, tmp_path)
+    r = subprocess.run([exe, "--no-device"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    assert "no CPU fallback" in r.stdout
+
+
+@pytest.mark.gpu
+def test_c_host_engine_host_slices_equal_graph(mxl, oracle, tmp_path):
+    """the same program on a GPU: config 1 tick by tick through host slices == one graph call, bit for bit; and the
+    checksum equals the oracle's."""
+    exe = _build_c_example(mxl, tmp_path)
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    assert "host-slice path == graph path" in r.stdout
+    # the program's sources are W.uniform_pm1(1..4) / W.uniform_01(5): recompute its checksum through the oracle
+    spt, ticks = 800, 12
+    ins = [W.uniform_pm1(1 + c, 2 * spt * ticks) for c in range(4)]
+    control = W.uniform_01(5, spt * ticks)
+    master, _ = oracle.mixer(ins, [0.0, -6.0, 3.0, -12.0], [1.0, 0.8, 0.5, 0.25], [0, 1, 0, 1], spt * ticks)
+    want = oracle.amplifier(master, control, 0.9, 0.5)
+    s = 0
+    for u in want.view(np.uint32).tolist():
+        s = (s * 1099511628211 + u) & 0xFFFFFFFFFFFFFFFF
+    assert ("checksum %016x" % s) in r.stdout, r.stdout
+
+
 def test_io_edge_kinds_are_not_provided(mxl, host_ctx):
     for kind in (mxl.MOD_MEDIA_SOURCE, 99):
         with pytest.raises(mxl.MxlError):

@@ -25,11 +25,14 @@ static float timed(cudaStream_t s0, cudaStream_t s1, void* d0, void* h0, void* d
     return ms;
 }
 
-int main()
+int main(int argc, char** argv)
 {
     const size_t n = 512ull << 20;
     void *h0, *h1, *d0, *d1;
-    cudaHostAlloc(&h0, n, cudaHostAllocDefault); cudaHostAlloc(&h1, n, cudaHostAllocDefault);
+    // `wc`: the upload buffer write-combined (not snooped): does the H2D side gain?
+    const bool wc = argc > 1 && !strcmp(argv[1], "wc");
+    cudaHostAlloc(&h0, n, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault); cudaHostAlloc(&h1, n, cudaHostAllocDefault);
+    if (wc) printf("{\"upload_buffer\": \"write-combined\"}\n");
     cudaMalloc(&d0, n); cudaMalloc(&d1, n);
     memset(h0, 1, n); memset(h1, 2, n);
     cudaStream_t s0, s1; cudaStreamCreate(&s0); cudaStreamCreate(&s1);
