@@ -178,3 +178,36 @@ def test_stream_output_feeds_only_while_live(mxl, oracle, ctx48):
         mod.stream_output_set_live(False)
         tick(stop)
         assert drain(mod) == ([], [])
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_randomized_ticks_against_the_oracle(mxl, oracle, ctx48, seed):
+    """random picture sizes, durations, offsets and gaps, calls of 1..12 ticks, audio beyond +-1: every fragment, every
+    job (timing, blank flag, pixels) as the oracle's."""
+    rng = np.random.default_rng(77 + seed)
+    sizes = [(560, 350), (640, 360), (320, 240)]
+    lays = {s: oracle.frame_layout(*s) for s in sizes}
+    orc = oracle.MonitorFeed(SR)
+    mod = ctx48.module(mxl.MOD_MONITOR)
+    tick = int(rng.integers(0, 5000))
+    na = nv = 0
+    for _ in range(10):
+        n = int(rng.integers(1, 13))
+        x = (W.uniform_pm1(int(rng.integers(0, 1 << 30)), 2 * SPT * n) * np.float32(1.2)).astype(np.float32)
+        vl = ctx48.video_line(n)
+        vids = {}
+        for k in range(n):
+            if rng.random() < 0.45:
+                s = sizes[int(rng.integers(0, len(sizes)))]
+                pix = W.random_bytes(int(rng.integers(0, 1 << 30)), lays[s].size)
+                dur = Fraction(1, int(rng.integers(10, 130)))
+                off = Fraction(int(rng.integers(0, SPT + 1)), SR)
+                vl.set(k, ctx48.frame(s[0], s[1], pix), duration=(dur.numerator, dur.denominator), offset=(off.numerator, off.denominator))
+                vids[k] = (pix, lays[s], dur, off)
+        mod.run_tick(tick * SPT, [vl, ctx48.stereo(x)], [])
+        for k in range(n):
+            orc.run_tick((tick + k) * SPT, x[2 * SPT * k:2 * SPT * (k + 1)], vids.get(k))
+        tick += n
+        if rng.random() < 0.2:
+            tick += int(rng.integers(1, 4))                          # the engine skipped ticks: a gap for the barrier
+        na, nv = compare(mod, orc, na, nv)

@@ -178,3 +178,28 @@ def test_queue_capacity_is_the_ring_buffers(mxl, ctx48):
     with pytest.raises(mxl.MxlError) as e:
         mod.stream_write_audio(1, (0, 1), one)
     assert e.value.status == mxl.ERR_LENGTH
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_randomized_pushes_against_the_oracle(mxl, oracle, ctx48, seed):
+    """random frame sizes (1..6000 samples), source ids, clock jumps, video frames early / late / in bursts, calls of
+    1..9 ticks: the device module and the oracle must agree on every sample, every gating decision and every offset."""
+    rng = np.random.default_rng(1000 + seed)
+    p = Pair(mxl, oracle, ctx48)
+    t_src = Fraction(int(rng.integers(0, 1000)), 7)
+    source_id, tick, tag = 1, int(rng.integers(0, 10_000)), 0
+    for _ in range(25):
+        for _ in range(int(rng.integers(0, 5))):
+            n = int(rng.integers(1, 6000))
+            p.audio(source_id, t_src, pcm(int(rng.integers(0, 1 << 30)), n))
+            t_src += Fraction(n // 2, SR)
+            if rng.random() < 0.08:
+                source_id += 1                                      # a new publisher connects
+                t_src = Fraction(int(rng.integers(0, 100_000)), 1000)
+        for _ in range(int(rng.integers(0, 3))):
+            jitter = Fraction(int(rng.integers(-3 * SPT, 6 * SPT)), SR)
+            p.video(source_id, t_src + jitter, tag, Fraction(1, int(rng.integers(24, 61))))
+            tag += 1
+        n_ticks = int(rng.integers(1, 10))
+        p.run(tick, n_ticks)
+        tick += n_ticks
