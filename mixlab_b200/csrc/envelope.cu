@@ -10,14 +10,14 @@
 //       TriggerOff{off: p, ..}) and, for an off, the transition q before it:
 //       off_amplitude = amplitude(TriggerOn{on: q}, p) -- a "latest two" scan over transition keys.
 // Both scans have trivial combine steps (max / latest-two), so they run as decoupled look-back
-// scans inside ONE kernel: a CTA owns a tile of 4096 consecutive samples (16 per thread, read once
+// scans inside ONE kernel: a CTA owns a tile of 2048 consecutive samples (16 per thread, read once
 // with four float4 loads), scans inside the tile with warp shuffles, publishes its tile aggregate,
 // and looks back over the preceding tiles 32 at a time (ballot + shuffle, no loops over lanes)
 // until the carry is decided: the nearest tile with any event decides scan (1), two transitions or
 // a tile whose inclusive value is known decide scan (3).  Every thread then starts the REFERENCE
 // state machine from its exact incoming state and walks its 16 samples, evaluating amplitude()
 // with the reference's f64 expressions (bit-exact: only IEEE +,-,*,/).
-// Line traffic is the algorithmic 8 B/sample; tile descriptors add 24 B per 4096 samples.  Tiles
+// Line traffic is the algorithmic 8 B/sample; tile descriptors add 24 B per 2048 samples.  Tiles
 // are handed out by an atomic ticket, so a tile only ever waits for tiles that already run.
 #include <stdlib.h>
 
@@ -29,8 +29,8 @@ namespace k {
 
 namespace {
 
-constexpr int kEnvThreads = 256;
-constexpr int kEnvPerThread = 16;     // 32 per thread (tiles of 8192) measured slower: 0.155 vs 0.130 ms per 2^25 samples
+constexpr int kEnvThreads = 128;      // 256 threads: 0.126 ms, 128: 0.117, 64: 0.120 (smaller CTAs wait less at the four barriers)
+constexpr int kEnvPerThread = 16;     // per 2^25 samples: 8 per thread 0.169 ms, 16: 0.117, 32: 0.155
 constexpr int kEnvTileSamples = kEnvThreads * kEnvPerThread;
 constexpr int kEnvWarps = kEnvThreads / 32;
 
@@ -99,7 +99,7 @@ __device__ __forceinline__ uint32_t wait_word(const unsigned long long* p, uint3
     return (uint32_t)(v >> 32) & 3u;
 }
 
-__global__ void __launch_bounds__(kEnvThreads, 6) envelope_kernel(const __grid_constant__ EnvBatch b)
+__global__ void __launch_bounds__(kEnvThreads, 12) envelope_kernel(const __grid_constant__ EnvBatch b)
 {
     pdl_prologue();
     const EnvInst& in = b.inst[blockIdx.y];
