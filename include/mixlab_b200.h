@@ -471,6 +471,14 @@ typedef struct mxl_stage_info {
                                 * (what a one-tick live call is bound by); always measured */
     float _pad;
 } mxl_stage_info;
+/* The same timings folded into PerformanceInfo.accounts (protocol/src/lib.rs:32-56; EngineStat::report,
+ * src/engine/timing.rs:45-60): one account per module that ran in the last call -- its stage's device time divided
+ * evenly among the stage's modules and by the ticks of the call, in microseconds per tick (`last`) -- and, first, the
+ * Engine account (module_id = -1): the host time of the last mxl_graph_run_ticks that no stage accounts for
+ * (planning, line bookkeeping, fork / join), per tick.  Needs mxl_graph_set_profiling(g, 1) before the run for the
+ * module accounts (else they are -1).  Returns the number of accounts written. */
+typedef struct mxl_perf_account { int32_t module_id; int32_t kind; float last_us; float host_us; } mxl_perf_account;
+MXL_API int mxl_graph_performance(mxl_graph *g, mxl_perf_account *out, uint32_t cap);
 MXL_API int mxl_graph_stage_count(mxl_graph *g);
 MXL_API int mxl_graph_stage_info(mxl_graph *g, uint32_t stage, mxl_stage_info *out);
 

@@ -112,6 +112,10 @@ class OutputDeviceParams(C.Structure):
     _fields_ = [("left", C.c_int32), ("right", C.c_int32), ("channels", C.c_uint32), ("_pad", C.c_uint32)]
 
 
+class PerfAccount(C.Structure):
+    _fields_ = [("module_id", C.c_int32), ("kind", C.c_int32), ("last_us", C.c_float), ("host_us", C.c_float)]
+
+
 class HostRef(C.Structure):
     """mxl_host_ref: one InputRef / OutputRef of the reference with host slices (io.rs:19-34,79-98)."""
     _fields_ = [("type", C.c_int32), ("connected", C.c_int32), ("samples", C.c_void_p), ("len", C.c_uint64),
@@ -272,6 +276,7 @@ def lib():
         "mxl_graph_set_stream_split": (i32, [vp, i32]),
         "mxl_graph_stage_count": (i32, [vp]),
         "mxl_graph_stage_info": (i32, [vp, u32, C.POINTER(StageInfo)]),
+        "mxl_graph_performance": (i32, [vp, C.POINTER(PerfAccount), u32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -940,6 +945,12 @@ class Graph:
             out.append(dict(kind=s.kind, n_modules=s.n_modules, n_launches=s.n_launches,
                             last_ms=s.last_ms, algorithmic_bytes=int(s.algorithmic_bytes), host_us=s.host_us))
         return out
+
+    def performance(self):
+        """PerformanceInfo.accounts: [(module_id or -1 for the Engine account, kind, last_us per tick, host_us per tick)]."""
+        arr = (PerfAccount * (len(self.modules) + 1))()
+        n = check(lib().mxl_graph_performance(self.h, arr, len(arr)))
+        return [(a.module_id, a.kind, a.last_us, a.host_us) for a in arr[:n]]
 
     def destroy(self):
         if self.h:

@@ -36,6 +36,8 @@ struct mxl_graph {
     bool profiling = false;
     bool timings_pending = false;
     bool split_streams = true;                                         // audio stages on ctx->stream_aux next to video stages
+    float last_call_host_us = 0.f;                                     // host time of the last run_ticks call
+    uint32_t last_call_ticks = 0;
 
     // plan
     std::vector<int> run_order;
@@ -265,6 +267,11 @@ int mxl_graph_run_ticks(mxl_graph* g, uint64_t tick0, uint32_t n_ticks)
     mxl_ctx* ctx = g->ctx;
     if (!ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "mxl_graph_run_ticks: context has no CUDA device; there is no CPU fallback");
     if (n_ticks == 0) return MXL_OK;
+    const auto call_t0 = std::chrono::steady_clock::now();
+    struct CallTimer {
+        mxl_graph* g; std::chrono::steady_clock::time_point t0; uint32_t ticks;
+        ~CallTimer() { g->last_call_host_us = std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - t0).count(); g->last_call_ticks = ticks; }
+    } call_timer{g, call_t0, n_ticks};
     MXL_TRY(ctx->activate());
     // a module whose params changed its terminals (Mixer::update re-creates itself, mixer.rs:40-44)
     for (size_t id = 0; id < g->modules.size() && !g->dirty; id++) {
@@ -390,6 +397,28 @@ int mxl_graph_set_profiling(mxl_graph* g, int enabled)
     if (!g) MXL_FAIL(MXL_ERR_INVALID, "NULL graph");
     g->profiling = enabled != 0;
     return MXL_OK;
+}
+
+int mxl_graph_performance(mxl_graph* g, mxl_perf_account* out, uint32_t cap)
+{
+    if (!g || (cap && !out)) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
+    if (g->dirty) MXL_TRY(build_plan(g));
+    collect_timings(g);
+    const float ticks = (float)(g->last_call_ticks ? g->last_call_ticks : 1);
+    uint32_t n = 0;
+    float staged_host = 0.f;
+    for (const Stage& s : g->stages) staged_host += s.last_launches ? s.last_host_us : 0.f;
+    if (n < cap) out[n] = mxl_perf_account{-1, -1, -1.f, std::max(0.f, g->last_call_host_us - staged_host) / ticks};   // PerformanceAccount::Engine
+    n++;
+    for (const Stage& s : g->stages) {
+        if (is_source(s.kind) || s.modules.empty()) continue;
+        const float share = 1.f / (float)s.modules.size() / ticks;
+        for (int id : s.modules) {
+            if (n < cap) out[n] = mxl_perf_account{id, s.kind, s.last_ms >= 0.f ? s.last_ms * 1000.f * share : -1.f, s.last_host_us * share};
+            n++;
+        }
+    }
+    return (int)std::min<uint32_t>(n, cap);
 }
 
 int mxl_graph_stage_count(mxl_graph* g)

@@ -235,3 +235,21 @@ def test_graph_stage_info_and_launch_count(mxl, ctx48):
     # one launch serves all ten modules of a kind
     assert launched <= 6
     g.destroy()
+
+
+def test_performance_accounts_shaped_like_engine_stat(mxl, ctx48):
+    """EngineStat::report (src/engine/timing.rs:45-60): an Engine account and one account per module that ran."""
+    d = W.config2_graph()
+    g, ids = W.build_graph(ctx48, d)
+    g.set_profiling(True)
+    g.run_ticks(0, 16)
+    g.run_ticks(16, 16)
+    acc = g.performance()
+    assert acc[0][0] == -1 and acc[0][3] >= 0.0                      # PerformanceAccount::Engine: host time outside the stages
+    mods = acc[1:]
+    assert sorted(a[0] for a in mods) == sorted(g.plan())            # every module of the run order, once
+    assert all(a[2] > 0.0 and a[3] > 0.0 for a in mods)              # device and host microseconds per tick
+    # the ten oscillators share one launch: equal shares
+    osc = [a[2] for a in mods if a[1] == mxl.MOD_OSCILLATOR]
+    assert len(osc) == 10 and max(osc) == min(osc)
+    g.destroy()
