@@ -226,6 +226,69 @@ __global__ void __launch_bounds__(kThreads) mixer_kernel(const __grid_constant__
     }
 }
 
+// One tick of a WIDE bus (many channels, few samples): the kernel above leaves a handful of threads walking all the
+// channels, 16 loads at a time.  Here a CTA owns 8 output vectors; its 256 threads first form the products of ALL
+// channels in parallel (8 vectors x 32 channel lanes, every load of the CTA in flight at once) into shared memory,
+// then one warp -- a lane per output float -- adds them up in channel order: the f32 accumulation order stays the
+// reference's, only the products were formed early (each is its own rounding, mixer.rs:62).
+constexpr int kMixWideVec = 8;
+__global__ void __launch_bounds__(kThreads) mixer_wide_kernel(const __grid_constant__ MixerLaunch p)
+{
+    pdl_prologue();
+    __shared__ float4 s_prod[kMixerMaxCh][kMixWideVec];     // (float)((double)x * gain)
+    __shared__ float4 s_raw[kMixerMaxCh][kMixWideVec];      // x, for the cue bus
+    const uint64_t n4 = p.len >> 2;
+    const int v = threadIdx.x & (kMixWideVec - 1), cl = threadIdx.x / kMixWideVec;       // 8 vectors x 32 channel lanes
+    const uint64_t i = (uint64_t)blockIdx.x * kMixWideVec + v;
+    constexpr int kLanes = kThreads / kMixWideVec;
+    constexpr int kPer = (kMixerMaxCh + kLanes - 1) / kLanes;
+    float4 x[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; k++) {
+        const int ch = cl + k * kLanes;
+        const float* src = ch < p.channels ? p.ch[ch].in : nullptr;
+        x[k] = (src && i < n4) ? ldg_stream(src + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; k++) {
+        const int ch = cl + k * kLanes;
+        if (ch < p.channels) {
+            const double g = p.ch[ch].gain;
+            s_prod[ch][v] = make_float4(mix1(x[k].x, g), mix1(x[k].y, g), mix1(x[k].z, g), mix1(x[k].w, g));
+            s_raw[ch][v] = x[k];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < kMixWideVec * 4) {                    // one warp: lane = (vector, component)
+        const int ov = threadIdx.x >> 2, oc = threadIdx.x & 3;
+        const uint64_t o = ((uint64_t)blockIdx.x * kMixWideVec + ov) * 4 + oc;
+        if (o < (n4 << 2)) {
+            float m = p.accumulate ? p.master[o] : 0.f, c = p.accumulate ? p.cue[o] : 0.f;     // util::zero (mixer.rs:54-55)
+            const float* prod = reinterpret_cast<const float*>(&s_prod[0][ov]) + oc;
+            const float* raw = reinterpret_cast<const float*>(&s_raw[0][ov]) + oc;
+            for (int ch = 0; ch < p.channels; ch++) {
+                m += prod[ch * kMixWideVec * 4];
+                if (p.ch[ch].cue) c += raw[ch * kMixWideVec * 4];
+            }
+            p.master[o] = m;
+            p.cue[o] = c;
+        }
+    }
+    // scalar tail (len % 4 floats), handled by the first threads of block 0
+    const uint64_t tail0 = n4 << 2;
+    if (blockIdx.x == 0 && tail0 + threadIdx.x < p.len) {
+        const uint64_t t = tail0 + threadIdx.x;
+        float m = p.accumulate ? p.master[t] : 0.f, c = p.accumulate ? p.cue[t] : 0.f;
+        for (int ch = 0; ch < p.channels; ch++) {
+            float xv = p.ch[ch].in ? p.ch[ch].in[t] : 0.f;
+            m += mix1(xv, p.ch[ch].gain);
+            if (p.ch[ch].cue) c += xv;
+        }
+        p.master[t] = m;
+        p.cue[t] = c;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Amplifier: amplifier.rs:52-57,71-73.  One thread = 4 frames = 8 stereo floats + 4 control floats.
 // ------------------------------------------------------------------------------------------
@@ -645,7 +708,13 @@ int launch_mixer(mxl_ctx* ctx, const MixerLaunch& p)
     int unroll = 2;
     if (const char* e = getenv("MXL_MIXER_UNROLL")) unroll = atoi(e);
     const uint64_t machine = (uint64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148) * 2048;
-    if (n4 < machine && p.channels > 4) {
+    static const bool wide_ok = getenv("MXL_MIXER_NO_WIDE") == nullptr;
+    if (wide_ok && p.channels >= 16 && n4 * (uint64_t)p.channels < machine) {
+        // one tick of a wide bus: all products in parallel, then the ordered sum (mixer_wide_kernel)
+        const unsigned g = (unsigned)((n4 + kMixWideVec - 1) / kMixWideVec);
+        MXL_TIMED(ctx, "mixer_kernel");
+        launch_chained(ctx, mixer_wide_kernel, dim3(g ? g : 1), dim3(kThreads), 0, p);
+    } else if (n4 < machine && p.channels > 4) {
         unsigned g = blocks_for(n4);
         MXL_TIMED(ctx, "mixer_kernel");
         launch_chained(ctx, mixer_kernel<1, 16>, dim3(g ? g : 1), dim3(kThreads), 0, p);

@@ -120,6 +120,8 @@ struct FmSine : mxl_module {                          // src/module/fm_sine.rs
 
 struct Mixer : mxl_module {                           // src/module/mixer.rs
     std::vector<mxl_mixer_channel_params> channels;
+    std::vector<double> channel_gain;                 // fader * gain.to_linear() (mixer.rs:59), formed when the params arrive:
+                                                      // the reference recomputes the same product (a powf) every tick
     Mixer(const mxl_mixer_params* in)
     {
         kind = MXL_MOD_MIXER;
@@ -129,6 +131,8 @@ struct Mixer : mxl_module {                           // src/module/mixer.rs
     {
         channels.clear();
         if (in && in->channels) channels.assign(in->channels, in->channels + in->n_channels);
+        channel_gain.resize(channels.size());
+        for (size_t i = 0; i < channels.size(); i++) channel_gain[i] = channels[i].fader * db_to_linear(channels[i].gain_db);
         inputs.clear();
         for (size_t i = 0; i < channels.size(); i++) inputs.push_back(labeled(MXL_LINE_STEREO, std::to_string(i + 1)));   // mixer.rs:23-25
         outputs = {labeled(MXL_LINE_STEREO, "Master"), labeled(MXL_LINE_STEREO, "Cue")};                                  // mixer.rs:26-29
@@ -597,7 +601,7 @@ static int run_mixers(mxl_ctx* ctx, mxl_module* const* mods, int n, const IoSet*
             for (uint32_t c = 0; c < take; c++) {
                 const mxl_mixer_channel_params& cp = m->channels[done + c];
                 p.ch[c].in = io[i].in[done + c] ? io[i].in[done + c]->dev : nullptr;
-                p.ch[c].gain = cp.fader * db_to_linear(cp.gain_db);       // mixer.rs:59
+                p.ch[c].gain = m->channel_gain[done + c];                 // mixer.rs:59
                 p.ch[c].cue = cp.cue ? 1 : 0;
                 if (bytes && io[i].in[done + c]) *bytes += 4 * len;
             }
