@@ -29,7 +29,7 @@ namespace k {
 
 namespace {
 
-constexpr int kEnvThreads = 128;      // 256 threads: 0.126 ms, 128: 0.117, 64: 0.120 (smaller CTAs wait less at the four barriers)
+constexpr int kEnvThreads = 128;      // 256 threads: 0.126 ms, 128: 0.117 (0.110 at 16 CTAs per SM), 64: 0.120: more, smaller CTAs cover the look-backs
 constexpr int kEnvPerThread = 16;     // per 2^25 samples: 8 per thread 0.169 ms, 16: 0.117, 32: 0.155
 constexpr int kEnvTileSamples = kEnvThreads * kEnvPerThread;
 constexpr int kEnvWarps = kEnvThreads / 32;
@@ -99,7 +99,7 @@ __device__ __forceinline__ uint32_t wait_word(const unsigned long long* p, uint3
     return (uint32_t)(v >> 32) & 3u;
 }
 
-__global__ void __launch_bounds__(kEnvThreads, 12) envelope_kernel(const __grid_constant__ EnvBatch b)
+__global__ void __launch_bounds__(kEnvThreads, 16) envelope_kernel(const __grid_constant__ EnvBatch b)
 {
     pdl_prologue();
     const EnvInst& in = b.inst[blockIdx.y];
