@@ -230,3 +230,69 @@ def test_engine_walker_cycle_reads_disconnected(oracle):
     order = g.last_order()
     assert order[-1] == m and sorted(order) == [a, s, p, m]
     assert g.connect(s, 0, p, 0) == 0 and g.connect(m, 0, s, 0) == -3 and g.connect(m, 9, a, 0) == -1 and g.connect(m, 0, a, 5) == -2
+
+
+# ---- the neighbours of the path (Python restatements): internal consistency, no GPU -----------------------------
+def test_monitor_feed_oracle_invariants(oracle):
+    """EncodeStream's bookkeeping (src/video/encode.rs:46-100,184-221): fragments are consecutive 2048-sample windows of
+    the packed stream with a clock advancing 1024 / SR each; video jobs tile the time line without gaps or overlaps
+    (each starts where the previous one ended, in time-base units) and blank fillers appear only where no frame covers."""
+    from fractions import Fraction
+    sr, spt = 48000, 800
+    rng = np.random.default_rng(5)
+    orc = oracle.MonitorFeed(sr)
+    lay = oracle.frame_layout(560, 350)
+    stream = []
+    for k in range(60):
+        x = rng.uniform(-1.3, 1.3, 2 * spt).astype(np.float32)
+        stream.append(oracle.pcm_pack_i16(x))
+        v = None
+        if rng.random() < 0.4:
+            v = (np.full(lay.size, k, np.uint8), lay, Fraction(1, int(rng.integers(20, 70))), Fraction(int(rng.integers(0, spt)), sr))
+        orc.run_tick((1000 + k) * spt, x, v)
+    packed = np.concatenate(stream)
+    for i, (dec, dur, frag) in enumerate(orc.audio_out):
+        assert dec == Fraction(1024 * i, sr) and dur == Fraction(1024, sr)
+        assert np.array_equal(frag, packed[2048 * i:2048 * (i + 1)])
+    assert len(orc.audio_out) == (packed.size - 1) // 2048                     # a fragment leaves only when MORE than 2048 are buffered
+    end = 0
+    for pts, dur, blank, pix in orc.video_out:
+        assert pts == end and dur >= 0
+        end = pts + dur
+        assert pix.size == lay.size and (not blank or np.array_equal(pix, orc.blank))
+    assert end == orc._round_to_base(orc.video_timestamp, orc.time_base)
+
+
+def test_stream_input_oracle_conserves_samples(oracle):
+    """StreamInput (stream_input.rs:92-124): every pushed sample comes out exactly once, in order, converted by
+    sample / 32768; ticks after the queue ran dry are silence."""
+    from fractions import Fraction
+    sr, spt = 48000, 800
+    rng = np.random.default_rng(6)
+    orc = oracle.StreamInput(sr)
+    pushed = []
+    t = Fraction(0)
+    for _ in range(30):
+        n = int(rng.integers(1, 5000))
+        d = rng.integers(-32768, 32768, n).astype(np.int16)
+        pushed.append(d)
+        orc.write_audio(1, t, d)
+        t += Fraction(n // 2, sr)
+    total = sum(d.size for d in pushed)
+    out = np.concatenate([orc.run_tick(k * spt, 2 * spt)[1] for k in range(total // (2 * spt) + 3)])
+    want = np.concatenate(pushed).astype(np.float32) / np.float32(32768.0)
+    assert np.array_equal(out[:total], want) and not out[total:].any()
+
+
+def test_output_device_oracle_routes_and_clips(oracle):
+    """OutputDevice (output_device.rs:177-207): routed channels carry the side's samples, the others silence; clip iff
+    a routed sample is outside [-1, 1]."""
+    x = np.array([0.5, -2.0] * 8, np.float32)                                 # left 0.5, right -2.0
+    dev = oracle.OutputDevice(2, None, 4)                                     # only the left side is routed
+    assert dev.run_tick(x) is False
+    out = dev.pop(1 << 10).reshape(8, 4)
+    assert np.all(out[:, 2] == 0.5) and not out[:, [0, 1, 3]].any()
+    dev.update(2, 3)
+    assert dev.run_tick(x) is True                                            # now the right side (-2.0) is routed: clip
+    out = dev.pop(1 << 10).reshape(8, 4)
+    assert np.all(out[:, 3] == -2.0) and np.all(out[:, 2] == 0.5)
