@@ -457,8 +457,19 @@ MXL_API int mxl_graph_run_ticks(mxl_graph *g, uint64_t tick0, uint32_t n_ticks);
 /* Audio and video sub-graphs share no line, so by default their stages run on two streams of the
  * context concurrently (joined before the call returns to the stream's order).  0 = one stream. */
 MXL_API int mxl_graph_set_stream_split(mxl_graph *g, int enabled);
-/* Output line of a module after the last run (borrowed; valid until the next run or edit). */
+/* Output line of a module after the last run (borrowed; valid until the next run or edit).
+ * Fused voice groups: a sub-graph Oscillator -> EqThree -> StereoPanner -> Mixer [-> Meter] whose interior lines no
+ * module outside it consumes runs as ONE launch (the reference runs the five modules one after another over fresh
+ * buffers, src/engine.rs:464-507).  Oscillator and StereoPanner lines inside such a group are written only when
+ * the host observes them: asking for one here (or mxl_graph_pin_output) makes it observed from the next run on; asked
+ * after a run that did not write it, this call returns NULL and says so.  Mixer, Meter and EqThree outputs are always
+ * written.  Results are those of the staged path (same kernels' arithmetic, same channel order). */
 MXL_API mxl_line *mxl_graph_output(mxl_graph *g, int module_id, uint32_t out_index);
+MXL_API int mxl_graph_pin_output(mxl_graph *g, int module_id, uint32_t out_index);
+/* 0 = every module runs as its own stage (default 1). */
+MXL_API int mxl_graph_set_fusion(mxl_graph *g, int enabled);
+/* mxl_stage_info.kind of a fused voice group's stage (not a module kind) */
+#define MXL_STAGE_FUSED_VOICE_MIX 1000
 /* Per-launch device timings, shaped like EngineStat (src/engine/timing.rs:46-60,86-94). */
 MXL_API int mxl_graph_set_profiling(mxl_graph *g, int enabled);
 typedef struct mxl_stage_info {

@@ -27,6 +27,7 @@ MOD_AMPLIFIER, MOD_ENVELOPE, MOD_EQ_THREE, MOD_FM_SINE, MOD_MIXER, MOD_MONITOR =
 MOD_OSCILLATOR, MOD_OUTPUT_DEVICE, MOD_PLOTTER, MOD_STEREO_PANNER, MOD_STEREO_SPLITTER = 6, 7, 8, 9, 10
 MOD_STREAM_INPUT, MOD_STREAM_OUTPUT, MOD_TRIGGER, MOD_VIDEO_MIXER, MOD_MEDIA_SOURCE = 11, 12, 13, 14, 15
 MOD_METER, MOD_SOURCE_MONO, MOD_SOURCE_STEREO, MOD_SOURCE_VIDEO, MOD_PCM_SINK = 32, 33, 34, 35, 36
+STAGE_FUSED_VOICE_MIX = 1000
 
 WAVE_ON, WAVE_OFF, WAVE_SINE, WAVE_SQUARE, WAVE_TRIANGLE, WAVE_SAW = 0, 1, 2, 3, 4, 5
 GATE_OPEN, GATE_CLOSED = 0, 1
@@ -272,6 +273,8 @@ def lib():
         "mxl_graph_plan": (i32, [vp, C.POINTER(C.c_int), u32]),
         "mxl_graph_run_ticks": (i32, [vp, u64, u32]),
         "mxl_graph_output": (vp, [vp, i32, u32]),
+        "mxl_graph_pin_output": (i32, [vp, i32, u32]),
+        "mxl_graph_set_fusion": (i32, [vp, i32]),
         "mxl_graph_set_profiling": (i32, [vp, i32]),
         "mxl_graph_set_stream_split": (i32, [vp, i32]),
         "mxl_graph_stage_count": (i32, [vp]),
@@ -925,10 +928,20 @@ class Graph:
     def output(self, mid, out_index):
         h = lib().mxl_graph_output(self.h, mid, out_index)
         if not h:
+            err = last_error()
+            if "fused voice group" in err:
+                raise MxlError(ERR_INVALID, err)
             return None
         if lib().mxl_line_type_of(h) == LINE_VIDEO:
             return VideoLine(self.ctx, handle=h, owned=False)
         return Line(self.ctx, 0, 0, handle=h, owned=False)
+
+    def pin_output(self, mid, out_index):
+        """Keep a line inside a fused voice group observable (mxl_graph_pin_output)."""
+        check(lib().mxl_graph_pin_output(self.h, mid, out_index))
+
+    def set_fusion(self, on):
+        check(lib().mxl_graph_set_fusion(self.h, 1 if on else 0))
 
     def set_profiling(self, on):
         check(lib().mxl_graph_set_profiling(self.h, 1 if on else 0))

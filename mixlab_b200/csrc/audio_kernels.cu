@@ -8,6 +8,7 @@
 
 #include "dsp_math.cuh"
 #include "kernels.h"
+#include "osc_core.cuh"
 
 namespace mxl {
 namespace k {
@@ -33,24 +34,6 @@ inline unsigned blocks_for(uint64_t items, int threads = kThreads)
 // ------------------------------------------------------------------------------------------
 // Oscillator: oscillator.rs:73-89
 // ------------------------------------------------------------------------------------------
-// `(t + i as u64) as f64 / SAMPLE_RATE as f64` (correctly rounded quotient) `* freq`: oscillator.rs:74-75
-__device__ __forceinline__ double osc_phase(double seq, double sr, double inv_sr, double freq)
-{
-    return div_by_const(seq, sr, inv_sr) * freq;
-}
-
-__device__ __forceinline__ float osc_wave(double n, int wf)
-{
-    switch (wf) {
-    case MXL_WAVE_SINE: return (float)wave_sine(n);
-    case MXL_WAVE_SQUARE: return (float)sign_bit_f64(wave_sine(n));
-    case MXL_WAVE_SAW: return (float)wave_saw(n);
-    case MXL_WAVE_TRIANGLE: return (float)wave_triangle(n);
-    case MXL_WAVE_ON: return 1.0f;
-    default: return 0.0f;
-    }
-}
-
 __global__ void __launch_bounds__(kThreads) oscillator_kernel(const __grid_constant__ OscBatch b)
 {
     pdl_prologue();
@@ -72,21 +55,7 @@ __global__ void __launch_bounds__(kThreads) oscillator_kernel(const __grid_const
             for (int j = 0; j < 4; j++) n[j] = osc_phase((double)(b.t0 + f0 + j), sr, inv_sr, freq);
         }
         float s[4];
-        // the waveform is the same for every sample of an instance: branch once, not per sample
-        if (wf == MXL_WAVE_SINE || wf == MXL_WAVE_SQUARE) {
-            double x[4], y[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) x[j] = n[j] * kTwoPi;          // oscillator.rs:25-27
-            sin_f64x4(x, y);
-#pragma unroll
-            for (int j = 0; j < 4; j++) s[j] = (float)(wf == MXL_WAVE_SINE ? y[j] : sign_bit_f64(y[j]));
-        } else if (wf == MXL_WAVE_SAW) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) s[j] = (float)wave_saw(n[j]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) s[j] = osc_wave(n[j], wf);
-        }
+        osc_wave4(wf, n, s);
         if (in.mono) st4(in.mono + f0, make_float4(s[0], s[1], s[2], s[3]));
         if (in.stereo) {
             st4(in.stereo + 2 * f0, make_float4(s[0], s[0], s[1], s[1]));
@@ -778,7 +747,9 @@ int launch_meter(mxl_ctx* ctx, const MeterBatch& b, uint32_t n_slots)
     if (b.n <= 0 || n_slots == 0) return MXL_OK;
     MXL_TIMED(ctx, "meter_kernel");
     const uint64_t machine = (uint64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148) * 16;     // warps that fill every SM's schedulers 4 deep
-    if ((uint64_t)n_slots * b.n >= machine) {
+    // Even ticks always take the warp kernel: its summation order (lane-strided vectors, then the xor tree) is the
+    // one the fused voice kernel reproduces, so a graph gives the same meter bits fused or staged, one tick or many.
+    if ((uint64_t)n_slots * b.n >= machine || (b.spt & 1u) == 0) {
         dim3 grid((n_slots + kMeterWarps - 1) / kMeterWarps, b.n);
         launch_chained(ctx, meter_warp_kernel, grid, dim3(kMeterThreads), 0, b, n_slots);
     } else {

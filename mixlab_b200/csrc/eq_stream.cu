@@ -32,63 +32,14 @@
 // Roofline: 8 B/sample of line traffic against ~47 FP64 operations per sample (34 exact + 8 zero
 // pass + ~4 scan + halo): at the measured 64 FP64 lanes/clk/SM (tools/pipe_rates.cu) the FP64 pipe
 // allows 0.40 of the HBM copy peak, so this kernel is FP64-issue-bound, not HBM-bound.
-#include "eq_core.cuh"
-#include "eq_plan.h"
-#include "kernels.h"
+#include "eq_stream.cuh"
 
 namespace mxl {
 namespace k {
 
 namespace {
 
-constexpr int kT = kEqStreamThreads;
-constexpr int kEqXchDoubles = 2 * (kT / 32) * 8 + 2 * 10 * 32;    // warp aggregates, final lane-31 values, lane table
-
-__device__ __forceinline__ int tri(int r, int c) { return r * (r + 1) / 2 + c; }
-
-__device__ __forceinline__ void tri_apply(const double* A, const double x[4], double y[4])
-{
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        double acc = 0.0;
-#pragma unroll
-        for (int c = 0; c <= r; c++) acc = fma(A[tri(r, c)], x[c], acc);
-        y[r] = acc;
-    }
-}
-
-// 16-byte slot of (row r, vector v) in a tile of VPR vectors per row.  Eight consecutive rows must
-// land in eight different 16-byte bank groups for a fixed v (thread-per-row float4 accesses are served
-// eight lanes at a time), and a row's VPR vectors stay inside the row (coalesced staging).
-template <int VPR>
-__device__ __forceinline__ int slot_of(int r, int v)
-{
-    constexpr int kRowsPerLine = VPR >= 8 ? 1 : 8 / VPR;          // rows sharing one 128-byte bank line
-    constexpr int kMask = VPR >= 8 ? 7 : VPR - 1;
-    return r * VPR + (v ^ ((r / kRowsPerLine) & kMask));
-}
-
-template <int LC>
-struct RowIo {
-    float4* tile; int r;
-    __device__ __forceinline__ EqF4 load(int v) const
-    {
-        const float4 x = tile[slot_of<LC / 4>(r, v)];
-        return EqF4{x.x, x.y, x.z, x.w};
-    }
-    __device__ __forceinline__ void store(int v, EqF4 y) { tile[slot_of<LC / 4>(r, v)] = make_float4(y.x, y.y, y.z, y.w); }
-};
-
-struct ParamTab {
-    const EqStreamBatch& b;
-    __device__ __forceinline__ double v(int j, int e) const { return b.V[j][e]; }
-};
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
-{
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
-}
+using namespace eqs;
 
 template <int LC>
 __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ EqStreamBatch b)
@@ -100,7 +51,8 @@ __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ E
     double* xch = reinterpret_cast<double*>(eq_smem + (size_t)kT * LC * sizeof(float));   // kEqXchDoubles
     const EqStreamInst& in = b.inst[blockIdx.y];
     const int tid = threadIdx.x;
-    const int halo = (int)b.halo;
+    const EqStreamConsts& q = b.eq;
+    const int halo = (int)q.halo;
     const int U = kT - halo;
     const int64_t c0 = (int64_t)blockIdx.x * U - halo;        // chunk of thread 0
     const int64_t c = c0 + tid;
@@ -142,116 +94,25 @@ __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ E
     for (int e = 0; e < 8; e++) v[e] = 0.0;
     if (active) {
 #pragma unroll
-        for (int e = 0; e < 8; e++) v[e] = b.K[e];
-        ParamTab tab{b};
+        for (int e = 0; e < 8; e++) v[e] = q.K[e];
+        ConstTab tab{q};
         eq_zero_state_dot<LC>(row, tab, v);
         if (c == 0) {                                      // v_0 = A p_init + z_0
             const double pl[4] = {st[0], st[1], st[2], st[3]}, ph[4] = {st[4], st[5], st[6], st[7]};
             double yl[4], yh[4];
-            tri_apply(b.pow_lo[0], pl, yl);
-            tri_apply(b.pow_hi[0], ph, yh);
+            tri_apply(q.pow_lo[0], pl, yl);
+            tri_apply(q.pow_hi[0], ph, yh);
 #pragma unroll
             for (int e = 0; e < 4; e++) { v[e] += yl[e]; v[4 + e] += yh[e]; }
         }
     }
 
     // a non-finite carry (NaN / inf input in my chunk, or a non-finite stored state): remember the first such chunk
-    if (active) {
-        uint32_t bad = 0;
-#pragma unroll
-        for (int e = 0; e < 8; e++) bad |= ((uint32_t)__double2hiint(v[e]) & 0x7ff00000u) == 0x7ff00000u ? 1u : 0u;
-        if (bad) atomicMin(in.poison, (uint32_t)c);
-    }
+    if (active && any_non_finite(v)) atomicMin(in.poison, (uint32_t)c);
 
-    // ---- 3. scan.  Inside a warp: Hillis-Steele with shuffles, v_i += A^(2^d) v_(i - 2^d), only the
-    //         levels the cascade still hears.  Across warps: the inclusive value of a warp's last lane
-    //         is its aggregate; the state entering warp w is P = agg[w-1] + A^32 agg[w-2] + A^64 agg[w-3]
-    //         (as many terms as the cascade still hears), and lane l adds A^(l+1) P from a per-lane
-    //         table.  Two block barriers in all. ----
-    const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-    for (int d = 0; d < 5; d++) {
-        const bool lo_live = d < (int)b.lev_lo, hi_live = d < (int)b.lev_hi;
-        if (!lo_live && !hi_live) break;
-        double o[8];
-#pragma unroll
-        for (int e = 0; e < 4; e++) o[e] = __shfl_up_sync(0xffffffffu, v[e], 1 << d);
-        if (hi_live) {
-#pragma unroll
-            for (int e = 4; e < 8; e++) o[e] = __shfl_up_sync(0xffffffffu, v[e], 1 << d);
-        }
-        if (lane >= (1 << d)) {
-            double y[4];
-            if (lo_live) {
-                tri_apply(b.pow_lo[d], o, y);
-#pragma unroll
-                for (int e = 0; e < 4; e++) v[e] += y[e];
-            }
-            if (hi_live) {
-                tri_apply(b.pow_hi[d], o + 4, y);
-#pragma unroll
-                for (int e = 0; e < 4; e++) v[4 + e] += y[e];
-            }
-        }
-    }
-    double2* agg = reinterpret_cast<double2*>(xch);              // [8 warps][4 double2]: warp aggregates
-    double2* fin = agg + (kT / 32) * 4;                          // [8 warps][4 double2]: final value of lane 31
-    double* lane_tab = xch + 2 * (kT / 32) * 8;                  // [2][10][32]
-    if (lane == 31) {
-        agg[warp * 4 + 0] = make_double2(v[0], v[1]); agg[warp * 4 + 1] = make_double2(v[2], v[3]);
-        agg[warp * 4 + 2] = make_double2(v[4], v[5]); agg[warp * 4 + 3] = make_double2(v[6], v[7]);
-    }
-    for (int i = tid; i < 2 * 10 * 32; i += kT) lane_tab[i] = b.lane_pow[i];
-    __syncthreads();
-    if (warp > 0) {
-        double P[8];
-        {
-            const double2 a0 = agg[(warp - 1) * 4 + 0], a1 = agg[(warp - 1) * 4 + 1];
-            const double2 a2 = agg[(warp - 1) * 4 + 2], a3 = agg[(warp - 1) * 4 + 3];
-            P[0] = a0.x; P[1] = a0.y; P[2] = a1.x; P[3] = a1.y; P[4] = a2.x; P[5] = a2.y; P[6] = a3.x; P[7] = a3.y;
-        }
-#pragma unroll
-        for (int k = 1; k <= 2; k++) {                     // A^(32k) = pow[4 + k]
-            if (warp - 1 - k < 0) break;
-            const bool lo_live = k < (int)b.back_lo, hi_live = k < (int)b.back_hi;
-            if (!lo_live && !hi_live) break;
-            const double2* a = agg + (warp - 1 - k) * 4;
-            double y[4];
-            if (lo_live) {
-                const double2 a0 = a[0], a1 = a[1];
-                const double o[4] = {a0.x, a0.y, a1.x, a1.y};
-                tri_apply(b.pow_lo[4 + k], o, y);
-#pragma unroll
-                for (int e = 0; e < 4; e++) P[e] += y[e];
-            }
-            if (hi_live) {
-                const double2 a2 = a[2], a3 = a[3];
-                const double o[4] = {a2.x, a2.y, a3.x, a3.y};
-                tri_apply(b.pow_hi[4 + k], o, y);
-#pragma unroll
-                for (int e = 0; e < 4; e++) P[4 + e] += y[e];
-            }
-        }
-        double Al[10], Ah[10];
-#pragma unroll
-        for (int q = 0; q < 10; q++) { Al[q] = lane_tab[q * 32 + lane]; Ah[q] = lane_tab[(10 + q) * 32 + lane]; }
-        double y[4];
-        tri_apply(Al, P, y);
-#pragma unroll
-        for (int e = 0; e < 4; e++) v[e] += y[e];
-        tri_apply(Ah, P + 4, y);
-#pragma unroll
-        for (int e = 0; e < 4; e++) v[4 + e] += y[e];
-    }
-    // start state of my chunk = inclusive value of the previous thread
+    // ---- 3. scan (eq_stream.cuh): two block barriers ----
     double S[8];
-#pragma unroll
-    for (int e = 0; e < 8; e++) S[e] = __shfl_up_sync(0xffffffffu, v[e], 1);
-    if (lane == 31) {
-        fin[warp * 4 + 0] = make_double2(v[0], v[1]); fin[warp * 4 + 1] = make_double2(v[2], v[3]);
-        fin[warp * 4 + 2] = make_double2(v[4], v[5]); fin[warp * 4 + 3] = make_double2(v[6], v[7]);
-    }
-    __syncthreads();
+    scan_start_states(q, v, S, xch, tid);
 
     // ---- 4. exact re-run of the owned chunks ----
     const bool owner = active && tid >= halo;
@@ -263,11 +124,6 @@ __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ E
             p = EqPoles{st[0], st[1], st[2], st[3], st[4], st[5], st[6], st[7]};
             hist[0] = st[8]; hist[1] = st[9]; hist[2] = st[10];
         } else {                                           // c > 0 and tid >= halo >= 1
-            if (lane == 0) {
-                const double2 a0 = fin[(warp - 1) * 4 + 0], a1 = fin[(warp - 1) * 4 + 1];
-                const double2 a2 = fin[(warp - 1) * 4 + 2], a3 = fin[(warp - 1) * 4 + 3];
-                S[0] = a0.x; S[1] = a0.y; S[2] = a1.x; S[3] = a1.y; S[4] = a2.x; S[5] = a2.y; S[6] = a3.x; S[7] = a3.y;
-            }
             p = EqPoles{S[0], S[1], S[2], S[3], S[4], S[5], S[6], S[7]};
             const float4 prev = tile[slot_of<VPR>(tid - 1, VPR - 1)];      // last vector of the chunk before mine
             hist[0] = (double)prev.y; hist[1] = (double)prev.z; hist[2] = (double)prev.w;
@@ -277,7 +133,7 @@ __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ E
     }
     __syncthreads();                                       // every history read precedes any overwrite
     if (owner) {
-        const EqGains g{b.c_lo, b.c_hi, in.g_lo, in.g_mid, in.g_hi};
+        const EqGains g{q.c_lo, q.c_hi, in.g_lo, in.g_mid, in.g_hi};
         if (count == LC) {
             eq_run_chunk_skewed<LC>(p, hist, row, g);
         } else {                                           // ragged end of the call: one thread, sequential form
@@ -355,7 +211,7 @@ int launch_lc(mxl_ctx* ctx, const EqStreamBatch& b)
         MXL_CUDA(cudaFuncSetAttribute(eq_stream_kernel<LC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->eq_stream_smem_set |= 1u << (LC / 16);
     }
-    const uint32_t U = kT - b.halo;
+    const uint32_t U = kT - b.eq.halo;
     dim3 grid((b.n_chunks + U - 1) / U, b.n);
     MXL_TIMED(ctx, "eq_stream_kernel");
     launch_chained(ctx, eq_stream_kernel<LC>, grid, dim3(kT), smem, b);
@@ -372,14 +228,15 @@ int launch_eq_stream(mxl_ctx* ctx, const EqStreamBatch& b)
     if (!ctx || !ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "no CUDA device bound to this context");
     MXL_TRY(ctx->activate());
     if (b.n <= 0 || b.frames == 0) return MXL_OK;
-    if (b.halo == 0 || b.halo > kT / 2 || b.lev_lo > (uint32_t)kEqPlanLevels || b.lev_hi > (uint32_t)kEqPlanLevels ||
-        b.back_lo > 3 || b.back_hi > 3 || !b.lane_pow)
-        MXL_FAIL(MXL_ERR_INVALID, "eq_stream_kernel: bad plan (chunk %u, halo %u, levels %u/%u)", b.chunk, b.halo, b.lev_lo, b.lev_hi);
-    switch (b.chunk) {
+    const EqStreamConsts& q = b.eq;
+    if (q.halo == 0 || q.halo > (uint32_t)eqs::kT / 2 || q.lev_lo > (uint32_t)kEqPlanLevels || q.lev_hi > (uint32_t)kEqPlanLevels ||
+        q.back_lo > 3 || q.back_hi > 3 || !q.lane_pow)
+        MXL_FAIL(MXL_ERR_INVALID, "eq_stream_kernel: bad plan (chunk %u, halo %u, levels %u/%u)", q.chunk, q.halo, q.lev_lo, q.lev_hi);
+    switch (q.chunk) {
     case 16: return launch_lc<16>(ctx, b);
     case 32: return launch_lc<32>(ctx, b);
     case 64: return launch_lc<64>(ctx, b);
-    default: MXL_FAIL(MXL_ERR_INVALID, "eq_stream_kernel: unsupported chunk length %u", b.chunk);
+    default: MXL_FAIL(MXL_ERR_INVALID, "eq_stream_kernel: unsupported chunk length %u", q.chunk);
     }
 }
 

@@ -21,6 +21,7 @@ struct Stage {
     int level = 0;
     int kind = 0;
     std::vector<int> modules;
+    int fused = -1;                     // index into mxl_graph::fused for a MXL_STAGE_FUSED_VOICE_MIX stage
     float last_ms = -1.f;
     int last_launches = 0;
     uint64_t last_bytes = 0;
@@ -36,6 +37,12 @@ struct mxl_graph {
     bool profiling = false;
     bool timings_pending = false;
     bool split_streams = true;                                         // audio stages on ctx->stream_aux next to video stages
+    bool fusion = true;                                                // Osc -> EqThree -> Panner -> Mixer [-> Meter] groups as one launch
+    std::set<std::pair<int, uint32_t>> pinned;                         // output lines the host observes: always materialised
+    std::set<std::pair<int, uint32_t>> hidden;                         // interior lines of fused groups the current plan does not write
+    std::set<int> fusion_veto;                                         // mixers whose group's parameters left the fused kernel's domain
+    std::vector<FusedGroup> fused;
+    uint64_t runs_since_plan = 0;
     float last_call_host_us = 0.f;                                     // host time of the last run_ticks call
     uint32_t last_call_ticks = 0;
 
@@ -80,6 +87,94 @@ void traverse(mxl_graph* g, int id, std::vector<char>& seen)
     g->run_order.push_back(id);
 }
 
+// Groups Oscillator -> EqThree -> StereoPanner -> Mixer [-> Meter] (BASELINE configs 2 and 4 are made of them) that can
+// run as one launch (fused_voice.cu).  A group is taken only when no module outside it consumes one of its interior
+// lines: those consumers would be scheduled by level, before the fused launch has written anything.  Lines the HOST
+// observes (mxl_graph_output / mxl_graph_pin_output) stay inside the group and are written by the fused kernel.
+void find_fused_groups(mxl_graph* g, const std::vector<int>& level, std::vector<int>& owner)
+{
+    g->fused.clear();
+    g->hidden.clear();
+    owner.assign(g->modules.size(), -1);
+    static const bool env_off = getenv("MXL_NO_FUSION") != nullptr;
+    if (!g->fusion || env_off || !g->ctx->has_device()) return;
+    std::map<std::pair<int, uint32_t>, int> consumers;
+    for (int id : g->run_order)
+        for (const auto& r : g->resolved[id])
+            if (r.first >= 0) consumers[r]++;
+    auto n_consumers = [&](int m, uint32_t o) { auto it = consumers.find({m, o}); return it == consumers.end() ? 0 : it->second; };
+    auto line_if_pinned = [&](int m, uint32_t o) -> mxl_line* { return g->pinned.count({m, o}) ? g->out_lines[m][o] : nullptr; };
+    for (int id : g->run_order) {
+        mxl_module* mx = g->modules[id];
+        if (mx->kind != MXL_MOD_MIXER || g->fusion_veto.count(id) || mx->inputs.empty()) continue;
+        FusedGroup grp;
+        grp.mixer = mx;
+        grp.members.push_back(id);
+        std::map<int, int> voice_of_eq, eq_refs;
+        bool ok = true;
+        for (uint32_t c = 0; ok && c < mx->inputs.size(); c++) {
+            FusedChanRef cr{false, -1, -1, nullptr};
+            const auto r = g->resolved[id][c];
+            if (r.first >= 0) {
+                mxl_module* pm = g->modules[r.first];
+                if (pm->kind != MXL_MOD_STEREO_PANNER || owner[r.first] >= 0 || n_consumers(r.first, 0) != 1) { ok = false; break; }
+                cr.connected = true;
+                cr.pan_out = line_if_pinned(r.first, 0);
+                grp.members.push_back(r.first);
+                for (uint32_t side = 0; ok && side < 2; side++) {
+                    const auto rr = g->resolved[r.first][side];
+                    if (rr.first < 0) continue;
+                    mxl_module* em = g->modules[rr.first];
+                    if (em->kind != MXL_MOD_EQ_THREE || owner[rr.first] >= 0) { ok = false; break; }
+                    auto it = voice_of_eq.find(rr.first);
+                    if (it == voice_of_eq.end()) {
+                        FusedVoiceRef v{nullptr, em, g->out_lines[rr.first][0], nullptr, nullptr};
+                        const auto ro = g->resolved[rr.first][0];
+                        if (ro.first >= 0) {
+                            mxl_module* om = g->modules[ro.first];
+                            if (om->kind != MXL_MOD_OSCILLATOR || ro.second != 0 || owner[ro.first] >= 0 ||
+                                n_consumers(ro.first, 0) != 1 || n_consumers(ro.first, 1) != 0) { ok = false; break; }
+                            v.osc = om;
+                            v.osc_mono = line_if_pinned(ro.first, 0);
+                            v.osc_stereo = line_if_pinned(ro.first, 1);
+                            grp.members.push_back(ro.first);
+                        }
+                        grp.members.push_back(rr.first);
+                        it = voice_of_eq.emplace(rr.first, (int)grp.voices.size()).first;
+                        grp.voices.push_back(v);
+                    }
+                    (side == 0 ? cr.left : cr.right) = it->second;
+                    eq_refs[rr.first]++;
+                }
+            }
+            grp.chans.push_back(cr);
+        }
+        for (const auto& e : eq_refs)
+            if (ok && n_consumers(e.first, 0) != e.second) ok = false;       // an EqThree line also feeds somebody else
+        if (!ok || !fused_group_supported(g->ctx, grp)) continue;
+        grp.master = g->out_lines[id][0];
+        grp.cue = g->out_lines[id][1];
+        if (fused_meter_supported(g->ctx)) {                                 // the first Meter on the master bus rides along
+            for (int mid : g->run_order) {
+                mxl_module* mm = g->modules[mid];
+                if (mm->kind == MXL_MOD_METER && owner[mid] < 0 && g->resolved[mid][0] == std::make_pair(id, 0u)) {
+                    grp.meter = mm;
+                    grp.members.push_back(mid);
+                    break;
+                }
+            }
+        }
+        for (int mid : grp.members) owner[mid] = (int)g->fused.size();
+        for (int mid : grp.members) {
+            const int kind = g->modules[mid]->kind;
+            if (kind == MXL_MOD_OSCILLATOR) { for (uint32_t o = 0; o < 2; o++) if (!g->pinned.count({mid, o})) g->hidden.insert({mid, o}); }
+            else if (kind == MXL_MOD_STEREO_PANNER) { if (!g->pinned.count({mid, 0u})) g->hidden.insert({mid, 0u}); }
+        }
+        (void)level;
+        g->fused.push_back(std::move(grp));
+    }
+}
+
 int build_plan(mxl_graph* g)
 {
     const size_t n = g->modules.size();
@@ -115,31 +210,6 @@ int build_plan(mxl_graph* g)
         level[id] = lv;
     }
 
-    // stages by (level, kind)
-    for (auto& s : g->stages) {
-        if (s.ev0) cudaEventDestroy(s.ev0);
-        if (s.ev1) cudaEventDestroy(s.ev1);
-    }
-    g->stages.clear();
-    std::map<std::pair<int, int>, size_t> index;
-    for (int id : g->run_order) {
-        const int kind = g->modules[id]->kind;
-        auto key = std::make_pair(level[id], kind);
-        auto it = index.find(key);
-        if (it == index.end()) {
-            index[key] = g->stages.size();
-            Stage s;
-            s.level = level[id];
-            s.kind = kind;
-            g->stages.push_back(s);
-            it = index.find(key);
-        }
-        g->stages[it->second].modules.push_back(id);
-    }
-    std::stable_sort(g->stages.begin(), g->stages.end(), [](const Stage& a, const Stage& b) {
-        return a.level != b.level ? a.level < b.level : a.kind < b.kind;
-    });
-
     // graph-owned output lines (sources present their own line)
     if (g->out_lines.size() < n) g->out_lines.resize(n);
     for (size_t id = 0; id < n; id++) {
@@ -158,8 +228,47 @@ int build_plan(mxl_graph* g)
             v.push_back(l);
         }
     }
+    // fused groups first: their modules leave the per-kind stages
+    std::vector<int> owner;
+    find_fused_groups(g, level, owner);
+
+    // stages by (level, kind)
+    for (auto& s : g->stages) {
+        if (s.ev0) cudaEventDestroy(s.ev0);
+        if (s.ev1) cudaEventDestroy(s.ev1);
+    }
+    g->stages.clear();
+    std::map<std::pair<int, int>, size_t> index;
+    for (int id : g->run_order) {
+        if (owner[id] >= 0) continue;
+        const int kind = g->modules[id]->kind;
+        auto key = std::make_pair(level[id], kind);
+        auto it = index.find(key);
+        if (it == index.end()) {
+            index[key] = g->stages.size();
+            Stage s;
+            s.level = level[id];
+            s.kind = kind;
+            g->stages.push_back(s);
+            it = index.find(key);
+        }
+        g->stages[it->second].modules.push_back(id);
+    }
+    for (size_t f = 0; f < g->fused.size(); f++) {                 // one stage per group, where its mixer stood
+        Stage s;
+        s.level = level[g->fused[f].members[0]];
+        s.kind = MXL_STAGE_FUSED_VOICE_MIX;
+        s.fused = (int)f;
+        s.modules = g->fused[f].members;
+        g->stages.push_back(s);
+    }
+    std::stable_sort(g->stages.begin(), g->stages.end(), [](const Stage& a, const Stage& b) {
+        return a.level != b.level ? a.level < b.level : a.kind < b.kind;
+    });
+
     g->dirty = false;
     g->timings_pending = false;
+    g->runs_since_plan = 0;
     return MXL_OK;
 }
 
@@ -224,6 +333,9 @@ int mxl_graph_remove_module(mxl_graph* g, int module_id)
     }
     delete m;
     g->modules[module_id] = nullptr;
+    for (auto it = g->pinned.begin(); it != g->pinned.end();) it = it->first == module_id ? g->pinned.erase(it) : std::next(it);
+    g->fusion_veto.erase(module_id);
+    g->fused.clear();                       // the groups hold module pointers: rebuilt by the next plan
     g->dirty = true;
     return MXL_OK;
 }
@@ -279,8 +391,12 @@ int mxl_graph_run_ticks(mxl_graph* g, uint64_t tick0, uint32_t n_ticks)
         if (m && !is_source(m->kind) && g->position.size() > id && g->position[id] >= 0 && g->out_lines[id].size() != m->outputs.size()) g->dirty = true;
         if (m && g->resolved.size() > id && g->position[id] >= 0 && g->resolved[id].size() != m->inputs.size()) g->dirty = true;
     }
+    // a fused group whose parameters left the fused kernel's domain (update() since the plan) goes back to stages
+    for (const FusedGroup& fg : g->fused)
+        if (!g->dirty && !fused_group_params_ok(fg)) { g->fusion_veto.insert(fg.members[0]); g->dirty = true; }
     if (g->dirty) MXL_TRY(build_plan(g));
     collect_timings(g);
+    g->runs_since_plan++;
 
     const uint64_t frames = (uint64_t)n_ticks * ctx->spt;
     const uint64_t t = tick0 * (uint64_t)ctx->spt;                     // engine.rs:490
@@ -314,7 +430,16 @@ int mxl_graph_run_ticks(mxl_graph* g, uint64_t tick0, uint32_t n_ticks)
     static const uint32_t split_min_ticks = getenv("MXL_SPLIT_MIN_TICKS") ? (uint32_t)atoi(getenv("MXL_SPLIT_MIN_TICKS")) : 1u;
     const bool split = g->split_streams && has_audio && has_video && !has_mixed && n_ticks >= split_min_ticks && !getenv("MXL_NO_STREAM_SPLIT");
     cudaStream_t main_stream = ctx->stream;
-    struct StreamGuard { mxl_ctx* c; cudaStream_t s; ~StreamGuard() { c->stream = s; c->pdl_hold = false; } } stream_guard{ctx, main_stream};
+    // every exit path re-serialises the two streams: later main-stream work (downloads, the next call's line_resize)
+    // must be ordered behind audio kernels already enqueued on the side stream, also when a stage fails half way
+    struct StreamGuard {
+        mxl_ctx* c; cudaStream_t s; bool forked = false;
+        ~StreamGuard()
+        {
+            c->stream = s; c->pdl_hold = false;
+            if (forked && cudaEventRecord(c->ev_join, c->stream_aux) == cudaSuccess) cudaStreamWaitEvent(s, c->ev_join, 0);
+        }
+    } stream_guard{ctx, main_stream};
     ctx->pdl_hold = split && n_ticks > 8;                            // see common.h: launch_chained
     if (split) {
         if (!ctx->stream_aux) {
@@ -326,6 +451,7 @@ int mxl_graph_run_ticks(mxl_graph* g, uint64_t tick0, uint32_t n_ticks)
         }
         MXL_CUDA(cudaEventRecord(ctx->ev_fork, main_stream));
         MXL_CUDA(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_fork, 0));
+        stream_guard.forked = true;
     }
     std::vector<mxl_module*> mods;
     std::vector<IoSet> ios;
@@ -333,6 +459,22 @@ int mxl_graph_run_ticks(mxl_graph* g, uint64_t tick0, uint32_t n_ticks)
     std::vector<mxl_line*> out_ptrs;
     for (Stage& s : g->stages) {
         if (is_source(s.kind)) { s.last_launches = 0; s.last_bytes = 0; continue; }
+        if (s.fused >= 0) {                                            // one launch for the whole voice group
+            ctx->stream = split ? ctx->stream_aux : main_stream;
+            if (g->profiling) {
+                if (!s.ev0) { MXL_CUDA(cudaEventCreate(&s.ev0)); MXL_CUDA(cudaEventCreate(&s.ev1)); }
+                MXL_CUDA(cudaEventRecord(s.ev0, ctx->stream));
+            }
+            const uint64_t before = ctx->launches;
+            uint64_t bytes = 0;
+            const auto host_t0 = std::chrono::steady_clock::now();
+            MXL_TRY(run_fused_group(ctx, g->fused[s.fused], t, &bytes));
+            s.last_host_us = std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - host_t0).count();
+            s.last_launches = (int)(ctx->launches - before);
+            s.last_bytes = bytes;
+            if (g->profiling) MXL_CUDA(cudaEventRecord(s.ev1, ctx->stream));
+            continue;
+        }
         mods.clear(); ios.clear(); in_ptrs.clear(); out_ptrs.clear();
         size_t n_in_total = 0, n_out_total = 0;
         for (int id : s.modules) { n_in_total += g->modules[id]->inputs.size(); n_out_total += g->modules[id]->outputs.size(); }
@@ -369,11 +511,7 @@ int mxl_graph_run_ticks(mxl_graph* g, uint64_t tick0, uint32_t n_ticks)
         s.last_bytes = bytes;
         if (g->profiling) MXL_CUDA(cudaEventRecord(s.ev1, ctx->stream));
     }
-    ctx->stream = main_stream;
-    if (split) {                                                       // join before anything downstream of the run
-        MXL_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream_aux));
-        MXL_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
-    }
+    ctx->stream = main_stream;              // (the guard joins the side stream before anything downstream of the run)
     g->timings_pending = g->profiling;
     return MXL_OK;
 }
@@ -387,9 +525,37 @@ int mxl_graph_set_stream_split(mxl_graph* g, int enabled)
 
 mxl_line* mxl_graph_output(mxl_graph* g, int module_id, uint32_t out_index)
 {
-    if (!g) return nullptr;
+    if (!g) { set_error("mxl_graph_output: NULL graph"); return nullptr; }
     if (g->dirty && build_plan(g) != MXL_OK) return nullptr;
+    if (g->hidden.count({module_id, out_index})) {
+        // a line inside a fused group that nothing observed so far: observed from now on
+        const bool stale = g->runs_since_plan > 0;
+        g->pinned.insert({module_id, out_index});
+        g->dirty = true;
+        if (stale) {
+            set_error("output %d:%u was interior to a fused voice group in the last run and was not written; it is from the next run on "
+                      "(call mxl_graph_pin_output or mxl_graph_output before running, or mxl_graph_set_fusion(g, 0))", module_id, out_index);
+            return nullptr;
+        }
+        if (build_plan(g) != MXL_OK) return nullptr;
+    }
     return output_line(g, module_id, out_index);
+}
+
+int mxl_graph_pin_output(mxl_graph* g, int module_id, uint32_t out_index)
+{
+    if (!g) MXL_FAIL(MXL_ERR_INVALID, "NULL graph");
+    mxl_module* m = module_at(g, module_id);
+    if (!m || out_index >= m->outputs.size()) MXL_FAIL(MXL_ERR_NO_OUTPUT, "pin: no output %d:%u", module_id, out_index);
+    if (g->pinned.insert({module_id, out_index}).second) g->dirty = true;
+    return MXL_OK;
+}
+
+int mxl_graph_set_fusion(mxl_graph* g, int enabled)
+{
+    if (!g) MXL_FAIL(MXL_ERR_INVALID, "NULL graph");
+    if (g->fusion != (enabled != 0)) { g->fusion = enabled != 0; g->dirty = true; }
+    return MXL_OK;
 }
 
 int mxl_graph_set_profiling(mxl_graph* g, int enabled)

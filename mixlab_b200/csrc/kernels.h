@@ -95,23 +95,69 @@ struct EqStreamInst {
     uint32_t* poison;                            // device: {first chunk with a non-finite carry (~0 = none), CTAs finished}
     double g_lo, g_mid, g_hi;
 };
-struct EqStreamBatch {                           // ~7 KB of kernel parameters (limit 32 KB on sm_100)
-    uint64_t frames;
+// Constants of the time-parallel scheme for one chunk length (host: EqStreamPlan, eq_plan.h), shared by
+// eq_stream_kernel and the fused voice kernel: ~5.6 KB of kernel parameters, read through the constant bank.
+struct EqStreamConsts {
     uint32_t chunk;                              // LC: 16, 32 or 64
     uint32_t halo;                               // chunks recomputed ahead of a CTA's own range
-    uint32_t n_chunks;
     uint32_t lev_lo, lev_hi;                     // scan levels per cascade (<= 8); levels >= 5 cross warps
     uint32_t back_lo, back_hi;                   // previous warps a warp's start states still hear (<= 3)
-    int32_t n;
     const double* lane_pow;                      // device: A^(lane+1), [cascade][entry][lane] (EqStreamPlan::lane_pow)
     double c_lo, c_hi;
     double pow_lo[8][10];                        // A^(2^d), packed lower-triangular
     double pow_hi[8][10];
     double K[8];                                 // zero-input (VSA) end state of a chunk
     double V[64][8];                             // end-state response to a unit input at sample j
+};
+struct EqStreamBatch {                           // ~7 KB of kernel parameters (limit 32 KB on sm_100)
+    uint64_t frames;
+    uint32_t n_chunks;
+    int32_t n;
+    EqStreamConsts eq;
     EqStreamInst inst[kMaxBatch];
 };
 int launch_eq_stream(mxl_ctx* ctx, const EqStreamBatch& b);
+
+// ---- Fused voice group: Oscillator -> EqThree -> StereoPanner -> Mixer [-> Meter] in ONE launch (fused_voice.cu) ----
+// The graph executor (graph.cu) replaces the five stages of such a sub-graph by this launch.  A "voice" is an
+// Oscillator feeding an EqThree; a mixer channel takes a StereoPanner whose sides are voices (or disconnected).
+// Grid (time tiles, voices), one thread-block cluster per time tile (a CTA per voice): every CTA generates its
+// voice's samples straight into the EqThree tile, filters them (the eq_stream scheme), stores the EqThree line;
+// after the cluster barrier the CTAs share the tile's mixer sum (channel order kept) and the meter records.
+struct MeterRecord;
+constexpr int kFusedMaxVoices = 16;  // = the largest thread-block cluster of sm_100 (non-portable size)
+constexpr int kFusedMaxChans = 64;
+struct FusedVoice {
+    double freq; int32_t waveform; int32_t _pad;   // Oscillator params (waveform Off = EqThree input disconnected)
+    const double* state; double* state_out;        // EqThree state: lo poles[4], hi poles[4], history[3]; double-buffered
+    double g_lo, g_mid, g_hi;
+    float* eq_out;                                 // EqThree output line: always written (the mix phase reads it)
+    float* osc_mono; float* osc_stereo;            // Oscillator output lines: written only when something observes them
+};
+struct FusedChan {
+    const float* left; const float* right;         // EqThree lines feeding the panner's L / R; nullptr = disconnected
+    float* pan_out;                                // StereoPanner output line: written only when observed
+    double gain;                                   // fader * 10^(gain_dB / 20) (mixer.rs:59)
+    int32_t cue; int32_t _pad;
+};
+struct FusedBatch {
+    uint64_t t0, frames;
+    double sample_rate, inv_sample_rate;
+    uint32_t n_chunks;
+    uint32_t owned;                                // chunks a tile owns (<= 256 - halo; tick-aligned when the meter is fused)
+    int32_t n_voices, n_channels;
+    float* master; float* cue;
+    MeterRecord* meter;                            // nullptr = no fused meter
+    uint32_t spt, _pad;
+    EqStreamConsts eq;
+    FusedVoice voice[kFusedMaxVoices];
+    FusedChan chan[kFusedMaxChans];
+};
+// chunks per tile for this plan; *meter_ok = the tile can be made a whole number of ticks of `spt` frames
+uint32_t fused_owned_chunks(const EqStreamConsts& eq, uint32_t spt, bool* meter_ok);
+// > 0 when a cluster of n_voices CTAs of this kernel can be resident (cudaOccupancyMaxActiveClusters)
+int fused_voice_mix_supported(mxl_ctx* ctx, uint32_t chunk, int n_voices);
+int launch_fused_voice_mix(mxl_ctx* ctx, const FusedBatch& b);
 
 // ---- Envelope (src/module/envelope.rs:91-120) ----
 struct EnvState { int32_t state; int32_t _pad; uint64_t seq; double off_amplitude; };

@@ -825,6 +825,38 @@ static uint32_t eq_pick_chunk(const mxl_ctx* ctx, uint64_t frames, int n_inst)
     return chunk;
 }
 
+// Kernel-parameter copy of a plan (eq_plan.h); the per-lane powers live in device memory (5 KB per plan, uploaded once).
+static int fill_eq_consts(mxl_ctx* ctx, const mxl::EqStreamPlan& plan, k::EqStreamConsts* q)
+{
+    static_assert(sizeof(plan.V) == sizeof(q->V) && sizeof(plan.pow_lo) == sizeof(q->pow_lo), "plan layout");
+    q->chunk = plan.lc;
+    q->halo = plan.halo;
+    q->lev_lo = plan.lev_lo;
+    q->lev_hi = plan.lev_hi;
+    q->back_lo = plan.back_lo;
+    q->back_hi = plan.back_hi;
+    void*& tab = ctx->eq_stream_tables[plan.lc];
+    if (!tab) {
+        MXL_CUDA(cudaMalloc(&tab, sizeof plan.lane_pow));
+        MXL_CUDA(cudaMemcpyAsync(tab, plan.lane_pow, sizeof plan.lane_pow, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    q->lane_pow = (const double*)tab;
+    q->c_lo = plan.c_lo; q->c_hi = plan.c_hi;
+    memcpy(q->pow_lo, plan.pow_lo, sizeof q->pow_lo);
+    memcpy(q->pow_hi, plan.pow_hi, sizeof q->pow_hi);
+    memcpy(q->K, plan.K, sizeof q->K);
+    memcpy(q->V, plan.V, sizeof q->V);
+    return MXL_OK;
+}
+
+static const mxl::EqStreamPlan* eq_stream_plan_for(mxl_ctx* ctx, uint32_t lc)
+{
+    auto it = ctx->eq_stream_plans.find(lc);
+    if (it == ctx->eq_stream_plans.end())
+        it = ctx->eq_stream_plans.emplace(lc, mxl::eq_stream_plan(ctx->sample_rate, lc, k::kEqStreamThreads / 2)).first;
+    return it->second.ok ? &it->second : nullptr;
+}
+
 // Single-launch path (eq_stream_kernel).  Returns 1 if it ran, 0 if no usable plan exists at this
 // sample rate (the cascades would need more than 128 chunks to forget), < 0 on error.
 static int run_eq_stream(mxl_ctx* ctx, mxl_module* const* mods, const IoSet* io, int first, int cnt, uint64_t frames, uint64_t* bytes)
@@ -834,12 +866,7 @@ static int run_eq_stream(mxl_ctx* ctx, mxl_module* const* mods, const IoSet* io,
     // cascade would not forget inside half a CTA at this sample rate is skipped.  MXL_EQ_STREAM_CHUNK forces one.
     uint32_t forced = 0;
     if (const char* e = getenv("MXL_EQ_STREAM_CHUNK")) forced = (uint32_t)atol(e);
-    auto plan_for = [&](uint32_t lc) -> const mxl::EqStreamPlan* {
-        auto it = ctx->eq_stream_plans.find(lc);
-        if (it == ctx->eq_stream_plans.end())
-            it = ctx->eq_stream_plans.emplace(lc, mxl::eq_stream_plan(ctx->sample_rate, lc, k::kEqStreamThreads / 2)).first;
-        return it->second.ok ? &it->second : nullptr;
-    };
+    auto plan_for = [&](uint32_t lc) { return eq_stream_plan_for(ctx, lc); };
     const mxl::EqStreamPlan* plan = nullptr;
     if (forced) {
         plan = plan_for(forced);
@@ -853,30 +880,11 @@ static int run_eq_stream(mxl_ctx* ctx, mxl_module* const* mods, const IoSet* io,
         if (!plan) plan = p32 ? p32 : plan_for(16);
     }
     if (!plan) return 0;
-    static_assert(sizeof(plan->V) == sizeof(k::EqStreamBatch::V) && sizeof(plan->pow_lo) == sizeof(k::EqStreamBatch::pow_lo), "plan layout");
     k::EqStreamBatch b{};
     b.frames = frames;
-    b.chunk = plan->lc;
-    b.halo = plan->halo;
     b.n_chunks = (uint32_t)((frames + plan->lc - 1) / plan->lc);
-    b.lev_lo = plan->lev_lo;
-    b.lev_hi = plan->lev_hi;
-    b.back_lo = plan->back_lo;
-    b.back_hi = plan->back_hi;
     b.n = cnt;
-    {   // per-lane powers live in device memory (5 KB per plan, uploaded once)
-        void*& tab = ctx->eq_stream_tables[plan->lc];
-        if (!tab) {
-            MXL_CUDA(cudaMalloc(&tab, sizeof plan->lane_pow));
-            MXL_CUDA(cudaMemcpyAsync(tab, plan->lane_pow, sizeof plan->lane_pow, cudaMemcpyHostToDevice, ctx->stream));
-        }
-        b.lane_pow = (const double*)tab;
-    }
-    b.c_lo = plan->c_lo; b.c_hi = plan->c_hi;
-    memcpy(b.pow_lo, plan->pow_lo, sizeof b.pow_lo);
-    memcpy(b.pow_hi, plan->pow_hi, sizeof b.pow_hi);
-    memcpy(b.K, plan->K, sizeof b.K);
-    memcpy(b.V, plan->V, sizeof b.V);
+    MXL_TRY(fill_eq_consts(ctx, *plan, &b.eq));
     for (int j = 0; j < cnt; j++) {
         EqThree* m = (EqThree*)mods[first + j];
         MXL_TRY(m->ensure_state());
@@ -1040,6 +1048,129 @@ static int run_meters(mxl_ctx* ctx, mxl_module* const* mods, int n, const IoSet*
         b.frames = frames; b.spt = ctx->spt; b.n = cnt;
         MXL_TRY(k::launch_meter(ctx, b, slots));
     }
+    return MXL_OK;
+}
+
+// ================================================================================================
+// Fused voice group (fused_voice.cu): Oscillator -> EqThree -> StereoPanner -> Mixer [-> Meter]
+// ================================================================================================
+bool fused_meter_supported(mxl_ctx* ctx)
+{
+    const mxl::EqStreamPlan* p32 = eq_stream_plan_for(ctx, 32);
+    if (!p32) return false;
+    k::EqStreamConsts q{};
+    q.chunk = p32->lc; q.halo = p32->halo;
+    bool ok = false;
+    k::fused_owned_chunks(q, ctx->spt, &ok);
+    return ok;
+}
+
+bool fused_group_params_ok(const FusedGroup& g)
+{
+    for (const FusedVoiceRef& v : g.voices) {
+        if (!v.osc) continue;
+        const Oscillator* o = (const Oscillator*)v.osc;
+        // a finite frequency keeps every phase finite, so the oscillator never produces a NaN the cascades would
+        // keep for ever (the staged EqThree kernel carries that case; the fused one does not)
+        if (!(fabs(o->p.freq) <= 1e12)) return false;
+    }
+    return g.mixer && ((const Mixer*)g.mixer)->channels.size() == g.chans.size();
+}
+
+bool fused_group_supported(mxl_ctx* ctx, const FusedGroup& g)
+{
+    if (!ctx->has_device() || !g.mixer || g.voices.empty() || g.voices.size() > (size_t)k::kFusedMaxVoices ||
+        g.chans.empty() || g.chans.size() > (size_t)k::kFusedMaxChans)
+        return false;
+    if (!fused_group_params_ok(g)) return false;
+    if (!eq_stream_plan_for(ctx, 32)) return false;         // sample rate outside what the time-parallel scheme handles
+    return k::fused_voice_mix_supported(ctx, 32, (int)g.voices.size()) > 0;
+}
+
+int run_fused_group(mxl_ctx* ctx, const FusedGroup& g, uint64_t t, uint64_t* bytes)
+{
+    if (bytes) *bytes = 0;
+    MXL_TRY(expect_output(g.master, MXL_LINE_STEREO, "Mixer.Master"));
+    MXL_TRY(expect_output(g.cue, MXL_LINE_STEREO, "Mixer.Cue"));
+    const uint64_t frames = g.master->frames;
+    if (frames == 0) return MXL_OK;
+    MXL_TRY(need_len(g.cue, 2 * frames, "Mixer.Cue"));
+    if (t + frames + (1ull << 20) >= (1ull << 53)) MXL_FAIL(MXL_ERR_LENGTH, "fused voice group: sample index beyond 2^53");
+    const Mixer* mx = (const Mixer*)g.mixer;
+    if (mx->channels.size() != g.chans.size()) MXL_FAIL(MXL_ERR_INVALID, "fused voice group: mixer has %zu channels, the plan %zu", mx->channels.size(), g.chans.size());
+
+    // chunk length: 64 samples once that still gives every SM two CTAs, else 32
+    const int nv = (int)g.voices.size();
+    const mxl::EqStreamPlan* plan = eq_stream_plan_for(ctx, 32);
+    if (!plan) MXL_FAIL(MXL_ERR_UNSUPPORTED, "fused voice group: no EqThree plan at %u Hz", ctx->sample_rate);
+    uint32_t forced = 0;
+    if (const char* e = getenv("MXL_FUSED_CHUNK")) forced = (uint32_t)atol(e);
+    if (forced != 32) {
+        if (const mxl::EqStreamPlan* p64 = eq_stream_plan_for(ctx, 64)) {
+            const uint64_t own64 = k::kEqStreamThreads - p64->halo;
+            const uint64_t tiles64 = ((frames + 63) / 64 + own64 - 1) / own64;
+            const uint64_t sms = (uint64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148);
+            if ((forced == 64 || tiles64 * nv >= 2 * sms) && k::fused_voice_mix_supported(ctx, 64, nv) > 0) plan = p64;
+        }
+    }
+    k::FusedBatch b{};
+    MXL_TRY(fill_eq_consts(ctx, *plan, &b.eq));
+    b.t0 = t; b.frames = frames;
+    b.sample_rate = (double)ctx->sample_rate; b.inv_sample_rate = 1.0 / b.sample_rate;
+    b.n_chunks = (uint32_t)((frames + plan->lc - 1) / plan->lc);
+    bool meter_ok = false;
+    b.owned = k::fused_owned_chunks(b.eq, ctx->spt, &meter_ok);
+    b.n_voices = nv; b.n_channels = (int32_t)g.chans.size();
+    b.master = g.master->dev; b.cue = g.cue->dev;
+    b.spt = ctx->spt;
+    if (g.meter) {
+        if (!meter_ok) MXL_FAIL(MXL_ERR_INVALID, "fused voice group: meter folded in but ticks of %u frames do not tile", ctx->spt);
+        Meter* me = (Meter*)g.meter;
+        const uint32_t slots = (uint32_t)((frames + ctx->spt - 1) / ctx->spt);
+        MXL_TRY(me->records.ensure(ctx, (size_t)slots * sizeof(k::MeterRecord)));
+        me->n_slots = slots;
+        b.meter = (k::MeterRecord*)me->records.p;
+        if (bytes) *bytes += 8 * frames;
+    } else {
+        b.owned = k::kEqStreamThreads - plan->halo;          // no tick alignment needed
+    }
+    for (int i = 0; i < nv; i++) {
+        const FusedVoiceRef& v = g.voices[i];
+        EqThree* e = (EqThree*)v.eq;
+        MXL_TRY(e->ensure_state());
+        MXL_TRY(expect_output(v.eq_out, MXL_LINE_MONO, "EqThree"));
+        MXL_TRY(need_len(v.eq_out, frames, "EqThree output"));
+        k::FusedVoice& fv = b.voice[i];
+        if (v.osc) {
+            const Oscillator* o = (const Oscillator*)v.osc;
+            fv.freq = o->p.freq; fv.waveform = o->p.waveform;
+            if (bytes) *bytes += 12 * frames;
+        } else {
+            fv.freq = 0.0; fv.waveform = MXL_WAVE_OFF;
+        }
+        fv.state = e->state_ptr(e->cur);
+        fv.state_out = e->state_ptr(e->cur ^ 1);
+        fv.g_lo = db_to_linear(e->p.gain_lo_db);             // eq_three.rs:62-64
+        fv.g_mid = db_to_linear(e->p.gain_mid_db);
+        fv.g_hi = db_to_linear(e->p.gain_hi_db);
+        fv.eq_out = v.eq_out->dev;
+        if (v.osc_mono) { MXL_TRY(need_len(v.osc_mono, frames, "Oscillator.Mono")); fv.osc_mono = v.osc_mono->dev; }
+        if (v.osc_stereo) { MXL_TRY(need_len(v.osc_stereo, 2 * frames, "Oscillator.Stereo")); fv.osc_stereo = v.osc_stereo->dev; }
+        if (bytes) *bytes += (v.osc ? 4 * frames : 0) + 4 * frames;
+    }
+    for (size_t c = 0; c < g.chans.size(); c++) {
+        const FusedChanRef& cr = g.chans[c];
+        k::FusedChan& fc = b.chan[c];
+        fc.left = cr.left >= 0 ? b.voice[cr.left].eq_out : nullptr;
+        fc.right = cr.right >= 0 ? b.voice[cr.right].eq_out : nullptr;
+        if (cr.pan_out) { MXL_TRY(need_len(cr.pan_out, 2 * frames, "StereoPanner output")); fc.pan_out = cr.pan_out->dev; }
+        fc.gain = mx->channel_gain[c];                       // mixer.rs:59
+        fc.cue = mx->channels[c].cue ? 1 : 0;
+        if (bytes && cr.connected) *bytes += (cr.left >= 0 ? 4 * frames : 0) + (cr.right >= 0 ? 4 * frames : 0) + 8 * frames + 8 * frames;
+    }
+    if (bytes) *bytes += 16 * frames;
+    MXL_TRY(k::launch_fused_voice_mix(ctx, b));
+    for (int i = 0; i < nv; i++) ((EqThree*)g.voices[i].eq)->cur ^= 1;
     return MXL_OK;
 }
 
@@ -1749,6 +1880,15 @@ int VideoMixer::run(uint64_t t0, const IoSet& io, uint64_t* bytes)
     struct KeepGuard { std::vector<mxl_frame*>& v; ~KeepGuard() { for (mxl_frame* f : v) frame_release(f); } } keep_guard{keepalive};
     jobs.reserve(ticks);
     const Rational tick_duration = Rational::make((int64_t)ctx->spt, (int64_t)ctx->sample_rate);   // 1/TICKS_PER_SECOND (video_mixer.rs:244)
+    // Input frames are scaled by ONE launch per geometry, normally at the end of the call.  A stored frame that has
+    // to be scaled AGAIN inside the call (another channel's picture grew the unified target, video_mixer.rs:262-274)
+    // may still be waiting for that launch: the pending groups run first, as the reference's synchronous scaler would
+    // have, then the immediate rescale reads finished pixels.
+    auto flush_scales = [&]() -> int {
+        for (auto& gq : scale_groups) MXL_TRY(scale_run(ctx, gq.sl, gq.w, gq.h, gq.jobs.data(), (uint32_t)gq.jobs.size()));
+        scale_groups.clear();
+        return MXL_OK;
+    };
 
     for (uint64_t kk = 0; kk < ticks; kk++) {
         const uint64_t t = t0 + kk * ctx->spt;
@@ -1812,6 +1952,7 @@ int VideoMixer::run(uint64_t t0, const IoSet& io, uint64_t* bytes)
                 c.frame = scaled;
                 c.active_until = now + s->tick_offset + s->duration_hint;                          // 140
             } else {
+                if (c.has_stored && (!c.has_scaler || c.scaler_out != target)) MXL_TRY(flush_scales());
                 MXL_TRY(rescale(c, target));
             }
         }
@@ -1839,7 +1980,7 @@ int VideoMixer::run(uint64_t t0, const IoSet& io, uint64_t* bytes)
     }
 
     // the scaler first (its outputs are crossfade inputs): one launch per geometry
-    for (auto& gq : scale_groups) MXL_TRY(scale_run(ctx, gq.sl, gq.w, gq.h, gq.jobs.data(), (uint32_t)gq.jobs.size()));
+    MXL_TRY(flush_scales());
     // one batched launch per run of equal layouts (normally exactly one)
     if (!jobs.empty()) {
         // a call of a few ticks (the live engine thread: one) carries its job table in the kernel parameters

@@ -54,6 +54,37 @@ mxl_module* module_create(mxl_ctx* ctx, int kind, const void* params);
 int run_batch(mxl_ctx* ctx, int kind, mxl_module* const* mods, int n, uint64_t t, const IoSet* io,
               uint64_t* bytes_out);
 
+// A sub-graph Oscillator -> EqThree -> StereoPanner -> Mixer [-> Meter] that the graph executor runs as ONE launch
+// (fused_voice.cu) instead of five stages.  Built by graph.cu's plan from the resolved connections.
+struct FusedVoiceRef {
+    mxl_module* osc;              // nullptr = the EqThree's input is disconnected (zeros)
+    mxl_module* eq;
+    mxl_line* eq_out;             // always written: it carries the voice from the filter to the mixer sum
+    mxl_line* osc_mono;           // nullptr = nobody observes the line: it is not written
+    mxl_line* osc_stereo;
+};
+struct FusedChanRef {
+    bool connected;               // false = the mixer input is disconnected (no panner)
+    int left, right;              // voice index feeding the panner's L / R, -1 = disconnected
+    mxl_line* pan_out;            // nullptr = not observed, not written
+};
+struct FusedGroup {
+    std::vector<FusedVoiceRef> voices;
+    std::vector<FusedChanRef> chans;        // one per mixer channel, in channel order
+    mxl_module* mixer = nullptr;
+    mxl_line* master = nullptr;
+    mxl_line* cue = nullptr;
+    mxl_module* meter = nullptr;            // Meter on the master bus folded into the launch, or nullptr
+    std::vector<int> members;               // ModuleIds of every module of the group (graph.cu's bookkeeping)
+};
+// Can this group run fused on this context (a cluster of that many CTAs fits, a plan exists at this sample rate)?
+bool fused_group_supported(mxl_ctx* ctx, const FusedGroup& g);
+// Do the modules' CURRENT parameters allow it (checked before every run: update() may have changed them)?
+bool fused_group_params_ok(const FusedGroup& g);
+// Can a Meter on the master bus be folded in (a time tile can be made a whole number of ticks)?
+bool fused_meter_supported(mxl_ctx* ctx);
+int run_fused_group(mxl_ctx* ctx, const FusedGroup& g, uint64_t t, uint64_t* bytes_out);
+
 // kind-specific accessors used by the ABI
 int eq_three_state(mxl_module* m, double state[11]);
 int envelope_state(mxl_module* m, int32_t* state, uint64_t* seq, double* off_amplitude);

@@ -46,7 +46,11 @@ KIND = {
     "StereoSplitter": api.MOD_STEREO_SPLITTER, "Trigger": api.MOD_TRIGGER,
     "VideoMixer": api.MOD_VIDEO_MIXER, "Meter": api.MOD_METER, "SourceMono": api.MOD_SOURCE_MONO,
     "SourceStereo": api.MOD_SOURCE_STEREO, "SourceVideo": api.MOD_SOURCE_VIDEO, "PcmSink": api.MOD_PCM_SINK,
+    "Monitor": api.MOD_MONITOR, "StreamInput": api.MOD_STREAM_INPUT, "StreamOutput": api.MOD_STREAM_OUTPUT,
+    "OutputDevice": api.MOD_OUTPUT_DEVICE,
 }
+# stage kinds that are not module kinds (mxl_stage_info.kind)
+STAGE_KIND = dict(KIND, FusedVoiceMix=api.STAGE_FUSED_VOICE_MIX)
 
 _WAVES = [api.WAVE_SINE, api.WAVE_SAW, api.WAVE_TRIANGLE, api.WAVE_SQUARE]
 _EQ_PATTERNS = [(-6.0, 0.0, 4.0), (0.0, 4.0, -6.0), (4.0, -6.0, 0.0), (4.0, 0.0, 4.0)]

@@ -201,6 +201,48 @@ def test_mixer_scales_all_ticks_of_a_call_in_one_launch(mxl, oracle, ctx48):
         assert np.array_equal(outs[0].get(k).download_raw(), oracle.video_crossfade(lay, fa[k][1], scaled, f8)), k
 
 
+def test_target_growing_inside_a_call_rescales_finished_pixels(mxl, oracle, ctx48):
+    """Channel A delivers one 320x180 frame at tick 0 that stays stored (long duration); channel B delivers 640x360
+    frames, then 1280x720 from tick 3 on.  At tick 0 A is scaled up to the unified 640x360 target and stored -- in a
+    batched call by the deferred scaler launch.  At tick 3 the target grows and A's STORED (scaled) frame is scaled
+    again, immediately (Channel::rescale, video_mixer.rs:262-274): it must read finished pixels, not a frame whose
+    scaler launch is still pending.  Six ticks in one call must equal six one-tick calls, and both the oracle."""
+    ticks = 6
+    fa = make_frame(ctx48, oracle, 320, 180, 4242)
+    fb = [make_frame(ctx48, oracle, 640, 360, 5000 + k) for k in range(3)] + [make_frame(ctx48, oracle, 1280, 720, 6000 + k) for k in range(3)]
+    f8 = oracle.fader_to_u8(0.4)
+
+    def feed(n_calls):
+        mod = ctx48.module(mxl.MOD_VIDEO_MIXER, (0, 1, 0.4))
+        got = []
+        per = ticks // n_calls
+        for c in range(n_calls):
+            la, lb = ctx48.video_line(per), ctx48.video_line(per)
+            for k in range(per):
+                tick = c * per + k
+                if tick == 0:
+                    la.set(k, fa[0], duration=(10, 1))            # stays stored for the whole test
+                lb.set(k, fb[tick][0], duration=(1, 60))
+            outs = [ctx48.video_line(per) for _ in range(3)]
+            mod.run_tick(c * per * 800, [la, lb, None, None], outs)
+            for k in range(per):
+                o = outs[0].get(k)
+                got.append(((o.layout.width, o.layout.height), o.download_raw()))
+        mod.destroy()
+        return got
+
+    batched, single = feed(1), feed(6)
+    a_mid = oracle_scale(oracle, fa[1], fa[2], 640, 360)
+    a_big = oracle_scale(oracle, a_mid, oracle.frame_layout(640, 360), 1280, 720)      # the stored frame scaled again
+    for k in range(ticks):
+        tw, th = (640, 360) if k < 3 else (1280, 720)
+        lay = oracle.frame_layout(tw, th)
+        want = oracle.video_crossfade(lay, a_mid if k < 3 else a_big, fb[k][1], f8)
+        assert single[k][0] == (tw, th) and batched[k][0] == (tw, th), k
+        assert np.array_equal(single[k][1], want), ("one tick per call", k)
+        assert np.array_equal(batched[k][1], want), ("six ticks in one call", k)
+
+
 def test_batched_scaler_one_launch(mxl, oracle, ctx48):
     frames = [make_frame(ctx48, oracle, 640, 360, 900 + k) for k in range(6)]
     before = ctx48.launch_count

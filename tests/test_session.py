@@ -88,9 +88,10 @@ def _check_step(oracle, desc, sess, frames, master, meter, tick0, T, spt=800, sr
         if k >= tick0:
             want = buf if want is None else np.concatenate([want, buf])
     err = np.abs(master.astype(np.float64) - want.astype(np.float64))
-    assert np.all(err <= 1e-6 * np.abs(want) + 1e-6 * np.abs(want).max())
-    pk, sq, clip = og.meter(oids[desc.taps["meter"][0]])
-    assert abs(meter[T - 1]["peak"][0] - pk[0]) <= 1e-6 * pk[0]
+    assert np.all(err <= 1e-6 * np.abs(want) + 1e-7)                     # SURVEY 8(d) gate
+    if "meter" in desc.taps:
+        pk, sq, clip = og.meter(oids[desc.taps["meter"][0]])
+        assert abs(meter[T - 1]["peak"][0] - pk[0]) <= 1e-6 * pk[0] + 1e-7
 
 
 @pytest.mark.gpu
@@ -120,6 +121,32 @@ def test_host_fed_steps_serial_and_pipelined(mxl, oracle):
         _check_step(oracle, desc, sess, sess.result_frames(1), np.array(sess.result_master(1)), sess.result_meter(1), T * 4, T)
         _check_step(oracle, desc, sess, sess.result_frames(0), np.array(sess.result_master(0)), sess.result_meter(0), T * 3, T)
         assert np.array_equal(keep, sess.result_frames(0))     # same inputs every step -> same composite
+        sess.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("session_id", [0, 3, 7])
+def test_config4_av_session_vs_oracle(mxl, oracle, session_id):
+    """BASELINE config 4: one of the 8 independent A/V sessions (16 audio modules + 1080p 2-layer composite), with
+    that session's own synthetic content (base seed + session id), host-fed through the C ABI for 9 ticks
+    and then 8 more: audio against the oracle's engine walker, every composited frame bit-exact."""
+    from mixlab_b200.session import AVSession, session_seed
+    T = 9
+    desc = W.config4_audio_graph()
+    assert W.algorithmic_bytes_per_tick(desc, 800) == 236 * 800
+    with mxl.Context(0, 48000, 800) as ctx:
+        sess = AVSession(ctx, desc, T, video=True, unique_frames=3, seed=session_seed(0xA11CE, session_id))
+        assert sess.frame_bytes == W.FRAME_BYTES
+        if session_id:                                       # distinct sessions carry distinct pictures
+            other = AVSession(ctx, None, 1, video=True, unique_frames=1, seed=session_seed(0xA11CE, 0))
+            assert not np.array_equal(other.host_a.array[:4096], sess.host_a.array[:4096])
+            other.close()
+        sess.run_step_host(0)
+        _check_step(oracle, desc, sess, sess.host_out.array.reshape(T, sess.frame_bytes), np.array(sess.host_master.array),
+                    sess.meter_records, 0, T)
+        sess.run_step_host(T)
+        _check_step(oracle, desc, sess, sess.host_out.array.reshape(T, sess.frame_bytes), np.array(sess.host_master.array),
+                    sess.meter_records, T, T)
         sess.close()
 
 
