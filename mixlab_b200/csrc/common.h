@@ -95,6 +95,7 @@ struct mxl_ctx {
     std::vector<cudaEvent_t> kernel_event_pool;
     uint32_t env_epoch = 0;           // Envelope launches so far (tags the look-back flags of a launch)
     std::map<uint32_t, void*> eq_stream_tables;   // device copies of EqStreamPlan::lane_pow by chunk length
+    std::map<uint32_t, int> fused_clusters;       // (chunk << 8 | voices) -> resident clusters of the fused voice kernel (0 = cannot launch)
 
     // Copy/compute overlap (mxl_ctx_set_copy_overlap): async uploads go to stream_in, async downloads
     // to stream_out, ordered against the compute stream with events:

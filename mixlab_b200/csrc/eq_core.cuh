@@ -89,7 +89,9 @@ MXL_HD void eq_run_chunk_skewed(EqPoles& p, double hist[3], Io& io, const EqGain
         s = (double)x.w; eq_skew_iter<true, true, true, true>(p, s, cl, ch);
         carry = eq_bands(p.l3, p.h3, d5, g); MXL_EQ_SHIFT(s);
     }
-#pragma unroll
+    // a real loop on the device (four samples per trip): fully unrolled, the chunk is ~1500 instructions of
+    // straight-line code per cascade length and the warps of a CTA stall on instruction fetch
+#pragma unroll 1
     for (int v = 1; v < LC / 4; v++) {
         const EqF4 x = io.load(v);
         EqF4 y;
@@ -121,7 +123,7 @@ MXL_HD void eq_run_chunk_skewed(EqPoles& p, double hist[3], Io& io, const EqGain
 template <int LC, class Io, class Tab>
 MXL_HD void eq_zero_state_dot(const Io& io, const Tab& tab, double acc[8])
 {
-#pragma unroll
+#pragma unroll 1
     for (int v = 0; v < LC / 4; v++) {
         const EqF4 x = io.load(v);
         const double s[4] = {(double)x.x, (double)x.y, (double)x.z, (double)x.w};

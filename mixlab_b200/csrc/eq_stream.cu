@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ E
     pdl_prologue();
     extern __shared__ __align__(16) unsigned char eq_smem[];
     float4* tile = reinterpret_cast<float4*>(eq_smem);                              // [256][VPR], swizzled
-    double* xch = reinterpret_cast<double*>(eq_smem + (size_t)kT * LC * sizeof(float));   // kEqXchDoubles
+    EqShared<LC>* sh = reinterpret_cast<EqShared<LC>*>(eq_smem + (size_t)kT * LC * sizeof(float));
     const EqStreamInst& in = b.inst[blockIdx.y];
     const int tid = threadIdx.x;
     const EqStreamConsts& q = b.eq;
@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ E
                 *dst = x;
             }
         }
+        load_tables<LC>(q.tab, sh, tid);                        // in flight with the staging copies
         asm volatile("cp.async.wait_all;" ::: "memory");
     }
     __syncthreads();
@@ -94,14 +95,14 @@ __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ E
     for (int e = 0; e < 8; e++) v[e] = 0.0;
     if (active) {
 #pragma unroll
-        for (int e = 0; e < 8; e++) v[e] = q.K[e];
-        ConstTab tab{q};
+        for (int e = 0; e < 8; e++) v[e] = sh->K[e];
+        SharedTab<LC> tab{sh};
         eq_zero_state_dot<LC>(row, tab, v);
         if (c == 0) {                                      // v_0 = A p_init + z_0
             const double pl[4] = {st[0], st[1], st[2], st[3]}, ph[4] = {st[4], st[5], st[6], st[7]};
             double yl[4], yh[4];
-            tri_apply(q.pow_lo[0], pl, yl);
-            tri_apply(q.pow_hi[0], ph, yh);
+            tri_apply(sh->pow_lo[0], pl, yl);
+            tri_apply(sh->pow_hi[0], ph, yh);
 #pragma unroll
             for (int e = 0; e < 4; e++) { v[e] += yl[e]; v[4 + e] += yh[e]; }
         }
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ E
 
     // ---- 3. scan (eq_stream.cuh): two block barriers ----
     double S[8];
-    scan_start_states(q, v, S, xch, tid);
+    scan_start_states<LC>(q, sh, v, S, tid);
 
     // ---- 4. exact re-run of the owned chunks ----
     const bool owner = active && tid >= halo;
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ E
 template <int LC>
 int launch_lc(mxl_ctx* ctx, const EqStreamBatch& b)
 {
-    const size_t smem = (size_t)kT * LC * sizeof(float) + (size_t)kEqXchDoubles * sizeof(double);
+    const size_t smem = (size_t)kT * LC * sizeof(float) + sizeof(EqShared<LC>);
     if (smem > 48 * 1024 && !(ctx->eq_stream_smem_set & (1u << (LC / 16)))) {
         MXL_CUDA(cudaFuncSetAttribute(eq_stream_kernel<LC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->eq_stream_smem_set |= 1u << (LC / 16);
@@ -230,7 +231,7 @@ int launch_eq_stream(mxl_ctx* ctx, const EqStreamBatch& b)
     if (b.n <= 0 || b.frames == 0) return MXL_OK;
     const EqStreamConsts& q = b.eq;
     if (q.halo == 0 || q.halo > (uint32_t)eqs::kT / 2 || q.lev_lo > (uint32_t)kEqPlanLevels || q.lev_hi > (uint32_t)kEqPlanLevels ||
-        q.back_lo > 3 || q.back_hi > 3 || !q.lane_pow)
+        q.back_lo > 3 || q.back_hi > 3 || !q.tab)
         MXL_FAIL(MXL_ERR_INVALID, "eq_stream_kernel: bad plan (chunk %u, halo %u, levels %u/%u)", q.chunk, q.halo, q.lev_lo, q.lev_hi);
     switch (q.chunk) {
     case 16: return launch_lc<16>(ctx, b);

@@ -13,7 +13,28 @@ namespace k {
 namespace eqs {
 
 constexpr int kT = kEqStreamThreads;
-constexpr int kEqXchDoubles = 2 * (kT / 32) * 8 + 2 * 10 * 32;    // warp aggregates, final lane-31 values, lane table
+
+// Shared memory next to the tile: the scan's exchange area and the plan's tables (EqDevTables, brought in by
+// load_tables with one round of coalesced loads per CTA).
+template <int LC>
+struct alignas(16) EqShared {
+    double2 agg[(kT / 32) * 4];                  // warp aggregates of the scan
+    double2 fin[(kT / 32) * 4];                  // final value of every warp's lane 31
+    double lane_pow[2 * 10 * 32];
+    double pow_lo[8][10];
+    double pow_hi[8][10];
+    double K[8];
+    double V[LC][8];
+};
+
+template <int LC>
+__device__ __forceinline__ void load_tables(const EqDevTables* __restrict__ g, EqShared<LC>* s, int tid)
+{
+    for (int i = tid; i < LC * 8; i += kT) (&s->V[0][0])[i] = (&g->V[0][0])[i];
+    for (int i = tid; i < 2 * 10 * 32; i += kT) s->lane_pow[i] = (&g->lane_pow[0][0][0])[i];
+    for (int i = tid; i < 160; i += kT) (&s->pow_lo[0][0])[i] = (&g->pow_lo[0][0])[i];    // pow_lo and pow_hi are adjacent in both
+    if (tid < 8) s->K[tid] = g->K[tid];
+}
 
 __device__ __forceinline__ int tri(int r, int c) { return r * (r + 1) / 2 + c; }
 
@@ -50,9 +71,10 @@ struct RowIo {
     __device__ __forceinline__ void store(int v, EqF4 y) { tile[slot_of<LC / 4>(r, v)] = make_float4(y.x, y.y, y.z, y.w); }
 };
 
-struct ConstTab {
-    const EqStreamConsts& c;
-    __device__ __forceinline__ double v(int j, int e) const { return c.V[j][e]; }
+template <int LC>
+struct SharedTab {
+    const EqShared<LC>* s;
+    __device__ __forceinline__ double v(int j, int e) const { return s->V[j][e]; }
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
@@ -75,8 +97,9 @@ __device__ __forceinline__ bool any_non_finite(const double v[8])
 // P = agg[w-1] + A^32 agg[w-2] + A^64 agg[w-3] (as many terms as the cascade still hears), and lane l adds
 // A^(l+1) P from a per-lane table.  Out: S = start state of this thread's chunk = inclusive value of the previous
 // thread (meaningless for thread 0, which owns a chunk only when it is the call's first: that one starts from the
-// module's stored state).  Two block barriers; xch = kEqXchDoubles doubles of shared memory.
-__device__ __forceinline__ void scan_start_states(const EqStreamConsts& b, double v[8], double S[8], double* xch, int tid)
+// module's stored state).  Two block barriers.
+template <int LC>
+__device__ __forceinline__ void scan_start_states(const EqStreamConsts& b, EqShared<LC>* sh, double v[8], double S[8], int tid)
 {
     const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
@@ -93,25 +116,24 @@ __device__ __forceinline__ void scan_start_states(const EqStreamConsts& b, doubl
         if (lane >= (1 << d)) {
             double y[4];
             if (lo_live) {
-                tri_apply(b.pow_lo[d], o, y);
+                tri_apply(sh->pow_lo[d], o, y);
 #pragma unroll
                 for (int e = 0; e < 4; e++) v[e] += y[e];
             }
             if (hi_live) {
-                tri_apply(b.pow_hi[d], o + 4, y);
+                tri_apply(sh->pow_hi[d], o + 4, y);
 #pragma unroll
                 for (int e = 0; e < 4; e++) v[4 + e] += y[e];
             }
         }
     }
-    double2* agg = reinterpret_cast<double2*>(xch);              // [8 warps][4 double2]: warp aggregates
-    double2* fin = agg + (kT / 32) * 4;                          // [8 warps][4 double2]: final value of lane 31
-    double* lane_tab = xch + 2 * (kT / 32) * 8;                  // [2][10][32]
+    double2* agg = sh->agg;                                      // [8 warps][4 double2]: warp aggregates
+    double2* fin = sh->fin;                                      // [8 warps][4 double2]: final value of lane 31
+    const double* lane_tab = sh->lane_pow;                       // [2][10][32]
     if (lane == 31) {
         agg[warp * 4 + 0] = make_double2(v[0], v[1]); agg[warp * 4 + 1] = make_double2(v[2], v[3]);
         agg[warp * 4 + 2] = make_double2(v[4], v[5]); agg[warp * 4 + 3] = make_double2(v[6], v[7]);
     }
-    for (int i = tid; i < 2 * 10 * 32; i += kT) lane_tab[i] = b.lane_pow[i];
     __syncthreads();
     if (warp > 0) {
         double P[8];
@@ -130,14 +152,14 @@ __device__ __forceinline__ void scan_start_states(const EqStreamConsts& b, doubl
             if (lo_live) {
                 const double2 a0 = a[0], a1 = a[1];
                 const double o[4] = {a0.x, a0.y, a1.x, a1.y};
-                tri_apply(b.pow_lo[4 + k], o, y);
+                tri_apply(sh->pow_lo[4 + k], o, y);
 #pragma unroll
                 for (int e = 0; e < 4; e++) P[e] += y[e];
             }
             if (hi_live) {
                 const double2 a2 = a[2], a3 = a[3];
                 const double o[4] = {a2.x, a2.y, a3.x, a3.y};
-                tri_apply(b.pow_hi[4 + k], o, y);
+                tri_apply(sh->pow_hi[4 + k], o, y);
 #pragma unroll
                 for (int e = 0; e < 4; e++) P[4 + e] += y[e];
             }

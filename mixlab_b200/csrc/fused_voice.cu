@@ -22,6 +22,7 @@
 // chunk), same channel order.  Roofline: FP64 pipe (~22 ops per sine sample + ~46 per EqThree sample + 1 per
 // channel product against 64 lanes/clk/SM), not HBM.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "eq_stream.cuh"
 #include "osc_core.cuh"
@@ -47,27 +48,27 @@ constexpr int kMixCU = 8;        // channels whose loads are in flight together
 
 // master / cue of the two frames at f (even), channels walked in order (mixer.rs:57-68); the panner outputs of
 // observed channels are written on the way.
-__device__ __forceinline__ void mix_pair(const FusedBatch& b, uint64_t f, float4& m, float4& cu)
+__device__ __forceinline__ void mix_pair(const FusedChan* __restrict__ chan, int n_channels, uint64_t f, float4& m, float4& cu)
 {
     m = make_float4(0.f, 0.f, 0.f, 0.f);                    // util::zero(master), util::zero(cue) (mixer.rs:54-55)
     cu = m;
-    for (int ch0 = 0; ch0 < b.n_channels; ch0 += kMixCU) {
+    for (int ch0 = 0; ch0 < n_channels; ch0 += kMixCU) {
         float2 L[kMixCU], R[kMixCU];
 #pragma unroll
         for (int k = 0; k < kMixCU; k++) {
             L[k] = make_float2(0.f, 0.f);
             R[k] = L[k];
-            if (ch0 + k < b.n_channels) {
-                const float* l = b.chan[ch0 + k].left;
-                const float* r = b.chan[ch0 + k].right;
+            if (ch0 + k < n_channels) {
+                const float* l = chan[ch0 + k].left;
+                const float* r = chan[ch0 + k].right;
                 if (l) L[k] = ldcg2(l + f);
                 if (r) R[k] = (r == l) ? L[k] : ldcg2(r + f);
             }
         }
 #pragma unroll
         for (int k = 0; k < kMixCU; k++) {
-            if (ch0 + k >= b.n_channels) break;
-            const FusedChan& c = b.chan[ch0 + k];
+            if (ch0 + k >= n_channels) break;
+            const FusedChan& c = chan[ch0 + k];
             const double g = c.gain;
             float lx = mix1(L[k].x, g), ly = mix1(L[k].y, g), rx, ry;
             if (c.left == c.right) { rx = lx; ry = ly; }
@@ -80,12 +81,12 @@ __device__ __forceinline__ void mix_pair(const FusedBatch& b, uint64_t f, float4
 }
 
 // the odd last frame of a call (one frame, scalar)
-__device__ __forceinline__ void mix_frame(const FusedBatch& b, uint64_t f, float2& m, float2& cu)
+__device__ __forceinline__ void mix_frame(const FusedChan* __restrict__ chan, int n_channels, uint64_t f, float2& m, float2& cu)
 {
     m = make_float2(0.f, 0.f);
     cu = m;
-    for (int ch = 0; ch < b.n_channels; ch++) {
-        const FusedChan& c = b.chan[ch];
+    for (int ch = 0; ch < n_channels; ch++) {
+        const FusedChan& c = chan[ch];
         const float l = c.left ? __ldcg(c.left + f) : 0.f, r = c.right ? __ldcg(c.right + f) : 0.f;
         m.x += mix1(l, c.gain); m.y += mix1(r, c.gain);
         if (c.cue) { cu.x += l; cu.y += r; }
@@ -100,10 +101,21 @@ __global__ void __launch_bounds__(kT) fused_voice_mix_kernel(const __grid_consta
     pdl_prologue();
     extern __shared__ __align__(16) unsigned char fv_smem[];
     float4* tile = reinterpret_cast<float4*>(fv_smem);                              // [256][VPR], swizzled
-    double* xch = reinterpret_cast<double*>(fv_smem + (size_t)kT * LC * sizeof(float));   // kEqXchDoubles
-    const FusedVoice& vc = b.voice[blockIdx.y];
+    EqShared<LC>* sh = reinterpret_cast<EqShared<LC>*>(fv_smem + (size_t)kT * LC * sizeof(float));
+    FusedChan* s_chan = reinterpret_cast<FusedChan*>(sh + 1);                       // [n_channels]
+    const FusedVoice vc = b.voice[blockIdx.y];
     const EqStreamConsts& q = b.eq;
     const int tid = threadIdx.x;
+    // Tables (device memory) and the channel table (kernel parameters) -> shared memory, a word per thread: one
+    // round of overlapping loads instead of a constant-bank miss per table line in program order.
+    load_tables<LC>(q.tab, sh, tid);
+    {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(b.chan);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(s_chan);
+        const int words = b.n_channels * (int)(sizeof(FusedChan) / 8);
+        for (int i = tid; i < words; i += kT) dst[i] = src[i];
+    }
+    __syncthreads();
     const int halo = (int)q.halo;
     const int U = (int)b.owned;
     const int64_t c0 = (int64_t)blockIdx.x * U - halo;        // chunk of thread 0
@@ -118,12 +130,14 @@ __global__ void __launch_bounds__(kT) fused_voice_mix_kernel(const __grid_consta
     for (int e = 0; e < 8; e++) v[e] = 0.0;
     if (active) {
 #pragma unroll
-        for (int e = 0; e < 8; e++) v[e] = q.K[e];
+        for (int e = 0; e < 8; e++) v[e] = sh->K[e];
         // (t + i) as f64: one conversion per chunk, the samples are exact +1.0 steps below 2^53 (checked by the host)
         const double base = (double)(b.t0 + (uint64_t)c * LC);
         const double freq = vc.freq, sr = b.sample_rate, inv_sr = b.inv_sample_rate;
         const int wf = vc.waveform;
-#pragma unroll
+        // a real loop (four samples per trip): unrolled it is VPR copies of the sine code and the warps of the CTA
+        // stall on instruction fetch
+#pragma unroll 1
         for (int vv = 0; vv < VPR; vv++) {
             double n[4];
 #pragma unroll
@@ -135,14 +149,14 @@ __global__ void __launch_bounds__(kT) fused_voice_mix_kernel(const __grid_consta
             for (int j = 0; j < 4; j++) {
                 const double sd = (double)s[j];
 #pragma unroll
-                for (int e = 0; e < 8; e++) v[e] = fma(sd, q.V[vv * 4 + j][e], v[e]);
+                for (int e = 0; e < 8; e++) v[e] = fma(sd, sh->V[vv * 4 + j][e], v[e]);
             }
         }
         if (c == 0) {                                      // v_0 = A p_init + z_0
             const double pl[4] = {st[0], st[1], st[2], st[3]}, ph[4] = {st[4], st[5], st[6], st[7]};
             double yl[4], yh[4];
-            tri_apply(q.pow_lo[0], pl, yl);
-            tri_apply(q.pow_hi[0], ph, yh);
+            tri_apply(sh->pow_lo[0], pl, yl);
+            tri_apply(sh->pow_hi[0], ph, yh);
 #pragma unroll
             for (int e = 0; e < 4; e++) { v[e] += yl[e]; v[4 + e] += yh[e]; }
         }
@@ -158,7 +172,7 @@ __global__ void __launch_bounds__(kT) fused_voice_mix_kernel(const __grid_consta
 
     // ---- A2. scan (eq_stream.cuh): two block barriers, the rows are visible after the first ----
     double S[8];
-    scan_start_states(q, v, S, xch, tid);
+    scan_start_states<LC>(q, sh, v, S, tid);
     if (bad_init) {
 #pragma unroll
         for (int e = 0; e < 8; e++) S[e] = __longlong_as_double(0x7ff8000000000000ll);
@@ -265,14 +279,14 @@ __global__ void __launch_bounds__(kT) fused_voice_mix_kernel(const __grid_consta
             for (uint32_t pi = tid; pi < npairs; pi += kT) {
                 float4 m, cu;
                 const uint64_t f = fb + 2ull * pi;
-                mix_pair(b, f, m, cu);
+                mix_pair(s_chan, b.n_channels, f, m, cu);
                 *reinterpret_cast<float4*>(b.master + 2 * f) = m;
                 *reinterpret_cast<float4*>(b.cue + 2 * f) = cu;
                 seg[pi] = m;
             }
             if (((fe - fb) & 1) && tid == 0) {             // odd frame count: last frame
                 float2 m, cu;
-                mix_frame(b, fe - 1, m, cu);
+                mix_frame(s_chan, b.n_channels, fe - 1, m, cu);
                 b.master[2 * (fe - 1)] = m.x; b.master[2 * (fe - 1) + 1] = m.y;
                 b.cue[2 * (fe - 1)] = cu.x; b.cue[2 * (fe - 1) + 1] = cu.y;
                 seg[npairs] = make_float4(m.x, m.y, 0.f, 0.f);
@@ -320,13 +334,13 @@ __global__ void __launch_bounds__(kT) fused_voice_mix_kernel(const __grid_consta
         for (uint64_t pi = p_lo + tid; pi < p_hi; pi += kT) {
             float4 m, cu;
             const uint64_t f = f_begin + 2ull * pi;
-            mix_pair(b, f, m, cu);
+            mix_pair(s_chan, b.n_channels, f, m, cu);
             *reinterpret_cast<float4*>(b.master + 2 * f) = m;
             *reinterpret_cast<float4*>(b.cue + 2 * f) = cu;
         }
         if (((f_end - f_begin) & 1) && rank == 0 && tid == 0) {
             float2 m, cu;
-            mix_frame(b, f_end - 1, m, cu);
+            mix_frame(s_chan, b.n_channels, f_end - 1, m, cu);
             b.master[2 * (f_end - 1)] = m.x; b.master[2 * (f_end - 1) + 1] = m.y;
             b.cue[2 * (f_end - 1)] = cu.x; b.cue[2 * (f_end - 1) + 1] = cu.y;
         }
@@ -334,7 +348,7 @@ __global__ void __launch_bounds__(kT) fused_voice_mix_kernel(const __grid_consta
 }
 
 template <int LC>
-size_t smem_bytes() { return (size_t)kT * LC * sizeof(float) + (size_t)kEqXchDoubles * sizeof(double); }
+size_t smem_bytes() { return (size_t)kT * LC * sizeof(float) + sizeof(EqShared<LC>) + (size_t)kFusedMaxChans * sizeof(FusedChan); }
 
 template <int LC>
 int configure(mxl_ctx* ctx)
@@ -408,12 +422,18 @@ uint32_t fused_owned_chunks(const EqStreamConsts& eq, uint32_t spt, bool* meter_
 int fused_voice_mix_supported(mxl_ctx* ctx, uint32_t chunk, int n_voices)
 {
     if (!ctx || !ctx->has_device() || n_voices < 1 || n_voices > kFusedMaxVoices) return 0;
+    const uint32_t key = (chunk << 8) | (uint32_t)n_voices;
+    auto it = ctx->fused_clusters.find(key);
+    if (it != ctx->fused_clusters.end()) return it->second;
     if (ctx->activate() != MXL_OK) return 0;
+    int clusters = 0;
     switch (chunk) {
-    case 32: return supported_lc<32>(ctx, n_voices);
-    case 64: return supported_lc<64>(ctx, n_voices);
-    default: return 0;
+    case 32: clusters = supported_lc<32>(ctx, n_voices); break;
+    case 64: clusters = supported_lc<64>(ctx, n_voices); break;
+    default: break;
     }
+    if (getenv("MXL_DEBUG")) fprintf(stderr, "[mxl] fused_voice_mix_kernel<%u>: cluster of %d CTAs -> %d clusters resident\n", chunk, n_voices, clusters);
+    return ctx->fused_clusters[key] = clusters;
 }
 
 int launch_fused_voice_mix(mxl_ctx* ctx, const FusedBatch& b)
@@ -425,7 +445,7 @@ int launch_fused_voice_mix(mxl_ctx* ctx, const FusedBatch& b)
     if (b.n_voices < 1 || b.n_voices > kFusedMaxVoices || b.n_channels < 1 || b.n_channels > kFusedMaxChans)
         MXL_FAIL(MXL_ERR_INVALID, "fused_voice_mix_kernel: %d voices / %d channels", b.n_voices, b.n_channels);
     if (q.halo == 0 || q.halo > (uint32_t)kT / 2 || q.lev_lo > (uint32_t)kEqPlanLevels || q.lev_hi > (uint32_t)kEqPlanLevels ||
-        q.back_lo > 3 || q.back_hi > 3 || !q.lane_pow || b.owned == 0 || b.owned + q.halo > (uint32_t)kT)
+        q.back_lo > 3 || q.back_hi > 3 || !q.tab || b.owned == 0 || b.owned + q.halo > (uint32_t)kT)
         MXL_FAIL(MXL_ERR_INVALID, "fused_voice_mix_kernel: bad plan (chunk %u, halo %u, owned %u)", q.chunk, q.halo, b.owned);
     switch (q.chunk) {
     case 32: return launch_lc<32>(ctx, b);

@@ -43,6 +43,7 @@ struct mxl_graph {
     std::set<int> fusion_veto;                                         // mixers whose group's parameters left the fused kernel's domain
     std::vector<FusedGroup> fused;
     uint64_t runs_since_plan = 0;
+    std::vector<mxl_line*> resize_list;                                // lines a run sizes to the call: every output the plan writes
     float last_call_host_us = 0.f;                                     // host time of the last run_ticks call
     uint32_t last_call_ticks = 0;
 
@@ -266,6 +267,10 @@ int build_plan(mxl_graph* g)
         return a.level != b.level ? a.level < b.level : a.kind < b.kind;
     });
 
+    g->resize_list.clear();
+    for (int id : g->run_order)
+        for (size_t o = 0; o < g->out_lines[id].size(); o++)
+            if (!g->hidden.count({id, (uint32_t)o})) g->resize_list.push_back(g->out_lines[id][o]);
     g->dirty = false;
     g->timings_pending = false;
     g->runs_since_plan = 0;
@@ -400,9 +405,7 @@ int mxl_graph_run_ticks(mxl_graph* g, uint64_t tick0, uint32_t n_ticks)
 
     const uint64_t frames = (uint64_t)n_ticks * ctx->spt;
     const uint64_t t = tick0 * (uint64_t)ctx->spt;                     // engine.rs:490
-    for (int id : g->run_order)
-        for (mxl_line* l : g->out_lines[id])
-            MXL_TRY(line_resize(l, l->type == MXL_LINE_VIDEO ? n_ticks : frames));
+    for (mxl_line* l : g->resize_list) MXL_TRY(line_resize(l, l->type == MXL_LINE_VIDEO ? n_ticks : frames));
     // host-fed sources must cover the call
     for (int id : g->run_order) {
         mxl_module* m = g->modules[id];
@@ -428,7 +431,8 @@ int mxl_graph_run_ticks(mxl_graph* g, uint64_t tick0, uint32_t n_ticks)
     // measured on a one-tick live call (the worst case for the fork/join's four API calls): 26.4 us per tick with
     // the split, 29.2 us without -- the overlap of the audio chain with the compositor still pays
     static const uint32_t split_min_ticks = getenv("MXL_SPLIT_MIN_TICKS") ? (uint32_t)atoi(getenv("MXL_SPLIT_MIN_TICKS")) : 1u;
-    const bool split = g->split_streams && has_audio && has_video && !has_mixed && n_ticks >= split_min_ticks && !getenv("MXL_NO_STREAM_SPLIT");
+    static const bool env_no_split = getenv("MXL_NO_STREAM_SPLIT") != nullptr;
+    const bool split = g->split_streams && has_audio && has_video && !has_mixed && n_ticks >= split_min_ticks && !env_no_split;
     cudaStream_t main_stream = ctx->stream;
     // every exit path re-serialises the two streams: later main-stream work (downloads, the next call's line_resize)
     // must be ordered behind audio kernels already enqueued on the side stream, also when a stage fails half way
@@ -580,7 +584,8 @@ int mxl_graph_performance(mxl_graph* g, mxl_perf_account* out, uint32_t cap)
         if (is_source(s.kind) || s.modules.empty()) continue;
         const float share = 1.f / (float)s.modules.size() / ticks;
         for (int id : s.modules) {
-            if (n < cap) out[n] = mxl_perf_account{id, s.kind, s.last_ms >= 0.f ? s.last_ms * 1000.f * share : -1.f, s.last_host_us * share};
+            // (a fused voice group's stage lists every module it replaced: each gets an equal share, under its own kind)
+            if (n < cap) out[n] = mxl_perf_account{id, g->modules[id] ? g->modules[id]->kind : s.kind, s.last_ms >= 0.f ? s.last_ms * 1000.f * share : -1.f, s.last_host_us * share};
             n++;
         }
     }

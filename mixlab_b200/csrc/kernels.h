@@ -95,21 +95,27 @@ struct EqStreamInst {
     uint32_t* poison;                            // device: {first chunk with a non-finite carry (~0 = none), CTAs finished}
     double g_lo, g_mid, g_hi;
 };
-// Constants of the time-parallel scheme for one chunk length (host: EqStreamPlan, eq_plan.h), shared by
-// eq_stream_kernel and the fused voice kernel: ~5.6 KB of kernel parameters, read through the constant bank.
+// Tables of the time-parallel scheme for one chunk length (host: EqStreamPlan, eq_plan.h).  They live in DEVICE memory,
+// one copy per chunk length and context, and every CTA brings them into shared memory with one round of coalesced
+// loads.  (As kernel parameters they sat in the constant bank: a cold bank serves one 64-byte line per ~700-cycle miss,
+// in program order -- 32 to 64 serialised misses at the head of every CTA, 10 us of a live one-tick call.)
+struct EqDevTables {
+    double V[64][8];                             // end-state response to a unit input at sample j
+    double K[8];                                 // zero-input (VSA) end state of a chunk
+    double pow_lo[8][10];                        // A^(2^d), packed lower-triangular
+    double pow_hi[8][10];
+    double lane_pow[2][10][32];                  // A^(lane+1), [cascade][entry][lane] (EqStreamPlan::lane_pow)
+};
+// Scalars of the scheme, shared by eq_stream_kernel and the fused voice kernel (kernel parameters).
 struct EqStreamConsts {
     uint32_t chunk;                              // LC: 16, 32 or 64
     uint32_t halo;                               // chunks recomputed ahead of a CTA's own range
     uint32_t lev_lo, lev_hi;                     // scan levels per cascade (<= 8); levels >= 5 cross warps
     uint32_t back_lo, back_hi;                   // previous warps a warp's start states still hear (<= 3)
-    const double* lane_pow;                      // device: A^(lane+1), [cascade][entry][lane] (EqStreamPlan::lane_pow)
+    const EqDevTables* tab;                      // device
     double c_lo, c_hi;
-    double pow_lo[8][10];                        // A^(2^d), packed lower-triangular
-    double pow_hi[8][10];
-    double K[8];                                 // zero-input (VSA) end state of a chunk
-    double V[64][8];                             // end-state response to a unit input at sample j
 };
-struct EqStreamBatch {                           // ~7 KB of kernel parameters (limit 32 KB on sm_100)
+struct EqStreamBatch {
     uint64_t frames;
     uint32_t n_chunks;
     int32_t n;

@@ -825,10 +825,9 @@ static uint32_t eq_pick_chunk(const mxl_ctx* ctx, uint64_t frames, int n_inst)
     return chunk;
 }
 
-// Kernel-parameter copy of a plan (eq_plan.h); the per-lane powers live in device memory (5 KB per plan, uploaded once).
+// Kernel-parameter scalars of a plan (eq_plan.h); its tables live in device memory (9 KB per plan, uploaded once).
 static int fill_eq_consts(mxl_ctx* ctx, const mxl::EqStreamPlan& plan, k::EqStreamConsts* q)
 {
-    static_assert(sizeof(plan.V) == sizeof(q->V) && sizeof(plan.pow_lo) == sizeof(q->pow_lo), "plan layout");
     q->chunk = plan.lc;
     q->halo = plan.halo;
     q->lev_lo = plan.lev_lo;
@@ -837,15 +836,21 @@ static int fill_eq_consts(mxl_ctx* ctx, const mxl::EqStreamPlan& plan, k::EqStre
     q->back_hi = plan.back_hi;
     void*& tab = ctx->eq_stream_tables[plan.lc];
     if (!tab) {
-        MXL_CUDA(cudaMalloc(&tab, sizeof plan.lane_pow));
-        MXL_CUDA(cudaMemcpyAsync(tab, plan.lane_pow, sizeof plan.lane_pow, cudaMemcpyHostToDevice, ctx->stream));
+        static_assert(sizeof(plan.V) == sizeof(k::EqDevTables::V) && sizeof(plan.pow_lo) == sizeof(k::EqDevTables::pow_lo) &&
+                      sizeof(plan.lane_pow) == sizeof(k::EqDevTables::lane_pow), "plan layout");
+        k::EqDevTables* host = new k::EqDevTables();
+        memcpy(host->V, plan.V, sizeof host->V);
+        memcpy(host->K, plan.K, sizeof host->K);
+        memcpy(host->pow_lo, plan.pow_lo, sizeof host->pow_lo);
+        memcpy(host->pow_hi, plan.pow_hi, sizeof host->pow_hi);
+        memcpy(host->lane_pow, plan.lane_pow, sizeof host->lane_pow);
+        cudaError_t e = cudaMalloc(&tab, sizeof(k::EqDevTables));
+        if (e == cudaSuccess) e = cudaMemcpy(tab, host, sizeof(k::EqDevTables), cudaMemcpyHostToDevice);   // synchronous: `host` dies here
+        delete host;
+        if (e != cudaSuccess) { tab = nullptr; MXL_FAIL(MXL_ERR_CUDA, "EqThree tables: %s", cudaGetErrorString(e)); }
     }
-    q->lane_pow = (const double*)tab;
+    q->tab = (const k::EqDevTables*)tab;
     q->c_lo = plan.c_lo; q->c_hi = plan.c_hi;
-    memcpy(q->pow_lo, plan.pow_lo, sizeof q->pow_lo);
-    memcpy(q->pow_hi, plan.pow_hi, sizeof q->pow_hi);
-    memcpy(q->K, plan.K, sizeof q->K);
-    memcpy(q->V, plan.V, sizeof q->V);
     return MXL_OK;
 }
 

@@ -495,6 +495,101 @@ void orc_bicubic_plane(const uint8_t *src, uint32_t sw, uint32_t sh, uint32_t ss
     free(xpos); free(ypos); free(xco); free(yco); free(tmp);
 }
 
+
+/* ---- the scaler as a CPU implementation would arrange it (same arithmetic, bit-identical) ---- */
+typedef struct { uint32_t src_n, dst_n; int32_t *pos; int16_t *coef; } tap_cache_entry;
+#define TAP_CACHE 32
+static __thread tap_cache_entry tap_cache[TAP_CACHE];
+static __thread int tap_cache_n = 0, tap_cache_next = 0;
+
+/* per-thread cache of tap tables by (source length, destination length); `keep` is never evicted */
+static const tap_cache_entry *taps_for(uint32_t src_n, uint32_t dst_n, const tap_cache_entry *keep)
+{
+    for (int i = 0; i < tap_cache_n; i++)
+        if (tap_cache[i].src_n == src_n && tap_cache[i].dst_n == dst_n) return &tap_cache[i];
+    tap_cache_entry *e;
+    if (tap_cache_n < TAP_CACHE) {
+        e = &tap_cache[tap_cache_n++];
+    } else {
+        e = &tap_cache[tap_cache_next];
+        if (e == keep) e = &tap_cache[(tap_cache_next + 1) % TAP_CACHE];
+        tap_cache_next = (int)((e - tap_cache) + 1) % TAP_CACHE;
+        free(e->pos); free(e->coef);
+    }
+    e->src_n = src_n; e->dst_n = dst_n;
+    e->pos = malloc(sizeof(int32_t) * dst_n);
+    e->coef = malloc(sizeof(int16_t) * 4 * dst_n);
+    bicubic_table(src_n, dst_n, e->pos, e->coef);
+    return e;
+}
+
+void orc_bicubic_plane_fast(const uint8_t *src, uint32_t sw, uint32_t sh, uint32_t sstride,
+                            uint8_t *dst, uint32_t dw, uint32_t dh, uint32_t dstride)
+{
+    const tap_cache_entry *tx = taps_for(sw, dw, NULL), *ty = taps_for(sh, dh, tx);
+    uint8_t *tmp = malloc((size_t)dw * sh);
+    /* columns whose four taps need no clamp */
+    uint32_t x_lo = 0, x_hi = dw;
+    while (x_lo < dw && tx->pos[x_lo] < 0) x_lo++;
+    while (x_hi > x_lo && tx->pos[x_hi - 1] + 3 >= (int)sw) x_hi--;
+    for (uint32_t y = 0; y < sh; y++) {
+        const uint8_t *row = src + (size_t)y * sstride;
+        uint8_t *out = tmp + (size_t)y * dw;
+        for (uint32_t x = 0; x < dw; x++) {
+            const int16_t *c = tx->coef + 4 * x;
+            int acc;
+            if (x >= x_lo && x < x_hi) {
+                const uint8_t *p = row + tx->pos[x];
+                acc = c[0] * p[0] + c[1] * p[1] + c[2] * p[2] + c[3] * p[3];
+            } else {
+                acc = 0;
+                for (int k = 0; k < 4; k++) {
+                    int sx = tx->pos[x] + k;
+                    sx = sx < 0 ? 0 : (sx >= (int)sw ? (int)sw - 1 : sx);
+                    acc += c[k] * (int)row[sx];
+                }
+            }
+            out[x] = clip_u8((acc + 8192) >> 14);
+        }
+    }
+    for (uint32_t y = 0; y < dh; y++) {
+        const uint8_t *r[4];
+        for (int k = 0; k < 4; k++) {
+            int sy = ty->pos[y] + k;
+            sy = sy < 0 ? 0 : (sy >= (int)sh ? (int)sh - 1 : sy);
+            r[k] = tmp + (size_t)sy * dw;
+        }
+        const int c0 = ty->coef[4 * y], c1 = ty->coef[4 * y + 1], c2 = ty->coef[4 * y + 2], c3 = ty->coef[4 * y + 3];
+        uint8_t *out = dst + (size_t)y * dstride;
+        for (uint32_t x = 0; x < dw; x++) {
+            int acc = c0 * r[0][x] + c1 * r[1][x] + c2 * r[2][x] + c3 * r[3][x];
+            acc = (acc + 8192) >> 14;
+            out[x] = (uint8_t)(acc < 0 ? 0 : (acc > 255 ? 255 : acc));
+        }
+    }
+    free(tmp);
+}
+
+void orc_letterbox_scale(const orc_frame_layout *li, const uint8_t *in, const orc_frame_layout *lo, uint8_t *out)
+{
+    if (li->width == lo->width && li->height == lo->height) {          /* encode.rs:342-345 */
+        memcpy(out, in, lo->size);
+        return;
+    }
+    orc_scale_geometry g;
+    orc_scale_geometry_yuv420p(li->width, li->height, lo->width, lo->height, &g);
+    orc_frame_blank(lo, out);                                           /* encode.rs:382 */
+    for (int p = 0; p < 3; p++) {
+        const int sh = p ? 1 : 0;
+        const uint32_t sw = p ? (li->width + 1) / 2 : li->width;
+        const uint32_t dw = g.scaled_w >> sh, dh = g.scaled_h >> sh;
+        if (!dw || !dh) continue;
+        orc_bicubic_plane_fast(in + li->offset[p], sw, li->plane_h[p], li->stride[p],
+                               out + lo->offset[p] + (size_t)(g.letterbox_y >> sh) * lo->stride[p] + (g.letterbox_x >> sh),
+                               dw, dh, lo->stride[p]);
+    }
+}
+
 /* ======================================================================================== */
 /* engine walker: Engine::run_tick, src/engine.rs:400-510                                   */
 /* ======================================================================================== */
@@ -766,4 +861,31 @@ void orc_graph_meter(const orc_graph *g, int module, float peak[2], double sumsq
     peak[0] = m->meter_peak[0]; peak[1] = m->meter_peak[1];
     sumsq[0] = m->meter_sumsq[0]; sumsq[1] = m->meter_sumsq[1];
     *clip = m->meter_clip;
+}
+
+/* ======================================================================================== */
+/* one live session, tick after tick (see the header)                                        */
+/* ======================================================================================== */
+void orc_session_run(orc_session *s, uint64_t tick0, uint32_t n_ticks)
+{
+    const size_t spt = s->graph->spt, n = 2 * spt;
+    for (uint32_t k = 0; k < n_ticks; k++) {
+        const uint64_t tick = tick0 + k;
+        /* StreamInput x2: the tick's i16 -> f32 (stream_input.rs:110-112) */
+        for (int src = 0; src < 2; src++) {
+            const size_t off = (size_t)((tick * 2 + (uint64_t)src) * n) % (s->pcm_in_samples - n + 1);
+            orc_pcm_unpack_i16(s->pcm_in + off, s->scratch + (size_t)src * n, n);
+        }
+        /* Engine::run_tick over the audio graph; the master bus goes to the monitor */
+        orc_graph_run_tick(s->graph, tick, s->master_module, 0, s->scratch + 2 * n);
+        /* VideoMixer: the stored layers change every ticks_per_frame ticks; blank + crossfade every tick */
+        const uint64_t fi = tick / s->ticks_per_frame;
+        const uint8_t *a = s->layers_a + (size_t)(fi % s->n_layers) * s->lay.size;
+        const uint8_t *b = s->layers_b + (size_t)(fi % s->n_layers) * s->lay.size;
+        orc_frame_blank(&s->lay, s->composite);                        /* video_mixer.rs:151 */
+        orc_video_crossfade(&s->lay, a, b, s->fade, s->composite);
+        /* Monitor: scale to the monitor's size, pack the bus */
+        orc_letterbox_scale(&s->lay, s->composite, &s->lay_mon, s->monitor_out);
+        orc_pcm_pack_i16(s->scratch + 2 * n, s->pcm_out, n);
+    }
 }

@@ -143,6 +143,16 @@ void orc_yuv420p_to_rgba(const orc_frame_layout *lay, const uint8_t *yuv, uint8_
 void orc_bicubic_plane(const uint8_t *src, uint32_t sw, uint32_t sh, uint32_t sstride,
                        uint8_t *dst, uint32_t dw, uint32_t dh, uint32_t dstride);
 
+/* The same arithmetic as orc_bicubic_plane (bit-identical, tests/test_oracle_golden.py) arranged the way a CPU scaler
+ * is written: tap tables built once per geometry and cached, edge columns clamped outside the inner loop, the
+ * vertical pass row-contiguous so the compiler vectorises it.  Used where the CPU arm is TIMED (bench.py's session
+ * variant), so that the baseline is not handicapped by the clamps in the definition's inner loops. */
+void orc_bicubic_plane_fast(const uint8_t *src, uint32_t sw, uint32_t sh, uint32_t sstride,
+                            uint8_t *dst, uint32_t dw, uint32_t dh, uint32_t dstride);
+/* DynamicScaler::scale (src/video/encode.rs:338-397): identity copy when the sizes agree, else the three planes
+ * resampled (orc_bicubic_plane_fast) into the letterboxed sub-frame of a blank `out` frame. */
+void orc_letterbox_scale(const orc_frame_layout *lay_in, const uint8_t *in, const orc_frame_layout *lay_out, uint8_t *out);
+
 /* ---- engine walker ---------------------------------------------------------------------- */
 
 enum { ORC_LINE_MONO = 0, ORC_LINE_STEREO = 1, ORC_LINE_VIDEO = 2 };
@@ -171,6 +181,25 @@ void orc_graph_run_tick(orc_graph *g, uint64_t tick, int capture_module, int cap
 int orc_graph_last_order(const orc_graph *g, int *order, int cap);
 /* meter values recorded by ORC_MOD_METER at the last tick */
 void orc_graph_meter(const orc_graph *g, int module, float peak[2], double sumsq[2], int *clip);
+
+/* ---- one live session tick after tick, as the reference's engine thread and its two neighbours do it per tick
+ * (timed CPU arm of bench.py's session variant; the per-function restatements above are what it calls):
+ *   StreamInput x2: convert_sample of the tick's i16 (stream_input.rs:110-112,167-173)
+ *   Engine::run_tick over the audio graph (engine.rs:400-510), master bus captured
+ *   VideoMixer: AvFrame::blank + crossfade of the two stored 1080p layers (video_mixer.rs:150-239); the sources
+ *     deliver a new frame every `ticks_per_frame` ticks and the mixer re-uses the stored ones in between (92-143)
+ *   Monitor: DynamicScaler to the monitor's size (encode.rs:279-287,338-397) and AudioCtx::send_audio's pack (184-195)
+ * layers_a / layers_b hold n_layers frames each, used round-robin.  Outputs of the LAST tick are left in
+ * monitor_out (lay_mon.size bytes) and pcm_out (2 * spt i16). */
+typedef struct {
+    orc_graph *graph; int master_module;
+    orc_frame_layout lay, lay_mon;
+    const uint8_t *layers_a, *layers_b; uint32_t n_layers, ticks_per_frame;
+    const int16_t *pcm_in; size_t pcm_in_samples;      /* ring of interleaved i16 the two StreamInputs read */
+    uint8_t fade;
+    uint8_t *composite, *monitor_out; int16_t *pcm_out; float *scratch;   /* caller-owned work buffers */
+} orc_session;
+void orc_session_run(orc_session *s, uint64_t tick0, uint32_t n_ticks);
 
 #ifdef __cplusplus
 }

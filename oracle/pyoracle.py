@@ -70,6 +70,7 @@ def lib():
         _lib.orc_fader_to_u8.restype = C.c_uint8
         _lib.orc_fader_to_u8.argtypes = [C.c_double]
         _lib.orc_clip_detect.restype = C.c_int
+        _lib.orc_session_run.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
     return _lib
 
 
@@ -354,6 +355,46 @@ def letterbox_scale(data, lay_in, out_w, out_h):
         plane = want[lay.offset[p]:lay.offset[p] + lay.stride[p] * lay.plane_h[p]].reshape(lay.plane_h[p], lay.stride[p])
         plane[(ly >> sh):(ly >> sh) + dh, (lx >> sh):(lx >> sh) + dw] = dst.reshape(dh, dw)
     return want
+
+
+def letterbox_scale_fast(data, lay_in, out_w, out_h):
+    """orc_letterbox_scale: the same result as letterbox_scale through the CPU-arranged scaler (the timed CPU arm)."""
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    lay = frame_layout(out_w, out_h)
+    out = np.empty(lay.size, np.uint8)
+    lib().orc_letterbox_scale(C.byref(lay_in), _p(data), C.byref(lay), _p(out))
+    return out
+
+
+class SessionStruct(C.Structure):
+    _fields_ = [("graph", C.c_void_p), ("master_module", C.c_int), ("lay", FrameLayout), ("lay_mon", FrameLayout),
+                ("layers_a", C.c_void_p), ("layers_b", C.c_void_p), ("n_layers", C.c_uint32), ("ticks_per_frame", C.c_uint32),
+                ("pcm_in", C.c_void_p), ("pcm_in_samples", C.c_size_t), ("fade", C.c_uint8),
+                ("composite", C.c_void_p), ("monitor_out", C.c_void_p), ("pcm_out", C.c_void_p), ("scratch", C.c_void_p)]
+
+
+class Session:
+    """orc_session: one live session of bench.py's session variant on the CPU -- per tick two StreamInput unpacks,
+    Engine::run_tick over the audio graph, VideoMixer blank + crossfade of the stored layers, the Monitor's scaler
+    and PCM pack -- entirely in C (one ctypes call runs n ticks), so that threads of the CPU arm do not meet on the GIL."""
+
+    def __init__(self, graph, master_module, width, height, mon_w, mon_h, layers_a, layers_b, ticks_per_frame, pcm_in, fader):
+        self.graph = graph
+        self.lay, self.lay_mon = frame_layout(width, height), frame_layout(mon_w, mon_h)
+        self.layers_a = np.ascontiguousarray(layers_a, np.uint8)
+        self.layers_b = np.ascontiguousarray(layers_b, np.uint8)
+        self.pcm_in = np.ascontiguousarray(pcm_in, np.int16)
+        n = 2 * graph.spt
+        self.composite = np.empty(self.lay.size, np.uint8)
+        self.monitor_out = np.empty(self.lay_mon.size, np.uint8)
+        self.pcm_out = np.empty(n, np.int16)
+        self.scratch = np.empty(3 * n, np.float32)
+        self.s = SessionStruct(graph._g, master_module, self.lay, self.lay_mon, _p(self.layers_a), _p(self.layers_b),
+                               self.layers_a.size // self.lay.size, ticks_per_frame, _p(self.pcm_in), self.pcm_in.size,
+                               fader_to_u8(fader), _p(self.composite), _p(self.monitor_out), _p(self.pcm_out), _p(self.scratch))
+
+    def run(self, tick0, n_ticks):
+        lib().orc_session_run(C.byref(self.s), C.c_uint64(tick0), C.c_uint32(n_ticks))
 
 
 class OutputDevice:

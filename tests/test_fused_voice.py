@@ -45,6 +45,15 @@ def eq_ids(desc):
     return [i for i, (k, _) in enumerate(desc.modules) if k == "EqThree"]
 
 
+def assert_same_state(a_states, b_states):
+    """EqThree poles after the call.  Chunks other than a call's first start from a scanned state that carries f64
+    rounding noise (~1e-16 relative; the `as f32` of the outputs absorbs it -- the lines above are bit-identical), and
+    the two paths cut the call into chunks differently: the stored f64 poles agree to that noise, not to the bit.
+    The history (the last three inputs) is exact."""
+    for a, b in zip(a_states, b_states):
+        assert np.allclose(a[:8], b[:8], rtol=1e-12, atol=1e-300) and np.array_equal(a[8:], b[8:])
+
+
 def assert_same_meter(a, b):
     assert np.array_equal(a["peak"], b["peak"]) and np.array_equal(a["clip"], b["clip"])
     assert np.array_equal(a["sumsq"], b["sumsq"])          # same summation order in both paths
@@ -66,8 +75,7 @@ def test_config2_fused_equals_staged(mxl, sr_spt, calls):
     for t in taps:
         assert mismatch_count(fl[t], sl[t]) == 0, t
     assert_same_meter(fm, sm)
-    for a, b in zip(fs, ss):
-        assert np.array_equal(a, b)
+    assert_same_state(fs, ss)
 
 
 def test_config2_is_one_launch_per_call(mxl, ctx48):
@@ -178,8 +186,7 @@ def test_odd_shapes_fused_equals_staged_and_oracle(mxl, oracle, sr_spt):
     for t in taps:
         assert mismatch_count(fl[t], sl[t]) == 0, t
     assert_same_meter(fm, sm)
-    for a, b in zip(fs, ss):
-        assert np.array_equal(a, b)
+    assert_same_state(fs, ss)
     want, _, _ = oracle_run(oracle, d, sr, spt, 0, sum(calls), d.taps["master"], 2)
     assert_close_audio(fl[d.taps["master"]], want, what="odd group master")
 
@@ -245,5 +252,4 @@ def test_long_call_takes_64_sample_chunks(mxl, ctx48):
     for t in taps:
         assert mismatch_count(r[True][0][t], r[False][0][t]) == 0, t
     assert_same_meter(r[True][1], r[False][1])
-    for a, b in zip(r[True][2], r[False][2]):
-        assert np.array_equal(a, b)
+    assert_same_state(r[True][2], r[False][2])

@@ -5,6 +5,7 @@ import math
 import os
 
 import numpy as np
+import pytest
 
 from helpers import GOLDEN, load_f32, oracle_run
 from mixlab_b200 import workloads as W
@@ -296,3 +297,42 @@ def test_output_device_oracle_routes_and_clips(oracle):
     assert dev.run_tick(x) is True                                            # now the right side (-2.0) is routed: clip
     out = dev.pop(1 << 10).reshape(8, 4)
     assert np.all(out[:, 3] == -2.0) and np.all(out[:, 2] == 0.5)
+
+
+@pytest.mark.parametrize("src,dst", [((1920, 1080), (560, 350)), ((1920, 1080), (1120, 700)), ((640, 480), (1280, 720)),
+                                     ((70, 50), (560, 350)), ((34, 18), (36, 20)), ((2, 2), (64, 64)), ((3840, 2160), (320, 180)),
+                                     ((560, 350), (560, 350))])
+def test_cpu_arranged_scaler_equals_the_definition(oracle, src, dst):
+    """orc_letterbox_scale (tap tables cached, clamps hoisted, row-contiguous vertical pass: what bench.py's CPU arm
+    is timed with) against the plain two-pass definition, byte for byte."""
+    from mixlab_b200 import workloads as W
+    lay_in = oracle.frame_layout(*src)
+    data = W.random_bytes(src[0] * 7 + dst[1], lay_in.size)
+    assert np.array_equal(oracle.letterbox_scale_fast(data, lay_in, dst[0], dst[1]), oracle.letterbox_scale(data, lay_in, dst[0], dst[1]))
+
+
+def test_session_driver_equals_its_parts(oracle):
+    """orc_session_run (the timed CPU arm of the session variant) does per tick exactly what the restated functions
+    do when called one by one: unpack, Engine::run_tick, blank + crossfade of the stored layers, monitor scaler, pack."""
+    from mixlab_b200 import workloads as W
+    sr, spt, w, h = 48000, 800, 128, 72
+    desc = W.config4_audio_graph()
+    lay = oracle.frame_layout(w, h)
+    la = W.random_bytes(1, 3 * lay.size)
+    lb = W.random_bytes(2, 3 * lay.size)
+    pcm = (W.splitmix64(3, 16 * 2 * spt) & np.uint64(0xFFFF)).astype(np.uint16).view(np.int16)
+    g, ids = oracle.build_graph(desc, sr, spt)
+    sess = oracle.Session(g, ids[desc.taps["master"][0]], w, h, 56, 34, la, lb, 2, pcm, 0.3)
+    g2, ids2 = oracle.build_graph(desc, sr, spt)
+    for tick in range(7):
+        sess.run(tick, 1)
+        master = g2.run_tick(tick, (ids2[desc.taps["master"][0]], 0), 2 * spt)
+        fi = (tick // 2) % 3
+        comp = oracle.video_crossfade(lay, la[fi * lay.size:(fi + 1) * lay.size], lb[fi * lay.size:(fi + 1) * lay.size], oracle.fader_to_u8(0.3))
+        assert np.array_equal(sess.composite, comp), tick
+        assert np.array_equal(sess.monitor_out, oracle.letterbox_scale(comp, lay, 56, 34)), tick
+        assert np.array_equal(sess.pcm_out, oracle.pcm_pack_i16(master)), tick
+    # several ticks in one call leave the last tick's outputs
+    sess2 = oracle.Session(oracle.build_graph(desc, sr, spt)[0], ids[desc.taps["master"][0]], w, h, 56, 34, la, lb, 2, pcm, 0.3)
+    sess2.run(0, 7)
+    assert np.array_equal(sess2.monitor_out, sess.monitor_out) and np.array_equal(sess2.pcm_out, sess.pcm_out)

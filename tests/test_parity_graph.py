@@ -206,9 +206,11 @@ def test_params_update_and_topology_edit_between_runs(mxl, oracle, ctx48):
     g.destroy()
 
 
-def test_kernel_timing_brackets_every_launch(mxl, ctx48):
+@pytest.mark.parametrize("fusion", [True, False])
+def test_kernel_timing_brackets_every_launch(mxl, ctx48, fusion):
     """mxl_ctx_set_kernel_timing: one event pair per kernel launch, folded per kernel name."""
     g, ids = W.build_graph(ctx48, W.config2_graph())
+    g.set_fusion(fusion)
     g.run_ticks(0, 4)
     ctx48.kernel_times()
     ctx48.set_kernel_timing(True)
@@ -219,7 +221,8 @@ def test_kernel_timing_brackets_every_launch(mxl, ctx48):
     times = ctx48.kernel_times()
     ctx48.set_kernel_timing(False)
     assert sum(n for n, _ in times.values()) == launched
-    assert set(times) == {"oscillator_kernel", "eq_stream_kernel", "panner_kernel", "mixer_kernel", "meter_kernel"}
+    staged = {"oscillator_kernel", "eq_stream_kernel", "panner_kernel", "mixer_kernel", "meter_kernel"}
+    assert set(times) == ({"fused_voice_mix_kernel"} if fusion else staged)
     assert all(n == 2 and 0.0 < ms < 50.0 for n, ms in times.values())
     g.run_ticks(20, 8)
     assert ctx48.kernel_times() == {}                  # disabled: nothing recorded
@@ -239,15 +242,23 @@ def test_graph_stage_info_and_launch_count(mxl, ctx48):
     assert sum(s["algorithmic_bytes"] for s in stages) == 464 * 800 * 16
     assert sum(s["n_modules"] for s in stages) == 32
     assert all(s["last_ms"] >= 0 for s in stages if s["n_launches"])
-    # one launch serves all ten modules of a kind
-    assert launched <= 6
+    # one launch serves all ten modules of a kind -- or, fused, the whole graph
+    assert launched == 1
+    g.set_fusion(False)
+    before = ctx48.launch_count
+    g.run_ticks(16, 16)
+    assert 5 <= ctx48.launch_count - before <= 6
+    stages = g.stages()
+    assert sum(s["algorithmic_bytes"] for s in stages) == 464 * 800 * 16 and sum(s["n_modules"] for s in stages) == 32
     g.destroy()
 
 
-def test_performance_accounts_shaped_like_engine_stat(mxl, ctx48):
+@pytest.mark.parametrize("fusion", [True, False])
+def test_performance_accounts_shaped_like_engine_stat(mxl, ctx48, fusion):
     """EngineStat::report (src/engine/timing.rs:45-60): an Engine account and one account per module that ran."""
     d = W.config2_graph()
     g, ids = W.build_graph(ctx48, d)
+    g.set_fusion(fusion)
     g.set_profiling(True)
     g.run_ticks(0, 16)
     g.run_ticks(16, 16)
