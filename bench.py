@@ -222,6 +222,47 @@ class CpuEngines:
             w.join()
 
 
+class CpuSessions:
+    """`threads` independent sessions of the SESSION variant on the CPU (oracle/: orc_session_run, all per-tick work in
+    C, one ctypes call per block of ticks so the threads never meet on the GIL): per tick two StreamInput i16 unpacks,
+    Engine::run_tick over the audio graph, VideoMixer's blank + crossfade of its stored 1080p layers (new pictures
+    every second tick, as a 30 fps source delivers them), the Monitor's scaler to 560 x 350 and its PCM pack."""
+
+    def __init__(self, po, desc, threads):
+        from mixlab_b200 import workloads as W
+        self.threads = threads
+        self.sessions = []
+        lay = po.frame_layout(W.FRAME_W, W.FRAME_H)
+        for i in range(threads):
+            g, ids = po.build_graph(desc, SAMPLE_RATE, SPT)
+            la = W.random_bytes(0xC0DE + 7 * i, 2 * lay.size)
+            lb = W.random_bytes(0xC0DE + 7 * i + 1, 2 * lay.size)
+            pcm = (W.splitmix64(0x51 + i, 64 * 2 * SPT) & np.uint64(0xFFFF)).astype(np.uint16).view(np.int16)
+            self.sessions.append(po.Session(g, ids[desc.taps["master"][0]], W.FRAME_W, W.FRAME_H, 560, 350, la, lb, 2, pcm, 0.5))
+        self.tick = 0
+
+    def run(self, n_ticks):
+        """Every session runs n_ticks ticks on its own thread; returns the wall time of the slowest (seconds)."""
+        t0 = time.perf_counter()
+        workers = [threading.Thread(target=s.run, args=(self.tick, n_ticks)) for s in self.sessions]
+        for w in workers:
+            w.start()
+        for w in workers:
+            w.join()
+        self.tick += n_ticks
+        return time.perf_counter() - t0
+
+
+def cpu_session_rate(po, desc, cores, seconds):
+    """ticks/s of `cores` CPU sessions (session variant) over about `seconds` of wall time."""
+    eng = CpuSessions(po, desc, cores)
+    eng.run(2)
+    per = 4.0 / eng.run(4)
+    n = max(4, int(per * seconds))
+    dt = eng.run(n)
+    return cores * n / dt, n, dt
+
+
 def cpu_baseline_leg(args):
     from oracle import pyoracle as po
     from mixlab_b200 import workloads as W
@@ -242,11 +283,16 @@ def cpu_baseline_leg(args):
     dtn = all_engines.run(tn)
     all_engines.close()
     multi = cores * tn / dtn
+    sess_rate, sess_n, sess_dt = cpu_session_rate(po, desc, cores, 4.0) if args.workload == "av" else (None, 0, 0.0)
     return {
         "value": multi, "unit": UNIT, "cores": cores, "kind": "port",
         "sample": "%d independent engines x %d ticks of the same workload (%.1f s); single engine thread: %d ticks (%.1f s)"
                   % (cores, tn, dtn, t1, dt1),
         "single_thread_value": single,
+        "session_value": sess_rate,
+        "session_sample": "%d independent sessions x %d ticks of the session variant (%.1f s): StreamInput unpack x2, audio graph, "
+                          "blank + crossfade, scaler to 560x350 (this repo's two-pass 4-tap definition standing in for swscale), PCM pack"
+                          % (cores, sess_n, sess_dt),
         "note": "C restatement of the reference CPU engine (oracle/), not the Rust binary: no cargo/rustc in this image",
     }
 
@@ -275,6 +321,7 @@ def reference_arm(args):
         dt += engines.run(tpt)
     engines.close()
     value = args.steps * cores * tpt / dt
+    sess_rate, sess_n, sess_dt = cpu_session_rate(po, desc, cores, 10.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -287,6 +334,12 @@ def reference_arm(args):
                          "sample": "each step: %d independent engines x %d ticks" % (cores, tpt),
                          "note": "C restatement of the reference CPU engine (oracle/); the Rust reference cannot be built here"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e_session": {"value": sess_rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                        "sample": "%d independent sessions x %d ticks (%.1f s)" % (cores, sess_n, sess_dt),
+                        "work_per_tick": "StreamInput i16 unpack x2, Engine::run_tick over the 32-module audio graph, VideoMixer blank + crossfade "
+                                         "of its stored 1080p layers (a new picture every second tick), Monitor scaler to 560x350 + PCM pack",
+                        "note": "the scaler is this repo's two-pass 4-tap bicubic definition in C (stands in for swscale, which the "
+                                "reference calls; not available here)"},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -513,6 +566,47 @@ def shared_source_check(mxl, ctx, dist):
             "note": "ncclBroadcast root 0 on each context's stream, device-timed, max over ranks; 50 frames / 200 lines back to back"}
 
 
+def e2e_session_leg(mxl, ctx, dist, args, T, Ke):
+    """The same ticks as a LIVE SESSION moves them (next to `e2e`, which is the worst case: a new full-size picture per
+    layer per tick up, every full-size composite down).  The reference's sources deliver pictures at their own frame rate
+    (30 fps into 60 Hz ticks; VideoMixer re-uses its stored frames, video_mixer.rs:92-143), audio arrives as i16
+    (stream_input.rs:110-112), and its sinks take the composite at the monitor's size (560 x 350, monitor.rs:21-22) plus
+    1024-sample PCM fragments: StreamInput x2 -> VideoMixer -> Monitor beside the 32-module audio graph, through the C
+    ABI with pinned host buffers, pipelined (uploads of step k+1 overlap the downloads of step k)."""
+    from mixlab_b200 import workloads as W
+    from mixlab_b200.session import StreamSession, session_seed
+    ss = StreamSession(ctx, W.config2_graph(), T, seed=session_seed(0x5E55, dist.rank))
+
+    def steps(n, tick):
+        for i in range(n):
+            ss.enqueue_step(tick, i & 1)
+            tick += T
+            if i > 0:
+                ss.finish_step((i - 1) & 1)
+        pics, frags = ss.finish_step((n - 1) & 1)
+        ctx.synchronize()
+        return tick, pics, frags
+
+    tick, _, _ = steps(3, 0)
+    dist.barrier()
+    h2d0, d2h0, l0 = ctx.h2d_bytes, ctx.d2h_bytes, ctx.launch_count
+    t0 = time.perf_counter()
+    tick, pics, frags = steps(Ke, tick)
+    dt = time.perf_counter() - t0
+    h2d_step, d2h_step = (ctx.h2d_bytes - h2d0) // Ke, (ctx.d2h_bytes - d2h0) // Ke
+    launches = (ctx.launch_count - l0) // Ke
+    dist.barrier()
+    dt_max = dist.max(dt)
+    out = {"value": Ke * T * dist.world / dt_max, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
+           "d2h_bytes_per_tick": d2h_step / T, "h2d_bytes_per_tick": h2d_step / T, "steps": Ke, "ms_per_step": dt_max / Ke * 1e3,
+           "h2d_gbs": h2d_step * Ke / dt_max / 1e9, "d2h_gbs": d2h_step * Ke / dt_max / 1e9, "launches_per_step": int(launches),
+           "pictures_per_step": pics, "pcm_fragments_per_step": frags, "source_fps": ss.fps, "monitor": "560x350",
+           "graph": "2 x StreamInput (1080p pictures at 30 fps + i16 audio) -> VideoMixer -> Monitor, + cfg2 32-module audio graph -> Monitor.Audio",
+           "timing": "host wall clock around K pipelined steps incl. pinned-host copies, synchronised both sides, max over ranks"}
+    ss.close()
+    return out
+
+
 def b200_arm(args):
     import mixlab_b200 as mxl
     from mixlab_b200 import workloads as W
@@ -672,6 +766,9 @@ def b200_arm(args):
                "h2d_gbs": h2d_step * Ke / dt_max / 1e9, "d2h_gbs": d2h_step * Ke / dt_max / 1e9,
                "bound": "pcie" if sess.video else "launch", "pcie_h2d_ceiling_gbs": pcie_ceiling(),
                "timing": "host wall clock around K steps incl. pinned-host copies, synchronised both sides, max over ranks"}
+    e2e_session = None
+    if not args.no_e2e and args.workload == "av":
+        e2e_session = e2e_session_leg(mxl, ctx, dist, args, T, args.e2e_steps or K)
     clocks = sampler.stop()
 
     shared = shared_source_check(mxl, ctx, dist) if dist.world > 1 else None
@@ -698,7 +795,7 @@ def b200_arm(args):
                        "l2": l2_note},
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"]},
-            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e, "e2e_session": e2e_session, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "stereo_frames_per_s": value * SPT if args.workload != "video" else None,
             "video_fps": value if args.workload != "audio" else None,
             "whole_step_gbs": whole, "whole_step_frac": whole / peak,

@@ -160,6 +160,11 @@ MXL_API int mxl_ctx_device_memory(mxl_ctx *ctx, uint64_t *free_bytes, uint64_t *
 typedef struct mxl_kernel_time { char name[48]; uint32_t launches; float total_ms; } mxl_kernel_time;
 MXL_API int mxl_ctx_set_kernel_timing(mxl_ctx *ctx, int enabled);
 MXL_API int mxl_ctx_kernel_times(mxl_ctx *ctx, mxl_kernel_time *out, uint32_t cap);
+/* Diagnostics of the fused voice kernel: with max_ctas > 0 every later launch of at most that many CTAs records 8 SM-clock
+ * stamps per CTA (start, table copies issued, samples generated, scanned, filtered, stored; two spare).  The call first
+ * copies the stamps of the LAST such launch to stamps_out (8 per CTA, voice-major; returns the CTA count), then applies
+ * max_ctas (0 = off).  Synchronises. */
+MXL_API int mxl_ctx_fused_profile(mxl_ctx *ctx, uint32_t max_ctas, uint64_t *stamps_out, uint32_t cap_ctas);
 MXL_API const char *mxl_last_error(void);
 MXL_API const char *mxl_version(void);
 /* Decibel::to_linear, protocol/src/lib.rs:469-471 (host scalar; exposed for tests) */
@@ -424,6 +429,15 @@ MXL_API int mxl_video_compose_rgba(mxl_ctx *ctx, mxl_frame *const *a, mxl_frame 
 /* yuv420p -> RGBA8 of n frames of one size, one launch (the compose path with a single layer). */
 MXL_API int mxl_frames_to_rgba(mxl_ctx *ctx, mxl_frame *const *frames, uint32_t n, mxl_rgba *out,
                                uint32_t first_picture);
+
+/* The other direction (north_star "YUV<->RGB"; NEW, self-specified like the conversion above -- the reference keeps
+ * everything yuv420p, video_mixer.rs:282-283): RGBA8 pictures -> yuv420p frames of the same size, BT.601 limited range,
+ * Y per pixel, U / V from the rounded mean colour of each 2x2 block (an odd edge repeats its last column / row), alpha
+ * ignored; one launch for n pictures.  Exact integer definition: oracle/mixlab_oracle.h (orc_rgba_to_yuv420p).  What an
+ * RGB source (a screen capture, a rendered title) needs before it can enter VideoMixer.  Stride padding of the frames
+ * is left untouched. */
+MXL_API int mxl_rgba_upload(mxl_rgba *pics, uint32_t first, uint32_t count, const uint8_t *host);
+MXL_API int mxl_rgba_to_frames(mxl_ctx *ctx, const mxl_rgba *pics, uint32_t first_picture, uint32_t n, mxl_frame *const *frames);
 
 /* ---- optional shared-source mode (NEW: no reference counterpart; one receiver per mountpoint there,
  * src/source.rs:93-95).  Sessions on different GPUs share nothing on the tick path; when several graphs fan

@@ -174,6 +174,7 @@ def lib():
         "mxl_ctx_device_memory": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
         "mxl_ctx_set_kernel_timing": (i32, [vp, i32]),
         "mxl_ctx_kernel_times": (i32, [vp, C.POINTER(KernelTime), u32]),
+        "mxl_ctx_fused_profile": (i32, [vp, u32, vp, u32]),
         "mxl_last_error": (C.c_char_p, []),
         "mxl_version": (C.c_char_p, []),
         "mxl_db_to_linear": (dbl, [dbl]),
@@ -258,6 +259,8 @@ def lib():
         "mxl_rgba_download_async": (i32, [vp, u32, u32, vp]),
         "mxl_video_compose_rgba": (i32, [vp, C.POINTER(vp), C.POINTER(vp), u32, dbl, vp, u32]),
         "mxl_frames_to_rgba": (i32, [vp, C.POINTER(vp), u32, vp, u32]),
+        "mxl_rgba_upload": (i32, [vp, u32, u32, vp]),
+        "mxl_rgba_to_frames": (i32, [vp, vp, u32, u32, C.POINTER(vp)]),
         "mxl_comm_unique_id": (i32, [vp]),
         "mxl_ctx_comm_init": (i32, [vp, vp, i32, i32]),
         "mxl_ctx_comm_destroy": (i32, [vp]),
@@ -419,6 +422,12 @@ class Context:
         check(lib().mxl_ctx_timer_elapsed_ms(self.h, C.byref(ms)))
         return ms.value
 
+    def fused_profile(self, max_ctas, read=True):
+        """mxl_ctx_fused_profile: (n_ctas, 8) SM-clock stamps of the last fused_voice_kernel launch; then re-arms for max_ctas."""
+        buf = np.zeros((8192, 8), np.uint64)
+        n = check(lib().mxl_ctx_fused_profile(self.h, max_ctas, _ptr(buf) if read else None, buf.shape[0]))
+        return buf[:n]
+
     def flush_l2(self):
         check(lib().mxl_ctx_flush_l2(self.h))
 
@@ -568,6 +577,17 @@ class RgbaPictures:
         out = np.empty(count * self.picture_bytes, np.uint8)
         check(lib().mxl_rgba_download(self.h, first, count, _ptr(out)))
         return out.reshape(count, self.picture_bytes)
+
+    def upload(self, data, first=0):
+        data = np.ascontiguousarray(data, np.uint8)
+        count = data.size // self.picture_bytes
+        check(lib().mxl_rgba_upload(self.h, first, count, _ptr(data)))
+
+    def to_frames(self, frames, first=0):
+        """RGBA8 -> yuv420p into existing frames of the pictures' size (mxl_rgba_to_frames), one launch."""
+        n = len(frames)
+        arr = (C.c_void_p * n)(*[f.h for f in frames])
+        check(lib().mxl_rgba_to_frames(self.ctx.h, self.h, first, n, arr))
 
     def download_async(self, host_ptr, first=0, count=None):
         count = self.n - first if count is None else count

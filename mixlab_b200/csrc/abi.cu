@@ -5,6 +5,7 @@
 #include <algorithm>
 
 #include "modules.h"
+#include "kernels.h"
 
 using namespace mxl;
 
@@ -50,6 +51,7 @@ int mxl_module_update(mxl_module* m, int kind, const void* params)
     // module.rs:104-110: a ModuleParams variant of another module panics
     if (kind != m->kind) MXL_FAIL(MXL_ERR_PARAMS, "module params mismatch! module = %s, params kind = %d", m->kind_name(), kind);
     if (kind_has_params(kind) && !params) MXL_FAIL(MXL_ERR_PARAMS, "%s: NULL params", m->kind_name());
+    if (m->ctx) m->ctx->change_epoch++;
     return m->update(params);
 }
 
@@ -438,6 +440,70 @@ int mxl_video_compose_rgba(mxl_ctx* ctx, mxl_frame* const* a, mxl_frame* const* 
 {
     if (n && !b) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
     return compose_rgba(ctx, a, b, n, mxl_fader_to_u8(fader), out, first_picture);      // video_mixer.rs:168
+}
+
+int mxl_ctx_fused_profile(mxl_ctx* ctx, uint32_t max_ctas, uint64_t* stamps_out, uint32_t cap_ctas)
+{
+    if (!ctx || !ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "no CUDA device bound to this context");
+    MXL_TRY(ctx->activate());
+    MXL_CUDA(cudaStreamSynchronize(ctx->stream));
+    int n = 0;
+    if (stamps_out && ctx->fused_prof) {
+        n = (int)std::min(ctx->fused_prof_ctas, cap_ctas);
+        MXL_CUDA(cudaMemcpy(stamps_out, ctx->fused_prof, (size_t)n * k::kFusedProfStamps * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    }
+    if (max_ctas != ctx->fused_prof_cap) {
+        if (ctx->fused_prof) { cudaFree(ctx->fused_prof); ctx->fused_prof = nullptr; }
+        ctx->fused_prof_cap = 0;
+        if (max_ctas) {
+            MXL_CUDA(cudaMalloc(&ctx->fused_prof, (size_t)max_ctas * k::kFusedProfStamps * sizeof(uint64_t)));
+            ctx->fused_prof_cap = max_ctas;
+        }
+        ctx->fused_prof_ctas = 0;
+    }
+    return n;
+}
+
+int mxl_rgba_upload(mxl_rgba* pics, uint32_t first, uint32_t count, const uint8_t* host)
+{
+    if (!pics || !host) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
+    if ((uint64_t)first + count > pics->n) MXL_FAIL(MXL_ERR_LENGTH, "pictures %u..%u of %u", first, first + count, pics->n);
+    mxl_ctx* ctx = pics->ctx;
+    MXL_TRY(ctx->activate());
+    const size_t bytes = pics->picture_bytes() * count;
+    MXL_CUDA(cudaMemcpyAsync(pics->dev + pics->picture_bytes() * first, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += bytes;
+    return mxl_ctx_synchronize(ctx);
+}
+
+int mxl_rgba_to_frames(mxl_ctx* ctx, const mxl_rgba* pics, uint32_t first_picture, uint32_t n, mxl_frame* const* frames)
+{
+    if (!ctx || !pics || (n && !frames)) MXL_FAIL(MXL_ERR_INVALID, "NULL argument");
+    if (!ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "mxl_rgba_to_frames: context has no CUDA device; there is no CPU fallback");
+    if (pics->ctx != ctx) MXL_FAIL(MXL_ERR_INVALID, "mxl_rgba_to_frames: pictures belong to another context");
+    if ((uint64_t)first_picture + n > pics->n) MXL_FAIL(MXL_ERR_LENGTH, "pictures %u..%u of %u", first_picture, first_picture + n, pics->n);
+    if (n == 0) return MXL_OK;
+    mxl_frame_layout lay;
+    frame_layout_yuv420p(pics->width, pics->height, &lay);
+    std::vector<k::RgbaToYuvJob> jobs(n);
+    for (uint32_t i = 0; i < n; i++) {
+        const mxl_frame* f = frames[i];
+        if (!f || f->ctx != ctx || f->layout.width != pics->width || f->layout.height != pics->height)
+            MXL_FAIL(MXL_ERR_INVALID, "mxl_rgba_to_frames: frame %u is NULL, of another context or not %ux%u", i, pics->width, pics->height);
+        jobs[i] = k::RgbaToYuvJob{pics->dev + pics->picture_bytes() * (first_picture + i), f->dev};
+    }
+    MXL_TRY(ctx->activate());
+    mxl_rgba* p = const_cast<mxl_rgba*>(pics);              // the job staging buffer rides on the picture set
+    if (p->jobs_cap * sizeof(k::ComposeRgbaJob) < n * sizeof(k::RgbaToYuvJob)) {
+        if (p->jobs) { MXL_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(p->jobs); p->jobs = nullptr; }
+        MXL_CUDA(cudaMalloc(&p->jobs, (size_t)n * 2 * sizeof(k::ComposeRgbaJob)));
+        p->jobs_cap = (size_t)n * 2;
+    }
+    MXL_TRY(ctx->compute_begin());
+    MXL_CUDA(cudaMemcpyAsync(p->jobs, jobs.data(), n * sizeof(k::RgbaToYuvJob), cudaMemcpyHostToDevice, ctx->stream));
+    const int st = k::launch_rgba_to_yuv(ctx, lay, (const k::RgbaToYuvJob*)p->jobs, n);
+    MXL_TRY(ctx->compute_end());
+    return st;
 }
 
 int mxl_frames_to_rgba(mxl_ctx* ctx, mxl_frame* const* frames, uint32_t n, mxl_rgba* out, uint32_t first_picture)

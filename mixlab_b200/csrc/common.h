@@ -65,6 +65,8 @@ struct mxl_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     uint64_t launches = 0;
+    uint64_t change_epoch = 1;        // bumped by whatever may invalidate cached launch parameters: a module update, a line
+                                      // (re)allocation, a new graph plan
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
@@ -95,6 +97,8 @@ struct mxl_ctx {
     std::vector<cudaEvent_t> kernel_event_pool;
     uint32_t env_epoch = 0;           // Envelope launches so far (tags the look-back flags of a launch)
     std::map<uint32_t, void*> eq_stream_tables;   // device copies of EqStreamPlan::lane_pow by chunk length
+    unsigned long long* fused_prof = nullptr;     // diagnostics: per-CTA phase clocks of the last fused voice launch (mxl_ctx_fused_profile)
+    uint32_t fused_prof_ctas = 0, fused_prof_cap = 0;
     std::map<uint32_t, int> fused_clusters;       // (chunk << 8 | voices) -> resident clusters of the fused voice kernel (0 = cannot launch)
 
     // Copy/compute overlap (mxl_ctx_set_copy_overlap): async uploads go to stream_in, async downloads

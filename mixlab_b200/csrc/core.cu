@@ -142,6 +142,7 @@ int line_resize(mxl_line* l, uint64_t frames)
     if (frames <= l->capacity) { l->frames = frames; return MXL_OK; }
     MXL_TRY(l->ctx->activate());
     // cudaFree synchronises the device; lines only grow between runs.
+    l->ctx->change_epoch++;
     if (l->dev) { MXL_CUDA(cudaFree(l->dev)); l->dev = nullptr; }
     l->frames = frames;
     l->capacity = frames;
@@ -407,6 +408,7 @@ int mxl_ctx_destroy(mxl_ctx* ctx)
         for (auto& kv : ctx->eq_stream_tables) if (kv.second) cudaFree(kv.second);
         for (auto& kv : ctx->scale_tables) if (kv.second) cudaFree(kv.second);
         if (ctx->scale_jobs) cudaFree(ctx->scale_jobs);
+        if (ctx->fused_prof) cudaFree(ctx->fused_prof);
         if (ctx->pcm_ring) cudaFree(ctx->pcm_ring);
         for (auto& kv : ctx->frame_pool)
             for (uint8_t* p : kv.second) cudaFree(p);

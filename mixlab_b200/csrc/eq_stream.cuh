@@ -36,6 +36,19 @@ __device__ __forceinline__ void load_tables(const EqDevTables* __restrict__ g, E
     if (tid < 8) s->K[tid] = g->K[tid];
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src);
+
+// The same with 16-byte cp.async copies (every table is a multiple of 16 bytes and 16-byte aligned in both structs):
+// the caller overlaps them with work that does not need the tables, then cp.async.wait_all + __syncthreads.
+template <int LC>
+__device__ __forceinline__ void load_tables_async(const EqDevTables* __restrict__ g, EqShared<LC>* s, int tid)
+{
+    for (int i = tid; i < LC * 4; i += kT) cp_async16(&s->V[0][0] + 2 * i, &g->V[0][0] + 2 * i);
+    for (int i = tid; i < 10 * 32; i += kT) cp_async16(s->lane_pow + 2 * i, &g->lane_pow[0][0][0] + 2 * i);
+    for (int i = tid; i < 80; i += kT) cp_async16(&s->pow_lo[0][0] + 2 * i, &g->pow_lo[0][0] + 2 * i);   // pow_lo and pow_hi are adjacent in both
+    if (tid < 4) cp_async16(s->K + 2 * tid, g->K + 2 * tid);
+}
+
 __device__ __forceinline__ int tri(int r, int c) { return r * (r + 1) / 2 + c; }
 
 __device__ __forceinline__ void tri_apply(const double* A, const double x[4], double y[4])

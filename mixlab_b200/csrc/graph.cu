@@ -43,6 +43,7 @@ struct mxl_graph {
     std::set<int> fusion_veto;                                         // mixers whose group's parameters left the fused kernel's domain
     std::vector<FusedGroup> fused;
     uint64_t runs_since_plan = 0;
+    uint64_t checked_epoch = 0;                                        // ctx->change_epoch the per-run validity checks last saw
     std::vector<mxl_line*> resize_list;                                // lines a run sizes to the call: every output the plan writes
     float last_call_host_us = 0.f;                                     // host time of the last run_ticks call
     uint32_t last_call_ticks = 0;
@@ -271,6 +272,7 @@ int build_plan(mxl_graph* g)
     for (int id : g->run_order)
         for (size_t o = 0; o < g->out_lines[id].size(); o++)
             if (!g->hidden.count({id, (uint32_t)o})) g->resize_list.push_back(g->out_lines[id][o]);
+    g->ctx->change_epoch++;
     g->dirty = false;
     g->timings_pending = false;
     g->runs_since_plan = 0;
@@ -390,16 +392,19 @@ int mxl_graph_run_ticks(mxl_graph* g, uint64_t tick0, uint32_t n_ticks)
         ~CallTimer() { g->last_call_host_us = std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - t0).count(); g->last_call_ticks = ticks; }
     } call_timer{g, call_t0, n_ticks};
     MXL_TRY(ctx->activate());
-    // a module whose params changed its terminals (Mixer::update re-creates itself, mixer.rs:40-44)
-    for (size_t id = 0; id < g->modules.size() && !g->dirty; id++) {
-        mxl_module* m = g->modules[id];
-        if (m && !is_source(m->kind) && g->position.size() > id && g->position[id] >= 0 && g->out_lines[id].size() != m->outputs.size()) g->dirty = true;
-        if (m && g->resolved.size() > id && g->position[id] >= 0 && g->resolved[id].size() != m->inputs.size()) g->dirty = true;
+    if (g->checked_epoch != ctx->change_epoch) {                       // (nothing was updated, resized or re-planned since: skip)
+        // a module whose params changed its terminals (Mixer::update re-creates itself, mixer.rs:40-44)
+        for (size_t id = 0; id < g->modules.size() && !g->dirty; id++) {
+            mxl_module* m = g->modules[id];
+            if (m && !is_source(m->kind) && g->position.size() > id && g->position[id] >= 0 && g->out_lines[id].size() != m->outputs.size()) g->dirty = true;
+            if (m && g->resolved.size() > id && g->position[id] >= 0 && g->resolved[id].size() != m->inputs.size()) g->dirty = true;
+        }
+        // a fused group whose parameters left the fused kernel's domain (update() since the plan) goes back to stages
+        for (const FusedGroup& fg : g->fused)
+            if (!g->dirty && !fused_group_params_ok(fg)) { g->fusion_veto.insert(fg.members[0]); g->dirty = true; }
     }
-    // a fused group whose parameters left the fused kernel's domain (update() since the plan) goes back to stages
-    for (const FusedGroup& fg : g->fused)
-        if (!g->dirty && !fused_group_params_ok(fg)) { g->fusion_veto.insert(fg.members[0]); g->dirty = true; }
     if (g->dirty) MXL_TRY(build_plan(g));
+    g->checked_epoch = ctx->change_epoch;
     collect_timings(g);
     g->runs_since_plan++;
 

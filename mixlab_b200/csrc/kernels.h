@@ -124,46 +124,59 @@ struct EqStreamBatch {
 };
 int launch_eq_stream(mxl_ctx* ctx, const EqStreamBatch& b);
 
-// ---- Fused voice group: Oscillator -> EqThree -> StereoPanner -> Mixer [-> Meter] in ONE launch (fused_voice.cu) ----
-// The graph executor (graph.cu) replaces the five stages of such a sub-graph by this launch.  A "voice" is an
-// Oscillator feeding an EqThree; a mixer channel takes a StereoPanner whose sides are voices (or disconnected).
-// Grid (time tiles, voices), one thread-block cluster per time tile (a CTA per voice): every CTA generates its
-// voice's samples straight into the EqThree tile, filters them (the eq_stream scheme), stores the EqThree line;
-// after the cluster barrier the CTAs share the tile's mixer sum (channel order kept) and the meter records.
+// ---- Fused voice group: Oscillator -> EqThree -> StereoPanner -> Mixer [-> Meter] in TWO launches (fused_voice.cu) ----
+// The graph executor (graph.cu) replaces the five stages of such a sub-graph.  A "voice" is an Oscillator feeding an
+// EqThree; a mixer channel takes a StereoPanner whose sides are voices (or disconnected).
+//   fused_voice_kernel   grid (time tiles, voices): a CTA generates its voice's samples straight into the EqThree tile
+//                        (the oscillator line never exists), filters them (the eq_stream scheme), stores the EqThree line
+//                        and the voice's mixer PRODUCTS (f64(y) * gain) as f32, one line per distinct channel gain;
+//   fused_mix_kernel     a CTA per tick: adds the channels' products IN CHANNEL ORDER (mixer.rs:57-68) -- the panner's
+//                        interleave is the addressing of that walk -- writes master and cue and reduces the tick to its
+//                        meter record in meter_warp_kernel's order.  Launched behind the first with programmatic
+//                        dependent launch; its inputs are L2-resident.
 struct MeterRecord;
-constexpr int kFusedMaxVoices = 16;  // = the largest thread-block cluster of sm_100 (non-portable size)
+constexpr int kFusedMaxVoices = 16;    // (a voice is 128 bytes of kernel parameters; launches get slower with their size)
 constexpr int kFusedMaxChans = 64;
+constexpr int kFusedMaxProducts = 2;   // distinct channel gains one voice is multiplied by (more: the group stays staged)
 struct FusedVoice {
-    double freq; int32_t waveform; int32_t _pad;   // Oscillator params (waveform Off = EqThree input disconnected)
+    double freq; int32_t waveform; int32_t n_products;   // Oscillator params (waveform Off = EqThree input disconnected)
     const double* state; double* state_out;        // EqThree state: lo poles[4], hi poles[4], history[3]; double-buffered
     double g_lo, g_mid, g_hi;
-    float* eq_out;                                 // EqThree output line: always written (the mix phase reads it)
+    float* eq_out;                                 // EqThree output line: always written (cue bus and observers read it)
     float* osc_mono; float* osc_stereo;            // Oscillator output lines: written only when something observes them
+    double product_gain[kFusedMaxProducts];        // fader * 10^(gain_dB / 20) of the channels this voice feeds (mixer.rs:59)
+    float* product_out[kFusedMaxProducts];         // scratch lines: (f64(y) * gain) as f32 (mixer.rs:62)
 };
-struct FusedChan {
-    const float* left; const float* right;         // EqThree lines feeding the panner's L / R; nullptr = disconnected
-    float* pan_out;                                // StereoPanner output line: written only when observed
-    double gain;                                   // fader * 10^(gain_dB / 20) (mixer.rs:59)
-    int32_t cue; int32_t _pad;
-};
-struct FusedBatch {
+struct FusedVoiceBatch {
     uint64_t t0, frames;
     double sample_rate, inv_sample_rate;
     uint32_t n_chunks;
-    uint32_t owned;                                // chunks a tile owns (<= 256 - halo; tick-aligned when the meter is fused)
-    int32_t n_voices, n_channels;
-    float* master; float* cue;
-    MeterRecord* meter;                            // nullptr = no fused meter
-    uint32_t spt, _pad;
+    uint32_t owned;                                // chunks a tile owns (256 - halo)
+    int32_t n_voices, _pad;
+    unsigned long long* prof;                      // diagnostics: kFusedProfStamps clock64 stamps per CTA, or nullptr
     EqStreamConsts eq;
     FusedVoice voice[kFusedMaxVoices];
-    FusedChan chan[kFusedMaxChans];
 };
-// chunks per tile for this plan; *meter_ok = the tile can be made a whole number of ticks of `spt` frames
-uint32_t fused_owned_chunks(const EqStreamConsts& eq, uint32_t spt, bool* meter_ok);
-// > 0 when a cluster of n_voices CTAs of this kernel can be resident (cudaOccupancyMaxActiveClusters)
-int fused_voice_mix_supported(mxl_ctx* ctx, uint32_t chunk, int n_voices);
-int launch_fused_voice_mix(mxl_ctx* ctx, const FusedBatch& b);
+struct FusedChan {
+    const float* left; const float* right;         // product lines of the voices feeding the panner's L / R; nullptr = disconnected
+    const float* left_raw; const float* right_raw; // their EqThree lines, set only when the cue bus or an observed panner line needs them
+    float* pan_out;                                // StereoPanner output line: written only when observed
+    float zero_product;                            // (f64(0.0) * gain) as f32: what a disconnected side adds (+-0, NaN for a non-finite gain)
+    int32_t cue;
+};
+struct FusedMixBatch {
+    uint64_t frames;
+    uint32_t spt;                                  // frames per CTA: a tick when the meter rides along, else any even number
+    int16_t n_channels;
+    int16_t mono;                                  // every channel's panner takes the same voice on both sides (or none)
+    float* master; float* cue;
+    MeterRecord* meter;                            // nullptr = no meter in the group
+    const FusedChan* chan;                         // device: [n_channels] (uploaded when it changes; as kernel parameters the
+                                                   // table cost a constant-bank miss per 64-byte line at the head of every CTA)
+};
+int launch_fused_voice(mxl_ctx* ctx, FusedVoiceBatch& b);
+int launch_fused_mix(mxl_ctx* ctx, const FusedMixBatch& b);
+constexpr int kFusedProfStamps = 8;
 
 // ---- Envelope (src/module/envelope.rs:91-120) ----
 struct EnvState { int32_t state; int32_t _pad; uint64_t seq; double off_amplitude; };
@@ -248,6 +261,10 @@ uint32_t scale_tile_width();
 // Crossfade + yuv420p -> RGBA8 in one pass
 struct ComposeRgbaJob { const uint8_t* a; const uint8_t* b; uint8_t* rgba; uint32_t fade; uint32_t _pad; };
 int launch_compose_rgba(mxl_ctx* ctx, const mxl_frame_layout& lay, const ComposeRgbaJob* jobs_dev, uint32_t n_jobs);
+
+// RGBA8 -> yuv420p (new, self-specified BT.601 integer form: oracle/mixlab_oracle.h orc_rgba_to_yuv420p)
+struct RgbaToYuvJob { const uint8_t* rgba; uint8_t* yuv; };
+int launch_rgba_to_yuv(mxl_ctx* ctx, const mxl_frame_layout& lay, const RgbaToYuvJob* jobs_dev, uint32_t n_jobs);
 
 // L2 flush helper
 int launch_fill_bytes(mxl_ctx* ctx, void* dst, size_t bytes, uint8_t value);

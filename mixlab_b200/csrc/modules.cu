@@ -122,6 +122,14 @@ struct Mixer : mxl_module {                           // src/module/mixer.rs
     std::vector<mxl_mixer_channel_params> channels;
     std::vector<double> channel_gain;                 // fader * gain.to_linear() (mixer.rs:59), formed when the params arrive:
                                                       // the reference recomputes the same product (a powf) every tick
+    DevBuf fused_products;                            // fused voice group: the channels' product lines (scratch, one per voice and gain)
+    DevBuf fused_chan;                                // ... and the mix kernel's channel table on the device,
+    std::vector<k::FusedChan> fused_chan_host;        //     uploaded when it differs from this copy
+    // launch parameters of the group's last run: rebuilt only when something that feeds them changed (ctx->change_epoch,
+    // the call length); a steady-state call patches t0 and the EqThree state pointers and launches
+    struct FusedCache { uint64_t epoch = 0, frames = 0; const void* group = nullptr; k::FusedVoiceBatch vb; k::FusedMixBatch mb; };
+    FusedCache* fused_cache = nullptr;
+    ~Mixer() override { fused_products.release(ctx); fused_chan.release(ctx); delete fused_cache; }
     Mixer(const mxl_mixer_params* in)
     {
         kind = MXL_MOD_MIXER;
@@ -1061,14 +1069,12 @@ static int run_meters(mxl_ctx* ctx, mxl_module* const* mods, int n, const IoSet*
 // ================================================================================================
 bool fused_meter_supported(mxl_ctx* ctx)
 {
-    const mxl::EqStreamPlan* p32 = eq_stream_plan_for(ctx, 32);
-    if (!p32) return false;
-    k::EqStreamConsts q{};
-    q.chunk = p32->lc; q.halo = p32->halo;
-    bool ok = false;
-    k::fused_owned_chunks(q, ctx->spt, &ok);
-    return ok;
+    // the mix kernel gives a tick to one CTA: frame pairs must not straddle ticks, and the tick's master samples sit in
+    // its shared memory for the meter warp
+    return ctx->spt > 0 && (ctx->spt & 1u) == 0 && (size_t)(ctx->spt / 2 + 1) * 16 + (size_t)k::kFusedMaxChans * sizeof(k::FusedChan) <= 48 * 1024;
 }
+
+static int fused_max_products(const FusedGroup& g);
 
 bool fused_group_params_ok(const FusedGroup& g)
 {
@@ -1079,7 +1085,31 @@ bool fused_group_params_ok(const FusedGroup& g)
         // keep for ever (the staged EqThree kernel carries that case; the fused one does not)
         if (!(fabs(o->p.freq) <= 1e12)) return false;
     }
-    return g.mixer && ((const Mixer*)g.mixer)->channels.size() == g.chans.size();
+    if (!g.mixer || ((const Mixer*)g.mixer)->channels.size() != g.chans.size()) return false;
+    if (fused_max_products(g) < 0) return false;            // a voice multiplied by too many distinct channel gains
+    return true;
+}
+
+// largest number of distinct channel gains any voice of the group is multiplied by (= product tiles per CTA); -1 = too many
+static int fused_max_products(const FusedGroup& g)
+{
+    const Mixer* mx = (const Mixer*)g.mixer;
+    int most = 0;
+    for (size_t v = 0; v < g.voices.size(); v++) {
+        double seen[k::kFusedMaxProducts];
+        int n = 0;
+        for (size_t c = 0; c < g.chans.size(); c++)
+            for (int side : {g.chans[c].left, g.chans[c].right}) {
+                if (side != (int)v) continue;
+                bool found = false;
+                for (int i = 0; i < n; i++) found = found || memcmp(&seen[i], &mx->channel_gain[c], sizeof(double)) == 0;
+                if (found) continue;
+                if (n == k::kFusedMaxProducts) return -1;
+                seen[n++] = mx->channel_gain[c];
+            }
+        most = std::max(most, n);
+    }
+    return most;
 }
 
 bool fused_group_supported(mxl_ctx* ctx, const FusedGroup& g)
@@ -1088,64 +1118,74 @@ bool fused_group_supported(mxl_ctx* ctx, const FusedGroup& g)
         g.chans.empty() || g.chans.size() > (size_t)k::kFusedMaxChans)
         return false;
     if (!fused_group_params_ok(g)) return false;
-    if (!eq_stream_plan_for(ctx, 32)) return false;         // sample rate outside what the time-parallel scheme handles
-    return k::fused_voice_mix_supported(ctx, 32, (int)g.voices.size()) > 0;
+    return eq_stream_plan_for(ctx, 32) != nullptr;          // else: a sample rate the time-parallel scheme does not handle
 }
+
+static int fused_bytes(const FusedGroup& g, uint64_t frames, uint64_t* bytes);
 
 int run_fused_group(mxl_ctx* ctx, const FusedGroup& g, uint64_t t, uint64_t* bytes)
 {
     if (bytes) *bytes = 0;
+    {   // steady state: same plan, same lines, same parameters, same call length as the last run
+        Mixer* mxc = (Mixer*)g.mixer;
+        Mixer::FusedCache* fc = mxc ? mxc->fused_cache : nullptr;
+        if (fc && fc->epoch == ctx->change_epoch && fc->group == (const void*)&g && g.master && fc->frames == g.master->frames && fc->frames) {
+            if (t + fc->frames + (1ull << 20) >= (1ull << 53)) MXL_FAIL(MXL_ERR_LENGTH, "fused voice group: sample index beyond 2^53");
+            fc->vb.t0 = t;
+            for (int i = 0; i < fc->vb.n_voices; i++) {
+                EqThree* e = (EqThree*)g.voices[i].eq;
+                fc->vb.voice[i].state = e->state_ptr(e->cur);
+                fc->vb.voice[i].state_out = e->state_ptr(e->cur ^ 1);
+            }
+            if (bytes) fused_bytes(g, fc->frames, bytes);
+            MXL_TRY(k::launch_fused_voice(ctx, fc->vb));
+            for (int i = 0; i < fc->vb.n_voices; i++) ((EqThree*)g.voices[i].eq)->cur ^= 1;
+            return k::launch_fused_mix(ctx, fc->mb);
+        }
+    }
     MXL_TRY(expect_output(g.master, MXL_LINE_STEREO, "Mixer.Master"));
     MXL_TRY(expect_output(g.cue, MXL_LINE_STEREO, "Mixer.Cue"));
     const uint64_t frames = g.master->frames;
     if (frames == 0) return MXL_OK;
     MXL_TRY(need_len(g.cue, 2 * frames, "Mixer.Cue"));
     if (t + frames + (1ull << 20) >= (1ull << 53)) MXL_FAIL(MXL_ERR_LENGTH, "fused voice group: sample index beyond 2^53");
-    const Mixer* mx = (const Mixer*)g.mixer;
+    Mixer* mx = (Mixer*)g.mixer;
     if (mx->channels.size() != g.chans.size()) MXL_FAIL(MXL_ERR_INVALID, "fused voice group: mixer has %zu channels, the plan %zu", mx->channels.size(), g.chans.size());
-
-    // chunk length: 64 samples once that still gives every SM two CTAs, else 32
+    if (fused_max_products(g) < 0) MXL_FAIL(MXL_ERR_INVALID, "fused voice group: a voice is multiplied by more than %d gains", k::kFusedMaxProducts);
     const int nv = (int)g.voices.size();
+
+    // Chunk length of the voice kernel.  A thread walks its chunk serially, so the chunk sets the latency of a CTA, while
+    // the halo (the ~1100 samples a tile recomputes ahead of its own) and the scan cost the same per tile whatever the
+    // chunk: 32 samples by default; 16 while the call is so short that 32 would leave SMs without a CTA; 64 for long
+    // calls (half the tiles, half the halo work) once that still fills the machine several CTAs deep.
+    const uint64_t sms = (uint64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148);
+    auto tiles_for = [&](const mxl::EqStreamPlan* pl) -> uint64_t {
+        const uint64_t own = k::kEqStreamThreads - pl->halo;
+        return ((frames + pl->lc - 1) / pl->lc + own - 1) / own;
+    };
     const mxl::EqStreamPlan* plan = eq_stream_plan_for(ctx, 32);
     if (!plan) MXL_FAIL(MXL_ERR_UNSUPPORTED, "fused voice group: no EqThree plan at %u Hz", ctx->sample_rate);
-    uint32_t forced = 0;
-    if (const char* e = getenv("MXL_FUSED_CHUNK")) forced = (uint32_t)atol(e);
-    if (forced != 32) {
-        if (const mxl::EqStreamPlan* p64 = eq_stream_plan_for(ctx, 64)) {
-            const uint64_t own64 = k::kEqStreamThreads - p64->halo;
-            const uint64_t tiles64 = ((frames + 63) / 64 + own64 - 1) / own64;
-            const uint64_t sms = (uint64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148);
-            if ((forced == 64 || tiles64 * nv >= 2 * sms) && k::fused_voice_mix_supported(ctx, 64, nv) > 0) plan = p64;
-        }
-    }
-    k::FusedBatch b{};
-    MXL_TRY(fill_eq_consts(ctx, *plan, &b.eq));
-    b.t0 = t; b.frames = frames;
-    b.sample_rate = (double)ctx->sample_rate; b.inv_sample_rate = 1.0 / b.sample_rate;
-    b.n_chunks = (uint32_t)((frames + plan->lc - 1) / plan->lc);
-    bool meter_ok = false;
-    b.owned = k::fused_owned_chunks(b.eq, ctx->spt, &meter_ok);
-    b.n_voices = nv; b.n_channels = (int32_t)g.chans.size();
-    b.master = g.master->dev; b.cue = g.cue->dev;
-    b.spt = ctx->spt;
-    if (g.meter) {
-        if (!meter_ok) MXL_FAIL(MXL_ERR_INVALID, "fused voice group: meter folded in but ticks of %u frames do not tile", ctx->spt);
-        Meter* me = (Meter*)g.meter;
-        const uint32_t slots = (uint32_t)((frames + ctx->spt - 1) / ctx->spt);
-        MXL_TRY(me->records.ensure(ctx, (size_t)slots * sizeof(k::MeterRecord)));
-        me->n_slots = slots;
-        b.meter = (k::MeterRecord*)me->records.p;
-        if (bytes) *bytes += 8 * frames;
-    } else {
-        b.owned = k::kEqStreamThreads - plan->halo;          // no tick alignment needed
-    }
+    const char* forced_env = getenv("MXL_FUSED_CHUNK");             // tests and tuning: 16, 32 or 64
+    const uint32_t forced = forced_env ? (uint32_t)atol(forced_env) : 0u;
+    const mxl::EqStreamPlan* p16 = eq_stream_plan_for(ctx, 16);
+    const mxl::EqStreamPlan* p64 = eq_stream_plan_for(ctx, 64);
+    if (p16 && (forced == 16 || (!forced && tiles_for(plan) * nv < 2 * sms))) plan = p16;
+    else if (p64 && (forced == 64 || (!forced && tiles_for(p64) * nv >= 6 * sms))) plan = p64;
+
+    k::FusedVoiceBatch vb{};
+    MXL_TRY(fill_eq_consts(ctx, *plan, &vb.eq));
+    vb.t0 = t; vb.frames = frames;
+    vb.sample_rate = (double)ctx->sample_rate; vb.inv_sample_rate = 1.0 / vb.sample_rate;
+    vb.n_chunks = (uint32_t)((frames + plan->lc - 1) / plan->lc);
+    vb.owned = k::kEqStreamThreads - plan->halo;
+    vb.n_voices = nv;
     for (int i = 0; i < nv; i++) {
         const FusedVoiceRef& v = g.voices[i];
         EqThree* e = (EqThree*)v.eq;
         MXL_TRY(e->ensure_state());
         MXL_TRY(expect_output(v.eq_out, MXL_LINE_MONO, "EqThree"));
         MXL_TRY(need_len(v.eq_out, frames, "EqThree output"));
-        k::FusedVoice& fv = b.voice[i];
+        k::FusedVoice& fv = vb.voice[i];
         if (v.osc) {
             const Oscillator* o = (const Oscillator*)v.osc;
             fv.freq = o->p.freq; fv.waveform = o->p.waveform;
@@ -1163,19 +1203,94 @@ int run_fused_group(mxl_ctx* ctx, const FusedGroup& g, uint64_t t, uint64_t* byt
         if (v.osc_stereo) { MXL_TRY(need_len(v.osc_stereo, 2 * frames, "Oscillator.Stereo")); fv.osc_stereo = v.osc_stereo->dev; }
         if (bytes) *bytes += (v.osc ? 4 * frames : 0) + 4 * frames;
     }
+    // product lines: one per (voice, distinct channel gain), in the mixer's scratch buffer
+    const uint64_t line_floats = (frames + 3) & ~3ull;                  // 16-byte aligned lines
+    int n_lines = 0;
+    auto product_of = [&](int voice, double gain) -> int {
+        k::FusedVoice& fv = vb.voice[voice];
+        for (int i = 0; i < fv.n_products; i++)
+            if (memcmp(&fv.product_gain[i], &gain, sizeof(double)) == 0) return i;
+        fv.product_gain[fv.n_products] = gain;
+        fv.product_out[fv.n_products] = (float*)nullptr + (size_t)(n_lines++) * line_floats;   // offset for now, based below
+        return fv.n_products++;
+    };
+    std::vector<int> side_product(2 * g.chans.size(), -1);
     for (size_t c = 0; c < g.chans.size(); c++) {
         const FusedChanRef& cr = g.chans[c];
-        k::FusedChan& fc = b.chan[c];
-        fc.left = cr.left >= 0 ? b.voice[cr.left].eq_out : nullptr;
-        fc.right = cr.right >= 0 ? b.voice[cr.right].eq_out : nullptr;
+        if (cr.left >= 0) side_product[2 * c] = product_of(cr.left, mx->channel_gain[c]);
+        if (cr.right >= 0) side_product[2 * c + 1] = product_of(cr.right, mx->channel_gain[c]);
+    }
+    MXL_TRY(mx->fused_products.ensure(ctx, (size_t)std::max(n_lines, 1) * line_floats * sizeof(float)));
+    float* scratch = (float*)mx->fused_products.p;
+    for (int i = 0; i < nv; i++)
+        for (int pi = 0; pi < vb.voice[i].n_products; pi++)
+            vb.voice[i].product_out[pi] = scratch + (vb.voice[i].product_out[pi] - (float*)nullptr);
+
+    k::FusedMixBatch mb{};
+    mb.frames = frames;
+    mb.n_channels = (int16_t)g.chans.size();
+    mb.mono = 1;
+    for (const FusedChanRef& cr : g.chans) if (cr.left != cr.right) mb.mono = 0;
+    mb.master = g.master->dev; mb.cue = g.cue->dev;
+    if (g.meter) {
+        if (!fused_meter_supported(ctx)) MXL_FAIL(MXL_ERR_INVALID, "fused voice group: meter folded in but ticks of %u frames do not fit", ctx->spt);
+        Meter* me = (Meter*)g.meter;
+        const uint32_t slots = (uint32_t)((frames + ctx->spt - 1) / ctx->spt);
+        MXL_TRY(me->records.ensure(ctx, (size_t)slots * sizeof(k::MeterRecord)));
+        me->n_slots = slots;
+        mb.meter = (k::MeterRecord*)me->records.p;
+        mb.spt = ctx->spt;
+        if (bytes) *bytes += 8 * frames;
+    } else {
+        mb.spt = 1024;                                       // frames per CTA: two frame pairs per thread
+    }
+    std::vector<k::FusedChan> chan(g.chans.size());
+    for (size_t c = 0; c < g.chans.size(); c++) {
+        const FusedChanRef& cr = g.chans[c];
+        k::FusedChan& fc = chan[c];
+        memset(&fc, 0, sizeof fc);
         if (cr.pan_out) { MXL_TRY(need_len(cr.pan_out, 2 * frames, "StereoPanner output")); fc.pan_out = cr.pan_out->dev; }
-        fc.gain = mx->channel_gain[c];                       // mixer.rs:59
         fc.cue = mx->channels[c].cue ? 1 : 0;
+        const bool need_raw = fc.cue || fc.pan_out;
+        if (cr.left >= 0) { fc.left = vb.voice[cr.left].product_out[side_product[2 * c]]; if (need_raw) fc.left_raw = vb.voice[cr.left].eq_out; }
+        if (cr.right >= 0) { fc.right = vb.voice[cr.right].product_out[side_product[2 * c + 1]]; if (need_raw) fc.right_raw = vb.voice[cr.right].eq_out; }
+        fc.zero_product = (float)(0.0 * mx->channel_gain[c]);           // what a disconnected side adds (mixer.rs:62 on the zero buffer)
         if (bytes && cr.connected) *bytes += (cr.left >= 0 ? 4 * frames : 0) + (cr.right >= 0 ? 4 * frames : 0) + 8 * frames + 8 * frames;
     }
     if (bytes) *bytes += 16 * frames;
-    MXL_TRY(k::launch_fused_voice_mix(ctx, b));
+    // the channel table travels to the device only when it changed (line pointers and gains are stable call to call)
+    if (mx->fused_chan_host.size() != chan.size() || memcmp(mx->fused_chan_host.data(), chan.data(), chan.size() * sizeof(k::FusedChan)) != 0) {
+        MXL_TRY(mx->fused_chan.ensure(ctx, (size_t)k::kFusedMaxChans * sizeof(k::FusedChan)));
+        // pageable source: staged by the runtime before the call returns; ordered on the stream before the launches below
+        MXL_CUDA(cudaMemcpyAsync(mx->fused_chan.p, chan.data(), chan.size() * sizeof(k::FusedChan), cudaMemcpyHostToDevice, ctx->stream));
+        mx->fused_chan_host = chan;
+    }
+    mb.chan = (const k::FusedChan*)mx->fused_chan.p;
+    if (bytes) { *bytes = 0; fused_bytes(g, frames, bytes); }
+    if (!mx->fused_cache) mx->fused_cache = new Mixer::FusedCache();
+    // (the epoch is read after the preparations above: table uploads and scratch growth do not touch it, line growth
+    // happened before the stage ran)
+    mx->fused_cache->epoch = ctx->change_epoch;
+    mx->fused_cache->frames = frames;
+    mx->fused_cache->group = (const void*)&g;
+    mx->fused_cache->vb = vb;
+    mx->fused_cache->mb = mb;
+    MXL_TRY(k::launch_fused_voice(ctx, vb));
     for (int i = 0; i < nv; i++) ((EqThree*)g.voices[i].eq)->cur ^= 1;
+    return k::launch_fused_mix(ctx, mb);
+}
+
+// API-level line bytes of the modules the group replaces (inputs read + outputs written), as the staged
+// stages count them
+static int fused_bytes(const FusedGroup& g, uint64_t frames, uint64_t* bytes)
+{
+    uint64_t n = 0;
+    for (const FusedVoiceRef& v : g.voices) n += (v.osc ? 12 * frames : 0) + (v.osc ? 4 * frames : 0) + 4 * frames;
+    for (const FusedChanRef& cr : g.chans)
+        if (cr.connected) n += (cr.left >= 0 ? 4 * frames : 0) + (cr.right >= 0 ? 4 * frames : 0) + 8 * frames + 8 * frames;
+    n += 16 * frames;
+    if (g.meter) n += 8 * frames;
+    *bytes += n;
     return MXL_OK;
 }
 

@@ -47,5 +47,36 @@ __device__ __forceinline__ void osc_wave4(int wf, const double n[4], float s[4])
     }
 }
 
+// Eight consecutive samples: two groups of four, the sines of both groups in flight together (same operations per
+// sample as osc_wave4, so the same bits).
+__device__ __forceinline__ void osc_wave8(int wf, const double n[8], float s[8])
+{
+    if (wf == MXL_WAVE_SINE || wf == MXL_WAVE_SQUARE) {
+        double x[8], y[8];
+        bool fast = true;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            x[j] = n[j] * kTwoPi;                                  // oscillator.rs:25-27
+            const uint32_t hi = high_word(x[j]) & 0x7fffffffu;
+            fast = fast && hi < 0x42c00000u && (hi | low_word(x[j])) != 0u;
+        }
+        if (fast) {
+            sin_reduced4(x, y);
+            sin_reduced4(x + 4, y + 4);
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < 8; j++) y[j] = sin_f64(x[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) s[j] = (float)(wf == MXL_WAVE_SINE ? y[j] : sign_bit_f64(y[j]));
+    } else if (wf == MXL_WAVE_SAW) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) s[j] = (float)wave_saw(n[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) s[j] = osc_wave(n[j], wf);
+    }
+}
+
 }  // namespace k
 }  // namespace mxl

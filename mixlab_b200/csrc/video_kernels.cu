@@ -408,6 +408,75 @@ __global__ void __launch_bounds__(kVidThreads) compose_rgba_kernel(const Compose
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// RGBA8 -> yuv420p, BT.601 limited range (the reference never converts colour, video_mixer.rs:282-283: self-specified,
+// oracle = definition).  One thread = 8 pixels x 2 rows = four 2x2 blocks: two 32-byte RGBA row segments in, two 8-byte
+// luma segments + 4 U + 4 V bytes out (11.4 MB per 1080p picture: 8.3 read, 3.1 written).  Luma per pixel, chroma from the
+// block's rounded mean colour; a block cut by an odd right / bottom edge repeats its last column / row.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t luma_of(uint32_t px)
+{
+    const int r = px & 255u, g = (px >> 8) & 255u, b = (px >> 16) & 255u;
+    return (uint32_t)(((66 * r + 129 * g + 25 * b + 128) >> 8) + 16);
+}
+
+__global__ void __launch_bounds__(kVidThreads) rgba_to_yuv_kernel(const RgbaToYuvJob* __restrict__ jobs, uint32_t width, uint32_t height,
+                                                                  uint32_t ystride, uint32_t cstride, uint64_t off_u, uint64_t off_v)
+{
+    const RgbaToYuvJob job = jobs[blockIdx.z];
+    const uint32_t x0 = (blockIdx.x * kVidThreads + threadIdx.x) * 8;
+    const uint32_t cy = blockIdx.y;
+    if (x0 >= width) return;
+    const bool row1 = 2 * cy + 1 < height;
+    const uint8_t* r0 = job.rgba + ((uint64_t)(2 * cy) * width + x0) * 4;
+    const uint8_t* r1 = row1 ? r0 + (uint64_t)width * 4 : r0;          // odd height: the last row again
+    uint32_t p0[8], p1[8];
+    if (x0 + 8 <= width && (width & 3u) == 0) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(r0)), b = __ldg(reinterpret_cast<const uint4*>(r0) + 1);
+        const uint4 c = __ldg(reinterpret_cast<const uint4*>(r1)), d = __ldg(reinterpret_cast<const uint4*>(r1) + 1);
+        p0[0] = a.x; p0[1] = a.y; p0[2] = a.z; p0[3] = a.w; p0[4] = b.x; p0[5] = b.y; p0[6] = b.z; p0[7] = b.w;
+        p1[0] = c.x; p1[1] = c.y; p1[2] = c.z; p1[3] = c.w; p1[4] = d.x; p1[5] = d.y; p1[6] = d.z; p1[7] = d.w;
+    } else {
+#pragma unroll
+        for (uint32_t i = 0; i < 8; i++) {
+            const uint32_t xx = x0 + i < width ? i : width - 1 - x0;    // odd width: the last column again
+            p0[i] = __ldg(reinterpret_cast<const uint32_t*>(r0) + xx);
+            p1[i] = __ldg(reinterpret_cast<const uint32_t*>(r1) + xx);
+        }
+    }
+    uint32_t y0w[2] = {0u, 0u}, y1w[2] = {0u, 0u}, uw = 0u, vw = 0u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        y0w[i >> 2] |= luma_of(p0[i]) << (8 * (i & 3));
+        y1w[i >> 2] |= luma_of(p1[i]) << (8 * (i & 3));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t a = p0[2 * j], b = p0[2 * j + 1], c = p1[2 * j], d = p1[2 * j + 1];
+        const int r = (int)(((a & 255u) + (b & 255u) + (c & 255u) + (d & 255u) + 2u) >> 2);
+        const int g = (int)((((a >> 8) & 255u) + ((b >> 8) & 255u) + ((c >> 8) & 255u) + ((d >> 8) & 255u) + 2u) >> 2);
+        const int bl = (int)((((a >> 16) & 255u) + ((b >> 16) & 255u) + ((c >> 16) & 255u) + ((d >> 16) & 255u) + 2u) >> 2);
+        uw |= (uint32_t)(((-38 * r - 74 * g + 112 * bl + 128) >> 8) + 128) << (8 * j);
+        vw |= (uint32_t)(((112 * r - 94 * g - 18 * bl + 128) >> 8) + 128) << (8 * j);
+    }
+    uint8_t* yo = job.yuv + (uint64_t)(2 * cy) * ystride + x0;
+    uint8_t* uo = job.yuv + off_u + (uint64_t)cy * cstride + (x0 >> 1);
+    uint8_t* vo = job.yuv + off_v + (uint64_t)cy * cstride + (x0 >> 1);
+    if (x0 + 8 <= width) {
+        *reinterpret_cast<uint2*>(yo) = make_uint2(y0w[0], y0w[1]);
+        if (row1) *reinterpret_cast<uint2*>(yo + ystride) = make_uint2(y1w[0], y1w[1]);
+        *reinterpret_cast<uint32_t*>(uo) = uw;
+        *reinterpret_cast<uint32_t*>(vo) = vw;
+    } else {
+        const uint32_t n = width - x0;
+        for (uint32_t i = 0; i < n; i++) {
+            yo[i] = (uint8_t)(y0w[i >> 2] >> (8 * (i & 3)));
+            if (row1) yo[ystride + i] = (uint8_t)(y1w[i >> 2] >> (8 * (i & 3)));
+        }
+        for (uint32_t j = 0; j < (n + 1) / 2; j++) { uo[j] = (uint8_t)(uw >> (8 * j)); vo[j] = (uint8_t)(vw >> (8 * j)); }
+    }
+}
+
 int after_launch(mxl_ctx* ctx, const char* name)
 {
     cudaError_t e = cudaGetLastError();
@@ -557,6 +626,20 @@ int launch_compose_rgba(mxl_ctx* ctx, const mxl_frame_layout& lay, const Compose
     compose_rgba_kernel<<<grid, kVidThreads, 0, ctx->stream>>>(jobs_dev, lay.width, lay.height, lay.stride[0], lay.stride[1],
                                                                lay.offset[1], lay.offset[2]);
     return after_launch(ctx, "compose_rgba_kernel");
+}
+
+int launch_rgba_to_yuv(mxl_ctx* ctx, const mxl_frame_layout& lay, const RgbaToYuvJob* jobs_dev, uint32_t n_jobs)
+{
+    if (!ctx || !ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "no CUDA device bound to this context");
+    MXL_TRY(ctx->activate());
+    if (n_jobs == 0) return MXL_OK;
+    if ((lay.stride[0] & 7) || (lay.stride[1] & 3) || (lay.offset[1] & 3) || (lay.offset[2] & 3))
+        MXL_FAIL(MXL_ERR_INVALID, "rgba_to_yuv: plane strides/offsets must be 8/4-byte aligned");
+    dim3 grid(((lay.width + 7) / 8 + kVidThreads - 1) / kVidThreads, (lay.height + 1) / 2, n_jobs);
+    MXL_TIMED(ctx, "rgba_to_yuv_kernel");
+    rgba_to_yuv_kernel<<<grid, kVidThreads, 0, ctx->stream>>>(jobs_dev, lay.width, lay.height, lay.stride[0], lay.stride[1],
+                                                              lay.offset[1], lay.offset[2]);
+    return after_launch(ctx, "rgba_to_yuv_kernel");
 }
 
 }  // namespace k

@@ -432,6 +432,32 @@ void orc_yuv420p_to_rgba(const orc_frame_layout *lay, const uint8_t *yuv, uint8_
     }
 }
 
+void orc_rgba_to_yuv420p(const orc_frame_layout *lay, const uint8_t *rgba, uint8_t *yuv)
+{
+    uint8_t *yp = yuv + lay->offset[0], *up = yuv + lay->offset[1], *vp = yuv + lay->offset[2];
+    const uint32_t w = lay->width, h = lay->height;
+    for (uint32_t y = 0; y < h; y++)
+        for (uint32_t x = 0; x < w; x++) {
+            const uint8_t *px = rgba + ((size_t)y * w + x) * 4;
+            yp[(size_t)y * lay->stride[0] + x] = (uint8_t)(((66 * px[0] + 129 * px[1] + 25 * px[2] + 128) >> 8) + 16);
+        }
+    for (uint32_t cy = 0; cy < (h + 1) / 2; cy++)
+        for (uint32_t cx = 0; cx < (w + 1) / 2; cx++) {
+            int sum[3] = {0, 0, 0};
+            for (int dy = 0; dy < 2; dy++)
+                for (int dx = 0; dx < 2; dx++) {
+                    uint32_t yy = 2 * cy + dy, xx = 2 * cx + dx;
+                    if (yy >= h) yy = h - 1;                         /* an odd edge repeats its last row / column */
+                    if (xx >= w) xx = w - 1;
+                    const uint8_t *px = rgba + ((size_t)yy * w + xx) * 4;
+                    sum[0] += px[0]; sum[1] += px[1]; sum[2] += px[2];
+                }
+            const int r = (sum[0] + 2) >> 2, g = (sum[1] + 2) >> 2, b = (sum[2] + 2) >> 2;
+            up[(size_t)cy * lay->stride[1] + cx] = (uint8_t)(((-38 * r - 74 * g + 112 * b + 128) >> 8) + 128);
+            vp[(size_t)cy * lay->stride[2] + cx] = (uint8_t)(((112 * r - 94 * g - 18 * b + 128) >> 8) + 128);
+        }
+}
+
 /* Keys cubic convolution kernel, a = -0.6 */
 static double cubic_weight(double x)
 {

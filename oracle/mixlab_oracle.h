@@ -136,6 +136,15 @@ void orc_scale_geometry_yuv420p(uint32_t in_w, uint32_t in_h, uint32_t out_w, ui
  * chroma sampled nearest (x>>1, y>>1).  rgba stride = 4*width. */
 void orc_yuv420p_to_rgba(const orc_frame_layout *lay, const uint8_t *yuv, uint8_t *rgba);
 
+/* UNPINNED (the other direction; the reference never converts colour, video_mixer.rs:282-283): RGBA8 -> yuv420p,
+ * BT.601 limited range, the integer form that inverts the one above to +-2 levels:
+ *   Y = ((66*R + 129*G + 25*B + 128) >> 8) + 16            per pixel
+ *   U = ((-38*R - 74*G + 112*B + 128) >> 8) + 128          per 2x2 block, from the block's rounded mean colour
+ *   V = ((112*R - 94*G - 18*B + 128) >> 8) + 128           (mean = (sum of the block's existing pixels * (4/n) + 2) >> 2,
+ *                                                            i.e. a block cut by an odd edge repeats its last column / row)
+ * alpha is ignored; >> is an arithmetic shift.  Bytes of the frame outside the picture (stride padding) are left alone. */
+void orc_rgba_to_yuv420p(const orc_frame_layout *lay, const uint8_t *rgba, uint8_t *yuv);
+
 /* UNPINNED: bicubic (Keys a=-0.6 as swscale's SWS_BICUBIC default, 4 taps, edge clamp,
  * separable, horizontal then vertical, each pass rounded to u8 via 14-bit fixed point)
  * resample of one plane.  Stands in for the third-party sws_scale call

@@ -327,6 +327,14 @@ def yuv420p_to_rgba(lay, yuv):
     return out
 
 
+def rgba_to_yuv420p(lay, rgba, into=None):
+    """into: frame bytes whose stride padding is kept (default: a blank frame)."""
+    rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+    out = frame_blank(lay) if into is None else np.array(into, np.uint8)
+    lib().orc_rgba_to_yuv420p(C.byref(lay), _p(rgba), _p(out))
+    return out
+
+
 def bicubic_plane(src, sw, sh, sstride, dw, dh, dstride):
     src = np.ascontiguousarray(src, dtype=np.uint8)
     dst = np.zeros(dstride * dh, np.uint8)

@@ -78,13 +78,13 @@ def test_config2_fused_equals_staged(mxl, sr_spt, calls):
     assert_same_state(fs, ss)
 
 
-def test_config2_is_one_launch_per_call(mxl, ctx48):
+def test_config2_is_two_launches_per_call(mxl, ctx48):
     d = W.config2_graph()
     g, ids = W.build_graph(ctx48, d)
     g.run_ticks(0, 4)
     before = ctx48.launch_count
     g.run_ticks(4, 4)
-    assert ctx48.launch_count - before == 1
+    assert ctx48.launch_count - before == 2             # the voices, then the ordered sum + meter
     st = [s for s in g.stages() if s["n_launches"]]
     assert len(st) == 1 and st[0]["kind"] == W.STAGE_KIND["FusedVoiceMix"] and st[0]["n_modules"] == 32
     assert st[0]["algorithmic_bytes"] == 464 * 800 * 4      # reported against the unfused API bytes
@@ -244,11 +244,14 @@ def test_switching_fusion_between_calls_continues_state(mxl, ctx48):
     assert mismatch_count(np.concatenate(parts), whole) == 0
 
 
-def test_long_call_takes_64_sample_chunks(mxl, ctx48):
-    """600 ticks: enough tiles for the 64-sample chunk plan (18 ticks per tile); still bit-identical to stages."""
+@pytest.mark.parametrize("chunk", ["16", "32", "64"])
+def test_every_chunk_length_of_the_voice_kernel(mxl, ctx48, chunk, monkeypatch):
+    """The voice kernel picks 16-, 32- or 64-sample chunks by call length; each of them forced on a 300-tick call and on
+    short ones: still bit-identical to stages."""
+    monkeypatch.setenv("MXL_FUSED_CHUNK", chunk)
     d = W.config2_graph()
     taps = [d.taps["master"], d.taps["cue"]]
-    r = run_pair(mxl, ctx48, d, [600], taps, meter=d.taps["meter"][0], eqs=eq_ids(d), tick0=12345)
+    r = run_pair(mxl, ctx48, d, [300, 1, 7], taps, meter=d.taps["meter"][0], eqs=eq_ids(d), tick0=12345)
     for t in taps:
         assert mismatch_count(r[True][0][t], r[False][0][t]) == 0, t
     assert_same_meter(r[True][1], r[False][1])

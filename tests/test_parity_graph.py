@@ -222,7 +222,7 @@ def test_kernel_timing_brackets_every_launch(mxl, ctx48, fusion):
     ctx48.set_kernel_timing(False)
     assert sum(n for n, _ in times.values()) == launched
     staged = {"oscillator_kernel", "eq_stream_kernel", "panner_kernel", "mixer_kernel", "meter_kernel"}
-    assert set(times) == ({"fused_voice_mix_kernel"} if fusion else staged)
+    assert set(times) == ({"fused_voice_kernel", "fused_mix_kernel"} if fusion else staged)
     assert all(n == 2 and 0.0 < ms < 50.0 for n, ms in times.values())
     g.run_ticks(20, 8)
     assert ctx48.kernel_times() == {}                  # disabled: nothing recorded
@@ -242,8 +242,8 @@ def test_graph_stage_info_and_launch_count(mxl, ctx48):
     assert sum(s["algorithmic_bytes"] for s in stages) == 464 * 800 * 16
     assert sum(s["n_modules"] for s in stages) == 32
     assert all(s["last_ms"] >= 0 for s in stages if s["n_launches"])
-    # one launch serves all ten modules of a kind -- or, fused, the whole graph
-    assert launched == 1
+    # one launch serves all ten modules of a kind -- or, fused, two launches the whole graph
+    assert launched == 2
     g.set_fusion(False)
     before = ctx48.launch_count
     g.run_ticks(16, 16)

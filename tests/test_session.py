@@ -201,3 +201,94 @@ def test_steady_state_holds_device_memory_constant(mxl, oracle):
         free1, _ = ctx.device_memory()
         assert free1 >= free0 - (1 << 20), (free0, free1)
         sess.close()
+
+
+class VideoMixerModel:
+    """VideoMixer::run_tick (video_mixer.rs:70-250) for two channels of one picture size (no scaler involved): stored
+    frames kept until `active_until`, one composite per tick from whatever is stored."""
+
+    def __init__(self, oracle, lay, fader, sr):
+        from fractions import Fraction
+        self.o, self.lay, self.f8, self.sr, self.F = oracle, lay, oracle.fader_to_u8(fader), sr, Fraction
+        self.stored = [None, None]                       # (pixels, active_until)
+
+    def run_tick(self, t, inputs):
+        now = self.F(int(t), self.sr)
+        for c in range(2):
+            if self.stored[c] is not None and now >= self.stored[c][1]:        # 94-101
+                self.stored[c] = None
+        if all(i is None for i in inputs) and all(s is None for s in self.stored):
+            return None                                                         # 113-119
+        for c, inp in enumerate(inputs):
+            if inp is not None:
+                pix, dur, off = inp
+                self.stored[c] = (pix, now + off + dur)                         # 139-143
+        a = self.stored[0][0] if self.stored[0] else None
+        b = self.stored[1][0] if self.stored[1] else None
+        return self.o.video_crossfade(self.lay, a, b, self.f8)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T", [6, 16])
+def test_stream_session_against_the_oracle_chain(mxl, oracle, T):
+    """bench.py's session variant end to end: two StreamInputs (30 fps pictures from pinned memory, i16 audio) ->
+    VideoMixer -> Monitor beside the audio graph, three pipelined steps.  Every monitor picture (timing, pixels) and
+    every PCM fragment against the oracle's StreamInput, engine walker, VideoMixer model and MonitorFeed."""
+    from fractions import Fraction
+    from mixlab_b200.session import StreamSession
+    sr, spt, w, h, mon = 48000, 800, 128, 72, (56, 34)
+    desc = W.config4_audio_graph()
+    steps = 3
+    with mxl.Context(0, sr, spt) as ctx:
+        sess = StreamSession(ctx, desc, T, width=w, height=h, monitor=mon, unique_frames=3, seed=0x5E55)
+        h2d0, d2h0 = ctx.h2d_bytes, ctx.d2h_bytes
+        got_jobs, got_pix, got_frags, got_pcm = [], [], [], []
+        for i in range(steps):
+            sess.enqueue_step(i * T, i & 1)
+            if i > 0:
+                n_pic, n_frag = sess.finish_step((i - 1) & 1)
+                got_jobs += [j[:3] for j in sess.jobs[(i - 1) & 1]]
+                got_pix += [np.array(p) for p in sess.pictures((i - 1) & 1)]
+                got_frags += sess.frags[(i - 1) & 1]
+                got_pcm += [np.array(sess.out_pcm[(i - 1) & 1][k]) for k in range(n_frag)]
+        slot = (steps - 1) & 1
+        n_pic, n_frag = sess.finish_step(slot)
+        got_jobs += [j[:3] for j in sess.jobs[slot]]
+        got_pix += [np.array(p) for p in sess.pictures(slot)]
+        got_frags += sess.frags[slot]
+        got_pcm += [np.array(sess.out_pcm[slot][k]) for k in range(n_frag)]
+        ctx.synchronize()
+        assert ctx.h2d_bytes - h2d0 == steps * sess.h2d_bytes_per_step
+        host_pix = [np.array(sess.host_pix[s].array).reshape(sess.n_frames, sess.frame_bytes) for s in range(2)]
+        host_pcm = [np.array(p) for p in sess.host_pcm]
+        n_frames, tpf, fps = sess.n_frames, sess.tpf, sess.fps
+        sess.close()
+
+    # ---- the oracle chain, fed the same pushes at the same ticks ----
+    lay = oracle.frame_layout(w, h)
+    ins = [oracle.StreamInput(sr), oracle.StreamInput(sr)]
+    og, oids = oracle.build_graph(desc, sr, spt)
+    vm = VideoMixerModel(oracle, lay, 0.5, sr)
+    feed = oracle.MonitorFeed(sr, mon[0], mon[1])
+    for i in range(steps):
+        for s in range(2):
+            for k in range(n_frames):
+                assert ins[s].write_video(1, Fraction(i * n_frames + k, fps), host_pix[s][k], Fraction(1, fps))
+            for off in range(0, T * spt, 1024):
+                cnt = min(1024, T * spt - off)
+                assert ins[s].write_audio(1, Fraction(i * T * spt + off, sr), host_pcm[s][2 * off:2 * (off + cnt)])
+        for k in range(T):
+            tick = i * T + k
+            vin = [ins[s].run_tick(tick * spt, 2 * spt)[0] for s in range(2)]
+            master = og.run_tick(tick, (oids[desc.taps["master"][0]], 0), 2 * spt)
+            comp = vm.run_tick(tick * spt, vin)
+            feed.run_tick(tick * spt, master, None if comp is None else (comp, lay, Fraction(spt, sr), Fraction(0)))
+    assert len(got_jobs) == len(feed.video_out) and len(got_jobs) >= steps * T - 1
+    for i, ((pts, dur, blank), pix, (wpts, wdur, wblank, wpix)) in enumerate(zip(got_jobs, got_pix, feed.video_out)):
+        assert (pts, dur, blank) == (wpts, wdur, wblank), i
+        assert np.array_equal(pix, wpix), i
+    assert len(got_frags) == len(feed.audio_out) == (steps * T * spt * 2 - 1) // 2048
+    for i, ((dec, dur), frag, (wdec, wdur, wfrag)) in enumerate(zip(got_frags, got_pcm, feed.audio_out)):
+        assert Fraction(*dec) == wdec and Fraction(*dur) == wdur, i
+        # the master bus is sine-based: packed i16 may differ by one step where a device sine differs from glibc's
+        assert np.max(np.abs(frag.astype(np.int32) - wfrag.astype(np.int32))) <= 1, i
