@@ -617,6 +617,9 @@ def b200_arm(args):
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, dist.world))
     T, K, Wm = args.ticks_per_step, args.steps, max(args.warmup, 3)
     ctx = mxl.Context(device=dist.local_rank, sample_rate=SAMPLE_RATE, samples_per_tick=SPT)
+    # host side of the host-fed legs: this rank's thread and the pinned staging buffers it allocates from here on move
+    # next to its GPU (a no-op on a single-node host)
+    numa = (-1, 0) if os.environ.get("MXL_NO_NUMA_BIND") else ctx.bind_host_to_gpu_node()
     desc = W.config2_graph() if args.workload in ("av", "audio") else None
     sess = AVSession(ctx, desc, T, video=args.workload in ("av", "video"), seed=session_seed(0xA11CE, dist.rank))
     sess.upload_inputs()
@@ -792,6 +795,7 @@ def b200_arm(args):
             "config": {"workload": workload_name(args), "ticks_per_step": T, "samples_per_tick": SPT,
                        "sample_rate": SAMPLE_RATE, "frame": "1920x1080 yuv420p", "sessions": dist.world,
                        "parallelism": "1 independent session per GPU, no collective",
+                       "host_numa": {"node_of_rank0_gpu": numa[0], "cpus_bound": numa[1]},
                        "l2": l2_note},
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"]},

@@ -170,6 +170,11 @@ MXL_API const char *mxl_version(void);
 /* Decibel::to_linear, protocol/src/lib.rs:469-471 (host scalar; exposed for tests) */
 MXL_API double mxl_db_to_linear(double db);
 
+/* Host-fed sessions on a multi-socket box: moves the CALLING thread (the engine thread of this context) onto the CPUs of
+ * the NUMA node the context's GPU hangs off (/sys/bus/pci/devices/<bdf>/numa_node) and makes that node the preferred
+ * one for its later allocations, so that pinned staging buffers (mxl_host_alloc) are first-touched next to the GPU.
+ * node_out = the node, or -1 when the platform reports none (nothing was changed); cpus_out = CPUs in the new mask. */
+MXL_API int mxl_ctx_bind_host_to_gpu_node(mxl_ctx *ctx, int32_t *node_out, int32_t *cpus_out);
 /* Pinned host memory for upload/download staging. */
 MXL_API void *mxl_host_alloc(size_t bytes);
 MXL_API int mxl_host_free(void *p);
@@ -398,6 +403,22 @@ MXL_API int mxl_pcm_pack_i16(mxl_ctx *ctx, const mxl_line *src, int16_t *host_pc
  * download fence has passed.  With copy overlap enabled the bus transfer runs on the copy streams. */
 MXL_API int mxl_pcm_unpack_i16_async(mxl_ctx *ctx, const int16_t *host_pcm, uint64_t n_samples, mxl_line *dst);
 MXL_API int mxl_pcm_pack_i16_async(mxl_ctx *ctx, const mxl_line *src, int16_t *host_pcm, uint64_t n_samples);
+
+/* ---- audio sample-rate converter (north_star "resample"; NEW and self-specified -- the reference has only the TODO:
+ * Icecast ingest drops every stream that is not at the engine's rate, src/icecast/mod.rs:94-97, RTMP ingest panics,
+ * src/rtmp/mod.rs:229-232).  What a receiver calls between its decoder and mxl_stream_input_write_audio / a source line:
+ * interleaved i16 (or an f32 line) at the source's rate in, an f32 line at out_rate out.  Polyphase windowed sinc for
+ * the exact ratio (44.1 k -> 48 k: 160 / 147), 32 taps per output frame accumulated in f64 with fma; the exact definition
+ * is oracle/mixlab_oracle.h (orc_resampler_*), parity unpinned.  The converter is a pure function of the stream pushed so
+ * far: any split into calls gives the same bits.  After N input frames, ceil((N - 16) * L / M) output frames are
+ * determined; each push resizes `out` to the frames it produced and returns that count (>= 0) or a negative status. */
+typedef struct mxl_resampler mxl_resampler;
+MXL_API mxl_resampler *mxl_resampler_create(mxl_ctx *ctx, uint32_t in_rate, uint32_t out_rate, uint32_t channels);
+MXL_API void mxl_resampler_destroy(mxl_resampler *r);
+MXL_API int mxl_resampler_reset(mxl_resampler *r);
+MXL_API uint64_t mxl_resampler_output_frames(const mxl_resampler *r, uint64_t in_frames);
+MXL_API int64_t mxl_resampler_push_i16(mxl_resampler *r, const int16_t *host_pcm, uint64_t in_frames, mxl_line *out);
+MXL_API int64_t mxl_resampler_push_line(mxl_resampler *r, const mxl_line *in, mxl_line *out);
 
 /* yuv420p -> RGBA8 of a frame (self-specified BT.601 integer form; the reference
  * never converts colour, video_mixer.rs:282-283).  rgba_host receives width*height*4 bytes. */

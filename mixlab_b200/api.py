@@ -175,6 +175,7 @@ def lib():
         "mxl_ctx_set_kernel_timing": (i32, [vp, i32]),
         "mxl_ctx_kernel_times": (i32, [vp, C.POINTER(KernelTime), u32]),
         "mxl_ctx_fused_profile": (i32, [vp, u32, vp, u32]),
+        "mxl_ctx_bind_host_to_gpu_node": (i32, [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
         "mxl_last_error": (C.c_char_p, []),
         "mxl_version": (C.c_char_p, []),
         "mxl_db_to_linear": (dbl, [dbl]),
@@ -261,6 +262,12 @@ def lib():
         "mxl_frames_to_rgba": (i32, [vp, C.POINTER(vp), u32, vp, u32]),
         "mxl_rgba_upload": (i32, [vp, u32, u32, vp]),
         "mxl_rgba_to_frames": (i32, [vp, vp, u32, u32, C.POINTER(vp)]),
+        "mxl_resampler_create": (vp, [vp, u32, u32, u32]),
+        "mxl_resampler_destroy": (None, [vp]),
+        "mxl_resampler_reset": (i32, [vp]),
+        "mxl_resampler_output_frames": (u64, [vp, u64]),
+        "mxl_resampler_push_i16": (C.c_int64, [vp, vp, u64, vp]),
+        "mxl_resampler_push_line": (C.c_int64, [vp, vp, vp]),
         "mxl_comm_unique_id": (i32, [vp]),
         "mxl_ctx_comm_init": (i32, [vp, vp, i32, i32]),
         "mxl_ctx_comm_destroy": (i32, [vp]),
@@ -422,6 +429,12 @@ class Context:
         check(lib().mxl_ctx_timer_elapsed_ms(self.h, C.byref(ms)))
         return ms.value
 
+    def bind_host_to_gpu_node(self):
+        """(numa node or -1, cpus in the new affinity mask) -- mxl_ctx_bind_host_to_gpu_node."""
+        node, cpus = C.c_int32(), C.c_int32()
+        check(lib().mxl_ctx_bind_host_to_gpu_node(self.h, C.byref(node), C.byref(cpus)))
+        return node.value, cpus.value
+
     def fused_profile(self, max_ctas, read=True):
         """mxl_ctx_fused_profile: (n_ctas, 8) SM-clock stamps of the last fused_voice_kernel launch; then re-arms for max_ctas."""
         buf = np.zeros((8192, 8), np.uint64)
@@ -482,6 +495,9 @@ class Context:
         out = (C.c_void_p * n)()
         check(lib().mxl_frames_alloc_batch(self.h, width, height, n, out))
         return [Frame(self, handle=out[i]) for i in range(n)]
+
+    def resampler(self, in_rate, out_rate, channels=2):
+        return Resampler(self, in_rate, out_rate, channels)
 
     def rgba(self, width, height, n_pictures):
         return RgbaPictures(self, width, height, n_pictures)
@@ -557,6 +573,39 @@ class Line:
         if self.h and self.owned:
             lib().mxl_line_free(self.h)
         self.h = None
+
+
+class Resampler:
+    """mxl_resampler: audio sample-rate converter of the ingest side (new; the reference has only the TODO)."""
+
+    def __init__(self, ctx, in_rate, out_rate, channels=2):
+        self.ctx, self.channels = ctx, channels
+        self.h = lib().mxl_resampler_create(ctx.h, in_rate, out_rate, channels)
+        if not self.h:
+            raise MxlError(ERR_INVALID, last_error())
+        self.out = ctx.line(LINE_STEREO if channels == 2 else LINE_MONO, 0)
+
+    def push_i16(self, pcm):
+        """interleaved int16 from the host -> the newly determined output frames (float32, interleaved)."""
+        pcm = np.ascontiguousarray(pcm, np.int16)
+        n = check(lib().mxl_resampler_push_i16(self.h, _ptr(pcm), pcm.size // self.channels, self.out.h))
+        return self.out.download(n * self.channels) if n else np.empty(0, np.float32)
+
+    def push_line(self, line):
+        n = check(lib().mxl_resampler_push_line(self.h, line.h, self.out.h))
+        return self.out.download(n * self.channels) if n else np.empty(0, np.float32)
+
+    def output_frames(self, in_frames):
+        return int(lib().mxl_resampler_output_frames(self.h, in_frames))
+
+    def reset(self):
+        check(lib().mxl_resampler_reset(self.h))
+
+    def close(self):
+        if self.h:
+            lib().mxl_resampler_destroy(self.h)
+            self.h = None
+        self.out.free()
 
 
 class RgbaPictures:

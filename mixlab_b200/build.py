@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(HERE, "libmixlab_b200.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "mixlab_b200.h")
 
 SOURCES = ["core.cu", "abi.cu", "modules.cu", "graph.cu", "audio_kernels.cu", "eq_three.cu", "eq_stream.cu",
-           "envelope.cu", "video_kernels.cu", "comm.cu", "fused_voice.cu"]
+           "envelope.cu", "video_kernels.cu", "comm.cu", "fused_voice.cu", "resample.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -5,6 +5,11 @@
 
 #include <stdlib.h>
 
+#include <ctype.h>
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include "common.h"
 #include "kernels.h"
 
@@ -359,6 +364,56 @@ int mxl_ctx_device_memory(mxl_ctx* ctx, uint64_t* free_bytes, uint64_t* total_by
     MXL_CUDA(cudaMemGetInfo(&f, &t));
     if (free_bytes) *free_bytes = f;
     if (total_bytes) *total_bytes = t;
+    return MXL_OK;
+}
+
+// Host side of a host-fed session: the engine thread and the pinned buffers it allocates afterwards move next to the GPU.
+// On a two-socket box a rank whose staging buffers live on the far socket pulls them through the inter-socket link, and
+// N ranks that all start on socket 0 share that socket's memory controllers (bench.py's e2e leg at 2-8 GPUs).
+int mxl_ctx_bind_host_to_gpu_node(mxl_ctx* ctx, int32_t* node_out, int32_t* cpus_out)
+{
+    if (node_out) *node_out = -1;
+    if (cpus_out) *cpus_out = 0;
+    if (!ctx) MXL_FAIL(MXL_ERR_INVALID, "NULL context");
+    if (!ctx->has_device()) MXL_FAIL(MXL_ERR_NO_DEVICE, "no CUDA device bound to this context");
+    MXL_TRY(ctx->activate());
+    char bdf[32] = {0};
+    MXL_CUDA(cudaDeviceGetPCIBusId(bdf, sizeof bdf, ctx->device));
+    for (char* p = bdf; *p; p++) *p = (char)tolower(*p);
+    auto read_small = [](const std::string& path) -> std::string {
+        FILE* f = fopen(path.c_str(), "r");
+        if (!f) return "";
+        char buf[4096];
+        size_t n = fread(buf, 1, sizeof buf - 1, f);
+        fclose(f);
+        buf[n] = 0;
+        while (n && (buf[n - 1] == '\n' || buf[n - 1] == ' ')) buf[--n] = 0;
+        return buf;
+    };
+    // the kernel's view of the topology (nvidia-smi topo is not trustworthy inside a VM)
+    const std::string node_s = read_small(std::string("/sys/bus/pci/devices/") + bdf + "/numa_node");
+    const int node = node_s.empty() ? -1 : atoi(node_s.c_str());
+    if (node < 0) return MXL_OK;                                   // single node, or the platform does not say: nothing to do
+    const std::string list = read_small("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist");
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int n_cpus = 0;
+    for (size_t i = 0; i < list.size();) {                         // "0-15,32-47"
+        const int a = atoi(list.c_str() + i);
+        int b = a;
+        while (i < list.size() && list[i] != '-' && list[i] != ',') i++;
+        if (i < list.size() && list[i] == '-') { b = atoi(list.c_str() + i + 1); while (i < list.size() && list[i] != ',') i++; }
+        for (int c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET(c, &set); n_cpus++; }
+        if (i < list.size()) i++;
+    }
+    if (n_cpus == 0) return MXL_OK;
+    if (sched_setaffinity(0, sizeof set, &set) != 0) return MXL_OK;               // not permitted (cgroup): leave things as they are
+    if (node < 64) {
+        unsigned long mask = 1ul << node;
+        syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, sizeof(mask) * 8);   // pinned buffers allocated from now on: near node first
+    }
+    if (node_out) *node_out = node;
+    if (cpus_out) *cpus_out = n_cpus;
     return MXL_OK;
 }
 

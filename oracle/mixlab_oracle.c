@@ -890,6 +890,76 @@ void orc_graph_meter(const orc_graph *g, int module, float peak[2], double sumsq
 }
 
 /* ======================================================================================== */
+/* audio sample-rate converter (definition: see the header)                                  */
+/* ======================================================================================== */
+struct orc_resampler {
+    uint32_t L, M, channels;
+    double *coef;                 /* [L][32] */
+    float *x; size_t n_in, cap;   /* the whole input stream */
+    size_t n_out;
+};
+
+static double rs_sinc(double u) { const double pi = 3.14159265358979323846264338327950288; return u == 0.0 ? 1.0 : sin(pi * u) / (pi * u); }
+static double rs_bh(double u)
+{
+    const double pi = 3.14159265358979323846264338327950288;
+    return 0.35875 + 0.48829 * cos(pi * u) + 0.14128 * cos(2.0 * pi * u) + 0.01168 * cos(3.0 * pi * u);
+}
+
+orc_resampler *orc_resampler_create(uint32_t in_rate, uint32_t out_rate, uint32_t channels)
+{
+    orc_resampler *r = calloc(1, sizeof *r);
+    uint64_t g = gcd_u64(in_rate, out_rate);
+    r->L = (uint32_t)(out_rate / g); r->M = (uint32_t)(in_rate / g); r->channels = channels;
+    r->coef = malloc(sizeof(double) * 32 * r->L);
+    const double ratio = (double)r->L / (double)r->M;
+    const double w = 0.92 * (ratio < 1.0 ? ratio : 1.0);
+    for (uint32_t ph = 0; ph < r->L; ph++) {
+        double row[32], sum = 0.0;
+        for (int k = 0; k < 32; k++) {
+            const double x = (double)(k - 16 + 1) - (double)ph / (double)r->L;
+            row[k] = w * rs_sinc(w * x) * rs_bh(x / 16.0);
+            sum += row[k];
+        }
+        for (int k = 0; k < 32; k++) r->coef[(size_t)ph * 32 + k] = row[k] / sum;
+    }
+    return r;
+}
+
+void orc_resampler_destroy(orc_resampler *r) { if (r) { free(r->coef); free(r->x); free(r); } }
+double orc_resampler_coef(const orc_resampler *r, uint32_t phase, uint32_t k) { return r->coef[(size_t)phase * 32 + k]; }
+void orc_resampler_ratio(const orc_resampler *r, uint32_t *L, uint32_t *M) { *L = r->L; *M = r->M; }
+
+size_t orc_resampler_push(orc_resampler *r, const float *in, size_t in_frames, float *out, size_t cap_frames)
+{
+    const size_t C = r->channels;
+    if (r->n_in + in_frames > r->cap) {
+        r->cap = (r->n_in + in_frames) * 2 + 1024;
+        r->x = realloc(r->x, r->cap * C * sizeof(float));
+    }
+    memcpy(r->x + r->n_in * C, in, in_frames * C * sizeof(float));
+    r->n_in += in_frames;
+    const size_t total = r->n_in <= 16 ? 0 : (size_t)(((uint64_t)(r->n_in - 16) * r->L + r->M - 1) / r->M);
+    size_t made = 0;
+    for (size_t m = r->n_out; m < total && made < cap_frames; m++, made++) {
+        const uint64_t pos = (uint64_t)m * r->M;
+        const int64_t n0 = (int64_t)(pos / r->L);
+        const double *c = r->coef + (size_t)(pos % r->L) * 32;
+        for (size_t ch = 0; ch < C; ch++) {
+            double acc = 0.0;
+            for (int k = 0; k < 32; k++) {
+                const int64_t n = n0 - 16 + 1 + k;
+                const double xv = n < 0 ? 0.0 : (double)r->x[(size_t)n * C + ch];
+                acc = fma(c[k], xv, acc);
+            }
+            out[made * C + ch] = (float)acc;
+        }
+    }
+    r->n_out += made;
+    return made;
+}
+
+/* ======================================================================================== */
 /* one live session, tick after tick (see the header)                                        */
 /* ======================================================================================== */
 void orc_session_run(orc_session *s, uint64_t tick0, uint32_t n_ticks)

@@ -191,6 +191,23 @@ int orc_graph_last_order(const orc_graph *g, int *order, int cap);
 /* meter values recorded by ORC_MOD_METER at the last tick */
 void orc_graph_meter(const orc_graph *g, int module, float peak[2], double sumsq[2], int *clip);
 
+/* ---- audio sample-rate converter: UNPINNED, this is its definition (the reference has only the TODO,
+ * src/icecast/mod.rs:94-97).  Rational ratio L / M = out_rate / in_rate reduced; output frame m of the stream sits at input
+ * position m * M / L: n0 = floor(m * M / L), phase = (m * M) mod L, and
+ *     y[m] = (float) sum_{k = 0}^{31} c[phase][k] * (double) x[n0 - 15 + k]      accumulated with fma(), k ascending, from 0.0
+ *     c[phase][k] = h(k - 15 - phase / L) / (sum over k of the same),  h(x) = w * sinc(w * x) * bh(x / 16),
+ *     w = 0.92 * min(1, L / M),  sinc(u) = sin(pi u) / (pi u),  bh(u) = 0.35875 + 0.48829 cos(pi u) + 0.14128 cos(2 pi u) + 0.01168 cos(3 pi u)
+ * x before the start of the stream is 0; i16 input is first converted like StreamInput does (s / 32768.0f).  After N input
+ * frames, ceil((N - 16) * L / M) output frames are determined.  The oracle keeps the whole stream. */
+typedef struct orc_resampler orc_resampler;
+orc_resampler *orc_resampler_create(uint32_t in_rate, uint32_t out_rate, uint32_t channels);
+void orc_resampler_destroy(orc_resampler *r);
+/* appends in_frames interleaved f32 frames; writes the newly determined output frames to out (cap_frames); returns their count */
+size_t orc_resampler_push(orc_resampler *r, const float *in, size_t in_frames, float *out, size_t cap_frames);
+/* c[phase][k], for tests */
+double orc_resampler_coef(const orc_resampler *r, uint32_t phase, uint32_t k);
+void orc_resampler_ratio(const orc_resampler *r, uint32_t *L, uint32_t *M);
+
 /* ---- one live session tick after tick, as the reference's engine thread and its two neighbours do it per tick
  * (timed CPU arm of bench.py's session variant; the per-function restatements above are what it calls):
  *   StreamInput x2: convert_sample of the tick's i16 (stream_input.rs:110-112,167-173)

@@ -71,6 +71,14 @@ def lib():
         _lib.orc_fader_to_u8.argtypes = [C.c_double]
         _lib.orc_clip_detect.restype = C.c_int
         _lib.orc_session_run.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
+        _lib.orc_resampler_create.restype = C.c_void_p
+        _lib.orc_resampler_create.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+        _lib.orc_resampler_destroy.argtypes = [C.c_void_p]
+        _lib.orc_resampler_push.restype = C.c_size_t
+        _lib.orc_resampler_push.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        _lib.orc_resampler_coef.restype = C.c_double
+        _lib.orc_resampler_coef.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        _lib.orc_resampler_ratio.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -403,6 +411,40 @@ class Session:
 
     def run(self, tick0, n_ticks):
         lib().orc_session_run(C.byref(self.s), C.c_uint64(tick0), C.c_uint32(n_ticks))
+
+
+class Resampler:
+    """orc_resampler: the definition of the audio sample-rate converter (UNPINNED: the reference has only the TODO,
+    src/icecast/mod.rs:94-97).  push() takes interleaved f32 (or int16, converted s / 32768 like StreamInput) and returns
+    the output frames that became determined."""
+
+    def __init__(self, in_rate, out_rate, channels):
+        self.channels = channels
+        self._r = lib().orc_resampler_create(in_rate, out_rate, channels)
+        L, M = C.c_uint32(), C.c_uint32()
+        lib().orc_resampler_ratio(self._r, C.byref(L), C.byref(M))
+        self.L, self.M = L.value, M.value
+
+    def push(self, x):
+        x = np.asarray(x)
+        if x.dtype == np.int16:
+            x = pcm_unpack_i16(x)
+        x = _f32(x)
+        n = x.size // self.channels
+        out = np.empty((n * self.L // self.M + 8) * self.channels, np.float32)
+        made = lib().orc_resampler_push(self._r, _p(x), n, _p(out), out.size // self.channels)
+        return out[:made * self.channels]
+
+    def coef(self, phase, k):
+        return lib().orc_resampler_coef(self._r, phase, k)
+
+    def close(self):
+        if self._r:
+            lib().orc_resampler_destroy(self._r)
+            self._r = None
+
+    def __del__(self):
+        self.close()
 
 
 class OutputDevice:

@@ -336,3 +336,39 @@ def test_session_driver_equals_its_parts(oracle):
     sess2 = oracle.Session(oracle.build_graph(desc, sr, spt)[0], ids[desc.taps["master"][0]], w, h, 56, 34, la, lb, 2, pcm, 0.3)
     sess2.run(0, 7)
     assert np.array_equal(sess2.monitor_out, sess.monitor_out) and np.array_equal(sess2.pcm_out, sess.pcm_out)
+
+
+def test_rgba_to_yuv420p_known_colours_and_round_trip(oracle):
+    """UNPINNED (the reference never converts colour): the integer BT.601 definition on the primaries, on a cut 2x2
+    block, and against its own inverse (yuv420p -> RGBA -> yuv420p) where nothing clipped."""
+    lay = oracle.frame_layout(4, 2)
+    colours = {(255, 255, 255): (235, 128, 128), (0, 0, 0): (16, 128, 128), (255, 0, 0): (82, 90, 240),
+               (0, 255, 0): (144, 54, 34), (0, 0, 255): (41, 240, 110)}
+    for rgb, yuv in colours.items():
+        rgba = np.tile(np.array(rgb + (7,), np.uint8), 8)               # alpha is ignored
+        out = oracle.rgba_to_yuv420p(lay, rgba)
+        assert set(out[lay.offset[0]:lay.offset[0] + 4]) == {yuv[0]} and out[lay.offset[1]] == yuv[1] and out[lay.offset[2]] == yuv[2], rgb
+    # odd picture: the last chroma block repeats its last column / row
+    lay3 = oracle.frame_layout(3, 3)
+    rgba = W.random_bytes(5, 3 * 3 * 4)
+    out = oracle.rgba_to_yuv420p(lay3, rgba)
+    px = rgba.reshape(3, 3, 4).astype(np.int64)
+    corner = px[2, 2, :3]                                               # the bottom-right block is one pixel, four times
+    assert out[lay3.offset[1] + lay3.stride[1] + 1] == ((-38 * corner[0] - 74 * corner[1] + 112 * corner[2] + 128) >> 8) + 128
+    # round trip from a frame whose conversion to RGB does not clip: luma back within 2 levels, chroma within 3
+    lay = oracle.frame_layout(64, 36)
+    yuv = oracle.frame_blank(lay)
+    rng = np.random.default_rng(3)
+    yuv[lay.offset[0]:lay.offset[0] + lay.stride[0] * 36] = rng.integers(60, 180, lay.stride[0] * 36)
+    for p in (1, 2):
+        yuv[lay.offset[p]:lay.offset[p] + lay.stride[p] * 18] = rng.integers(108, 148, lay.stride[p] * 18)
+    rgba = oracle.yuv420p_to_rgba(lay, yuv)
+    assert rgba.reshape(-1, 4)[:, :3].min() > 0 and rgba.reshape(-1, 4)[:, :3].max() < 255
+    back = oracle.rgba_to_yuv420p(lay, rgba)
+    y0 = yuv[lay.offset[0]:lay.offset[0] + lay.stride[0] * 36].reshape(36, -1)[:, :64].astype(int)
+    y1 = back[lay.offset[0]:lay.offset[0] + lay.stride[0] * 36].reshape(36, -1)[:, :64].astype(int)
+    assert np.abs(y0 - y1).max() <= 2
+    for p in (1, 2):
+        c0 = yuv[lay.offset[p]:lay.offset[p] + lay.stride[p] * 18].reshape(18, -1)[:, :32].astype(int)
+        c1 = back[lay.offset[p]:lay.offset[p] + lay.stride[p] * 18].reshape(18, -1)[:, :32].astype(int)
+        assert np.abs(c0 - c1).max() <= 3

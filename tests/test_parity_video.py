@@ -325,6 +325,31 @@ def test_frame_batch_moves_as_one_copy(mxl, oracle, ctx48):
     host.free(); back.free()
 
 
+@pytest.mark.parametrize("size", [(1920, 1080), (560, 350), (70, 50), (34, 18), (35, 19), (9, 3), (2, 2)])
+def test_rgba_to_yuv_self_specified(mxl, oracle, ctx48, size):
+    """UNPINNED (north_star's "YUV<->RGB", no reference counterpart): RGBA8 -> yuv420p against the oracle's integer
+    definition, byte for byte incl. odd pictures (cut chroma blocks) and untouched stride padding; n pictures, one launch."""
+    w, h = size
+    n = 3
+    lay = oracle.frame_layout(w, h)
+    rgba = W.random_bytes(w * 131 + h, n * w * h * 4)
+    pics = ctx48.rgba(w, h, n)
+    pics.upload(rgba)
+    pad = [W.random_bytes(900 + k, lay.size) for k in range(n)]          # what the frames held before: padding must survive
+    frames = [ctx48.frame(w, h, pad[k]) for k in range(n)]
+    before = ctx48.launch_count
+    pics.to_frames(frames)
+    assert ctx48.launch_count - before == 1
+    for k in range(n):
+        want = oracle.rgba_to_yuv420p(lay, rgba[k * w * h * 4:(k + 1) * w * h * 4], into=pad[k])
+        assert np.array_equal(frames[k].download_raw(), want), k
+    # and through the compositor: a picture converted to yuv420p enters VideoMixer like any frame
+    mod, outs = run_mixer(mxl, ctx48, (0, -1, 1.0), {0: [frames[0]]})
+    assert np.array_equal(outs[0].get(0).download_raw()[:lay.offset[1]].reshape(lay.plane_h[0], lay.stride[0])[:, :w],
+                          oracle.rgba_to_yuv420p(lay, rgba[:w * h * 4]) [:lay.offset[1]].reshape(lay.plane_h[0], lay.stride[0])[:, :w])
+    pics.free()
+
+
 def test_yuv_to_rgba_self_specified(mxl, oracle, ctx48):
     # UNPINNED: the reference never converts colour (video_mixer.rs:282-283); spec = oracle header
     for (w, h) in [(1920, 1080), (70, 50), (34, 18)]:
