@@ -276,3 +276,19 @@ def test_workload_byte_accounting():
     a = W.uniform_pm1(1, 1000)
     assert a.dtype == np.float32 and a.min() >= -1.0 and a.max() < 1.0 and np.array_equal(a, W.uniform_pm1(1, 1000))
     assert int(W.splitmix64(0, 1)[0]) == 0xE220A8397B1DCDAF        # published splitmix64 first output for seed 0
+
+
+def test_rust_sys_declares_every_exported_symbol(mxl):
+    """rust/src/sys.rs (generated from the header by tools/gen_rust_sys.py; uncompiled: no rustc in this image) declares
+    every entry point the header does, once, and is up to date with the header."""
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "rust", "src", "sys.rs")
+    before = open(path).read()
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "gen_rust_sys.py")], stdout=subprocess.DEVNULL)
+    assert open(path).read() == before, "rust/src/sys.rs is stale: run tools/gen_rust_sys.py"
+    declared = re.findall(r"pub fn (mxl_[a-z0-9_]+)\(", before)
+    assert sorted(declared) == sorted(mxl.declared_symbols()) and len(set(declared)) == len(declared)
+
