@@ -70,7 +70,11 @@ MXL_HD float eq_bands(double l3, double h3, double x0, const EqGains& g)
 // A full chunk of LC samples (LC % 4 == 0, LC >= 8).  `io` gives the chunk as LC/4 vectors:
 // EqF4 io.load(v), void io.store(v, EqF4); outputs overwrite the inputs in place, vector v is stored
 // only after vector v+1 has been loaded.  p: poles before the chunk -> after; hist likewise.
-template <int LC, class Io>
+// ROLL: the steady-state loop stays a loop of four samples per trip (~190 instructions) instead of LC / 4 unrolled copies.
+// Unrolled is faster once several CTAs share an SM and keep its instruction cache warm (the stand-alone EqThree kernel on
+// long lines: 0.125 vs 0.154 ms per 2^25 samples); rolled is faster for a CTA that runs the code once, alone (a live
+// one-tick call: the unrolled body stalled its warps on instruction fetch for 5.8 of every 6.8 issue slots).
+template <int LC, bool ROLL = false, class Io>
 MXL_HD void eq_run_chunk_skewed(EqPoles& p, double hist[3], Io& io, const EqGains& g)
 {
     static_assert(LC % 4 == 0 && LC >= 8, "chunk length");
@@ -89,9 +93,9 @@ MXL_HD void eq_run_chunk_skewed(EqPoles& p, double hist[3], Io& io, const EqGain
         s = (double)x.w; eq_skew_iter<true, true, true, true>(p, s, cl, ch);
         carry = eq_bands(p.l3, p.h3, d5, g); MXL_EQ_SHIFT(s);
     }
-    // a real loop on the device (four samples per trip): fully unrolled, the chunk is ~1500 instructions of
-    // straight-line code per cascade length and the warps of a CTA stall on instruction fetch
-#pragma unroll 1
+#if defined(__CUDACC__)
+#pragma unroll (ROLL ? 1 : LC / 4)
+#endif
     for (int v = 1; v < LC / 4; v++) {
         const EqF4 x = io.load(v);
         EqF4 y;
@@ -120,10 +124,12 @@ MXL_HD void eq_run_chunk_skewed(EqPoles& p, double hist[3], Io& io, const EqGain
 // acc[e] = K[e] + sum_j x_j * V[j][e].  V[j] = response at the chunk end to a unit input at j, K = the
 // VSA terms; both come from the host plan.  Independent FMA chains -- accuracy 1e-16 relative is all
 // the carry needs (its error is absorbed by the final `as f32`).
-template <int LC, class Io, class Tab>
+template <int LC, bool ROLL = false, class Io, class Tab>
 MXL_HD void eq_zero_state_dot(const Io& io, const Tab& tab, double acc[8])
 {
-#pragma unroll 1
+#if defined(__CUDACC__)
+#pragma unroll (ROLL ? 1 : LC / 4)
+#endif
     for (int v = 0; v < LC / 4; v++) {
         const EqF4 x = io.load(v);
         const double s[4] = {(double)x.x, (double)x.y, (double)x.z, (double)x.w};

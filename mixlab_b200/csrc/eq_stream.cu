@@ -32,6 +32,9 @@
 // Roofline: 8 B/sample of line traffic against ~47 FP64 operations per sample (34 exact + 8 zero
 // pass + ~4 scan + halo): at the measured 64 FP64 lanes/clk/SM (tools/pipe_rates.cu) the FP64 pipe
 // allows 0.40 of the HBM copy peak, so this kernel is FP64-issue-bound, not HBM-bound.
+#include <stdlib.h>
+#include <string.h>
+
 #include "eq_stream.cuh"
 
 namespace mxl {
@@ -41,14 +44,24 @@ namespace {
 
 using namespace eqs;
 
-template <int LC>
-__global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ EqStreamBatch b)
+// zero-pass table of the long-call variant: kernel parameters = constant-bank operands of the unrolled FMA chains
+struct EqVParam { double K[8]; double V[64][8]; };
+struct EqNoParam {};
+struct ParamTab {
+    const EqVParam& p;
+    __device__ __forceinline__ double v(int j, int e) const { return p.V[j][e]; }
+};
+
+// BIG = the long-call variant: chunk loops unrolled (eq_core.cuh), V / K from the kernel parameters, no V in shared memory.
+template <int LC, bool BIG, class VP>
+__device__ __forceinline__ void eq_stream_body(const EqStreamBatch& b, const VP& vp)
 {
     constexpr int VPR = LC / 4;
-    pdl_prologue();
+    constexpr bool ROLL = !BIG;
+    using Shared = EqShared<LC, !BIG>;
     extern __shared__ __align__(16) unsigned char eq_smem[];
     float4* tile = reinterpret_cast<float4*>(eq_smem);                              // [256][VPR], swizzled
-    EqShared<LC>* sh = reinterpret_cast<EqShared<LC>*>(eq_smem + (size_t)kT * LC * sizeof(float));
+    Shared* sh = reinterpret_cast<Shared*>(eq_smem + (size_t)kT * LC * sizeof(float));
     const EqStreamInst& in = b.inst[blockIdx.y];
     const int tid = threadIdx.x;
     const EqStreamConsts& q = b.eq;
@@ -57,12 +70,23 @@ __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ E
     const int64_t c0 = (int64_t)blockIdx.x * U - halo;        // chunk of thread 0
     const int64_t c = c0 + tid;
     const bool active = c >= 0 && c < (int64_t)b.n_chunks;
+    // every chunk of the tile exists and is full, lines 16-byte aligned: staging and store are straight copies
+    const bool interior = c0 >= 0 && (uint64_t)(c0 + kT) * LC <= b.frames && in.in &&
+                          ((reinterpret_cast<uintptr_t>(in.in) | reinterpret_cast<uintptr_t>(in.out)) & 15) == 0;
+    // vector idx = it * kT + tid of the tile is (row it * (kT / VPR) + tid / VPR, vector tid % VPR): the swizzle term depends
+    // on the row's low bits only, which `it` does not touch, so slots and addresses advance by constants
+    static_assert((kT / VPR) % 8 == 0, "rows per staging round");
 
     // ---- 1. stage ----
-    {
+    if (interior) {
+        const float* src = in.in + c0 * LC + 4 * tid;
+        float4* dst = tile + slot_of<VPR>(tid / VPR, tid % VPR);
+#pragma unroll
+        for (int it = 0; it < VPR; it++) cp_async16(dst + it * kT, src + it * kT * 4);
+    } else {
         const float* src = in.in;
         const bool vec_ok = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
-#pragma unroll
+#pragma unroll 1
         for (int it = 0; it < VPR; it++) {
             const int idx = it * kT + tid;
             const int r = idx / VPR, v = idx % VPR;
@@ -81,9 +105,9 @@ __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ E
                 *dst = x;
             }
         }
-        load_tables<LC>(q.tab, sh, tid);                        // in flight with the staging copies
-        asm volatile("cp.async.wait_all;" ::: "memory");
     }
+    load_tables<LC>(q.tab, sh, tid);                            // in flight with the staging copies
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
 
     const double* st = in.state;
@@ -94,10 +118,17 @@ __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ E
 #pragma unroll
     for (int e = 0; e < 8; e++) v[e] = 0.0;
     if (active) {
+        if constexpr (BIG) {
 #pragma unroll
-        for (int e = 0; e < 8; e++) v[e] = sh->K[e];
-        SharedTab<LC> tab{sh};
-        eq_zero_state_dot<LC>(row, tab, v);
+            for (int e = 0; e < 8; e++) v[e] = vp.K[e];
+            ParamTab tab{vp};
+            eq_zero_state_dot<LC, ROLL>(row, tab, v);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) v[e] = sh->K[e];
+            SharedTab<LC> tab{sh};
+            eq_zero_state_dot<LC, ROLL>(row, tab, v);
+        }
         if (c == 0) {                                      // v_0 = A p_init + z_0
             const double pl[4] = {st[0], st[1], st[2], st[3]}, ph[4] = {st[4], st[5], st[6], st[7]};
             double yl[4], yh[4];
@@ -136,7 +167,7 @@ __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ E
     if (owner) {
         const EqGains g{q.c_lo, q.c_hi, in.g_lo, in.g_mid, in.g_hi};
         if (count == LC) {
-            eq_run_chunk_skewed<LC>(p, hist, row, g);
+            eq_run_chunk_skewed<LC, ROLL>(p, hist, row, g);
         } else {                                           // ragged end of the call: one thread, sequential form
             float* mine = reinterpret_cast<float*>(tile);
             for (uint32_t j = 0; j < count; j++) {
@@ -154,7 +185,15 @@ __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ E
     __syncthreads();
 
     // ---- 5. coalesced store of the owned rows ----
-    {
+    if (interior) {
+        // vector idx of the owned part is (row halo + idx / VPR, vector idx % VPR): constants per round, as in the staging
+        const int total = U * VPR;
+        float* dst = in.out + (c0 + halo) * LC + 4 * tid;
+        const float4* srcv = tile + slot_of<VPR>(halo + tid / VPR, tid % VPR);
+#pragma unroll
+        for (int it = 0; it < VPR; it++)
+            if (it * kT + tid < total) *reinterpret_cast<float4*>(dst + it * kT * 4) = srcv[it * kT];
+    } else {
         float* dst = in.out;
         const bool vec_ok = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
         const int total = U * VPR;
@@ -176,10 +215,12 @@ __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ E
     }
 
     // ---- 6. poison fix-up by the CTA of this instance that finishes last ----
+    // The barrier orders every thread's stores before thread 0's fence (fences are cumulative), so one fence per CTA makes
+    // the tile's outputs visible before the CTA counts itself done.
     __shared__ uint32_t s_first_bad;
-    __threadfence();                                       // my outputs are visible before I count myself done
     __syncthreads();
     if (tid == 0) {
+        __threadfence();
         uint32_t first_bad = 0xffffffffu;
         if (atomicAdd(in.poison + 1, 1u) == gridDim.x - 1) {
             first_bad = atomicExch(in.poison, 0xffffffffu) ;  // read and re-arm for the next launch
@@ -204,18 +245,48 @@ __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ E
     }
 }
 
+// short calls (a CTA or two per SM, code run once): rolled loops, every table in shared memory
+template <int LC>
+__global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ EqStreamBatch b)
+{
+    pdl_prologue();
+    eq_stream_body<LC, false>(b, EqNoParam{});
+}
+
+// long calls (several waves of CTAs): unrolled loops, zero-pass table in the constant bank
+template <int LC>
+__global__ void __launch_bounds__(kT, LC == 64 ? 3 : 4) eq_stream_kernel_long(const __grid_constant__ EqStreamBatch b, const __grid_constant__ EqVParam vp)
+{
+    pdl_prologue();
+    eq_stream_body<LC, true>(b, vp);
+}
+
 template <int LC>
 int launch_lc(mxl_ctx* ctx, const EqStreamBatch& b)
 {
-    const size_t smem = (size_t)kT * LC * sizeof(float) + sizeof(EqShared<LC>);
-    if (smem > 48 * 1024 && !(ctx->eq_stream_smem_set & (1u << (LC / 16)))) {
-        MXL_CUDA(cudaFuncSetAttribute(eq_stream_kernel<LC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem_short = (size_t)kT * LC * sizeof(float) + sizeof(EqShared<LC, true>);
+    const size_t smem_long = (size_t)kT * LC * sizeof(float) + sizeof(EqShared<LC, false>);
+    if (!(ctx->eq_stream_smem_set & (1u << (LC / 16)))) {
+        MXL_CUDA(cudaFuncSetAttribute(eq_stream_kernel<LC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_short));
+        MXL_CUDA(cudaFuncSetAttribute(eq_stream_kernel_long<LC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_long));
+        MXL_CUDA(cudaFuncSetAttribute(eq_stream_kernel_long<LC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         ctx->eq_stream_smem_set |= 1u << (LC / 16);
     }
     const uint32_t U = kT - b.eq.halo;
     dim3 grid((b.n_chunks + U - 1) / U, b.n);
+    // the long-call variant once the SMs hold several CTAs each (see eq_core.cuh), the short one otherwise
+    const uint64_t ctas = (uint64_t)grid.x * grid.y, sms = (uint64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148);
+    static const char* force = getenv("MXL_EQ_ROLL");
+    const bool roll = force ? atoi(force) != 0 : ctas < 2 * sms;
     MXL_TIMED(ctx, "eq_stream_kernel");
-    launch_chained(ctx, eq_stream_kernel<LC>, grid, dim3(kT), smem, b);
+    if (roll || !b.eq.host_V || !b.eq.host_K) {
+        launch_chained(ctx, eq_stream_kernel<LC>, grid, dim3(kT), smem_short, b);
+    } else {
+        static thread_local EqVParam vp;                   // copied into the launch by cudaLaunchKernelEx
+        memcpy(vp.K, b.eq.host_K, sizeof vp.K);
+        memcpy(vp.V, b.eq.host_V, sizeof(double) * 8 * LC);
+        launch_chained(ctx, eq_stream_kernel_long<LC>, grid, dim3(kT), smem_long, b, vp);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) MXL_FAIL(MXL_ERR_CUDA, "launch of eq_stream_kernel<%d> failed: %s", LC, cudaGetErrorString(e));
     ctx->launches++;

@@ -16,7 +16,9 @@ constexpr int kT = kEqStreamThreads;
 
 // Shared memory next to the tile: the scan's exchange area and the plan's tables (EqDevTables, brought in by
 // load_tables with one round of coalesced loads per CTA).
-template <int LC>
+// HASV = false: the zero-pass table V stays out of shared memory (eq_stream_kernel's long-call variant takes it as
+// constant-bank operands from its kernel parameters: 4 KB less per CTA, which is the third resident CTA at LC = 64).
+template <int LC, bool HASV = true>
 struct alignas(16) EqShared {
     double2 agg[(kT / 32) * 4];                  // warp aggregates of the scan
     double2 fin[(kT / 32) * 4];                  // final value of every warp's lane 31
@@ -24,13 +26,13 @@ struct alignas(16) EqShared {
     double pow_lo[8][10];
     double pow_hi[8][10];
     double K[8];
-    double V[LC][8];
+    double V[HASV ? LC : 1][8];
 };
 
-template <int LC>
-__device__ __forceinline__ void load_tables(const EqDevTables* __restrict__ g, EqShared<LC>* s, int tid)
+template <int LC, bool HASV>
+__device__ __forceinline__ void load_tables(const EqDevTables* __restrict__ g, EqShared<LC, HASV>* s, int tid)
 {
-    for (int i = tid; i < LC * 8; i += kT) (&s->V[0][0])[i] = (&g->V[0][0])[i];
+    if (HASV) for (int i = tid; i < LC * 8; i += kT) (&s->V[0][0])[i] = (&g->V[0][0])[i];
     for (int i = tid; i < 2 * 10 * 32; i += kT) s->lane_pow[i] = (&g->lane_pow[0][0][0])[i];
     for (int i = tid; i < 160; i += kT) (&s->pow_lo[0][0])[i] = (&g->pow_lo[0][0])[i];    // pow_lo and pow_hi are adjacent in both
     if (tid < 8) s->K[tid] = g->K[tid];
@@ -111,8 +113,8 @@ __device__ __forceinline__ bool any_non_finite(const double v[8])
 // A^(l+1) P from a per-lane table.  Out: S = start state of this thread's chunk = inclusive value of the previous
 // thread (meaningless for thread 0, which owns a chunk only when it is the call's first: that one starts from the
 // module's stored state).  Two block barriers.
-template <int LC>
-__device__ __forceinline__ void scan_start_states(const EqStreamConsts& b, EqShared<LC>* sh, double v[8], double S[8], int tid)
+template <int LC, bool HASV>
+__device__ __forceinline__ void scan_start_states(const EqStreamConsts& b, EqShared<LC, HASV>* sh, double v[8], double S[8], int tid)
 {
     const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kT, 3) fused_voice_kernel(const __grid_constan
     if (owner) {
         const EqGains g{q.c_lo, q.c_hi, vc.g_lo, vc.g_mid, vc.g_hi};
         if (count == LC) {
-            eq_run_chunk_skewed<LC>(p, hist, row, g);
+            eq_run_chunk_skewed<LC, true>(p, hist, row, g);
         } else {                                           // ragged end of the call: one thread, sequential form
             float* mine = reinterpret_cast<float*>(tile);
             for (uint32_t j = 0; j < count; j++) {

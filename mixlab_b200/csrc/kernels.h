@@ -113,6 +113,8 @@ struct EqStreamConsts {
     uint32_t lev_lo, lev_hi;                     // scan levels per cascade (<= 8); levels >= 5 cross warps
     uint32_t back_lo, back_hi;                   // previous warps a warp's start states still hear (<= 3)
     const EqDevTables* tab;                      // device
+    const double (*host_V)[8];                   // HOST copies of V and K (the plan's, alive as long as the context): the
+    const double* host_K;                        // long-call variant of eq_stream_kernel takes them as kernel parameters
     double c_lo, c_hi;
 };
 struct EqStreamBatch {

@@ -858,6 +858,7 @@ static int fill_eq_consts(mxl_ctx* ctx, const mxl::EqStreamPlan& plan, k::EqStre
         if (e != cudaSuccess) { tab = nullptr; MXL_FAIL(MXL_ERR_CUDA, "EqThree tables: %s", cudaGetErrorString(e)); }
     }
     q->tab = (const k::EqDevTables*)tab;
+    q->host_V = plan.V; q->host_K = plan.K;
     q->c_lo = plan.c_lo; q->c_hi = plan.c_hi;
     return MXL_OK;
 }

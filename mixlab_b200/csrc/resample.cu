@@ -10,13 +10,15 @@
 // The stream is a pure function of everything pushed so far: any split into calls gives the same bits.  After N input
 // frames, ceil((N - H) L / M) output frames are determined (a latency of H input frames, 0.36 ms at 44.1 kHz).
 //
-// Kernel: a CTA owns 256 consecutive output frames; the input window they touch (256 M / L + 2H frames) is staged once in
-// shared memory AS f64 (one conversion per input sample instead of one per tap), i16 sources are unpacked on the way
-// (s / 32768, stream_input.rs:167-173); every thread then runs the 32 taps of its frame for all channels.  FP64-bound by
-// design (64 fma per stereo frame against 16 bytes of line traffic).
+// Kernel: outputs m and m + L share a phase, so a thread OWNS a phase: it loads its 32 coefficients once into registers
+// and walks the outputs m0 + p + L r, r = 0 .. R-1, of its block (consecutive lanes = consecutive outputs: coalesced
+// stores).  The input window the block touches (R M + 2H frames) is staged once in shared memory AS f64 (one conversion per
+// input sample instead of one per tap); i16 sources are unpacked on the way (s / 32768, stream_input.rs:167-173).
+// FP64-bound by design: 64 fma per stereo output frame against 15.4 bytes of line traffic.
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "kernels.h"
@@ -40,7 +42,10 @@ struct ResampleLaunch {
     uint64_t n_new;                        // new input frames
     uint64_t out_base;                     // absolute index of out[0]
     uint64_t n_out;
-    uint32_t L, M, channels, window;       // window = input frames a CTA stages (<= shared memory)
+    uint64_t block0;                       // absolute index (a multiple of L) of the first output of block 0
+    uint32_t L, M, channels;
+    uint32_t repeats;                      // R: outputs per thread; a block is L * R consecutive outputs
+    uint32_t window;                       // input frames a block stages: R * M + kRsTaps (+ slack)
 };
 
 __device__ __forceinline__ float fetch(const ResampleLaunch& p, int64_t n, uint32_t ch)
@@ -54,37 +59,48 @@ __device__ __forceinline__ float fetch(const ResampleLaunch& p, int64_t n, uint3
     return p.in_f32[(size_t)rel * p.channels + ch];
 }
 
+// grid (blocks, ceil(L / 256)): thread = phase.
+template <int CH>
 __global__ void __launch_bounds__(kRsThreads) resample_kernel(const ResampleLaunch p)
 {
-    extern __shared__ double rs_x[];                       // [window][channels]
-    const uint64_t m0 = p.out_base + (uint64_t)blockIdx.x * kRsThreads;
-    const int64_t n_first = (int64_t)((m0 * p.M) / p.L) - kRsH + 1;       // first input frame this CTA touches
-    for (uint32_t i = threadIdx.x; i < p.window * p.channels; i += kRsThreads) {
-        const uint32_t fr = i / p.channels, ch = i % p.channels;
-        rs_x[i] = (double)fetch(p, n_first + fr, ch);
+    extern __shared__ __align__(16) double rs_x[];         // [window][CH]
+    const uint64_t m0 = p.block0 + (uint64_t)blockIdx.x * p.L * p.repeats;     // a multiple of L
+    const int64_t n_first = (int64_t)(m0 / p.L) * p.M - kRsH + 1;              // first input frame this block touches
+    for (uint32_t i = threadIdx.x; i < p.window * CH; i += kRsThreads)
+        rs_x[i] = (double)fetch(p, n_first + i / CH, i % CH);
+    const uint32_t ph_idx = blockIdx.y * kRsThreads + threadIdx.x;             // output offset inside a run of L
+    double c[kRsTaps];
+    uint32_t x_off = 0;
+    if (ph_idx < p.L) {
+        const uint64_t pos = (uint64_t)ph_idx * p.M;                           // (m0 + ph_idx) * M = (m0 / L) * M * L + pos
+        const double* row = p.coef + (size_t)(pos % p.L) * kRsTaps;
+#pragma unroll
+        for (int kk = 0; kk < kRsTaps; kk++) c[kk] = __ldg(row + kk);
+        x_off = (uint32_t)(pos / p.L);                                         // n0 - (m0 / L) * M for r = 0
     }
     __syncthreads();
-    const uint64_t m = m0 + threadIdx.x;
-    if (m >= p.out_base + p.n_out) return;
-    const uint64_t pos = m * p.M;
-    const int64_t n0 = (int64_t)(pos / p.L);
-    const uint32_t phase = (uint32_t)(pos % p.L);
-    const double* c = p.coef + (size_t)phase * kRsTaps;
-    const double* x = rs_x + (size_t)(n0 - kRsH + 1 - n_first) * p.channels;
-    if (p.channels == 2) {
-        double a0 = 0.0, a1 = 0.0;
-#pragma unroll 8
-        for (int kk = 0; kk < kRsTaps; kk++) {
-            const double w = __ldg(c + kk);
-            a0 = fma(w, x[2 * kk], a0);
-            a1 = fma(w, x[2 * kk + 1], a1);
+    if (ph_idx >= p.L) return;
+    const uint64_t out_end = p.out_base + p.n_out;
+#pragma unroll 1
+    for (uint32_t r = 0; r < p.repeats; r++) {
+        const uint64_t m = m0 + ph_idx + (uint64_t)r * p.L;
+        if (m < p.out_base || m >= out_end) continue;
+        const double* x = rs_x + (size_t)(x_off + r * p.M) * CH;              // x[0] = input frame n0 - H + 1
+        if (CH == 2) {
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < kRsTaps; kk++) {
+                const double2 xv = *reinterpret_cast<const double2*>(x + 2 * kk);
+                a0 = fma(c[kk], xv.x, a0);
+                a1 = fma(c[kk], xv.y, a1);
+            }
+            *reinterpret_cast<float2*>(p.out + 2 * (m - p.out_base)) = make_float2((float)a0, (float)a1);
+        } else {
+            double a0 = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < kRsTaps; kk++) a0 = fma(c[kk], x[kk], a0);
+            p.out[m - p.out_base] = (float)a0;
         }
-        *reinterpret_cast<float2*>(p.out + 2 * (m - p.out_base)) = make_float2((float)a0, (float)a1);
-    } else {
-        double a0 = 0.0;
-#pragma unroll 8
-        for (int kk = 0; kk < kRsTaps; kk++) a0 = fma(__ldg(c + kk), x[kk], a0);
-        p.out[m - p.out_base] = (float)a0;
     }
 }
 
@@ -203,14 +219,25 @@ static int64_t resampler_push(mxl_resampler* r, const float* in_f32, const short
     p.in_f32 = in_f32; p.in_i16 = in_i16; p.hist = r->hist[r->cur]; p.out = out->dev; p.coef = r->coef;
     p.in_base = r->total_in; p.n_new = in_frames; p.out_base = r->total_out; p.n_out = n_out;
     p.L = r->L; p.M = r->M; p.channels = r->channels;
-    p.window = (uint32_t)(((uint64_t)k::kRsThreads * r->M + r->L - 1) / r->L + k::kRsTaps + 2);
+    // a block = L * R consecutive outputs starting at a multiple of L; R so that the staged window stays near 32 KB
+    p.repeats = std::max<uint32_t>(1u, std::min<uint32_t>(32u, 2048u / r->M));
+    p.window = p.repeats * r->M + k::kRsTaps + 2;
+    p.block0 = r->total_out / r->L * r->L;
     const size_t smem = (size_t)p.window * r->channels * sizeof(double);
     if (smem > 200 * 1024) MXL_FAIL(MXL_ERR_UNSUPPORTED, "mxl_resampler: ratio %u / %u needs a %zu-byte window", r->L, r->M, smem);
     MXL_TRY(ctx->compute_begin());
     if (n_out) {
-        if (smem > 48 * 1024) MXL_CUDA(cudaFuncSetAttribute(k::resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const uint64_t per_block = (uint64_t)r->L * p.repeats;
+        const unsigned blocks = (unsigned)((r->total_out + n_out - p.block0 + per_block - 1) / per_block);
+        dim3 grid(blocks, (r->L + k::kRsThreads - 1) / k::kRsThreads);
         MXL_TIMED(ctx, "resample_kernel");
-        k::resample_kernel<<<(unsigned)((n_out + k::kRsThreads - 1) / k::kRsThreads), k::kRsThreads, smem, ctx->stream>>>(p);
+        if (r->channels == 2) {
+            if (smem > 48 * 1024) MXL_CUDA(cudaFuncSetAttribute(k::resample_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k::resample_kernel<2><<<grid, k::kRsThreads, smem, ctx->stream>>>(p);
+        } else {
+            if (smem > 48 * 1024) MXL_CUDA(cudaFuncSetAttribute(k::resample_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k::resample_kernel<1><<<grid, k::kRsThreads, smem, ctx->stream>>>(p);
+        }
         if (cudaGetLastError() != cudaSuccess) MXL_FAIL(MXL_ERR_CUDA, "launch of resample_kernel failed");
         ctx->launches++;
     }

@@ -72,6 +72,37 @@ def main():
     run("Meter", mxl.MOD_METER, None, [stereo], [], 8 * S)
     run("PcmSink(pack i16)", mxl.MOD_PCM_SINK, None, [stereo], [], 12 * S)
     run("Mixer(2)", mxl.MOD_MIXER, [(0.0, 1.0, True), (-6.0, 0.5, False)], [stereo, o_s2], [o_s, ctx.line(mxl.LINE_STEREO, n)], 8 * S * 4)
+    if not args.only or args.only in "Resampler":
+        # audio sample-rate converter (self-specified): 44.1 kHz -> 48 kHz, stereo f32 line in, f32 line out
+        rs = ctx.resampler(44100, 48000, 2)
+        n_in = min(n, 1 << 24)
+        src_line = ctx.line(mxl.LINE_STEREO, n_in)
+        L = mxl.lib()
+        def push():
+            mxl.check(L.mxl_resampler_push_line(rs.h, src_line.h, rs.out.h))
+        ms, launches = timed(ctx, push, args.reps)
+        n_out = n_in * 160 // 147
+        nb = 8 * n_in + 8 * n_out
+        rows.append({"kernel": "Resampler 44.1k->48k stereo", "frames": n_in, "algorithmic_bytes": nb, "ms": ms, "gbs": nb / ms / 1e6,
+                     "frac_of_measured_peak": nb / ms / 1e6 / peak, "launches": launches,
+                     "note": "FP64-bound by design: 64 fma per output frame against 15.3 bytes of line traffic"})
+        print(json.dumps(rows[-1]), flush=True)
+        rs.close(); src_line.free()
+    if not args.only or args.only in "FusedVoiceMix":
+        # the fused voice group (BASELINE config 2's graph) on a call far larger than L2: 2^21 frames x 10 voices
+        d = W.config2_graph()
+        g, ids = W.build_graph(ctx, d)
+        T2 = (1 << 21) // 800
+        tick = [0]
+        def step():
+            g.run_ticks(tick[0], T2); tick[0] += T2
+        ms, launches = timed(ctx, step, args.reps)
+        nb = W.algorithmic_bytes_per_tick(d, 800) * T2
+        rows.append({"kernel": "FusedVoiceMix (config 2 graph, %d ticks per call)" % T2, "frames": T2 * 800, "algorithmic_bytes": nb, "ms": ms,
+                     "gbs": nb / ms / 1e6, "frac_of_measured_peak": nb / ms / 1e6 / peak, "launches": launches,
+                     "compulsory_bytes": T2 * (16 * 800 + 32), "note": "API-level bytes of the 32 modules it replaces (464*S per tick); FP64-bound"})
+        print(json.dumps(rows[-1]), flush=True)
+        g.destroy()
     if args.only and args.only not in "VideoMixer NOAUDIO":
         ctx.close()
         return
@@ -102,6 +133,11 @@ def main():
     ms, launches = timed(ctx, lambda: ctx.frames_to_rgba(fa, pics), args.reps)
     nb = T * (W.FRAME_BYTES + 1920 * 1080 * 4)
     print(json.dumps({"kernel": "frames_to_rgba 1080p x64", "algorithmic_bytes": nb, "ms": ms, "gbs": nb / ms / 1e6,
+                      "frac_of_measured_peak": nb / ms / 1e6 / peak, "launches": launches}), flush=True)
+    # the other direction: RGBA8 -> yuv420p (self-specified), 64 pictures per launch
+    ms, launches = timed(ctx, lambda: pics.to_frames(fa), args.reps)
+    nb = T * (W.FRAME_BYTES + 1920 * 1080 * 4)
+    print(json.dumps({"kernel": "rgba_to_yuv 1080p x64", "algorithmic_bytes": nb, "ms": ms, "gbs": nb / ms / 1e6,
                       "frac_of_measured_peak": nb / ms / 1e6 / peak, "launches": launches}), flush=True)
     pics.free()
     # tiled letterbox scaler: 32 frames per launch, 720p -> 1080p and 2160p -> 1080p (bytes: source read + scaled frame written)
