@@ -127,6 +127,11 @@ MXL_API mxl_ctx *mxl_ctx_create_on_stream(int device, uint32_t sample_rate, uint
                                           void *cuda_stream);
 MXL_API int mxl_ctx_destroy(mxl_ctx *ctx);
 MXL_API int mxl_ctx_synchronize(mxl_ctx *ctx);
+/* Released frame buffers are parked per size class for reuse (the reference mallocs a frame per tick,
+ * src/module/video_mixer.rs:150-160 via AvFrame::blank).  Frees parked buffers until at most keep_bytes remain
+ * (0 = everything; call it after a source changed resolution) and, when new_cap_bytes != 0, sets the cap beyond which a
+ * released buffer goes straight back to the driver (default 8 GiB).  freed_out (may be NULL) = bytes returned. */
+MXL_API int mxl_ctx_trim_frame_pool(mxl_ctx *ctx, uint64_t keep_bytes, uint64_t new_cap_bytes, uint64_t *freed_out);
 /* Copy/compute overlap for host-fed sessions.  When enabled, the *_async upload calls run on an
  * upload stream and the *_async download calls on a download stream, ordered against the compute
  * stream by events (upload waits for the last run, a run waits for the uploads and downloads enqueued

@@ -158,6 +158,7 @@ def lib():
         "mxl_ctx_create_on_stream": (vp, [i32, u32, u32, vp]),
         "mxl_ctx_destroy": (i32, [vp]),
         "mxl_ctx_synchronize": (i32, [vp]),
+        "mxl_ctx_trim_frame_pool": (i32, [vp, u64, u64, C.POINTER(u64)]),
         "mxl_ctx_set_copy_overlap": (i32, [vp, i32]),
         "mxl_ctx_download_fence": (i32, [vp, u32]),
         "mxl_ctx_wait_fence": (i32, [vp, u32]),
@@ -396,6 +397,12 @@ class Context:
 
     def synchronize(self):
         check(lib().mxl_ctx_synchronize(self.h))
+
+    def trim_frame_pool(self, keep_bytes=0, new_cap_bytes=0):
+        """Frees parked frame buffers down to keep_bytes; returns the bytes given back to the driver."""
+        freed = C.c_uint64(0)
+        check(lib().mxl_ctx_trim_frame_pool(self.h, keep_bytes, new_cap_bytes, C.byref(freed)))
+        return freed.value
 
     def set_copy_overlap(self, on):
         check(lib().mxl_ctx_set_copy_overlap(self.h, 1 if on else 0))

@@ -75,6 +75,8 @@ struct mxl_ctx {
     // free yuv420p frame buffers by byte size: frames come and go every tick (AvFrame::blank per
     // tick in the reference, video_mixer.rs:151), cudaMalloc/cudaFree must not.
     std::unordered_map<uint64_t, std::vector<uint8_t*>> frame_pool;
+    uint64_t frame_pool_bytes = 0;                    // bytes parked in frame_pool
+    uint64_t frame_pool_cap = 8ull << 30;             // beyond this a released frame goes back to the driver (mxl_ctx_trim_frame_pool)
     // EqThree chunk plans by chunk length (see modules.cu: eq_plan_for)
     std::map<uint32_t, std::vector<double>> eq_plans;
     // eq_stream_kernel plans by chunk length (eq_plan.h); ok == false = unusable at this sample rate

@@ -10,6 +10,8 @@
 #include <sys/syscall.h>
 #include <unistd.h>
 
+#include <algorithm>
+
 #include "common.h"
 #include "kernels.h"
 
@@ -191,6 +193,7 @@ mxl_frame* frame_alloc(mxl_ctx* ctx, uint32_t w, uint32_t h)
     if (pooled != ctx->frame_pool.end() && !pooled->second.empty()) {
         f->dev = pooled->second.back();      // same stream => reuse is ordered after the last use
         pooled->second.pop_back();
+        ctx->frame_pool_bytes -= f->layout.size;
         return f;
     }
     cudaError_t e = cudaMalloc(&f->dev, f->layout.size);
@@ -209,7 +212,14 @@ void frame_release(mxl_frame* f)
                 delete f->slab;
             }
         } else if (f->dev) {
-            f->ctx->frame_pool[f->layout.size].push_back(f->dev);
+            mxl_ctx* c = f->ctx;
+            if (c->frame_pool_bytes + f->layout.size > c->frame_pool_cap) {      // the pool is full: back to the driver
+                c->activate();
+                cudaFree(f->dev);             // synchronises with whatever still reads the frame
+            } else {
+                c->frame_pool[f->layout.size].push_back(f->dev);
+                c->frame_pool_bytes += f->layout.size;
+            }
         }
         delete f;
     }
@@ -489,6 +499,33 @@ int mxl_ctx_synchronize(mxl_ctx* ctx)
     MXL_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->stream_in) MXL_CUDA(cudaStreamSynchronize(ctx->stream_in));
     if (ctx->stream_out) MXL_CUDA(cudaStreamSynchronize(ctx->stream_out));
+    return MXL_OK;
+}
+
+// Frees pooled frame buffers until at most keep_bytes stay parked (size classes a session no longer uses -- its sources
+// changed resolution -- would otherwise stay allocated until the context dies), and sets the pool's cap.
+int mxl_ctx_trim_frame_pool(mxl_ctx* ctx, uint64_t keep_bytes, uint64_t new_cap_bytes, uint64_t* freed_out)
+{
+    if (!ctx) MXL_FAIL(MXL_ERR_INVALID, "NULL context");
+    uint64_t freed = 0;
+    if (ctx->has_device() && ctx->frame_pool_bytes > keep_bytes) {
+        MXL_TRY(mxl_ctx_synchronize(ctx));
+        // largest classes first: the ones a changed geometry left behind are usually not the smallest
+        std::vector<uint64_t> sizes;
+        for (auto& kv : ctx->frame_pool) if (!kv.second.empty()) sizes.push_back(kv.first);
+        std::sort(sizes.begin(), sizes.end(), [](uint64_t a, uint64_t b) { return a > b; });
+        for (uint64_t sz : sizes) {
+            auto& v = ctx->frame_pool[sz];
+            while (!v.empty() && ctx->frame_pool_bytes > keep_bytes) {
+                cudaFree(v.back());
+                v.pop_back();
+                ctx->frame_pool_bytes -= sz;
+                freed += sz;
+            }
+        }
+    }
+    if (new_cap_bytes) ctx->frame_pool_cap = new_cap_bytes;
+    if (freed_out) *freed_out = freed;
     return MXL_OK;
 }
 

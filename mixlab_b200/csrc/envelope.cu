@@ -4,21 +4,29 @@
 // the machine is "on" (TriggerOn) or not (Initial / TriggerOff): a gate sample == 1.0 switches
 // not-on to on, a gate sample == 0.0 switches on to not-on, every other sample is inert.  Hence
 //   (1) the class after sample i is the class of the last EVENT (sample that is exactly 1.0 or 0.0)
-//       at or before i -- "last event wins", a max-scan over keys (index+1)<<1 | class;
-//   (2) an event is a TRANSITION iff its class differs from the class just before it;
+//       at or before i;
+//   (2) an event is a TRANSITION iff its class differs from the class just before it, i.e. from the
+//       class of the event before it (or, for the first event of the call, from the stored state);
 //   (3) the machine state at sample i is fixed by the last transition p <= i (TriggerOn{on: p} or
 //       TriggerOff{off: p, ..}) and, for an off, the transition q before it:
-//       off_amplitude = amplitude(TriggerOn{on: q}, p) -- a "latest two" scan over transition keys.
-// Both scans have trivial combine steps (max / latest-two), so they run as decoupled look-back
-// scans inside ONE kernel: a CTA owns a tile of 2048 consecutive samples (16 per thread, read once
-// with four float4 loads), scans inside the tile with warp shuffles, publishes its tile aggregate,
-// and looks back over the preceding tiles 32 at a time (ballot + shuffle, no loops over lanes)
-// until the carry is decided: the nearest tile with any event decides scan (1), two transitions or
-// a tile whose inclusive value is known decide scan (3).  Every thread then starts the REFERENCE
-// state machine from its exact incoming state and walks its 16 samples, evaluating amplitude()
-// with the reference's f64 expressions (bit-exact: only IEEE +,-,*,/).
-// Line traffic is the algorithmic 8 B/sample; tile descriptors add 24 B per 2048 samples.  Tiles
-// are handed out by an atomic ticket, so a tile only ever waits for tiles that already run.
+//       off_amplitude = amplitude(TriggerOn{on: q}, p).
+// All of that follows from ONE associative summary of a run of samples, Seg = {first event, last
+// event, the latest two transitions among the events after the first}: joining two runs adds at most
+// the boundary transition (first event of the later run against the last event of the earlier one).
+// The kernel is therefore one decoupled look-back scan over Seg: a CTA owns a tile of 2048
+// consecutive samples (16 per thread, read once with four float4 loads), summarises and scans inside
+// the tile with warp shuffles, publishes the tile's Seg, and warp 0 looks back over the preceding
+// tiles 32 at a time (ballot + shuffle) until the carry is decided -- two transitions known (nothing
+// earlier can matter) or a tile whose published value already covers everything before it.  Every
+// thread then starts the REFERENCE state machine from its exact incoming state and walks its 16
+// samples, evaluating amplitude() with the reference's f64 expressions (bit-exact: only IEEE +,-,*,/).
+// Line traffic is the algorithmic 8 B/sample; tile descriptors add 32 B per 2048 samples.
+//
+// History: the first single-pass version ran (1) and (3) as two scans with two look-backs behind an atomic
+// ticket -- four dependent global round trips per CTA (ticket, samples, look-back, look-back) and five block
+// barriers; its warps sat at those barriers for 45 % of their samples.  One scan needs two round trips and two
+// barriers.  Tiles are taken in blockIdx order, which relies on CTAs being dispatched in index order (as
+// single-pass scans generally do); MXL_ENV_TICKET=1 brings the ticket back.
 #include <stdlib.h>
 
 #include "dsp_math.cuh"
@@ -30,22 +38,40 @@ namespace k {
 namespace {
 
 constexpr int kEnvThreads = 128;      // 256 threads: 0.126 ms, 128: 0.117 (0.110 at 16 CTAs per SM), 64: 0.120: more, smaller CTAs cover the look-backs
-constexpr int kEnvPerThread = 16;     // per 2^25 samples: 8 per thread 0.169 ms, 16: 0.117, 32: 0.155
-constexpr int kEnvTileSamples = kEnvThreads * kEnvPerThread;
 constexpr int kEnvWarps = kEnvThreads / 32;
 
 // event / transition key of sample idx (index inside the call): 0 = none; later samples have larger keys
-__device__ __forceinline__ uint32_t key_of(uint32_t idx, bool on) { return ((idx + 1u) << 1) | (on ? 1u : 0u); }
+__device__ __forceinline__ uint32_t key_of(uint32_t idx, uint32_t on) { return ((idx + 1u) << 1) | on; }
 __device__ __forceinline__ uint32_t key_idx(uint32_t key) { return (key >> 1) - 1u; }
 __device__ __forceinline__ bool key_on(uint32_t key) { return (key & 1u) != 0; }
 
-// latest two transitions, a later than b (0 = none); `x` earlier in time than `y`
-struct Top2 { uint32_t a, b; };
-__device__ __forceinline__ Top2 top2_combine(Top2 x, Top2 y)
+// Summary of a run of samples: F / L = its first / last event; a, b = the latest two transitions among the events
+// after F (a later than b; 0 = none) -- whether F itself is a transition depends on what came before the run.
+struct Seg { uint32_t F, L, a, b; };
+
+// x earlier in time than y.  Transitions in time order: x.b, x.a, boundary, y.b, y.a -- keep the latest two.
+__device__ __forceinline__ Seg seg_combine(const Seg x, const Seg y)
 {
-    if (y.a == 0u) return x;
-    if (y.b != 0u) return y;
-    return Top2{y.a, x.a};
+    const bool xh = x.L != 0u, yh = y.L != 0u;
+    const uint32_t boundary = (xh && ((x.L ^ y.F) & 1u)) ? y.F : 0u;   // y's first event changes the class x left (y.F = 0: none)
+    Seg r;
+    r.F = xh ? x.F : y.F;
+    r.L = yh ? y.L : x.L;
+    const uint32_t third = boundary ? boundary : x.a;                  // the latest transition before y's own
+    const uint32_t fourth = boundary ? x.a : x.b;
+    r.a = y.a ? y.a : third;
+    r.b = y.a ? (y.b ? y.b : third) : fourth;
+    return r;
+}
+// A Seg with two transitions is SATURATED: joined with anything later it stays saturated, and nothing earlier can
+// change its L, a, b -- only its F, which a saturated Seg's users never read.
+
+__device__ __forceinline__ Seg seg_shfl(const Seg s, int l)
+{
+    Seg o;
+    o.F = __shfl_sync(0xffffffffu, s.F, l); o.L = __shfl_sync(0xffffffffu, s.L, l);
+    o.a = __shfl_sync(0xffffffffu, s.a, l); o.b = __shfl_sync(0xffffffffu, s.b, l);
+    return o;
 }
 
 struct EnvParams { double sr, inv_sr, attack_ms, inv_attack, inv_decay, sustain, inv_release; };
@@ -74,47 +100,64 @@ __device__ __forceinline__ double amp_off(const EnvParams& p, uint64_t off, doub
     return off_amplitude * release_amplitude;
 }
 
-// Tile descriptors: 64-bit words (tag << 32 | value), tag = epoch << 2 | status, written and read
-// whole, so a word is either stale (other epoch), an aggregate or an inclusive value -- no fences.
+// Tile descriptors: four 64-bit words (tag << 32 | value), tag = epoch << 2 | status, each written and read whole, so a
+// word is either stale (other epoch), part of the tile's own summary (kAgg) or of its inclusive one (kIncl); a reader
+// retries until the four tags agree -- no fences.
 constexpr uint32_t kAgg = 1u, kIncl = 2u;
 
-__device__ __forceinline__ unsigned long long ld_word(const unsigned long long* p)
+__device__ __forceinline__ void st_seg(EnvTile* d, uint32_t tag, const Seg s)
 {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_word(unsigned long long* p, uint32_t tag, uint32_t value)
-{
-    const unsigned long long v = ((unsigned long long)tag << 32) | value;
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+    const unsigned long long t = (unsigned long long)tag << 32;
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" :: "l"(&d->w[0]), "l"(t | s.F), "l"(t | s.L) : "memory");
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" :: "l"(&d->w[2]), "l"(t | s.a), "l"(t | s.b) : "memory");
 }
 
-// spins until the word carries this launch's epoch; returns status, value through *value
-__device__ __forceinline__ uint32_t wait_word(const unsigned long long* p, uint32_t epoch, uint32_t* value)
+// one look at a descriptor: true once its four words carry this launch's epoch and one status
+__device__ __forceinline__ bool try_seg(const EnvTile* d, uint32_t epoch, Seg* s, uint32_t* status)
 {
-    unsigned long long v;
-    do { v = ld_word(p); } while ((uint32_t)(v >> 34) != epoch);
-    *value = (uint32_t)v;
-    return (uint32_t)(v >> 32) & 3u;
+    unsigned long long w0, w1, w2, w3;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(&d->w[0]) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "l"(&d->w[2]) : "memory");
+    const uint32_t t0 = (uint32_t)(w0 >> 32), t1 = (uint32_t)(w1 >> 32), t2 = (uint32_t)(w2 >> 32), t3 = (uint32_t)(w3 >> 32);
+    if ((t0 >> 2) != epoch || t0 != t1 || t0 != t2 || t0 != t3) return false;
+    s->F = (uint32_t)w0; s->L = (uint32_t)w1; s->a = (uint32_t)w2; s->b = (uint32_t)w3;
+    *status = t0 & 3u;
+    return true;
 }
 
-__global__ void __launch_bounds__(kEnvThreads, 16) envelope_kernel(const __grid_constant__ EnvBatch b)
+__device__ __forceinline__ int top_bit(uint32_t m) { return 31 - __clz(m); }
+
+// a thread's outputs, four at a time: f(j) -> sample j; every float4 leaves as soon as it is formed
+template <int PT, class F>
+__device__ __forceinline__ void emit(float* out, F f)
 {
+#pragma unroll
+    for (int v = 0; v < PT / 4; v++) {
+        float4 y;
+        y.x = f(4 * v); y.y = f(4 * v + 1); y.z = f(4 * v + 2); y.w = f(4 * v + 3);
+        *reinterpret_cast<float4*>(out + 4 * v) = y;
+    }
+}
+
+// PT = samples per thread (16 or 32); a tile = kEnvThreads * PT samples
+template <bool TICKET, int MINB, int PT>
+__global__ void __launch_bounds__(kEnvThreads, MINB) envelope_kernel(const __grid_constant__ EnvBatch b)
+{
+    constexpr int kEnvPerThread = PT, kEnvTileSamples = kEnvThreads * PT;
     pdl_prologue();
     const EnvInst& in = b.inst[blockIdx.y];
     __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_ev[kEnvWarps];                  // per-warp last-event key
-    __shared__ Top2 s_tr[kEnvWarps];                      // per-warp latest two transitions
-    __shared__ uint32_t s_ev_in;                          // last-event key before the tile (0 = none in this call)
-    __shared__ Top2 s_tr_in;                              // latest two transitions before the tile
+    __shared__ Seg s_seg[kEnvWarps];                      // per-warp summaries
+    __shared__ Seg s_in;                                  // summary of everything in this call before the tile
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = (uint32_t)(atomicAdd(in.ticket, 1ull) - in.ticket_base);
-    __syncthreads();
-    const uint32_t tile = s_tile;
+    uint32_t tile = blockIdx.x;
+    if (TICKET) {
+        if (tid == 0) s_tile = (uint32_t)(atomicAdd(in.ticket, 1ull) - in.ticket_base);
+        __syncthreads();
+        tile = s_tile;
+    }
     EnvTile* const desc = in.tiles + tile;
     const EnvParams p{b.sample_rate, b.inv_sample_rate, in.attack_ms, in.inv_attack, in.inv_decay, in.sustain, in.inv_release};
-    const EnvState st0 = *in.state;                        // machine state before the call
 
     // ---- my samples ----
     const uint64_t base = (uint64_t)tile * kEnvTileSamples + (uint64_t)tid * kEnvPerThread;
@@ -130,151 +173,162 @@ __global__ void __launch_bounds__(kEnvThreads, 16) envelope_kernel(const __grid_
         for (int j = 0; j < kEnvPerThread; j++)            // disconnected input = zeros (io.rs:8-9); past the end = inert
             x[j] = base + j < b.frames ? (in.in ? in.in[base + j] : 0.0f) : 2.0f;
     }
+    const EnvState st0 = *in.state;                        // machine state before the call
 
-    // ---- scan 1: last event.  envelope.rs:101,106: exact float ==, so -0.0 counts as 0.0 ----
+    // ---- my summary.  envelope.rs:101,106: exact float ==, so -0.0 counts as 0.0 ----
     uint32_t on_mask = 0, off_mask = 0;                    // bit j: sample j is exactly 1.0 / 0.0
 #pragma unroll
     for (int j = 0; j < kEnvPerThread; j++) {
         on_mask |= (x[j] == 1.0f ? 1u : 0u) << j;
         off_mask |= (x[j] == 0.0f ? 1u : 0u) << j;
     }
-    uint32_t ev = 0;
-    if (on_mask | off_mask) {
-        const int j = 31 - __clz(on_mask | off_mask);
-        ev = key_of((uint32_t)(base + j), (on_mask >> j) & 1u);
-    }
-    uint32_t ev_incl = ev;
+    const uint32_t E = on_mask | off_mask;
+    uint32_t Tm = 0;                                       // events (after my first) whose class differs from the event before
+    Seg me{0u, 0u, 0u, 0u};
+    if (E) {
+        // class of the nearest event at or below each bit, by doubling (a bit is filled from the nearest event below it
+        // because nearer events reach it in earlier, shorter steps)
+        uint32_t val = on_mask, known = E;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) ev_incl = max(ev_incl, __shfl_up_sync(0xffffffffu, ev_incl, d));
-    uint32_t ev_excl = __shfl_up_sync(0xffffffffu, ev_incl, 1);
-    if (lane == 0) ev_excl = 0;
-    if (lane == 31) s_ev[warp] = ev_incl;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t agg = 0;
-#pragma unroll
-        for (int w = 0; w < kEnvWarps; w++) agg = max(agg, s_ev[w]);
-        uint32_t carry = 0;                                // last event before the tile, inside this call
-        if (tile != 0) {
-            // a tile with an event decides everything after it: its aggregate is already inclusive
-            if (lane == 0) st_word(&desc->ev, (b.epoch << 2) | (agg ? kIncl : kAgg), agg);
-            int64_t j = (int64_t)tile - 1;
-            for (;;) {
-                const int64_t mj = j - lane;
-                uint32_t status = kIncl, val = 0;          // before the call: inclusive "none"
-                if (mj >= 0) status = wait_word(&in.tiles[mj].ev, b.epoch, &val);
-                const uint32_t decided = __ballot_sync(0xffffffffu, status == kIncl);
-                if (decided) {                             // nearest decided tile; the ones nearer had no event
-                    carry = __shfl_sync(0xffffffffu, val, __ffs(decided) - 1);
-                    break;
-                }
-                j -= 32;
-            }
-            if (agg == 0 && lane == 0) st_word(&desc->ev, (b.epoch << 2) | kIncl, carry);
-        } else if (lane == 0) {
-            st_word(&desc->ev, (b.epoch << 2) | kIncl, agg);
+        for (int s = 1; s < kEnvPerThread; s <<= 1) {
+            val |= (val << s) & ~known;
+            known |= known << s;
         }
-        if (lane == 0) s_ev_in = carry;
+        Tm = E & (known << 1) & ((val << 1) ^ on_mask) & (PT == 32 ? 0xffffffffu : ((1u << (PT & 31)) - 1u));
+        const int f0 = __ffs(E) - 1, l0 = top_bit(E);
+        me.F = key_of((uint32_t)base + f0, (on_mask >> f0) & 1u);
+        me.L = key_of((uint32_t)base + l0, (on_mask >> l0) & 1u);
+        if (Tm) {
+            const int h = top_bit(Tm);
+            me.a = key_of((uint32_t)base + h, (on_mask >> h) & 1u);
+            const uint32_t rest = Tm & ~(1u << h);
+            if (rest) {
+                const int h2 = top_bit(rest);
+                me.b = key_of((uint32_t)base + h2, (on_mask >> h2) & 1u);
+            }
+        }
     }
-    __syncthreads();
-    // class just before my first sample
-    uint32_t before = s_ev_in;
-    for (int w = 0; w < warp; w++) before = max(before, s_ev[w]);
-    before = max(before, ev_excl);
-    bool cls = before ? key_on(before) : (st0.state == 1);
 
-    // ---- scan 3: latest two transitions ----
-    Top2 tr{0u, 0u};
-    if ((cls ? off_mask : on_mask) != 0u) {                // an event of the other class: at least one transition
-#pragma unroll
-        for (int j = 0; j < kEnvPerThread; j++) {
-            const bool on = (on_mask >> j) & 1u, off = (off_mask >> j) & 1u;
-            if ((on && !cls) || (off && cls)) {
-                tr.b = tr.a;
-                tr.a = key_of((uint32_t)(base + j), on);
-                cls = on;
-            }
-        }
+    // ---- inside the warp: ballots instead of a scan ----
+    // Every lane learns the class of the last event before it from two ballots, hence whether its first event is a
+    // transition; the latest two transitions before a lane are then found with two more ballots (lanes with >= 1 / >= 2
+    // transitions) and three shuffles from lanes picked by bit scans.  The warp's first event stays apart: whether it is a
+    // transition depends on what came before the warp.
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t H = __ballot_sync(0xffffffffu, E != 0u);
+    const uint32_t CL = __ballot_sync(0xffffffffu, E != 0u && (me.L & 1u));
+    const uint32_t Hb = H & lt;                            // lanes before me with events
+    const bool e_has = Hb != 0u;
+    const bool e_cls = e_has && ((CL >> top_bit(Hb | 1u)) & 1u) && Hb != 0u;     // class of the last event before me in the warp
+    uint32_t wa = me.a, wb = me.b;                          // my latest two warp-internal transitions
+    if (e_has && E != 0u && ((me.F & 1u) != 0u) != e_cls) {  // my first event changes the class the lanes before me left
+        if (wa == 0u) wa = me.F;
+        else if (wb == 0u) wb = me.F;
     }
-    Top2 tr_incl = tr;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        Top2 o;
-        o.a = __shfl_up_sync(0xffffffffu, tr_incl.a, d);
-        o.b = __shfl_up_sync(0xffffffffu, tr_incl.b, d);
-        if (lane >= d) tr_incl = top2_combine(o, tr_incl);
+    const uint32_t T1 = __ballot_sync(0xffffffffu, wa != 0u), T2 = __ballot_sync(0xffffffffu, wb != 0u);
+    // latest two among lanes selected by `m` (lanes before me: m = lt; the whole warp: m = ~0)
+    uint32_t e_a, e_b, g_a, g_b;
+    {
+        const uint32_t m1 = T1 & lt;
+        const int q1 = top_bit(m1 | 1u);
+        const uint32_t m2 = m1 & ~(1u << q1);
+        const int q2 = top_bit(m2 | 1u);
+        const uint32_t a1 = __shfl_sync(0xffffffffu, wa, q1), b1 = __shfl_sync(0xffffffffu, wb, q1), a2 = __shfl_sync(0xffffffffu, wa, q2);
+        e_a = m1 ? a1 : 0u;
+        e_b = m1 ? (((T2 >> q1) & 1u) ? b1 : (m2 ? a2 : 0u)) : 0u;
     }
-    Top2 tr_excl;
-    tr_excl.a = __shfl_up_sync(0xffffffffu, tr_incl.a, 1);
-    tr_excl.b = __shfl_up_sync(0xffffffffu, tr_incl.b, 1);
-    if (lane == 0) tr_excl = Top2{0u, 0u};
-    if (lane == 31) s_tr[warp] = tr_incl;
+    {
+        const int q1 = top_bit(T1 | 1u);
+        const uint32_t m2 = T1 & ~(1u << q1);
+        const int q2 = top_bit(m2 | 1u);
+        const uint32_t a1 = __shfl_sync(0xffffffffu, wa, q1), b1 = __shfl_sync(0xffffffffu, wb, q1), a2 = __shfl_sync(0xffffffffu, wa, q2);
+        g_a = T1 ? a1 : 0u;
+        g_b = T1 ? (((T2 >> q1) & 1u) ? b1 : (m2 ? a2 : 0u)) : 0u;
+    }
+    const uint32_t Fw = __shfl_sync(0xffffffffu, me.F, __ffs(H | 0x80000000u) - 1);     // the warp's first / last event
+    const uint32_t Lw = __shfl_sync(0xffffffffu, me.L, top_bit(H | 1u));
+    if (lane == 0) s_seg[warp] = H ? Seg{Fw, Lw, g_a, g_b} : Seg{0u, 0u, 0u, 0u};
     __syncthreads();
+
+    // ---- look-back (warp 0) ----
     if (warp == 0) {
-        Top2 agg{0u, 0u};
+        Seg agg = s_seg[0];
 #pragma unroll
-        for (int w = 0; w < kEnvWarps; w++) agg = top2_combine(agg, s_tr[w]);
-        Top2 carry{0u, 0u};
+        for (int w = 1; w < kEnvWarps; w++) agg = seg_combine(agg, s_seg[w]);
+        Seg carry{0u, 0u, 0u, 0u};
         if (tile != 0) {
-            const bool full = agg.b != 0u;                 // two transitions of its own: inclusive as it stands
-            if (lane == 0) {
-                st_word(&desc->tr_a, (b.epoch << 2) | (full ? kIncl : kAgg), agg.a);
-                st_word(&desc->tr_b, (b.epoch << 2) | (full ? kIncl : kAgg), agg.b);
-            }
+            const bool full = agg.b != 0u;                 // saturated: inclusive as it stands
+            if (lane == 0) st_seg(desc, (b.epoch << 2) | (full ? kIncl : kAgg), agg);
+            // Lane l looks at tile j - l.  Only the NEAREST tiles matter (until two transitions are known), so the walk never
+            // waits for a far tile: it folds the contiguous run of published descriptors from lane 0 on, and looks again
+            // only while that run has not decided the carry.
             int64_t j = (int64_t)tile - 1;
-            for (;;) {
+            bool decided = false;
+            while (!decided) {
                 const int64_t mj = j - lane;
-                uint32_t status = kIncl, va = 0, vb = 0;   // before the call: inclusive "none"
-                if (mj >= 0) {
-                    uint32_t sa, sb;
-                    do {                                   // the two words of a descriptor change status one after the other
-                        sa = wait_word(&in.tiles[mj].tr_a, b.epoch, &va);
-                        sb = wait_word(&in.tiles[mj].tr_b, b.epoch, &vb);
-                    } while (sa != sb);
-                    status = sa;
+                bool ready = mj < 0;                       // before the call: inclusive "nothing"
+                uint32_t status = kIncl;
+                Seg d{0u, 0u, 0u, 0u};
+                int folded = 0;                            // lanes 0 .. folded-1 are in `carry`
+                for (;;) {
+                    if (!ready) ready = try_seg(in.tiles + mj, b.epoch, &d, &status);
+                    const uint32_t rdy = __ballot_sync(0xffffffffu, ready);
+                    const int n_ready = rdy == 0xffffffffu ? 32 : __ffs(~rdy) - 1;       // published tiles, counted from the nearest
+                    if (n_ready > folded) {
+                        const uint32_t window = (n_ready == 32 ? 0xffffffffu : ((1u << n_ready) - 1u)) & ~((1u << folded) - 1u);
+                        const uint32_t has = __ballot_sync(0xffffffffu, ready && d.L != 0u) & window;
+                        const uint32_t inc = __ballot_sync(0xffffffffu, ready && status == kIncl) & window;
+                        const int stop = inc ? __ffs(inc) - 1 : 32;                       // nearest inclusive tile
+                        const uint32_t reach = stop >= 31 ? 0xffffffffu : ((2u << stop) - 1u);   // lanes 0..stop
+                        uint32_t cand = has & reach;
+                        while (cand && carry.b == 0u) {    // from the nearest tile back: join until saturated
+                            const int l = __ffs(cand) - 1;
+                            carry = seg_combine(seg_shfl(d, l), carry);
+                            cand &= cand - 1u;
+                        }
+                        if (carry.b != 0u || inc) { decided = true; break; }
+                        folded = n_ready;
+                        if (folded == 32) break;           // the whole batch had nothing decisive: 32 tiles further back
+                    }
                 }
-                // walk from the nearest tile back: collect transitions until two are known or a tile is inclusive
-                const uint32_t has = __ballot_sync(0xffffffffu, va != 0u);
-                const uint32_t incl = __ballot_sync(0xffffffffu, status == kIncl);
-                const int stop = incl ? __ffs(incl) - 1 : 32;          // nearest inclusive tile
-                const uint32_t reach = stop >= 31 ? 0xffffffffu : ((2u << stop) - 1u);   // lanes 0..stop
-                uint32_t cand = has & reach;
-                while (cand && carry.b == 0u) {
-                    const int l = __ffs(cand) - 1;
-                    const uint32_t la = __shfl_sync(0xffffffffu, va, l), lb = __shfl_sync(0xffffffffu, vb, l);
-                    if (carry.a == 0u) { carry.a = la; carry.b = lb; }
-                    else carry.b = la;
-                    cand &= cand - 1u;
-                }
-                if (carry.b != 0u || incl) break;
                 j -= 32;
             }
-            if (!full && lane == 0) {
-                const Top2 inc = top2_combine(carry, agg);
-                st_word(&desc->tr_a, (b.epoch << 2) | kIncl, inc.a);
-                st_word(&desc->tr_b, (b.epoch << 2) | kIncl, inc.b);
-            }
+            if (!full && lane == 0) st_seg(desc, (b.epoch << 2) | kIncl, seg_combine(carry, agg));
         } else if (lane == 0) {
-            st_word(&desc->tr_a, (b.epoch << 2) | kIncl, agg.a);
-            st_word(&desc->tr_b, (b.epoch << 2) | kIncl, agg.b);
+            st_seg(desc, (b.epoch << 2) | kIncl, agg);
         }
-        if (lane == 0) s_tr_in = carry;
+        if (lane == 0) s_in = carry;
     }
     __syncthreads();
-    Top2 tin = s_tr_in;
-    for (int w = 0; w < warp; w++) tin = top2_combine(tin, s_tr[w]);
-    tin = top2_combine(tin, tr_excl);
+
+    // ---- everything in this call before my first sample ----
+    Seg P = s_in;                                          // ... before my warp
+    for (int w = 0; w < warp; w++) P = seg_combine(P, s_seg[w]);
+    const bool c0 = st0.state == 1;                        // class the call starts in
+    const bool cls_w = P.L ? key_on(P.L) : c0;             // class just before my warp's first sample
+    // latest two transitions before my warp: P's own, then P's first event if it changed the stored class
+    const uint32_t first_tr = (P.F != 0u && key_on(P.F) != c0) ? P.F : 0u;
+    const uint32_t pw_a = P.a ? P.a : first_tr;
+    const uint32_t pw_b = P.a ? (P.b ? P.b : first_tr) : 0u;
+    // ... then, inside the warp, its first event (if before me and a transition) and the warp-internal ones before me
+    const uint32_t fw_tr = (e_has && key_on(Fw) != cls_w) ? Fw : 0u;
+    const uint32_t third = fw_tr ? fw_tr : pw_a, fourth = fw_tr ? pw_a : pw_b;
+    const uint32_t tin_a = e_a ? e_a : third;
+    const uint32_t tin_b = e_a ? (e_b ? e_b : third) : fourth;
+    const bool cls = e_has ? e_cls : cls_w;                // class just before my first sample
+    // a transition among my own samples: one of Tm, or my first event against cls
+    const bool own_transition = Tm != 0u || (E != 0u && ((me.F & 1u) != 0u) != cls);
 
     // ---- machine state before my first sample ----
     EnvState s = st0;
-    if (tin.a != 0u) {
-        s.seq = b.t0 + key_idx(tin.a);
-        if (key_on(tin.a)) {
+    if (tin_a != 0u) {
+        s.seq = b.t0 + key_idx(tin_a);
+        if (key_on(tin_a)) {
             s.state = 1;
         } else {
             // envelope.rs:108-112: off_amplitude = amplitude(TriggerOn{on}, off); the class before an off
             // transition is "on": the transition before it, or the incoming TriggerOn of the call
-            const uint64_t on = tin.b != 0u ? b.t0 + key_idx(tin.b) : st0.seq;
+            const uint64_t on = tin_b != 0u ? b.t0 + key_idx(tin_b) : st0.seq;
             s.state = 2;
             s.off_amplitude = amp_on(p, on, s.seq);
         }
@@ -282,59 +336,119 @@ __global__ void __launch_bounds__(kEnvThreads, 16) envelope_kernel(const __grid_
 
     // ---- outputs ----
     const uint64_t seq0 = b.t0 + base;
-    if (tr.a == 0u && base + kEnvPerThread <= b.frames && seq0 + kEnvPerThread - s.seq < (1ull << 53) &&
-        (reinterpret_cast<uintptr_t>(in.out) & 15) == 0) {
+    const bool fast = !own_transition && base + kEnvPerThread <= b.frames && seq0 + kEnvPerThread - s.seq < (1ull << 53) &&
+                      (reinterpret_cast<uintptr_t>(in.out) & 15) == 0;
+    if (fast) {
         // no transition among my samples: the machine keeps state s; amplitude() (envelope.rs:33-58) per
-        // sample with the elapsed sample count stepped in f64 (exact below 2^53)
-        float y[kEnvPerThread];
+        // sample with the elapsed sample count stepped in f64 (exact below 2^53).  ms grows with the sample
+        // index (every step of its evaluation is monotone), so the branch amplitude() takes at my first and
+        // last sample is the branch of all sixteen: the other arm's arithmetic is skipped, the results are the same bits.
+        float* const o = in.out + base;
         if (s.state == 1) {
             const double d0 = (double)(seq0 - s.seq), rest = 1.0 - p.sustain;
-#pragma unroll
-            for (int j = 0; j < kEnvPerThread; j++) {
-                const double ms = div_by_const(d0 + (double)j, p.sr, p.inv_sr) * 1000.0;
-                const double decay_amplitude = 1.0 - clamp01(p.inv_decay * (ms - p.attack_ms));
-                y[j] = (float)(ms < p.attack_ms ? p.inv_attack * ms : p.sustain + (rest * decay_amplitude));
+            const double ms_first = div_by_const(d0, p.sr, p.inv_sr) * 1000.0;
+            const double ms_last = div_by_const(d0 + (double)(kEnvPerThread - 1), p.sr, p.inv_sr) * 1000.0;
+            auto ms_of = [&](int j) { return div_by_const(d0 + (double)j, p.sr, p.inv_sr) * 1000.0; };
+            if (ms_last < p.attack_ms) {                   // attack
+                emit<PT>(o, [&](int j) { return (float)(p.inv_attack * ms_of(j)); });
+            } else if (!(ms_first < p.attack_ms)) {        // decay / sustain
+                // x = inv_decay * (ms - attack) grows with the sample index when inv_decay >= 0: clamp(x) is 1 for all
+                // sixteen, or x itself for all sixteen, when it is so at the ends
+                const double x_first = p.inv_decay * (ms_first - p.attack_ms), x_last = p.inv_decay * (ms_last - p.attack_ms);
+                if (p.inv_decay >= 0.0 && x_first > 1.0) {
+                    const float c = (float)(p.sustain + (rest * (1.0 - 1.0)));
+                    emit<PT>(o, [&](int) { return c; });
+                } else if (p.inv_decay >= 0.0 && x_first >= 0.0 && x_last <= 1.0) {
+                    emit<PT>(o, [&](int j) { return (float)(p.sustain + (rest * (1.0 - (p.inv_decay * (ms_of(j) - p.attack_ms))))); });
+                } else {
+                    emit<PT>(o, [&](int j) { return (float)(p.sustain + (rest * (1.0 - clamp01(p.inv_decay * (ms_of(j) - p.attack_ms))))); });
+                }
+            } else {                                       // the attack ends among my samples
+                emit<PT>(o, [&](int j) {
+                    const double ms = ms_of(j);
+                    const double decay_amplitude = 1.0 - clamp01(p.inv_decay * (ms - p.attack_ms));
+                    return (float)(ms < p.attack_ms ? p.inv_attack * ms : p.sustain + (rest * decay_amplitude));
+                });
             }
         } else if (s.state == 2) {
             const double d0 = (double)(seq0 - s.seq);
-#pragma unroll
-            for (int j = 0; j < kEnvPerThread; j++) {
-                const double ms = div_by_const(d0 + (double)j, p.sr, p.inv_sr) * 1000.0;
-                y[j] = (float)(s.off_amplitude * (1.0 - clamp01(p.inv_release * ms)));
+            auto ms_of = [&](int j) { return div_by_const(d0 + (double)j, p.sr, p.inv_sr) * 1000.0; };
+            const double x_first = p.inv_release * ms_of(0), x_last = p.inv_release * ms_of(kEnvPerThread - 1);
+            if (p.inv_release >= 0.0 && x_first > 1.0) {
+                const float c = (float)(s.off_amplitude * (1.0 - 1.0));            // released: the clamp holds from here on
+                emit<PT>(o, [&](int) { return c; });
+            } else if (p.inv_release >= 0.0 && x_first >= 0.0 && x_last <= 1.0) {  // the clamp is the identity for all sixteen
+                emit<PT>(o, [&](int j) { return (float)(s.off_amplitude * (1.0 - (p.inv_release * ms_of(j)))); });
+            } else {
+                emit<PT>(o, [&](int j) { return (float)(s.off_amplitude * (1.0 - clamp01(p.inv_release * ms_of(j)))); });
             }
         } else {
-#pragma unroll
-            for (int j = 0; j < kEnvPerThread; j++) y[j] = 0.f;
+            emit<PT>(o, [&](int) { return 0.f; });
         }
-#pragma unroll
-        for (int v = 0; v < kEnvPerThread / 4; v++)
-            *reinterpret_cast<float4*>(in.out + base + 4 * v) = make_float4(y[4 * v], y[4 * v + 1], y[4 * v + 2], y[4 * v + 3]);
         if (base + kEnvPerThread == b.frames) *in.state_out = s;
-    } else {
-        // the reference state machine, sample by sample (envelope.rs:96-117)
-#pragma unroll 1
-        for (int j = 0; j < kEnvPerThread; j++) {
-            const uint64_t i = base + j;
-            if (i >= b.frames) break;
+    }
+    // Threads with a transition among their samples (or at the ragged end of the call): the reference state machine
+    // (envelope.rs:96-117), one SAMPLE per lane -- the warp takes such a thread's samples together instead of leaving one
+    // lane to walk them while 31 wait.  The machine state at sample k follows from the thread's own transitions at or
+    // below k (bit scans): none -> the incoming state; the last one an "on" -> TriggerOn{that sample}; an "off" ->
+    // TriggerOff{that sample, amplitude(TriggerOn{the transition before it, or the incoming on}, that sample)}.
+    const uint32_t own = Tm | ((E != 0u && ((me.F & 1u) != 0u) != cls) ? (E & (0u - E)) : 0u);   // my transitions, given cls
+    uint32_t slow = __ballot_sync(0xffffffffu, !fast && base < b.frames);
+    while (slow) {
+        const int l = __ffs(slow) - 1;
+        slow &= slow - 1u;
+        const uint32_t M = __shfl_sync(0xffffffffu, own, l), onm = __shfl_sync(0xffffffffu, on_mask, l);
+        const int st = __shfl_sync(0xffffffffu, s.state, l);
+        const uint64_t sseq = __shfl_sync(0xffffffffu, (unsigned long long)s.seq, l);
+        const double soff = __shfl_sync(0xffffffffu, s.off_amplitude, l);
+        const uint64_t base_l = base + (uint64_t)((int64_t)(l - lane) * kEnvPerThread);
+        for (int k = lane; k < kEnvPerThread; k += 32) {
+            const uint64_t i = base_l + k;
+            if (i >= b.frames) continue;
             const uint64_t seq = b.t0 + i;
-            if (s.state != 1) {
-                if ((on_mask >> j) & 1u) { s.state = 1; s.seq = seq; }
-            } else if ((off_mask >> j) & 1u) {
-                s.off_amplitude = amp_on(p, s.seq, seq);
-                s.state = 2; s.seq = seq;
+            const uint32_t Mk = M & ((2u << k) - 1u);      // transitions at or below sample k
+            int state = st;
+            uint64_t start = sseq;
+            double offa = soff;
+            if (Mk) {
+                const int t = top_bit(Mk);
+                start = b.t0 + base_l + t;
+                if ((onm >> t) & 1u) {
+                    state = 1;
+                } else {
+                    const uint32_t before = Mk & ~(1u << t);
+                    const uint64_t on = before ? b.t0 + base_l + top_bit(before) : sseq;
+                    state = 2;
+                    offa = amp_on(p, on, start);           // envelope.rs:108-112
+                }
             }
             double a = 0.0;                                // Initial
-            if (s.state == 1) a = amp_on(p, s.seq, seq);
-            else if (s.state == 2) a = amp_off(p, s.seq, s.off_amplitude, seq);
+            if (state == 1) a = amp_on(p, start, seq);
+            else if (state == 2) a = amp_off(p, start, offa, seq);
             in.out[i] = (float)a;
-            if (i + 1 == b.frames) *in.state_out = s;
+            if (i + 1 == b.frames) {
+                EnvState so;
+                so.state = state; so._pad = 0; so.seq = start; so.off_amplitude = offa;
+                *in.state_out = so;
+            }
         }
     }
 }
 
 }  // namespace
 
-uint32_t envelope_tiles(uint64_t frames) { return (uint32_t)((frames + kEnvTileSamples - 1) / kEnvTileSamples); }
+// samples per thread and CTAs per SM (tuning: MXL_ENV_PT = 16 | 32, MXL_ENV_MINB = 8 | 12 | 16)
+static int env_pt()
+{
+    static const int pt = (getenv("MXL_ENV_PT") && atoi(getenv("MXL_ENV_PT")) == 32) ? 32 : 16;
+    return pt;
+}
+
+uint32_t envelope_tiles(uint64_t frames)
+{
+    const uint64_t tile = (uint64_t)kEnvThreads * env_pt();
+    return (uint32_t)((frames + tile - 1) / tile);
+}
 
 int launch_envelope(mxl_ctx* ctx, const EnvBatch& b)
 {
@@ -344,7 +458,19 @@ int launch_envelope(mxl_ctx* ctx, const EnvBatch& b)
     if (b.frames >= 0x7ffffff0ull) MXL_FAIL(MXL_ERR_LENGTH, "Envelope: call longer than 2^31 samples");
     dim3 grid(envelope_tiles(b.frames), b.n);
     MXL_TIMED(ctx, "envelope_kernel");
-    launch_chained(ctx, envelope_kernel, grid, dim3(kEnvThreads), 0, b);
+    static const bool ticket = getenv("MXL_ENV_TICKET") && atoi(getenv("MXL_ENV_TICKET")) != 0;
+    static const int minb = getenv("MXL_ENV_MINB") ? atoi(getenv("MXL_ENV_MINB")) : 12;
+    const dim3 block(kEnvThreads);
+    if (env_pt() == 32) {
+        if (minb == 8) launch_chained(ctx, envelope_kernel<false, 8, 32>, grid, block, 0, b);
+        else if (minb == 12) launch_chained(ctx, envelope_kernel<false, 12, 32>, grid, block, 0, b);
+        else launch_chained(ctx, envelope_kernel<false, 16, 32>, grid, block, 0, b);
+    } else {
+        if (ticket) launch_chained(ctx, envelope_kernel<true, 16, 16>, grid, block, 0, b);
+        else if (minb == 8) launch_chained(ctx, envelope_kernel<false, 8, 16>, grid, block, 0, b);
+        else if (minb == 12) launch_chained(ctx, envelope_kernel<false, 12, 16>, grid, block, 0, b);
+        else launch_chained(ctx, envelope_kernel<false, 16, 16>, grid, block, 0, b);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) MXL_FAIL(MXL_ERR_CUDA, "envelope launch failed: %s", cudaGetErrorString(e));
     ctx->launches++;

@@ -182,8 +182,9 @@ constexpr int kFusedProfStamps = 8;
 
 // ---- Envelope (src/module/envelope.rs:91-120) ----
 struct EnvState { int32_t state; int32_t _pad; uint64_t seq; double off_amplitude; };
-// look-back descriptor of one tile: three words (epoch << 2 | status) << 32 | key -- last event, latest two transitions
-struct EnvTile { unsigned long long ev, tr_a, tr_b; };
+// look-back descriptor of one tile: four words (epoch << 2 | status) << 32 | key -- first event, last event, latest two
+// transitions after the first event (envelope.cu)
+struct alignas(16) EnvTile { unsigned long long w[4]; };
 struct EnvInst {
     const float* in; float* out;
     const EnvState* state;           // machine state before the call

@@ -190,12 +190,28 @@ __device__ __forceinline__ void cp_async_16s(uint32_t smem_dst, const void* gmem
 // Four taps in two instructions: weights as two s16 pairs, the four u8 samples in one word (dp2a.lo takes the
 // two low bytes, dp2a.hi the two high ones); then the two-pass definition's rounding and clip.
 __device__ __forceinline__ int pack_s16x2(short lo, short hi) { return (int)(((uint32_t)(uint16_t)hi << 16) | (uint16_t)lo); }
-__device__ __forceinline__ uint32_t tap4(uint32_t px, int c01, int c23)
+__device__ __forceinline__ int dp2a_lo(int c, uint32_t px, int acc)
 {
-    int acc;
-    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(acc) : "r"(c01), "r"(px), "r"(8192));
-    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(acc) : "r"(c23), "r"(px), "r"(acc));
-    return (uint32_t)__vimin_s32_relu(acc >> 14, 255);
+    int r;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(c), "r"(px), "r"(acc));
+    return r;
+}
+__device__ __forceinline__ int dp2a_hi(int c, uint32_t px, int acc)
+{
+    int r;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(c), "r"(px), "r"(acc));
+    return r;
+}
+// the two-pass definition's rounding (+8192 before, >> 14 after) for the four taps of one pixel held in one word
+__device__ __forceinline__ int tap4(uint32_t px, int c01, int c23) { return dp2a_hi(c23, px, dp2a_lo(c01, px, 8192)) >> 14; }
+// four pixel sums -> four bytes, each clipped to [0, 255]: two saturating pack instructions (I2IP) instead of four min/max
+// and three byte permutes
+__device__ __forceinline__ uint32_t pack4_sat_u8(int v0, int v1, int v2, int v3)
+{
+    uint32_t hi, all;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(v3), "r"(v2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(all) : "r"(v1), "r"(v0), "r"(hi));
+    return all;                                            // bytes v0, v1, v2, v3
 }
 
 template <int kScaleTH>
@@ -297,43 +313,50 @@ __global__ void __launch_bounds__(kVidThreads) scale_tiled_kernel(const __grid_c
         const uint32_t step = (kVidThreads / (kScaleTW / 4)) * pitch;
         uint32_t out = mid_a + r_first * kScaleTW + 4 * q;
         for (int r = r_first; r < rows; r += kVidThreads / (kScaleTW / 4)) {
-            uint32_t v[4];
+            int v[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 v[j] = tap4(__byte_perm(lds32(a[j]), lds32(a[j] + 4), sel[j]), c01[j], c23[j]);
                 a[j] += step;
             }
-            sts32(out, __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410));
+            sts32(out, pack4_sat_u8(v[0], v[1], v[2], v[3]));
             out += (kVidThreads / (kScaleTW / 4)) * kScaleTW;
         }
     }
     __syncthreads();
-    // vertical pass: thread = 4 adjacent output columns of one output row at a time, one 32-bit load per tap row
+    // vertical pass: thread = 8 adjacent output columns of one output row at a time, one 64-bit load per tap row.  Two
+    // byte permutes per pair of tap rows interleave them so that dp2a.lo / dp2a.hi see (row r, row r+1) of pixel 0 / 1:
+    // the 4 x 4 transposition costs four permutes per four pixels, the row table and the weights are read once per eight.
     {
-        const int q = threadIdx.x % (kScaleTW / 4);
-        const uint32_t gx = x0 + 4 * q;
-        const bool word_ok = ((P.dst_off | P.dst_stride) & 3u) == 0 && gx + 3 <= x1;
-        const uint32_t ly0 = threadIdx.x / (kScaleTW / 4);
+        constexpr int kOct = kScaleTW / 8;                        // column octets per row: 16 threads per output row
+        constexpr int kRowsPerPass = kVidThreads / kOct;
+        const int q = threadIdx.x % kOct;
+        const uint32_t gx = x0 + 8 * q;
+        const bool wide_ok = ((P.dst_off | P.dst_stride) & 7u) == 0 && gx + 7 <= x1;
+        const uint32_t ly0 = threadIdx.x / kOct;
         uint8_t* o = job.dst + P.dst_off + (size_t)(y0 + ly0) * P.dst_stride + gx;
-        const size_t ostep = (size_t)(kVidThreads / (kScaleTW / 4)) * P.dst_stride;
-        const uint32_t mq = mid_a + 4 * q;
+        const size_t ostep = (size_t)kRowsPerPass * P.dst_stride;
+        const uint32_t mq = mid_a + 8 * q;
         uint32_t yr_a = smem_addr(s_yr) + ly0 * 16, yc_a = smem_addr(s_yc) + ly0 * 8;
-        for (uint32_t ly = ly0; y0 + ly <= y1; ly += kVidThreads / (kScaleTW / 4), o += ostep,
-                      yr_a += (kVidThreads / (kScaleTW / 4)) * 16, yc_a += (kVidThreads / (kScaleTW / 4)) * 8) {
+        for (uint32_t ly = ly0; y0 + ly <= y1; ly += kRowsPerPass, o += ostep, yr_a += kRowsPerPass * 16, yc_a += kRowsPerPass * 8) {
             const uint4 rr = lds128(yr_a);
             const uint2 cc = lds64(yc_a);
-            const uint32_t a0 = lds32(mq + rr.x), a1 = lds32(mq + rr.y), a2 = lds32(mq + rr.z), a3 = lds32(mq + rr.w);
-            // transpose 4 rows x 4 pixels into 4 pixels x 4 taps with byte permutes, then two dp2a per pixel
-            const uint32_t lo01 = __byte_perm(a0, a1, 0x5140), hi01 = __byte_perm(a0, a1, 0x7362);   // (a0.b0,a1.b0,a0.b1,a1.b1), (.b2,.b3)
-            const uint32_t lo23 = __byte_perm(a2, a3, 0x5140), hi23 = __byte_perm(a2, a3, 0x7362);
+            const uint2 a0 = lds64(mq + rr.x), a1 = lds64(mq + rr.y), a2 = lds64(mq + rr.z), a3 = lds64(mq + rr.w);
             const int c01 = (int)cc.x, c23 = (int)cc.y;
-            const uint32_t v0 = tap4(__byte_perm(lo01, lo23, 0x5410), c01, c23), v1 = tap4(__byte_perm(lo01, lo23, 0x7632), c01, c23);
-            const uint32_t v2 = tap4(__byte_perm(hi01, hi23, 0x5410), c01, c23), v3 = tap4(__byte_perm(hi01, hi23, 0x7632), c01, c23);
-            const uint32_t packed = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
-            if (word_ok) {
-                *reinterpret_cast<uint32_t*>(o) = packed;
+            uint32_t out[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t r0 = h ? a0.y : a0.x, r1 = h ? a1.y : a1.x, r2 = h ? a2.y : a2.x, r3 = h ? a3.y : a3.x;
+                const uint32_t lo01 = __byte_perm(r0, r1, 0x5140), hi01 = __byte_perm(r0, r1, 0x7362);   // (r0.b0,r1.b0,r0.b1,r1.b1), (.b2,.b3)
+                const uint32_t lo23 = __byte_perm(r2, r3, 0x5140), hi23 = __byte_perm(r2, r3, 0x7362);
+                const int v0 = dp2a_lo(c23, lo23, dp2a_lo(c01, lo01, 8192)) >> 14, v1 = dp2a_hi(c23, lo23, dp2a_hi(c01, lo01, 8192)) >> 14;
+                const int v2 = dp2a_lo(c23, hi23, dp2a_lo(c01, hi01, 8192)) >> 14, v3 = dp2a_hi(c23, hi23, dp2a_hi(c01, hi01, 8192)) >> 14;
+                out[h] = pack4_sat_u8(v0, v1, v2, v3);
+            }
+            if (wide_ok) {
+                *reinterpret_cast<uint2*>(o) = make_uint2(out[0], out[1]);
             } else {
-                for (uint32_t j = 0; j < 4 && gx + j <= x1; j++) o[j] = (uint8_t)(packed >> (8 * j));
+                for (uint32_t j = 0; j < 8 && gx + j <= x1; j++) o[j] = (uint8_t)(out[j >> 2] >> (8 * (j & 3)));
             }
         }
     }

@@ -350,6 +350,32 @@ def test_rgba_to_yuv_self_specified(mxl, oracle, ctx48, size):
     pics.free()
 
 
+@pytest.mark.parametrize("size", [(1920, 1080), (70, 50)])
+def test_rgb_yuv_rgb_round_trip(mxl, oracle, ctx48, size):
+    """The two self-specified conversions are inverse to each other up to quantisation: a picture whose 2x2 blocks are
+    flat (so the chroma mean loses nothing) goes RGBA8 -> yuv420p -> RGBA8 through both kernels and comes back within
+    3 levels per channel (0.5 of rounding in each of Y, U, V times the BT.601 gains 1.164 / 2.018, plus the final rounding),
+    alpha 255.  Colours are kept inside the limited-range gamut so that no clip is involved."""
+    w, h = size
+    rng = np.random.default_rng(w * 7 + h)
+    blocks = rng.integers(40, 216, size=(h // 2, w // 2, 3), dtype=np.uint8)
+    rgb = np.repeat(np.repeat(blocks, 2, axis=0), 2, axis=1)
+    rgba = np.concatenate([rgb, np.full((h, w, 1), 255, np.uint8)], axis=2).reshape(-1)
+    pics = ctx48.rgba(w, h, 1)
+    pics.upload(rgba)
+    fr = ctx48.frame(w, h, blank=True)
+    pics.to_frames([fr])
+    back = fr.to_rgba().reshape(h, w, 4)
+    assert np.all(back[:, :, 3] == 255)
+    err = np.abs(back[:, :, :3].astype(np.int32) - rgb.astype(np.int32))
+    assert err.max() <= 3, err.max()
+    # the device round trip is the oracle's round trip, byte for byte
+    lay = oracle.frame_layout(w, h)
+    want = oracle.yuv420p_to_rgba(lay, oracle.rgba_to_yuv420p(lay, rgba))
+    assert np.array_equal(back.reshape(-1), want)
+    pics.free()
+
+
 def test_yuv_to_rgba_self_specified(mxl, oracle, ctx48):
     # UNPINNED: the reference never converts colour (video_mixer.rs:282-283); spec = oracle header
     for (w, h) in [(1920, 1080), (70, 50), (34, 18)]:

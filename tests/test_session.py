@@ -203,6 +203,33 @@ def test_steady_state_holds_device_memory_constant(mxl, oracle):
         sess.close()
 
 
+@pytest.mark.gpu
+def test_frame_pool_cap_and_trim(mxl):
+    """Released frames park in a per-size pool for reuse; the pool is capped and can be trimmed (a session whose sources
+    changed resolution must not keep the old size class until the context dies)."""
+    with mxl.Context(0, 48000, 800) as ctx:
+        ctx.synchronize()
+        frames = [ctx.frame(1920, 1080, blank=True) for _ in range(8)]
+        ctx.synchronize()
+        free_held, _ = ctx.device_memory()
+        for f in frames:
+            f.release()
+        free_parked, _ = ctx.device_memory()
+        assert free_parked <= free_held + (1 << 20)            # parked, not freed
+        again = ctx.frame(1920, 1080, blank=True)              # comes out of the pool: no new allocation
+        assert ctx.device_memory()[0] <= free_parked + (1 << 20)
+        again.release()
+        freed = ctx.trim_frame_pool(0)
+        assert freed == 8 * 3110400
+        assert ctx.device_memory()[0] >= free_parked + 6 * 3110400
+        # with a small cap a released frame goes straight back to the driver
+        ctx.trim_frame_pool(0, new_cap_bytes=2 * 3110400)
+        frames = [ctx.frame(1920, 1080, blank=True) for _ in range(6)]
+        for f in frames:
+            f.release()
+        assert ctx.trim_frame_pool(0) == 2 * 3110400
+
+
 class VideoMixerModel:
     """VideoMixer::run_tick (video_mixer.rs:70-250) for two channels of one picture size (no scaler involved): stored
     frames kept until `active_until`, one composite per tick from whatever is stored."""
