@@ -82,7 +82,7 @@ struct mxl_ctx {
     // eq_stream_kernel plans by chunk length (eq_plan.h); ok == false = unusable at this sample rate
     std::map<uint32_t, mxl::EqStreamPlan> eq_stream_plans;
     uint32_t eq_stream_smem_set = 0;  // bit LC/16: opt-in shared memory size configured
-    uint32_t scale_smem[4] = {0, 0, 0, 0};   // dynamic shared memory the scale_tiled_kernel variants have been configured for
+    uint32_t scale_smem[5] = {0, 0, 0, 0, 0};   // dynamic shared memory the scale_tiled_kernel variants have been configured for
     // scaler tap tables by (source length, destination length): device [pos int32 x n][coef int16 x 4n]
     std::map<uint64_t, void*> scale_tables;
     std::map<uint64_t, std::vector<int32_t>> scale_positions;   // host copies of the first-tap columns (tile bounds)
@@ -97,6 +97,7 @@ struct mxl_ctx {
     struct KernelEvents { const char* name; cudaEvent_t a, b; };
     std::vector<KernelEvents> kernel_events;      // pairs recorded since the last read
     std::vector<cudaEvent_t> kernel_event_pool;
+    bool env_carveout_set = false;    // envelope_kernel's shared-memory carve-out preference has been set
     uint32_t env_epoch = 0;           // Envelope launches so far (tags the look-back flags of a launch)
     std::map<uint32_t, void*> eq_stream_tables;   // device copies of EqStreamPlan::lane_pow by chunk length
     unsigned long long* fused_prof = nullptr;     // diagnostics: per-CTA phase clocks of the last fused voice launch (mxl_ctx_fused_profile)

@@ -20,7 +20,12 @@
 // The first `halo` chunks of a CTA belong to the previous CTA's range and only feed the scan: after
 // `halo` chunks the cascades have forgotten their start state to below 2^-75, so CTAs never
 // communicate and the whole module is a single launch.  The chunk that starts the call runs from the
-// module's stored state, exactly, so successive calls continue bit-exactly.
+// module's stored state, exactly.  Every other chunk starts from a CARRIED state (FMA dot products and a scan),
+// equal to the reference's serially rounded poles to ~1e-16 relative, not bit for bit: the f32 output differs
+// from the reference's only where a sum lies within that noise of an f32 rounding boundary, ~1e-8 per sample
+// (0 of the golden vector's 355 285 samples; tests/test_parity_audio.py::test_eq_three_long_differential_run
+// counts them on 2^23-sample calls).  "Bit-exact" for this module means that, not a theorem; the two-launch
+// kernel with a large MXL_EQ_CHUNK (few carried starts) is the strict mode.
 //
 // Non-finite samples: in the reference a NaN or an infinity entering the poles stays there for ever (every
 // later output is NaN, in this call and the next).  The carry above forgets by construction, so it would let
@@ -245,6 +250,8 @@ __device__ __forceinline__ void eq_stream_body(const EqStreamBatch& b, const VP&
     }
 }
 
+// (128-thread CTAs for the long-call variant -- more, smaller CTAs per SM passing through their phases at different
+// times -- measured slower: 0.143 against 0.126 ms per 2^25 samples at LC = 64, twice the halo share.)
 // short calls (a CTA or two per SM, code run once): rolled loops, every table in shared memory
 template <int LC>
 __global__ void __launch_bounds__(kT) eq_stream_kernel(const __grid_constant__ EqStreamBatch b)

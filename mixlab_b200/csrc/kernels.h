@@ -190,8 +190,6 @@ struct EnvInst {
     const EnvState* state;           // machine state before the call
     EnvState* state_out;             // after the call (other half of a double buffer)
     EnvTile* tiles;                  // device, one per tile of the call; flags carry the launch epoch
-    unsigned long long* ticket;      // device: tiles handed out so far (never reset)
-    unsigned long long ticket_base;  // value of *ticket when this launch starts
     double attack_ms, inv_attack, inv_decay, sustain, inv_release;
 };
 struct EnvBatch {

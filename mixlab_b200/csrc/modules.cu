@@ -54,8 +54,7 @@ struct Envelope : mxl_module {                        // src/module/envelope.rs
     DevBuf state, scratch;
     bool state_init = false;
     int cur = 0;                                      // which half of the state double buffer is current
-    size_t tiles_cap = 0;                             // look-back descriptors allocated (scratch: [ticket][tiles])
-    unsigned long long tickets = 0;                   // tiles launched so far (mirrors the device ticket counter)
+    size_t tiles_cap = 0;                             // look-back descriptors allocated (scratch)
     Envelope(const mxl_envelope_params* in)
     {
         kind = MXL_MOD_ENVELOPE;
@@ -1000,21 +999,18 @@ static int run_envelopes(mxl_ctx* ctx, mxl_module* const* mods, int n, uint64_t 
         for (int j = 0; j < cnt; j++) {
             Envelope* m = (Envelope*)mods[first + j];
             MXL_TRY(m->ensure_state());
-            if (m->tiles_cap < nt) {                       // [ticket counter (16 B)][tiles]; zeroed once: epoch 0 is never used
+            if (m->tiles_cap < nt) {                       // look-back descriptors; zeroed once: epoch 0 is never used
                 const size_t cap = (size_t)nt + nt / 2 + 16;
-                MXL_TRY(m->scratch.ensure(ctx, 16 + cap * sizeof(k::EnvTile)));
-                MXL_CUDA(cudaMemsetAsync(m->scratch.p, 0, 16 + cap * sizeof(k::EnvTile), ctx->stream));
+                MXL_TRY(m->scratch.ensure(ctx, cap * sizeof(k::EnvTile)));
+                MXL_CUDA(cudaMemsetAsync(m->scratch.p, 0, cap * sizeof(k::EnvTile), ctx->stream));
                 m->tiles_cap = cap;
-                m->tickets = 0;
             }
             k::EnvInst& e = b.inst[j];
             e.in = io[first + j].in[0] ? io[first + j].in[0]->dev : nullptr;
             e.out = io[first + j].out[0]->dev;
             e.state = (const k::EnvState*)m->state.p + m->cur;
             e.state_out = (k::EnvState*)m->state.p + (m->cur ^ 1);
-            e.ticket = (unsigned long long*)m->scratch.p;
-            e.tiles = (k::EnvTile*)((char*)m->scratch.p + 16);
-            e.ticket_base = m->tickets;
+            e.tiles = (k::EnvTile*)m->scratch.p;
             e.attack_ms = m->p.attack_ms;
             e.inv_attack = 1.0 / m->p.attack_ms;           // envelope.rs:43,48,55: `1.0 / x_ms * ms`, left to right
             e.inv_decay = 1.0 / m->p.decay_ms;
@@ -1028,11 +1024,7 @@ static int run_envelopes(mxl_ctx* ctx, mxl_module* const* mods, int n, uint64_t 
         b.epoch = ++ctx->env_epoch;
         if ((b.epoch << 2) == 0) b.epoch = ctx->env_epoch = 1;   // 30-bit epoch wrapped: flags of 2^30 launches ago are long gone
         MXL_TRY(k::launch_envelope(ctx, b));
-        for (int j = 0; j < cnt; j++) {
-            Envelope* m = (Envelope*)mods[first + j];
-            m->cur ^= 1;
-            m->tickets += nt;
-        }
+        for (int j = 0; j < cnt; j++) ((Envelope*)mods[first + j])->cur ^= 1;
     }
     return MXL_OK;
 }
@@ -1862,9 +1854,13 @@ int scale_run(mxl_ctx* ctx, const mxl_frame_layout& sl, uint32_t out_w, uint32_t
     k::ScaleLaunch L{};
     const uint32_t tw = k::scale_tile_width();
     auto clampi = [](int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); };
-    // tallest tile whose staged source rectangle fits comfortably (several CTAs per SM): 64 output rows, else
-    // 32, or 8 / 2 for strong down-scales
-    for (uint32_t th : {64u, 32u, 8u, 2u}) {
+    // tallest tile whose staged source rectangle fits comfortably (several CTAs per SM): 128 output rows when the batch
+    // still fills the machine four CTAs deep (a tile's prologue -- geometry, tap-table slices, staging set-up -- is a
+    // quarter of the kernel's instructions at 64 rows), else 64, 32, or 8 / 2 for strong down-scales
+    static const uint32_t th_max = getenv("MXL_SCALE_TH") ? (uint32_t)atoi(getenv("MXL_SCALE_TH")) : 128u;
+    const uint64_t sms = (uint64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148);
+    for (uint32_t th : {128u, 64u, 32u, 8u, 2u}) {
+        if (th > th_max && th > 2u) continue;
         uint32_t tile_base = 0, max_span = 16, max_rows = 1;
         for (int p = 0; p < 3; p++) {
             // subframe addressing (codec/src/ffmpeg/frame.rs:219-281): offsets are chroma-aligned already
@@ -1902,6 +1898,7 @@ int scale_run(mxl_ctx* ctx, const mxl_frame_layout& sl, uint32_t out_w, uint32_t
         L.region_pitch = max_span;
         L.region_rows = max_rows;
         L.tile_h = th;
+        if (th == 128 && ((uint64_t)tile_base * n < 20 * sms || k::scale_smem_bytes(max_rows, max_span) > 40u * 1024u)) continue;
         if (k::scale_smem_bytes(max_rows, max_span) <= (th == 64 ? 72u * 1024u : k::kScaleMaxSmem)) break;
     }
     // job tables rotate through a ring: a table must stay intact until the launch that reads it has run,

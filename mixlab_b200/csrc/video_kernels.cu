@@ -167,7 +167,7 @@ __device__ __forceinline__ uint32_t yuv_px_terms(uint32_t y, const ChromaTerms& 
 // Every source byte is read from HBM once per tile that needs it (neighbouring tiles share a 3-pixel
 // apron through L2); the intermediate never leaves the SM.
 // ------------------------------------------------------------------------------------------------
-constexpr int kScaleTW = 128;     // tile width; the tile height is a template parameter (64, 32, 8 or 2 output rows)
+constexpr int kScaleTW = 128;     // tile width; the tile height is a template parameter (128, 64, 32, 8 or 2 output rows)
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src)
 {
@@ -267,7 +267,8 @@ __global__ void __launch_bounds__(kVidThreads) scale_tiled_kernel(const __grid_c
         const uint32_t gx = min(x0 + threadIdx.x, x1);
         const int rel = __ldg(P.xpos + gx) - gx0;                 // >= 0
         const short4 cf = *reinterpret_cast<const short4*>(P.xcoef + (size_t)gx * 4);
-        s_x[threadIdx.x] = make_uint4((uint32_t)(rel & ~3), 0x3210u + 0x1111u * (uint32_t)(rel & 3),
+        // column x = 4 q + j is kept at [j][q]: the horizontal pass reads one j for 32 consecutive q (no bank conflicts)
+        s_x[(threadIdx.x & 3) * (kScaleTW / 4) + (threadIdx.x >> 2)] = make_uint4((uint32_t)(rel & ~3), 0x3210u + 0x1111u * (uint32_t)(rel & 3),
                                       (uint32_t)pack_s16x2(cf.x, cf.y), (uint32_t)pack_s16x2(cf.z, cf.w));
     } else if (threadIdx.x < kScaleTW + kScaleTH) {
         const uint32_t i = threadIdx.x - kScaleTW, gy = min(y0 + i, y1);
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(kVidThreads) scale_tiled_kernel(const __grid_c
         const uint32_t sx_a = smem_addr(s_x);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const uint4 e = lds128(sx_a + (4 * q + j) * 16);
+            const uint4 e = lds128(sx_a + (j * (kScaleTW / 4) + q) * 16);
             a[j] = region_a + r_first * pitch + e.x;
             sel[j] = e.y; c01[j] = (int)e.z; c23[j] = (int)e.w;
         }
@@ -609,7 +610,7 @@ int launch_blank(mxl_ctx* ctx, const mxl_frame_layout& lay, uint8_t* frame)
 template <int TH>
 static int launch_scale_th(mxl_ctx* ctx, const ScaleLaunch& L, uint32_t n_jobs, size_t smem)
 {
-    uint32_t& configured = ctx->scale_smem[TH == 64 ? 3 : (TH == 32 ? 0 : (TH == 8 ? 1 : 2))];
+    uint32_t& configured = ctx->scale_smem[TH == 128 ? 4 : (TH == 64 ? 3 : (TH == 32 ? 0 : (TH == 8 ? 1 : 2)))];
     if (smem > 48 * 1024 && smem > configured) {
         MXL_CUDA(cudaFuncSetAttribute(scale_tiled_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = (uint32_t)smem;
@@ -630,6 +631,7 @@ int launch_scale_tiled(mxl_ctx* ctx, const ScaleLaunch& L, uint32_t n_jobs)
     const size_t smem = scale_smem_bytes(L.region_rows, L.region_pitch);
     if (smem > kScaleMaxSmem) MXL_FAIL(MXL_ERR_INVALID, "scale_tiled_kernel: source rectangle of a tile needs %zu bytes of shared memory", smem);
     switch (L.tile_h) {
+    case 128: return launch_scale_th<128>(ctx, L, n_jobs, smem);
     case 64: return launch_scale_th<64>(ctx, L, n_jobs, smem);
     case 32: return launch_scale_th<32>(ctx, L, n_jobs, smem);
     case 8: return launch_scale_th<8>(ctx, L, n_jobs, smem);

@@ -140,6 +140,29 @@ def test_eq_three_random(mxl, oracle, ctx48, frames, gains):
     assert mismatch_count(out.download(), want) == 0
 
 
+@pytest.mark.parametrize("seed,scale", [(11, 1.0), (12, 0.02), (13, 30.0)])
+def test_eq_three_long_differential_run(mxl, oracle, ctx48, seed, scale):
+    """The time-parallel kernel starts every chunk but the call's first from a carried state that equals the reference's
+    serially rounded poles only to f64 rounding noise (~1e-16 relative); the final `as f32` absorbs that except where a sum
+    sits within that noise of a rounding boundary -- about 1e-8 per sample.  So "bit-exact" is a statement about
+    probability, not a theorem: this run counts.  2^23 samples (three minutes of audio) in ONE call, i.e. 130 000 carried
+    chunk starts: every differing sample must differ by exactly one f32 ulp, and there may be at most 4 of them."""
+    n = 1 << 23
+    x = (W.uniform_pm1(seed, n) * np.float32(scale)).astype(np.float32)
+    gains = (3.0, -2.0, 1.5)
+    want = oracle.EqThree(48000.0).run(gains, x)
+    mod = ctx48.module(mxl.MOD_EQ_THREE, gains)
+    out = ctx48.line(mxl.LINE_MONO, n)
+    mod.run_tick(0, [ctx48.mono(x)], [out])
+    got = out.download()
+    diff = np.flatnonzero(got.view(np.uint32) != want.view(np.uint32))
+    print("EqThree differential run: %d of %d samples differ (scale %g)" % (diff.size, n, scale))
+    assert diff.size <= 4
+    if diff.size:
+        ulps = np.abs(got.view(np.int32)[diff].astype(np.int64) - want.view(np.int32)[diff].astype(np.int64))
+        assert ulps.max() == 1
+
+
 @pytest.mark.parametrize("sr_spt", [(22050, 368), (96000, 1600), (192000, 3200)])
 def test_eq_three_other_sample_rates(mxl, oracle, sr_spt):
     """The chunk/halo plan follows the pole decay at the context's sample rate."""
