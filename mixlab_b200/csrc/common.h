@@ -65,6 +65,9 @@ struct mxl_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     uint64_t launches = 0;
+    uint64_t fused_mix_launch_no = 0; // value of `launches` right after the last fused_mix_kernel launch ...
+    const void* fused_mix_group = nullptr;   // ... and the group it belonged to (fused_voice_kernel's late dependency wait)
+    const void* fused_group_now = nullptr;   // group whose launches are being issued (set by run_fused_group)
     uint64_t change_epoch = 1;        // bumped by whatever may invalidate cached launch parameters: a module update, a line
                                       // (re)allocation, a new graph plan
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -168,10 +171,12 @@ struct KernelTimer {
 // 616 k ticks/s at 128 ticks per call with it on; audio alone 3.36 M -> 4.05 M, a live one-tick call 24.8 -> 17.2 us).
 #ifdef __CUDACC__
 namespace mxl {
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_prologue()
 {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    pdl_wait();
+    pdl_launch_dependents();
 }
 
 bool pdl_enabled(const mxl_ctx* ctx);

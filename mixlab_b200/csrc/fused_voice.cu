@@ -57,7 +57,14 @@ template <int LC>
 __global__ void __launch_bounds__(kT, 3) fused_voice_kernel(const __grid_constant__ FusedVoiceBatch b)
 {
     constexpr int VPR = LC / 4;
-    pdl_prologue();
+    // Steady state (b.late_wait): the kernel before this one is the group's mix kernel of the previous call, which still
+    // READS the product / EqThree lines this kernel will overwrite, and which itself only started after the previous voice
+    // kernel had completed (so the EqThree states this kernel reads are final).  Everything up to the first global store
+    // -- generating, the scan, the exact pass, all in shared memory and registers -- runs beside that mix kernel; the
+    // dependency wait sits in front of the stores.
+    const bool late_wait = b.late_wait != 0;
+    if (!late_wait) pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ __align__(16) unsigned char fv_smem[];
     float4* tile = reinterpret_cast<float4*>(fv_smem);                              // [256][VPR], swizzled
     EqShared<LC>* sh = reinterpret_cast<EqShared<LC>*>(fv_smem + tile_bytes<LC>());
@@ -166,6 +173,7 @@ __global__ void __launch_bounds__(kT, 3) fused_voice_kernel(const __grid_constan
     }
     // observed oscillator lines leave from the tile before the exact pass overwrites it
     if (vc.osc_mono || vc.osc_stereo) {
+        if (late_wait) pdl_wait();
         const int total = U * VPR;
         for (int idx = tid; idx < total; idx += kT) {
             const int r = halo + idx / VPR, vv = idx % VPR;
@@ -205,6 +213,7 @@ __global__ void __launch_bounds__(kT, 3) fused_voice_kernel(const __grid_constan
     MXL_STAMP(4);
 
     // ---- A4. coalesced store of the owned rows: the EqThree line and this voice's mixer products ----
+    if (late_wait) pdl_wait();                             // (a second wait returns at once)
     {
         float* dst = vc.eq_out;
         bool vec_ok = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
@@ -411,6 +420,9 @@ int launch_voice_lc(mxl_ctx* ctx, FusedVoiceBatch& b)
     }
     const uint32_t tiles = (b.n_chunks + b.owned - 1) / b.owned;
     b.prof = nullptr;
+    // late dependency wait: only behind this group's own mix kernel (the host's steady-state path sets group_tag)
+    b.late_wait = (b.late_wait && ctx->launches == ctx->fused_mix_launch_no && ctx->fused_group_now && ctx->fused_mix_group == ctx->fused_group_now &&
+                   !ctx->fused_prof_cap && pdl_enabled(ctx)) ? 1 : 0;
     if (ctx->fused_prof_cap) {                             // diagnostics on: phase clocks of this launch
         const uint32_t ctas = tiles * (uint32_t)b.n_voices;
         if (ctas <= ctx->fused_prof_cap) { b.prof = ctx->fused_prof; ctx->fused_prof_ctas = ctas; }
@@ -459,6 +471,8 @@ int launch_fused_mix(mxl_ctx* ctx, const FusedMixBatch& b)
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) MXL_FAIL(MXL_ERR_CUDA, "launch of fused_mix_kernel failed: %s", cudaGetErrorString(e));
     ctx->launches++;
+    ctx->fused_mix_launch_no = ctx->launches;
+    ctx->fused_mix_group = ctx->fused_group_now;
     return MXL_OK;
 }
 

@@ -154,7 +154,9 @@ struct FusedVoiceBatch {
     double sample_rate, inv_sample_rate;
     uint32_t n_chunks;
     uint32_t owned;                                // chunks a tile owns (256 - halo)
-    int32_t n_voices, _pad;
+    int32_t n_voices;
+    int32_t late_wait;                             // the kernel launched before this one is this group's mix kernel of the previous
+                                                   // call: generate / scan / filter before waiting for it (fused_voice.cu)
     unsigned long long* prof;                      // diagnostics: kFusedProfStamps clock64 stamps per CTA, or nullptr
     EqStreamConsts eq;
     FusedVoice voice[kFusedMaxVoices];

@@ -1131,6 +1131,8 @@ int run_fused_group(mxl_ctx* ctx, const FusedGroup& g, uint64_t t, uint64_t* byt
                 fc->vb.voice[i].state_out = e->state_ptr(e->cur ^ 1);
             }
             if (bytes) fused_bytes(g, fc->frames, bytes);
+            ctx->fused_group_now = (const void*)&g;
+            fc->vb.late_wait = 1;                          // (the launcher checks that this group's mix kernel is what runs before it)
             MXL_TRY(k::launch_fused_voice(ctx, fc->vb));
             for (int i = 0; i < fc->vb.n_voices; i++) ((EqThree*)g.voices[i].eq)->cur ^= 1;
             return k::launch_fused_mix(ctx, fc->mb);
@@ -1268,6 +1270,8 @@ int run_fused_group(mxl_ctx* ctx, const FusedGroup& g, uint64_t t, uint64_t* byt
     mx->fused_cache->group = (const void*)&g;
     mx->fused_cache->vb = vb;
     mx->fused_cache->mb = mb;
+    ctx->fused_group_now = (const void*)&g;
+    vb.late_wait = 0;                                      // parameters were just rebuilt (uploads, line growth): wait first
     MXL_TRY(k::launch_fused_voice(ctx, vb));
     for (int i = 0; i < nv; i++) ((EqThree*)g.voices[i].eq)->cur ^= 1;
     return k::launch_fused_mix(ctx, mb);
