@@ -22,6 +22,13 @@
 // waiting for the slowest voice (a sine costs 5x a saw), against 8 k for generating and 5 k for filtering; the product
 // tiles it needed in shared memory cost a resident CTA per SM.  As its own launch the mix is ~3 us of the whole machine.
 //
+// Also measured and dropped (r2): CHAINED tiles -- no halo chunks recomputed ahead of a tile's own (at 16-sample chunks the
+// halo is 73 of a tile's 256 chunks, 1.4 x the oscillator work); instead a tile hands the aggregates of its last three warps
+// to the next tile of its voice through global memory right after its first scan barrier.  Bit-identical results, but
+// slower: 7.0-7.3 M against 7.7 M ticks/s at 128 ticks per call, 12.8 M against 15.2 M at 1024 -- the extra block barrier
+// and the neighbour's hand-off sit on every CTA's critical path, and the kernel is bound by that path (FP64 pipe 25-40 %
+// busy), not by the amount of oscillator arithmetic.
+//
 // Lines nobody observes (Oscillator outputs, StereoPanner output) are not written.  State, numerics and results are those
 // of the staged kernels: same oscillator code, same EqThree scheme (chunk 0 from the stored state, state_out after the
 // last chunk), same channel order.  Roofline: FP64 pipe (~22 ops per sine sample + ~46 per EqThree sample + 1 per channel
