@@ -28,6 +28,7 @@ def main():
     sess = AVSession(ctx, W.config2_graph(), T, video=not args.no_video, unique_frames=2)
     sess.upload_inputs()
     kind_names = {v: k for k, v in W.KIND.items()}
+    kind_names[mxl.STAGE_FUSED_VOICE_MIX] = "FusedVoiceMix"
     tick = 0
     for _ in range(100):
         sess.run_step(tick)
@@ -42,7 +43,7 @@ def main():
         tick += T
         for s in sess.graph.stages():
             if s["n_launches"]:
-                per_stage.setdefault(kind_names[s["kind"]], []).append(s["host_us"])
+                per_stage.setdefault(kind_names.get(s["kind"], "kind%d" % s["kind"]), []).append(s["host_us"])
     ctx.synchronize()
     wall = (time.perf_counter() - t_all) / args.ticks * 1e6
     out = {"ticks_per_call": T, "calls": args.ticks, "wall_us_per_call_incl_stage_queries": wall,
