@@ -250,6 +250,8 @@ __device__ __forceinline__ void eq_stream_body(const EqStreamBatch& b, const VP&
     }
 }
 
+// (Starting the k-th resident CTA of an SM k * 1-6 us late, so that the CTAs sharing an SM do not pass through their phases
+// in step, changed nothing: 0.125-0.127 ms at every delay.)
 // (128-thread CTAs for the long-call variant -- more, smaller CTAs per SM passing through their phases at different
 // times -- measured slower: 0.143 against 0.126 ms per 2^25 samples at LC = 64, twice the halo share.)
 // short calls (a CTA or two per SM, code run once): rolled loops, every table in shared memory

@@ -66,9 +66,30 @@ __global__ void __launch_bounds__(kRsThreads) resample_kernel(const ResampleLaun
     extern __shared__ __align__(16) double rs_x[];         // [window][CH]
     const uint64_t m0 = p.block0 + (uint64_t)blockIdx.x * p.L * p.repeats;     // a multiple of L
     const int64_t n_first = (int64_t)(m0 / p.L) * p.M - kRsH + 1;              // first input frame this block touches
-    for (uint32_t i = threadIdx.x; i < p.window * CH; i += kRsThreads)
-        rs_x[i] = (double)fetch(p, n_first + i / CH, i % CH);
-    const uint32_t ph_idx = blockIdx.y * kRsThreads + threadIdx.x;             // output offset inside a run of L
+    // Staging, one FRAME per thread and trip.  The window [n_first, n_first + window) is, in order: frames before the stream
+    // (zeros), the kRsTaps frames of history, the new input, frames not pushed yet (zeros, never used by a determined output);
+    // the boundaries are block-uniform, the new input of an interior block is one straight vector copy.
+    {
+        const int64_t rel0 = n_first - (int64_t)p.in_base;                     // window frame i is new-input frame rel0 + i
+        const bool interior = rel0 >= 0 && (uint64_t)rel0 + p.window <= p.n_new;
+        if (interior && CH == 2 && p.in_f32) {
+            const float2* src = reinterpret_cast<const float2*>(p.in_f32) + rel0;
+            for (uint32_t i = threadIdx.x; i < p.window; i += blockDim.x) {
+                const float2 v = __ldg(src + i);
+                *reinterpret_cast<double2*>(rs_x + 2 * i) = make_double2((double)v.x, (double)v.y);
+            }
+        } else if (interior && CH == 2 && p.in_i16) {
+            const short2* src = reinterpret_cast<const short2*>(p.in_i16) + rel0;
+            for (uint32_t i = threadIdx.x; i < p.window; i += blockDim.x) {
+                const short2 v = __ldg(src + i);
+                *reinterpret_cast<double2*>(rs_x + 2 * i) = make_double2((double)((float)v.x / 32768.0f), (double)((float)v.y / 32768.0f));
+            }
+        } else {
+            for (uint32_t i = threadIdx.x; i < p.window * CH; i += blockDim.x)
+                rs_x[i] = (double)fetch(p, n_first + i / CH, i % CH);
+        }
+    }
+    const uint32_t ph_idx = blockIdx.y * blockDim.x + threadIdx.x;             // output offset inside a run of L
     double c[kRsTaps];
     uint32_t x_off = 0;
     if (ph_idx < p.L) {
@@ -229,14 +250,16 @@ static int64_t resampler_push(mxl_resampler* r, const float* in_f32, const short
     if (n_out) {
         const uint64_t per_block = (uint64_t)r->L * p.repeats;
         const unsigned blocks = (unsigned)((r->total_out + n_out - p.block0 + per_block - 1) / per_block);
-        dim3 grid(blocks, (r->L + k::kRsThreads - 1) / k::kRsThreads);
+        // a thread per phase: L rounded up to whole warps, at most 256 per block (44.1 k -> 48 k: 160 threads, no idle warps)
+        const unsigned threads = std::min<unsigned>(k::kRsThreads, (r->L + 31u) / 32u * 32u);
+        dim3 grid(blocks, (r->L + threads - 1) / threads);
         MXL_TIMED(ctx, "resample_kernel");
         if (r->channels == 2) {
             if (smem > 48 * 1024) MXL_CUDA(cudaFuncSetAttribute(k::resample_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k::resample_kernel<2><<<grid, k::kRsThreads, smem, ctx->stream>>>(p);
+            k::resample_kernel<2><<<grid, threads, smem, ctx->stream>>>(p);
         } else {
             if (smem > 48 * 1024) MXL_CUDA(cudaFuncSetAttribute(k::resample_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k::resample_kernel<1><<<grid, k::kRsThreads, smem, ctx->stream>>>(p);
+            k::resample_kernel<1><<<grid, threads, smem, ctx->stream>>>(p);
         }
         if (cudaGetLastError() != cudaSuccess) MXL_FAIL(MXL_ERR_CUDA, "launch of resample_kernel failed");
         ctx->launches++;

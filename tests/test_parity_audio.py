@@ -422,6 +422,42 @@ def test_envelope_long_call_many_tiles(mxl, oracle, ctx48, kind):
     assert bits_equal(out.download(), want2)
 
 
+@pytest.mark.parametrize("params", [
+    (0.0, 0.0, 0.3, 0.0),            # 1/0 = inf everywhere: inf * 0 = NaN at the sample a phase begins
+    (0.001, 5.0, 0.0, 1.0),          # sustain and "released" reached within a tile: the constant arms
+    (2.0, 30.0, 0.6, 10.0),
+    (50.0, -10.0, 1.2, -5.0),        # negative times: the clamp's lower bound, amplitudes above 1
+    (25.0, 500.0, -0.0, 200.0),      # sustain -0.0: the sign of the sustained zero
+    (float("inf"), 100.0, 0.5, 100.0),
+    (10.0, float("nan"), 0.5, float("nan")),
+])
+def test_envelope_parameter_corners(mxl, oracle, ctx48, params):
+    """The output arms are specialised per thread (attack only / decay without clamp / sustain / release without clamp /
+    released) on the strength of monotonicity arguments that need finite, non-negative slopes: corner parameters must fall
+    back to the general arm and still give the reference's bits.  Trigger-like gate: long runs of exact 1.0 / 0.0 with
+    inert stretches in between, so that every arm occurs, over 40 tiles."""
+    frames = 2048 * 40 + 77
+    g = np.full(frames, 0.5, np.float32)
+    rng = np.random.default_rng(99)
+    pos = 0
+    on = True
+    while pos < frames:
+        run = int(rng.integers(5, 9000))
+        kind = rng.integers(0, 3)
+        if kind < 2:
+            g[pos:pos + run] = 1.0 if on else 0.0
+            on = not on
+        pos += run
+    env = oracle.Envelope()
+    want = env.run(777, 48000.0, *params, g)
+    mod = ctx48.module(mxl.MOD_ENVELOPE, params)
+    out = ctx48.line(mxl.LINE_MONO, frames)
+    mod.run_tick(777, [ctx48.mono(g)], [out])
+    got = out.download()
+    same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+    assert same.all(), (int((~same).sum()), int(np.flatnonzero(~same)[0]))
+
+
 def test_pcm_async_ring_many_calls(mxl, oracle, ctx48):
     """N2/N3 hand-off without per-call allocation: 40 blocks of i16 PCM in, Amplifier, i16 PCM out, all queued
     before one synchronise; 5 MB pass through the 1 MB staging ring, which wraps several times
