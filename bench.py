@@ -493,6 +493,38 @@ def sub_benchmarks(mxl, ctx, args, peak):
     pics.free()
     for f in fa + fb:
         f.release()
+
+    # config 5: the mixer bus alone, C channels x 800-sample ticks, 128 ticks per launch (bandwidth regime) and one tick
+    # per launch (latency regime); algorithmic bytes 8*S*(C+2) per tick.  The full C x S sweep is tools/roofline_sweep.py.
+    points = []
+    for C in (2, 16, 64, 256):
+        rng = np.random.default_rng(C)
+        mod = ctx.module(mxl.MOD_MIXER, list(zip(rng.uniform(-24.0, 6.0, C), rng.uniform(0.1, 1.0, C), (np.arange(C) % 2 == 0))))
+        for T in (128, 1):
+            frames = SPT * T
+            nbytes = 8 * frames * (C + 2)
+            n_sets = int(max(1, min(16, np.ceil(300e6 / nbytes))))           # rotate over more than L2 holds
+            host = np.resize(W.uniform_pm1(C * 131 + T, 2 * min(frames, 1 << 16)), 2 * frames)
+            sets = [([ctx.stereo(host) for _ in range(C)], ctx.line(mxl.LINE_STEREO, frames), ctx.line(mxl.LINE_STEREO, frames))
+                    for _ in range(n_sets)]
+            it = [0]
+
+            def one():
+                ins, m, c = sets[it[0] % n_sets]
+                it[0] += 1
+                mod.run_tick(0, ins, [m, c])
+            for _ in range(3):
+                one()
+            ms, nb, _ = timed_blocks(ctx, nd, one, K, 0.1)
+            points.append({"channels": C, "ticks_per_launch": T, "ms_per_launch": ms / K, "gbs": nbytes / (ms / K * 1e-3) / 1e9,
+                           "frac_of_hbm_peak": nbytes / (ms / K * 1e-3) / 1e9 / peak})
+            for ins, m, c in sets:
+                for ln in ins:
+                    ln.free()
+                m.free(); c.free()
+        mod.destroy()
+    sub["config5_mixer_bus"] = {"samples_per_tick": SPT, "points": points,
+                                "note": "BASELINE config 5 at S = 800; the whole C x S sweep: tools/roofline_sweep.py -> profiles/r1_mixer_sweep.jsonl"}
     return sub
 
 
