@@ -250,6 +250,10 @@ __device__ __forceinline__ void eq_stream_body(const EqStreamBatch& b, const VP&
     }
 }
 
+// (A persistent form -- one resident CTA per SM walking the tiles with two tile buffers, the next tile's cp.async copies in
+// flight during the current tile's passes, tables loaded once -- gave the same bits and 0.180 ms instead of 0.127: with 8
+// warps per SM the FP64 pipe is 50 % busy, with 24 (three one-tile CTAs) 73 %; in the exact pass a warp's stalls are fixed-
+// latency dependency waits, so the pipe is fed by the NUMBER of warps, and the 64 KB tile caps that at 24.)
 // (Starting the k-th resident CTA of an SM k * 1-6 us late, so that the CTAs sharing an SM do not pass through their phases
 // in step, changed nothing: 0.125-0.127 ms at every delay.)
 // (128-thread CTAs for the long-call variant -- more, smaller CTAs per SM passing through their phases at different
