@@ -84,6 +84,10 @@ __global__ void __launch_bounds__(kRsThreads) resample_kernel(const ResampleLaun
                 const short2 v = __ldg(src + i);
                 *reinterpret_cast<double2*>(rs_x + 2 * i) = make_double2((double)((float)v.x / 32768.0f), (double)((float)v.y / 32768.0f));
             }
+        } else if (interior && CH == 1 && p.in_f32) {
+            for (uint32_t i = threadIdx.x; i < p.window; i += blockDim.x) rs_x[i] = (double)__ldg(p.in_f32 + rel0 + i);
+        } else if (interior && CH == 1 && p.in_i16) {
+            for (uint32_t i = threadIdx.x; i < p.window; i += blockDim.x) rs_x[i] = (double)((float)__ldg(p.in_i16 + rel0 + i) / 32768.0f);
         } else {
             for (uint32_t i = threadIdx.x; i < p.window * CH; i += blockDim.x)
                 rs_x[i] = (double)fetch(p, n_first + i / CH, i % CH);
