@@ -311,6 +311,47 @@ def test_cpu_arranged_scaler_equals_the_definition(oracle, src, dst):
     assert np.array_equal(oracle.letterbox_scale_fast(data, lay_in, dst[0], dst[1]), oracle.letterbox_scale(data, lay_in, dst[0], dst[1]))
 
 
+def _float_bicubic(src, dw, dh, a=-0.6):
+    """Independent statement of the scaler's definition in float: separable Keys cubic convolution (a = -0.6), four taps,
+    pixel centres aligned (u = (d + 0.5) * src / dst - 0.5), edge pixels repeated, no intermediate rounding."""
+    def weights(src_n, dst_n):
+        u = (np.arange(dst_n) + 0.5) * src_n / dst_n - 0.5
+        i0 = np.floor(u).astype(np.int64)
+        f = u - i0
+        taps = np.stack([i0 - 1, i0, i0 + 1, i0 + 2], axis=1)
+        x = np.abs(f[:, None] - np.array([-1.0, 0.0, 1.0, 2.0])[None, :])
+        w = np.where(x <= 1.0, ((a + 2.0) * x - (a + 3.0)) * x * x + 1.0, np.where(x < 2.0, ((a * x - 5.0 * a) * x + 8.0 * a) * x - 4.0 * a, 0.0))
+        w = w / w.sum(axis=1, keepdims=True)
+        return np.clip(taps, 0, src_n - 1), w
+    sh, sw = src.shape
+    tx, wx = weights(sw, dw)
+    ty, wy = weights(sh, dh)
+    s = src.astype(np.float64)
+    mid = (s[:, tx] * wx[None, :, :]).sum(axis=2)                  # [sh][dw]
+    out = (mid[ty, :] * wy[:, :, None]).sum(axis=1)                # [dh][dw]
+    return out
+
+
+@pytest.mark.parametrize("src,dst", [((640, 360), (960, 540)), ((960, 540), (560, 315)), ((320, 240), (321, 241)), ((64, 48), (640, 480))])
+def test_scaler_definition_against_an_independent_float_bicubic(oracle, src, dst):
+    """The scaler is self-specified (it stands in for un-vendored swscale: parity UNPINNED).  What can be checked without
+    swscale is that the integer two-pass definition is the filter it claims to be: against a float separable Keys bicubic
+    written independently here (same taps and alignment, no 14-bit weights, no intermediate u8 rounding) a smooth picture
+    must agree to rounding -- PSNR >= 50 dB, no pixel more than 2 levels off.  A half-pixel shift, a transposed weight or a
+    wrong clamp shows up as tens of levels."""
+    sw, sh = src
+    dw, dh = dst
+    yy, xx = np.mgrid[0:sh, 0:sw]
+    pic = 128 + 60 * np.sin(xx / 17.0) * np.cos(yy / 11.0) + 40 * np.sin((xx + 2 * yy) / 29.0) + 0.05 * xx
+    pic = np.clip(np.rint(pic), 0, 255).astype(np.uint8)
+    got = oracle.bicubic_plane(pic.reshape(-1), sw, sh, sw, dw, dh, dw).reshape(dh, dw).astype(np.float64)
+    want = np.clip(_float_bicubic(pic, dw, dh), 0, 255)
+    err = got - want
+    psnr = 10 * np.log10(255.0 ** 2 / np.mean(err ** 2))
+    assert psnr >= 50.0, psnr
+    assert np.abs(err).max() <= 2.0, np.abs(err).max()
+
+
 def test_session_driver_equals_its_parts(oracle):
     """orc_session_run (the timed CPU arm of the session variant) does per tick exactly what the restated functions
     do when called one by one: unpack, Engine::run_tick, blank + crossfade of the stored layers, monitor scaler, pack."""
