@@ -12,10 +12,12 @@ python tools/live_profile.py --no-video >> gpurun_out/r2f_live_profile.jsonl 2>>
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2f_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-sub > gpurun_out/r2f_ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:crossfade_flat -s 2 -c 1 -o gpurun_out/r2f_prof_crossfade python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-sub > gpurun_out/r2f_ncu_crossfade.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:fused -s 6 -c 2 -o gpurun_out/r2f_prof_fused python bench.py --workload audio --steps 3 --warmup 2 --no-cpu-baseline --no-e2e --no-sub > gpurun_out/r2f_ncu_fused.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"scale_tiled|rgba_to_yuv" -c 4 -o gpurun_out/r2f_prof_video python tools/kernel_roofline.py --only NOAUDIO --reps 1 > gpurun_out/r2f_ncu_video.log 2>&1
-for k in EqThree Envelope Resampler; do
-  ncu --set full --clock-control none --import-source on -k regex:"eq_stream|envelope|resample" -s 3 -c 1 -o gpurun_out/r2f_prof_big_$k python tools/kernel_roofline.py --only "$k" --reps 1 > gpurun_out/r2f_ncu_big_$k.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:rgba_to_yuv -c 1 -o gpurun_out/r2f_prof_video python tools/kernel_roofline.py --only NOAUDIO --reps 1 > gpurun_out/r2f_ncu_video.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:scale_tiled -c 8 -o gpurun_out/r2f_prof_scale python tools/kernel_roofline.py --only NOAUDIO --reps 1 > gpurun_out/r2f_ncu_scale.log 2>&1
+for k in EqThree Envelope; do
+  ncu --set full --clock-control none --import-source on -k regex:"eq_stream|envelope" -s 3 -c 1 -o gpurun_out/r2f_prof_big_$k python tools/kernel_roofline.py --only "$k" --reps 1 > gpurun_out/r2f_ncu_big_$k.log 2>&1
 done
+ncu --set full --clock-control none --import-source on -k regex:resample_kernel -s 2 -c 1 -o gpurun_out/r2f_prof_resample python tools/kernel_roofline.py --only Resampler --reps 1 > gpurun_out/r2f_ncu_resample.log 2>&1
 ( echo "compute-sanitizer (memcheck, racecheck, synccheck) over the tests of the kernels written or rewritten in round 2";
   compute-sanitizer --tool memcheck python -m pytest tests/test_fused_voice.py tests/test_resampler.py -m gpu -x -q 2>&1 | grep -E "passed|failed|ERROR SUMMARY";
   compute-sanitizer --tool memcheck python -m pytest tests/test_parity_audio.py tests/test_parity_video.py -m gpu -x -q -k "nvelope or eq_three_random or eq_three_golden or rgba or tiled_scaler or scal" 2>&1 | grep -E "passed|failed|ERROR SUMMARY";
